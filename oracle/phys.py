@@ -1,0 +1,150 @@
+"""TEST INFRASTRUCTURE — ctypes front end of the C physics oracle (oracle/phys_impl.h).
+
+PARITY UNPINNED for physics (closed-source PhysX in the reference; see phys_impl.h).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference arm import this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libgrx_oracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("phys_oracle.c", "phys_impl.h")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+    return _LIB
+
+
+def _mk_structs(real):
+    P = C.POINTER(real)
+    PI = C.POINTER(C.c_int)
+
+    class Model(C.Structure):
+        _fields_ = [("nb", C.c_int), ("nd", C.c_int), ("nl", C.c_int), ("ns", C.c_int), ("nf", C.c_int),
+                    ("parent", PI), ("jpos", P), ("jrot", P), ("axis", P), ("mass", P), ("com", P), ("inertia", P),
+                    ("dof_lower", P), ("dof_upper", P), ("dof_vel_limit", P), ("dof_effort", P),
+                    ("link_body", PI), ("link_pos", P), ("link_rot", P),
+                    ("sph_body", PI), ("sph_link", PI), ("sph_pos", P), ("sph_rad", P),
+                    ("foot_links", PI), ("kp", P), ("kd", P), ("default_pos", P)]
+
+    class Terrain(C.Structure):
+        _fields_ = [("type", C.c_int), ("rows", C.c_int), ("cols", C.c_int), ("heights", C.POINTER(C.c_short)),
+                    ("hscale", real), ("vscale", real), ("border", real), ("friction", real), ("restitution", real)]
+
+    class SimCfg(C.Structure):
+        _fields_ = [("dt", real), ("gravity", real), ("contact_offset", real), ("bounce_threshold", real),
+                    ("max_depen_vel", real), ("erp", real), ("solver_iters", C.c_int), ("decimation", C.c_int),
+                    ("action_scale", real), ("max_contacts", C.c_int)]
+    return Model, Terrain, SimCfg
+
+
+class PhysOracle:
+    """Physics oracle for one robot model / terrain / sim config, f32 or f64."""
+
+    def __init__(self, model, ctl, terrain=None, sim=None, dtype=np.float64):
+        """model: dict from grx_b200.urdf; ctl: dict(kp, kd, default_pos, foot_links);
+        terrain: None (plane) or dict(heights int16 [rows, cols], hscale, vscale, border, friction, restitution);
+        sim: dict overriding dt / decimation / solver_iters / erp / ..."""
+        self.np_real = np.dtype(dtype)
+        self.real = C.c_double if self.np_real == np.float64 else C.c_float
+        self.sfx = "_f64" if self.np_real == np.float64 else "_f32"
+        Model, Terrain, SimCfg = _mk_structs(self.real)
+        self._keep = []
+        m = Model()
+        m.nb, m.nd, m.nl, m.ns = model["nb"], model["nd"], len(model["link_names"]), len(model["sph_rad"])
+        fl = np.asarray(ctl["foot_links"], dtype=np.int32)
+        m.nf = len(fl)
+        for k in ("parent", "link_body", "sph_body", "sph_link"):
+            setattr(m, k, self._iptr(model[k]))
+        m.foot_links = self._iptr(fl)
+        for k in ("jpos", "jrot", "axis", "mass", "com", "inertia", "dof_lower", "dof_upper", "dof_effort",
+                  "link_pos", "link_rot", "sph_pos", "sph_rad"):
+            setattr(m, k, self._rptr(model[k]))
+        m.dof_vel_limit = self._rptr(model["dof_velocity"])
+        m.kp, m.kd, m.default_pos = self._rptr(ctl["kp"]), self._rptr(ctl["kd"]), self._rptr(ctl["default_pos"])
+        self.model, self.m = model, m
+        self.nd, self.nl, self.nf = m.nd, m.nl, m.nf
+        t = Terrain()
+        if terrain is None:
+            t.type, t.friction, t.restitution = 0, 1.0, 0.0
+            t.hscale, t.vscale, t.border = 1.0, 1.0, 0.0
+        elif terrain.get("heights") is None:
+            t.type, t.friction, t.restitution = 0, terrain.get("friction", 1.0), terrain.get("restitution", 0.0)
+            t.hscale, t.vscale, t.border = 1.0, 1.0, 0.0
+        else:
+            hs = np.ascontiguousarray(terrain["heights"], dtype=np.int16)
+            self._keep.append(hs)
+            t.type, t.rows, t.cols = 1, hs.shape[0], hs.shape[1]
+            t.heights = hs.ctypes.data_as(C.POINTER(C.c_short))
+            t.hscale, t.vscale, t.border = terrain["hscale"], terrain["vscale"], terrain["border"]
+            t.friction, t.restitution = terrain.get("friction", 1.0), terrain.get("restitution", 0.0)
+        self.t = t
+        s = SimCfg()
+        d = dict(dt=0.002, gravity=-9.81, contact_offset=0.01, bounce_threshold=0.5, max_depen_vel=1.0, erp=0.2,
+                 solver_iters=4, decimation=10, action_scale=1.0, max_contacts=16)
+        d.update(sim or {})
+        for k, v in d.items():
+            setattr(s, k, v)
+        self.s = s
+        self.sim = d
+
+    def _rptr(self, a):
+        a = np.ascontiguousarray(a, dtype=self.np_real)
+        self._keep.append(a)
+        return a.ctypes.data_as(C.POINTER(self.real))
+
+    def _iptr(self, a):
+        a = np.ascontiguousarray(a, dtype=np.int32)
+        self._keep.append(a)
+        return a.ctypes.data_as(C.POINTER(C.c_int))
+
+    def _p(self, a):
+        assert a.dtype == self.np_real and a.flags.c_contiguous, (a.dtype, a.flags)
+        return a.ctypes.data_as(C.POINTER(self.real))
+
+    def step(self, root, dof_pos, dof_vel, actions, last_actions, delay, motor_strength, base_inertial, friction,
+             restitution):
+        """In place on root [N,13], dof_pos/dof_vel [N,nd].  Returns dict of outputs."""
+        N = root.shape[0]
+        r = self.np_real
+        c = lambda a: np.ascontiguousarray(a, dtype=r)
+        actions, last_actions, motor_strength = c(actions), c(last_actions), c(motor_strength)
+        base_inertial, friction, restitution = c(base_inertial), c(friction), c(restitution)
+        out = dict(torques=np.zeros((N, self.nd), r), link_state=np.zeros((N, self.nl, 13), r),
+                   contact_force=np.zeros((N, self.nl, 3), r), avg_foot_force=np.zeros((N, self.nf), r),
+                   avg_foot_linvel=np.zeros((N, self.nf, 3), r), avg_foot_angvel=np.zeros((N, self.nf, 3), r))
+        fn = getattr(lib(), "grx_oracle_physics_step" + self.sfx)
+        fn.restype = C.c_int
+        err = fn(C.byref(self.m), C.byref(self.t), C.byref(self.s), C.c_int(N), self._p(root), self._p(dof_pos),
+                 self._p(dof_vel), self._p(actions), self._p(last_actions), self.real(delay), self._p(motor_strength),
+                 self._p(base_inertial), self._p(friction), self._p(restitution), self._p(out["torques"]),
+                 self._p(out["link_state"]), self._p(out["contact_force"]), self._p(out["avg_foot_force"]),
+                 self._p(out["avg_foot_linvel"]), self._p(out["avg_foot_angvel"]))
+        if err:
+            raise RuntimeError(f"physics oracle failed (code {err})")
+        return out
+
+    def dynamics_terms(self, base_inertial, root, q, qd):
+        r = self.np_real
+        nv = self.nd + 6
+        Mq, h, en = np.zeros((nv, nv), r), np.zeros(nv, r), np.zeros(2, r)
+        c = lambda a: np.ascontiguousarray(a, dtype=r)
+        fn = getattr(lib(), "grx_oracle_dynamics_terms" + self.sfx)
+        fn(C.byref(self.m), C.byref(self.s), self._p(c(base_inertial)), self._p(c(root)), self._p(c(q)), self._p(c(qd)),
+           self._p(Mq), self._p(h), self._p(en))
+        return Mq, h, en
