@@ -139,6 +139,31 @@ class PhysOracle:
             raise RuntimeError(f"physics oracle failed (code {err})")
         return out
 
+    def substep(self, root, dof_pos, dof_vel, tau, base_inertial, friction, restitution):
+        """One dt with given torques, in place.  Returns (link_state [N,nl,13], contact_force [N,nl,3])."""
+        N = root.shape[0]
+        r = self.np_real
+        c = lambda a: np.ascontiguousarray(a, dtype=r)
+        ls, cf = np.zeros((N, self.nl, 13), r), np.zeros((N, self.nl, 3), r)
+        fn = getattr(lib(), "grx_oracle_substep" + self.sfx)
+        fn.restype = C.c_int
+        err = fn(C.byref(self.m), C.byref(self.t), C.byref(self.s), C.c_int(N), self._p(root), self._p(dof_pos),
+                 self._p(dof_vel), self._p(c(tau)), self._p(c(base_inertial)), self._p(c(friction)),
+                 self._p(c(restitution)), self._p(ls), self._p(cf))
+        if err:
+            raise RuntimeError(f"physics oracle failed (code {err})")
+        return ls, cf
+
+    def link_states(self, root, dof_pos, dof_vel, base_inertial):
+        N = root.shape[0]
+        r = self.np_real
+        c = lambda a: np.ascontiguousarray(a, dtype=r)
+        ls = np.zeros((N, self.nl, 13), r)
+        fn = getattr(lib(), "grx_oracle_link_states" + self.sfx)
+        fn(C.byref(self.m), C.c_int(N), self._p(c(root)), self._p(c(dof_pos)), self._p(c(dof_vel)),
+           self._p(c(base_inertial)), self._p(ls))
+        return ls
+
     def dynamics_terms(self, base_inertial, root, q, qd):
         r = self.np_real
         nv = self.nd + 6

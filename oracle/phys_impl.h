@@ -486,6 +486,43 @@ int FN(grx_oracle_physics_step)(const FN(Model) *M, const FN(Terrain) *T, const 
     return err;
 }
 
+/* One simulate() call (dt) with given joint torques for N envs: what FakeGym.simulate() of the reference
+ * harness calls (oracle/ref_harness), i.e. the stand-in for gym.simulate + refresh_* (legged_robot_fftai.py:67-76). */
+int FN(grx_oracle_substep)(const FN(Model) *M, const FN(Terrain) *T, const FN(SimCfg) *cfg, int N,
+                           REAL *root, REAL *dof_pos, REAL *dof_vel, const REAL *tau,
+                           const REAL *base_inertial, const REAL *friction, const REAL *restitution,
+                           REAL *link_state, REAL *contact_force) {
+    const int nd = M->nd, nl = M->nl;
+    int err = 0;
+    if (M->nb > MAXB || nd + 6 > MAXV || cfg->max_contacts > MAXC) return 2;
+#pragma omp parallel for schedule(static) reduction(| : err)
+    for (int e = 0; e < N; e++) {
+        REAL *rt = root + 13 * e, *q = dof_pos + nd * e, *qd = dof_vel + nd * e;
+        const REAL *bin = base_inertial + 10 * e;
+        REAL cf[MAXB * 4 * 3];
+        FN(Kin) K;
+        FN(kinematics)(M, bin, rt, q, qd, &K);
+        err |= FN(substep)(M, T, cfg, bin, friction[e], restitution[e], rt, q, qd, tau + nd * e, &K, cf);
+        FN(kinematics)(M, bin, rt, q, qd, &K);
+        for (int l = 0; l < nl; l++) {
+            FN(link_state)(M, &K, l, link_state + (size_t)(e * nl + l) * 13);
+            for (int k = 0; k < 3; k++) contact_force[(size_t)(e * nl + l) * 3 + k] = cf[3 * l + k];
+        }
+    }
+    return err;
+}
+
+/* link states only (FK of the current state), for initialisation of rigid_body_states */
+int FN(grx_oracle_link_states)(const FN(Model) *M, int N, const REAL *root, const REAL *dof_pos, const REAL *dof_vel,
+                               const REAL *base_inertial, REAL *link_state) {
+    for (int e = 0; e < N; e++) {
+        FN(Kin) K;
+        FN(kinematics)(M, base_inertial + 10 * e, root + 13 * e, dof_pos + M->nd * e, dof_vel + M->nd * e, &K);
+        for (int l = 0; l < M->nl; l++) FN(link_state)(M, &K, l, link_state + (size_t)(e * M->nl + l) * 13);
+    }
+    return 0;
+}
+
 /* Diagnostics for the invariants tests: mass matrix, bias vector and total energy of one env. */
 int FN(grx_oracle_dynamics_terms)(const FN(Model) *M, const FN(SimCfg) *cfg, const REAL *base_inertial,
                                   const REAL *root, const REAL *q, const REAL *qd, REAL *Mq_out, REAL *h_out, REAL *energy_out) {

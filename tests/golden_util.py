@@ -1,0 +1,56 @@
+"""Helpers shared by the parity tests: rebuild configs / oracles from a golden fixture."""
+import os
+
+import numpy as np
+
+from grx_b200.config import make_cfg
+from grx_b200.robot import task_tables
+from grx_b200.urdf import builtin_model
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ENV_FIXTURES = ["plane64_dec1", "plane_gr1t1", "hf_gr1t1", "hf_gr1t2_dr"]
+
+
+def load_fixture(name):
+    return dict(np.load(os.path.join(GOLDEN, f"env_{name}.npz"), allow_pickle=False))
+
+
+def cfg_from_fixture(fx):
+    task, mesh = str(fx["meta/task"]), str(fx["meta/mesh_type"])
+    N = fx["const/friction"].shape[0]
+    cfg = make_cfg(task, N, mesh)
+    cfg.control.decimation = int(fx["meta/decimation"])
+    fl = fx["meta/flags"]
+    cfg.noise.add_noise, cfg.domain_rand.push_robots = bool(fl[0]), bool(fl[1])
+    cfg.terrain.curriculum = bool(fl[2])
+    cfg.domain_rand.randomize_init_dof_pos, cfg.domain_rand.randomize_init_base_velocity = bool(fl[3]), bool(fl[4])
+    if "meta/terrain_rows_cols" in fx:
+        cfg.terrain.num_rows, cfg.terrain.num_cols = [int(v) for v in fx["meta/terrain_rows_cols"]]
+        cfg.terrain.max_init_terrain_level = cfg.terrain.num_rows - 1
+    return cfg
+
+
+def setup_from_fixture(fx):
+    cfg = cfg_from_fixture(fx)
+    model = builtin_model(str(fx["meta/task"]))
+    tables = task_tables(model, cfg)
+    consts = dict(friction=fx["const/friction"], restitution=fx["const/restitution"],
+                  base_inertial=fx["const/base_inertial"], motor_strength=fx["const/motor_strength"],
+                  env_origins=fx["init/env_origins"])
+    terrain = None
+    if "const/height_samples" in fx:
+        consts.update(terrain_origins=fx["const/terrain_origins"], terrain_levels=fx["init/terrain_levels"],
+                      terrain_types=fx["const/terrain_types"])
+        terrain = dict(heights=fx["const/height_samples"], hscale=cfg.terrain.horizontal_scale,
+                       vscale=cfg.terrain.vertical_scale, border=float(cfg.terrain.border_size),
+                       friction=cfg.terrain.static_friction, restitution=cfg.terrain.restitution)
+    return cfg, model, tables, consts, terrain
+
+
+def init_state(fx):
+    return {k[len("init/"):]: v for k, v in fx.items() if k.startswith("init/")}
+
+
+def step_items(fx, t, group):
+    pre = f"step{t:02d}/{group}/"
+    return {k[len(pre):]: v for k, v in fx.items() if k.startswith(pre)}
