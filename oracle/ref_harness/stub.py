@@ -350,8 +350,7 @@ def install():
     # the REAL Isaac Gym python helpers, loaded by path
     pkg.torch_utils = _load_by_path("isaacgym.torch_utils", os.path.join(IG, "torch_utils.py"))
     from scipy import interpolate
-    if not hasattr(interpolate, "interp2d"):
-        interpolate.interp2d = _interp2d_linear   # removed in SciPy 1.14 (terrain_utils.py:44)
+    interpolate.interp2d = _interp2d_linear       # removed in SciPy 1.14 (still present as a raising stub); terrain_utils.py:44
     pkg.terrain_utils = _load_by_path("isaacgym.terrain_utils", os.path.join(IG, "terrain_utils.py"))
     if "matplotlib" not in sys.modules:
         try:
