@@ -1,0 +1,211 @@
+/*
+ * grx_b200 — C ABI of the B200-native GRx locomotion-RL hot path (libgrx_b200.so).
+ *
+ * Plain pointers and sizes only; no torch types.  Every entry returns 0 on success or a
+ * negative GRX_E_* code; the message is available from grx_last_error().  Device work is
+ * enqueued on the caller's stream (cudaStream_t passed as void*, NULL = legacy default
+ * stream); nothing in the step / update entries synchronises with the host.
+ *
+ * Reference interfaces replaced (paths under the reference repo, FFTAI/Wiki-GRx-Gym):
+ *   env side  — the `gym` object + gymtorch tensor interop used by
+ *               legged_gym/legged_gym/envs/base/legged_robot.py (create_sim/load_asset/create_actor:
+ *               507-528, 926-1090; acquire_*_tensor + wrap_tensor: 110-135; set_dof_actuation_force_tensor /
+ *               simulate / refresh_*: legged_robot_fftai.py:67-76; set_*_tensor_indexed: 737-740, 782-784)
+ *               and the task arithmetic on top of it (step: legged_robot.py:222-246).
+ *               GymTensor descriptor: IsaacGym_Preview_4_Package/isaacgym/python/isaacgym/_bindings/src/gymtorch/GymTensor.h:20-41.
+ *   PPO side  — rsl_rl/rsl_rl/algorithms/ppo.py (act 144-171, process_env_step 177-196, compute_returns 198-205,
+ *               update 215-321), storage/base_storage.py:80-141, storage/rollout_storage.py:56-112,
+ *               modules/actor_critic_mlp.py:165-231.
+ */
+#ifndef GRX_B200_H
+#define GRX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GRX_OK 0
+#define GRX_E_INVALID (-1)  /* bad argument / unsupported model topology */
+#define GRX_E_CUDA (-2)     /* CUDA runtime error (see grx_last_error) */
+#define GRX_E_NOTFOUND (-3) /* unknown buffer name */
+#define GRX_E_STATE (-4)    /* call order violated (e.g. step before set_params) */
+
+/* dtype codes follow GymTensor.h:20-27 (fp32, u32, u64, u8, i16) extended with i32 */
+enum { GRX_F32 = 0, GRX_U32 = 1, GRX_U64 = 2, GRX_U8 = 3, GRX_I16 = 4, GRX_I32 = 5 };
+
+/* Non-owning description of a device buffer (same role as GymTensor; adds element strides because
+ * per-env state lives in one array-of-records and is exported as strided views). */
+typedef struct {
+    void *data;
+    int32_t dtype;
+    int32_t ndim;
+    int64_t dims[4];
+    int64_t strides[4]; /* in elements */
+} grx_buffer;
+
+/* Flat dynamic model (host pointers, copied at create).  Produced by grx_b200/urdf.py + robot.py from the URDF
+ * (what gym.load_asset + the name-matching loops of legged_robot.py:176-192,594-616,1092-1161 produce). */
+typedef struct {
+    int32_t nb, nd, nl, ns, nf, nterm, nankle;
+    const int32_t *parent;                                       /* [nb] */
+    const float *jpos, *jrot, *axis;                             /* [nb*3] [nb*9] [nb*3] */
+    const float *mass, *com, *inertia;                           /* [nb] [nb*3] [nb*6] */
+    const float *dof_lower, *dof_upper, *dof_vel_limit, *dof_effort; /* [nd] hard limits (URDF) */
+    const float *soft_lower, *soft_upper;                        /* [nd] reward soft limits */
+    const float *kp, *kd, *default_pos;                          /* [nd] */
+    const int32_t *link_body;                                    /* [nl] */
+    const float *link_pos, *link_rot;                            /* [nl*3] [nl*9] */
+    const int32_t *sph_body, *sph_link;                          /* [ns] already in contact-priority order */
+    const float *sph_pos, *sph_rad;                              /* [ns*3] [ns] */
+    const int32_t *foot_links, *term_links, *ankle_dofs;         /* [nf] [nterm] [nankle] */
+    int32_t torso_link;
+} grx_model_desc;
+
+/* Simulation + task parameters (legged_robot_config.py / gr1t1_config.py values after _parse_cfg, legged_robot.py:91-104). */
+typedef struct {
+    /* sim */
+    float sim_dt, gravity, contact_offset, bounce_threshold, max_depen_vel, erp;
+    int32_t solver_iters, decimation;
+    float action_scale;
+    /* task */
+    int32_t num_obs, num_pri_obs, num_actions, num_height_points; /* 39, 168, 10, 121 */
+    float clip_actions_min[32], clip_actions_max[32], clip_observations;
+    float max_episode_length;        /* ceil(episode_length_s / dt) */
+    float max_episode_length_s;
+    int32_t resample_interval;       /* steps */
+    float cmd_range[3][2];           /* lin_vel_x, lin_vel_y, ang_vel_yaw */
+    float max_push_vel_xy;
+    int32_t add_noise, randomize_init_dof_pos, randomize_init_base_velocity, curriculum, custom_origins, measure_heights;
+    float noise_scale_vec[64];       /* [num_obs] */
+    float obs_scale_lin_vel, obs_scale_ang_vel, obs_scale_gravity, obs_scale_dof_pos, obs_scale_dof_vel,
+          obs_scale_action, obs_scale_height;
+    float base_init_state[13];
+    float measured_points_x[16], measured_points_y[16];
+    int32_t n_points_x, n_points_y;
+    float terrain_env_length;        /* terrain.env_length (curriculum move_up threshold = /2) */
+    /* rewards: scale*dt per term in alphabetical order of the 24 active terms, then parameters */
+    float reward_scale[24];
+    float base_height_target, swing_feet_height_target, feet_stumble_ratio, feet_air_time_target, feet_land_time_max;
+    float soft_dof_vel_limit, soft_torque_limit;
+    float sigma_action_diff, sigma_action_diff_diff, sigma_cmd_diff_ang_vel_yaw, sigma_cmd_diff_base_height,
+          sigma_cmd_diff_base_orient, sigma_cmd_diff_lin_vel_x, sigma_cmd_diff_lin_vel_y, sigma_cmd_diff_lin_vel_z,
+          sigma_cmd_diff_torso_orient, sigma_dof_acc_new, sigma_dof_tor_ankle_feet_lift_up, sigma_dof_tor_new,
+          sigma_feet_air_force, sigma_feet_air_height, sigma_feet_air_time, sigma_feet_land_time,
+          sigma_feet_speed_xy_close_to_ground, sigma_feet_stumble, sigma_limits_dof_pos, sigma_limits_dof_tor,
+          sigma_limits_dof_vel, sigma_pose_offset, sigma_stand_still;
+    uint64_t seed;                   /* Philox key for fast-mode draws */
+    int32_t env_id_offset;           /* global index of local env 0 (multi-GPU sharding; RNG streams keyed by global id) */
+} grx_task_cfg;
+
+typedef struct grx_env grx_env;
+
+const char *grx_last_error(void);
+int grx_version(void);
+/* sizeof() of {grx_buffer, grx_model_desc, grx_task_cfg, grx_injected_physics}, for FFI bindings to self-check their layouts */
+int grx_abi_sizes(int32_t *out, int32_t n);
+
+/* ---- environment -------------------------------------------------------------------------------------------- */
+int grx_env_create(const grx_model_desc *model, const grx_task_cfg *cfg, int32_t num_envs, int32_t device, grx_env **out);
+int grx_env_destroy(grx_env *env);
+
+/* terrain: replaces gym.add_ground (legged_robot.py:868-876) / gym.add_heightfield (878-901); samples = host int16
+ * [rows, cols], x = row axis, world x = row*hscale - border (same convention as height_samples at legged_robot.py:899-901) */
+int grx_env_set_terrain_plane(grx_env *env, float friction, float restitution);
+int grx_env_set_terrain_heightfield(grx_env *env, const int16_t *samples, int32_t rows, int32_t cols, float hscale,
+                                    float vscale, float border, float friction, float restitution);
+
+/* per-env parameters (host pointers): replaces the O(num_envs) create_actor loop, legged_robot.py:1008-1082.
+ * terrain_* may be NULL when custom_origins == 0.  terrain_origins = [t_rows, t_cols, 3]. */
+int grx_env_set_params(grx_env *env, const float *friction, const float *restitution, const float *motor_strength,
+                       const float *base_inertial, const float *env_origins, const int32_t *terrain_levels,
+                       const int32_t *terrain_types, const float *terrain_origins, int32_t t_rows, int32_t t_cols);
+
+/* zero-copy views of device state, by name (what acquire_*_tensor + gymtorch.wrap_tensor give, legged_robot.py:110-135):
+ * root_states dof_pos dof_vel last_dof_vel last_actions last_last_actions commands base_heights_offset feet_air_time
+ * feet_land_time feet_contact_last episode_length terrain_levels terrain_types env_origins episode_sums
+ * obs pri_obs rew reset time_out torques contact_forces foot_state episode_accum */
+int grx_env_get_buffer(grx_env *env, const char *name, grx_buffer *out);
+
+/* One policy step = legged_robot.py:222-246 with the GR1T1 MRO: action clip, `decimation` substeps of
+ * PD torque + articulated dynamics + contact + integration, then the whole post-physics path, in ONE kernel launch.
+ *   d_actions [N, num_actions] device fp32;  d_uniform: [N, GRX_RNG_K] device fp32 draws (parity mode) or NULL (fast
+ *   mode: counter-based Philox in-kernel);  delay: the scalar of legged_robot_fftai.py:53-54;  push != 0 on steps where
+ *   common_step_counter % push_interval == 0 (legged_robot.py:333-334);  step_index feeds the Philox counter. */
+int grx_env_step(grx_env *env, const float *d_actions, const float *d_uniform, float delay, int32_t push,
+                 uint64_t step_index, void *stream);
+
+/* Test entry: the post-physics half only, on injected physics outputs (device pointers); the env records must already
+ * hold the post-physics root / dof state.  Isolates the reference's own arithmetic (LR/FF/G1) from our dynamics spec. */
+typedef struct {
+    const float *torques;         /* [N, nd] */
+    const float *foot_state;      /* [N, nf, 13] */
+    const float *torso_quat;      /* [N, 4] */
+    const float *contact_forces;  /* [N, nl, 3] */
+    const float *avg_foot_force;  /* [N, nf] */
+    const float *avg_foot_linvel; /* [N, nf, 3] */
+} grx_injected_physics;
+int grx_env_post_physics(grx_env *env, const float *d_actions, const float *d_uniform, const grx_injected_physics *inj,
+                         int32_t push, uint64_t step_index, void *stream);
+
+/* Host-buffer convenience used for end-to-end timing: H2D of actions (pinned or pageable host memory), step,
+ * D2H of obs / pri_obs / rew / reset, then a stream synchronise.  Any output pointer may be NULL. */
+int grx_env_step_host(grx_env *env, const float *h_actions, float delay, int32_t push, uint64_t step_index,
+                      float *h_obs, float *h_pri_obs, float *h_rew, uint8_t *h_reset, void *stream);
+
+/* Debug / parity: mass matrix [nv*nv] and bias vector [nv] (internal velocity order: joints, base linear, base angular)
+ * of env `index` for its current state, computed by the same device code the step uses.  Host output pointers. */
+int grx_env_debug_dynamics(grx_env *env, int32_t index, float *h_M, float *h_h);
+
+#define GRX_RNG_K 68 /* == grx_b200/rng_layout.py K */
+
+/* ---- PPO ---------------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t num_envs, num_steps;             /* N (local), T */
+    int32_t num_obs, num_pri_obs, num_actions;
+    int32_t actor_hidden[3], critic_hidden[3];
+    int32_t num_learning_epochs, num_mini_batches;
+    float clip_param, gamma, lam, value_loss_coef, entropy_coef;
+    float learning_rate, learning_rate_min, learning_rate_max, desired_kl, max_grad_norm;
+    int32_t adaptive_schedule, use_clipped_value_loss;
+    float init_noise_std;
+    int32_t use_tensor_cores;                /* 1: tcgen05 kind::tf32 GEMMs for the dense layers, 0: fp32 SIMT GEMMs */
+    int32_t world_size;                      /* gradient / KL sums are divided by this after the caller's all-reduce */
+} grx_ppo_cfg;
+
+typedef struct grx_ppo grx_ppo;
+
+int grx_ppo_create(const grx_ppo_cfg *cfg, int32_t device, grx_ppo **out);
+int grx_ppo_destroy(grx_ppo *ppo);
+/* views: params grads adam_m adam_v (flat, reference state_dict order: std, actor.model.{0,2,4,6}.{weight,bias},
+ * critic...), obs critic_obs actions values rewards dones actions_log_prob mu sigma returns advantages,
+ * lr kl_mean stats (device scalars), reduce_buf (grads + [kl_sum, count, nan] tail; what the caller all-reduces) */
+int grx_ppo_get_buffer(grx_ppo *ppo, const char *name, grx_buffer *out);
+/* PPO.act (ppo.py:144-171) for rollout step t: actor+critic forward, a = mu + sigma*eps, log-prob; everything stored
+ * into row t of the rollout storage (base_storage.py:80-100).  d_eps [N, A] standard normal draws or NULL (Philox). */
+int grx_ppo_act(grx_ppo *ppo, const float *d_obs, const float *d_critic_obs, const float *d_eps, int32_t t,
+                float *d_actions_out, uint64_t step_index, void *stream);
+/* PPO.process_env_step (ppo.py:177-196): rewards += gamma * V * time_out; store rewards / dones in row t. */
+int grx_ppo_process_env_step(grx_ppo *ppo, const float *d_rewards, const uint8_t *d_dones, const uint8_t *d_time_outs,
+                             int32_t t, void *stream);
+/* PPO.compute_returns (ppo.py:198-205, base_storage.py:120-141): critic(last obs), reverse GAE scan, advantage
+ * normalisation.  For multi-GPU the three moments [sum, sum of squares, count] are left in `adv_moments` between
+ * grx_ppo_compute_returns_local and grx_ppo_normalize_advantages so the caller can all-reduce them. */
+int grx_ppo_compute_returns(grx_ppo *ppo, const float *d_last_critic_obs, void *stream);
+int grx_ppo_compute_returns_local(grx_ppo *ppo, const float *d_last_critic_obs, void *stream);
+int grx_ppo_normalize_advantages(grx_ppo *ppo, void *stream);
+/* One minibatch of PPO.update (ppo.py:244-305), split so a gradient all-reduce can sit in between:
+ *   grads: gather rows d_indices[mb*B .. (mb+1)*B) of the rollout, forward, losses, backward -> reduce_buf
+ *   apply: KL -> adaptive LR (device scalar, no .item()), NaN-skip, global-norm clip, Adam */
+int grx_ppo_minibatch_grads(grx_ppo *ppo, const int64_t *d_indices, int32_t mb, void *stream);
+int grx_ppo_minibatch_apply(grx_ppo *ppo, void *stream);
+/* Whole PPO.update (ppo.py:215-321) for world_size == 1: epochs x minibatches of grads+apply. */
+int grx_ppo_update(grx_ppo *ppo, const int64_t *d_indices, void *stream);
+/* actor-only forward for play.py / get_inference_policy (actor_critic_mlp.py:209-217) */
+int grx_ppo_act_inference(grx_ppo *ppo, const float *d_obs, int32_t n, float *d_actions_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRX_B200_H */

@@ -69,6 +69,9 @@ class PhysOracle:
         m.nb, m.nd, m.nl, m.ns = model["nb"], model["nd"], len(model["link_names"]), len(model["sph_rad"])
         fl = np.asarray(ctl["foot_links"], dtype=np.int32)
         m.nf = len(fl)
+        order = np.asarray(ctl.get("sph_order", np.arange(len(model["sph_rad"]))))   # contact priority (robot.task_tables)
+        model = dict(model, sph_body=model["sph_body"][order], sph_link=model["sph_link"][order],
+                     sph_pos=model["sph_pos"][order], sph_rad=model["sph_rad"][order])
         for k in ("parent", "link_body", "sph_body", "sph_link"):
             setattr(m, k, self._iptr(model[k]))
         m.foot_links = self._iptr(fl)
@@ -96,7 +99,7 @@ class PhysOracle:
         self.t = t
         s = SimCfg()
         d = dict(dt=0.002, gravity=-9.81, contact_offset=0.01, bounce_threshold=0.5, max_depen_vel=1.0, erp=0.2,
-                 solver_iters=4, decimation=10, action_scale=1.0, max_contacts=16)
+                 solver_iters=4, decimation=10, action_scale=1.0, max_contacts=8)
         d.update(sim or {})
         for k, v in d.items():
             setattr(s, k, v)

@@ -63,12 +63,13 @@ typedef struct {
     int solver_iters;       /* 4 */
     int decimation;         /* 10 */
     REAL action_scale;      /* 1.0 */
-    int max_contacts;       /* 16 */
+    int max_contacts;       /* 8: with <= 8 limit rows the solver has at most 32 rows = one warp lane per row */
 } FN(SimCfg);
 
 #define MAXB 36
 #define MAXV 40
 #define MAXC 16
+#define MAXLIM 8
 #define MAXROWS (3 * MAXC + MAXV)
 
 static inline void FN(v3cross)(const REAL *a, const REAL *b, REAL *o) {
@@ -347,10 +348,11 @@ static int FN(substep)(const FN(Model) *M, const FN(Terrain) *T, const FN(SimCfg
         bias[3 * c] = target; bias[3 * c + 1] = 0; bias[3 * c + 2] = 0;
     }
     int nrows = 3 * C.count;
-    /* joint limit rows (speculative): lower: qd >= (lo - q)/dt ; upper: -qd >= (q - hi)/dt */
+    /* joint limit rows (speculative, predicted with the PRE-step joint rate so that all constraint rows are known
+     * before the single M^-1 solve pass): lower: qd >= (lo - q)/dt ; upper: -qd >= (q - hi)/dt.  At most MAXLIM rows. */
     int lim_joint[MAXV]; REAL lim_sign[MAXV], lim_lam[MAXV]; int nlim = 0;
-    for (int j = 0; j < nd; j++) {
-        REAL qn = q[j] + dt * u[j];
+    for (int j = 0; j < nd && nlim < MAXLIM; j++) {
+        REAL qn = q[j] + dt * qd[j];
         REAL sgn = 0, tgt = 0;
         if (qn < M->dof_lower[j]) { sgn = 1; tgt = (M->dof_lower[j] - q[j]) / dt; }
         else if (qn > M->dof_upper[j]) { sgn = -1; tgt = (q[j] - M->dof_upper[j]) / dt; }
@@ -545,4 +547,5 @@ int FN(grx_oracle_dynamics_terms)(const FN(Model) *M, const FN(SimCfg) *cfg, con
 #undef MAXB
 #undef MAXV
 #undef MAXC
+#undef MAXLIM
 #undef MAXROWS

@@ -220,7 +220,10 @@ class FakeGym:
             m, c, I6 = base_inertial_for(self.model, e["mass_scale"], e["com_offset"])
             bi[i, 0], bi[i, 1:4], bi[i, 4:10] = m, c, I6
         self.base_inertial = bi
-        ctl = dict(kp=np.zeros(nd), kd=np.zeros(nd), default_pos=np.zeros(nd), foot_links=[0])
+        from grx_b200.config import make_cfg
+        from grx_b200.robot import task_tables
+        order = task_tables(self.model, make_cfg(self.model["name"]))["sph_order"]   # same contact priority as the product
+        ctl = dict(kp=np.zeros(nd), kd=np.zeros(nd), default_pos=np.zeros(nd), foot_links=[0], sph_order=order)
         sp = self.sim_params
         terr = self.terrain
         if terr is not None and "trimesh" in terr:

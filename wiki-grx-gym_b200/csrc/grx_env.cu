@@ -1,0 +1,1435 @@
+// grx_env.cu — the fused GRx env-step kernel for sm_100a and its C ABI (include/grx_b200.h).
+//
+// One warp per robot.  One launch = one policy step of the reference's LeggedRobot.step() with the GR1T1 MRO
+// (legged_robot.py:222-246, legged_robot_fftai.py:46-133, gr1t1.py:281-589):
+//   action clip -> `decimation` x [PD torque -> articulated-body dynamics -> contact/limit solve -> integrate]
+//   -> state update, height sampling, termination, 24 reward terms, reset + curriculum, observations.
+// The per-env state record (432 B) and parameter record (96 B) are staged into shared memory with TMA bulk copies
+// (cp.async.bulk + mbarrier) and the updated record / privileged-observation row go back the same way; the small
+// outputs are written with coalesced lane-strided stores.  Dynamics = spec "GRX-dyn v1" (oracle/phys_impl.h is the
+// fp64/fp32 CPU statement of the same equations): Kane's equations with composite-rigid-body mass matrix about the
+// base origin, branch-sparse Cholesky, one lane per constraint row (<= 8 contacts x 3 + <= 8 joint limits = 32 rows),
+// Delassus-space projected Gauss-Seidel.
+//
+// Topology handled by this kernel: floating base + 2 serial chains of 5 revolute joints (the registered lower-limb
+// GR1T1 / GR1T2 tasks); grx_env_create rejects anything else.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "grx_b200.h"
+
+namespace {
+
+constexpr int NB = 11, ND = 10, NV = 16, CH = 5, NLMAX = 40, NSMAX = 32, NF = 2, KC = 8, KLIM = 8;
+constexpr int NREW = 24, NHMAX = 128;
+constexpr int WARPS_PER_CTA = 4;
+constexpr unsigned FULL = 0xffffffffu;
+
+// ---- per-env state record (floats; ints stored bit-wise) — 108 floats = 432 B, 16-B aligned
+enum { R_ROOT = 0, R_DOFPOS = 16, R_DOFVEL = 26, R_LASTDOFVEL = 36, R_LASTACT = 46, R_LASTLASTACT = 56, R_CMD = 66,
+       R_BHO = 69, R_AIR = 70, R_LAND = 72, R_CLAST = 74, R_EPLEN = 76, R_TLEVEL = 77, R_ORIGIN = 78, R_TTYPE = 81,
+       R_SUMS = 82, REC_F = 108 };
+// ---- per-env parameter record — 24 floats = 96 B
+enum { C_MOTOR = 0, C_BI = 10, C_FRIC = 20, C_REST = 21, CST_F = 24 };
+// ---- uniform-draw slots (grx_b200/rng_layout.py)
+enum { U_NOISE = 0, U_RESET_DOF = 39, U_RESET_XY = 49, U_RESET_YAW = 51, U_RESET_VEL = 52, U_CMD_TIME = 58,
+       U_CMD_RESET = 61, U_PUSH = 64, U_CURRICULUM = 66 };
+static_assert(GRX_RNG_K == 68, "rng layout");
+
+struct ModelDev {
+    float jpos[NB][3], jrot[NB][9], axis[NB][3], mass[NB], com[NB][3], inertia[NB][6];
+    float dof_lower[ND], dof_upper[ND], dof_vel_limit[ND], dof_effort[ND], soft_lower[ND], soft_upper[ND];
+    float kp[ND], kd[ND], q0[ND];
+    int ns, nl;
+    int sph_body[NSMAX], sph_link[NSMAX];
+    float sph_pos[NSMAX][3], sph_rad[NSMAX];
+    int foot_link[NF], foot_body[NF];
+    float foot_pos[NF][3];
+    float torso_rot[9];
+    int torso_body;
+    unsigned long long term_mask;
+    int ankle_dof[2];
+    int pad_;
+};
+
+struct TerrainDev {
+    int type, rows, cols;
+    const short *h;
+    float hscale, vscale, border, friction, restitution;
+};
+
+struct EnvArgs {
+    float *rec;
+    const float *cst;
+    const ModelDev *model;
+    TerrainDev terrain;
+    const float *terrain_origins;  // [t_rows, t_cols, 3]
+    int t_rows, t_cols;
+    int N;
+    const float *actions;
+    const float *U;  // nullable
+    float delay;
+    int push;
+    unsigned long long step_index;
+    float *obs, *pri_obs, *rew, *torques, *contact_forces, *foot_state, *episode_accum;
+    unsigned char *reset, *time_out;
+    grx_injected_physics inj;
+    float *dbg_M, *dbg_h;  // debug_dynamics
+    int dbg_index;
+};
+
+// per-warp shared-memory workspace
+struct alignas(16) WS {
+    float rec[REC_F];
+    float cst[CST_F];
+    float pri[168];  // privileged-observation row staging (bulk-stored)
+    float R[NB][9], o[NB][3], a[NB][3], c[NB][3], Iw[NB][6], w[NB][3], vo[NB][3], al[NB][3], ao[NB][3];
+    float bi[NB][10], bw[NB][6];
+    float S[ND][6], F[ND][6];
+    float M[NV][NV + 1];
+    float invd[NV], h[NV], u[NV], tau[NV];
+    float Y[32][NV];     // reused after physics: measured heights [121] + obs staging
+    float rowc[32][2];   // invA, bias
+    float cfr[KC][9];    // contact frame n, t1, t2
+    float cpt[KC][4];    // contact point xyz, target velocity
+    int cbody[KC], clink[KC];
+    int limj[KLIM];
+    float lims[KLIM], limt[KLIM];
+    float cf[NLMAX * 3];
+    float rterm[NREW];
+    unsigned long long mbar;
+};
+
+__device__ __forceinline__ void cross3(const float *a, const float *b, float *o) {
+    float x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+    o[0] = x; o[1] = y; o[2] = z;
+}
+__device__ __forceinline__ float dot3(const float *a, const float *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+__device__ __forceinline__ void m3v(const float *R, const float *v, float *o) {
+    float x = R[0] * v[0] + R[1] * v[1] + R[2] * v[2];
+    float y = R[3] * v[0] + R[4] * v[1] + R[5] * v[2];
+    float z = R[6] * v[0] + R[7] * v[1] + R[8] * v[2];
+    o[0] = x; o[1] = y; o[2] = z;
+}
+__device__ __forceinline__ void m3m(const float *A, const float *B, float *C) {
+    float t[9];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) t[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+#pragma unroll
+    for (int i = 0; i < 9; i++) C[i] = t[i];
+}
+__device__ __forceinline__ void quat2mat(const float *q, float *R) {
+    float x = q[0], y = q[1], z = q[2], w = q[3];
+    R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - z * w);     R[2] = 2 * (x * z + y * w);
+    R[3] = 2 * (x * y + z * w);     R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - x * w);
+    R[6] = 2 * (x * z - y * w);     R[7] = 2 * (y * z + x * w);     R[8] = 1 - 2 * (x * x + y * y);
+}
+__device__ __forceinline__ void mat2quat(const float *R, float *q) {
+    float tr = R[0] + R[4] + R[8];
+    if (tr > 0) { float s = sqrtf(tr + 1) * 2; q[3] = s / 4; q[0] = (R[7] - R[5]) / s; q[1] = (R[2] - R[6]) / s; q[2] = (R[3] - R[1]) / s; }
+    else if (R[0] > R[4] && R[0] > R[8]) { float s = sqrtf(1 + R[0] - R[4] - R[8]) * 2; q[3] = (R[7] - R[5]) / s; q[0] = s / 4; q[1] = (R[1] + R[3]) / s; q[2] = (R[2] + R[6]) / s; }
+    else if (R[4] > R[8]) { float s = sqrtf(1 + R[4] - R[0] - R[8]) * 2; q[3] = (R[2] - R[6]) / s; q[0] = (R[1] + R[3]) / s; q[1] = s / 4; q[2] = (R[5] + R[7]) / s; }
+    else { float s = sqrtf(1 + R[8] - R[0] - R[4]) * 2; q[3] = (R[3] - R[1]) / s; q[0] = (R[2] + R[6]) / s; q[1] = (R[5] + R[7]) / s; q[2] = s / 4; }
+}
+__device__ __forceinline__ void axang2mat(const float *a, float th, float *R) {
+    float s, c;
+    sincosf(th, &s, &c);
+    float t = 1 - c;
+    R[0] = c + a[0] * a[0] * t;        R[1] = a[0] * a[1] * t - a[2] * s; R[2] = a[0] * a[2] * t + a[1] * s;
+    R[3] = a[1] * a[0] * t + a[2] * s; R[4] = c + a[1] * a[1] * t;        R[5] = a[1] * a[2] * t - a[0] * s;
+    R[6] = a[2] * a[0] * t - a[1] * s; R[7] = a[2] * a[1] * t + a[0] * s; R[8] = c + a[2] * a[2] * t;
+}
+__device__ __forceinline__ void sym6v(const float *S, const float *v, float *o) {
+    float x = S[0] * v[0] + S[3] * v[1] + S[4] * v[2];
+    float y = S[3] * v[0] + S[1] * v[1] + S[5] * v[2];
+    float z = S[4] * v[0] + S[5] * v[1] + S[2] * v[2];
+    o[0] = x; o[1] = y; o[2] = z;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+// torch_utils.py:72-81 quat_rotate_inverse
+__device__ __forceinline__ void quat_rotate_inverse(const float *q, const float *v, float *o) {
+    float qw = q[3];
+    float s = 2.0f * qw * qw - 1.0f;
+    float cx[3]; cross3(q, v, cx);
+    float d = q[0] * v[0] + q[1] * v[1] + q[2] * v[2];
+#pragma unroll
+    for (int k = 0; k < 3; k++) o[k] = v[k] * s - cx[k] * qw * 2.0f + q[k] * d * 2.0f;
+}
+
+// ---- TMA bulk copies (1-D) + mbarrier
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- Philox4x32-10 (counter-based draws for fast mode)
+__device__ __forceinline__ void philox4(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t *out) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+struct Draw {
+    const float *U;  // row of this env or nullptr
+    uint32_t k0, k1, gid, step_lo, step_hi;
+    __device__ __forceinline__ float operator()(int slot) const {
+        if (U) return U[slot];
+        uint32_t r[4];
+        philox4(k0, k1, gid, step_lo, step_hi, (uint32_t)(slot >> 2), r);
+        return (float)(r[slot & 3] >> 8) * (1.0f / 16777216.0f);  // 24-bit mantissa uniform in [0,1), like torch.rand
+    }
+};
+
+// ---- terrain query (oracle/phys_impl.h terrain_query)
+__device__ __forceinline__ void terrain_query(const TerrainDev &t, float x, float y, float &h, float *n) {
+    if (t.type == 0) { h = 0; n[0] = 0; n[1] = 0; n[2] = 1; return; }
+    float gx = (x + t.border) / t.hscale, gy = (y + t.border) / t.hscale;
+    int i = (int)floorf(gx), j = (int)floorf(gy);
+    if (i < 0) { i = 0; gx = 0; }
+    if (j < 0) { j = 0; gy = 0; }
+    if (i > t.rows - 2) { i = t.rows - 2; gx = (float)(t.rows - 1); }
+    if (j > t.cols - 2) { j = t.cols - 2; gy = (float)(t.cols - 1); }
+    float fx = gx - (float)i, fy = gy - (float)j;
+    const short *p = t.h + (size_t)i * t.cols + j;
+    float h00 = __ldg(p) * t.vscale, h01 = __ldg(p + 1) * t.vscale;
+    float h10 = __ldg(p + t.cols) * t.vscale, h11 = __ldg(p + t.cols + 1) * t.vscale;
+    float dhx, dhy;
+    if (fx >= fy) { dhx = h10 - h00; dhy = h11 - h10; }
+    else { dhx = h11 - h01; dhy = h01 - h00; }
+    h = h00 + dhx * fx + dhy * fy;
+    float sx = -dhx / t.hscale, sy = -dhy / t.hscale;
+    float inv = 1.0f / sqrtf(sx * sx + sy * sy + 1.0f);
+    n[0] = sx * inv; n[1] = sy * inv; n[2] = inv;
+}
+
+// ---- forward kinematics + body velocities + velocity-product accelerations; lane b < NB owns body b and walks its own chain
+__device__ __forceinline__ void kinematics(WS &s, const ModelDev &m, int lane) {
+    if (lane < NB) {
+        const float *rt = s.rec + R_ROOT;
+        float R[9], o[3], w[3], vo[3], al[3] = {0, 0, 0}, ao[3] = {0, 0, 0}, a[3] = {0, 0, 0};
+        quat2mat(rt + 3, R);
+#pragma unroll
+        for (int k = 0; k < 3; k++) { o[k] = rt[k]; vo[k] = rt[7 + k]; w[k] = rt[10 + k]; }
+        const int leg = (lane - 1) / CH, depth = lane == 0 ? 0 : (lane - 1) % CH + 1;
+#pragma unroll
+        for (int k = 0; k < CH; k++) {
+            if (k < depth) {
+                const int j = 1 + leg * CH + k;
+                const float q = s.rec[R_DOFPOS + j - 1], qd = s.rec[R_DOFVEL + j - 1];
+                float Rj[9], Rq[9], r[3], an[3], t1[3], t2[3], t3[3], t4[3];
+                m3m(R, m.jrot[j], Rj);
+                axang2mat(m.axis[j], q, Rq);
+                m3v(R, m.jpos[j], r);
+                m3m(Rj, Rq, R);
+                m3v(R, m.axis[j], an);
+                cross3(w, r, t1);
+                cross3(al, r, t2);
+                cross3(w, t1, t3);
+                cross3(w, an, t4);
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    o[i] += r[i]; vo[i] += t1[i]; ao[i] += t2[i] + t3[i];
+                    al[i] += t4[i] * qd; w[i] += an[i] * qd; a[i] = an[i];
+                }
+            }
+        }
+        const float *com = lane == 0 ? s.cst + C_BI + 1 : m.com[lane];
+        const float *I6 = lane == 0 ? s.cst + C_BI + 4 : m.inertia[lane];
+        float rc[3];
+        m3v(R, com, rc);
+        float I[9] = {I6[0], I6[3], I6[4], I6[3], I6[1], I6[5], I6[4], I6[5], I6[2]}, T[9], Rt[9];
+        m3m(R, I, T);
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) Rt[3 * i + j] = R[3 * j + i];
+        m3m(T, Rt, T);
+#pragma unroll
+        for (int i = 0; i < 9; i++) s.R[lane][i] = R[i];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            s.o[lane][i] = o[i]; s.a[lane][i] = a[i]; s.c[lane][i] = o[i] + rc[i];
+            s.w[lane][i] = w[i]; s.vo[lane][i] = vo[i]; s.al[lane][i] = al[i]; s.ao[lane][i] = ao[i];
+        }
+        s.Iw[lane][0] = T[0]; s.Iw[lane][1] = T[4]; s.Iw[lane][2] = T[8];
+        s.Iw[lane][3] = T[1]; s.Iw[lane][4] = T[2]; s.Iw[lane][5] = T[5];
+    }
+    __syncwarp();
+}
+
+// ---- mass matrix (internal order: joints 0..9, base linear 10..12, base angular 13..15) + bias vector
+__device__ __forceinline__ void mass_and_bias(WS &s, const ModelDev &m, float gravity, int lane) {
+    for (int i = lane; i < NV * (NV + 1); i += 32) (&s.M[0][0])[i] = 0.0f;
+    if (lane < NB) {
+        const int b = lane;
+        const float mass = b == 0 ? s.cst[C_BI] : m.mass[b];
+        float r[3], rc[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) { r[k] = s.c[b][k] - s.o[0][k]; rc[k] = s.c[b][k] - s.o[b][k]; }
+        const float rr = dot3(r, r);
+        float *bi = s.bi[b];
+        bi[0] = mass; bi[1] = mass * r[0]; bi[2] = mass * r[1]; bi[3] = mass * r[2];
+        bi[4] = s.Iw[b][0] + mass * (rr - r[0] * r[0]); bi[5] = s.Iw[b][1] + mass * (rr - r[1] * r[1]);
+        bi[6] = s.Iw[b][2] + mass * (rr - r[2] * r[2]);
+        bi[7] = s.Iw[b][3] - mass * r[0] * r[1]; bi[8] = s.Iw[b][4] - mass * r[0] * r[2]; bi[9] = s.Iw[b][5] - mass * r[1] * r[2];
+        float t1[3], t2[3], ac[3], Iw_[3], Ial[3], g3[3], f[3];
+        cross3(s.al[b], rc, t1); cross3(s.w[b], rc, t2); cross3(s.w[b], t2, t2);
+#pragma unroll
+        for (int k = 0; k < 3; k++) ac[k] = s.ao[b][k] + t1[k] + t2[k];
+        ac[2] -= gravity;
+#pragma unroll
+        for (int k = 0; k < 3; k++) f[k] = mass * ac[k];
+        sym6v(s.Iw[b], s.w[b], Iw_); sym6v(s.Iw[b], s.al[b], Ial);
+        cross3(s.w[b], Iw_, g3); cross3(r, f, t1);
+#pragma unroll
+        for (int k = 0; k < 3; k++) { s.bw[b][k] = f[k]; s.bw[b][3 + k] = Ial[k] + g3[k] + t1[k]; }
+    }
+    __syncwarp();
+    if (lane <= ND) {
+        // lanes 0..9: composite of the chain suffix starting at joint body lane+1; lane 10: whole robot
+        int first, last;
+        if (lane < ND) { first = lane + 1; last = 1 + (lane / CH) * CH + CH - 1; }
+        else { first = 0; last = NB - 1; }
+        float ci[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, cw[6] = {0, 0, 0, 0, 0, 0};
+        for (int b = first; b <= last; b++) {
+#pragma unroll
+            for (int k = 0; k < 10; k++) ci[k] += s.bi[b][k];
+#pragma unroll
+            for (int k = 0; k < 6; k++) cw[k] += s.bw[b][k];
+        }
+        if (lane < ND) {
+            const int j = lane + 1;
+            float d[3], Sl[3], Sa[3], t1[3], t2[3], t3[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) { d[k] = s.o[0][k] - s.o[j][k]; Sa[k] = s.a[j][k]; }
+            cross3(Sa, d, Sl);
+            cross3(Sa, ci + 1, t1);
+            cross3(ci + 1, Sl, t2);
+            sym6v(ci + 4, Sa, t3);
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                s.S[lane][k] = Sl[k]; s.S[lane][3 + k] = Sa[k];
+                s.F[lane][k] = ci[0] * Sl[k] + t1[k]; s.F[lane][3 + k] = t2[k] + t3[k];
+            }
+            s.h[lane] = dot3(Sl, cw) + dot3(Sa, cw + 3);
+        } else {
+            const float mm = ci[0], *hh = ci + 1, *I = ci + 4;
+            const int L = ND, A = ND + 3;
+            const float hx[9] = {0, -hh[2], hh[1], hh[2], 0, -hh[0], -hh[1], hh[0], 0};
+#pragma unroll
+            for (int k = 0; k < 3; k++) s.M[L + k][L + k] = mm;
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int j = 0; j < 3; j++) { s.M[A + i][L + j] = hx[3 * i + j]; s.M[L + j][A + i] = hx[3 * i + j]; }
+            s.M[A][A] = I[0]; s.M[A + 1][A + 1] = I[1]; s.M[A + 2][A + 2] = I[2];
+            s.M[A][A + 1] = s.M[A + 1][A] = I[3];
+            s.M[A][A + 2] = s.M[A + 2][A] = I[4];
+            s.M[A + 1][A + 2] = s.M[A + 2][A + 1] = I[5];
+#pragma unroll
+            for (int k = 0; k < 6; k++) s.h[L + k] = cw[k];
+        }
+    }
+    __syncwarp();
+    if (lane < 30) {  // joint-joint entries: 15 (ancestor, descendant) pairs per leg
+        const int leg = lane / 15, idx = lane % 15;
+        int kj = 0, acc = 0;
+#pragma unroll
+        for (int t = 0; t < CH; t++) if (idx >= acc + t + 1) { acc += t + 1; kj = t + 1; }
+        const int ki = idx - acc;
+        const int i = leg * CH + ki, j = leg * CH + kj;
+        const float v = dot3(s.S[i], s.F[j]) + dot3(s.S[i] + 3, s.F[j] + 3);
+        s.M[i][j] = v; s.M[j][i] = v;
+    }
+    for (int e = lane; e < 6 * ND; e += 32) {  // base-joint coupling: M[10+k][j] = F_j[k]
+        const int j = e % ND, k = e / ND;
+        const float v = s.F[j][k];
+        s.M[ND + k][j] = v; s.M[j][ND + k] = v;
+    }
+    __syncwarp();
+}
+
+// ---- branch-sparse Cholesky of M in place (lower factor; zero block between the two legs never fills)
+__device__ __forceinline__ void cholesky(WS &s, int lane) {
+    if (lane < 2) {
+        const int base = lane * CH;
+        float L[CH][CH];
+#pragma unroll
+        for (int i = 0; i < CH; i++)
+#pragma unroll
+            for (int j = 0; j <= i; j++) L[i][j] = s.M[base + i][base + j];
+#pragma unroll
+        for (int k = 0; k < CH; k++) {
+            float d = L[k][k];
+#pragma unroll
+            for (int p = 0; p < k; p++) d -= L[k][p] * L[k][p];
+            d = sqrtf(d);
+            const float inv = 1.0f / d;
+            L[k][k] = d;
+            s.invd[base + k] = inv;
+#pragma unroll
+            for (int i = k + 1; i < CH; i++) {
+                float t = L[i][k];
+#pragma unroll
+                for (int p = 0; p < k; p++) t -= L[i][p] * L[k][p];
+                L[i][k] = t * inv;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < CH; i++)
+#pragma unroll
+            for (int j = 0; j <= i; j++) s.M[base + i][base + j] = L[i][j];
+    }
+    __syncwarp();
+    if (lane < 12) {  // W = C L^-T for the 6 base rows x 2 legs
+        const int i = ND + lane / 2, base = (lane % 2) * CH;
+        float W[CH];
+#pragma unroll
+        for (int k = 0; k < CH; k++) {
+            float t = s.M[i][base + k];
+#pragma unroll
+            for (int p = 0; p < k; p++) t -= W[p] * s.M[base + k][base + p];
+            W[k] = t * s.invd[base + k];
+        }
+#pragma unroll
+        for (int k = 0; k < CH; k++) s.M[i][base + k] = W[k];
+    }
+    __syncwarp();
+    if (lane < 21) {  // Schur complement on the base block (lower triangle)
+        int i = 0, acc = 0;
+#pragma unroll
+        for (int t = 0; t < 6; t++) if (lane >= acc + t + 1) { acc += t + 1; i = t + 1; }
+        const int j = lane - acc;
+        float t = s.M[ND + i][ND + j];
+#pragma unroll
+        for (int c = 0; c < ND; c++) t -= s.M[ND + i][c] * s.M[ND + j][c];
+        s.M[ND + i][ND + j] = t;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        float L[6][6];
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+#pragma unroll
+            for (int j = 0; j <= i; j++) L[i][j] = s.M[ND + i][ND + j];
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            float d = L[k][k];
+#pragma unroll
+            for (int p = 0; p < k; p++) d -= L[k][p] * L[k][p];
+            d = sqrtf(d);
+            const float inv = 1.0f / d;
+            L[k][k] = d;
+            s.invd[ND + k] = inv;
+#pragma unroll
+            for (int i = k + 1; i < 6; i++) {
+                float t = L[i][k];
+#pragma unroll
+                for (int p = 0; p < k; p++) t -= L[i][p] * L[k][p];
+                L[i][k] = t * inv;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+#pragma unroll
+            for (int j = 0; j <= i; j++) s.M[ND + i][ND + j] = L[i][j];
+    }
+    __syncwarp();
+}
+
+// x <- M^-1 x with the factor in s.M (every lane solves its own right-hand side; reads of L are warp-broadcasts)
+__device__ __forceinline__ void chol_solve(const WS &s, float *x) {
+#pragma unroll
+    for (int leg = 0; leg < 2; leg++) {
+#pragma unroll
+        for (int i = 0; i < CH; i++) {
+            float t = x[leg * CH + i];
+#pragma unroll
+            for (int p = 0; p < i; p++) t -= s.M[leg * CH + i][leg * CH + p] * x[leg * CH + p];
+            x[leg * CH + i] = t * s.invd[leg * CH + i];
+        }
+    }
+#pragma unroll
+    for (int i = ND; i < NV; i++) {
+        float t = x[i];
+#pragma unroll
+        for (int p = 0; p < i; p++) t -= s.M[i][p] * x[p];
+        x[i] = t * s.invd[i];
+    }
+#pragma unroll
+    for (int i = NV - 1; i >= ND; i--) {
+        float t = x[i];
+#pragma unroll
+        for (int p = i + 1; p < NV; p++) t -= s.M[p][i] * x[p];
+        x[i] = t * s.invd[i];
+    }
+#pragma unroll
+    for (int leg = 0; leg < 2; leg++) {
+#pragma unroll
+        for (int i = CH - 1; i >= 0; i--) {
+            float t = x[leg * CH + i];
+#pragma unroll
+            for (int p = i + 1; p < CH; p++) t -= s.M[leg * CH + p][leg * CH + i] * x[leg * CH + p];
+#pragma unroll
+            for (int p = ND; p < NV; p++) t -= s.M[p][leg * CH + i] * x[p];
+            x[leg * CH + i] = t * s.invd[leg * CH + i];
+        }
+    }
+}
+
+// ---- one dt: contacts + limits + solve + integrate.  Needs kinematics() of the current state in s.
+__device__ __forceinline__ void substep(WS &s, const ModelDev &m, const EnvArgs &A, const grx_task_cfg &cfg, int lane) {
+    const float dt = cfg.sim_dt;
+    mass_and_bias(s, m, cfg.gravity, lane);
+    if (A.dbg_M != nullptr && A.dbg_index == (int)(blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5))) {  // debug_dynamics: export before factorisation
+        for (int i = lane; i < NV * NV; i += 32) A.dbg_M[i] = s.M[i / NV][i % NV];
+        if (lane < NV) A.dbg_h[lane] = s.h[lane];
+        __syncwarp();
+    }
+    cholesky(s, lane);
+    const float mu = 0.5f * (s.cst[C_FRIC] + A.terrain.friction), rest = 0.5f * (s.cst[C_REST] + A.terrain.restitution);
+    // ---- contact detection: lane = sphere
+    bool act = false;
+    float n[3] = {0, 0, 1}, xs[3] = {0, 0, 0}, dist = 0, rad = 0;
+    int sb = 0;
+    if (lane < m.ns) {
+        sb = m.sph_body[lane];
+        rad = m.sph_rad[lane];
+        m3v(s.R[sb], m.sph_pos[lane], xs);
+#pragma unroll
+        for (int k = 0; k < 3; k++) xs[k] += s.o[sb][k];
+        float hgt;
+        terrain_query(A.terrain, xs[0], xs[1], hgt, n);
+        dist = (xs[2] - hgt) * n[2] - rad;
+        act = dist < cfg.contact_offset;
+    }
+    const unsigned bal = __ballot_sync(FULL, act);
+    const int rank = __popc(bal & ((1u << lane) - 1u));
+    const int nc = min(__popc(bal), KC);
+    if (act && rank < KC) {
+        float xc[3], t1[3], t2[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) xc[k] = xs[k] - n[k] * rad;
+        const bool usey = n[0] > 0.9f || n[0] < -0.9f;
+        const float e[3] = {usey ? 0.f : 1.f, usey ? 1.f : 0.f, 0.f};
+        const float dn = dot3(e, n);
+#pragma unroll
+        for (int k = 0; k < 3; k++) t1[k] = e[k] - dn * n[k];
+        const float inv = 1.0f / sqrtf(dot3(t1, t1));
+#pragma unroll
+        for (int k = 0; k < 3; k++) t1[k] *= inv;
+        cross3(n, t1, t2);
+        float rv[3], vc[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) rv[k] = xc[k] - s.o[sb][k];
+        cross3(s.w[sb], rv, vc);
+        const float vn0 = dot3(n, s.vo[sb]) + dot3(n, vc);
+        float target;
+        if (dist > 0) target = -dist / dt;
+        else { target = -dist * cfg.erp / dt; if (target > cfg.max_depen_vel) target = cfg.max_depen_vel; }
+        if (vn0 < -cfg.bounce_threshold && -rest * vn0 > target) target = -rest * vn0;
+#pragma unroll
+        for (int k = 0; k < 3; k++) { s.cfr[rank][k] = n[k]; s.cfr[rank][3 + k] = t1[k]; s.cfr[rank][6 + k] = t2[k]; s.cpt[rank][k] = xc[k]; }
+        s.cpt[rank][3] = target;
+        s.cbody[rank] = sb;
+        s.clink[rank] = m.sph_link[lane];
+    }
+    // ---- joint-limit rows (predicted with the pre-step rate): lane = joint
+    float lsgn = 0, ltgt = 0;
+    if (lane < ND) {
+        const float q = s.rec[R_DOFPOS + lane], qn = q + dt * s.rec[R_DOFVEL + lane];
+        if (qn < m.dof_lower[lane]) { lsgn = 1.f; ltgt = (m.dof_lower[lane] - q) / dt; }
+        else if (qn > m.dof_upper[lane]) { lsgn = -1.f; ltgt = (q - m.dof_upper[lane]) / dt; }
+    }
+    const unsigned lbal = __ballot_sync(FULL, lsgn != 0.f);
+    const int lrank = __popc(lbal & ((1u << lane) - 1u));
+    const int nlim = min(__popc(lbal), KLIM);
+    if (lsgn != 0.f && lrank < KLIM) { s.limj[lrank] = lane; s.lims[lrank] = lsgn; s.limt[lrank] = ltgt; }
+    __syncwarp();
+    const int nrow = 3 * nc + nlim;  // <= 32
+    // ---- build row lane's Jacobian, solve Y = M^-1 J^T ; lane 31 (if free) solves the unconstrained update
+    float J[NV], x[NV], bias = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; i++) J[i] = 0.f;
+    if (lane < 3 * nc) {
+        const int c = lane / 3, k = lane % 3, b = s.cbody[c];
+        const float *dir = s.cfr[c] + 3 * k, *xc = s.cpt[c];
+        const int leg = (b - 1) / CH, depth = b == 0 ? 0 : (b - 1) % CH + 1;
+#pragma unroll
+        for (int jj = 0; jj < ND; jj++) {
+            const bool on = b > 0 && (jj / CH) == leg && (jj % CH) < depth;
+            float r[3], t[3];
+#pragma unroll
+            for (int i = 0; i < 3; i++) r[i] = xc[i] - s.o[jj + 1][i];
+            cross3(s.a[jj + 1], r, t);
+            J[jj] = on ? dot3(t, dir) : 0.f;
+        }
+        float r[3], t[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) r[i] = xc[i] - s.o[0][i];
+        cross3(r, dir, t);
+#pragma unroll
+        for (int i = 0; i < 3; i++) { J[ND + i] = dir[i]; J[ND + 3 + i] = t[i]; }
+        bias = k == 0 ? xc[3] : 0.f;
+    } else if (lane < nrow) {
+        const int l = lane - 3 * nc, j = s.limj[l];
+        const float sg = s.lims[l];
+#pragma unroll
+        for (int jj = 0; jj < ND; jj++) J[jj] = jj == j ? sg : 0.f;
+        bias = s.limt[l];
+    }
+    const bool rhs_lane = lane == 31 && nrow < 32;
+#pragma unroll
+    for (int i = 0; i < NV; i++) x[i] = rhs_lane ? ((i < ND ? s.tau[i] : 0.f) - s.h[i]) : J[i];
+    chol_solve(s, x);
+    if (lane < nrow) {
+        float arr = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; i++) { s.Y[lane][i] = x[i]; arr += J[i] * x[i]; }
+        s.rowc[lane][0] = 1.0f / arr;
+        s.rowc[lane][1] = bias;
+    }
+    const float *rs = s.rec + R_ROOT;
+    if (rhs_lane) {
+#pragma unroll
+        for (int i = 0; i < NV; i++) s.u[i] = (i < ND ? s.rec[R_DOFVEL + i] : rs[7 + i - ND]) + dt * x[i];
+    }
+    if (nrow == 32) {  // all 32 lanes hold rows: second pass for the unconstrained update (warp-uniform branch)
+#pragma unroll
+        for (int i = 0; i < NV; i++) x[i] = (i < ND ? s.tau[i] : 0.f) - s.h[i];
+        chol_solve(s, x);
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < NV; i++) s.u[i] = (i < ND ? s.rec[R_DOFVEL + i] : rs[7 + i - ND]) + dt * x[i];
+        }
+    }
+    __syncwarp();
+    // ---- Delassus row A[lane][.] = J_lane . Y_s, and the constraint-space velocity w = J u*
+    float Arow[32], lam[32];
+    float wv = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; i++) wv += J[i] * s.u[i];
+#pragma unroll
+    for (int r = 0; r < 32; r++) {
+        lam[r] = 0.f;
+        float acc = 0.f;
+        if (r < nrow) {
+#pragma unroll
+            for (int i = 0; i < NV; i++) acc += J[i] * s.Y[r][i];
+        }
+        Arow[r] = acc;
+    }
+    // ---- projected Gauss-Seidel in constraint space; every lane tracks all multipliers (warp-uniform values)
+    for (int it = 0; it < cfg.solver_iters; it++) {
+#pragma unroll
+        for (int r = 0; r < 32; r++) {
+            if (r < nrow) {
+                const float wr = __shfl_sync(FULL, wv, r);
+                const float l0 = lam[r];
+                float ln = l0 - (wr - s.rowc[r][1]) * s.rowc[r][0];
+                if (r < 3 * nc && (r % 3) != 0) {
+                    const float lim = mu * lam[r - (r % 3)];
+                    ln = fminf(fmaxf(ln, -lim), lim);
+                } else {
+                    ln = fmaxf(ln, 0.f);
+                }
+                const float d = ln - l0;
+                lam[r] = ln;
+                wv += Arow[r] * d;
+            }
+        }
+    }
+    // ---- u = u* + sum_r Y_r lam_r ; own multiplier for the force report
+    float mylam = 0.f;
+#pragma unroll
+    for (int r = 0; r < 32; r++) if (r == lane) mylam = lam[r];
+    float unew = 0.f;
+    if (lane < NV) {
+        unew = s.u[lane];
+#pragma unroll
+        for (int r = 0; r < 32; r++) if (r < nrow) unew += s.Y[r][lane] * lam[r];
+    }
+    for (int i = lane; i < m.nl * 3; i += 32) s.cf[i] = 0.f;
+    __syncwarp();
+    {   // net contact force per URDF link (world frame, on the body) = impulse / dt
+        const float l0 = __shfl_sync(FULL, mylam, min(3 * lane, 31)), l1 = __shfl_sync(FULL, mylam, min(3 * lane + 1, 31)),
+                    l2 = __shfl_sync(FULL, mylam, min(3 * lane + 2, 31));
+        if (lane < nc) {
+            const float *f = s.cfr[lane];
+            const int link = s.clink[lane];
+#pragma unroll
+            for (int k = 0; k < 3; k++) atomicAdd(&s.cf[3 * link + k], (f[k] * l0 + f[3 + k] * l1 + f[6 + k] * l2) / dt);
+        }
+    }
+    // ---- joint-rate limit + integrate
+    if (lane < ND) {
+        const float vl = m.dof_vel_limit[lane];
+        const float v = fminf(fmaxf(unew, -vl), vl);
+        s.rec[R_DOFVEL + lane] = v;
+        s.rec[R_DOFPOS + lane] += dt * v;
+    } else if (lane < NV) {
+        s.rec[R_ROOT + 7 + lane - ND] = unew;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        float *rt = s.rec + R_ROOT;
+#pragma unroll
+        for (int k = 0; k < 3; k++) rt[k] += dt * rt[7 + k];
+        const float wx = rt[10], wy = rt[11], wz = rt[12];
+        const float wn = sqrtf(wx * wx + wy * wy + wz * wz), th = wn * dt;
+        float sn, cs;
+        sincosf(0.5f * th, &sn, &cs);
+        const float sc = wn > 1e-9f ? sn / wn : 0.5f * dt;
+        const float dq[4] = {wx * sc, wy * sc, wz * sc, cs};
+        float *p = rt + 3;
+        const float qx = dq[3] * p[0] + dq[0] * p[3] + dq[1] * p[2] - dq[2] * p[1];
+        const float qy = dq[3] * p[1] - dq[0] * p[2] + dq[1] * p[3] + dq[2] * p[0];
+        const float qz = dq[3] * p[2] + dq[0] * p[1] - dq[1] * p[0] + dq[2] * p[3];
+        const float qw = dq[3] * p[3] - dq[0] * p[0] - dq[1] * p[1] - dq[2] * p[2];
+        const float nn = 1.0f / sqrtf(qx * qx + qy * qy + qz * qz + qw * qw);
+        p[0] = qx * nn; p[1] = qy * nn; p[2] = qz * nn; p[3] = qw * nn;
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void resample_commands(WS &s, const grx_task_cfg &cfg, const Draw &draw, int base) {
+    // legged_robot.py:650-677 ((upper - lower) * u + lower; small xy commands zeroed)
+    float cx = (cfg.cmd_range[0][1] - cfg.cmd_range[0][0]) * draw(base) + cfg.cmd_range[0][0];
+    float cy = (cfg.cmd_range[1][1] - cfg.cmd_range[1][0]) * draw(base + 1) + cfg.cmd_range[1][0];
+    const float keep = sqrtf(cx * cx + cy * cy) > 0.1f ? 1.f : 0.f;
+    s.rec[R_CMD] = cx * keep;
+    s.rec[R_CMD + 1] = cy * keep;
+    s.rec[R_CMD + 2] = (cfg.cmd_range[2][1] - cfg.cmd_range[2][0]) * draw(base + 2) + cfg.cmd_range[2][0];
+}
+
+template <bool PHYS>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) env_step_kernel(const __grid_constant__ EnvArgs A,
+                                                                         const __grid_constant__ grx_task_cfg cfg) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ModelDev &m = *reinterpret_cast<ModelDev *>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WS &s = *reinterpret_cast<WS *>(smem_raw + ((sizeof(ModelDev) + 15) & ~15) + (size_t)warp * sizeof(WS));
+    const int e = blockIdx.x * WARPS_PER_CTA + warp;
+    {   // model tables -> shared memory (divergent per-body indexing would serialise on the constant bank)
+        const int4 *src = reinterpret_cast<const int4 *>(A.model);
+        int4 *dst = reinterpret_cast<int4 *>(&m);
+        for (int i = threadIdx.x; i < (int)(sizeof(ModelDev) / 16); i += blockDim.x) dst[i] = src[i];
+    }
+    const bool valid = e < A.N;
+    if (valid) {
+        if (lane == 0) {
+            mbar_init(&s.mbar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        if (lane == 0) {   // stage this robot's state + parameter records with TMA bulk copies
+            mbar_expect_tx(&s.mbar, (REC_F + CST_F) * 4);
+            bulk_g2s(s.rec, A.rec + (size_t)e * REC_F, REC_F * 4, &s.mbar);
+            bulk_g2s(s.cst, A.cst + (size_t)e * CST_F, CST_F * 4, &s.mbar);
+        }
+    }
+    __syncthreads();  // model copy visible
+    if (!valid) return;
+    mbar_wait(&s.mbar, 0);
+
+    const int nd = ND;
+    Draw draw;
+    draw.U = A.U ? A.U + (size_t)e * GRX_RNG_K : nullptr;
+    draw.k0 = (uint32_t)cfg.seed; draw.k1 = (uint32_t)(cfg.seed >> 32);
+    draw.gid = (uint32_t)(cfg.env_id_offset + e);
+    draw.step_lo = (uint32_t)A.step_index; draw.step_hi = (uint32_t)(A.step_index >> 32);
+
+    // ---- clip_actions (legged_robot_fftai.py:171-177)
+    float act_l = 0.f, last_act_l = 0.f;
+    if (lane < nd) {
+        act_l = fminf(fmaxf(A.actions[(size_t)e * nd + lane], cfg.clip_actions_min[lane]), cfg.clip_actions_max[lane]);
+        last_act_l = s.rec[R_LASTACT + lane];
+    }
+    float ff_acc = 0.f, fl_acc[3] = {0, 0, 0};  // lane f < NF: substep sums of |F_foot|, |v_foot| (FF:79-81)
+    float foot_z = 0.f;
+    float torso_q[4] = {0, 0, 0, 1};
+    if (PHYS) {
+        kinematics(s, m, lane);
+        for (int deci = 0; deci < cfg.decimation; deci++) {
+            if (lane < nd) {   // _compute_torques (legged_robot.py:691-713) with the action delay of FF:58-61
+                const float a = ((float)deci < A.delay) ? last_act_l : act_l;
+                float t = m.kp[lane] * (a * cfg.action_scale + m.q0[lane] - s.rec[R_DOFPOS + lane]) - m.kd[lane] * s.rec[R_DOFVEL + lane];
+                t *= s.cst[C_MOTOR + lane];
+                const float lim = m.dof_effort[lane];
+                s.tau[lane] = fminf(fmaxf(t, -lim), lim);
+            }
+            __syncwarp();
+            substep(s, m, A, cfg, lane);
+            kinematics(s, m, lane);
+            if (lane < NF) {
+                const int l = m.foot_link[lane], b = m.foot_body[lane];
+                float r[3], t[3];
+                m3v(s.R[b], m.foot_pos[lane], r);
+                cross3(s.w[b], r, t);
+                const float *f = s.cf + 3 * l;
+                ff_acc += sqrtf(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]);
+#pragma unroll
+                for (int k = 0; k < 3; k++) fl_acc[k] += fabsf(s.vo[b][k] + t[k]);
+                foot_z = s.o[b][2] + r[2];
+            }
+        }
+        if (A.dbg_M != nullptr) return;
+        const float invd = 1.0f / (float)cfg.decimation;
+        ff_acc *= invd;
+#pragma unroll
+        for (int k = 0; k < 3; k++) fl_acc[k] *= invd;
+        float Rt[9];
+        m3m(s.R[m.torso_body], m.torso_rot, Rt);
+        mat2quat(Rt, torso_q);
+        if (A.foot_state != nullptr && lane < NF) {   // compat export: feet link states (play.py / tests)
+            float *fs = A.foot_state + ((size_t)e * NF + lane) * 13;
+            const int b = m.foot_body[lane];
+            float r[3], t[3], Rf[9], qf[4];
+            m3v(s.R[b], m.foot_pos[lane], r);
+            cross3(s.w[b], r, t);
+            m3m(s.R[b], m.torso_rot, Rf);   // foot links share their body's frame up to the link rotation (identity for GRx)
+            mat2quat(s.R[b], qf);
+#pragma unroll
+            for (int k = 0; k < 3; k++) { fs[k] = s.o[b][k] + r[k]; fs[7 + k] = s.vo[b][k] + t[k]; fs[10 + k] = s.w[b][k]; }
+#pragma unroll
+            for (int k = 0; k < 4; k++) fs[3 + k] = qf[k];
+        }
+    } else {
+        // injected physics outputs (grx_env_post_physics)
+        if (lane < nd) s.tau[lane] = A.inj.torques[(size_t)e * nd + lane];
+        for (int i = lane; i < m.nl * 3; i += 32) s.cf[i] = A.inj.contact_forces[(size_t)e * m.nl * 3 + i];
+        if (lane < NF) {
+            foot_z = A.inj.foot_state[((size_t)e * NF + lane) * 13 + 2];
+            ff_acc = A.inj.avg_foot_force[(size_t)e * NF + lane];
+#pragma unroll
+            for (int k = 0; k < 3; k++) fl_acc[k] = A.inj.avg_foot_linvel[((size_t)e * NF + lane) * 3 + k];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) torso_q[k] = A.inj.torso_quat[(size_t)e * 4 + k];
+        __syncwarp();
+    }
+
+    // =====================================================================================================
+    // post_physics_step (legged_robot.py:269-305, legged_robot_fftai.py:90-133)
+    // =====================================================================================================
+    const float dtp = (float)cfg.decimation * cfg.sim_dt;
+    float *rec = s.rec;
+    int ep_len = __float_as_int(rec[R_EPLEN]) + 1;                                   // LR:282
+    float base_quat[4], v_b[3], w_b[3], g_b[3];
+    const float gvec[3] = {0.f, 0.f, -1.f};
+#pragma unroll
+    for (int k = 0; k < 4; k++) base_quat[k] = rec[R_ROOT + 3 + k];
+    quat_rotate_inverse(base_quat, rec + R_ROOT + 7, v_b);                           // LR:309-311
+    quat_rotate_inverse(base_quat, rec + R_ROOT + 10, w_b);
+    quat_rotate_inverse(base_quat, gvec, g_b);
+    const float root_pos[3] = {rec[R_ROOT], rec[R_ROOT + 1], rec[R_ROOT + 2]};
+    __syncwarp();
+    if (ep_len % cfg.resample_interval == 0) {                                        // LR:317-318
+        if (lane == 0) resample_commands(s, cfg, draw, U_CMD_TIME);
+    }
+    __syncwarp();
+    // ---- _get_heights (legged_robot.py:1235-1274): trunc-to-int grid index, min of 3 samples
+    float *mh = &s.Y[0][0];   // [num_height_points]
+    const int H = cfg.num_height_points;
+    if (cfg.measure_heights && A.terrain.type != 0) {
+        float qz = base_quat[2], qw = base_quat[3];
+        const float nrm = fmaxf(sqrtf(qz * qz + qw * qw), 1e-9f);
+        qz /= nrm; qw /= nrm;
+        for (int k = lane; k < H; k += 32) {
+            const float px_ = cfg.measured_points_x[k / cfg.n_points_y], py_ = cfg.measured_points_y[k % cfg.n_points_y];
+            // quat_apply with q = (0, 0, qz, qw), b = (px, py, 0): t = 2 * cross(xyz, b); out = b + w t + cross(xyz, t)
+            const float tx = -qz * py_ * 2.f, ty = qz * px_ * 2.f;
+            const float ox = px_ + qw * tx + (-qz * ty), oy = py_ + qw * ty + (qz * tx);
+            float fx = ox + root_pos[0], fy = oy + root_pos[1];
+            fx += A.terrain.border; fy += A.terrain.border;
+            long long ix = (long long)(fx / A.terrain.hscale), iy = (long long)(fy / A.terrain.hscale);
+            ix = min(max(ix, 0LL), (long long)A.terrain.rows - 2);
+            iy = min(max(iy, 0LL), (long long)A.terrain.cols - 2);
+            const short *p = A.terrain.h + (size_t)ix * A.terrain.cols + iy;
+            const short h1 = __ldg(p), h2 = __ldg(p + A.terrain.cols), h3 = __ldg(p + 1);
+            const short hm = min(min(h1, h2), h3);
+            mh[k] = (float)hm * A.terrain.vscale;
+        }
+    } else {
+        for (int k = lane; k < H; k += 32) mh[k] = 0.f;
+    }
+    __syncwarp();
+    if (A.push && lane < 2) {                                                         // LR:333-334, 786-797
+        const float mv = cfg.max_push_vel_xy;
+        rec[R_ROOT + 7 + lane] = (mv - -mv) * draw(U_PUSH + lane) + -mv;
+    }
+    // ---- feet bookkeeping (FF:108-133): lane f < NF owns foot f
+    bool contact = false, filt = false, first = false;
+    float air = 0.f, land = 0.f, fh_sum = 0.f, fxy = 0.f, fz = 0.f;
+    {
+        // sum_k (foot_z - mh[k]) for both feet, and sum_k clip(z - target - mh[k]) for the base: lanes stride over k
+        const float fz0 = __shfl_sync(FULL, foot_z, 0), fz1 = __shfl_sync(FULL, foot_z, 1);
+        float s0 = 0.f, s1 = 0.f;
+        for (int k = lane; k < H; k += 32) { s0 += fz0 - mh[k]; s1 += fz1 - mh[k]; }
+        s0 = warp_sum(s0); s1 = warp_sum(s1);
+        fh_sum = lane == 0 ? s0 : s1;
+    }
+    const float feet_h = fh_sum / (float)H;   // valid on lanes 0,1
+    if (lane < NF) {
+        const float *f = s.cf + 3 * m.foot_link[lane];
+        fz = f[2];
+        fxy = sqrtf(f[0] * f[0] + f[1] * f[1]);
+        contact = fz > 1.0f;
+        const bool lastc = rec[R_CLAST + lane] != 0.f;
+        filt = contact || lastc;
+        air = rec[R_AIR + lane];
+        first = (air > 0.f) && filt;
+        air += dtp;
+        land = (rec[R_LAND + lane] + dtp) * (contact ? 1.f : 0.f);
+    }
+    // ---- check_termination (LR:336-353)
+    bool term = false;
+    for (int l = lane; l < m.nl; l += 32) {
+        if ((m.term_mask >> l) & 1ull) {
+            const float *f = s.cf + 3 * l;
+            term |= sqrtf(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]) > 1.0f;
+        }
+    }
+    bool reset = __any_sync(FULL, term);
+    reset |= fabsf(g_b[2]) < 0.33f;
+    const bool time_out = (float)ep_len > cfg.max_episode_length;
+    reset |= time_out;
+
+    // ---- compute_reward (LR:355-375): per-DOF sums by warp reduction, then the 24 terms
+    float sa = 0, sadd = 0, sacc = 0, stor = 0, spose = 0, slpos = 0, slvel = 0, sltor = 0;
+    float q_l = 0, qd_l = 0, tau_l = 0;
+    if (lane < nd) {
+        q_l = rec[R_DOFPOS + lane]; qd_l = rec[R_DOFVEL + lane]; tau_l = s.tau[lane];
+        const float la = last_act_l, lla = rec[R_LASTLASTACT + lane], asc = cfg.action_scale;
+        const float e1 = (la - act_l) * asc, e0 = (lla - la) * asc;
+        sa = fabsf(e1);
+        sadd = fabsf(e1 - e0);
+        sacc = fabsf((qd_l - rec[R_LASTDOFVEL + lane]) / dtp);
+        stor = fabsf(tau_l);
+        spose = fabsf(q_l - m.q0[lane]);
+        float ool = -fminf(q_l - m.soft_lower[lane], 0.f);
+        ool += fmaxf(q_l - m.soft_upper[lane], 0.f);
+        slpos = fabsf(ool);
+        slvel = fminf(fmaxf(fabsf(qd_l) - m.dof_vel_limit[lane] * cfg.soft_dof_vel_limit, 0.f), 1.f);
+        sltor = fmaxf(fabsf(tau_l) - m.dof_effort[lane] * cfg.soft_torque_limit, 0.f);
+    }
+    sa = warp_sum(sa); sadd = warp_sum(sadd); sacc = warp_sum(sacc); stor = warp_sum(stor);
+    spose = warp_sum(spose); slpos = warp_sum(slpos); slvel = warp_sum(slvel); sltor = warp_sum(sltor);
+    // foot quantities broadcast to every lane
+    const float lfh = __shfl_sync(FULL, feet_h, 0), rfh = __shfl_sync(FULL, feet_h, 1);
+    const float air0 = __shfl_sync(FULL, air, 0), air1 = __shfl_sync(FULL, air, 1);
+    const float land0 = __shfl_sync(FULL, land, 0), land1 = __shfl_sync(FULL, land, 1);
+    const float ff0 = __shfl_sync(FULL, ff_acc, 0), ff1 = __shfl_sync(FULL, ff_acc, 1);
+    const float vx0 = __shfl_sync(FULL, fl_acc[0], 0), vy0 = __shfl_sync(FULL, fl_acc[1], 0);
+    const float vx1 = __shfl_sync(FULL, fl_acc[0], 1), vy1 = __shfl_sync(FULL, fl_acc[1], 1);
+    const float fxy0 = __shfl_sync(FULL, fxy, 0), fxy1 = __shfl_sync(FULL, fxy, 1);
+    const float fz0 = __shfl_sync(FULL, fz, 0), fz1 = __shfl_sync(FULL, fz, 1);
+    const unsigned cbal = __ballot_sync(FULL, contact), fbal = __ballot_sync(FULL, first);
+    const float tau_a0 = fabsf(s.tau[m.ankle_dof[0]]), tau_a1 = fabsf(s.tau[m.ankle_dof[1]]);
+    const float cmdx = rec[R_CMD], cmdy = rec[R_CMD + 1], cmdw = rec[R_CMD + 2];
+    const float cnorm = sqrtf(cmdx * cmdx + cmdy * cmdy);
+    const float nz = cnorm > 0.1f ? 1.f : 0.f;
+    float rew = 0.f;
+    if (lane == 0) {
+        float r[NREW];
+        const float bh = rec[R_BHO];   // one step stale on purpose
+        float tg[3];
+        quat_rotate_inverse(torso_q, gvec, tg);
+        const float tgt = cfg.swing_feet_height_target, q4 = tgt / 4.f;
+        const float mid0 = fabsf(air0 - cfg.feet_air_time_target / 2.f), mid1 = fabsf(air1 - cfg.feet_air_time_target / 2.f);
+        const float mn = fminf(lfh, rfh);
+        r[0] = 1.f - expf(cfg.sigma_action_diff * sa);                                                    // action_diff
+        r[1] = 1.f - expf(cfg.sigma_action_diff_diff * sadd);                                             // action_diff_diff
+        r[2] = expf(cfg.sigma_cmd_diff_ang_vel_yaw * fabsf(cmdw - w_b[2]));                               // cmd_diff_ang_vel_yaw
+        r[3] = expf(cfg.sigma_cmd_diff_base_height * (fabsf(bh) * (bh < 0.f ? 1.f : 0.f)));               // cmd_diff_base_height
+        r[4] = expf(cfg.sigma_cmd_diff_base_orient * (fabsf(g_b[0]) + fabsf(g_b[1])));                    // cmd_diff_base_orient
+        r[5] = expf(cfg.sigma_cmd_diff_lin_vel_x * fabsf(cmdx - v_b[0]));                                 // cmd_diff_lin_vel_x
+        r[6] = expf(cfg.sigma_cmd_diff_lin_vel_y * fabsf(cmdy - v_b[1]));                                 // cmd_diff_lin_vel_y
+        r[7] = expf(cfg.sigma_cmd_diff_lin_vel_z * fabsf(0.f - v_b[2]));                                  // cmd_diff_lin_vel_z
+        r[8] = expf(cfg.sigma_cmd_diff_torso_orient * (fabsf(tg[0]) + fabsf(tg[1])));                     // cmd_diff_torso_orient
+        r[9] = 1.f - expf(cfg.sigma_dof_acc_new * sacc);                                                  // dof_acc_new
+        {
+            const float el = tau_a0 * fabsf(lfh) * (lfh > tgt / 2.f ? 1.f : 0.f);
+            const float er = tau_a1 * fabsf(rfh) * (rfh > tgt / 2.f ? 1.f : 0.f);
+            r[10] = 1.f - expf(cfg.sigma_dof_tor_ankle_feet_lift_up * (el + er));                         // dof_tor_ankle_feet_lift_up
+        }
+        r[11] = 1.f - expf(cfg.sigma_dof_tor_new * stor);                                                 // dof_tor_new
+        r[12] = expf(cfg.sigma_feet_air_force * (mid0 * ff0 + mid1 * ff1)) * nz;                          // feet_air_force
+        r[13] = expf(cfg.sigma_feet_air_height * (mid0 * fabsf(lfh - mn - tgt) + mid1 * fabsf(rfh - mn - tgt))) * nz;  // feet_air_height
+        r[14] = (expf(cfg.sigma_feet_air_time * fabsf(air0 - cfg.feet_air_time_target)) * ((fbal & 1u) ? 1.f : 0.f) +
+                 expf(cfg.sigma_feet_air_time * fabsf(air1 - cfg.feet_air_time_target)) * ((fbal & 2u) ? 1.f : 0.f)) * nz;  // feet_air_time
+        {
+            const float e0 = (land0 - cfg.feet_land_time_max) * (land0 > cfg.feet_land_time_max ? 1.f : 0.f);
+            const float e1 = (land1 - cfg.feet_land_time_max) * (land1 > cfg.feet_land_time_max ? 1.f : 0.f);
+            r[15] = ((1.f - expf(cfg.sigma_feet_land_time * e0)) + (1.f - expf(cfg.sigma_feet_land_time * e1))) * nz;  // feet_land_time
+        }
+        {
+            const float cl = fabsf(lfh - q4) * (lfh < q4 ? 1.f : 0.f) / q4, cr = fabsf(rfh - q4) * (rfh < q4 ? 1.f : 0.f) / q4;
+            const float e_ = sqrtf(vx0 * vx0 + vy0 * vy0) * cl + sqrtf(vx1 * vx1 + vy1 * vy1) * cr;
+            r[16] = expf(cfg.sigma_feet_speed_xy_close_to_ground * e_);                                   // feet_speed_xy_close_to_ground
+        }
+        {
+            float el = fxy0 - cfg.feet_stumble_ratio * fabsf(fz0), er = fxy1 - cfg.feet_stumble_ratio * fabsf(fz1);
+            el = el * (el > 0.f ? 1.f : 0.f); er = er * (er > 0.f ? 1.f : 0.f);
+            r[17] = (1.f - expf(cfg.sigma_feet_stumble * el)) + (1.f - expf(cfg.sigma_feet_stumble * er));  // feet_stumble
+        }
+        r[18] = 1.f - expf(cfg.sigma_limits_dof_pos * slpos);                                             // limits_dof_pos
+        r[19] = 1.f - expf(cfg.sigma_limits_dof_tor * sltor);                                             // limits_dof_tor
+        r[20] = 1.f - expf(cfg.sigma_limits_dof_vel * slvel);                                             // limits_dof_vel
+        r[21] = (cbal & 3u) == 0u ? 1.f : 0.f;                                                            // on_the_air
+        r[22] = expf(cfg.sigma_pose_offset * spose);                                                      // pose_offset
+        r[23] = expf(cfg.sigma_stand_still * spose) * (cnorm < 0.1f ? 1.f : 0.f);                         // stand_still
+#pragma unroll
+        for (int k = 0; k < NREW; k++) {
+            const float v = r[k] * cfg.reward_scale[k];
+            rew += v;                   // alphabetical summation order (App. B-15)
+            s.rterm[k] = v;
+        }
+    }
+    __syncwarp();
+    if (lane < NREW) rec[R_SUMS + lane] += s.rterm[lane];                             // LR:366
+    __syncwarp();
+
+    // ---- reset_idx (LR:377-440, FF:137-146), curriculum (LR:799-826)
+    bool contact_for_obs = contact;
+    if (reset) {
+        if (cfg.curriculum) {
+            if (lane == 0) {
+                const float dx = rec[R_ROOT] - rec[R_ORIGIN], dy = rec[R_ROOT + 1] - rec[R_ORIGIN + 1];
+                const float distance = sqrtf(dx * dx + dy * dy);
+                const bool up = distance > cfg.terrain_env_length / 2.f;
+                const bool down = (distance < cnorm * cfg.max_episode_length_s * 0.5f) && !up;
+                int level = __float_as_int(rec[R_TLEVEL]) + (up ? 1 : 0) - (down ? 1 : 0);
+                if (level >= A.t_rows) level = min((int)floorf(draw(U_CURRICULUM) * (float)A.t_rows), A.t_rows - 1);
+                else level = max(level, 0);
+                rec[R_TLEVEL] = __int_as_float(level);
+                const int type = __float_as_int(rec[R_TTYPE]);
+                const float *org = A.terrain_origins + ((size_t)level * A.t_cols + type) * 3;
+                rec[R_ORIGIN] = org[0]; rec[R_ORIGIN + 1] = org[1]; rec[R_ORIGIN + 2] = org[2];
+            }
+            __syncwarp();
+        }
+        if (lane < nd) {                                                              // _reset_dofs LR:717-734
+            rec[R_DOFPOS + lane] = cfg.randomize_init_dof_pos ? ((1.5f - 0.5f) * draw(U_RESET_DOF + lane) + 0.5f) * m.q0[lane] : m.q0[lane];
+            rec[R_DOFVEL + lane] = 0.f;
+            rec[R_LASTACT + lane] = 0.f;
+            rec[R_LASTDOFVEL + lane] = 0.f;
+            rec[R_LASTLASTACT + lane] = 0.f;
+        }
+        if (lane == 0) {                                                              // _reset_root_states LR:742-779
+            float *rt = rec + R_ROOT;
+#pragma unroll
+            for (int k = 0; k < 13; k++) rt[k] = cfg.base_init_state[k];
+#pragma unroll
+            for (int k = 0; k < 3; k++) rt[k] += rec[R_ORIGIN + k];
+            if (cfg.custom_origins) {
+                rt[0] += (1.0f - -1.0f) * draw(U_RESET_XY) + -1.0f;
+                rt[1] += (1.0f - -1.0f) * draw(U_RESET_XY + 1) + -1.0f;
+            }
+            const float yaw = 12.566370614359172f * draw(U_RESET_YAW) + -6.283185307179586f;
+            float sy, cy;
+            sincosf(yaw * 0.5f, &sy, &cy);
+            rt[3] = 0.f; rt[4] = 0.f; rt[5] = sy; rt[6] = cy;
+            if (cfg.randomize_init_base_velocity) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) rt[7 + k] = (0.5f - -0.5f) * draw(U_RESET_VEL + k) + -0.5f;
+            }
+            resample_commands(s, cfg, draw, U_CMD_RESET);                             // LR:402
+            ep_len = 0;
+        }
+        ep_len = __shfl_sync(FULL, ep_len, 0);
+        if (lane < NF) { air = 0.f; land = 0.f; contact_for_obs = false; }
+        if (lane < NREW) {                                                            // extras["episode"] sums LR:420-424
+            atomicAdd(A.episode_accum + lane, rec[R_SUMS + lane]);
+            rec[R_SUMS + lane] = 0.f;
+        }
+        if (lane == NREW) atomicAdd(A.episode_accum + NREW, 1.0f);
+    }
+    __syncwarp();
+
+    // ---- compute_observations (LR:442-452, FF:148-167, G1:281-313) — after the reset, with stale base quantities (App. B-2)
+    const float hm = cfg.obs_scale_height;
+    const float z_new = rec[R_ROOT + 2];
+    float bsum = 0.f;
+    float *pri = s.pri;
+    const int O = cfg.num_obs;
+    for (int k = lane; k < H; k += 32) {
+        const float off = fminf(fmaxf(z_new - cfg.base_height_target - mh[k], -1.f), 1.f) * hm;
+        bsum += off;
+        pri[O + 8 + k] = off * hm;                                                    // surround_heights_offset * 5 (x25 net, App. B-7)
+    }
+    bsum = warp_sum(bsum);
+    const float bho = bsum / (float)H;
+    float *ob = &s.Y[0][0] + NHMAX;   // unclipped, noise-free obs staging [num_obs]
+    if (lane < 3) {
+        ob[lane] = rec[R_CMD + lane] * 1.0f;                                         // commands * commands_scale (ones, G1:125)
+        ob[3 + lane] = w_b[lane] * cfg.obs_scale_ang_vel;
+        ob[6 + lane] = g_b[lane] * cfg.obs_scale_gravity;
+    }
+    if (lane < nd) {
+        ob[9 + lane] = (rec[R_DOFPOS + lane] - m.q0[lane]) * cfg.obs_scale_dof_pos;
+        ob[9 + nd + lane] = rec[R_DOFVEL + lane] * cfg.obs_scale_dof_vel;
+        ob[9 + 2 * nd + lane] = act_l * cfg.obs_scale_action;
+    }
+    __syncwarp();
+    const float co = cfg.clip_observations;
+    for (int i = lane; i < O; i += 32) {
+        const float v = ob[i];
+        pri[i] = fminf(fmaxf(v, -co), co);                                            // privileged obs embeds the noise-free obs
+        float vn = v;
+        if (cfg.add_noise) vn += (2.f * draw(U_NOISE + i) - 1.f) * cfg.noise_scale_vec[i];   // LR:478-481
+        A.obs[(size_t)e * O + i] = fminf(fmaxf(vn, -co), co);                        // LR:240-241
+    }
+    if (lane < 3) pri[O + lane] = fminf(fmaxf(v_b[lane] * cfg.obs_scale_lin_vel, -co), co);
+    if (lane == 3) pri[O + 3] = fminf(fmaxf(bho * hm, -co), co);
+    if (lane < NF) {
+        pri[O + 4 + lane] = contact_for_obs ? 1.f : 0.f;
+        pri[O + 6 + lane] = fminf(fmaxf(feet_h * hm, -co), co);
+    }
+    __syncwarp();
+    for (int k = lane; k < H; k += 32) pri[O + 8 + k] = fminf(fmaxf(pri[O + 8 + k], -co), co);
+
+    // ---- carry-over (LR:299-300, FF:94-97) and outputs
+    if (lane < nd) {
+        rec[R_LASTACT + lane] = act_l;
+        rec[R_LASTLASTACT + lane] = act_l;                                            // == last_actions (App. B-1)
+        rec[R_LASTDOFVEL + lane] = rec[R_DOFVEL + lane];
+        A.torques[(size_t)e * nd + lane] = s.tau[lane];
+    }
+    if (lane < NF) {
+        rec[R_AIR + lane] = air * (filt ? 0.f : 1.f);
+        rec[R_LAND + lane] = land;
+        rec[R_CLAST + lane] = contact_for_obs ? 1.f : 0.f;
+    }
+    if (lane == 0) {
+        rec[R_BHO] = bho;
+        rec[R_EPLEN] = __int_as_float(ep_len);
+        A.rew[e] = rew;
+        A.reset[e] = reset ? 1 : 0;
+        A.time_out[e] = time_out ? 1 : 0;
+    }
+    if (A.contact_forces != nullptr)
+        for (int i = lane; i < m.nl * 3; i += 32) A.contact_forces[(size_t)e * m.nl * 3 + i] = s.cf[i];
+    __syncwarp();
+    fence_async_smem();   // generic-proxy writes to smem -> visible to the bulk-copy (async) proxy
+    __syncwarp();
+    if (lane == 0) {
+        bulk_s2g(A.rec + (size_t)e * REC_F, s.rec, REC_F * 4);
+        bulk_s2g(A.pri_obs + (size_t)e * cfg.num_pri_obs, s.pri, (uint32_t)cfg.num_pri_obs * 4);
+        bulk_commit_wait();
+    }
+}
+
+}  // namespace
+
+// =========================================================================================================
+// Host side: C ABI (include/grx_b200.h)
+// =========================================================================================================
+static thread_local std::string g_err;
+extern "C" const char *grx_last_error(void) { return g_err.c_str(); }
+extern "C" int grx_version(void) { return 100; }
+int grx_set_error(int code, const std::string &msg) { g_err = msg; return code; }
+
+#define CK(call)                                                                                             \
+    do {                                                                                                     \
+        cudaError_t err__ = (call);                                                                          \
+        if (err__ != cudaSuccess)                                                                            \
+            return grx_set_error(GRX_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(err__));        \
+    } while (0)
+
+struct grx_env {
+    int N = 0, device = 0, nl = 0;
+    grx_task_cfg cfg;
+    ModelDev hmodel;
+    ModelDev *dmodel = nullptr;
+    float *rec = nullptr, *cst = nullptr, *obs = nullptr, *pri_obs = nullptr, *rew = nullptr, *torques = nullptr;
+    float *contact_forces = nullptr, *foot_state = nullptr, *episode_accum = nullptr, *terrain_origins = nullptr;
+    float *actions_stage = nullptr;
+    unsigned char *reset = nullptr, *time_out = nullptr;
+    short *heights = nullptr;
+    TerrainDev terrain;
+    int t_rows = 1, t_cols = 1;
+    bool params_set = false;
+    size_t smem = 0;
+};
+
+static size_t env_smem_bytes() { return ((sizeof(ModelDev) + 15) & ~(size_t)15) + WARPS_PER_CTA * sizeof(WS); }
+
+extern "C" int grx_env_create(const grx_model_desc *md, const grx_task_cfg *cfg, int32_t num_envs, int32_t device, grx_env **out) {
+    if (!md || !cfg || !out || num_envs <= 0) return grx_set_error(GRX_E_INVALID, "grx_env_create: null argument or num_envs <= 0");
+    static const int want_parent[NB] = {-1, 0, 1, 2, 3, 4, 0, 6, 7, 8, 9};
+    if (md->nb != NB || md->nd != ND || md->nf != NF || md->nankle != 2 || md->nl > NLMAX || md->ns > NSMAX)
+        return grx_set_error(GRX_E_INVALID, "grx_env_create: this build handles the lower-limb topology only (11 bodies, 10 DOF, 2 feet, <=40 links, <=32 contact spheres)");
+    for (int b = 0; b < NB; b++)
+        if (md->parent[b] != want_parent[b]) return grx_set_error(GRX_E_INVALID, "grx_env_create: unsupported kinematic tree (need floating base + 2 chains of 5)");
+    const int H = cfg->num_height_points;
+    if (cfg->num_actions != ND || cfg->num_obs != 9 + 3 * ND || H > NHMAX || cfg->num_pri_obs != cfg->num_obs + 8 + H ||
+        H != cfg->n_points_x * cfg->n_points_y || cfg->n_points_x > 16 || cfg->n_points_y > 16 || (cfg->num_pri_obs * 4) % 16 != 0)
+        return grx_set_error(GRX_E_INVALID, "grx_env_create: observation layout mismatch (need obs = 9+3*nd, pri_obs = obs+8+H, H <= 128)");
+    if (cfg->decimation < 1 || cfg->solver_iters < 1 || cfg->resample_interval < 1)
+        return grx_set_error(GRX_E_INVALID, "grx_env_create: decimation / solver_iters / resample_interval must be >= 1");
+    CK(cudaSetDevice(device));
+    grx_env *e = new grx_env();
+    e->N = num_envs; e->device = device; e->cfg = *cfg; e->nl = md->nl;
+    ModelDev &m = e->hmodel;
+    memset(&m, 0, sizeof(m));
+    for (int b = 0; b < NB; b++) {
+        memcpy(m.jpos[b], md->jpos + 3 * b, 12); memcpy(m.jrot[b], md->jrot + 9 * b, 36); memcpy(m.axis[b], md->axis + 3 * b, 12);
+        m.mass[b] = md->mass[b]; memcpy(m.com[b], md->com + 3 * b, 12); memcpy(m.inertia[b], md->inertia + 6 * b, 24);
+    }
+    for (int j = 0; j < ND; j++) {
+        m.dof_lower[j] = md->dof_lower[j]; m.dof_upper[j] = md->dof_upper[j]; m.dof_vel_limit[j] = md->dof_vel_limit[j];
+        m.dof_effort[j] = md->dof_effort[j]; m.soft_lower[j] = md->soft_lower[j]; m.soft_upper[j] = md->soft_upper[j];
+        m.kp[j] = md->kp[j]; m.kd[j] = md->kd[j]; m.q0[j] = md->default_pos[j];
+    }
+    m.ns = md->ns; m.nl = md->nl;
+    for (int s = 0; s < md->ns; s++) {
+        m.sph_body[s] = md->sph_body[s]; m.sph_link[s] = md->sph_link[s]; memcpy(m.sph_pos[s], md->sph_pos + 3 * s, 12);
+        m.sph_rad[s] = md->sph_rad[s];
+    }
+    for (int f = 0; f < NF; f++) {
+        const int l = md->foot_links[f];
+        m.foot_link[f] = l; m.foot_body[f] = md->link_body[l]; memcpy(m.foot_pos[f], md->link_pos + 3 * l, 12);
+    }
+    memcpy(m.torso_rot, md->link_rot + 9 * md->torso_link, 36);
+    m.torso_body = md->link_body[md->torso_link];
+    m.term_mask = 0;
+    for (int t = 0; t < md->nterm; t++) m.term_mask |= 1ull << md->term_links[t];
+    m.ankle_dof[0] = md->ankle_dofs[0]; m.ankle_dof[1] = md->ankle_dofs[1];
+    const size_t N = num_envs;
+#define ALLOC(ptr, count) CK(cudaMalloc((void **)&(ptr), (count))); CK(cudaMemset((ptr), 0, (count)))
+    ALLOC(e->dmodel, sizeof(ModelDev));
+    ALLOC(e->rec, N * REC_F * 4); ALLOC(e->cst, N * CST_F * 4);
+    ALLOC(e->obs, N * cfg->num_obs * 4); ALLOC(e->pri_obs, N * cfg->num_pri_obs * 4);
+    ALLOC(e->rew, N * 4); ALLOC(e->torques, N * ND * 4); ALLOC(e->contact_forces, N * md->nl * 3 * 4);
+    ALLOC(e->foot_state, N * NF * 13 * 4); ALLOC(e->episode_accum, 32 * 4); ALLOC(e->actions_stage, N * ND * 4);
+    ALLOC(e->reset, N); ALLOC(e->time_out, N);
+    ALLOC(e->terrain_origins, 3 * 4);
+#undef ALLOC
+    CK(cudaMemcpy(e->dmodel, &m, sizeof(ModelDev), cudaMemcpyHostToDevice));
+    {   // identity root quaternion
+        std::vector<float> h(N * REC_F, 0.f);
+        for (size_t i = 0; i < N; i++) h[i * REC_F + R_ROOT + 6] = 1.f;
+        CK(cudaMemcpy(e->rec, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+    }
+    e->terrain.type = 0; e->terrain.rows = e->terrain.cols = 0; e->terrain.h = nullptr;
+    e->terrain.hscale = 1.f; e->terrain.vscale = 1.f; e->terrain.border = 0.f; e->terrain.friction = 1.f; e->terrain.restitution = 0.f;
+    e->smem = env_smem_bytes();
+    CK(cudaFuncSetAttribute(env_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+    CK(cudaFuncSetAttribute(env_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+    *out = e;
+    return GRX_OK;
+}
+
+extern "C" int grx_env_destroy(grx_env *e) {
+    if (!e) return GRX_OK;
+    cudaSetDevice(e->device);
+    void *ptrs[] = {e->dmodel, e->rec, e->cst, e->obs, e->pri_obs, e->rew, e->torques, e->contact_forces, e->foot_state,
+                    e->episode_accum, e->terrain_origins, e->actions_stage, e->reset, e->time_out, e->heights};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    delete e;
+    return GRX_OK;
+}
+
+extern "C" int grx_env_set_terrain_plane(grx_env *e, float friction, float restitution) {
+    if (!e) return grx_set_error(GRX_E_INVALID, "null env");
+    e->terrain.type = 0; e->terrain.friction = friction; e->terrain.restitution = restitution;
+    return GRX_OK;
+}
+
+extern "C" int grx_env_set_terrain_heightfield(grx_env *e, const int16_t *samples, int32_t rows, int32_t cols, float hscale,
+                                               float vscale, float border, float friction, float restitution) {
+    if (!e || !samples || rows < 2 || cols < 2) return grx_set_error(GRX_E_INVALID, "grx_env_set_terrain_heightfield: bad arguments");
+    CK(cudaSetDevice(e->device));
+    if (e->heights) { cudaFree(e->heights); e->heights = nullptr; }
+    CK(cudaMalloc((void **)&e->heights, (size_t)rows * cols * 2));
+    CK(cudaMemcpy(e->heights, samples, (size_t)rows * cols * 2, cudaMemcpyHostToDevice));
+    e->terrain.type = 1; e->terrain.rows = rows; e->terrain.cols = cols; e->terrain.h = e->heights;
+    e->terrain.hscale = hscale; e->terrain.vscale = vscale; e->terrain.border = border;
+    e->terrain.friction = friction; e->terrain.restitution = restitution;
+    return GRX_OK;
+}
+
+extern "C" int grx_env_set_params(grx_env *e, const float *friction, const float *restitution, const float *motor_strength,
+                                  const float *base_inertial, const float *env_origins, const int32_t *terrain_levels,
+                                  const int32_t *terrain_types, const float *terrain_origins, int32_t t_rows, int32_t t_cols) {
+    if (!e || !friction || !restitution || !motor_strength || !base_inertial || !env_origins)
+        return grx_set_error(GRX_E_INVALID, "grx_env_set_params: null argument");
+    CK(cudaSetDevice(e->device));
+    const size_t N = e->N;
+    std::vector<float> c(N * CST_F, 0.f), r(N * REC_F);
+    CK(cudaMemcpy(r.data(), e->rec, r.size() * 4, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < N; i++) {
+        for (int j = 0; j < ND; j++) c[i * CST_F + C_MOTOR + j] = motor_strength[i * ND + j];
+        for (int j = 0; j < 10; j++) c[i * CST_F + C_BI + j] = base_inertial[i * 10 + j];
+        c[i * CST_F + C_FRIC] = friction[i]; c[i * CST_F + C_REST] = restitution[i];
+        for (int k = 0; k < 3; k++) r[i * REC_F + R_ORIGIN + k] = env_origins[i * 3 + k];
+        int lv = terrain_levels ? terrain_levels[i] : 0, ty = terrain_types ? terrain_types[i] : 0;
+        memcpy(&r[i * REC_F + R_TLEVEL], &lv, 4); memcpy(&r[i * REC_F + R_TTYPE], &ty, 4);
+    }
+    CK(cudaMemcpy(e->cst, c.data(), c.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->rec, r.data(), r.size() * 4, cudaMemcpyHostToDevice));
+    if (terrain_origins && t_rows > 0 && t_cols > 0) {
+        cudaFree(e->terrain_origins);
+        CK(cudaMalloc((void **)&e->terrain_origins, (size_t)t_rows * t_cols * 3 * 4));
+        CK(cudaMemcpy(e->terrain_origins, terrain_origins, (size_t)t_rows * t_cols * 3 * 4, cudaMemcpyHostToDevice));
+        e->t_rows = t_rows; e->t_cols = t_cols;
+    } else if (e->cfg.curriculum) {
+        return grx_set_error(GRX_E_INVALID, "grx_env_set_params: curriculum needs terrain_origins");
+    }
+    e->params_set = true;
+    return GRX_OK;
+}
+
+static void set_buf(grx_buffer *b, void *data, int dtype, int ndim, int64_t d0, int64_t d1, int64_t d2, int64_t s0, int64_t s1, int64_t s2) {
+    b->data = data; b->dtype = dtype; b->ndim = ndim;
+    b->dims[0] = d0; b->dims[1] = d1; b->dims[2] = d2; b->dims[3] = 1;
+    b->strides[0] = s0; b->strides[1] = s1; b->strides[2] = s2; b->strides[3] = 1;
+}
+
+extern "C" int grx_env_get_buffer(grx_env *e, const char *name, grx_buffer *b) {
+    if (!e || !name || !b) return grx_set_error(GRX_E_INVALID, "grx_env_get_buffer: null argument");
+    const int64_t N = e->N;
+    const std::string n(name);
+    struct RecView { const char *name; int off, width, dtype; };
+    static const RecView views[] = {
+        {"root_states", R_ROOT, 13, GRX_F32}, {"dof_pos", R_DOFPOS, ND, GRX_F32}, {"dof_vel", R_DOFVEL, ND, GRX_F32},
+        {"last_dof_vel", R_LASTDOFVEL, ND, GRX_F32}, {"last_actions", R_LASTACT, ND, GRX_F32},
+        {"last_last_actions", R_LASTLASTACT, ND, GRX_F32}, {"commands", R_CMD, 3, GRX_F32},
+        {"base_heights_offset", R_BHO, 1, GRX_F32}, {"feet_air_time", R_AIR, NF, GRX_F32}, {"feet_land_time", R_LAND, NF, GRX_F32},
+        {"feet_contact_last", R_CLAST, NF, GRX_F32}, {"episode_length", R_EPLEN, 1, GRX_I32}, {"terrain_levels", R_TLEVEL, 1, GRX_I32},
+        {"terrain_types", R_TTYPE, 1, GRX_I32}, {"env_origins", R_ORIGIN, 3, GRX_F32}, {"episode_sums", R_SUMS, NREW, GRX_F32},
+        {"records", 0, REC_F, GRX_F32}};
+    for (const RecView &v : views)
+        if (n == v.name) { set_buf(b, e->rec + v.off, v.dtype, 2, N, v.width, 1, REC_F, 1, 1); return GRX_OK; }
+    if (n == "obs") { set_buf(b, e->obs, GRX_F32, 2, N, e->cfg.num_obs, 1, e->cfg.num_obs, 1, 1); return GRX_OK; }
+    if (n == "pri_obs") { set_buf(b, e->pri_obs, GRX_F32, 2, N, e->cfg.num_pri_obs, 1, e->cfg.num_pri_obs, 1, 1); return GRX_OK; }
+    if (n == "rew") { set_buf(b, e->rew, GRX_F32, 1, N, 1, 1, 1, 1, 1); return GRX_OK; }
+    if (n == "reset") { set_buf(b, e->reset, GRX_U8, 1, N, 1, 1, 1, 1, 1); return GRX_OK; }
+    if (n == "time_out") { set_buf(b, e->time_out, GRX_U8, 1, N, 1, 1, 1, 1, 1); return GRX_OK; }
+    if (n == "torques") { set_buf(b, e->torques, GRX_F32, 2, N, ND, 1, ND, 1, 1); return GRX_OK; }
+    if (n == "contact_forces") { set_buf(b, e->contact_forces, GRX_F32, 3, N, e->nl, 3, (int64_t)e->nl * 3, 3, 1); return GRX_OK; }
+    if (n == "foot_state") { set_buf(b, e->foot_state, GRX_F32, 3, N, NF, 13, NF * 13, 13, 1); return GRX_OK; }
+    if (n == "episode_accum") { set_buf(b, e->episode_accum, GRX_F32, 1, 32, 1, 1, 1, 1, 1); return GRX_OK; }
+    if (n == "params") { set_buf(b, e->cst, GRX_F32, 2, N, CST_F, 1, CST_F, 1, 1); return GRX_OK; }
+    return grx_set_error(GRX_E_NOTFOUND, "grx_env_get_buffer: unknown buffer '" + n + "'");
+}
+
+static EnvArgs make_args(grx_env *e, const float *d_actions, const float *d_uniform, float delay, int push, uint64_t step_index) {
+    EnvArgs A;
+    memset(&A, 0, sizeof(A));
+    A.rec = e->rec; A.cst = e->cst; A.model = e->dmodel; A.terrain = e->terrain; A.terrain_origins = e->terrain_origins;
+    A.t_rows = e->t_rows; A.t_cols = e->t_cols; A.N = e->N; A.actions = d_actions; A.U = d_uniform; A.delay = delay; A.push = push;
+    A.step_index = step_index; A.obs = e->obs; A.pri_obs = e->pri_obs; A.rew = e->rew; A.torques = e->torques;
+    A.contact_forces = e->contact_forces; A.foot_state = e->foot_state; A.episode_accum = e->episode_accum;
+    A.reset = e->reset; A.time_out = e->time_out;
+    return A;
+}
+
+extern "C" int grx_env_step(grx_env *e, const float *d_actions, const float *d_uniform, float delay, int32_t push,
+                            uint64_t step_index, void *stream) {
+    if (!e || !d_actions) return grx_set_error(GRX_E_INVALID, "grx_env_step: null argument");
+    if (!e->params_set) return grx_set_error(GRX_E_STATE, "grx_env_step: call grx_env_set_params first");
+    EnvArgs A = make_args(e, d_actions, d_uniform, delay, push, step_index);
+    const int grid = (e->N + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    env_step_kernel<true><<<grid, WARPS_PER_CTA * 32, e->smem, (cudaStream_t)stream>>>(A, e->cfg);
+    CK(cudaGetLastError());
+    return GRX_OK;
+}
+
+extern "C" int grx_env_post_physics(grx_env *e, const float *d_actions, const float *d_uniform, const grx_injected_physics *inj,
+                                    int32_t push, uint64_t step_index, void *stream) {
+    if (!e || !d_actions || !inj) return grx_set_error(GRX_E_INVALID, "grx_env_post_physics: null argument");
+    if (!e->params_set) return grx_set_error(GRX_E_STATE, "grx_env_post_physics: call grx_env_set_params first");
+    EnvArgs A = make_args(e, d_actions, d_uniform, 0.f, push, step_index);
+    A.inj = *inj;
+    const int grid = (e->N + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    env_step_kernel<false><<<grid, WARPS_PER_CTA * 32, e->smem, (cudaStream_t)stream>>>(A, e->cfg);
+    CK(cudaGetLastError());
+    return GRX_OK;
+}
+
+extern "C" int grx_env_step_host(grx_env *e, const float *h_actions, float delay, int32_t push, uint64_t step_index,
+                                 float *h_obs, float *h_pri_obs, float *h_rew, uint8_t *h_reset, void *stream) {
+    if (!e || !h_actions) return grx_set_error(GRX_E_INVALID, "grx_env_step_host: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t N = e->N;
+    CK(cudaMemcpyAsync(e->actions_stage, h_actions, N * ND * 4, cudaMemcpyHostToDevice, st));
+    int rc = grx_env_step(e, e->actions_stage, nullptr, delay, push, step_index, stream);
+    if (rc) return rc;
+    if (h_obs) CK(cudaMemcpyAsync(h_obs, e->obs, N * e->cfg.num_obs * 4, cudaMemcpyDeviceToHost, st));
+    if (h_pri_obs) CK(cudaMemcpyAsync(h_pri_obs, e->pri_obs, N * e->cfg.num_pri_obs * 4, cudaMemcpyDeviceToHost, st));
+    if (h_rew) CK(cudaMemcpyAsync(h_rew, e->rew, N * 4, cudaMemcpyDeviceToHost, st));
+    if (h_reset) CK(cudaMemcpyAsync(h_reset, e->reset, N, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return GRX_OK;
+}
+
+extern "C" int grx_env_debug_dynamics(grx_env *e, int32_t index, float *h_M, float *h_h) {
+    if (!e || !h_M || !h_h || index < 0 || index >= e->N) return grx_set_error(GRX_E_INVALID, "grx_env_debug_dynamics: bad argument");
+    if (!e->params_set) return grx_set_error(GRX_E_STATE, "grx_env_debug_dynamics: call grx_env_set_params first");
+    CK(cudaSetDevice(e->device));
+    float *tmp_rec = nullptr, *dM = nullptr, *dh = nullptr, *dact = nullptr;
+    CK(cudaMalloc((void **)&tmp_rec, (size_t)e->N * REC_F * 4));
+    CK(cudaMalloc((void **)&dM, NV * NV * 4)); CK(cudaMalloc((void **)&dh, NV * 4));
+    CK(cudaMalloc((void **)&dact, (size_t)e->N * ND * 4)); CK(cudaMemset(dact, 0, (size_t)e->N * ND * 4));
+    CK(cudaMemcpy(tmp_rec, e->rec, (size_t)e->N * REC_F * 4, cudaMemcpyDeviceToDevice));
+    EnvArgs A = make_args(e, dact, nullptr, 0.f, 0, 0);
+    A.rec = tmp_rec; A.dbg_M = dM; A.dbg_h = dh; A.dbg_index = index;
+    grx_task_cfg c = e->cfg;
+    c.decimation = 1;
+    const int grid = (e->N + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    env_step_kernel<true><<<grid, WARPS_PER_CTA * 32, e->smem>>>(A, c);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(h_M, dM, NV * NV * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(h_h, dh, NV * 4, cudaMemcpyDeviceToHost));
+    cudaFree(tmp_rec); cudaFree(dM); cudaFree(dh); cudaFree(dact);
+    return GRX_OK;
+}
+
+// ABI self-check for foreign-function bindings: sizes of the public structs
+extern "C" int grx_abi_sizes(int32_t *out, int32_t n) {
+    const int32_t v[4] = {(int32_t)sizeof(grx_buffer), (int32_t)sizeof(grx_model_desc), (int32_t)sizeof(grx_task_cfg),
+                          (int32_t)sizeof(grx_injected_physics)};
+    for (int i = 0; i < n && i < 4; i++) out[i] = v[i];
+    return 4;
+}

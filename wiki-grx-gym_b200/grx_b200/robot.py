@@ -34,7 +34,11 @@ def task_tables(model, cfg):
     for name in a.terminate_after_contacts_on:                                         # legged_robot.py:1148-1159
         term.extend(i for i, s in enumerate(link_names) if name in s)
     ankle = [i for i, s in enumerate(dof_names) if _get(a, "ankle_name", "ankle") in s]  # gr1t1.py:219-220
-    return dict(kp=kp, kd=kd, default_pos=q0, torque_limits=model["dof_effort"].copy(),
+    # contact-sphere priority: spheres on termination links first (they must never lose their slot to the 8-contact cap,
+    # or a fall would go undetected), then the rest in model order
+    ts = set(term)
+    sph_order = sorted(range(len(model["sph_rad"])), key=lambda s: (0 if int(model["sph_link"][s]) in ts else 1, s))
+    return dict(sph_order=np.array(sph_order, dtype=np.int32), kp=kp, kd=kd, default_pos=q0, torque_limits=model["dof_effort"].copy(),
                 dof_vel_limits=model["dof_velocity"].copy(), hard_lower=lo, hard_upper=hi,
                 soft_lower=soft_lo, soft_upper=soft_hi, foot_links=feet, torso_links=torso,
                 termination_links=term, ankle_dofs=ankle)
