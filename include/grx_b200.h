@@ -125,7 +125,7 @@ int grx_env_set_params(grx_env *env, const float *friction, const float *restitu
 /* zero-copy views of device state, by name (what acquire_*_tensor + gymtorch.wrap_tensor give, legged_robot.py:110-135):
  * root_states dof_pos dof_vel last_dof_vel last_actions last_last_actions commands base_heights_offset feet_air_time
  * feet_land_time feet_contact_last episode_length terrain_levels terrain_types env_origins episode_sums
- * obs pri_obs rew reset time_out torques contact_forces foot_state episode_accum */
+ * obs pri_obs rew reset time_out torques contact_forces foot_state episode_accum params records */
 int grx_env_get_buffer(grx_env *env, const char *name, grx_buffer *out);
 
 /* One policy step = legged_robot.py:222-246 with the GR1T1 MRO: action clip, `decimation` substeps of
@@ -135,6 +135,18 @@ int grx_env_get_buffer(grx_env *env, const char *name, grx_buffer *out);
  *   common_step_counter % push_interval == 0 (legged_robot.py:333-334);  step_index feeds the Philox counter. */
 int grx_env_step(grx_env *env, const float *d_actions, const float *d_uniform, float delay, int32_t push,
                  uint64_t step_index, void *stream);
+
+/* Host-invoked reset_idx (legged_robot.py:377-440 as reached from BaseTask.reset(), base_task.py:117-121): d_ids = device int32
+ * env indices (NULL = all, then n must be num_envs); d_uniform as in grx_env_step; curriculum_active = the reference's
+ * `init_done` guard (legged_robot.py:806-808). */
+int grx_env_reset_idx(grx_env *env, const int32_t *d_ids, int32_t n, const float *d_uniform, int32_t curriculum_active,
+                      uint64_t step_index, void *stream);
+
+/* extras["episode"] (legged_robot.py:420-427): every step / reset launch accumulates, over the envs it resets, the 24
+ * episode sums [0..23], the reset count [24] and the sum of terrain levels over ALL envs [25] into one 32-float slot of the
+ * ring buffer `episode_accum` [256, 32].  Returns the slot the most recent launch used (no host sync needed to read it
+ * later on the stream). */
+int64_t grx_env_accum_slot(grx_env *env);
 
 /* Test entry: the post-physics half only, on injected physics outputs (device pointers); the env records must already
  * hold the post-physics root / dof state.  Isolates the reference's own arithmetic (LR/FF/G1) from our dynamics spec. */

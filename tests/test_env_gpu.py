@@ -1,0 +1,180 @@
+"""GPU parity tests of the fused env kernel, through the C ABI (libgrx_b200.so -> grx_b200.env.GRXVecEnv).
+
+ * post-physics half vs golden trajectories of the UNMODIFIED reference classes (reference-pinned, tight tolerance)
+ * full step (our dynamics spec) vs the golden full steps, whose physics was the C oracle in fp32 (teacher-forced per step)
+ * mass matrix / bias vector vs the fp64 oracle
+ * size-independent properties at BASELINE.json's full size (4096 envs, rough heightfield)
+"""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import ENV_FIXTURES, load_fixture, step_items
+from parity_util import PHYS_TOL, POST_TOL, make_gpu_env
+
+pytestmark = pytest.mark.gpu
+
+CARRIED_F = ("root_states", "dof_pos", "dof_vel", "last_dof_vel", "last_actions", "last_last_actions", "commands",
+             "base_heights_offset", "feet_air_time", "feet_land_time")
+
+
+def _cmp_state(env, st, tol, msg):
+    for k in CARRIED_F:
+        got = getattr(env, k).cpu().numpy()
+        np.testing.assert_allclose(got, st[k].reshape(got.shape), err_msg=f"{msg} state {k}", **tol)
+    np.testing.assert_array_equal(env.feet_contact_last.cpu().numpy() != 0, st["feet_contact_last"].astype(bool), err_msg=msg)
+    np.testing.assert_array_equal(env.episode_length_buf.cpu().numpy(), st["episode_length_buf"], err_msg=msg)
+    np.testing.assert_allclose(env.episode_sums_buf.cpu().numpy(), st["episode_sums"], err_msg=f"{msg} episode_sums", rtol=tol["rtol"], atol=10 * tol["atol"])
+    if "terrain_levels" in st and env.custom_origins:
+        np.testing.assert_array_equal(env.terrain_levels.cpu().numpy(), st["terrain_levels"], err_msg=msg)
+        np.testing.assert_allclose(env.env_origins.cpu().numpy(), st["env_origins"], err_msg=msg, **tol)
+
+
+@pytest.mark.parametrize("name", ENV_FIXTURES)
+def test_post_physics_matches_reference(name):
+    """obs / pri_obs / rew / reset / time_out / carried state / extras of the CUDA post-physics path == the unmodified
+    reference GR1T1 / GR1T2 classes (golden), given the same physics outputs and the same random draws."""
+    fx = load_fixture(name)
+    env = make_gpu_env(fx, sync_extras=True)[0]
+    dev = env.device
+    n_reset = 0
+    for t in range(int(fx["meta/steps"])):
+        pre = f"step{t:02d}/"
+        ph = step_items(fx, t, "phys")
+        env.root_states.copy_(torch.from_numpy(ph["root_states_phys"]).to(dev))
+        env.dof_pos.copy_(torch.from_numpy(ph["dof_pos_phys"]).to(dev))
+        env.dof_vel.copy_(torch.from_numpy(ph["dof_vel_phys"]).to(dev))
+        inj = dict(torques=torch.from_numpy(ph["torques_phys"]), foot_state=torch.from_numpy(ph["foot_state"]),
+                   torso_quat=torch.from_numpy(ph["torso_quat"]), contact_forces=torch.from_numpy(ph["contact_forces"]),
+                   avg_foot_force=torch.from_numpy(ph["avg_feet_contact_force"]), avg_foot_linvel=torch.from_numpy(ph["avg_feet_speed_xyz"]))
+        U = torch.from_numpy(fx[pre + "U"]).to(dev)
+        obs, pri, rew, reset, extras = env.post_physics_injected(torch.from_numpy(fx[pre + "actions"]), U, inj)
+        out, st = step_items(fx, t, "out"), step_items(fx, t, "state")
+        msg = f"{name} t={t}"
+        np.testing.assert_array_equal(reset.cpu().numpy(), out["reset_buf"].astype(bool), err_msg=msg)
+        np.testing.assert_array_equal(env.time_out_buf.cpu().numpy(), out["time_out_buf"].astype(bool), err_msg=msg)
+        np.testing.assert_allclose(obs.cpu().numpy(), out["obs_buf"], err_msg=msg + " obs", **POST_TOL)
+        np.testing.assert_allclose(pri.cpu().numpy(), out["pri_obs_buf"], err_msg=msg + " pri_obs", **POST_TOL)
+        np.testing.assert_allclose(rew.cpu().numpy(), out["rew_buf"], err_msg=msg + " rew", **POST_TOL)
+        _cmp_state(env, st, POST_TOL, msg)
+        if pre + "extras_episode" in fx:
+            got = np.array([float(extras["episode"]["rew_" + n]) for n in env.reward_names], np.float32)
+            np.testing.assert_allclose(got, fx[pre + "extras_episode"], rtol=1e-4, atol=1e-6, err_msg=msg + " extras")
+            if pre + "extras_terrain_level" in fx:
+                np.testing.assert_allclose(float(extras["episode"]["terrain_level"]), float(fx[pre + "extras_terrain_level"]), rtol=1e-6)
+        n_reset += int(reset.sum())
+    assert n_reset >= 3
+
+
+@pytest.mark.parametrize("name", ENV_FIXTURES)
+def test_full_step_matches_oracle(name):
+    """The whole fused step (PD torque -> dynamics -> contact -> integrate x decimation -> post-physics) vs the golden
+    trajectory, restarted from the golden state before every step so fp32 rounding does not accumulate chaotically."""
+    fx = load_fixture(name)
+    env = make_gpu_env(fx)[0]
+    dev = env.device
+    N = env.num_envs
+    bad_rows = 0
+    for t in range(int(fx["meta/steps"])):
+        pre = f"step{t:02d}/"
+        if t > 0:
+            env.load_state(step_items(fx, t - 1, "state"))
+        U = torch.from_numpy(fx[pre + "U"]).to(dev)
+        obs, pri, rew, reset, _ = env.step(torch.from_numpy(fx[pre + "actions"]).to(dev), U=U, delay=float(fx[pre + "delay"]))
+        torch.cuda.synchronize()
+        out, ph = step_items(fx, t, "out"), step_items(fx, t, "phys")
+        # contact on/off decisions near a threshold may legitimately flip under different rounding: tolerate a few envs
+        ok = np.ones(N, bool)
+        ok &= reset.cpu().numpy() == out["reset_buf"].astype(bool)
+        ok &= np.isclose(env.torques.cpu().numpy(), out["torques"], **PHYS_TOL).all(1)
+        ok &= np.isclose(obs.cpu().numpy(), out["obs_buf"], **PHYS_TOL).all(1)
+        ok &= np.isclose(pri.cpu().numpy(), out["pri_obs_buf"], rtol=5e-3, atol=5e-3).all(1)
+        ok &= np.isclose(rew.cpu().numpy(), out["rew_buf"], **PHYS_TOL)
+        cf = env.contact_forces.cpu().numpy()
+        ok &= np.isclose(cf, ph["contact_forces"], rtol=2e-2, atol=0.5).all((1, 2))
+        bad_rows += int((~ok).sum())
+        assert (~ok).sum() <= max(1, N // 16), f"{name} t={t}: {(~ok).sum()} of {N} envs differ: {np.nonzero(~ok)[0]}"
+    assert bad_rows <= int(fx["meta/steps"]) * max(1, N // 32)
+
+
+@pytest.mark.parametrize("robot", ["GR1T1", "GR1T2"])
+def test_mass_matrix_and_bias_match_fp64_oracle(robot):
+    from grx_b200.config import make_cfg
+    from grx_b200.env import GRXVecEnv
+    from oracle.phys import PhysOracle
+    cfg = make_cfg(robot, 8, "plane")
+    env = GRXVecEnv(cfg, sim_device="cuda:0")
+    g = torch.Generator().manual_seed(3)
+    root = torch.zeros(8, 13)
+    root[:, 2] = 1.0
+    q = torch.randn(8, 4, generator=g)
+    root[:, 3:7] = q / q.norm(dim=1, keepdim=True)
+    root[:, 7:13] = torch.randn(8, 6, generator=g)
+    dq = 0.3 * torch.randn(8, 10, generator=g)
+    dqd = 2.0 * torch.randn(8, 10, generator=g)
+    env.root_states.copy_(root.cuda()); env.dof_pos.copy_(dq.cuda()); env.dof_vel.copy_(dqd.cuda())
+    torch.cuda.synchronize()
+    ora = PhysOracle(env.model, env.tables, None, dtype=np.float64)
+    for i in range(8):
+        M, h = env.debug_dynamics(i)
+        Mo, ho, _ = ora.dynamics_terms(env.params["base_inertial"][i], root[i].numpy(), dq[i].numpy(), dqd[i].numpy())
+        np.testing.assert_allclose(M, Mo, rtol=2e-4, atol=2e-4)
+        np.testing.assert_allclose(h, ho, rtol=2e-4, atol=2e-3)
+
+
+def test_full_size_properties():
+    """BASELINE config #2 shape: 4096 robots on the rough heightfield, fast-mode (in-kernel Philox) draws."""
+    from grx_b200.config import make_cfg
+    from grx_b200.env import GRXVecEnv
+    cfg = make_cfg("GR1T1", 4096, "heightfield")
+    env = GRXVecEnv(cfg, sim_device="cuda:0")
+    obs, pri = env.reset()
+    assert obs.shape == (4096, 39) and pri.shape == (4096, 168)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    n_reset, n_steps = 0, 150
+    lvl0 = env.terrain_levels.clone()
+    for _ in range(n_steps):
+        a = 0.3 * torch.randn(4096, 10, device="cuda", generator=g)
+        obs, pri, rew, reset, extras = env.step(a)
+        n_reset += int(reset.sum())
+    torch.cuda.synchronize()
+    for t in (obs, pri, rew, env.root_states, env.dof_pos, env.dof_vel):
+        assert torch.isfinite(t).all()
+    assert obs.abs().max() <= 100.0 and pri.abs().max() <= 100.0                       # clip_observations
+    assert 0 < n_reset < 4096 * n_steps // 4                                           # random actions: robots fall, but not at once
+    assert torch.allclose(pri[:, 3:9], obs[:, 3:9], atol=0.06)                         # obs = pri[:39] + bounded noise
+    noise = (obs - pri[:, :39]).abs().max(0).values.cpu().numpy()
+    bound = np.array([0] * 3 + [0.05] * 3 + [0.03] * 3 + [0.04] * 10 + [0.2] * 10 + [0] * 10) + 1e-6
+    assert (noise <= bound).all() and noise[3:29].min() > 0.0
+    q = env.root_states[:, 3:7]
+    assert torch.allclose(q.norm(dim=1), torch.ones(4096, device="cuda"), atol=1e-4)   # integrator keeps the quaternion unit
+    lim_lo = torch.tensor(env.model["dof_lower"], device="cuda", dtype=torch.float32) - 0.05
+    lim_hi = torch.tensor(env.model["dof_upper"], device="cuda", dtype=torch.float32) + 0.05
+    inside = ((env.dof_pos >= lim_lo) & (env.dof_pos <= lim_hi)).all(1)
+    assert inside.float().mean() > 0.95                                                # joint-limit rows hold (reset draws may start outside)
+    assert (env.terrain_levels != lvl0).any()                                          # curriculum moved somebody
+    ep = extras["episode"]
+    assert set(ep.keys()) == {"rew_" + n for n in env.reward_names} | {"terrain_level"}
+    assert all(torch.isfinite(v) for v in ep.values())
+
+
+def test_standing_contact_force_balances_weight():
+    """Physical envelope: a robot holding its default pose on the plane settles with sum F_z ~= m g."""
+    from grx_b200.config import make_cfg
+    from grx_b200.env import GRXVecEnv
+    from grx_b200.robot import nominal_params
+    from grx_b200.urdf import builtin_model
+    cfg = make_cfg("GR1T1", 16, "plane")
+    cfg.noise.add_noise = False
+    cfg.domain_rand.push_robots = cfg.domain_rand.randomize_init_dof_pos = cfg.domain_rand.randomize_init_base_velocity = False
+    env = GRXVecEnv(cfg, sim_device="cuda:0", params=nominal_params(builtin_model("GR1T1"), 16))
+    env.reset()
+    for _ in range(50):
+        env.step(torch.zeros(16, 10, device="cuda"), delay=0.0)
+    torch.cuda.synchronize()
+    fz = env.contact_forces[:, :, 2].sum(1).cpu().numpy()
+    mg = float(env.model["mass"][1:].sum() + env.params["base_inertial"][0, 0]) * 9.81
+    alive = ~env.reset_buf.cpu().numpy()
+    assert alive.mean() > 0.7
+    np.testing.assert_allclose(fz[alive], mg, rtol=0.15)
+    assert abs(mg - 52.83 * 9.81) < 1.0                                               # GR1T1 mass

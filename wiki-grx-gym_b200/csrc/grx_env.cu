@@ -28,6 +28,7 @@ namespace {
 constexpr int NB = 11, ND = 10, NV = 16, CH = 5, NLMAX = 40, NSMAX = 32, NF = 2, KC = 8, KLIM = 8;
 constexpr int NREW = 24, NHMAX = 128;
 constexpr int WARPS_PER_CTA = 4;
+constexpr int ACC_RING = 256, ACC_W = 32;   // extras["episode"] accumulators: one 32-float slot per launch, ring of 256
 constexpr unsigned FULL = 0xffffffffu;
 
 // ---- per-env state record (floats; ints stored bit-wise) — 108 floats = 432 B, 16-B aligned
@@ -76,7 +77,8 @@ struct EnvArgs {
     float delay;
     int push;
     unsigned long long step_index;
-    float *obs, *pri_obs, *rew, *torques, *contact_forces, *foot_state, *episode_accum;
+    float *obs, *pri_obs, *rew, *torques, *contact_forces, *foot_state;
+    float *episode_accum, *episode_accum_next;  // this launch's slot of the extras ring, and the slot to clear for the next launch
     unsigned char *reset, *time_out;
     grx_injected_physics inj;
     float *dbg_M, *dbg_h;  // debug_dynamics
@@ -740,6 +742,64 @@ __device__ __forceinline__ void resample_commands(WS &s, const grx_task_cfg &cfg
     s.rec[R_CMD + 2] = (cfg.cmd_range[2][1] - cfg.cmd_range[2][0]) * draw(base + 2) + cfg.cmd_range[2][0];
 }
 
+// ---- reset of one env (warp-cooperative): _update_terrain_curriculum LR:799-826, _reset_dofs LR:717-740,
+// _reset_root_states LR:742-784, _resample_commands LR:402, buffer zeroing LR:405-415 + FF:137-146, episode sums -> extras LR:420-424
+__device__ __forceinline__ void reset_env(WS &s, const ModelDev &m, const EnvArgs &A, const grx_task_cfg &cfg, const Draw &draw,
+                                          int lane, float cnorm, bool curriculum_active) {
+    float *rec = s.rec;
+    if (cfg.curriculum && curriculum_active) {
+        if (lane == 0) {
+            const float dx = rec[R_ROOT] - rec[R_ORIGIN], dy = rec[R_ROOT + 1] - rec[R_ORIGIN + 1];
+            const float distance = sqrtf(dx * dx + dy * dy);
+            const bool up = distance > cfg.terrain_env_length / 2.f;
+            const bool down = (distance < cnorm * cfg.max_episode_length_s * 0.5f) && !up;
+            int level = __float_as_int(rec[R_TLEVEL]) + (up ? 1 : 0) - (down ? 1 : 0);
+            if (level >= A.t_rows) level = min((int)floorf(draw(U_CURRICULUM) * (float)A.t_rows), A.t_rows - 1);
+            else level = max(level, 0);
+            rec[R_TLEVEL] = __int_as_float(level);
+            const int type = __float_as_int(rec[R_TTYPE]);
+            const float *org = A.terrain_origins + ((size_t)level * A.t_cols + type) * 3;
+            rec[R_ORIGIN] = org[0]; rec[R_ORIGIN + 1] = org[1]; rec[R_ORIGIN + 2] = org[2];
+        }
+        __syncwarp();
+    }
+    if (lane < ND) {                                                                  // _reset_dofs LR:717-734
+        rec[R_DOFPOS + lane] = cfg.randomize_init_dof_pos ? ((1.5f - 0.5f) * draw(U_RESET_DOF + lane) + 0.5f) * m.q0[lane] : m.q0[lane];
+        rec[R_DOFVEL + lane] = 0.f;
+        rec[R_LASTACT + lane] = 0.f;
+        rec[R_LASTDOFVEL + lane] = 0.f;
+        rec[R_LASTLASTACT + lane] = 0.f;
+    }
+    if (lane == 0) {                                                                  // _reset_root_states LR:742-779
+        float *rt = rec + R_ROOT;
+#pragma unroll
+        for (int k = 0; k < 13; k++) rt[k] = cfg.base_init_state[k];
+#pragma unroll
+        for (int k = 0; k < 3; k++) rt[k] += rec[R_ORIGIN + k];
+        if (cfg.custom_origins) {
+            rt[0] += (1.0f - -1.0f) * draw(U_RESET_XY) + -1.0f;
+            rt[1] += (1.0f - -1.0f) * draw(U_RESET_XY + 1) + -1.0f;
+        }
+        const float yaw = 12.566370614359172f * draw(U_RESET_YAW) + -6.283185307179586f;
+        float sy, cy;
+        sincosf(yaw * 0.5f, &sy, &cy);
+        rt[3] = 0.f; rt[4] = 0.f; rt[5] = sy; rt[6] = cy;
+        if (cfg.randomize_init_base_velocity) {
+#pragma unroll
+            for (int k = 0; k < 6; k++) rt[7 + k] = (0.5f - -0.5f) * draw(U_RESET_VEL + k) + -0.5f;
+        }
+        resample_commands(s, cfg, draw, U_CMD_RESET);                                 // LR:402
+        rec[R_EPLEN] = __int_as_float(0);
+    }
+    if (lane < NF) { rec[R_AIR + lane] = 0.f; rec[R_LAND + lane] = 0.f; rec[R_CLAST + lane] = 0.f; }
+    if (lane < NREW) {                                                                // extras["episode"] sums LR:420-424
+        atomicAdd(A.episode_accum + lane, rec[R_SUMS + lane]);
+        rec[R_SUMS + lane] = 0.f;
+    }
+    if (lane == NREW) atomicAdd(A.episode_accum + NREW, 1.0f);
+    __syncwarp();
+}
+
 template <bool PHYS>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) env_step_kernel(const __grid_constant__ EnvArgs A,
                                                                          const __grid_constant__ grx_task_cfg cfg) {
@@ -753,6 +813,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) env_step_kernel(const _
         int4 *dst = reinterpret_cast<int4 *>(&m);
         for (int i = threadIdx.x; i < (int)(sizeof(ModelDev) / 16); i += blockDim.x) dst[i] = src[i];
     }
+    if (blockIdx.x == 0 && threadIdx.x < ACC_W) A.episode_accum_next[threadIdx.x] = 0.f;   // nobody accumulates into the next slot during this launch
     const bool valid = e < A.N;
     if (valid) {
         if (lane == 0) {
@@ -1031,58 +1092,11 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) env_step_kernel(const _
     // ---- reset_idx (LR:377-440, FF:137-146), curriculum (LR:799-826)
     bool contact_for_obs = contact;
     if (reset) {
-        if (cfg.curriculum) {
-            if (lane == 0) {
-                const float dx = rec[R_ROOT] - rec[R_ORIGIN], dy = rec[R_ROOT + 1] - rec[R_ORIGIN + 1];
-                const float distance = sqrtf(dx * dx + dy * dy);
-                const bool up = distance > cfg.terrain_env_length / 2.f;
-                const bool down = (distance < cnorm * cfg.max_episode_length_s * 0.5f) && !up;
-                int level = __float_as_int(rec[R_TLEVEL]) + (up ? 1 : 0) - (down ? 1 : 0);
-                if (level >= A.t_rows) level = min((int)floorf(draw(U_CURRICULUM) * (float)A.t_rows), A.t_rows - 1);
-                else level = max(level, 0);
-                rec[R_TLEVEL] = __int_as_float(level);
-                const int type = __float_as_int(rec[R_TTYPE]);
-                const float *org = A.terrain_origins + ((size_t)level * A.t_cols + type) * 3;
-                rec[R_ORIGIN] = org[0]; rec[R_ORIGIN + 1] = org[1]; rec[R_ORIGIN + 2] = org[2];
-            }
-            __syncwarp();
-        }
-        if (lane < nd) {                                                              // _reset_dofs LR:717-734
-            rec[R_DOFPOS + lane] = cfg.randomize_init_dof_pos ? ((1.5f - 0.5f) * draw(U_RESET_DOF + lane) + 0.5f) * m.q0[lane] : m.q0[lane];
-            rec[R_DOFVEL + lane] = 0.f;
-            rec[R_LASTACT + lane] = 0.f;
-            rec[R_LASTDOFVEL + lane] = 0.f;
-            rec[R_LASTLASTACT + lane] = 0.f;
-        }
-        if (lane == 0) {                                                              // _reset_root_states LR:742-779
-            float *rt = rec + R_ROOT;
-#pragma unroll
-            for (int k = 0; k < 13; k++) rt[k] = cfg.base_init_state[k];
-#pragma unroll
-            for (int k = 0; k < 3; k++) rt[k] += rec[R_ORIGIN + k];
-            if (cfg.custom_origins) {
-                rt[0] += (1.0f - -1.0f) * draw(U_RESET_XY) + -1.0f;
-                rt[1] += (1.0f - -1.0f) * draw(U_RESET_XY + 1) + -1.0f;
-            }
-            const float yaw = 12.566370614359172f * draw(U_RESET_YAW) + -6.283185307179586f;
-            float sy, cy;
-            sincosf(yaw * 0.5f, &sy, &cy);
-            rt[3] = 0.f; rt[4] = 0.f; rt[5] = sy; rt[6] = cy;
-            if (cfg.randomize_init_base_velocity) {
-#pragma unroll
-                for (int k = 0; k < 6; k++) rt[7 + k] = (0.5f - -0.5f) * draw(U_RESET_VEL + k) + -0.5f;
-            }
-            resample_commands(s, cfg, draw, U_CMD_RESET);                             // LR:402
-            ep_len = 0;
-        }
-        ep_len = __shfl_sync(FULL, ep_len, 0);
+        reset_env(s, m, A, cfg, draw, lane, cnorm, true);
+        ep_len = 0;
         if (lane < NF) { air = 0.f; land = 0.f; contact_for_obs = false; }
-        if (lane < NREW) {                                                            // extras["episode"] sums LR:420-424
-            atomicAdd(A.episode_accum + lane, rec[R_SUMS + lane]);
-            rec[R_SUMS + lane] = 0.f;
-        }
-        if (lane == NREW) atomicAdd(A.episode_accum + NREW, 1.0f);
     }
+    if (lane == 0 && cfg.curriculum) atomicAdd(A.episode_accum + NREW + 1, (float)__float_as_int(rec[R_TLEVEL]));   // LR:427
     __syncwarp();
 
     // ---- compute_observations (LR:442-452, FF:148-167, G1:281-313) — after the reset, with stale base quantities (App. B-2)
@@ -1158,6 +1172,38 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) env_step_kernel(const _
     }
 }
 
+// Host-invoked reset_idx (BaseTask.reset(), base_task.py:117-121): one warp per listed env (ids == nullptr: all envs).
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) env_reset_kernel(const __grid_constant__ EnvArgs A, const __grid_constant__ grx_task_cfg cfg,
+                                                                      const int *ids, int n, int curriculum_active) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ModelDev &m = *reinterpret_cast<ModelDev *>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WS &s = *reinterpret_cast<WS *>(smem_raw + ((sizeof(ModelDev) + 15) & ~15) + (size_t)warp * sizeof(WS));
+    {
+        const int4 *src = reinterpret_cast<const int4 *>(A.model);
+        int4 *dst = reinterpret_cast<int4 *>(&m);
+        for (int i = threadIdx.x; i < (int)(sizeof(ModelDev) / 16); i += blockDim.x) dst[i] = src[i];
+    }
+    if (blockIdx.x == 0 && threadIdx.x < ACC_W) A.episode_accum_next[threadIdx.x] = 0.f;
+    __syncthreads();
+    const int w = blockIdx.x * WARPS_PER_CTA + warp;
+    if (w >= n) return;
+    const int e = ids ? ids[w] : w;
+    if (e < 0 || e >= A.N) return;
+    float *g = A.rec + (size_t)e * REC_F;
+    for (int i = lane; i < REC_F; i += 32) s.rec[i] = g[i];
+    __syncwarp();
+    Draw draw;
+    draw.U = A.U ? A.U + (size_t)e * GRX_RNG_K : nullptr;
+    draw.k0 = (uint32_t)cfg.seed ^ 0x5bd1e995u; draw.k1 = (uint32_t)(cfg.seed >> 32);
+    draw.gid = (uint32_t)(cfg.env_id_offset + e);
+    draw.step_lo = (uint32_t)A.step_index; draw.step_hi = (uint32_t)(A.step_index >> 32);
+    const float cx = s.rec[R_CMD], cy = s.rec[R_CMD + 1];
+    reset_env(s, m, A, cfg, draw, lane, sqrtf(cx * cx + cy * cy), curriculum_active != 0);
+    if (lane == 0 && cfg.curriculum) atomicAdd(A.episode_accum + NREW + 1, (float)__float_as_int(s.rec[R_TLEVEL]));
+    for (int i = lane; i < REC_F; i += 32) g[i] = s.rec[i];
+}
+
 }  // namespace
 
 // =========================================================================================================
@@ -1189,6 +1235,7 @@ struct grx_env {
     int t_rows = 1, t_cols = 1;
     bool params_set = false;
     size_t smem = 0;
+    uint64_t launches = 0;   // step / reset launches so far; launch k accumulates extras into ring slot k % ACC_RING
 };
 
 static size_t env_smem_bytes() { return ((sizeof(ModelDev) + 15) & ~(size_t)15) + WARPS_PER_CTA * sizeof(WS); }
@@ -1240,7 +1287,7 @@ extern "C" int grx_env_create(const grx_model_desc *md, const grx_task_cfg *cfg,
     ALLOC(e->rec, N * REC_F * 4); ALLOC(e->cst, N * CST_F * 4);
     ALLOC(e->obs, N * cfg->num_obs * 4); ALLOC(e->pri_obs, N * cfg->num_pri_obs * 4);
     ALLOC(e->rew, N * 4); ALLOC(e->torques, N * ND * 4); ALLOC(e->contact_forces, N * md->nl * 3 * 4);
-    ALLOC(e->foot_state, N * NF * 13 * 4); ALLOC(e->episode_accum, 32 * 4); ALLOC(e->actions_stage, N * ND * 4);
+    ALLOC(e->foot_state, N * NF * 13 * 4); ALLOC(e->episode_accum, ACC_RING * ACC_W * 4); ALLOC(e->actions_stage, N * ND * 4);
     ALLOC(e->reset, N); ALLOC(e->time_out, N);
     ALLOC(e->terrain_origins, 3 * 4);
 #undef ALLOC
@@ -1255,6 +1302,7 @@ extern "C" int grx_env_create(const grx_model_desc *md, const grx_task_cfg *cfg,
     e->smem = env_smem_bytes();
     CK(cudaFuncSetAttribute(env_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
     CK(cudaFuncSetAttribute(env_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+    CK(cudaFuncSetAttribute(env_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
     *out = e;
     return GRX_OK;
 }
@@ -1348,7 +1396,7 @@ extern "C" int grx_env_get_buffer(grx_env *e, const char *name, grx_buffer *b) {
     if (n == "torques") { set_buf(b, e->torques, GRX_F32, 2, N, ND, 1, ND, 1, 1); return GRX_OK; }
     if (n == "contact_forces") { set_buf(b, e->contact_forces, GRX_F32, 3, N, e->nl, 3, (int64_t)e->nl * 3, 3, 1); return GRX_OK; }
     if (n == "foot_state") { set_buf(b, e->foot_state, GRX_F32, 3, N, NF, 13, NF * 13, 13, 1); return GRX_OK; }
-    if (n == "episode_accum") { set_buf(b, e->episode_accum, GRX_F32, 1, 32, 1, 1, 1, 1, 1); return GRX_OK; }
+    if (n == "episode_accum") { set_buf(b, e->episode_accum, GRX_F32, 2, ACC_RING, ACC_W, 1, ACC_W, 1, 1); return GRX_OK; }
     if (n == "params") { set_buf(b, e->cst, GRX_F32, 2, N, CST_F, 1, CST_F, 1, 1); return GRX_OK; }
     return grx_set_error(GRX_E_NOTFOUND, "grx_env_get_buffer: unknown buffer '" + n + "'");
 }
@@ -1359,7 +1407,9 @@ static EnvArgs make_args(grx_env *e, const float *d_actions, const float *d_unif
     A.rec = e->rec; A.cst = e->cst; A.model = e->dmodel; A.terrain = e->terrain; A.terrain_origins = e->terrain_origins;
     A.t_rows = e->t_rows; A.t_cols = e->t_cols; A.N = e->N; A.actions = d_actions; A.U = d_uniform; A.delay = delay; A.push = push;
     A.step_index = step_index; A.obs = e->obs; A.pri_obs = e->pri_obs; A.rew = e->rew; A.torques = e->torques;
-    A.contact_forces = e->contact_forces; A.foot_state = e->foot_state; A.episode_accum = e->episode_accum;
+    A.contact_forces = e->contact_forces; A.foot_state = e->foot_state;
+    A.episode_accum = e->episode_accum + (size_t)(e->launches % ACC_RING) * ACC_W;
+    A.episode_accum_next = e->episode_accum + (size_t)((e->launches + 1) % ACC_RING) * ACC_W;
     A.reset = e->reset; A.time_out = e->time_out;
     return A;
 }
@@ -1372,6 +1422,7 @@ extern "C" int grx_env_step(grx_env *e, const float *d_actions, const float *d_u
     const int grid = (e->N + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     env_step_kernel<true><<<grid, WARPS_PER_CTA * 32, e->smem, (cudaStream_t)stream>>>(A, e->cfg);
     CK(cudaGetLastError());
+    e->launches++;
     return GRX_OK;
 }
 
@@ -1384,8 +1435,24 @@ extern "C" int grx_env_post_physics(grx_env *e, const float *d_actions, const fl
     const int grid = (e->N + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     env_step_kernel<false><<<grid, WARPS_PER_CTA * 32, e->smem, (cudaStream_t)stream>>>(A, e->cfg);
     CK(cudaGetLastError());
+    e->launches++;
     return GRX_OK;
 }
+
+extern "C" int grx_env_reset_idx(grx_env *e, const int32_t *d_ids, int32_t n, const float *d_uniform, int32_t curriculum_active,
+                                 uint64_t step_index, void *stream) {
+    if (!e || n < 0 || (d_ids == nullptr && n != e->N)) return grx_set_error(GRX_E_INVALID, "grx_env_reset_idx: bad arguments (ids == NULL needs n == num_envs)");
+    if (!e->params_set) return grx_set_error(GRX_E_STATE, "grx_env_reset_idx: call grx_env_set_params first");
+    if (n == 0) return GRX_OK;                                                        // LR:387-388
+    EnvArgs A = make_args(e, nullptr, d_uniform, 0.f, 0, step_index);
+    const int grid = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    env_reset_kernel<<<grid, WARPS_PER_CTA * 32, e->smem, (cudaStream_t)stream>>>(A, e->cfg, d_ids, n, curriculum_active);
+    CK(cudaGetLastError());
+    e->launches++;
+    return GRX_OK;
+}
+
+extern "C" int64_t grx_env_accum_slot(grx_env *e) { return e ? (int64_t)((e->launches + ACC_RING - 1) % ACC_RING) : -1; }
 
 extern "C" int grx_env_step_host(grx_env *e, const float *h_actions, float delay, int32_t push, uint64_t step_index,
                                  float *h_obs, float *h_pri_obs, float *h_rew, uint8_t *h_reset, void *stream) {

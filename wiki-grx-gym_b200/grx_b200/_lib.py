@@ -84,6 +84,8 @@ def lib():
             raise GrxError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
         _lib = C.CDLL(LIB_PATH)
         _lib.grx_last_error.restype = C.c_char_p
+        _lib.grx_env_accum_slot.restype = C.c_int64
+        _lib.grx_env_accum_slot.argtypes = [C.c_void_p]
         sizes = (I32 * 4)()
         _lib.grx_abi_sizes(sizes, 4)
         want = [C.sizeof(Buffer), C.sizeof(ModelDesc), C.sizeof(TaskCfg), C.sizeof(InjectedPhysics)]
@@ -99,7 +101,7 @@ def check(rc):
 
 EXPORTED = ["grx_last_error", "grx_version", "grx_abi_sizes", "grx_env_create", "grx_env_destroy",
             "grx_env_set_terrain_plane", "grx_env_set_terrain_heightfield", "grx_env_set_params", "grx_env_get_buffer",
-            "grx_env_step", "grx_env_post_physics", "grx_env_step_host", "grx_env_debug_dynamics",
+            "grx_env_step", "grx_env_reset_idx", "grx_env_accum_slot", "grx_env_post_physics", "grx_env_step_host", "grx_env_debug_dynamics",
             "grx_ppo_create", "grx_ppo_destroy", "grx_ppo_get_buffer", "grx_ppo_act", "grx_ppo_process_env_step",
             "grx_ppo_compute_returns", "grx_ppo_compute_returns_local", "grx_ppo_normalize_advantages",
             "grx_ppo_minibatch_grads", "grx_ppo_minibatch_apply", "grx_ppo_update", "grx_ppo_act_inference"]

@@ -1,0 +1,422 @@
+"""GRXVecEnv — the reference's VecEnv surface (rsl_rl/rsl_rl/env/vec_env.py:7-40 as concretised by
+legged_gym/legged_gym/envs/base/base_task.py:39-121 and legged_robot.py:53-246) over the fused B200 env kernel.
+
+Every public tensor is a zero-copy (possibly strided) view of device memory owned by libgrx_b200.so, the same
+contract gymtorch.wrap_tensor gives (gymtorch.py:61-95).  One ``step()`` is ONE kernel launch on torch's current
+stream; nothing in it synchronises with the host (the reference syncs 3x per step: legged_robot.py:292, 317, 387).
+
+There is no CPU fallback: without the CUDA library and a CUDA device the constructor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import rng_layout as RL
+from .config import make_cfg
+from .robot import nominal_params, sample_domain_rand, task_tables
+from .terrain import Terrain
+from .urdf import builtin_model
+
+REWARD_NAMES = list(L._SIGMAS[:21]) + ["on_the_air", "pose_offset", "stand_still"]   # alphabetical
+assert REWARD_NAMES == sorted(REWARD_NAMES) and len(REWARD_NAMES) == 24
+
+_TORCH_DT = {0: torch.float32, 3: torch.uint8, 4: torch.int16, 5: torch.int32}
+_TYPESTR = {0: "<f4", 3: "|u1", 4: "<i2", 5: "<i4"}
+
+
+class _DevArray:
+    """__cuda_array_interface__ holder so torch can alias a raw device pointer (role of gymtorch.wrap_tensor)."""
+
+    def __init__(self, buf: L.Buffer, owner):
+        nd = buf.ndim
+        item = {0: 4, 3: 1, 4: 2, 5: 4}[buf.dtype]
+        self.owner = owner
+        self.__cuda_array_interface__ = {
+            "shape": tuple(int(buf.dims[i]) for i in range(nd)),
+            "strides": tuple(int(buf.strides[i]) * item for i in range(nd)),
+            "typestr": _TYPESTR[buf.dtype], "data": (int(buf.data), False), "version": 2}
+
+
+def _f32p(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a, a.ctypes.data_as(L.PF)
+
+
+def _i32p(a):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    return a, a.ctypes.data_as(L.PI)
+
+
+def model_desc(model, tables):
+    """Flatten (model, task tables) into the C ``grx_model_desc`` (keeps the numpy arrays alive in ``keep``)."""
+    keep, d = [], L.ModelDesc()
+    order = np.asarray(tables["sph_order"])
+    d.nb, d.nd, d.nl, d.ns = model["nb"], model["nd"], len(model["link_names"]), len(model["sph_rad"])
+    d.nf, d.nterm, d.nankle = len(tables["foot_links"]), len(tables["termination_links"]), len(tables["ankle_dofs"])
+
+    def F(name, arr):
+        a, p = _f32p(arr); keep.append(a); setattr(d, name, p)
+
+    def I(name, arr):
+        a, p = _i32p(arr); keep.append(a); setattr(d, name, p)
+    I("parent", model["parent"])
+    for k in ("jpos", "jrot", "axis", "mass", "com", "inertia", "dof_lower", "dof_upper", "dof_effort", "link_pos", "link_rot"):
+        F(k, model[k])
+    F("dof_vel_limit", model["dof_velocity"])
+    F("soft_lower", tables["soft_lower"]); F("soft_upper", tables["soft_upper"])
+    F("kp", tables["kp"]); F("kd", tables["kd"]); F("default_pos", tables["default_pos"])
+    I("link_body", model["link_body"])
+    I("sph_body", model["sph_body"][order]); I("sph_link", model["sph_link"][order])
+    F("sph_pos", model["sph_pos"][order]); F("sph_rad", model["sph_rad"][order])
+    I("foot_links", tables["foot_links"]); I("term_links", tables["termination_links"]); I("ankle_dofs", tables["ankle_dofs"])
+    d.torso_link = int(tables["torso_links"][0])
+    return d, keep
+
+
+def task_cfg(cfg, tables, seed=1, env_id_offset=0):
+    """The C ``grx_task_cfg`` from a task config (ours or the reference's cfg object): what _parse_cfg
+    (legged_robot.py:91-104), _prepare_reward_function (:840-866) and compute_noise_scale_vec_profile
+    (gr1t1.py:315-336) derive at construction."""
+    t = L.TaskCfg()
+    px = cfg.sim.physx
+    t.sim_dt, t.gravity = cfg.sim.dt, cfg.sim.gravity[2]
+    t.contact_offset, t.bounce_threshold, t.max_depen_vel = px.contact_offset, px.bounce_threshold_velocity, px.max_depenetration_velocity
+    t.erp, t.solver_iters, t.decimation = 0.2, px.num_position_iterations, cfg.control.decimation
+    t.action_scale = cfg.control.action_scale
+    nd = len(tables["kp"])
+    H = len(cfg.terrain.measured_points_x) * len(cfg.terrain.measured_points_y)
+    t.num_obs, t.num_pri_obs, t.num_actions, t.num_height_points = cfg.env.num_obs, cfg.env.num_pri_obs, cfg.env.num_actions, H
+    nz = cfg.normalization
+    for i in range(nd):
+        t.clip_actions_min[i], t.clip_actions_max[i] = float(nz.clip_actions_min[i]), float(nz.clip_actions_max[i])
+    t.clip_observations = nz.clip_observations
+    dt = cfg.control.decimation * cfg.sim.dt
+    t.max_episode_length = float(np.ceil(cfg.env.episode_length_s / dt))
+    t.max_episode_length_s = cfg.env.episode_length_s
+    t.resample_interval = int(cfg.commands.resampling_command_interval_s / dt)
+    r = cfg.commands.ranges
+    for i, rng in enumerate((r.lin_vel_x, r.lin_vel_y, r.ang_vel_yaw)):
+        t.cmd_range[i][0], t.cmd_range[i][1] = rng[0], rng[1]
+    dr = cfg.domain_rand
+    t.max_push_vel_xy = dr.max_push_vel_xy
+    rough = cfg.terrain.mesh_type in ("heightfield", "trimesh")
+    t.add_noise = int(cfg.noise.add_noise)
+    t.randomize_init_dof_pos, t.randomize_init_base_velocity = int(dr.randomize_init_dof_pos), int(dr.randomize_init_base_velocity)
+    t.curriculum, t.custom_origins = int(bool(cfg.terrain.curriculum) and rough), int(rough)
+    t.measure_heights = int(cfg.terrain.measure_heights)
+    ns, os_, nl = cfg.noise.noise_scales, nz.obs_scales, cfg.noise.noise_level
+    nv = np.zeros(9 + 3 * nd)
+    nv[3:6], nv[6:9] = ns.ang_vel * nl * os_.ang_vel, ns.gravity * nl * os_.gravity
+    nv[9:9 + nd], nv[9 + nd:9 + 2 * nd] = ns.dof_pos * nl * os_.dof_pos, ns.dof_vel * nl * os_.dof_vel
+    nv[9 + 2 * nd:] = ns.action * nl * os_.action
+    for i, v in enumerate(nv):
+        t.noise_scale_vec[i] = v
+    t.obs_scale_lin_vel, t.obs_scale_ang_vel, t.obs_scale_gravity = os_.lin_vel, os_.ang_vel, os_.gravity
+    t.obs_scale_dof_pos, t.obs_scale_dof_vel, t.obs_scale_action = os_.dof_pos, os_.dof_vel, os_.action
+    t.obs_scale_height = os_.height_measurements
+    ini = cfg.init_state
+    for i, v in enumerate(list(ini.pos) + list(ini.rot) + list(ini.lin_vel) + list(ini.ang_vel)):
+        t.base_init_state[i] = v
+    for i, v in enumerate(cfg.terrain.measured_points_x):
+        t.measured_points_x[i] = v
+    for i, v in enumerate(cfg.terrain.measured_points_y):
+        t.measured_points_y[i] = v
+    t.n_points_x, t.n_points_y = len(cfg.terrain.measured_points_x), len(cfg.terrain.measured_points_y)
+    t.terrain_env_length = getattr(cfg.terrain, "terrain_length", 8.0)
+    rw = cfg.rewards
+    active = [n for n in sorted(k for k in dir(rw.scales) if not k.startswith("_") and k != "to_dict")
+              if getattr(rw.scales, n) != 0 and n != "termination"]
+    if active != REWARD_NAMES:
+        raise L.GrxError(f"the fused kernel implements exactly the 24 reward terms of the registered GRx tasks; cfg enables {active}")
+    for i, n in enumerate(REWARD_NAMES):
+        t.reward_scale[i] = getattr(rw.scales, n) * dt                                 # legged_robot.py:849-850
+    for k in ("base_height_target", "swing_feet_height_target", "feet_stumble_ratio", "feet_air_time_target",
+              "feet_land_time_max", "soft_dof_vel_limit", "soft_torque_limit"):
+        setattr(t, k, getattr(rw, k))
+    for n in L._SIGMAS:
+        setattr(t, "sigma_" + n, getattr(rw, "sigma_" + n))
+    t.seed, t.env_id_offset = seed, env_id_offset
+    return t
+
+
+class _EpisodeInfo(dict):
+    """extras["episode"] (legged_robot.py:420-427) evaluated lazily from one slot of the device accumulator ring:
+    building 25 0-d tensors eagerly would cost 25+ launches per step for values that are read once per iteration."""
+
+    def __init__(self, slot_view, names, inv_len_s, num_envs_total, curriculum):
+        super().__init__()
+        self._v, self._names, self._s, self._n = slot_view, names, inv_len_s, num_envs_total
+        keys = ["rew_" + n for n in names] + (["terrain_level"] if curriculum else [])
+        for k in keys:
+            dict.__setitem__(self, k, None)
+        self._done = False
+
+    def _fill(self):
+        if not self._done:
+            v = self._v.clone()
+            cnt = torch.clamp(v[24], min=1.0)
+            for i, n in enumerate(self._names):
+                dict.__setitem__(self, "rew_" + n, v[i] / cnt * self._s)
+            if "terrain_level" in self.keys():
+                dict.__setitem__(self, "terrain_level", v[25] / self._n)
+            self._done = True
+
+    def __getitem__(self, k):
+        self._fill()
+        return dict.__getitem__(self, k)
+
+    def items(self):
+        self._fill()
+        return dict.items(self)
+
+    def values(self):
+        self._fill()
+        return dict.values(self)
+
+
+class GRXVecEnv:
+    """Drop-in for ``GR1T1(cfg, sim_params, physics_engine, sim_device, headless)`` as seen by ``OnPolicyRunner`` / play.py."""
+
+    def __init__(self, cfg=None, sim_params=None, physics_engine=None, sim_device="cuda:0", headless=True, *,
+                 rank=0, world_size=1, params=None, terrain=None, env_origins=None, terrain_levels=None, terrain_types=None,
+                 parity_rng=False, sync_extras=False):
+        """cfg: grx_b200.config.make_cfg(...) or the reference's GR1T1LowerLimbCfg()/GR1T2LowerLimbCfg() object
+        (cfg.env.num_envs is the GLOBAL env count; this rank simulates the contiguous block rank*N/W..(rank+1)*N/W).
+        params / terrain / env_origins...: override the sampled per-env parameters (tests)."""
+        if cfg is None:
+            cfg = make_cfg("GR1T1")
+        if not torch.cuda.is_available():
+            raise L.GrxError("GRXVecEnv needs a CUDA device (no CPU fallback)")
+        self.lib = L.lib()
+        self.cfg = cfg
+        self.headless = headless
+        self.device = torch.device(sim_device)
+        self.rank, self.world_size = rank, world_size
+        n_total = int(cfg.env.num_envs)
+        assert n_total % world_size == 0, "num_envs must divide evenly over ranks"
+        self.num_envs_total, self.num_envs = n_total, n_total // world_size
+        self.env_id_offset = rank * self.num_envs
+        self.num_obs, self.num_pri_obs, self.num_actions = cfg.env.num_obs, cfg.env.num_pri_obs, cfg.env.num_actions
+        self.num_privileged_obs = self.num_pri_obs
+        robot = getattr(cfg, "robot", None) or ("GR1T2" if "GR1T2" in getattr(cfg.asset, "file", getattr(cfg.asset, "name", "")) else "GR1T1")
+        self.model = builtin_model(robot)
+        self.tables = task_tables(self.model, cfg)
+        self.sim_dt = cfg.sim.dt
+        self.dt = cfg.control.decimation * cfg.sim.dt                                  # legged_robot.py:92
+        self.max_episode_length_s = cfg.env.episode_length_s
+        self.max_episode_length = np.ceil(self.max_episode_length_s / self.dt)         # legged_robot.py:101 (numpy float)
+        self.push_interval = np.ceil(cfg.domain_rand.push_interval_s / self.dt)        # legged_robot.py:103
+        rough = cfg.terrain.mesh_type in ("heightfield", "trimesh")
+        if not rough:
+            cfg.terrain.curriculum = False                                              # legged_robot.py:97-98
+        self.custom_origins = rough
+        seed = int(getattr(cfg, "seed", 1))
+        self.parity_rng, self.sync_extras = parity_rng, sync_extras
+        self.reward_names = list(REWARD_NAMES)
+        N = self.num_envs
+
+        # ---- terrain (legged_robot.py:513-526) — every rank builds the same grid from the same numpy seed
+        self.terrain = None
+        if rough and terrain is None:
+            st = np.random.get_state()
+            np.random.seed(seed)
+            self.terrain = Terrain(cfg.terrain, n_total)
+            np.random.set_state(st)
+            terrain = dict(heights=self.terrain.heightsamples, terrain_origins=self.terrain.env_origins)
+        # ---- env origins (legged_robot.py:1163-1195), keyed by GLOBAL env index
+        g = np.random.default_rng(seed + 7919)
+        if rough:
+            t_org = np.asarray(terrain["terrain_origins"], np.float32)
+            rows, cols = t_org.shape[:2]
+            if terrain_levels is None:
+                max_init = cfg.terrain.max_init_terrain_level if cfg.terrain.curriculum else rows - 1
+                terrain_levels = g.integers(0, max_init + 1, n_total)[self.env_id_offset:self.env_id_offset + N]
+            if terrain_types is None:
+                gi = np.arange(self.env_id_offset, self.env_id_offset + N)
+                terrain_types = np.floor(gi / (n_total / cols)).astype(np.int64)
+            if env_origins is None:
+                env_origins = t_org[np.asarray(terrain_levels), np.asarray(terrain_types)]
+        elif env_origins is None:
+            ncol = np.floor(np.sqrt(n_total))
+            gi = np.arange(self.env_id_offset, self.env_id_offset + N)
+            env_origins = np.zeros((N, 3), np.float32)
+            env_origins[:, 0] = cfg.env.env_spacing * (gi // ncol)
+            env_origins[:, 1] = cfg.env.env_spacing * (gi % ncol)
+        # ---- per-env physical parameters (legged_robot.py:538-648, 1060-1064)
+        if params is None:
+            full = sample_domain_rand(self.model, cfg, n_total, np.random.default_rng(seed + 104729))
+            params = {k: v[self.env_id_offset:self.env_id_offset + N] for k, v in full.items()}
+        self.params = params
+
+        # ---- C objects
+        self._md, self._keep = model_desc(self.model, self.tables)
+        self._tc = task_cfg(cfg, self.tables, seed=seed, env_id_offset=self.env_id_offset)
+        self._h = C.c_void_p()
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        L.check(self.lib.grx_env_create(C.byref(self._md), C.byref(self._tc), N, dev_index, C.byref(self._h)))
+        tc = cfg.terrain
+        if rough:
+            hs = np.ascontiguousarray(terrain["heights"], np.int16)
+            L.check(self.lib.grx_env_set_terrain_heightfield(self._h, hs.ctypes.data_as(C.POINTER(C.c_int16)), hs.shape[0], hs.shape[1],
+                                                             C.c_float(tc.horizontal_scale), C.c_float(tc.vertical_scale),
+                                                             C.c_float(tc.border_size), C.c_float(tc.static_friction), C.c_float(tc.restitution)))
+        else:
+            L.check(self.lib.grx_env_set_terrain_plane(self._h, C.c_float(tc.static_friction), C.c_float(tc.restitution)))
+        fr, p_fr = _f32p(params["friction"]); rs, p_rs = _f32p(params["restitution"])
+        ms, p_ms = _f32p(params["motor_strength"]); bi, p_bi = _f32p(params["base_inertial"])
+        eo, p_eo = _f32p(env_origins)
+        if rough:
+            lv, p_lv = _i32p(terrain_levels); ty, p_ty = _i32p(terrain_types)
+            to, p_to = _f32p(t_org)
+            L.check(self.lib.grx_env_set_params(self._h, p_fr, p_rs, p_ms, p_bi, p_eo, p_lv, p_ty, p_to, t_org.shape[0], t_org.shape[1]))
+            self.terrain_origins = torch.from_numpy(to.copy()).to(self.device)
+            self.max_terrain_level = t_org.shape[0]
+        else:
+            L.check(self.lib.grx_env_set_params(self._h, p_fr, p_rs, p_ms, p_bi, p_eo, None, None, None, 0, 0))
+
+        # ---- zero-copy views (legged_robot.py:106-203)
+        v = self._view
+        self.root_states, self.dof_pos, self.dof_vel = v("root_states"), v("dof_pos"), v("dof_vel")
+        self.last_dof_vel, self.last_actions, self.last_last_actions = v("last_dof_vel"), v("last_actions"), v("last_last_actions")
+        self.commands, self.base_heights_offset = v("commands"), v("base_heights_offset")
+        self.feet_air_time, self.feet_land_time, self.feet_contact_last = v("feet_air_time"), v("feet_land_time"), v("feet_contact_last")
+        self._episode_length = v("episode_length").squeeze(1)
+        self.terrain_levels, self.terrain_types = v("terrain_levels").squeeze(1), v("terrain_types").squeeze(1)
+        self.env_origins, self.episode_sums_buf = v("env_origins"), v("episode_sums")
+        self.obs_buf, self.pri_obs_buf, self.rew_buf = v("obs"), v("pri_obs"), v("rew")
+        self.privileged_obs_buf = self.pri_obs_buf
+        self._reset_u8, self._time_out_u8 = v("reset"), v("time_out")
+        self.reset_buf, self.time_out_buf = self._reset_u8.view(torch.bool), self._time_out_u8.view(torch.bool)
+        self.torques, self.contact_forces, self.foot_state = v("torques"), v("contact_forces"), v("foot_state")
+        self.records, self._accum = v("records"), v("episode_accum")
+        self.base_quat = self.root_states[:, 3:7]
+        self.feet_indices = torch.tensor(self.tables["foot_links"], device=self.device)
+        self.default_dof_pos = torch.tensor(self.tables["default_pos"], dtype=torch.float32, device=self.device).unsqueeze(0)
+        self.commands_scale = torch.ones(N, 3, device=self.device)
+        self.extras = {}
+        self.common_step_counter = 0
+        self._step_index = 0
+        self._delay_rng = np.random.default_rng(seed + 15485863)
+        self._zero_actions = torch.zeros(N, self.num_actions, device=self.device)
+        self.init_done = True
+
+    # ------------------------------------------------------------------ plumbing
+    def _view(self, name):
+        b = L.Buffer()
+        L.check(self.lib.grx_env_get_buffer(self._h, name.encode(), C.byref(b)))
+        return torch.as_tensor(_DevArray(b, self), device=self.device)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @property
+    def episode_length_buf(self):
+        return self._episode_length
+
+    @episode_length_buf.setter
+    def episode_length_buf(self, value):   # OnPolicyRunner.learn assigns a new tensor (on_policy_runner.py:125-127)
+        self._episode_length.copy_(torch.as_tensor(value).to(self._episode_length.dtype))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.grx_env_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ VecEnv surface
+    def get_observations(self):                                                        # base_task.py:107-108
+        return self.obs_buf
+
+    def get_privileged_observations(self):                                             # base_task.py:110-111
+        return self.pri_obs_buf
+
+    def reset_idx(self, env_ids, U=None):                                              # legged_robot.py:377-440
+        ids = torch.as_tensor(env_ids, device=self.device).to(torch.int32).contiguous()
+        if ids.numel() == 0:
+            return
+        pU = C.c_void_p(U.data_ptr()) if U is not None else None
+        self._step_index += 1
+        L.check(self.lib.grx_env_reset_idx(self._h, C.c_void_p(ids.data_ptr()), ids.numel(), pU, int(self.init_done),
+                                           C.c_uint64(self._step_index), self._stream()))
+        self._publish_extras(True)
+
+    def reset(self):                                                                   # base_task.py:117-121
+        self.reset_idx(torch.arange(self.num_envs, device=self.device))
+        obs, pri, _, _, _ = self.step(self._zero_actions)
+        return obs, pri
+
+    def sample_delay(self):
+        """legged_robot_fftai.py:53-54: one N(5, 2) draw per step shared by all envs, clamped at 0 (host RNG in the reference too)."""
+        return max(0.0, float(self._delay_rng.normal(5.0, 2.0)))
+
+    def step(self, actions, U=None, delay=None):                                       # legged_robot.py:222-246
+        """actions [N, num_actions] fp32 on this env's device.  U / delay: parity-mode overrides (tests)."""
+        a = actions if (actions.dtype == torch.float32 and actions.is_contiguous()) else actions.float().contiguous()
+        if delay is None:
+            delay = self.sample_delay()
+        self.common_step_counter += 1                                                   # legged_robot.py:281
+        push = int(bool(self.cfg.domain_rand.push_robots) and (self.common_step_counter % self.push_interval == 0))
+        self._step_index += 1
+        pU = C.c_void_p(U.data_ptr()) if U is not None else None
+        L.check(self.lib.grx_env_step(self._h, C.c_void_p(a.data_ptr()), pU, C.c_float(delay), push,
+                                      C.c_uint64(self._step_index), self._stream()))
+        self._publish_extras(False)
+        return self.obs_buf, self.pri_obs_buf, self.rew_buf, self.reset_buf, self.extras
+
+    def _publish_extras(self, from_reset):
+        slot = int(self.lib.grx_env_accum_slot(self._h))
+        if self.sync_extras:   # reference-exact staleness: rebuild only when something reset; costs a host sync
+            if not from_reset and not bool(self._reset_u8.any()):
+                return
+        self.extras["episode"] = _EpisodeInfo(self._accum[slot], self.reward_names, 1.0 / self.max_episode_length_s,
+                                              float(self.num_envs), bool(self.cfg.terrain.curriculum))
+        if self.cfg.env.send_timeouts:
+            self.extras["time_outs"] = self.time_out_buf
+
+    # ------------------------------------------------------------------ state in/out (tests, checkpointing of env state)
+    CARRIED = ("root_states", "dof_pos", "dof_vel", "last_dof_vel", "last_actions", "last_last_actions", "commands",
+               "base_heights_offset", "feet_air_time", "feet_land_time", "feet_contact_last")
+
+    def load_state(self, d):
+        for k in self.CARRIED:
+            dst = getattr(self, k)
+            dst.copy_(torch.as_tensor(np.asarray(d[k]).astype(np.float32)).reshape(dst.shape).to(self.device))
+        self._episode_length.copy_(torch.as_tensor(np.asarray(d["episode_length_buf"]).astype(np.int32)).to(self.device))
+        self.episode_sums_buf.copy_(torch.as_tensor(np.asarray(d["episode_sums"], np.float32)).to(self.device))
+        self.common_step_counter = int(d["common_step_counter"])
+        if self.custom_origins and "terrain_levels" in d:
+            self.terrain_levels.copy_(torch.as_tensor(np.asarray(d["terrain_levels"]).astype(np.int32)).to(self.device))
+            self.env_origins.copy_(torch.as_tensor(np.asarray(d["env_origins"], np.float32)).to(self.device))
+
+    def post_physics_injected(self, actions, U, inj):
+        """Test entry (grx_env_post_physics): run only the post-physics half on injected physics outputs."""
+        ip = L.InjectedPhysics()
+        keep = {}
+        for k in ("torques", "foot_state", "torso_quat", "contact_forces", "avg_foot_force", "avg_foot_linvel"):
+            keep[k] = inj[k].to(self.device, torch.float32).contiguous()
+            setattr(ip, k, keep[k].data_ptr())
+        self.common_step_counter += 1
+        push = int(bool(self.cfg.domain_rand.push_robots) and (self.common_step_counter % self.push_interval == 0))
+        self._step_index += 1
+        a = actions.to(self.device, torch.float32).contiguous()
+        L.check(self.lib.grx_env_post_physics(self._h, C.c_void_p(a.data_ptr()), C.c_void_p(U.data_ptr()) if U is not None else None,
+                                              C.byref(ip), push, C.c_uint64(self._step_index), self._stream()))
+        torch.cuda.synchronize(self.device)
+        self._publish_extras(False)
+        return self.obs_buf, self.pri_obs_buf, self.rew_buf, self.reset_buf, self.extras
+
+    def debug_dynamics(self, index):
+        nv = self.model["nd"] + 6
+        M, h = np.zeros((nv, nv), np.float32), np.zeros(nv, np.float32)
+        L.check(self.lib.grx_env_debug_dynamics(self._h, index, M.ctypes.data_as(L.PF), h.ctypes.data_as(L.PF)))
+        return M, h
