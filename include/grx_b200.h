@@ -103,7 +103,7 @@ typedef struct grx_env grx_env;
 
 const char *grx_last_error(void);
 int grx_version(void);
-/* sizeof() of {grx_buffer, grx_model_desc, grx_task_cfg, grx_injected_physics}, for FFI bindings to self-check their layouts */
+/* sizeof() of {grx_buffer, grx_model_desc, grx_task_cfg, grx_injected_physics, grx_ppo_cfg}, for FFI bindings to self-check their layouts */
 int grx_abi_sizes(int32_t *out, int32_t n);
 
 /* ---- environment -------------------------------------------------------------------------------------------- */

@@ -1495,8 +1495,8 @@ extern "C" int grx_env_debug_dynamics(grx_env *e, int32_t index, float *h_M, flo
 
 // ABI self-check for foreign-function bindings: sizes of the public structs
 extern "C" int grx_abi_sizes(int32_t *out, int32_t n) {
-    const int32_t v[4] = {(int32_t)sizeof(grx_buffer), (int32_t)sizeof(grx_model_desc), (int32_t)sizeof(grx_task_cfg),
-                          (int32_t)sizeof(grx_injected_physics)};
-    for (int i = 0; i < n && i < 4; i++) out[i] = v[i];
-    return 4;
+    const int32_t v[5] = {(int32_t)sizeof(grx_buffer), (int32_t)sizeof(grx_model_desc), (int32_t)sizeof(grx_task_cfg),
+                          (int32_t)sizeof(grx_injected_physics), (int32_t)sizeof(grx_ppo_cfg)};
+    for (int i = 0; i < n && i < 5; i++) out[i] = v[i];
+    return 5;
 }

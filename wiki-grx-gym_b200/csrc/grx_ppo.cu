@@ -1,0 +1,768 @@
+// grx_ppo.cu — the rsl_rl side of the hot path for sm_100a (C ABI in include/grx_b200.h):
+//   ActorCriticMLP forward (rollout + update), GAE reverse scan (warp-shuffle linear-recurrence scan), the PPO
+//   clipped-surrogate / clipped-value / entropy loss with its hand-derived backward, global-norm clip + Adam with the
+//   adaptive-KL learning rate decided on the device (the reference syncs with .item() three times per minibatch,
+//   ppo.py:264, 308-309).  Reference arithmetic: rsl_rl/rsl_rl/algorithms/ppo.py:144-321,
+//   storage/base_storage.py:80-141, storage/rollout_storage.py:63-112, modules/actor_critic_mlp.py:160-231,
+//   modules/mlp.py:7-42.  oracle/ppo_oracle.py is the CPU statement of the same equations.
+//
+// Dense layers: gemm_kernel (fp32 SIMT, any shape) or, for the 128-aligned hidden layers when
+// cfg.use_tensor_cores != 0, the tcgen05 kind::tf32 kernels in grx_gemm_tc.cuh.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "grx_b200.h"
+
+int grx_set_error(int code, const std::string &msg);   // grx_env.cu
+
+#define CK(call)                                                                                             \
+    do {                                                                                                     \
+        cudaError_t err__ = (call);                                                                          \
+        if (err__ != cudaSuccess)                                                                            \
+            return grx_set_error(GRX_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(err__));        \
+    } while (0)
+
+namespace {
+
+constexpr int MAXA = 32;          // max action dim
+constexpr int TAIL = 8;           // reduce_buf tail: [kl_sum, count, surrogate_sum, value_loss_sum, 0...]
+constexpr float LOG_SQRT_2PI = 0.91893853320467274178f;
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ float elu(float x) { return x > 0.f ? x : expm1f(x); }          // nn.ELU(alpha=1)
+__device__ __forceinline__ float elu_grad_from_out(float h) { return h > 0.f ? 1.f : h + 1.f; }   // ELU'(z) = e^z = h + 1 for z <= 0
+
+// =========================================================================================================
+// fp32 SIMT GEMM, C[m,n] (+)= sum_k A(m,k) B(k,n), 64x64x16 tiles, 256 threads, 4x4 outputs per thread.
+//   A_KC: A(m,k) = A[m*lda + k] (contraction index contiguous) else A[k*lda + m]
+//   B_KC: B(k,n) = B[n*ldb + k]                                else B[k*ldb + n]
+// Epilogues: 0 C = acc + bias[n]; 1 C = elu(acc + bias[n]); 2 C = acc * ELU'(aux[m,n]) ; 3 split-K: atomicAdd(C, acc) and
+// (n-tile 0 only) bias_out[m] += sum_k A(m,k)   [dW = dY^T H with db = column sums of dY in the same pass]
+// =========================================================================================================
+struct GemmArgs {
+    const float *A, *B;
+    float *C;
+    const float *bias;   // epi 0/1
+    const float *aux;    // epi 2 (same layout as C)
+    float *bias_out;     // epi 3
+    int M, N, K, lda, ldb, ldc, kchunk;
+};
+
+constexpr int BM = 64, BN = 64, BK = 16;
+
+template <bool A_KC, bool B_KC, int EPI>
+__global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs g) {
+    __shared__ __align__(16) float As[BK][BM + 4];
+    __shared__ __align__(16) float Bs[BK][BN + 4];
+    const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int kbeg = blockIdx.z * g.kchunk, kend = min(g.K, kbeg + g.kchunk);
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+    float bsum = 0.f;
+    for (int k0 = kbeg; k0 < kend; k0 += BK) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int idx = t + i * 256;
+            {
+                const int m = A_KC ? idx / BK : idx % BM, k = A_KC ? idx % BK : idx / BM;
+                const int gm = m0 + m, gk = k0 + k;
+                float v = 0.f;
+                if (gm < g.M && gk < kend) v = A_KC ? g.A[(size_t)gm * g.lda + gk] : g.A[(size_t)gk * g.lda + gm];
+                As[k][m] = v;
+            }
+            {
+                const int n = B_KC ? idx / BK : idx % BN, k = B_KC ? idx % BK : idx / BN;
+                const int gn = n0 + n, gk = k0 + k;
+                float v = 0.f;
+                if (gn < g.N && gk < kend) v = B_KC ? g.B[(size_t)gn * g.ldb + gk] : g.B[(size_t)gk * g.ldb + gn];
+                Bs[k][n] = v;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; k++) {
+            const float4 a = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4 *>(&Bs[k][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (EPI == 3 && blockIdx.x == 0 && t < BM) {
+#pragma unroll
+            for (int k = 0; k < BK; k++) bsum += As[k][t];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= g.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= g.N) continue;
+            const size_t o = (size_t)m * g.ldc + n;
+            if (EPI == 0) g.C[o] = acc[i][j] + g.bias[n];
+            else if (EPI == 1) g.C[o] = elu(acc[i][j] + g.bias[n]);
+            else if (EPI == 2) g.C[o] = acc[i][j] * elu_grad_from_out(g.aux[o]);
+            else atomicAdd(&g.C[o], acc[i][j]);
+        }
+    }
+    if (EPI == 3 && blockIdx.x == 0 && t < BM && m0 + t < g.M) atomicAdd(&g.bias_out[m0 + t], bsum);
+}
+
+template <bool A_KC, bool B_KC, int EPI>
+void launch_gemm(const GemmArgs &g, int splits, cudaStream_t st) {
+    GemmArgs a = g;
+    a.kchunk = ((g.K + splits - 1) / splits + BK - 1) / BK * BK;
+    const int z = (g.K + a.kchunk - 1) / a.kchunk;
+    dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, z);
+    gemm_kernel<A_KC, B_KC, EPI><<<grid, 256, 0, st>>>(a);
+}
+
+// =========================================================================================================
+// Philox4x32-10 + Box-Muller for the rollout's Normal.sample() in fast mode (actor_critic_mlp.py:192-194)
+// =========================================================================================================
+__device__ __forceinline__ void philox4(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t *out) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// PPO.act tail (ppo.py:150-171, base_storage.py:80-100): a = mu + sigma * eps, log-prob, and the transition's row of the
+// rollout storage (obs, critic_obs, actions, values, log-prob, mu, sigma).  One thread per env.
+struct ActArgs {
+    const float *obs, *critic_obs, *mu, *value, *std, *eps;
+    float *actions_out;
+    float *s_obs, *s_cobs, *s_act, *s_val, *s_logp, *s_mu, *s_sigma;   // storage rows of step t
+    int N, O, P, A;
+    uint64_t seed, step_index;
+    int env_id_offset;
+};
+__global__ void act_sample_store_kernel(const ActArgs a) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < a.N) {
+        float lp = 0.f;
+        for (int j0 = 0; j0 < a.A; j0 += 4) {
+            float z[4];
+            if (a.eps) {
+                for (int r = 0; r < 4; r++) z[r] = j0 + r < a.A ? a.eps[(size_t)n * a.A + j0 + r] : 0.f;
+            } else {
+                uint32_t rnd[4];
+                philox4((uint32_t)a.seed ^ 0x2545F491u, (uint32_t)(a.seed >> 32), (uint32_t)(a.env_id_offset + n), (uint32_t)a.step_index,
+                        (uint32_t)(a.step_index >> 32), (uint32_t)(j0 >> 2), rnd);
+                for (int r = 0; r < 4; r += 2) {   // Box-Muller on (0,1] x [0,1)
+                    const float u1 = ((float)(rnd[r] >> 8) + 1.0f) * (1.0f / 16777216.0f), u2 = (float)(rnd[r + 1] >> 8) * (1.0f / 16777216.0f);
+                    const float rad = sqrtf(-2.0f * logf(u1));
+                    float sn, cs;
+                    sincospif(2.0f * u2, &sn, &cs);
+                    z[r] = rad * cs; z[r + 1] = rad * sn;
+                }
+            }
+            for (int r = 0; r < 4 && j0 + r < a.A; r++) {
+                const int j = j0 + r;
+                const float mu = a.mu[(size_t)n * a.A + j], sg = a.std[j];                          // sigma = mu * 0 + std (ACM:179-181)
+                const float act = mu + sg * z[r];
+                const float d = act - mu;
+                lp += -(d * d) / (2.f * sg * sg) - logf(sg) - LOG_SQRT_2PI;                           // ACM:205
+                a.actions_out[(size_t)n * a.A + j] = act;
+                a.s_act[(size_t)n * a.A + j] = act; a.s_mu[(size_t)n * a.A + j] = mu; a.s_sigma[(size_t)n * a.A + j] = sg;
+            }
+        }
+        a.s_logp[n] = lp;
+        a.s_val[n] = a.value[n];
+    }
+    // coalesced copies of the observation rows into the storage (grid-stride over the flat arrays)
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = tid; i < (size_t)a.N * a.O; i += nth) a.s_obs[i] = a.obs[i];
+    for (size_t i = tid; i < (size_t)a.N * a.P; i += nth) a.s_cobs[i] = a.critic_obs[i];
+}
+
+// PPO.process_env_step (ppo.py:186-194): r += gamma * V * time_out; store rewards / dones of step t
+__global__ void process_env_step_kernel(const float *rew, const uint8_t *dones, const uint8_t *time_outs, const float *values, float gamma,
+                                        float *s_rew, uint8_t *s_done, int N) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float r = rew[n];
+    if (time_outs) r += gamma * (values[n] * (time_outs[n] ? 1.f : 0.f));
+    s_rew[n] = r;
+    s_done[n] = dones[n] ? 1 : 0;
+}
+
+// =========================================================================================================
+// GAE (base_storage.py:120-141).  A_t = delta_t + c_t A_{t+1} is a linear recurrence; composing the affine maps
+// f_t(x) = delta_t + c_t x is associative, so the reverse scan over T runs as a warp-shuffle scan: one warp per env,
+// lane l owns the time steps of chunk l (T / 32 consecutive steps), tiles of 32 envs are transposed through shared
+// memory so that HBM reads / writes stay coalesced along the env axis.  Also accumulates sum / sum of squares of the
+// raw advantages (double) for the global normalisation.
+// =========================================================================================================
+constexpr int GAE_TMAX = 256;
+__global__ void __launch_bounds__(1024) gae_kernel(const float *rew, const uint8_t *dones, const float *values, const float *last_values,
+                                                   float gamma, float lam, float *returns, float *adv, double *moments, int T, int N) {
+    extern __shared__ float gae_smem[];   // 3 x [T][33]
+    float (*s_d)[33] = reinterpret_cast<float (*)[33]>(gae_smem);
+    float (*s_c)[33] = s_d + T;
+    float (*s_v)[33] = s_c + T;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, n0 = blockIdx.x * 32;
+    const int nw = blockDim.x >> 5;
+    for (int t = w; t < T; t += nw) {   // coalesced along n: delta_t and c_t per (t, n)
+        const int n = n0 + lane;
+        if (n < N) {
+            const float v = values[(size_t)t * N + n];
+            const float nv = t == T - 1 ? last_values[n] : values[(size_t)(t + 1) * N + n];
+            const float nt = 1.0f - (dones[(size_t)t * N + n] ? 1.f : 0.f);
+            s_d[t][lane] = rew[(size_t)t * N + n] + nt * gamma * nv - v;
+            s_c[t][lane] = nt * gamma * lam;
+            s_v[t][lane] = v;
+        }
+    }
+    __syncthreads();
+    double sum = 0.0, sq = 0.0;
+    for (int e = w; e < 32; e += nw) {   // warp e scans env n0 + e; lane l owns steps [l*per, (l+1)*per)
+        if (n0 + e >= N) continue;
+        const int per = (T + 31) / 32, tb = lane * per, te = min(T, tb + per);
+        // compose the chunk's maps from its last step backwards: A_tb = D + C * A_te
+        float D = 0.f, Cc = 1.f;
+        for (int t = te - 1; t >= tb; t--) { D = s_d[t][e] + s_c[t][e] * D; Cc = s_c[t][e] * Cc; }
+        // exclusive reverse scan over lanes: incoming A for lane l = A_{te(l)} = composition of lanes l+1.. applied to 0
+        float sd = D, sc = Cc;   // inclusive suffix composition
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float od = __shfl_down_sync(FULL, sd, o), oc = __shfl_down_sync(FULL, sc, o);
+            if (lane + o < 32) { sd = sd + sc * od; sc = sc * oc; }
+        }
+        float a = __shfl_down_sync(FULL, sd, 1);
+        if (lane == 31) a = 0.f;
+        for (int t = te - 1; t >= tb; t--) {
+            a = s_d[t][e] + s_c[t][e] * a;
+            s_d[t][e] = a;   // raw advantage; returns = a + v
+            sum += (double)a; sq += (double)a * (double)a;
+        }
+    }
+    __syncthreads();
+    for (int t = w; t < T; t += nw) {
+        const int n = n0 + lane;
+        if (n < N) {
+            const float a = s_d[t][lane];
+            returns[(size_t)t * N + n] = a + s_v[t][lane];
+            adv[(size_t)t * N + n] = (a + s_v[t][lane]) - s_v[t][lane];   // advantages = returns - values (BS:140)
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { sum += __shfl_xor_sync(FULL, sum, o); sq += __shfl_xor_sync(FULL, sq, o); }
+    if (lane == 0) { atomicAdd(&moments[0], sum); atomicAdd(&moments[1], sq); }
+    if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(&moments[2], (double)T * (double)N);
+}
+// (A - mean) / (unbiased std + 1e-8) over all T*N (BS:141), moments = [sum, sum of squares, count] (all-reduced by the caller when sharded)
+__global__ void normalize_adv_kernel(float *adv, const double *moments, size_t n) {
+    const double cnt = moments[2], mean = moments[0] / cnt;
+    const double var = fmax((moments[1] - cnt * mean * mean) / (cnt - 1.0), 0.0);
+    const float m = (float)mean, inv = 1.0f / ((float)sqrt(var) + 1e-8f);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) adv[i] = (adv[i] - m) * inv;
+}
+
+// =========================================================================================================
+// Minibatch gather (rollout_storage.py:77-112): rows d_indices[mb*B + r] of the flat [T*N, .] storage
+// =========================================================================================================
+struct GatherArgs {
+    const int64_t *indices;
+    const int *mb_counter;   // device-side minibatch index (so the same CUDA graph replays for every minibatch), or NULL
+    int mb, nmb, B, O, P, A;
+    const float *s_obs, *s_cobs, *s_act, *s_val, *s_ret, *s_adv, *s_logp, *s_mu, *s_sigma;
+    float *xa, *xc, *act, *val, *ret, *adv, *logp, *mu, *sigma;
+};
+__global__ void gather_kernel(const GatherArgs g) {
+    const int mb = g.mb_counter ? (*g.mb_counter % g.nmb) : g.mb;
+    const int64_t *idx = g.indices + (size_t)mb * g.B;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, nwarp = (gridDim.x * blockDim.x) >> 5;
+    for (int r = warp; r < g.B; r += nwarp) {
+        const size_t s = (size_t)idx[r];
+        for (int i = lane; i < g.O; i += 32) g.xa[(size_t)r * g.O + i] = g.s_obs[s * g.O + i];
+        for (int i = lane; i < g.P; i += 32) g.xc[(size_t)r * g.P + i] = g.s_cobs[s * g.P + i];
+        for (int i = lane; i < g.A; i += 32) {
+            g.act[(size_t)r * g.A + i] = g.s_act[s * g.A + i];
+            g.mu[(size_t)r * g.A + i] = g.s_mu[s * g.A + i];
+            g.sigma[(size_t)r * g.A + i] = g.s_sigma[s * g.A + i];
+        }
+        if (lane == 0) { g.val[r] = g.s_val[s]; g.ret[r] = g.s_ret[s]; g.adv[r] = g.s_adv[s]; g.logp[r] = g.s_logp[s]; }
+    }
+}
+
+// =========================================================================================================
+// PPO losses + their gradients w.r.t. the network outputs (ppo.py:246-295; backward as in oracle/ppo_oracle.py)
+//   per row: log-prob, ratio, clipped surrogate, clipped value loss, KL(old || new); outputs dmu [B,A], dv [B];
+//   block-reduced sums -> tail[kl_sum, count, surrogate_sum, value_loss_sum] and grad(std)
+// =========================================================================================================
+struct LossArgs {
+    const float *mu, *v, *std;                                   // new policy outputs
+    const float *act, *old_mu, *old_sigma, *old_logp, *adv, *ret, *old_v;
+    float *dmu, *dv, *gstd, *tail;
+    int B, A;
+    float clip, vcoef, ecoef;
+    int clipped_value;
+};
+__global__ void __launch_bounds__(256) ppo_loss_kernel(const LossArgs a) {
+    __shared__ float red[8][MAXA + 4];
+    const int r = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float kl = 0.f, surr = 0.f, vl = 0.f, cnt = 0.f;
+    float gs[MAXA];
+#pragma unroll
+    for (int j = 0; j < MAXA; j++) gs[j] = 0.f;
+    if (r < a.B) {
+        const float invB = 1.0f / (float)a.B;
+        float lp = 0.f;
+        for (int j = 0; j < a.A; j++) {
+            const float mu = a.mu[(size_t)r * a.A + j], sg = a.std[j], d = a.act[(size_t)r * a.A + j] - mu;
+            lp += -(d * d) / (2.f * sg * sg) - logf(sg) - LOG_SQRT_2PI;
+            const float os = a.old_sigma[(size_t)r * a.A + j], om = a.old_mu[(size_t)r * a.A + j];
+            kl += logf(sg / os + 1.0e-5f) + (os * os + (om - mu) * (om - mu)) / (2.0f * sg * sg) - 0.5f;   // ppo.py:257-261
+        }
+        const float A_ = a.adv[r];
+        const float ratio = expf(lp - a.old_logp[r]);
+        const float s1 = -A_ * ratio, s2 = -A_ * fminf(fmaxf(ratio, 1.0f - a.clip), 1.0f + a.clip);
+        surr = fmaxf(s1, s2);                                                                            // ppo.py:271-277
+        const bool use1 = s1 >= s2, in_clip = ratio >= 1.0f - a.clip && ratio <= 1.0f + a.clip;
+        const float dratio = (use1 || in_clip ? -A_ : 0.f) * invB;
+        const float dlp = dratio * ratio;
+        for (int j = 0; j < a.A; j++) {
+            const float mu = a.mu[(size_t)r * a.A + j], sg = a.std[j], d = a.act[(size_t)r * a.A + j] - mu;
+            a.dmu[(size_t)r * a.A + j] = dlp * d / (sg * sg);
+            gs[j] = dlp * (d * d / (sg * sg * sg) - 1.0f / sg);
+        }
+        const float v = a.v[r], R = a.ret[r], V0 = a.old_v[r];
+        float dv;
+        if (a.clipped_value) {                                                                           // ppo.py:280-285
+            const float vc = V0 + fminf(fmaxf(v - V0, -a.clip), a.clip);
+            const float l1 = (v - R) * (v - R), l2 = (vc - R) * (vc - R);
+            vl = fmaxf(l1, l2);
+            const bool inc = (v - V0) >= -a.clip && (v - V0) <= a.clip;
+            dv = l1 >= l2 ? 2.f * (v - R) : (inc ? 2.f * (vc - R) : 0.f);
+        } else {
+            vl = (R - v) * (R - v);
+            dv = -2.f * (R - v);
+        }
+        a.dv[r] = dv * (a.vcoef * invB);
+        cnt = 1.f;
+    }
+    // block reduction: 4 scalars + A std-gradients
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        kl += __shfl_xor_sync(FULL, kl, o); surr += __shfl_xor_sync(FULL, surr, o);
+        vl += __shfl_xor_sync(FULL, vl, o); cnt += __shfl_xor_sync(FULL, cnt, o);
+    }
+    for (int j = 0; j < a.A; j++) {
+        float x = gs[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+        if (lane == 0) red[w][4 + j] = x;
+    }
+    if (lane == 0) { red[w][0] = kl; red[w][1] = cnt; red[w][2] = surr; red[w][3] = vl; }
+    __syncthreads();
+    if (threadIdx.x < 4 + a.A) {
+        float x = 0.f;
+        for (int k = 0; k < 8; k++) x += red[k][threadIdx.x];
+        if (threadIdx.x < 4) atomicAdd(&a.tail[threadIdx.x], x);
+        else {
+            const int j = threadIdx.x - 4;
+            if (blockIdx.x == 0) x += -a.ecoef * (1.0f / a.std[j]);   // d(-c_e * mean entropy)/d std_j, once per rank
+            atomicAdd(&a.gstd[j], x);
+        }
+    }
+}
+
+// =========================================================================================================
+// apply: grad-norm -> control block (adaptive LR from KL, NaN skip, clip coefficient, Adam bias corrections) -> Adam
+// =========================================================================================================
+struct Ctl {            // device control block
+    float lr;           // current learning rate (persistent)
+    float coef;         // clip coefficient / world_size for this step
+    int skip;           // NaN loss -> skip the optimiser step (ppo.py:297-299)
+    int step;           // Adam step counter (persistent, shared by all parameters)
+    float bc1, bc2s;    // 1 - beta1^t, sqrt(1 - beta2^t)
+    float kl_mean, loss, value_loss, surrogate_loss, grad_norm;
+    float sum_value_loss, sum_surrogate_loss;   // accumulated over the update (ppo.py:308-309)
+    int mb_counter;     // minibatches processed in this update (device-side so a replayed graph advances by itself)
+    double sumsq;       // scratch: sum of squares of the gradient
+};
+__global__ void gradnorm_kernel(const float *g, int n, Ctl *ctl) {
+    float s = 0.f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += g[i] * g[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+    __shared__ float red[32];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float x = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+        if (threadIdx.x == 0) atomicAdd(&ctl->sumsq, (double)x);
+    }
+}
+struct PrepArgs {
+    Ctl *ctl;
+    const float *tail, *std;
+    int A, adaptive, world_size;
+    float desired_kl, lr_min, lr_max, max_grad_norm, vcoef, ecoef;
+};
+__global__ void prep_apply_kernel(const PrepArgs a) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    Ctl &c = *a.ctl;
+    const float cnt = a.tail[1];
+    const float kl_mean = a.tail[0] / cnt;
+    if (a.adaptive) {                                                                  // ppo.py:262-268, 207-213
+        if (kl_mean > a.desired_kl * 2.0f) c.lr = fmaxf(a.lr_min, c.lr / 1.5f);
+        else if (kl_mean < a.desired_kl / 2.0f && kl_mean > 0.0f) c.lr = fminf(a.lr_max, c.lr * 1.5f);
+    }
+    float ent = 0.f;
+    for (int j = 0; j < a.A; j++) ent += 0.5f + 0.5f * 1.8378770664093453f + logf(a.std[j]);   // ACM:160-163
+    const float surr = a.tail[2] / cnt, vl = a.tail[3] / cnt;
+    const float loss = surr + a.vcoef * vl - a.ecoef * ent;
+    c.kl_mean = kl_mean; c.loss = loss; c.value_loss = vl; c.surrogate_loss = surr;
+    c.skip = isnan(loss) ? 1 : 0;
+    const float W = (float)a.world_size;
+    const float total = (float)sqrt(c.sumsq) / W;                                      // grads in reduce_buf are sums over ranks
+    c.grad_norm = total;
+    c.coef = fminf(a.max_grad_norm / (total + 1e-6f), 1.0f) / W;                       // clip_grad_norm_ (ppo.py:304)
+    c.sumsq = 0.0;
+    c.mb_counter += 1;
+    if (!c.skip) {
+        c.step += 1;
+        c.bc1 = (float)(1.0 - pow(0.9, (double)c.step));
+        c.bc2s = (float)sqrt(1.0 - pow(0.999, (double)c.step));
+        c.sum_value_loss += vl; c.sum_surrogate_loss += surr;
+    }
+}
+// torch.optim.Adam (ppo.py:81; betas 0.9/0.999, eps 1e-8, no weight decay)
+__global__ void adam_kernel(float *p, const float *g, float *m, float *v, int n, const Ctl *ctl) {
+    if (ctl->skip) return;
+    const float lr = ctl->lr, coef = ctl->coef, bc1 = ctl->bc1, bc2s = ctl->bc2s;
+    const float step_size = lr / bc1;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float gi = g[i] * coef;
+        const float mi = 0.9f * m[i] + (1.0f - 0.9f) * gi;
+        const float vi = 0.999f * v[i] + (1.0f - 0.999f) * gi * gi;
+        m[i] = mi; v[i] = vi;
+        const float denom = sqrtf(vi) / bc2s + 1e-8f;
+        p[i] -= step_size * (mi / denom);
+    }
+}
+
+struct Net {            // one MLP: offsets into the flat parameter vector
+    int dims[5];        // in, h1, h2, h3, out
+    size_t w[4], b[4];
+};
+
+}  // namespace
+
+// =========================================================================================================
+// Host side
+// =========================================================================================================
+struct grx_ppo {
+    grx_ppo_cfg cfg;
+    int device = 0;
+    int N = 0, T = 0, O = 0, P = 0, A = 0, B = 0, MR = 0;   // B = minibatch rows, MR = workspace rows = max(N, B)
+    size_t nparam = 0;
+    Net actor, critic;
+    float *params = nullptr, *reduce_buf = nullptr, *adam_m = nullptr, *adam_v = nullptr;
+    // storage [T, N, .]
+    float *s_obs = nullptr, *s_cobs = nullptr, *s_act = nullptr, *s_val = nullptr, *s_rew = nullptr, *s_logp = nullptr, *s_mu = nullptr,
+          *s_sigma = nullptr, *s_ret = nullptr, *s_adv = nullptr;
+    uint8_t *s_done = nullptr;
+    // workspace
+    float *ha[4] = {nullptr, nullptr, nullptr, nullptr}, *hc[4] = {nullptr, nullptr, nullptr, nullptr};     // activations (h1..h3, out)
+    float *da[4] = {nullptr, nullptr, nullptr, nullptr}, *dc[4] = {nullptr, nullptr, nullptr, nullptr};     // gradients w.r.t. them
+    float *xa = nullptr, *xc = nullptr, *mb_act = nullptr, *mb_val = nullptr, *mb_ret = nullptr, *mb_adv = nullptr, *mb_logp = nullptr,
+          *mb_mu = nullptr, *mb_sigma = nullptr, *last_values = nullptr;
+    double *moments = nullptr;
+    Ctl *ctl = nullptr;
+    std::vector<void *> allocs;
+    cudaGraphExec_t graph = nullptr;
+    const int64_t *graph_indices = nullptr;
+};
+
+static int ppo_alloc(grx_ppo *p, void **ptr, size_t bytes) {
+    CK(cudaMalloc(ptr, bytes));
+    CK(cudaMemset(*ptr, 0, bytes));
+    p->allocs.push_back(*ptr);
+    return GRX_OK;
+}
+#define PALLOC(ptr, count) do { int rc__ = ppo_alloc(p, (void **)&(ptr), (size_t)(count)); if (rc__) return rc__; } while (0)
+
+static void layout_net(Net &n, const int *dims, size_t &off) {
+    for (int i = 0; i < 5; i++) n.dims[i] = dims[i];
+    for (int l = 0; l < 4; l++) {
+        n.w[l] = off; off += (size_t)dims[l + 1] * dims[l];
+        n.b[l] = off; off += (size_t)dims[l + 1];
+    }
+}
+
+extern "C" int grx_ppo_create(const grx_ppo_cfg *cfg, int32_t device, grx_ppo **out) {
+    if (!cfg || !out) return grx_set_error(GRX_E_INVALID, "grx_ppo_create: null argument");
+    if (cfg->num_envs <= 0 || cfg->num_steps <= 0 || cfg->num_steps > GAE_TMAX || cfg->num_actions > MAXA || cfg->num_actions <= 0 ||
+        cfg->num_mini_batches <= 0 || cfg->num_learning_epochs <= 0 || cfg->world_size <= 0)
+        return grx_set_error(GRX_E_INVALID, "grx_ppo_create: bad sizes (need num_steps <= 256, num_actions <= 32)");
+    CK(cudaSetDevice(device));
+    grx_ppo *p = new grx_ppo();
+    p->cfg = *cfg; p->device = device;
+    p->N = cfg->num_envs; p->T = cfg->num_steps; p->O = cfg->num_obs; p->P = cfg->num_pri_obs; p->A = cfg->num_actions;
+    p->B = (int)(((size_t)p->N * p->T) / cfg->num_mini_batches);                       // rollout_storage.py:71-72
+    if (p->B <= 0) { delete p; return grx_set_error(GRX_E_INVALID, "grx_ppo_create: fewer transitions than minibatches"); }
+    p->MR = p->N > p->B ? p->N : p->B;
+    // flat parameter vector in the reference's state_dict order: std, actor.model.{0,2,4,6}.{weight,bias}, critic...
+    size_t off = (size_t)p->A;
+    const int da[5] = {p->O, cfg->actor_hidden[0], cfg->actor_hidden[1], cfg->actor_hidden[2], p->A};
+    const int dc[5] = {p->P, cfg->critic_hidden[0], cfg->critic_hidden[1], cfg->critic_hidden[2], 1};
+    layout_net(p->actor, da, off);
+    layout_net(p->critic, dc, off);
+    p->nparam = off;
+    const size_t TN = (size_t)p->T * p->N, MR = p->MR;
+    PALLOC(p->params, off * 4); PALLOC(p->reduce_buf, (off + TAIL) * 4); PALLOC(p->adam_m, off * 4); PALLOC(p->adam_v, off * 4);
+    PALLOC(p->s_obs, TN * p->O * 4); PALLOC(p->s_cobs, TN * p->P * 4); PALLOC(p->s_act, TN * p->A * 4); PALLOC(p->s_val, TN * 4);
+    PALLOC(p->s_rew, TN * 4); PALLOC(p->s_logp, TN * 4); PALLOC(p->s_mu, TN * p->A * 4); PALLOC(p->s_sigma, TN * p->A * 4);
+    PALLOC(p->s_ret, TN * 4); PALLOC(p->s_adv, TN * 4); PALLOC(p->s_done, TN);
+    for (int l = 0; l < 4; l++) {
+        PALLOC(p->ha[l], MR * da[l + 1] * 4); PALLOC(p->da[l], MR * da[l + 1] * 4);
+        PALLOC(p->hc[l], MR * dc[l + 1] * 4); PALLOC(p->dc[l], MR * dc[l + 1] * 4);
+    }
+    PALLOC(p->xa, MR * p->O * 4); PALLOC(p->xc, MR * p->P * 4); PALLOC(p->mb_act, MR * p->A * 4); PALLOC(p->mb_val, MR * 4);
+    PALLOC(p->mb_ret, MR * 4); PALLOC(p->mb_adv, MR * 4); PALLOC(p->mb_logp, MR * 4); PALLOC(p->mb_mu, MR * p->A * 4);
+    PALLOC(p->mb_sigma, MR * p->A * 4); PALLOC(p->last_values, (size_t)p->N * 4);
+    PALLOC(p->moments, 4 * sizeof(double)); PALLOC(p->ctl, sizeof(Ctl));
+    CK(cudaFuncSetAttribute(gae_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * GAE_TMAX * 33 * (int)sizeof(float)));
+    {   // std = init_noise_std (ACM:79-82); weights are loaded by the host (same nn.Linear init stream as the reference); lr
+        std::vector<float> s(p->A, cfg->init_noise_std);
+        CK(cudaMemcpy(p->params, s.data(), p->A * 4, cudaMemcpyHostToDevice));
+        Ctl c; memset(&c, 0, sizeof(c));
+        c.lr = cfg->learning_rate;
+        CK(cudaMemcpy(p->ctl, &c, sizeof(c), cudaMemcpyHostToDevice));
+    }
+    *out = p;
+    return GRX_OK;
+}
+
+extern "C" int grx_ppo_destroy(grx_ppo *p) {
+    if (!p) return GRX_OK;
+    cudaSetDevice(p->device);
+    if (p->graph) cudaGraphExecDestroy(p->graph);
+    for (void *q : p->allocs) cudaFree(q);
+    delete p;
+    return GRX_OK;
+}
+
+static void set_buf(grx_buffer *b, void *data, int dtype, int ndim, int64_t d0, int64_t d1, int64_t d2) {
+    b->data = data; b->dtype = dtype; b->ndim = ndim;
+    b->dims[0] = d0; b->dims[1] = d1; b->dims[2] = d2; b->dims[3] = 1;
+    b->strides[0] = d1 * d2; b->strides[1] = d2; b->strides[2] = 1; b->strides[3] = 1;
+}
+
+extern "C" int grx_ppo_get_buffer(grx_ppo *p, const char *name, grx_buffer *b) {
+    if (!p || !name || !b) return grx_set_error(GRX_E_INVALID, "grx_ppo_get_buffer: null argument");
+    const std::string n(name);
+    const int64_t T = p->T, N = p->N, np_ = (int64_t)p->nparam;
+    if (n == "params") { set_buf(b, p->params, GRX_F32, 1, np_, 1, 1); return GRX_OK; }
+    if (n == "grads") { set_buf(b, p->reduce_buf, GRX_F32, 1, np_, 1, 1); return GRX_OK; }
+    if (n == "reduce_buf") { set_buf(b, p->reduce_buf, GRX_F32, 1, np_ + TAIL, 1, 1); return GRX_OK; }
+    if (n == "adam_m") { set_buf(b, p->adam_m, GRX_F32, 1, np_, 1, 1); return GRX_OK; }
+    if (n == "adam_v") { set_buf(b, p->adam_v, GRX_F32, 1, np_, 1, 1); return GRX_OK; }
+    if (n == "obs") { set_buf(b, p->s_obs, GRX_F32, 3, T, N, p->O); return GRX_OK; }
+    if (n == "critic_obs") { set_buf(b, p->s_cobs, GRX_F32, 3, T, N, p->P); return GRX_OK; }
+    if (n == "actions") { set_buf(b, p->s_act, GRX_F32, 3, T, N, p->A); return GRX_OK; }
+    if (n == "mu") { set_buf(b, p->s_mu, GRX_F32, 3, T, N, p->A); return GRX_OK; }
+    if (n == "sigma") { set_buf(b, p->s_sigma, GRX_F32, 3, T, N, p->A); return GRX_OK; }
+    if (n == "values") { set_buf(b, p->s_val, GRX_F32, 3, T, N, 1); return GRX_OK; }
+    if (n == "rewards") { set_buf(b, p->s_rew, GRX_F32, 3, T, N, 1); return GRX_OK; }
+    if (n == "actions_log_prob") { set_buf(b, p->s_logp, GRX_F32, 3, T, N, 1); return GRX_OK; }
+    if (n == "returns") { set_buf(b, p->s_ret, GRX_F32, 3, T, N, 1); return GRX_OK; }
+    if (n == "advantages") { set_buf(b, p->s_adv, GRX_F32, 3, T, N, 1); return GRX_OK; }
+    if (n == "dones") { set_buf(b, p->s_done, GRX_U8, 3, T, N, 1); return GRX_OK; }
+    if (n == "adv_moments") { set_buf(b, p->moments, GRX_U64, 1, 3, 1, 1); return GRX_OK; }   // 3 doubles (bit pattern)
+    if (n == "ctl") { set_buf(b, p->ctl, GRX_F32, 1, sizeof(Ctl) / 4, 1, 1); return GRX_OK; }
+    return grx_set_error(GRX_E_NOTFOUND, "grx_ppo_get_buffer: unknown buffer '" + n + "'");
+}
+
+// MLP forward over M rows: h[l] = elu(h[l-1] W_l^T + b_l), out = h3 W_3^T + b_3 (mlp.py:26-41)
+static void mlp_forward(grx_ppo *p, const Net &net, const float *x, float *const *h, int M, cudaStream_t st) {
+    const float *in = x;
+    for (int l = 0; l < 4; l++) {
+        GemmArgs g; memset(&g, 0, sizeof(g));
+        g.A = in; g.B = p->params + net.w[l]; g.C = h[l]; g.bias = p->params + net.b[l];
+        g.M = M; g.N = net.dims[l + 1]; g.K = net.dims[l]; g.lda = g.K; g.ldb = g.K; g.ldc = g.N;
+        if (l < 3) launch_gemm<true, true, 1>(g, 1, st);
+        else launch_gemm<true, true, 0>(g, 1, st);
+        in = h[l];
+    }
+}
+// MLP backward: d[3] holds dL/d(out); writes weight / bias grads (accumulating into zeroed `grads`) and d[2..0]
+static void mlp_backward(grx_ppo *p, const Net &net, const float *x, float *const *h, float *const *d, float *grads, int M, cudaStream_t st) {
+    for (int l = 3; l >= 0; l--) {
+        const float *hin = l == 0 ? x : h[l - 1];
+        {   // dW_l [out, in] += dY^T hin ; db_l += colsum(dY)
+            GemmArgs g; memset(&g, 0, sizeof(g));
+            g.A = d[l]; g.B = hin; g.C = grads + net.w[l]; g.bias_out = grads + net.b[l];
+            g.M = net.dims[l + 1]; g.N = net.dims[l]; g.K = M; g.lda = net.dims[l + 1]; g.ldb = net.dims[l]; g.ldc = net.dims[l];
+            const int tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
+            int splits = (2 * 148 + tiles - 1) / tiles;
+            const int maxs = (M + 255) / 256;
+            if (splits > maxs) splits = maxs;
+            if (splits < 1) splits = 1;
+            launch_gemm<false, false, 3>(g, splits, st);
+        }
+        if (l > 0) {   // d[l-1] = (dY W_l) * ELU'(h[l-1])
+            GemmArgs g; memset(&g, 0, sizeof(g));
+            g.A = d[l]; g.B = p->params + net.w[l]; g.C = d[l - 1]; g.aux = h[l - 1];
+            g.M = M; g.N = net.dims[l]; g.K = net.dims[l + 1]; g.lda = net.dims[l + 1]; g.ldb = net.dims[l]; g.ldc = net.dims[l];
+            launch_gemm<true, false, 2>(g, 1, st);
+        }
+    }
+}
+
+extern "C" int grx_ppo_act(grx_ppo *p, const float *d_obs, const float *d_critic_obs, const float *d_eps, int32_t t, float *d_actions_out,
+                           uint64_t step_index, void *stream) {
+    if (!p || !d_obs || !d_critic_obs || !d_actions_out || t < 0 || t >= p->T) return grx_set_error(GRX_E_INVALID, "grx_ppo_act: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    mlp_forward(p, p->actor, d_obs, p->ha, p->N, st);
+    mlp_forward(p, p->critic, d_critic_obs, p->hc, p->N, st);
+    ActArgs a; memset(&a, 0, sizeof(a));
+    const size_t row = (size_t)t * p->N;
+    a.obs = d_obs; a.critic_obs = d_critic_obs; a.mu = p->ha[3]; a.value = p->hc[3]; a.std = p->params; a.eps = d_eps;
+    a.actions_out = d_actions_out;
+    a.s_obs = p->s_obs + row * p->O; a.s_cobs = p->s_cobs + row * p->P; a.s_act = p->s_act + row * p->A; a.s_val = p->s_val + row;
+    a.s_logp = p->s_logp + row; a.s_mu = p->s_mu + row * p->A; a.s_sigma = p->s_sigma + row * p->A;
+    a.N = p->N; a.O = p->O; a.P = p->P; a.A = p->A; a.seed = 0x9E3779B97F4A7C15ull; a.step_index = step_index; a.env_id_offset = 0;
+    act_sample_store_kernel<<<(p->N + 127) / 128, 128, 0, st>>>(a);
+    CK(cudaGetLastError());
+    return GRX_OK;
+}
+
+extern "C" int grx_ppo_process_env_step(grx_ppo *p, const float *d_rewards, const uint8_t *d_dones, const uint8_t *d_time_outs, int32_t t,
+                                        void *stream) {
+    if (!p || !d_rewards || !d_dones || t < 0 || t >= p->T) return grx_set_error(GRX_E_INVALID, "grx_ppo_process_env_step: bad argument");
+    const size_t row = (size_t)t * p->N;
+    process_env_step_kernel<<<(p->N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_rewards, d_dones, d_time_outs, p->s_val + row, p->cfg.gamma,
+                                                                                   p->s_rew + row, p->s_done + row, p->N);
+    CK(cudaGetLastError());
+    return GRX_OK;
+}
+
+extern "C" int grx_ppo_compute_returns_local(grx_ppo *p, const float *d_last_critic_obs, void *stream) {
+    if (!p || !d_last_critic_obs) return grx_set_error(GRX_E_INVALID, "grx_ppo_compute_returns: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    mlp_forward(p, p->critic, d_last_critic_obs, p->hc, p->N, st);                     // ppo.py:204
+    CK(cudaMemcpyAsync(p->last_values, p->hc[3], (size_t)p->N * 4, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemsetAsync(p->moments, 0, 4 * sizeof(double), st));
+    gae_kernel<<<(p->N + 31) / 32, 1024, (size_t)3 * p->T * 33 * sizeof(float), st>>>(p->s_rew, p->s_done, p->s_val, p->last_values, p->cfg.gamma, p->cfg.lam, p->s_ret, p->s_adv,
+                                                  p->moments, p->T, p->N);
+    CK(cudaGetLastError());
+    return GRX_OK;
+}
+extern "C" int grx_ppo_normalize_advantages(grx_ppo *p, void *stream) {
+    if (!p) return grx_set_error(GRX_E_INVALID, "null ppo");
+    normalize_adv_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(p->s_adv, p->moments, (size_t)p->T * p->N);
+    CK(cudaGetLastError());
+    return GRX_OK;
+}
+extern "C" int grx_ppo_compute_returns(grx_ppo *p, const float *d_last_critic_obs, void *stream) {
+    int rc = grx_ppo_compute_returns_local(p, d_last_critic_obs, stream);
+    if (rc) return rc;
+    return grx_ppo_normalize_advantages(p, stream);
+}
+
+static int minibatch_grads(grx_ppo *p, const int64_t *d_indices, int mb, bool device_counter, cudaStream_t st) {
+    const int B = p->B;
+    CK(cudaMemsetAsync(p->reduce_buf, 0, (p->nparam + TAIL) * 4, st));
+    GatherArgs g; memset(&g, 0, sizeof(g));
+    g.indices = d_indices; g.mb_counter = device_counter ? &p->ctl->mb_counter : nullptr; g.mb = mb; g.nmb = p->cfg.num_mini_batches;
+    g.B = B; g.O = p->O; g.P = p->P; g.A = p->A;
+    g.s_obs = p->s_obs; g.s_cobs = p->s_cobs; g.s_act = p->s_act; g.s_val = p->s_val; g.s_ret = p->s_ret; g.s_adv = p->s_adv;
+    g.s_logp = p->s_logp; g.s_mu = p->s_mu; g.s_sigma = p->s_sigma;
+    g.xa = p->xa; g.xc = p->xc; g.act = p->mb_act; g.val = p->mb_val; g.ret = p->mb_ret; g.adv = p->mb_adv; g.logp = p->mb_logp;
+    g.mu = p->mb_mu; g.sigma = p->mb_sigma;
+    gather_kernel<<<592, 256, 0, st>>>(g);
+    mlp_forward(p, p->actor, p->xa, p->ha, B, st);                                     // ppo.py:244-248
+    mlp_forward(p, p->critic, p->xc, p->hc, B, st);
+    LossArgs a; memset(&a, 0, sizeof(a));
+    a.mu = p->ha[3]; a.v = p->hc[3]; a.std = p->params; a.act = p->mb_act; a.old_mu = p->mb_mu; a.old_sigma = p->mb_sigma;
+    a.old_logp = p->mb_logp; a.adv = p->mb_adv; a.ret = p->mb_ret; a.old_v = p->mb_val;
+    a.dmu = p->da[3]; a.dv = p->dc[3]; a.gstd = p->reduce_buf; a.tail = p->reduce_buf + p->nparam;
+    a.B = B; a.A = p->A; a.clip = p->cfg.clip_param; a.vcoef = p->cfg.value_loss_coef; a.ecoef = p->cfg.entropy_coef;
+    a.clipped_value = p->cfg.use_clipped_value_loss;
+    ppo_loss_kernel<<<(B + 255) / 256, 256, 0, st>>>(a);
+    mlp_backward(p, p->actor, p->xa, p->ha, p->da, p->reduce_buf, B, st);
+    mlp_backward(p, p->critic, p->xc, p->hc, p->dc, p->reduce_buf, B, st);
+    CK(cudaGetLastError());
+    return GRX_OK;
+}
+static int minibatch_apply(grx_ppo *p, cudaStream_t st) {
+    gradnorm_kernel<<<148, 256, 0, st>>>(p->reduce_buf, (int)p->nparam, p->ctl);
+    PrepArgs a; memset(&a, 0, sizeof(a));
+    a.ctl = p->ctl; a.tail = p->reduce_buf + p->nparam; a.std = p->params; a.A = p->A; a.adaptive = p->cfg.adaptive_schedule;
+    a.world_size = p->cfg.world_size; a.desired_kl = p->cfg.desired_kl; a.lr_min = p->cfg.learning_rate_min; a.lr_max = p->cfg.learning_rate_max;
+    a.max_grad_norm = p->cfg.max_grad_norm; a.vcoef = p->cfg.value_loss_coef; a.ecoef = p->cfg.entropy_coef;
+    prep_apply_kernel<<<1, 32, 0, st>>>(a);
+    adam_kernel<<<296, 256, 0, st>>>(p->params, p->reduce_buf, p->adam_m, p->adam_v, (int)p->nparam, p->ctl);
+    CK(cudaGetLastError());
+    return GRX_OK;
+}
+
+extern "C" int grx_ppo_minibatch_grads(grx_ppo *p, const int64_t *d_indices, int32_t mb, void *stream) {
+    if (!p || !d_indices || mb < 0 || mb >= p->cfg.num_mini_batches) return grx_set_error(GRX_E_INVALID, "grx_ppo_minibatch_grads: bad argument");
+    return minibatch_grads(p, d_indices, mb, false, (cudaStream_t)stream);
+}
+extern "C" int grx_ppo_minibatch_apply(grx_ppo *p, void *stream) {
+    if (!p) return grx_set_error(GRX_E_INVALID, "null ppo");
+    return minibatch_apply(p, (cudaStream_t)stream);
+}
+
+// Whole PPO.update (ppo.py:215-321): one minibatch (grads + apply) is captured once as a CUDA graph whose gather kernel
+// reads the minibatch index from the device control block, then replayed epochs x minibatches times.
+extern "C" int grx_ppo_update(grx_ppo *p, const int64_t *d_indices, void *stream) {
+    if (!p || !d_indices) return grx_set_error(GRX_E_INVALID, "grx_ppo_update: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    // reset the per-update accumulators (mb_counter, loss sums); lr / Adam step persist
+    CK(cudaMemsetAsync(&p->ctl->sum_value_loss, 0, 2 * sizeof(float) + sizeof(int), st));
+    if (!p->graph || p->graph_indices != d_indices) {
+        if (p->graph) { cudaGraphExecDestroy(p->graph); p->graph = nullptr; }
+        cudaStream_t cs;
+        CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        cudaGraph_t gr;
+        CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+        int rc = minibatch_grads(p, d_indices, 0, true, cs);
+        if (!rc) rc = minibatch_apply(p, cs);
+        cudaError_t ce = cudaStreamEndCapture(cs, &gr);
+        cudaStreamDestroy(cs);
+        if (rc) return rc;
+        CK(ce);
+        CK(cudaGraphInstantiate(&p->graph, gr, 0));
+        cudaGraphDestroy(gr);
+        p->graph_indices = d_indices;
+    }
+    const int total = p->cfg.num_learning_epochs * p->cfg.num_mini_batches;
+    for (int i = 0; i < total; i++) CK(cudaGraphLaunch(p->graph, st));
+    return GRX_OK;
+}
+
+extern "C" int grx_ppo_act_inference(grx_ppo *p, const float *d_obs, int32_t n, float *d_actions_out, void *stream) {
+    if (!p || !d_obs || !d_actions_out || n <= 0 || n > p->MR) return grx_set_error(GRX_E_INVALID, "grx_ppo_act_inference: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    mlp_forward(p, p->actor, d_obs, p->ha, n, st);
+    CK(cudaMemcpyAsync(d_actions_out, p->ha[3], (size_t)n * p->A * 4, cudaMemcpyDeviceToDevice, st));
+    return GRX_OK;
+}

@@ -86,9 +86,9 @@ def lib():
         _lib.grx_last_error.restype = C.c_char_p
         _lib.grx_env_accum_slot.restype = C.c_int64
         _lib.grx_env_accum_slot.argtypes = [C.c_void_p]
-        sizes = (I32 * 4)()
-        _lib.grx_abi_sizes(sizes, 4)
-        want = [C.sizeof(Buffer), C.sizeof(ModelDesc), C.sizeof(TaskCfg), C.sizeof(InjectedPhysics)]
+        sizes = (I32 * 5)()
+        _lib.grx_abi_sizes(sizes, 5)
+        want = [C.sizeof(Buffer), C.sizeof(ModelDesc), C.sizeof(TaskCfg), C.sizeof(InjectedPhysics), C.sizeof(PPOCfg)]
         if list(sizes) != want:
             raise GrxError(f"ABI mismatch between grx_b200/_lib.py and libgrx_b200.so: {list(sizes)} vs {want}")
     return _lib
