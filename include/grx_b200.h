@@ -217,6 +217,13 @@ int grx_ppo_update(grx_ppo *ppo, const int64_t *d_indices, void *stream);
 /* actor-only forward for play.py / get_inference_policy (actor_critic_mlp.py:209-217) */
 int grx_ppo_act_inference(grx_ppo *ppo, const float *d_obs, int32_t n, float *d_actions_out, void *stream);
 
+/* Debug / parity: one dense-layer GEMM on device pointers through the fp32 SIMT kernel (use_tc = 0) or the tcgen05 TF32 kernel.
+ *   variant 0: C[M,N] = A[M,K] B[N,K]^T + bias (epi 0) or elu(...) (epi 1)      — forward (mlp.py:40-41)
+ *   variant 1: C[M,N] = (A[M,K] B[K,N]) * ELU'(aux[M,N])                         — input gradient
+ *   variant 2: C[M,N] += A[K,M]^T B[K,N], bias_out[M] += column sums of A        — weight / bias gradient (split-K) */
+int grx_gemm_debug(int32_t variant, int32_t epi, int32_t M, int32_t N, int32_t K, const float *A, const float *B, float *C,
+                   const float *bias, const float *aux, float *bias_out, int32_t splits, int32_t use_tc, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

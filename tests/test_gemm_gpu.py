@@ -1,0 +1,107 @@
+"""tcgen05 TF32 dense-layer kernel vs the fp32 SIMT kernel and torch fp32, through the C ABI (grx_gemm_debug):
+forward (K-major x K-major), input gradient (K-major x MN-major), weight gradient (MN-major x MN-major, split-K)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+# TF32 rounds the operands to 10 mantissa bits (rel 2^-11 each); fp32 accumulate.  Error of a length-K dot product of O(1)
+# terms grows ~ sqrt(K) * 2^-11: tolerance relative to the output scale.
+TF32_RTOL = 2e-3
+
+
+def _run(variant, epi, M, N, K, use_tc, splits=1, seed=0):
+    from grx_b200 import _lib as L
+    lib = L.lib()
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    r = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    if variant == 0:
+        A, B = r(M, K), r(N, K) / K ** 0.5
+        bias, aux, bias_out = r(N), None, None
+        C_ = torch.zeros(M, N, device="cuda")
+        ref = A @ B.t() + bias
+        if epi == 1:
+            ref = torch.nn.functional.elu(ref)
+    elif variant == 1:
+        A, B = r(M, K), r(K, N) / K ** 0.5
+        bias, bias_out = None, None
+        aux = torch.nn.functional.elu(r(M, N))
+        C_ = torch.zeros(M, N, device="cuda")
+        ref = (A @ B) * torch.where(aux > 0, torch.ones_like(aux), aux + 1)
+    else:
+        A, B = r(K, M), r(K, N) / K ** 0.5
+        bias, aux = None, None
+        bias_out = torch.zeros(M, device="cuda")
+        C_ = torch.zeros(M, N, device="cuda")
+        ref = A.t() @ B
+    p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+    L.check(lib.grx_gemm_debug(variant, epi, M, N, K, p(A), p(B), p(C_), p(bias), p(aux), p(bias_out), splits, use_tc,
+                               C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    extra = (bias_out, A.sum(0)) if variant == 2 else None
+    return C_, ref, extra
+
+
+SHAPES_FWD = [(10485, 512, 168), (10485, 256, 512), (10485, 128, 256), (4096, 512, 168), (300, 64, 64), (129, 48, 40), (128, 16, 8)]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES_FWD)
+@pytest.mark.parametrize("epi", [0, 1])
+def test_forward_layer(M, N, K, epi):
+    got, ref, _ = _run(0, epi, M, N, K, use_tc=1)
+    simt, _, _ = _run(0, epi, M, N, K, use_tc=0)
+    scale = float(ref.abs().max())
+    assert float((simt - ref).abs().max()) <= 2e-5 * scale + 1e-5
+    assert float((got - ref).abs().max()) <= TF32_RTOL * scale, float((got - ref).abs().max()) / scale
+
+
+@pytest.mark.parametrize("M,N,K", [(10485, 512, 256), (10485, 256, 128), (777, 168, 512), (128, 64, 64)])
+def test_input_gradient_layer(M, N, K):
+    got, ref, _ = _run(1, 2, M, N, K, use_tc=1)
+    scale = float(ref.abs().max())
+    assert float((got - ref).abs().max()) <= TF32_RTOL * scale, float((got - ref).abs().max()) / scale
+
+
+@pytest.mark.parametrize("M,N,K,splits", [(512, 168, 10485, 37), (256, 512, 10485, 20), (128, 256, 10485, 74), (128, 64, 333, 3), (512, 168, 64, 1)])
+def test_weight_gradient_layer(M, N, K, splits):
+    got, ref, (bo, bo_ref) = _run(2, 3, M, N, K, use_tc=1, splits=splits)
+    scale = float(ref.abs().max())
+    assert float((got - ref).abs().max()) <= TF32_RTOL * scale, float((got - ref).abs().max()) / scale
+    np.testing.assert_allclose(bo.cpu().numpy(), bo_ref.cpu().numpy(), rtol=1e-4, atol=1e-3)
+
+
+def test_tensor_core_update_matches_simt_update():
+    """Whole PPO minibatch at the registered width through the tcgen05 path vs the fp32 SIMT path: gradients agree to TF32 accuracy."""
+    from grx_b200.config import make_train_cfg
+    from grx_b200.ppo import PPO, ActorCriticMLP
+    from grx_b200 import _lib as L
+    tc = make_train_cfg()
+    O, P, A, N, T = 39, 168, 10, 512, 8
+    grads = []
+    for use_tc in (0, 1):
+        torch.manual_seed(5)
+        ac = ActorCriticMLP(O, P, A, **tc["policy"])
+        alg = PPO(ac, device="cuda:0", use_tensor_cores=use_tc, **dict(tc["algorithm"], num_mini_batches=2, num_learning_epochs=1))
+        alg.init_storage(N, T)
+        g = torch.Generator().manual_seed(7)
+        for s in range(T):
+            alg.act(torch.randn(N, O, generator=g).cuda(), torch.randn(N, P, generator=g).cuda(), eps=torch.randn(N, A, generator=g).cuda())
+            alg.process_env_step((0.1 * torch.randn(N, generator=g)).cuda(), (torch.rand(N, generator=g) < 0.1).cuda(), {})
+        alg.compute_returns(torch.randn(N, P, generator=g).cuda())
+        with torch.no_grad():
+            for k, v in ac.state_dict().items():
+                v.add_(0.02 * torch.randn(v.shape, generator=g).cuda() * (v.abs().mean() + 0.05))
+        alg._indices.copy_(torch.randperm(N * T, generator=g).cuda())
+        L.check(alg.lib.grx_ppo_minibatch_grads(alg._h, C.c_void_p(alg._indices.data_ptr()), 0, alg._stream()))
+        torch.cuda.synchronize()
+        grads.append((alg.grads.clone(), [(k, v.numel()) for k, v in ac.state_dict().items()]))
+    (g0, names), (g1, _) = grads
+    off = 0
+    for k, n in names:
+        a, b = g0[off:off + n], g1[off:off + n]
+        scale = float(a.abs().max()) + 1e-12
+        assert float((a - b).abs().max()) <= 5e-3 * scale, (k, float((a - b).abs().max()) / scale)
+        off += n

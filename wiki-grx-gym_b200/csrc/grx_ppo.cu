@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "grx_b200.h"
+#include "grx_gemm_tc.cuh"
 
 int grx_set_error(int code, const std::string &msg);   // grx_env.cu
 
@@ -129,6 +130,43 @@ void launch_gemm(const GemmArgs &g, int splits, cudaStream_t st) {
     const int z = (g.K + a.kchunk - 1) / a.kchunk;
     dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, z);
     gemm_kernel<A_KC, B_KC, EPI><<<grid, 256, 0, st>>>(a);
+}
+
+// column sums of a row-major [M, N] matrix into out[N] (+=): bias gradients on the tensor-core path
+__global__ void __launch_bounds__(256) colsum_kernel(const float *X, int M, int N, int rows_per_block, float *out) {
+    const int n = blockIdx.x * 32 + (threadIdx.x & 31), w = threadIdx.x >> 5;
+    const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+    float s = 0.f;
+    if (n < N)
+        for (int r = r0 + w; r < r1; r += 8) s += X[(size_t)r * N + n];
+    __shared__ float red[8][33];
+    red[w][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (w == 0 && n < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; k++) t += red[k][threadIdx.x];
+        atomicAdd(&out[n], t);
+    }
+}
+
+// Dense-layer dispatch: tcgen05 TF32 kernel when enabled and the shape / alignment allows, else the fp32 SIMT kernel.
+template <bool A_KC, bool B_KC, int EPI>
+void dense(const GemmArgs &g, int splits, bool use_tc, cudaStream_t st) {
+    if (use_tc) {
+        tc::Args a;
+        a.A = g.A; a.B = g.B; a.C = g.C; a.bias = g.bias; a.aux = g.aux; a.M = g.M; a.N = g.N; a.K = g.K;
+        a.lda = g.lda; a.ldb = g.ldb; a.ldc = g.ldc; a.BN = 0; a.kchunk = 0; a.stages = 0;
+        if (tc::supported<A_KC, B_KC>(a)) {
+            if (EPI == 3 && g.bias_out) {
+                const int rpb = 512;
+                colsum_kernel<<<dim3((g.M + 31) / 32, (g.K + rpb - 1) / rpb), 256, 0, st>>>(g.A, g.K, g.M, rpb, g.bias_out);   // A = dY [rows, out]
+            }
+            tc::launch<A_KC, B_KC, EPI>(a, splits, st);
+            return;
+        }
+    }
+    launch_gemm<A_KC, B_KC, EPI>(g, splits, st);
 }
 
 // =========================================================================================================
@@ -605,8 +643,8 @@ static void mlp_forward(grx_ppo *p, const Net &net, const float *x, float *const
         GemmArgs g; memset(&g, 0, sizeof(g));
         g.A = in; g.B = p->params + net.w[l]; g.C = h[l]; g.bias = p->params + net.b[l];
         g.M = M; g.N = net.dims[l + 1]; g.K = net.dims[l]; g.lda = g.K; g.ldb = g.K; g.ldc = g.N;
-        if (l < 3) launch_gemm<true, true, 1>(g, 1, st);
-        else launch_gemm<true, true, 0>(g, 1, st);
+        if (l < 3) dense<true, true, 1>(g, 1, p->cfg.use_tensor_cores != 0, st);
+        else dense<true, true, 0>(g, 1, p->cfg.use_tensor_cores != 0, st);
         in = h[l];
     }
 }
@@ -618,18 +656,19 @@ static void mlp_backward(grx_ppo *p, const Net &net, const float *x, float *cons
             GemmArgs g; memset(&g, 0, sizeof(g));
             g.A = d[l]; g.B = hin; g.C = grads + net.w[l]; g.bias_out = grads + net.b[l];
             g.M = net.dims[l + 1]; g.N = net.dims[l]; g.K = M; g.lda = net.dims[l + 1]; g.ldb = net.dims[l]; g.ldc = net.dims[l];
-            const int tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
+            const bool use_tc = p->cfg.use_tensor_cores != 0 && g.M >= 64 && g.N >= 64;
+            const int tiles = use_tc ? ((g.M + 127) / 128) * ((g.N + 255) / 256) : ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
             int splits = (2 * 148 + tiles - 1) / tiles;
             const int maxs = (M + 255) / 256;
             if (splits > maxs) splits = maxs;
             if (splits < 1) splits = 1;
-            launch_gemm<false, false, 3>(g, splits, st);
+            dense<false, false, 3>(g, splits, use_tc, st);
         }
         if (l > 0) {   // d[l-1] = (dY W_l) * ELU'(h[l-1])
             GemmArgs g; memset(&g, 0, sizeof(g));
             g.A = d[l]; g.B = p->params + net.w[l]; g.C = d[l - 1]; g.aux = h[l - 1];
             g.M = M; g.N = net.dims[l]; g.K = net.dims[l + 1]; g.lda = net.dims[l + 1]; g.ldb = net.dims[l]; g.ldc = net.dims[l];
-            launch_gemm<true, false, 2>(g, 1, st);
+            dense<true, false, 2>(g, 1, p->cfg.use_tensor_cores != 0 && g.K >= 64, st);
         }
     }
 }
@@ -764,5 +803,20 @@ extern "C" int grx_ppo_act_inference(grx_ppo *p, const float *d_obs, int32_t n, 
     cudaStream_t st = (cudaStream_t)stream;
     mlp_forward(p, p->actor, d_obs, p->ha, n, st);
     CK(cudaMemcpyAsync(d_actions_out, p->ha[3], (size_t)n * p->A * 4, cudaMemcpyDeviceToDevice, st));
+    return GRX_OK;
+}
+
+// Debug / parity entry: one dense-layer GEMM on device pointers, through either implementation.
+//   variant 0: C[M,N] = A[M,K] B[N,K]^T (+bias, epi 0/1)   1: C[M,N] = (A[M,K] B[K,N]) * ELU'(aux) (epi 2)   2: C[M,N] += A[K,M]^T B[K,N] (epi 3)
+extern "C" int grx_gemm_debug(int32_t variant, int32_t epi, int32_t M, int32_t N, int32_t K, const float *A, const float *B, float *C,
+                              const float *bias, const float *aux, float *bias_out, int32_t splits, int32_t use_tc, void *stream) {
+    GemmArgs g; memset(&g, 0, sizeof(g));
+    g.A = A; g.B = B; g.C = C; g.bias = bias; g.aux = aux; g.bias_out = bias_out; g.M = M; g.N = N; g.K = K; g.ldc = N;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (variant == 0) { g.lda = K; g.ldb = K; if (epi == 1) dense<true, true, 1>(g, 1, use_tc != 0, st); else dense<true, true, 0>(g, 1, use_tc != 0, st); }
+    else if (variant == 1) { g.lda = K; g.ldb = N; dense<true, false, 2>(g, 1, use_tc != 0, st); }
+    else if (variant == 2) { g.lda = M; g.ldb = N; dense<false, false, 3>(g, splits, use_tc != 0, st); }
+    else return grx_set_error(GRX_E_INVALID, "grx_gemm_debug: variant must be 0, 1 or 2");
+    CK(cudaGetLastError());
     return GRX_OK;
 }
