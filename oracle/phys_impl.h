@@ -63,13 +63,13 @@ typedef struct {
     int solver_iters;       /* 4 */
     int decimation;         /* 10 */
     REAL action_scale;      /* 1.0 */
-    int max_contacts;       /* 8: with <= 8 limit rows the solver has at most 32 rows = one warp lane per row */
+    int max_contacts;       /* 8: with <= 7 limit rows the solver has at most 31 rows = one warp lane per row + one lane for the unconstrained update */
 } FN(SimCfg);
 
 #define MAXB 36
 #define MAXV 40
 #define MAXC 16
-#define MAXLIM 8
+#define MAXLIM 7
 #define MAXROWS (3 * MAXC + MAXV)
 
 static inline void FN(v3cross)(const REAL *a, const REAL *b, REAL *o) {

@@ -25,7 +25,8 @@
 
 namespace {
 
-constexpr int NB = 11, ND = 10, NV = 16, CH = 5, NLMAX = 40, NSMAX = 32, NF = 2, KC = 8, KLIM = 8;
+constexpr int NB = 11, ND = 10, NV = 16, CH = 5, NLMAX = 40, NSMAX = 32, NF = 2, KC = 8, KLIM = 7;
+constexpr int YS = 20;   // row stride of WS::Y (floats): 16-byte aligned and conflict-free for per-lane float4 stores
 constexpr int NREW = 24, NHMAX = 128;
 constexpr int WARPS_PER_CTA = 4;
 constexpr int ACC_RING = 256, ACC_W = 32;   // extras["episode"] accumulators: one 32-float slot per launch, ring of 256
@@ -89,23 +90,24 @@ struct EnvArgs {
 struct alignas(16) WS {
     float rec[REC_F];
     float cst[CST_F];
-    float pri[168];  // privileged-observation row staging (bulk-stored)
     float R[NB][9], o[NB][3], a[NB][3], c[NB][3], Iw[NB][6], w[NB][3], vo[NB][3], al[NB][3], ao[NB][3];
     float bi[NB][10], bw[NB][6];
     float S[ND][6], F[ND][6];
     float M[NV][NV + 1];
     float invd[NV], h[NV], u[NV], tau[NV];
-    float Y[32][NV];     // reused after physics: measured heights [121] + obs staging
-    float rowc[32][2];   // invA, bias
+    float Y[32][YS];     // M^-1 J^T, one row per constraint; after the physics: privileged-observation row staging (bulk-stored)
+    float As[32][32];    // Delassus matrix, As[r][c] = J_c . Y_r (symmetric); after the physics: measured heights + obs staging
+    float rowc[32][2];   // 1 / A_rr, bias
     float cfr[KC][9];    // contact frame n, t1, t2
     float cpt[KC][4];    // contact point xyz, target velocity
     int cbody[KC], clink[KC];
-    int limj[KLIM];
-    float lims[KLIM], limt[KLIM];
+    int limj[8];
+    float lims[8], limt[8];
     float cf[NLMAX * 3];
     float rterm[NREW];
     unsigned long long mbar;
 };
+static_assert(sizeof(float) * 32 * YS >= 168 * 4, "pri_obs staging aliases Y");
 
 __device__ __forceinline__ void cross3(const float *a, const float *b, float *o) {
     float x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
@@ -142,7 +144,7 @@ __device__ __forceinline__ void mat2quat(const float *R, float *q) {
 }
 __device__ __forceinline__ void axang2mat(const float *a, float th, float *R) {
     float s, c;
-    sincosf(th, &s, &c);
+    __sincosf(th, &s, &c);   // |joint angle| < pi: abs error < 5e-7; the libm slow path alone is ~1000 instructions
     float t = 1 - c;
     R[0] = c + a[0] * a[0] * t;        R[1] = a[0] * a[1] * t - a[2] * s; R[2] = a[0] * a[2] * t + a[1] * s;
     R[3] = a[1] * a[0] * t + a[2] * s; R[4] = c + a[1] * a[1] * t;        R[5] = a[1] * a[2] * t - a[0] * s;
@@ -198,7 +200,7 @@ __device__ __forceinline__ void bulk_commit_wait() {
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- Philox4x32-10 (counter-based draws for fast mode)
-__device__ __forceinline__ void philox4(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t *out) {
+__device__ __noinline__ void philox4(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t *out) {
 #pragma unroll
     for (int r = 0; r < 10; r++) {
         uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
@@ -243,7 +245,7 @@ __device__ __forceinline__ void terrain_query(const TerrainDev &t, float x, floa
 }
 
 // ---- forward kinematics + body velocities + velocity-product accelerations; lane b < NB owns body b and walks its own chain
-__device__ __forceinline__ void kinematics(WS &s, const ModelDev &m, int lane) {
+__device__ __noinline__ void kinematics(WS &s, const ModelDev &m, int lane) {
     if (lane < NB) {
         const float *rt = s.rec + R_ROOT;
         float R[9], o[3], w[3], vo[3], al[3] = {0, 0, 0}, ao[3] = {0, 0, 0}, a[3] = {0, 0, 0};
@@ -251,26 +253,24 @@ __device__ __forceinline__ void kinematics(WS &s, const ModelDev &m, int lane) {
 #pragma unroll
         for (int k = 0; k < 3; k++) { o[k] = rt[k]; vo[k] = rt[7 + k]; w[k] = rt[10 + k]; }
         const int leg = (lane - 1) / CH, depth = lane == 0 ? 0 : (lane - 1) % CH + 1;
+#pragma unroll 1
+        for (int k = 0; k < depth; k++) {
+            const int j = 1 + leg * CH + k;
+            const float q = s.rec[R_DOFPOS + j - 1], qd = s.rec[R_DOFVEL + j - 1];
+            float Rj[9], Rq[9], r[3], an[3], t1[3], t2[3], t3[3], t4[3];
+            m3m(R, m.jrot[j], Rj);
+            axang2mat(m.axis[j], q, Rq);
+            m3v(R, m.jpos[j], r);
+            m3m(Rj, Rq, R);
+            m3v(R, m.axis[j], an);
+            cross3(w, r, t1);
+            cross3(al, r, t2);
+            cross3(w, t1, t3);
+            cross3(w, an, t4);
 #pragma unroll
-        for (int k = 0; k < CH; k++) {
-            if (k < depth) {
-                const int j = 1 + leg * CH + k;
-                const float q = s.rec[R_DOFPOS + j - 1], qd = s.rec[R_DOFVEL + j - 1];
-                float Rj[9], Rq[9], r[3], an[3], t1[3], t2[3], t3[3], t4[3];
-                m3m(R, m.jrot[j], Rj);
-                axang2mat(m.axis[j], q, Rq);
-                m3v(R, m.jpos[j], r);
-                m3m(Rj, Rq, R);
-                m3v(R, m.axis[j], an);
-                cross3(w, r, t1);
-                cross3(al, r, t2);
-                cross3(w, t1, t3);
-                cross3(w, an, t4);
-#pragma unroll
-                for (int i = 0; i < 3; i++) {
-                    o[i] += r[i]; vo[i] += t1[i]; ao[i] += t2[i] + t3[i];
-                    al[i] += t4[i] * qd; w[i] += an[i] * qd; a[i] = an[i];
-                }
+            for (int i = 0; i < 3; i++) {
+                o[i] += r[i]; vo[i] += t1[i]; ao[i] += t2[i] + t3[i];
+                al[i] += t4[i] * qd; w[i] += an[i] * qd; a[i] = an[i];
             }
         }
         const float *com = lane == 0 ? s.cst + C_BI + 1 : m.com[lane];
@@ -389,92 +389,25 @@ __device__ __forceinline__ void mass_and_bias(WS &s, const ModelDev &m, float gr
     __syncwarp();
 }
 
-// ---- branch-sparse Cholesky of M in place (lower factor; zero block between the two legs never fills)
-__device__ __forceinline__ void cholesky(WS &s, int lane) {
-    if (lane < 2) {
-        const int base = lane * CH;
-        float L[CH][CH];
-#pragma unroll
-        for (int i = 0; i < CH; i++)
-#pragma unroll
-            for (int j = 0; j <= i; j++) L[i][j] = s.M[base + i][base + j];
-#pragma unroll
-        for (int k = 0; k < CH; k++) {
-            float d = L[k][k];
-#pragma unroll
-            for (int p = 0; p < k; p++) d -= L[k][p] * L[k][p];
-            d = sqrtf(d);
-            const float inv = 1.0f / d;
-            L[k][k] = d;
-            s.invd[base + k] = inv;
-#pragma unroll
-            for (int i = k + 1; i < CH; i++) {
-                float t = L[i][k];
-#pragma unroll
-                for (int p = 0; p < k; p++) t -= L[i][p] * L[k][p];
-                L[i][k] = t * inv;
-            }
+// ---- Cholesky of M in place (lower factor), right-looking, rolled: lane = (row i = lane & 15, half = lane >> 4).  The zero
+// block between the two legs stays exactly zero (no fill), which chol_solve exploits.
+__device__ __noinline__ void cholesky(WS &s, int lane) {
+    const int i = lane & 15, half = lane >> 4;
+#pragma unroll 1
+    for (int k = 0; k < NV; k++) {
+        const float inv = rsqrtf(s.M[k][k]);           // all lanes: broadcast read of the pivot (updated by the previous step)
+        const float lik = s.M[i][k] * inv;               // column k of L (rows i >= k meaningful)
+        __syncwarp();
+        if (half == 0) {
+            if (i == k) { s.M[k][k] = s.M[k][k] * inv; s.invd[k] = inv; }
+            else if (i > k) s.M[i][k] = lik;
         }
-#pragma unroll
-        for (int i = 0; i < CH; i++)
-#pragma unroll
-            for (int j = 0; j <= i; j++) s.M[base + i][base + j] = L[i][j];
-    }
-    __syncwarp();
-    if (lane < 12) {  // W = C L^-T for the 6 base rows x 2 legs
-        const int i = ND + lane / 2, base = (lane % 2) * CH;
-        float W[CH];
-#pragma unroll
-        for (int k = 0; k < CH; k++) {
-            float t = s.M[i][base + k];
-#pragma unroll
-            for (int p = 0; p < k; p++) t -= W[p] * s.M[base + k][base + p];
-            W[k] = t * s.invd[base + k];
+        __syncwarp();
+        if (i > k) {                                     // trailing update of row i, columns k+1+half, step 2
+            for (int j = k + 1 + half; j <= i; j += 2) s.M[i][j] -= lik * s.M[j][k];
         }
-#pragma unroll
-        for (int k = 0; k < CH; k++) s.M[i][base + k] = W[k];
+        __syncwarp();
     }
-    __syncwarp();
-    if (lane < 21) {  // Schur complement on the base block (lower triangle)
-        int i = 0, acc = 0;
-#pragma unroll
-        for (int t = 0; t < 6; t++) if (lane >= acc + t + 1) { acc += t + 1; i = t + 1; }
-        const int j = lane - acc;
-        float t = s.M[ND + i][ND + j];
-#pragma unroll
-        for (int c = 0; c < ND; c++) t -= s.M[ND + i][c] * s.M[ND + j][c];
-        s.M[ND + i][ND + j] = t;
-    }
-    __syncwarp();
-    if (lane == 0) {
-        float L[6][6];
-#pragma unroll
-        for (int i = 0; i < 6; i++)
-#pragma unroll
-            for (int j = 0; j <= i; j++) L[i][j] = s.M[ND + i][ND + j];
-#pragma unroll
-        for (int k = 0; k < 6; k++) {
-            float d = L[k][k];
-#pragma unroll
-            for (int p = 0; p < k; p++) d -= L[k][p] * L[k][p];
-            d = sqrtf(d);
-            const float inv = 1.0f / d;
-            L[k][k] = d;
-            s.invd[ND + k] = inv;
-#pragma unroll
-            for (int i = k + 1; i < 6; i++) {
-                float t = L[i][k];
-#pragma unroll
-                for (int p = 0; p < k; p++) t -= L[i][p] * L[k][p];
-                L[i][k] = t * inv;
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 6; i++)
-#pragma unroll
-            for (int j = 0; j <= i; j++) s.M[ND + i][ND + j] = L[i][j];
-    }
-    __syncwarp();
 }
 
 // x <- M^-1 x with the factor in s.M (every lane solves its own right-hand side; reads of L are warp-broadcasts)
@@ -518,7 +451,10 @@ __device__ __forceinline__ void chol_solve(const WS &s, float *x) {
 }
 
 // ---- one dt: contacts + limits + solve + integrate.  Needs kinematics() of the current state in s.
-__device__ __forceinline__ void substep(WS &s, const ModelDev &m, const EnvArgs &A, const grx_task_cfg &cfg, int lane) {
+// Constraint rows: 3 per contact (<= KC contacts) then <= KLIM joint-limit rows, one lane per row (<= 31); lane 31 solves the
+// unconstrained update.  The projected Gauss-Seidel sweep runs in constraint space on the Delassus matrix A = J M^-1 J^T
+// (same iterates as the velocity-space sweep of oracle/phys_impl.h): all loops are rolled to keep the instruction footprint small.
+__device__ __noinline__ void substep(WS &s, const ModelDev &m, const EnvArgs &A, const grx_task_cfg &cfg, int lane) {
     const float dt = cfg.sim_dt;
     mass_and_bias(s, m, cfg.gravity, lane);
     if (A.dbg_M != nullptr && A.dbg_index == (int)(blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5))) {  // debug_dynamics: export before factorisation
@@ -586,8 +522,8 @@ __device__ __forceinline__ void substep(WS &s, const ModelDev &m, const EnvArgs 
     const int nlim = min(__popc(lbal), KLIM);
     if (lsgn != 0.f && lrank < KLIM) { s.limj[lrank] = lane; s.lims[lrank] = lsgn; s.limt[lrank] = ltgt; }
     __syncwarp();
-    const int nrow = 3 * nc + nlim;  // <= 32
-    // ---- build row lane's Jacobian, solve Y = M^-1 J^T ; lane 31 (if free) solves the unconstrained update
+    const int nrow = 3 * nc + nlim;  // <= 31
+    // ---- build row lane's Jacobian, solve Y = M^-1 J^T ; lane 31 solves the unconstrained update
     float J[NV], x[NV], bias = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; i++) J[i] = 0.f;
@@ -618,15 +554,19 @@ __device__ __forceinline__ void substep(WS &s, const ModelDev &m, const EnvArgs 
         for (int jj = 0; jj < ND; jj++) J[jj] = jj == j ? sg : 0.f;
         bias = s.limt[l];
     }
-    const bool rhs_lane = lane == 31 && nrow < 32;
+    const bool rhs_lane = lane == 31;
 #pragma unroll
     for (int i = 0; i < NV; i++) x[i] = rhs_lane ? ((i < ND ? s.tau[i] : 0.f) - s.h[i]) : J[i];
     chol_solve(s, x);
+    float invA = 0.f;
     if (lane < nrow) {
         float arr = 0.f;
 #pragma unroll
-        for (int i = 0; i < NV; i++) { s.Y[lane][i] = x[i]; arr += J[i] * x[i]; }
-        s.rowc[lane][0] = 1.0f / arr;
+        for (int i = 0; i < NV; i++) arr += J[i] * x[i];
+        invA = 1.0f / arr;
+#pragma unroll
+        for (int i = 0; i < NV; i += 4) *reinterpret_cast<float4 *>(&s.Y[lane][i]) = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
+        s.rowc[lane][0] = invA;
         s.rowc[lane][1] = bias;
     }
     const float *rs = s.rec + R_ROOT;
@@ -634,66 +574,54 @@ __device__ __forceinline__ void substep(WS &s, const ModelDev &m, const EnvArgs 
 #pragma unroll
         for (int i = 0; i < NV; i++) s.u[i] = (i < ND ? s.rec[R_DOFVEL + i] : rs[7 + i - ND]) + dt * x[i];
     }
-    if (nrow == 32) {  // all 32 lanes hold rows: second pass for the unconstrained update (warp-uniform branch)
-#pragma unroll
-        for (int i = 0; i < NV; i++) x[i] = (i < ND ? s.tau[i] : 0.f) - s.h[i];
-        chol_solve(s, x);
-        if (lane == 0) {
-#pragma unroll
-            for (int i = 0; i < NV; i++) s.u[i] = (i < ND ? s.rec[R_DOFVEL + i] : rs[7 + i - ND]) + dt * x[i];
-        }
-    }
     __syncwarp();
-    // ---- Delassus row A[lane][.] = J_lane . Y_s, and the constraint-space velocity w = J u*
-    float Arow[32], lam[32];
+    // ---- constraint-space velocity w = J u*, Delassus column block As[r][lane] = J_lane . Y_r
     float wv = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; i++) wv += J[i] * s.u[i];
-#pragma unroll
-    for (int r = 0; r < 32; r++) {
-        lam[r] = 0.f;
+#pragma unroll 2
+    for (int r = 0; r < nrow; r++) {
         float acc = 0.f;
-        if (r < nrow) {
 #pragma unroll
-            for (int i = 0; i < NV; i++) acc += J[i] * s.Y[r][i];
+        for (int i = 0; i < NV; i += 4) {
+            const float4 y = *reinterpret_cast<const float4 *>(&s.Y[r][i]);
+            acc += J[i] * y.x + J[i + 1] * y.y + J[i + 2] * y.z + J[i + 3] * y.w;
         }
-        Arow[r] = acc;
+        s.As[r][lane] = acc;
     }
-    // ---- projected Gauss-Seidel in constraint space; every lane tracks all multipliers (warp-uniform values)
+    __syncwarp();
+    // ---- projected Gauss-Seidel in constraint space.  Row r is owned by lane r; every lane evaluates the row update from the
+    // owner's (w, lambda) obtained with two independent shuffles, so the multiplier change d is warp-uniform without a third one.
+    float lam = 0.f;
+#pragma unroll 1
     for (int it = 0; it < cfg.solver_iters; it++) {
-#pragma unroll
-        for (int r = 0; r < 32; r++) {
-            if (r < nrow) {
-                const float wr = __shfl_sync(FULL, wv, r);
-                const float l0 = lam[r];
-                float ln = l0 - (wr - s.rowc[r][1]) * s.rowc[r][0];
-                if (r < 3 * nc && (r % 3) != 0) {
-                    const float lim = mu * lam[r - (r % 3)];
-                    ln = fminf(fmaxf(ln, -lim), lim);
-                } else {
-                    ln = fmaxf(ln, 0.f);
-                }
-                const float d = ln - l0;
-                lam[r] = ln;
-                wv += Arow[r] * d;
-            }
+        float lam_n = 0.f;   // multiplier of the current contact's normal row (friction pyramid bound)
+#pragma unroll 1
+        for (int r = 0; r < nrow; r++) {
+            const float wr = __shfl_sync(FULL, wv, r), l0 = __shfl_sync(FULL, lam, r);
+            const float2 rc = *reinterpret_cast<const float2 *>(s.rowc[r]);
+            float ln = l0 - (wr - rc.y) * rc.x;
+            const bool fric = r < 3 * nc && (r % 3) != 0;
+            const float lim = mu * lam_n;
+            ln = fric ? fminf(fmaxf(ln, -lim), lim) : fmaxf(ln, 0.f);
+            if (!fric) lam_n = ln;
+            const float d = ln - l0;
+            if (lane == r) lam = ln;
+            wv += s.As[r][lane] * d;
         }
     }
-    // ---- u = u* + sum_r Y_r lam_r ; own multiplier for the force report
-    float mylam = 0.f;
-#pragma unroll
-    for (int r = 0; r < 32; r++) if (r == lane) mylam = lam[r];
-    float unew = 0.f;
-    if (lane < NV) {
-        unew = s.u[lane];
-#pragma unroll
-        for (int r = 0; r < 32; r++) if (r < nrow) unew += s.Y[r][lane] * lam[r];
+    // ---- u = u* + sum_r Y_r lam_r (lane i < NV owns component i)
+    float unew = lane < NV ? s.u[lane] : 0.f;
+#pragma unroll 1
+    for (int r = 0; r < nrow; r++) {
+        const float lr = __shfl_sync(FULL, lam, r);
+        if (lane < NV) unew += s.Y[r][lane] * lr;
     }
     for (int i = lane; i < m.nl * 3; i += 32) s.cf[i] = 0.f;
     __syncwarp();
     {   // net contact force per URDF link (world frame, on the body) = impulse / dt
-        const float l0 = __shfl_sync(FULL, mylam, min(3 * lane, 31)), l1 = __shfl_sync(FULL, mylam, min(3 * lane + 1, 31)),
-                    l2 = __shfl_sync(FULL, mylam, min(3 * lane + 2, 31));
+        const float l0 = __shfl_sync(FULL, lam, min(3 * lane, 31)), l1 = __shfl_sync(FULL, lam, min(3 * lane + 1, 31)),
+                    l2 = __shfl_sync(FULL, lam, min(3 * lane + 2, 31));
         if (lane < nc) {
             const float *f = s.cfr[lane];
             const int link = s.clink[lane];
@@ -718,7 +646,7 @@ __device__ __forceinline__ void substep(WS &s, const ModelDev &m, const EnvArgs 
         const float wx = rt[10], wy = rt[11], wz = rt[12];
         const float wn = sqrtf(wx * wx + wy * wy + wz * wz), th = wn * dt;
         float sn, cs;
-        sincosf(0.5f * th, &sn, &cs);
+        __sincosf(0.5f * th, &sn, &cs);
         const float sc = wn > 1e-9f ? sn / wn : 0.5f * dt;
         const float dq[4] = {wx * sc, wy * sc, wz * sc, cs};
         float *p = rt + 3;
@@ -726,7 +654,7 @@ __device__ __forceinline__ void substep(WS &s, const ModelDev &m, const EnvArgs 
         const float qy = dq[3] * p[1] - dq[0] * p[2] + dq[1] * p[3] + dq[2] * p[0];
         const float qz = dq[3] * p[2] + dq[0] * p[1] - dq[1] * p[0] + dq[2] * p[3];
         const float qw = dq[3] * p[3] - dq[0] * p[0] - dq[1] * p[1] - dq[2] * p[2];
-        const float nn = 1.0f / sqrtf(qx * qx + qy * qy + qz * qz + qw * qw);
+        const float nn = rsqrtf(qx * qx + qy * qy + qz * qz + qw * qw);
         p[0] = qx * nn; p[1] = qy * nn; p[2] = qz * nn; p[3] = qw * nn;
     }
     __syncwarp();
@@ -848,19 +776,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) env_step_kernel(const _
     float foot_z = 0.f;
     float torso_q[4] = {0, 0, 0, 1};
     if (PHYS) {
-        kinematics(s, m, lane);
-        for (int deci = 0; deci < cfg.decimation; deci++) {
-            if (lane < nd) {   // _compute_torques (legged_robot.py:691-713) with the action delay of FF:58-61
-                const float a = ((float)deci < A.delay) ? last_act_l : act_l;
-                float t = m.kp[lane] * (a * cfg.action_scale + m.q0[lane] - s.rec[R_DOFPOS + lane]) - m.kd[lane] * s.rec[R_DOFVEL + lane];
-                t *= s.cst[C_MOTOR + lane];
-                const float lim = m.dof_effort[lane];
-                s.tau[lane] = fminf(fmaxf(t, -lim), lim);
-            }
-            __syncwarp();
-            substep(s, m, A, cfg, lane);
+#pragma unroll 1
+        for (int deci = 0; deci <= cfg.decimation; deci++) {
             kinematics(s, m, lane);
-            if (lane < NF) {
+            if (deci > 0 && lane < NF) {   // foot statistics of the substep just integrated (FF:79-81)
                 const int l = m.foot_link[lane], b = m.foot_body[lane];
                 float r[3], t[3];
                 m3v(s.R[b], m.foot_pos[lane], r);
@@ -871,6 +790,16 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) env_step_kernel(const _
                 for (int k = 0; k < 3; k++) fl_acc[k] += fabsf(s.vo[b][k] + t[k]);
                 foot_z = s.o[b][2] + r[2];
             }
+            if (deci == cfg.decimation) break;
+            if (lane < nd) {   // _compute_torques (legged_robot.py:691-713) with the action delay of FF:58-61
+                const float a = ((float)deci < A.delay) ? last_act_l : act_l;
+                float t = m.kp[lane] * (a * cfg.action_scale + m.q0[lane] - s.rec[R_DOFPOS + lane]) - m.kd[lane] * s.rec[R_DOFVEL + lane];
+                t *= s.cst[C_MOTOR + lane];
+                const float lim = m.dof_effort[lane];
+                s.tau[lane] = fminf(fmaxf(t, -lim), lim);
+            }
+            __syncwarp();
+            substep(s, m, A, cfg, lane);
         }
         if (A.dbg_M != nullptr) return;
         const float invd = 1.0f / (float)cfg.decimation;
@@ -928,7 +857,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) env_step_kernel(const _
     }
     __syncwarp();
     // ---- _get_heights (legged_robot.py:1235-1274): trunc-to-int grid index, min of 3 samples
-    float *mh = &s.Y[0][0];   // [num_height_points]
+    float *mh = &s.As[0][0];   // [num_height_points] (the Delassus block is dead after the physics)
     const int H = cfg.num_height_points;
     if (cfg.measure_heights && A.terrain.type != 0) {
         float qz = base_quat[2], qw = base_quat[3];
@@ -1103,7 +1032,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) env_step_kernel(const _
     const float hm = cfg.obs_scale_height;
     const float z_new = rec[R_ROOT + 2];
     float bsum = 0.f;
-    float *pri = s.pri;
+    float *pri = &s.Y[0][0];   // privileged-observation row staging (Y is dead after the physics)
     const int O = cfg.num_obs;
     for (int k = lane; k < H; k += 32) {
         const float off = fminf(fmaxf(z_new - cfg.base_height_target - mh[k], -1.f), 1.f) * hm;
@@ -1112,7 +1041,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) env_step_kernel(const _
     }
     bsum = warp_sum(bsum);
     const float bho = bsum / (float)H;
-    float *ob = &s.Y[0][0] + NHMAX;   // unclipped, noise-free obs staging [num_obs]
+    float *ob = &s.As[0][0] + NHMAX;   // unclipped, noise-free obs staging [num_obs]
     if (lane < 3) {
         ob[lane] = rec[R_CMD + lane] * 1.0f;                                         // commands * commands_scale (ones, G1:125)
         ob[3 + lane] = w_b[lane] * cfg.obs_scale_ang_vel;
@@ -1167,7 +1096,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) env_step_kernel(const _
     __syncwarp();
     if (lane == 0) {
         bulk_s2g(A.rec + (size_t)e * REC_F, s.rec, REC_F * 4);
-        bulk_s2g(A.pri_obs + (size_t)e * cfg.num_pri_obs, s.pri, (uint32_t)cfg.num_pri_obs * 4);
+        bulk_s2g(A.pri_obs + (size_t)e * cfg.num_pri_obs, &s.Y[0][0], (uint32_t)cfg.num_pri_obs * 4);
         bulk_commit_wait();
     }
 }
