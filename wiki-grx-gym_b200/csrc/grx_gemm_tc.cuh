@@ -13,7 +13,10 @@
 //   B_KMAJ: B(k,n) = B[n*ldb + k]                              else  B[k*ldb + n]
 // Shared-memory layouts (bytes; rows = 128 for A, BN for B; one chunk = 32 k):
 //   K-major : off(r,k) = (r%8)*16 + (r/8)*128 + (k/4)*LBO + (k%4)*4,  LBO = rows*16 + 16 (the +16 staggers banks), SBO = 128
-//   MN-major: off(r,k) = (r%4)*4 + (k%8)*16 + (r/4)*SBO + (k/8)*LBO,  SBO = 144 (128 + 16 stagger), LBO = (rows/4)*144
+//   MN-major: TF32 operands that are contiguous along M/N exist in ONE canonical form only, SWIZZLE_128B_BASE32B: atoms of
+//             32 (mn) x 4 (k) elements = 4 rows of 128 B with the 32-byte units of a row XOR-ed with the row index
+//             (byte address bits [5,7) ^= bits [7,9)); atoms are LBO = 512 B apart along mn and SBO = (rows/32)*512 B apart along k:
+//             off(r,k) = (k/4)*SBO + (r/32)*512 + (k%4)*128 + ((((r%32)/8) ^ (k%4)) * 32) + (r%8)*4   (rows padded to 32)
 // Requirements checked by the host launcher: lda/ldb/ldc % 4 == 0, 16-byte aligned bases, N-extent of MN-major operands
 // and K-extent of K-major operands multiples of 4, BN % 16 == 0, 16 <= BN <= 256.
 #pragma once
@@ -71,13 +74,15 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float *v) {
     for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
 // shared-memory matrix descriptor, SWIZZLE_NONE, version 1 (sm_100): start[0,14) LBO[16,30) SBO[32,46) (all >> 4)
-__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+// layout type [61,64): 0 = SWIZZLE_NONE (K-major tiles here), 1 = SWIZZLE_128B_BASE32B (MN-major TF32 tiles)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout_type) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46) |
+           ((uint64_t)layout_type << 61);
 }
 __device__ __forceinline__ float elu_f(float x) { return x > 0.f ? x : expm1f(x); }
 
-template <bool KMAJ> __host__ __device__ constexpr uint32_t tile_bytes(int rows) {
-    return KMAJ ? 8u * (uint32_t)(rows * 16 + 16) : 4u * (uint32_t)((rows / 4) * 144);
+template <bool KMAJ> __host__ __device__ constexpr uint32_t tile_bytes(int rows) {   // multiple of 1024 (swizzle atoms need 512-byte aligned tiles)
+    return KMAJ ? ((8u * (uint32_t)(rows * 16 + 16) + 1023u) & ~1023u) : (uint32_t)((rows + 31) / 32 * 32) * 128u;
 }
 
 // stage one 32-deep contraction chunk of an operand (rows = tile extent along its M/N dimension)
@@ -92,13 +97,15 @@ __device__ __forceinline__ void load_tile(uint32_t tile, const float *G, int ld,
             cp_async16(tile + (uint32_t)((r & 7) * 16 + (r >> 3) * 128) + (uint32_t)c * lbo, src, ok ? 16 : 0);
         }
     } else {
-        const int cpr = rows >> 2;   // 16-byte chunks per k row
-        const uint32_t lbo = (uint32_t)(cpr * 144);
+        const int rows32 = (rows + 31) / 32 * 32, cpr = rows32 >> 2;   // 16-byte chunks per k row (tile padded to 32 rows)
+        const uint32_t sbo = (uint32_t)(rows32 / 32) * 512u;
         for (int idx = tid; idx < cpr * TK; idx += NTHREADS) {
             const int j = idx % cpr, k = idx / cpr, gk = k0 + k, gr = row0 + j * 4;
             const bool ok = gk < kend && gr < rows_total;
             const float *src = ok ? G + (size_t)gk * ld + gr : G;
-            cp_async16(tile + (uint32_t)((k & 7) * 16 + j * 144) + (uint32_t)(k >> 3) * lbo, src, ok ? 16 : 0);
+            const uint32_t off = (uint32_t)(k >> 2) * sbo + (uint32_t)(j >> 3) * 512u + (uint32_t)(k & 3) * 128u +
+                                 ((uint32_t)((((j & 7) >> 1) ^ (k & 3))) << 5) + (uint32_t)(j & 1) * 16u;
+            cp_async16(tile + off, src, ok ? 16 : 0);
         }
     }
 }
@@ -106,7 +113,7 @@ __device__ __forceinline__ void load_tile(uint32_t tile, const float *G, int ld,
 // EPI: 0 C = acc + bias[n] | 1 C = elu(acc + bias[n]) | 2 C = acc * ELU'(aux[m,n]) | 3 split-K: C += acc (red.global.add)
 template <bool A_KMAJ, bool B_KMAJ, int EPI>
 __global__ void __launch_bounds__(NTHREADS) gemm_tf32_kernel(const Args g) {
-    extern __shared__ __align__(128) unsigned char smem[];
+    extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ __align__(8) unsigned long long bars[5];   // stage-free barriers [0..3], accumulator-ready [4]
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -115,7 +122,7 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tf32_kernel(const Args g) {
     const int kbeg = blockIdx.z * g.kchunk, kend = min(g.K, kbeg + g.kchunk);
     const int nchunks = (kend - kbeg + TK - 1) / TK;
     const uint32_t a_bytes = tile_bytes<A_KMAJ>(TM), b_bytes = tile_bytes<B_KMAJ>(BN);
-    const uint32_t stage_bytes = (a_bytes + b_bytes + 127u) & ~127u;
+    const uint32_t stage_bytes = a_bytes + b_bytes;   // both multiples of 1024
     const uint32_t smem0 = smem_u32(smem);
     const uint32_t ncols = BN <= 32 ? 32u : BN <= 64 ? 64u : BN <= 128 ? 128u : 256u;
 
@@ -135,9 +142,11 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tf32_kernel(const Args g) {
     // instruction descriptor: D fp32 [4,6)=1, A/B tf32 [7,10)=[10,13)=2, a_major bit 15, b_major bit 16 (1 = MN-major), N>>3 [17,23), M>>4 [24,29)
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_KMAJ ? 0u : 1u) << 15) | ((B_KMAJ ? 0u : 1u) << 16) |
                            ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-    const uint32_t a_lbo = A_KMAJ ? (uint32_t)(TM * 16 + 16) : (uint32_t)((TM / 4) * 144), a_sbo = A_KMAJ ? 128u : 144u;
-    const uint32_t b_lbo = B_KMAJ ? (uint32_t)(BN * 16 + 16) : (uint32_t)((BN / 4) * 144), b_sbo = B_KMAJ ? 128u : 144u;
-    const uint32_t a_step = A_KMAJ ? 2u * a_lbo : a_lbo, b_step = B_KMAJ ? 2u * b_lbo : b_lbo;   // advance per K = 8
+    const uint32_t bn32 = (uint32_t)((BN + 31) / 32);
+    const uint32_t a_lbo = A_KMAJ ? (uint32_t)(TM * 16 + 16) : 512u, a_sbo = A_KMAJ ? 128u : (uint32_t)(TM / 32) * 512u;
+    const uint32_t b_lbo = B_KMAJ ? (uint32_t)(BN * 16 + 16) : 512u, b_sbo = B_KMAJ ? 128u : bn32 * 512u;
+    const uint32_t a_step = A_KMAJ ? 2u * a_lbo : 2u * a_sbo, b_step = B_KMAJ ? 2u * b_lbo : 2u * b_sbo;   // advance per K = 8
+    const uint32_t a_type = A_KMAJ ? 0u : 1u, b_type = B_KMAJ ? 0u : 1u;
 
     auto issue_load = [&](int kb) {
         const int s = kb % S;
@@ -168,8 +177,8 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tf32_kernel(const Args g) {
             const uint32_t ta = smem0 + (uint32_t)s * stage_bytes, tb = ta + a_bytes;
 #pragma unroll
             for (int j = 0; j < TK / 8; j++) {
-                const uint64_t da = smem_desc(ta + (uint32_t)j * a_step, a_lbo, a_sbo);
-                const uint64_t db = smem_desc(tb + (uint32_t)j * b_step, b_lbo, b_sbo);
+                const uint64_t da = smem_desc(ta + (uint32_t)j * a_step, a_lbo, a_sbo, a_type);
+                const uint64_t db = smem_desc(tb + (uint32_t)j * b_step, b_lbo, b_sbo, b_type);
                 tc_mma_tf32(tmem, da, db, idesc, (kb > 0 || j > 0) ? 1u : 0u);
             }
             tc_commit(smem_u32(&bars[s]));                       // frees stage s when these MMAs have read it
@@ -254,7 +263,7 @@ inline cudaError_t launch(Args g, int splits, cudaStream_t st) {
     // N tile: whole N if it fits one tile (rounded up to 16), else 256 / 128 by divisibility
     int BN = g.N <= 256 ? (g.N + 15) / 16 * 16 : (g.N % 256 == 0 ? 256 : (g.N % 128 == 0 ? 128 : 256));
     g.BN = BN;
-    const uint32_t stage = (tile_bytes<A_KMAJ>(TM) + tile_bytes<B_KMAJ>(BN) + 127u) & ~127u;
+    const uint32_t stage = tile_bytes<A_KMAJ>(TM) + tile_bytes<B_KMAJ>(BN);
     g.stages = stage * 3 <= 110 * 1024 ? 3 : 2;
     if (splits < 1) splits = 1;
     g.kchunk = ((g.K + splits - 1) / splits + TK - 1) / TK * TK;

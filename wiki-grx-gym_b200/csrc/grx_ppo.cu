@@ -150,6 +150,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float *X, int M, int 
     }
 }
 
+thread_local cudaError_t g_launch_err = cudaSuccess;   // first failed tensor-core launch (reported by the C entry points)
+
 // Dense-layer dispatch: tcgen05 TF32 kernel when enabled and the shape / alignment allows, else the fp32 SIMT kernel.
 template <bool A_KC, bool B_KC, int EPI>
 void dense(const GemmArgs &g, int splits, bool use_tc, cudaStream_t st) {
@@ -162,7 +164,8 @@ void dense(const GemmArgs &g, int splits, bool use_tc, cudaStream_t st) {
                 const int rpb = 512;
                 colsum_kernel<<<dim3((g.M + 31) / 32, (g.K + rpb - 1) / rpb), 256, 0, st>>>(g.A, g.K, g.M, rpb, g.bias_out);   // A = dY [rows, out]
             }
-            tc::launch<A_KC, B_KC, EPI>(a, splits, st);
+            const cudaError_t e = tc::launch<A_KC, B_KC, EPI>(a, splits, st);
+            if (e != cudaSuccess && g_launch_err == cudaSuccess) g_launch_err = e;
             return;
         }
     }
@@ -817,6 +820,7 @@ extern "C" int grx_gemm_debug(int32_t variant, int32_t epi, int32_t M, int32_t N
     else if (variant == 1) { g.lda = K; g.ldb = N; dense<true, false, 2>(g, 1, use_tc != 0, st); }
     else if (variant == 2) { g.lda = M; g.ldb = N; dense<false, false, 3>(g, splits, use_tc != 0, st); }
     else return grx_set_error(GRX_E_INVALID, "grx_gemm_debug: variant must be 0, 1 or 2");
+    if (g_launch_err != cudaSuccess) { const cudaError_t e = g_launch_err; g_launch_err = cudaSuccess; return grx_set_error(GRX_E_CUDA, std::string("tensor-core GEMM launch: ") + cudaGetErrorString(e)); }
     CK(cudaGetLastError());
     return GRX_OK;
 }
