@@ -146,13 +146,12 @@ def test_minibatch_gradients_match_oracle_full_width():
              advantages=flat(st.advantages)[sel], returns=flat(st.returns)[sel], old_log_prob=flat(st.actions_log_prob)[sel],
              old_mu=flat(st.mu)[sel], old_sigma=flat(st.sigma)[sel])
     stats, grads = po.minibatch_loss_and_grads(p_new, b, 0.2, 1.0, 0.01, True)
-    got, off = alg.grads.cpu(), 0
+    got = alg.grads.cpu()
     for k, v in p_new.items():
-        n = v.numel()
+        off, n = ac._slices[k]
         gk = got[off:off + n].view(v.shape)
         scale = float(grads[k].abs().max()) + 1e-12
         np.testing.assert_allclose(gk.numpy() / scale, grads[k].numpy() / scale, rtol=0, atol=3e-4, err_msg=k)
-        off += n
     tail = alg.reduce_buf[-8:].cpu()
     np.testing.assert_allclose(float(tail[0] / tail[1]), float(stats["kl_mean"]), rtol=1e-3)
     np.testing.assert_allclose(float(tail[2] / tail[1]), float(stats["surrogate_loss"]), rtol=1e-3, atol=1e-6)
@@ -166,7 +165,7 @@ def test_gae_full_size_matches_oracle():
     tc = make_train_cfg()
     N, T = 4096, 64
     ac = ActorCriticMLP(39, 168, 10, **dict(tc["policy"], actor_hidden_dims=[32, 32, 32], critic_hidden_dims=[32, 32, 32]))
-    alg = PPO(ac, device="cuda:0", **tc["algorithm"])
+    alg = PPO(ac, device="cuda:0", use_tensor_cores=0, **tc["algorithm"])   # fp32 critic for the bootstrap value: this test pins the scan
     alg.init_storage(N, T)
     g = torch.Generator().manual_seed(3)
     st = alg.storage

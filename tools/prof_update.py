@@ -1,0 +1,35 @@
+"""Small driver for ncu: a rollout of T steps at N envs with random observations, then `nmb` minibatches of the PPO update
+(explicit grads/apply, no graph) at the registered sizes.  Usage: prof_update.py [N] [T] [nmb] [use_tc]"""
+import ctypes as C, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "wiki-grx-gym_b200")]
+import torch
+from grx_b200 import _lib as L
+from grx_b200.config import make_train_cfg
+from grx_b200.ppo import PPO, ActorCriticMLP
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+T = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+nmb = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+use_tc = int(sys.argv[4]) if len(sys.argv) > 4 else 1
+tc = make_train_cfg()
+torch.manual_seed(1)
+ac = ActorCriticMLP(39, 168, 10, **tc["policy"])
+alg = PPO(ac, device="cuda:0", use_tensor_cores=use_tc, **tc["algorithm"])
+alg.init_storage(N, T)
+obs, cobs = torch.randn(N, 39, device="cuda"), torch.randn(N, 168, device="cuda")
+for s in range(T):
+    alg.act(obs, cobs)
+    alg.process_env_step(torch.randn(N, device="cuda") * 0.1, torch.rand(N, device="cuda") < 0.01, {})
+alg.compute_returns(cobs)
+alg.draw_indices()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+for rep in range(2):
+    e0.record()
+    for mb in range(nmb):
+        L.check(alg.lib.grx_ppo_minibatch_grads(alg._h, C.c_void_p(alg._indices.data_ptr()), mb, alg._stream()))
+        L.check(alg.lib.grx_ppo_minibatch_apply(alg._h, alg._stream()))
+    e1.record()
+    torch.cuda.synchronize()
+print(f"N={N} T={T} use_tc={use_tc}: {e0.elapsed_time(e1) / nmb * 1e3:.1f} us per minibatch (B={alg.mini_batch_size})", alg.minibatch_stats())

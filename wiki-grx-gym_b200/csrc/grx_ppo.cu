@@ -158,7 +158,7 @@ void dense(const GemmArgs &g, int splits, bool use_tc, cudaStream_t st) {
     if (use_tc) {
         tc::Args a;
         a.A = g.A; a.B = g.B; a.C = g.C; a.bias = g.bias; a.aux = g.aux; a.M = g.M; a.N = g.N; a.K = g.K;
-        a.lda = g.lda; a.ldb = g.ldb; a.ldc = g.ldc; a.BN = 0; a.kchunk = 0; a.stages = 0;
+        a.lda = g.lda; a.ldb = g.ldb; a.ldc = g.ldc; a.kchunk = 0; a.stages = 0;
         if (tc::supported<A_KC, B_KC>(a)) {
             if (EPI == 3 && g.bias_out) {
                 const int rpb = 512;
@@ -549,9 +549,9 @@ static int ppo_alloc(grx_ppo *p, void **ptr, size_t bytes) {
 
 static void layout_net(Net &n, const int *dims, size_t &off) {
     for (int i = 0; i < 5; i++) n.dims[i] = dims[i];
-    for (int l = 0; l < 4; l++) {
-        n.w[l] = off; off += (size_t)dims[l + 1] * dims[l];
-        n.b[l] = off; off += (size_t)dims[l + 1];
+    for (int l = 0; l < 4; l++) {   // every tensor starts on a 16-byte boundary (cp.async / vector loads in the dense kernels)
+        off = (off + 3) & ~(size_t)3; n.w[l] = off; off += (size_t)dims[l + 1] * dims[l];
+        off = (off + 3) & ~(size_t)3; n.b[l] = off; off += (size_t)dims[l + 1];
     }
 }
 
@@ -573,9 +573,9 @@ extern "C" int grx_ppo_create(const grx_ppo_cfg *cfg, int32_t device, grx_ppo **
     const int dc[5] = {p->P, cfg->critic_hidden[0], cfg->critic_hidden[1], cfg->critic_hidden[2], 1};
     layout_net(p->actor, da, off);
     layout_net(p->critic, dc, off);
-    p->nparam = off;
+    p->nparam = (off + 3) & ~(size_t)3;
     const size_t TN = (size_t)p->T * p->N, MR = p->MR;
-    PALLOC(p->params, off * 4); PALLOC(p->reduce_buf, (off + TAIL) * 4); PALLOC(p->adam_m, off * 4); PALLOC(p->adam_v, off * 4);
+    PALLOC(p->params, p->nparam * 4); PALLOC(p->reduce_buf, (p->nparam + TAIL) * 4); PALLOC(p->adam_m, p->nparam * 4); PALLOC(p->adam_v, p->nparam * 4);
     PALLOC(p->s_obs, TN * p->O * 4); PALLOC(p->s_cobs, TN * p->P * 4); PALLOC(p->s_act, TN * p->A * 4); PALLOC(p->s_val, TN * 4);
     PALLOC(p->s_rew, TN * 4); PALLOC(p->s_logp, TN * 4); PALLOC(p->s_mu, TN * p->A * 4); PALLOC(p->s_sigma, TN * p->A * 4);
     PALLOC(p->s_ret, TN * 4); PALLOC(p->s_adv, TN * 4); PALLOC(p->s_done, TN);
@@ -689,7 +689,7 @@ extern "C" int grx_ppo_act(grx_ppo *p, const float *d_obs, const float *d_critic
     a.s_obs = p->s_obs + row * p->O; a.s_cobs = p->s_cobs + row * p->P; a.s_act = p->s_act + row * p->A; a.s_val = p->s_val + row;
     a.s_logp = p->s_logp + row; a.s_mu = p->s_mu + row * p->A; a.s_sigma = p->s_sigma + row * p->A;
     a.N = p->N; a.O = p->O; a.P = p->P; a.A = p->A; a.seed = 0x9E3779B97F4A7C15ull; a.step_index = step_index; a.env_id_offset = 0;
-    act_sample_store_kernel<<<(p->N + 127) / 128, 128, 0, st>>>(a);
+    act_sample_store_kernel<<<max((p->N + 127) / 128, 592), 128, 0, st>>>(a);
     CK(cudaGetLastError());
     return GRX_OK;
 }

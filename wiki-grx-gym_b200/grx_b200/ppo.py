@@ -73,11 +73,14 @@ class ActorCriticMLP:
     def _bind(self, ppo, flat):
         self._ppo = ppo
         views, off = OrderedDict(), 0
-        for k, v in self._host_init.items():
+        self._slices = OrderedDict()
+        for k, v in self._host_init.items():   # flat layout of csrc/grx_ppo.cu: reference state_dict order, each tensor 16-byte aligned
             n = v.numel()
+            off = (off + 3) // 4 * 4
             views[k] = flat[off:off + n].view(v.shape)
+            self._slices[k] = (off, n)
             off += n
-        assert off == flat.numel()
+        assert (off + 3) // 4 * 4 == flat.numel(), (off, flat.numel())
         self._views = views
         self.load_state_dict(self._host_init, set_std=False)
         self._host_init = None
@@ -290,27 +293,24 @@ class PPO:
 
     # ---- optimizer state in torch.optim.Adam's state_dict layout (on_policy_runner.py:297-331)
     def optimizer_state_dict(self):
-        state, off = {}, 0
+        state = {}
         step = float(self.adam_step)
         for i, (k, v) in enumerate(self.actor_critic.state_dict().items()):
-            n = v.numel()
+            off, n = self.actor_critic._slices[k]
             state[i] = {"step": torch.tensor(step), "exp_avg": self.adam_m[off:off + n].view(v.shape).clone(),
                         "exp_avg_sq": self.adam_v[off:off + n].view(v.shape).clone()}
-            off += n
         group = {"lr": self.learning_rate, "betas": (0.9, 0.999), "eps": 1e-8, "weight_decay": 0, "amsgrad": False,
                  "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
                  "params": list(range(len(state)))}
         return {"state": state, "param_groups": [group]}
 
     def load_optimizer_state_dict(self, sd):
-        off = 0
         for i, (k, v) in enumerate(self.actor_critic.state_dict().items()):
-            n = v.numel()
+            off, n = self.actor_critic._slices[k]
             if i in sd["state"]:
                 self.adam_m[off:off + n].copy_(sd["state"][i]["exp_avg"].reshape(-1).to(self.device))
                 self.adam_v[off:off + n].copy_(sd["state"][i]["exp_avg_sq"].reshape(-1).to(self.device))
                 step = int(float(sd["state"][i]["step"]))
-            off += n
         if sd["state"]:
             self.ctl[3:4].view(torch.int32).fill_(step)
         self.learning_rate = sd["param_groups"][0]["lr"]
