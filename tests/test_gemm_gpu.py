@@ -97,11 +97,11 @@ def test_tensor_core_update_matches_simt_update():
         alg._indices.copy_(torch.randperm(N * T, generator=g).cuda())
         L.check(alg.lib.grx_ppo_minibatch_grads(alg._h, C.c_void_p(alg._indices.data_ptr()), 0, alg._stream()))
         torch.cuda.synchronize()
-        grads.append((alg.grads.clone(), [(k,) + ac._slices[k] for k in ac.state_dict()]))
-    (g0, names), (g1, _) = grads
+        grads.append({k: ac.view_of(alg.grads, k).clone() for k in ac.state_dict()})
+    g0, g1 = grads
     worst = {}
-    for k, off, n in names:
-        a, b = g0[off:off + n], g1[off:off + n]
+    for k in g0:
+        a, b = g0[k], g1[k]
         worst[k] = float((a - b).abs().max()) / (float(a.abs().max()) + 1e-12)
     # three TF32 layers forward and three backward: operand rounding 2^-11 per product, accumulated over both passes
     assert max(worst.values()) <= 1e-2, worst

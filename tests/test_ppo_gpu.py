@@ -148,8 +148,7 @@ def test_minibatch_gradients_match_oracle_full_width():
     stats, grads = po.minibatch_loss_and_grads(p_new, b, 0.2, 1.0, 0.01, True)
     got = alg.grads.cpu()
     for k, v in p_new.items():
-        off, n = ac._slices[k]
-        gk = got[off:off + n].view(v.shape)
+        gk = ac.view_of(got, k)
         scale = float(grads[k].abs().max()) + 1e-12
         np.testing.assert_allclose(gk.numpy() / scale, grads[k].numpy() / scale, rtol=0, atol=3e-4, err_msg=k)
     tail = alg.reduce_buf[-8:].cpu()

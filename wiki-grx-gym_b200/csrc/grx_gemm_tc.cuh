@@ -2,51 +2,52 @@
 //
 //   C[m,n] (op)= sum_k A(m,k) B(k,n)        fp32 in HBM, TF32 multiply, fp32 accumulate in TMEM
 //
-// One CTA (8 warps) per 128 x BN output tile (BN = 128 / 64 / 32, two CTAs per SM so one tile's epilogue overlaps the other's
-// main loop).  The contraction runs in chunks of 32: every thread stages its fixed slots of the A / B chunk into shared
-// memory with 16-byte cp.async (zero-filled at the edges) directly in the UMMA canonical layouts below, one elected thread
-// issues 4 x tcgen05.mma.kind::tf32 (K = 8 each) per chunk and commits them to an mbarrier that releases the stage; the
-// accumulator never leaves TMEM until the epilogue reads it back with tcgen05.ld (32 lanes x 32 bit x 16 columns per
-// instruction; warp w reads lane quadrant w % 4, column half w / 4) and applies bias / ELU / ELU' / split-K reduction.
-// Both operand majors are supported through the shared-memory descriptors, so the three GEMM shapes of an MLP layer
-// (forward X W^T, input gradient dY W, weight gradient dY^T X) run on the same kernel without transposed copies:
+// One CTA per 128 x BN output tile (BN = 128 / 64 / 32; two CTAs per SM so one tile's epilogue overlaps the other's main
+// loop), 10 warps with fixed roles:
+//   warp 8, one lane  TMA producer: per 32-deep contraction chunk it arms the stage's `full` mbarrier with the byte count
+//                     (mbarrier.arrive.expect_tx) and issues cp.async.bulk.tensor.2d loads for the A and B boxes; TMA writes the
+//                     boxes straight into the UMMA canonical shared-memory layouts and zero-fills everything out of bounds
+//                     (ragged M / N / K need no predication anywhere);
+//   warp 9, one lane  MMA issuer: waits `full`, issues 4 x tcgen05.mma.cta_group::1.kind::tf32 (K = 8 each) on shared-memory
+//                     descriptors, then tcgen05.commit -> the stage's `empty` mbarrier (and the accumulator barrier at the end);
+//   warps 0-7         epilogue: tcgen05.ld 32x32b.x16 from TMEM (warp w: lane quadrant w % 4, column half w / 4), then
+//                     bias / ELU / ELU' / split-K red.global.add.v4.f32, 16-byte stores.
+// Both operand majors are supported, so the three GEMM shapes of an MLP layer (forward X W^T, input gradient dY W, weight
+// gradient dY^T X) run on this kernel without transposed copies:
 //   A_KMAJ: A(m,k) = A[m*lda + k]  (contraction contiguous)   else  A[k*lda + m]
 //   B_KMAJ: B(k,n) = B[n*ldb + k]                              else  B[k*ldb + n]
-// Shared-memory layouts (bytes; rows = 128 for A, BN for B; one chunk = 32 k):
-//   K-major : off(r,k) = (r%8)*16 + (r/8)*128 + (k/4)*LBO + (k%4)*4,  LBO = rows*16 + 16 (the +16 staggers banks), SBO = 128
-//   MN-major: TF32 operands that are contiguous along M/N exist in ONE canonical form only, SWIZZLE_128B_BASE32B: atoms of
-//             32 (mn) x 4 (k) elements = 4 rows of 128 B with the 32-byte units of a row XOR-ed with the row index
-//             (byte address bits [5,7) ^= bits [7,9)); atoms are LBO = 512 B apart along mn and SBO = (rows/32)*512 B apart along k:
-//             off(r,k) = (k/4)*SBO + (r/32)*512 + (k%4)*128 + ((((r%32)/8) ^ (k%4)) * 32) + (r%8)*4   (rows padded to 32)
-// Requirements checked by the host launcher: lda/ldb/ldc % 4 == 0, 16-byte aligned bases, N-extent of MN-major operands
-// and K-extent of K-major operands multiples of 4, BN % 16 == 0, 16 <= BN <= 256.
+// Shared-memory layouts (one chunk = 32 k; rows = 128 for A, BN for B):
+//   K-major : TMA box {32 k, rows}, CU_TENSOR_MAP_SWIZZLE_128B  == UMMA SWIZZLE_128B K-major: rows of 128 B, the 16-byte units of a
+//             row XOR-ed with (row % 8); SBO = 1024 B (8 rows); one MMA (K = 8) advances the descriptor start by 32 B.
+//   MN-major: TF32 operands contiguous along M/N exist in ONE canonical form, UMMA SWIZZLE_128B_BASE32B == TMA box {32 mn, 32 k},
+//             CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B: k rows of 128 B (32 mn), the 32-byte units of a row XOR-ed with (row % 4);
+//             one box per 32 mn columns (4 KB): atoms of 4 k rows are SBO = 512 B apart, mn blocks LBO = 4096 B apart; one MMA
+//             (K = 8 = two atoms) advances the start by 1024 B.
+// Requirements (checked by supported()): 16-byte aligned bases, leading dimensions % 4 == 0, N % 4 == 0.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <mutex>
+#include <unordered_map>
+
 namespace tc {
 
-constexpr int TM = 128, TK = 32, NTHREADS = 256, NTHREADS_CTA = 288;   // 8 producer / epilogue warps + 1 MMA-issuing warp
+constexpr int TM = 128, TK = 32, NTHREADS_CTA = 320;   // 8 epilogue warps + TMA warp + MMA warp
 
 struct Args {
-    const float *A, *B;
     float *C;
     const float *bias;   // EPI 0/1: [N]
     const float *aux;    // EPI 2: same layout as C
-    int M, N, K, lda, ldb, ldc;
+    float *colsum;       // EPI 2, optional: colsum[n] += sum over rows of the stored C (bias gradient of the layer below)
+    int M, N, K, ldc;
     int kchunk;          // contraction elements per blockIdx.z (multiple of 32)
-    int stages;
     int dbg;             // profiling switches (GRX_TC_DEBUG): 1 skip MMA issue, 2 skip operand loads, 4 skip epilogue stores
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, int src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok = 0;
@@ -54,6 +55,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     }
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+// TMA: 2-D tiled box load global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -75,8 +85,8 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float *v) {
 #pragma unroll
     for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
-// shared-memory matrix descriptor, SWIZZLE_NONE, version 1 (sm_100): start[0,14) LBO[16,30) SBO[32,46) (all >> 4)
-// layout type [61,64): 0 = SWIZZLE_NONE (K-major tiles here), 1 = SWIZZLE_128B_BASE32B (MN-major TF32 tiles)
+// shared-memory matrix descriptor, version 1 (sm_100): start[0,14) LBO[16,30) SBO[32,46) (all >> 4), layout type [61,64):
+// 2 = SWIZZLE_128B (K-major tiles), 1 = SWIZZLE_128B_BASE32B (MN-major TF32 tiles)
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout_type) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46) |
            ((uint64_t)layout_type << 61);
@@ -84,66 +94,25 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo, uint
 // ELU on the tensor-core path: ex2.approx based exp; abs error ~1e-7, far below the TF32 operand rounding (2^-11 relative)
 __device__ __forceinline__ float elu_f(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
 
-template <bool KMAJ> __host__ __device__ constexpr uint32_t tile_bytes(int rows) {   // multiple of 1024 (swizzle atoms need 512-byte aligned tiles)
-    return KMAJ ? ((8u * (uint32_t)(rows * 16 + 16) + 1023u) & ~1023u) : (uint32_t)((rows + 31) / 32 * 32) * 128u;
-}
-
-// One operand's share of a 32-deep contraction chunk for this thread: CNT fixed 16-byte slots (source pointer, smem offset).
-template <bool KMAJ, int ROWS>
-struct Slots {
-    static constexpr int CNT = ROWS * 8 / NTHREADS;
-    const float *src[CNT];
-    uint32_t dst[CNT];
-    int kofs[CNT];      // k offset of the slot inside a chunk
-    bool ok[CNT];       // row (M / N extent) in range
-    size_t step;        // source advance per chunk (elements)
-    const float *base;  // always-valid address for zero-filled slots
-    __device__ __forceinline__ void init(const float *G, int ld, int row0, int rows_total, int kbeg, int tid) {
-        base = G;
-#pragma unroll
-        for (int i = 0; i < CNT; i++) {
-            const int idx = tid + i * NTHREADS;
-            if (KMAJ) {
-                const int r = idx >> 3, c = idx & 7, gr = row0 + r;
-                ok[i] = gr < rows_total; kofs[i] = c * 4;
-                src[i] = G + (size_t)(ok[i] ? gr : 0) * ld + kbeg + c * 4;
-                dst[i] = (uint32_t)((r & 7) * 16 + (r >> 3) * 128) + (uint32_t)c * (uint32_t)(ROWS * 16 + 16);
-            } else {
-                constexpr int cpr = ROWS / 4;
-                const int j = idx % cpr, k = idx / cpr, gr = row0 + j * 4;
-                ok[i] = gr < rows_total; kofs[i] = k;
-                src[i] = G + (size_t)(kbeg + k) * ld + (ok[i] ? gr : 0);
-                dst[i] = (uint32_t)(k >> 2) * (uint32_t)(ROWS / 32 * 512) + (uint32_t)(j >> 3) * 512u + (uint32_t)(k & 3) * 128u +
-                         ((uint32_t)((((j & 7) >> 1) ^ (k & 3))) << 5) + (uint32_t)(j & 1) * 16u;
-            }
-        }
-        step = KMAJ ? (size_t)TK : (size_t)TK * ld;
-    }
-    __device__ __forceinline__ void issue(uint32_t tile, int k0, int kend) {
-#pragma unroll
-        for (int i = 0; i < CNT; i++) {
-            const bool v = ok[i] && (k0 + kofs[i] < kend);
-            cp_async16(tile + dst[i], v ? src[i] : base, v ? 16 : 0);
-            src[i] += step;
-        }
-    }
-};
+__host__ __device__ constexpr uint32_t tile_bytes(int rows) { return (uint32_t)rows * 128u; }   // rows x 32 fp32, either major
 
 // EPI: 0 C = acc + bias[n] | 1 C = elu(acc + bias[n]) | 2 C = acc * ELU'(aux[m,n]) | 3 split-K: C += acc (red.global.add)
 template <bool A_KMAJ, bool B_KMAJ, int EPI, int BN, int S>
-__global__ void __launch_bounds__(NTHREADS_CTA, 2) gemm_tf32_kernel(const Args g) {
+__global__ void __launch_bounds__(NTHREADS_CTA, 2) gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                                                                    const Args g) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ __align__(8) unsigned long long full_bar[S], empty_bar[S], accum_bar;
     __shared__ uint32_t tmem_slot;
+    __shared__ float colsum_s[BN];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = blockIdx.y * TM, n0 = blockIdx.x * BN;
     const int kbeg = blockIdx.z * g.kchunk, kend = min(g.K, kbeg + g.kchunk);
     const int nchunks = (kend - kbeg + TK - 1) / TK;
-    constexpr uint32_t a_bytes = tile_bytes<A_KMAJ>(TM), b_bytes = tile_bytes<B_KMAJ>(BN), stage_bytes = a_bytes + b_bytes;
-    const uint32_t smem0 = smem_u32(smem);
+    constexpr uint32_t a_bytes = tile_bytes(TM), b_bytes = tile_bytes(BN), stage_bytes = a_bytes + b_bytes;
+    const uint32_t smem0 = (smem_u32(smem) + 1023u) & ~1023u;   // swizzle atoms need 1024-byte aligned tiles
 
     if (tid == 0) {
-        for (int i = 0; i < S; i++) { mbar_init(smem_u32(&full_bar[i]), 8); mbar_init(smem_u32(&empty_bar[i]), 1); }
+        for (int i = 0; i < S; i++) { mbar_init(smem_u32(&full_bar[i]), 1); mbar_init(smem_u32(&empty_bar[i]), 1); }
         mbar_init(smem_u32(&accum_bar), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -151,176 +120,225 @@ __global__ void __launch_bounds__(NTHREADS_CTA, 2) gemm_tf32_kernel(const Args g
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(BN) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    if (warp == 8 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
 
-    // instruction descriptor: D fp32 [4,6)=1, A/B tf32 [7,10)=[10,13)=2, a_major bit 15, b_major bit 16 (1 = MN-major), N>>3 [17,23), M>>4 [24,29)
-    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_KMAJ ? 0u : 1u) << 15) | ((B_KMAJ ? 0u : 1u) << 16) |
-                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-    constexpr uint32_t a_lbo = A_KMAJ ? (uint32_t)(TM * 16 + 16) : 512u, a_sbo = A_KMAJ ? 128u : (uint32_t)(TM / 32) * 512u;
-    constexpr uint32_t b_lbo = B_KMAJ ? (uint32_t)(BN * 16 + 16) : 512u, b_sbo = B_KMAJ ? 128u : (uint32_t)(BN / 32) * 512u;
-    constexpr uint32_t a_step = A_KMAJ ? 2u * a_lbo : 2u * a_sbo, b_step = B_KMAJ ? 2u * b_lbo : 2u * b_sbo;   // advance per K = 8
-    constexpr uint32_t a_type = A_KMAJ ? 0u : 1u, b_type = B_KMAJ ? 0u : 1u;
-
-    // Warp-specialised main loop, no CTA-wide barrier inside:
-    //   warps 0-7 (256 threads) = producers: wait for the stage to be free, issue their cp.async slots, and let the stage's `full`
-    //     mbarrier track their completion (cp.async.mbarrier.arrive.noinc) — they run up to S chunks ahead of the tensor core;
-    //   warp 8, one lane     = MMA issuer: wait `full`, proxy fence, 4 x tcgen05.mma, tcgen05.commit -> `empty` (frees the stage).
-    if (warp < 8) {
-        Slots<A_KMAJ, TM> sa;
-        Slots<B_KMAJ, BN> sb;
-        sa.init(g.A, g.lda, m0, g.M, kbeg, tid);
-        sb.init(g.B, g.ldb, n0, g.N, kbeg, tid);
-        // Each thread keeps up to S - 1 of its own cp.async groups in flight; once the group of chunk kb - (S-1) has landed for
-        // every lane of the warp, ONE lane arrives on that stage's `full` barrier (8 arrivals per stage instead of 256).
-        constexpr int D = S - 1;
-        for (int kb = 0; kb < nchunks + D; kb++) {
-            if (kb < nchunks) {
+    if (warp == 8) {
+        if (lane == 0) {   // ---- TMA producer
+            for (int kb = 0; kb < nchunks; kb++) {
                 const int st = kb % S;
                 if (kb >= S) mbar_wait(smem_u32(&empty_bar[st]), (uint32_t)(((kb / S) - 1) & 1));
-                const uint32_t ta = smem0 + (uint32_t)st * stage_bytes;
+                const uint32_t ta = smem0 + (uint32_t)st * stage_bytes, tb = ta + a_bytes, bar = smem_u32(&full_bar[st]);
                 const int k0 = kbeg + kb * TK;
-                if (!(g.dbg & 2)) {
-                    sa.issue(ta, k0, kend);
-                    sb.issue(ta + a_bytes, k0, kend);
+                if (g.dbg & 2) { mbar_arrive(bar); continue; }
+                mbar_expect_tx(bar, stage_bytes);
+                if (A_KMAJ) tma_load_2d(ta, &map_a, k0, m0, bar);
+                else {
+#pragma unroll
+                    for (int j = 0; j < TM / 32; j++) tma_load_2d(ta + (uint32_t)j * 4096u, &map_a, m0 + 32 * j, k0, bar);
+                }
+                if (B_KMAJ) tma_load_2d(tb, &map_b, k0, n0, bar);
+                else {
+#pragma unroll
+                    for (int j = 0; j < BN / 32; j++) tma_load_2d(tb + (uint32_t)j * 4096u, &map_b, n0 + 32 * j, k0, bar);
                 }
             }
-            cp_async_commit();
-            if (kb >= D) {
-                cp_async_wait<D>();      // this thread's group for chunk kb - D is complete
-                fence_proxy_async();     // its smem writes -> visible to the async proxy (tensor core)
-                __syncwarp();
-                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_bar[(kb - D) % S])) : "memory");
-            }
         }
-    } else if (lane == 0) {
-        for (int kb = 0; kb < nchunks; kb++) {
-            const int st = kb % S;
-            mbar_wait(smem_u32(&full_bar[st]), (uint32_t)((kb / S) & 1));
-            fence_proxy_async();   // generic-proxy (cp.async) writes -> visible to the tensor core (async proxy)
-            tc_fence_after();
-            const uint32_t ta = smem0 + (uint32_t)st * stage_bytes, tb = ta + a_bytes;
+    } else if (warp == 9) {
+        if (lane == 0) {   // ---- MMA issuer
+            // instruction descriptor: D fp32 [4,6)=1, A/B tf32 [7,10)=[10,13)=2, a_major bit 15, b_major bit 16 (1 = MN-major), N>>3 [17,23), M>>4 [24,29)
+            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_KMAJ ? 0u : 1u) << 15) | ((B_KMAJ ? 0u : 1u) << 16) |
+                                       ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+            constexpr uint32_t a_lbo = A_KMAJ ? 16u : 4096u, a_sbo = A_KMAJ ? 1024u : 512u, a_step = A_KMAJ ? 32u : 1024u, a_type = A_KMAJ ? 2u : 1u;
+            constexpr uint32_t b_lbo = B_KMAJ ? 16u : 4096u, b_sbo = B_KMAJ ? 1024u : 512u, b_step = B_KMAJ ? 32u : 1024u, b_type = B_KMAJ ? 2u : 1u;
+            for (int kb = 0; kb < nchunks; kb++) {
+                const int st = kb % S;
+                mbar_wait(smem_u32(&full_bar[st]), (uint32_t)((kb / S) & 1));
+                tc_fence_after();
+                const uint32_t ta = smem0 + (uint32_t)st * stage_bytes, tb = ta + a_bytes;
 #pragma unroll
-            for (int j = 0; j < TK / 8; j++) {
-                const uint64_t da = smem_desc(ta + (uint32_t)j * a_step, a_lbo, a_sbo, a_type);
-                const uint64_t db = smem_desc(tb + (uint32_t)j * b_step, b_lbo, b_sbo, b_type);
-                if (!(g.dbg & 1)) tc_mma_tf32(tmem, da, db, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+                for (int j = 0; j < TK / 8; j++) {
+                    const uint64_t da = smem_desc(ta + (uint32_t)j * a_step, a_lbo, a_sbo, a_type);
+                    const uint64_t db = smem_desc(tb + (uint32_t)j * b_step, b_lbo, b_sbo, b_type);
+                    if (!(g.dbg & 1)) tc_mma_tf32(tmem, da, db, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+                }
+                tc_commit(smem_u32(&empty_bar[st]));                      // frees the stage when these MMAs have read it
+                if (kb == nchunks - 1) tc_commit(smem_u32(&accum_bar));   // accumulator complete
             }
-            tc_commit(smem_u32(&empty_bar[st]));                      // frees the stage when these MMAs have read it
-            if (kb == nchunks - 1) tc_commit(smem_u32(&accum_bar));   // accumulator complete
         }
-    }
-    if (warp < 8) {
-    // ---- epilogue: warp w owns TMEM lanes [32 (w%4), +32) = output rows m0 + 32 (w%4) + lane, and column half w/4
-    if (nchunks > 0) mbar_wait(smem_u32(&accum_bar), 0);
-    tc_fence_after();
-    const int quad = warp & 3, chalf = warp >> 2;
-    const int m = m0 + quad * 32 + lane;
+    } else {
+        // ---- epilogue, two phases so that every global access is a full coalesced row segment:
+        //  1. TMEM -> registers -> shared (warp w reads TMEM lanes [32 (w%4), +32) = tile rows, column half w/4; the pipeline
+        //     stages are free by now and hold the 128 x BN fp32 tile with a 16-byte row pad: conflict-free float4 stores);
+        //  2. each warp streams 16 tile rows shared -> global with lane = 4 consecutive columns: bias / ELU / ELU' (aux read with
+        //     the same coalesced pattern) / split-K red.global.add.v4.f32.
+        if (nchunks > 0) mbar_wait(smem_u32(&accum_bar), 0);
+        tc_fence_after();
+        constexpr int PITCH = BN + 4;   // floats
+        float *tile = reinterpret_cast<float *>(smem + (smem0 - smem_u32(smem)));
+        {
+            const int quad = warp & 3, chalf = warp >> 2, r = quad * 32 + lane;
 #pragma unroll 1
-    for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 16) {
-        if (n0 + c0 >= g.N) break;   // warp-uniform
-        float v[16];
-        if (nchunks > 0) tc_ld16(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
-        else {
+            for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 16) {
+                float v[16];
+                if (nchunks > 0) tc_ld16(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
+                else {
 #pragma unroll
-            for (int i = 0; i < 16; i++) v[i] = 0.f;
+                    for (int i = 0; i < 16; i++) v[i] = 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4 *>(tile + r * PITCH + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
         }
-        if (m < g.M && !(g.dbg & 4)) {
-            float *crow = g.C + (size_t)m * g.ldc + n0 + c0;
-            const int nvalid = min(16, g.N - (n0 + c0));
-            if (EPI == 3) {
-                if (nvalid == 16) {
-#pragma unroll
-                    for (int i = 0; i < 16; i += 4)
-                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow + i), "f"(v[i]), "f"(v[i + 1]), "f"(v[i + 2]), "f"(v[i + 3]) : "memory");
+        if (EPI == 2 && tid < BN) colsum_s[tid] = 0.f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 epilogue warps only
+        float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);    // EPI 2: a lane always owns the same 4 columns (32 % (BN/4) == 0)
+        if (!(g.dbg & 4)) {
+            constexpr int V4 = BN / 4;                    // float4 per tile row
+#pragma unroll 1
+            for (int idx = lane; idx < 16 * V4; idx += 32) {
+                const int r = warp * 16 + idx / V4, c = (idx % V4) * 4;
+                const int m = m0 + r, n = n0 + c;
+                if (m >= g.M || n >= g.N) continue;       // N % 4 == 0: a float4 is either fully valid or fully out
+                float4 v = *reinterpret_cast<const float4 *>(tile + r * PITCH + c);
+                float *dst = g.C + (size_t)m * g.ldc + n;
+                if (EPI == 3) {
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
                 } else {
-                    for (int i = 0; i < nvalid; i++) atomicAdd(crow + i, v[i]);
-                }
-            } else {
-                if (EPI == 0 || EPI == 1) {
-                    if (nvalid == 16) {
-#pragma unroll
-                        for (int i = 0; i < 16; i += 4) {
-                            const float4 b = __ldg(reinterpret_cast<const float4 *>(g.bias + n0 + c0 + i));
-                            v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
-                        }
-                        if (EPI == 1) {
-#pragma unroll
-                            for (int i = 0; i < 16; i++) v[i] = elu_f(v[i]);
-                        }
+                    if (EPI == 0 || EPI == 1) {
+                        const float4 bb = __ldg(reinterpret_cast<const float4 *>(g.bias + n));
+                        v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+                        if (EPI == 1) { v.x = elu_f(v.x); v.y = elu_f(v.y); v.z = elu_f(v.z); v.w = elu_f(v.w); }
                     } else {
-                        for (int i = 0; i < nvalid; i++) { const float x = v[i] + __ldg(g.bias + n0 + c0 + i); v[i] = EPI == 1 ? elu_f(x) : x; }
+                        const float4 h = *reinterpret_cast<const float4 *>(g.aux + (size_t)m * g.ldc + n);
+                        v.x *= h.x > 0.f ? 1.f : h.x + 1.f; v.y *= h.y > 0.f ? 1.f : h.y + 1.f;
+                        v.z *= h.z > 0.f ? 1.f : h.z + 1.f; v.w *= h.w > 0.f ? 1.f : h.w + 1.f;
+                        csum.x += v.x; csum.y += v.y; csum.z += v.z; csum.w += v.w;
                     }
-                } else {
-                    const float *arow = g.aux + (size_t)m * g.ldc + n0 + c0;
-                    if (nvalid == 16) {
-#pragma unroll
-                        for (int i = 0; i < 16; i += 4) {
-                            const float4 h = *reinterpret_cast<const float4 *>(arow + i);
-                            v[i] *= h.x > 0.f ? 1.f : h.x + 1.f; v[i + 1] *= h.y > 0.f ? 1.f : h.y + 1.f;
-                            v[i + 2] *= h.z > 0.f ? 1.f : h.z + 1.f; v[i + 3] *= h.w > 0.f ? 1.f : h.w + 1.f;
-                        }
-                    } else {
-                        for (int i = 0; i < nvalid; i++) { const float h = arow[i]; v[i] *= h > 0.f ? 1.f : h + 1.f; }
-                    }
-                }
-                if (nvalid == 16) {
-#pragma unroll
-                    for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4 *>(crow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                } else {
-                    for (int i = 0; i < nvalid; i++) crow[i] = v[i];
+                    *reinterpret_cast<float4 *>(dst) = v;
                 }
             }
         }
+        if (EPI == 2 && g.colsum != nullptr) {            // 8 warps -> shared -> one global atomic per column per CTA
+            const int c = (lane % (BN / 4)) * 4;
+            atomicAdd(&colsum_s[c], csum.x); atomicAdd(&colsum_s[c + 1], csum.y); atomicAdd(&colsum_s[c + 2], csum.z); atomicAdd(&colsum_s[c + 3], csum.w);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (tid < BN && n0 + tid < g.N) atomicAdd(&g.colsum[n0 + tid], colsum_s[tid]);
+        }
     }
-    }   // warp < 8
     tc_fence_before();
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(BN) : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Host side: tensor-map cache + launcher
+// ---------------------------------------------------------------------------------------------------------------------
+struct Problem {
+    const float *A, *B;
+    float *C;
+    const float *bias, *aux;
+    float *colsum;
+    int M, N, K, lda, ldb, ldc;
+};
+
 inline bool aligned16(const void *p) { return ((uintptr_t)p & 15u) == 0; }
 
-// true if this problem can run on the tensor-core kernel
 template <bool A_KMAJ, bool B_KMAJ>
-inline bool supported(const Args &g) {
+inline bool supported(const Problem &g) {
     if (!aligned16(g.A) || !aligned16(g.B) || !aligned16(g.C) || (g.lda & 3) || (g.ldb & 3) || (g.ldc & 3)) return false;
-    if (A_KMAJ ? (g.K & 3) : (g.M & 3)) return false;
-    if (B_KMAJ ? (g.K & 3) : (g.N & 3)) return false;
     if (g.N < 16 || (g.N & 3) || g.M < 1 || g.K < 1) return false;
     if (g.aux && !aligned16(g.aux)) return false;
     if (g.bias && !aligned16(g.bias)) return false;
     return true;
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// Tensor map of a row-major fp32 matrix [rows, cols] (leading dimension ld) with box {32 (inner), box_rows}
+inline cudaError_t get_tensor_map(const float *base, int rows, int cols, int ld, int box_rows, bool kmajor_use, CUtensorMap *out) {
+    struct Key {
+        const void *p; int rows, cols, ld, box, km;
+        bool operator==(const Key &o) const { return p == o.p && rows == o.rows && cols == o.cols && ld == o.ld && box == o.box && km == o.km; }
+    };
+    struct Hash {
+        size_t operator()(const Key &k) const {
+            size_t h = (size_t)k.p;
+            for (int v : {k.rows, k.cols, k.ld, k.box, k.km}) h = h * 1000003u ^ (size_t)v;
+            return h;
+        }
+    };
+    static std::unordered_map<Key, CUtensorMap, Hash> cache;
+    static std::mutex mu;
+    static EncodeTiledFn encode = nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    const Key key{base, rows, cols, ld, box_rows, kmajor_use ? 1 : 0};
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return cudaSuccess; }
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+        if (e != cudaSuccess) return e;
+        if (q != cudaDriverEntryPointSuccess || !fn) return cudaErrorNotSupported;
+        encode = (EncodeTiledFn)fn;
+    }
+    CUtensorMap m;
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    const cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1u, 1u};
+    const CUresult r = encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              kmajor_use ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    cache.emplace(key, m);
+    *out = m;
+    return cudaSuccess;
+}
+
 template <bool A_KMAJ, bool B_KMAJ, int EPI, int BN, int S>
-inline cudaError_t launch_bn(Args g, int z, cudaStream_t st) {
-    constexpr size_t smem = (size_t)(tile_bytes<A_KMAJ>(TM) + tile_bytes<B_KMAJ>(BN)) * S;
+inline cudaError_t launch_bn(const Problem &p, Args g, int z, cudaStream_t st) {
+    constexpr size_t smem = (size_t)(tile_bytes(TM) + tile_bytes(BN)) * S + 1024;
+    static_assert((size_t)TM * (BN + 4) * 4 <= (size_t)(tile_bytes(TM) + tile_bytes(BN)) * S, "epilogue tile must fit in the pipeline stages");
     static bool attr_done = false;   // per template instantiation
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<A_KMAJ, B_KMAJ, EPI, BN, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    dim3 grid((g.N + BN - 1) / BN, (g.M + TM - 1) / TM, z);
-    gemm_tf32_kernel<A_KMAJ, B_KMAJ, EPI, BN, S><<<grid, NTHREADS_CTA, smem, st>>>(g);
+    CUtensorMap ma, mb;
+    // K-major operand: matrix [extent, K] -> box {32 k, tile rows}.  MN-major operand: matrix [K, extent] -> box {32 mn, 32 k}.
+    cudaError_t e = A_KMAJ ? get_tensor_map(p.A, p.M, p.K, p.lda, TM, true, &ma) : get_tensor_map(p.A, p.K, p.M, p.lda, 32, false, &ma);
+    if (e != cudaSuccess) return e;
+    e = B_KMAJ ? get_tensor_map(p.B, p.N, p.K, p.ldb, BN, true, &mb) : get_tensor_map(p.B, p.K, p.N, p.ldb, 32, false, &mb);
+    if (e != cudaSuccess) return e;
+    dim3 grid((p.N + BN - 1) / BN, (p.M + TM - 1) / TM, z);
+    gemm_tf32_kernel<A_KMAJ, B_KMAJ, EPI, BN, S><<<grid, NTHREADS_CTA, smem, st>>>(ma, mb, g);
     return cudaGetLastError();
 }
 
 template <bool A_KMAJ, bool B_KMAJ, int EPI>
-inline cudaError_t launch(Args g, int splits, cudaStream_t st) {
+inline cudaError_t launch(const Problem &p, int splits, cudaStream_t st) {
+    Args g;
+    g.C = p.C; g.bias = p.bias; g.aux = p.aux; g.colsum = p.colsum; g.M = p.M; g.N = p.N; g.K = p.K; g.ldc = p.ldc;
     if (splits < 1) splits = 1;
     { static const char *e = getenv("GRX_TC_DEBUG"); g.dbg = e ? atoi(e) : 0; }
-    g.kchunk = ((g.K + splits - 1) / splits + TK - 1) / TK * TK;
-    const int z = (g.K + g.kchunk - 1) / g.kchunk;
+    g.kchunk = ((p.K + splits - 1) / splits + TK - 1) / TK * TK;
+    const int z = (p.K + g.kchunk - 1) / g.kchunk;
     // N tile: these GEMMs are small, parallelism first: 128 only if it divides N and still yields >= ~1 CTA per SM slot
-    const long tiles_m = (g.M + TM - 1) / TM;
-    if (g.N % 128 == 0 && tiles_m * (g.N / 128) * z >= 148) return launch_bn<A_KMAJ, B_KMAJ, EPI, 128, 3>(g, z, st);
-    if (g.N > 32 && tiles_m * ((g.N + 63) / 64) * z >= 100) return launch_bn<A_KMAJ, B_KMAJ, EPI, 64, 4>(g, z, st);
-    if (g.N > 32 && g.N % 64 == 0) return launch_bn<A_KMAJ, B_KMAJ, EPI, 64, 4>(g, z, st);
-    return launch_bn<A_KMAJ, B_KMAJ, EPI, 32, 5>(g, z, st);
+    const long tiles_m = (p.M + TM - 1) / TM;
+    if (p.N % 128 == 0 && tiles_m * (p.N / 128) * z >= 148) return launch_bn<A_KMAJ, B_KMAJ, EPI, 128, 3>(p, g, z, st);
+    if (p.N > 32 && tiles_m * ((p.N + 63) / 64) * z >= 100) return launch_bn<A_KMAJ, B_KMAJ, EPI, 64, 4>(p, g, z, st);
+    if (p.N > 32 && p.N % 64 == 0) return launch_bn<A_KMAJ, B_KMAJ, EPI, 64, 4>(p, g, z, st);
+    return launch_bn<A_KMAJ, B_KMAJ, EPI, 32, 4>(p, g, z, st);
 }
 
 }  // namespace tc

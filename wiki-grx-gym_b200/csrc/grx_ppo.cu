@@ -133,12 +133,12 @@ void launch_gemm(const GemmArgs &g, int splits, cudaStream_t st) {
 }
 
 // column sums of a row-major [M, N] matrix into out[N] (+=): bias gradients on the tensor-core path
-__global__ void __launch_bounds__(256) colsum_kernel(const float *X, int M, int N, int rows_per_block, float *out) {
+__global__ void __launch_bounds__(256) colsum_kernel(const float *X, int M, int N, int ld, int rows_per_block, float *out) {
     const int n = blockIdx.x * 32 + (threadIdx.x & 31), w = threadIdx.x >> 5;
     const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
     float s = 0.f;
     if (n < N)
-        for (int r = r0 + w; r < r1; r += 8) s += X[(size_t)r * N + n];
+        for (int r = r0 + w; r < r1; r += 8) s += X[(size_t)r * ld + n];
     __shared__ float red[8][33];
     red[w][threadIdx.x & 31] = s;
     __syncthreads();
@@ -156,13 +156,13 @@ thread_local cudaError_t g_launch_err = cudaSuccess;   // first failed tensor-co
 template <bool A_KC, bool B_KC, int EPI>
 void dense(const GemmArgs &g, int splits, bool use_tc, cudaStream_t st) {
     if (use_tc) {
-        tc::Args a;
-        a.A = g.A; a.B = g.B; a.C = g.C; a.bias = g.bias; a.aux = g.aux; a.M = g.M; a.N = g.N; a.K = g.K;
-        a.lda = g.lda; a.ldb = g.ldb; a.ldc = g.ldc; a.kchunk = 0; a.stages = 0;
+        tc::Problem a;
+        a.A = g.A; a.B = g.B; a.C = g.C; a.bias = g.bias; a.aux = g.aux; a.colsum = EPI == 2 ? g.bias_out : nullptr;
+        a.M = g.M; a.N = g.N; a.K = g.K; a.lda = g.lda; a.ldb = g.ldb; a.ldc = g.ldc;
         if (tc::supported<A_KC, B_KC>(a)) {
             if (EPI == 3 && g.bias_out) {
                 const int rpb = 512;
-                colsum_kernel<<<dim3((g.M + 31) / 32, (g.K + rpb - 1) / rpb), 256, 0, st>>>(g.A, g.K, g.M, rpb, g.bias_out);   // A = dY [rows, out]
+                colsum_kernel<<<dim3((g.M + 31) / 32, (g.K + rpb - 1) / rpb), 256, 0, st>>>(g.A, g.K, g.M, g.lda, rpb, g.bias_out);   // A = dY [rows, out]
             }
             const cudaError_t e = tc::launch<A_KC, B_KC, EPI>(a, splits, st);
             if (e != cudaSuccess && g_launch_err == cudaSuccess) g_launch_err = e;
@@ -170,6 +170,10 @@ void dense(const GemmArgs &g, int splits, bool use_tc, cudaStream_t st) {
         }
     }
     launch_gemm<A_KC, B_KC, EPI>(g, splits, st);
+    if (EPI == 2 && g.bias_out) {   // column sums of the produced gradient = bias gradient of the layer below
+        const int rpb = 512;
+        colsum_kernel<<<dim3((g.N + 31) / 32, (g.M + rpb - 1) / rpb), 256, 0, st>>>(g.C, g.M, g.N, g.ldc, rpb, g.bias_out);
+    }
 }
 
 // =========================================================================================================
@@ -325,7 +329,7 @@ __global__ void normalize_adv_kernel(float *adv, const double *moments, size_t n
 struct GatherArgs {
     const int64_t *indices;
     const int *mb_counter;   // device-side minibatch index (so the same CUDA graph replays for every minibatch), or NULL
-    int mb, nmb, B, O, P, A;
+    int mb, nmb, B, O, P, A, Opad, Ppad;
     const float *s_obs, *s_cobs, *s_act, *s_val, *s_ret, *s_adv, *s_logp, *s_mu, *s_sigma;
     float *xa, *xc, *act, *val, *ret, *adv, *logp, *mu, *sigma;
 };
@@ -335,8 +339,8 @@ __global__ void gather_kernel(const GatherArgs g) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, nwarp = (gridDim.x * blockDim.x) >> 5;
     for (int r = warp; r < g.B; r += nwarp) {
         const size_t s = (size_t)idx[r];
-        for (int i = lane; i < g.O; i += 32) g.xa[(size_t)r * g.O + i] = g.s_obs[s * g.O + i];
-        for (int i = lane; i < g.P; i += 32) g.xc[(size_t)r * g.P + i] = g.s_cobs[s * g.P + i];
+        for (int i = lane; i < g.O; i += 32) g.xa[(size_t)r * g.Opad + i] = g.s_obs[s * g.O + i];
+        for (int i = lane; i < g.P; i += 32) g.xc[(size_t)r * g.Ppad + i] = g.s_cobs[s * g.P + i];
         for (int i = lane; i < g.A; i += 32) {
             g.act[(size_t)r * g.A + i] = g.s_act[s * g.A + i];
             g.mu[(size_t)r * g.A + i] = g.s_mu[s * g.A + i];
@@ -429,6 +433,158 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(const LossArgs a) {
 }
 
 // =========================================================================================================
+// Fused output heads for the update: for each minibatch row (one warp per row)
+//   mu = W3a h3a + b3a, v = W3c h3c + b3c   (the N = 10 / N = 1 output layers: far too narrow for a tensor-core tile)
+//   -> the PPO losses and d(loss)/d(mu, v) exactly as ppo_loss_kernel
+//   -> dh3 = (d(out) W3) * ELU'(h3) for both nets, and the head gradients dW3 += d(out) (x) h3, db3 += d(out), db2 += colsum(dh3)
+// Replaces 2 head GEMMs + loss + 2 head dW GEMMs + 2 head dX GEMMs + 2 column-sum passes.  Memory-bound on h3 / dh3.
+// =========================================================================================================
+constexpr int HA = 16;   // max action dim for the fused path (register accumulators)
+struct HeadsArgs {
+    const float *h3a, *h3c;            // [B, H3a], [B, H3c]
+    float *dh3a, *dh3c;                // same shapes
+    const float *W3a, *b3a, *W3c, *b3c, *std;
+    float *gW3a, *gb3a, *gW3c, *gb3c, *gb2a, *gb2c, *gstd, *tail;
+    const float *act, *old_mu, *old_sigma, *old_logp, *adv, *ret, *old_v;
+    int B, A, H3a, H3c;
+    float clip, vcoef, ecoef;
+    int clipped_value;
+};
+__global__ void __launch_bounds__(256) ppo_heads_kernel(const HeadsArgs a) {
+    extern __shared__ __align__(16) float hs[];   // W3a [A*H3a] | W3c [H3c] | block accumulators: gW3a [A*H3a] | gW3c [H3c] | gb2a [H3a] | gb2c [H3c] | misc [A + 6 + A]
+    const int A = a.A, Ha = a.H3a, Hc = a.H3c;
+    float *sWa = hs, *sWc = sWa + A * Ha, *aWa = sWc + Hc, *aWc = aWa + A * Ha, *ab2a = aWc + Hc, *ab2c = ab2a + Ha, *amisc = ab2c + Hc;
+    const int nacc = A * Ha + Hc + Ha + Hc + (2 * A + 6);
+    for (int i = threadIdx.x; i < A * Ha; i += blockDim.x) sWa[i] = a.W3a[i];
+    for (int i = threadIdx.x; i < Hc; i += blockDim.x) sWc[i] = a.W3c[i];
+    for (int i = threadIdx.x; i < nacc; i += blockDim.x) aWa[i] = 0.f;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const float invB = 1.0f / (float)a.B;
+    // per-lane register accumulators over this warp's rows: lane owns columns {lane*4 + 128 k}
+    float gWa[HA][4], gWc[4], g2a[4], g2c[4], gba[HA], gstd[HA];
+#pragma unroll
+    for (int j = 0; j < HA; j++) { gba[j] = 0.f; gstd[j] = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; q++) gWa[j][q] = 0.f; }
+#pragma unroll
+    for (int q = 0; q < 4; q++) { gWc[q] = 0.f; g2a[q] = 0.f; g2c[q] = 0.f; }
+    float gbc = 0.f, kl_s = 0.f, surr_s = 0.f, vl_s = 0.f, cnt_s = 0.f;
+    const int c0 = lane * 4;   // Ha, Hc <= 128 on this path: one float4 per lane
+    for (int r = blockIdx.x * (blockDim.x >> 5) + warp; r < a.B; r += nwarps) {
+        float4 ha = make_float4(0.f, 0.f, 0.f, 0.f), hc = ha;
+        if (c0 < Ha) ha = *reinterpret_cast<const float4 *>(a.h3a + (size_t)r * Ha + c0);
+        if (c0 < Hc) hc = *reinterpret_cast<const float4 *>(a.h3c + (size_t)r * Hc + c0);
+        float mu[HA], v = 0.f;
+#pragma unroll
+        for (int j = 0; j < HA; j++) {
+            mu[j] = 0.f;
+            if (j < A && c0 < Ha) {
+                const float4 w = *reinterpret_cast<const float4 *>(sWa + j * Ha + c0);
+                mu[j] = ha.x * w.x + ha.y * w.y + ha.z * w.z + ha.w * w.w;
+            }
+        }
+        if (c0 < Hc) { const float4 w = *reinterpret_cast<const float4 *>(sWc + c0); v = hc.x * w.x + hc.y * w.y + hc.z * w.z + hc.w * w.w; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            v += __shfl_xor_sync(FULL, v, o);
+#pragma unroll
+            for (int j = 0; j < HA; j++) if (j < A) mu[j] += __shfl_xor_sync(FULL, mu[j], o);
+        }
+        v += a.b3c[0];
+        // ---- losses + output gradients (identical arithmetic to ppo_loss_kernel; every lane computes the row redundantly)
+        float lp = 0.f, kl = 0.f, dmu[HA];
+#pragma unroll
+        for (int j = 0; j < HA; j++) {
+            dmu[j] = 0.f;
+            if (j < A) {
+                mu[j] += a.b3a[j];
+                const float sg = a.std[j], d = a.act[(size_t)r * A + j] - mu[j];
+                lp += -(d * d) / (2.f * sg * sg) - logf(sg) - LOG_SQRT_2PI;
+                const float os = a.old_sigma[(size_t)r * A + j], om = a.old_mu[(size_t)r * A + j];
+                kl += logf(sg / os + 1.0e-5f) + (os * os + (om - mu[j]) * (om - mu[j])) / (2.0f * sg * sg) - 0.5f;
+            }
+        }
+        const float A_ = a.adv[r];
+        const float ratio = expf(lp - a.old_logp[r]);
+        const float s1 = -A_ * ratio, s2 = -A_ * fminf(fmaxf(ratio, 1.0f - a.clip), 1.0f + a.clip);
+        const bool use1 = s1 >= s2, in_clip = ratio >= 1.0f - a.clip && ratio <= 1.0f + a.clip;
+        const float dlp = (use1 || in_clip ? -A_ : 0.f) * invB * ratio;
+        const float R = a.ret[r], V0 = a.old_v[r];
+        float dv, vl;
+        if (a.clipped_value) {
+            const float vc = V0 + fminf(fmaxf(v - V0, -a.clip), a.clip);
+            const float l1 = (v - R) * (v - R), l2 = (vc - R) * (vc - R);
+            vl = fmaxf(l1, l2);
+            const bool inc = (v - V0) >= -a.clip && (v - V0) <= a.clip;
+            dv = l1 >= l2 ? 2.f * (v - R) : (inc ? 2.f * (vc - R) : 0.f);
+        } else { vl = (R - v) * (R - v); dv = -2.f * (R - v); }
+        dv *= a.vcoef * invB;
+        if (lane == 0) { kl_s += kl; surr_s += fmaxf(s1, s2); vl_s += vl; cnt_s += 1.f; gbc += dv; }
+        // ---- head backward
+        float4 da = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < HA; j++) {
+            if (j < A) {
+                const float sg = a.std[j], d = a.act[(size_t)r * A + j] - mu[j];
+                dmu[j] = dlp * d / (sg * sg);
+                if (lane == 0) { gba[j] += dmu[j]; gstd[j] += dlp * (d * d / (sg * sg * sg) - 1.0f / sg); }
+                if (c0 < Ha) {
+                    const float4 w = *reinterpret_cast<const float4 *>(sWa + j * Ha + c0);
+                    da.x += dmu[j] * w.x; da.y += dmu[j] * w.y; da.z += dmu[j] * w.z; da.w += dmu[j] * w.w;
+                    gWa[j][0] += dmu[j] * ha.x; gWa[j][1] += dmu[j] * ha.y; gWa[j][2] += dmu[j] * ha.z; gWa[j][3] += dmu[j] * ha.w;
+                }
+            }
+        }
+        if (c0 < Ha) {
+            da.x *= elu_grad_from_out(ha.x); da.y *= elu_grad_from_out(ha.y); da.z *= elu_grad_from_out(ha.z); da.w *= elu_grad_from_out(ha.w);
+            *reinterpret_cast<float4 *>(a.dh3a + (size_t)r * Ha + c0) = da;
+            g2a[0] += da.x; g2a[1] += da.y; g2a[2] += da.z; g2a[3] += da.w;
+        }
+        if (c0 < Hc) {
+            const float4 w = *reinterpret_cast<const float4 *>(sWc + c0);
+            float4 dc = make_float4(dv * w.x * elu_grad_from_out(hc.x), dv * w.y * elu_grad_from_out(hc.y), dv * w.z * elu_grad_from_out(hc.z),
+                                    dv * w.w * elu_grad_from_out(hc.w));
+            *reinterpret_cast<float4 *>(a.dh3c + (size_t)r * Hc + c0) = dc;
+            g2c[0] += dc.x; g2c[1] += dc.y; g2c[2] += dc.z; g2c[3] += dc.w;
+            gWc[0] += dv * hc.x; gWc[1] += dv * hc.y; gWc[2] += dv * hc.z; gWc[3] += dv * hc.w;
+        }
+    }
+    // ---- block reduction in shared memory, then one global atomic per element per block
+#pragma unroll
+    for (int j = 0; j < HA; j++) {
+        if (j < A && c0 < Ha) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) atomicAdd(&aWa[j * Ha + c0 + q], gWa[j][q]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        if (c0 < Hc) { atomicAdd(&aWc[c0 + q], gWc[q]); atomicAdd(&ab2c[c0 + q], g2c[q]); }
+        if (c0 < Ha) atomicAdd(&ab2a[c0 + q], g2a[q]);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < HA; j++) if (j < A) { atomicAdd(&amisc[j], gba[j]); atomicAdd(&amisc[A + 6 + j], gstd[j]); }
+        atomicAdd(&amisc[A], gbc); atomicAdd(&amisc[A + 1], kl_s); atomicAdd(&amisc[A + 2], cnt_s); atomicAdd(&amisc[A + 3], surr_s); atomicAdd(&amisc[A + 4], vl_s);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < A * Ha; i += blockDim.x) atomicAdd(&a.gW3a[i], aWa[i]);
+    for (int i = threadIdx.x; i < Hc; i += blockDim.x) { atomicAdd(&a.gW3c[i], aWc[i]); atomicAdd(&a.gb2c[i], ab2c[i]); }
+    for (int i = threadIdx.x; i < Ha; i += blockDim.x) atomicAdd(&a.gb2a[i], ab2a[i]);
+    if (threadIdx.x < A) {
+        atomicAdd(&a.gb3a[threadIdx.x], amisc[threadIdx.x]);
+        float gs = amisc[A + 6 + threadIdx.x];
+        if (blockIdx.x == 0) gs += -a.ecoef * (1.0f / a.std[threadIdx.x]);   // d(-c_e * mean entropy)/d std_j, once per rank
+        atomicAdd(&a.gstd[threadIdx.x], gs);
+    }
+    if (threadIdx.x == 0) {
+        atomicAdd(&a.gb3c[0], amisc[A]);
+        atomicAdd(&a.tail[0], amisc[A + 1]); atomicAdd(&a.tail[1], amisc[A + 2]); atomicAdd(&a.tail[2], amisc[A + 3]); atomicAdd(&a.tail[3], amisc[A + 4]);
+    }
+}
+
+// =========================================================================================================
 // apply: grad-norm -> control block (adaptive LR from KL, NaN skip, clip coefficient, Adam bias corrections) -> Adam
 // =========================================================================================================
 struct Ctl {            // device control block
@@ -508,6 +664,7 @@ __global__ void adam_kernel(float *p, const float *g, float *m, float *v, int n,
 
 struct Net {            // one MLP: offsets into the flat parameter vector
     int dims[5];        // in, h1, h2, h3, out
+    int ld[4];          // leading dimension of weight l = in-dim rounded up to 4 floats (16-byte rows for TMA / vector loads)
     size_t w[4], b[4];
 };
 
@@ -519,6 +676,7 @@ struct Net {            // one MLP: offsets into the flat parameter vector
 struct grx_ppo {
     grx_ppo_cfg cfg;
     int device = 0;
+    int Opad = 0, Ppad = 0;   // row stride of the staged actor / critic inputs (O, P rounded up to 4 floats)
     int N = 0, T = 0, O = 0, P = 0, A = 0, B = 0, MR = 0;   // B = minibatch rows, MR = workspace rows = max(N, B)
     size_t nparam = 0;
     Net actor, critic;
@@ -550,7 +708,8 @@ static int ppo_alloc(grx_ppo *p, void **ptr, size_t bytes) {
 static void layout_net(Net &n, const int *dims, size_t &off) {
     for (int i = 0; i < 5; i++) n.dims[i] = dims[i];
     for (int l = 0; l < 4; l++) {   // every tensor starts on a 16-byte boundary (cp.async / vector loads in the dense kernels)
-        off = (off + 3) & ~(size_t)3; n.w[l] = off; off += (size_t)dims[l + 1] * dims[l];
+        n.ld[l] = (dims[l] + 3) & ~3;
+        off = (off + 3) & ~(size_t)3; n.w[l] = off; off += (size_t)dims[l + 1] * n.ld[l];
         off = (off + 3) & ~(size_t)3; n.b[l] = off; off += (size_t)dims[l + 1];
     }
 }
@@ -567,6 +726,7 @@ extern "C" int grx_ppo_create(const grx_ppo_cfg *cfg, int32_t device, grx_ppo **
     p->B = (int)(((size_t)p->N * p->T) / cfg->num_mini_batches);                       // rollout_storage.py:71-72
     if (p->B <= 0) { delete p; return grx_set_error(GRX_E_INVALID, "grx_ppo_create: fewer transitions than minibatches"); }
     p->MR = p->N > p->B ? p->N : p->B;
+    p->Opad = (p->O + 3) & ~3; p->Ppad = (p->P + 3) & ~3;
     // flat parameter vector in the reference's state_dict order: std, actor.model.{0,2,4,6}.{weight,bias}, critic...
     size_t off = (size_t)p->A;
     const int da[5] = {p->O, cfg->actor_hidden[0], cfg->actor_hidden[1], cfg->actor_hidden[2], p->A};
@@ -583,7 +743,7 @@ extern "C" int grx_ppo_create(const grx_ppo_cfg *cfg, int32_t device, grx_ppo **
         PALLOC(p->ha[l], MR * da[l + 1] * 4); PALLOC(p->da[l], MR * da[l + 1] * 4);
         PALLOC(p->hc[l], MR * dc[l + 1] * 4); PALLOC(p->dc[l], MR * dc[l + 1] * 4);
     }
-    PALLOC(p->xa, MR * p->O * 4); PALLOC(p->xc, MR * p->P * 4); PALLOC(p->mb_act, MR * p->A * 4); PALLOC(p->mb_val, MR * 4);
+    PALLOC(p->xa, MR * p->Opad * 4); PALLOC(p->xc, MR * p->Ppad * 4); PALLOC(p->mb_act, MR * p->A * 4); PALLOC(p->mb_val, MR * 4);
     PALLOC(p->mb_ret, MR * 4); PALLOC(p->mb_adv, MR * 4); PALLOC(p->mb_logp, MR * 4); PALLOC(p->mb_mu, MR * p->A * 4);
     PALLOC(p->mb_sigma, MR * p->A * 4); PALLOC(p->last_values, (size_t)p->N * 4);
     PALLOC(p->moments, 4 * sizeof(double)); PALLOC(p->ctl, sizeof(Ctl));
@@ -639,49 +799,58 @@ extern "C" int grx_ppo_get_buffer(grx_ppo *p, const char *name, grx_buffer *b) {
     return grx_set_error(GRX_E_NOTFOUND, "grx_ppo_get_buffer: unknown buffer '" + n + "'");
 }
 
-// MLP forward over M rows: h[l] = elu(h[l-1] W_l^T + b_l), out = h3 W_3^T + b_3 (mlp.py:26-41)
-static void mlp_forward(grx_ppo *p, const Net &net, const float *x, float *const *h, int M, cudaStream_t st) {
+// MLP forward over M rows (x has row stride ldx): h[l] = elu(h[l-1] W_l^T + b_l) for l < nlayers, last of 4 without ELU (mlp.py:26-41)
+static void mlp_forward(grx_ppo *p, const Net &net, const float *x, int ldx, float *const *h, int M, int nlayers, cudaStream_t st) {
     const float *in = x;
-    for (int l = 0; l < 4; l++) {
+    for (int l = 0; l < nlayers; l++) {
         GemmArgs g; memset(&g, 0, sizeof(g));
         g.A = in; g.B = p->params + net.w[l]; g.C = h[l]; g.bias = p->params + net.b[l];
-        g.M = M; g.N = net.dims[l + 1]; g.K = net.dims[l]; g.lda = g.K; g.ldb = g.K; g.ldc = g.N;
+        g.M = M; g.N = net.dims[l + 1]; g.K = net.dims[l]; g.lda = l == 0 ? ldx : net.dims[l]; g.ldb = net.ld[l]; g.ldc = g.N;
         if (l < 3) dense<true, true, 1>(g, 1, p->cfg.use_tensor_cores != 0, st);
         else dense<true, true, 0>(g, 1, p->cfg.use_tensor_cores != 0, st);
         in = h[l];
     }
 }
-// MLP backward: d[3] holds dL/d(out); writes weight / bias grads (accumulating into zeroed `grads`) and d[2..0]
-static void mlp_backward(grx_ppo *p, const Net &net, const float *x, float *const *h, float *const *d, float *grads, int M, cudaStream_t st) {
-    for (int l = 3; l >= 0; l--) {
+// MLP backward from layer `top` down: d[top] holds dL/d(output of layer top).  Writes weight grads for l <= top, bias grads for
+// l < top (and for l == top when top == 3; with the fused heads kernel top == 2 and db_2, dW_3, db_3 are already done), and d[l-1].
+static void mlp_backward(grx_ppo *p, const Net &net, const float *x, int ldx, float *const *h, float *const *d, float *grads, int M, int top,
+                         cudaStream_t st) {
+    for (int l = top; l >= 0; l--) {
         const float *hin = l == 0 ? x : h[l - 1];
-        {   // dW_l [out, in] += dY^T hin ; db_l += colsum(dY)
+        {   // dW_l [out, in (padded)] += dY^T hin
             GemmArgs g; memset(&g, 0, sizeof(g));
-            g.A = d[l]; g.B = hin; g.C = grads + net.w[l]; g.bias_out = grads + net.b[l];
-            g.M = net.dims[l + 1]; g.N = net.dims[l]; g.K = M; g.lda = net.dims[l + 1]; g.ldb = net.dims[l]; g.ldc = net.dims[l];
-            const bool use_tc = p->cfg.use_tensor_cores != 0 && g.M >= 64 && g.N >= 64;
-            const int tiles = use_tc ? ((g.M + 127) / 128) * ((g.N + 255) / 256) : ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
+            g.A = d[l]; g.B = hin; g.C = grads + net.w[l]; g.bias_out = (l == top && top == 3) ? grads + net.b[l] : nullptr;
+            g.M = net.dims[l + 1]; g.N = l == 0 ? net.ld[0] : net.dims[l]; g.K = M; g.lda = net.dims[l + 1]; g.ldb = l == 0 ? ldx : net.dims[l];
+            g.ldc = net.ld[l];
+            const bool use_tc = p->cfg.use_tensor_cores != 0 && g.M >= 64 && g.N >= 32;
+            const int tiles = use_tc ? ((g.M + 127) / 128) * ((g.N + 127) / 128) : ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
             int splits = (2 * 148 + tiles - 1) / tiles;
             const int maxs = (M + 255) / 256;
             if (splits > maxs) splits = maxs;
             if (splits < 1) splits = 1;
             dense<false, false, 3>(g, splits, use_tc, st);
         }
-        if (l > 0) {   // d[l-1] = (dY W_l) * ELU'(h[l-1])
+        if (l > 0) {   // d[l-1] = (dY W_l) * ELU'(h[l-1]) ; db_{l-1} += colsum(d[l-1])
             GemmArgs g; memset(&g, 0, sizeof(g));
-            g.A = d[l]; g.B = p->params + net.w[l]; g.C = d[l - 1]; g.aux = h[l - 1];
-            g.M = M; g.N = net.dims[l]; g.K = net.dims[l + 1]; g.lda = net.dims[l + 1]; g.ldb = net.dims[l]; g.ldc = net.dims[l];
+            g.A = d[l]; g.B = p->params + net.w[l]; g.C = d[l - 1]; g.aux = h[l - 1]; g.bias_out = grads + net.b[l - 1];
+            g.M = M; g.N = net.dims[l]; g.K = net.dims[l + 1]; g.lda = net.dims[l + 1]; g.ldb = net.ld[l]; g.ldc = net.dims[l];
             dense<true, false, 2>(g, 1, p->cfg.use_tensor_cores != 0 && g.K >= 64, st);
         }
     }
+}
+// stage caller-provided observation rows (any row stride >= width) into the padded, 16-byte aligned input buffers
+static cudaError_t stage_rows(float *dst, int ld_dst, const float *src, int width, int rows, cudaStream_t st) {
+    return cudaMemcpy2DAsync(dst, (size_t)ld_dst * 4, src, (size_t)width * 4, (size_t)width * 4, rows, cudaMemcpyDeviceToDevice, st);
 }
 
 extern "C" int grx_ppo_act(grx_ppo *p, const float *d_obs, const float *d_critic_obs, const float *d_eps, int32_t t, float *d_actions_out,
                            uint64_t step_index, void *stream) {
     if (!p || !d_obs || !d_critic_obs || !d_actions_out || t < 0 || t >= p->T) return grx_set_error(GRX_E_INVALID, "grx_ppo_act: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
-    mlp_forward(p, p->actor, d_obs, p->ha, p->N, st);
-    mlp_forward(p, p->critic, d_critic_obs, p->hc, p->N, st);
+    CK(stage_rows(p->xa, p->Opad, d_obs, p->O, p->N, st));
+    CK(stage_rows(p->xc, p->Ppad, d_critic_obs, p->P, p->N, st));
+    mlp_forward(p, p->actor, p->xa, p->Opad, p->ha, p->N, 4, st);
+    mlp_forward(p, p->critic, p->xc, p->Ppad, p->hc, p->N, 4, st);
     ActArgs a; memset(&a, 0, sizeof(a));
     const size_t row = (size_t)t * p->N;
     a.obs = d_obs; a.critic_obs = d_critic_obs; a.mu = p->ha[3]; a.value = p->hc[3]; a.std = p->params; a.eps = d_eps;
@@ -707,7 +876,8 @@ extern "C" int grx_ppo_process_env_step(grx_ppo *p, const float *d_rewards, cons
 extern "C" int grx_ppo_compute_returns_local(grx_ppo *p, const float *d_last_critic_obs, void *stream) {
     if (!p || !d_last_critic_obs) return grx_set_error(GRX_E_INVALID, "grx_ppo_compute_returns: null argument");
     cudaStream_t st = (cudaStream_t)stream;
-    mlp_forward(p, p->critic, d_last_critic_obs, p->hc, p->N, st);                     // ppo.py:204
+    CK(stage_rows(p->xc, p->Ppad, d_last_critic_obs, p->P, p->N, st));
+    mlp_forward(p, p->critic, p->xc, p->Ppad, p->hc, p->N, 4, st);                     // ppo.py:204
     CK(cudaMemcpyAsync(p->last_values, p->hc[3], (size_t)p->N * 4, cudaMemcpyDeviceToDevice, st));
     CK(cudaMemsetAsync(p->moments, 0, 4 * sizeof(double), st));
     gae_kernel<<<(p->N + 31) / 32, 1024, (size_t)3 * p->T * 33 * sizeof(float), st>>>(p->s_rew, p->s_done, p->s_val, p->last_values, p->cfg.gamma, p->cfg.lam, p->s_ret, p->s_adv,
@@ -732,23 +902,42 @@ static int minibatch_grads(grx_ppo *p, const int64_t *d_indices, int mb, bool de
     CK(cudaMemsetAsync(p->reduce_buf, 0, (p->nparam + TAIL) * 4, st));
     GatherArgs g; memset(&g, 0, sizeof(g));
     g.indices = d_indices; g.mb_counter = device_counter ? &p->ctl->mb_counter : nullptr; g.mb = mb; g.nmb = p->cfg.num_mini_batches;
-    g.B = B; g.O = p->O; g.P = p->P; g.A = p->A;
+    g.B = B; g.O = p->O; g.P = p->P; g.A = p->A; g.Opad = p->Opad; g.Ppad = p->Ppad;
     g.s_obs = p->s_obs; g.s_cobs = p->s_cobs; g.s_act = p->s_act; g.s_val = p->s_val; g.s_ret = p->s_ret; g.s_adv = p->s_adv;
     g.s_logp = p->s_logp; g.s_mu = p->s_mu; g.s_sigma = p->s_sigma;
     g.xa = p->xa; g.xc = p->xc; g.act = p->mb_act; g.val = p->mb_val; g.ret = p->mb_ret; g.adv = p->mb_adv; g.logp = p->mb_logp;
     g.mu = p->mb_mu; g.sigma = p->mb_sigma;
     gather_kernel<<<592, 256, 0, st>>>(g);
-    mlp_forward(p, p->actor, p->xa, p->ha, B, st);                                     // ppo.py:244-248
-    mlp_forward(p, p->critic, p->xc, p->hc, B, st);
-    LossArgs a; memset(&a, 0, sizeof(a));
-    a.mu = p->ha[3]; a.v = p->hc[3]; a.std = p->params; a.act = p->mb_act; a.old_mu = p->mb_mu; a.old_sigma = p->mb_sigma;
-    a.old_logp = p->mb_logp; a.adv = p->mb_adv; a.ret = p->mb_ret; a.old_v = p->mb_val;
-    a.dmu = p->da[3]; a.dv = p->dc[3]; a.gstd = p->reduce_buf; a.tail = p->reduce_buf + p->nparam;
-    a.B = B; a.A = p->A; a.clip = p->cfg.clip_param; a.vcoef = p->cfg.value_loss_coef; a.ecoef = p->cfg.entropy_coef;
-    a.clipped_value = p->cfg.use_clipped_value_loss;
-    ppo_loss_kernel<<<(B + 255) / 256, 256, 0, st>>>(a);
-    mlp_backward(p, p->actor, p->xa, p->ha, p->da, p->reduce_buf, B, st);
-    mlp_backward(p, p->critic, p->xc, p->hc, p->dc, p->reduce_buf, B, st);
+    const Net &na = p->actor, &nc = p->critic;
+    const bool fused_heads = p->A <= HA && nc.dims[4] == 1 && na.dims[3] <= 128 && nc.dims[3] <= 128 && (na.dims[3] & 3) == 0 && (nc.dims[3] & 3) == 0;
+    mlp_forward(p, na, p->xa, p->Opad, p->ha, B, fused_heads ? 3 : 4, st);             // ppo.py:244-248
+    mlp_forward(p, nc, p->xc, p->Ppad, p->hc, B, fused_heads ? 3 : 4, st);
+    float *gr = p->reduce_buf;
+    if (fused_heads) {
+        HeadsArgs a; memset(&a, 0, sizeof(a));
+        a.h3a = p->ha[2]; a.h3c = p->hc[2]; a.dh3a = p->da[2]; a.dh3c = p->dc[2];
+        a.W3a = p->params + na.w[3]; a.b3a = p->params + na.b[3]; a.W3c = p->params + nc.w[3]; a.b3c = p->params + nc.b[3]; a.std = p->params;
+        a.gW3a = gr + na.w[3]; a.gb3a = gr + na.b[3]; a.gW3c = gr + nc.w[3]; a.gb3c = gr + nc.b[3]; a.gb2a = gr + na.b[2]; a.gb2c = gr + nc.b[2];
+        a.gstd = gr; a.tail = gr + p->nparam;
+        a.act = p->mb_act; a.old_mu = p->mb_mu; a.old_sigma = p->mb_sigma; a.old_logp = p->mb_logp; a.adv = p->mb_adv; a.ret = p->mb_ret; a.old_v = p->mb_val;
+        a.B = B; a.A = p->A; a.H3a = na.dims[3]; a.H3c = nc.dims[3];
+        a.clip = p->cfg.clip_param; a.vcoef = p->cfg.value_loss_coef; a.ecoef = p->cfg.entropy_coef; a.clipped_value = p->cfg.use_clipped_value_loss;
+        const size_t sm = (size_t)(2 * (p->A * a.H3a + a.H3c) + a.H3a + a.H3c + 2 * p->A + 6) * sizeof(float);
+        ppo_heads_kernel<<<296, 256, sm, st>>>(a);
+        mlp_backward(p, na, p->xa, p->Opad, p->ha, p->da, gr, B, 2, st);
+        mlp_backward(p, nc, p->xc, p->Ppad, p->hc, p->dc, gr, B, 2, st);
+    } else {
+        LossArgs a; memset(&a, 0, sizeof(a));
+        a.mu = p->ha[3]; a.v = p->hc[3]; a.std = p->params; a.act = p->mb_act; a.old_mu = p->mb_mu; a.old_sigma = p->mb_sigma;
+        a.old_logp = p->mb_logp; a.adv = p->mb_adv; a.ret = p->mb_ret; a.old_v = p->mb_val;
+        a.dmu = p->da[3]; a.dv = p->dc[3]; a.gstd = gr; a.tail = gr + p->nparam;
+        a.B = B; a.A = p->A; a.clip = p->cfg.clip_param; a.vcoef = p->cfg.value_loss_coef; a.ecoef = p->cfg.entropy_coef;
+        a.clipped_value = p->cfg.use_clipped_value_loss;
+        ppo_loss_kernel<<<(B + 255) / 256, 256, 0, st>>>(a);
+        mlp_backward(p, na, p->xa, p->Opad, p->ha, p->da, gr, B, 3, st);
+        mlp_backward(p, nc, p->xc, p->Ppad, p->hc, p->dc, gr, B, 3, st);
+    }
+    if (g_launch_err != cudaSuccess) { const cudaError_t e = g_launch_err; g_launch_err = cudaSuccess; return grx_set_error(GRX_E_CUDA, std::string("tensor-core GEMM launch: ") + cudaGetErrorString(e)); }
     CK(cudaGetLastError());
     return GRX_OK;
 }
@@ -804,7 +993,8 @@ extern "C" int grx_ppo_update(grx_ppo *p, const int64_t *d_indices, void *stream
 extern "C" int grx_ppo_act_inference(grx_ppo *p, const float *d_obs, int32_t n, float *d_actions_out, void *stream) {
     if (!p || !d_obs || !d_actions_out || n <= 0 || n > p->MR) return grx_set_error(GRX_E_INVALID, "grx_ppo_act_inference: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
-    mlp_forward(p, p->actor, d_obs, p->ha, n, st);
+    CK(stage_rows(p->xa, p->Opad, d_obs, p->O, n, st));
+    mlp_forward(p, p->actor, p->xa, p->Opad, p->ha, n, 4, st);
     CK(cudaMemcpyAsync(d_actions_out, p->ha[3], (size_t)n * p->A * 4, cudaMemcpyDeviceToDevice, st));
     return GRX_OK;
 }

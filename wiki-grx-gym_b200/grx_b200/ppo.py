@@ -72,18 +72,30 @@ class ActorCriticMLP:
     # ---- bound once PPO created the device buffers
     def _bind(self, ppo, flat):
         self._ppo = ppo
-        views, off = OrderedDict(), 0
-        self._slices = OrderedDict()
-        for k, v in self._host_init.items():   # flat layout of csrc/grx_ppo.cu: reference state_dict order, each tensor 16-byte aligned
-            n = v.numel()
+        # flat layout of csrc/grx_ppo.cu: reference state_dict order; every tensor starts 16-byte aligned and weight matrices are
+        # stored with their rows padded to a multiple of 4 floats (TMA / vector loads) — the views hide the padding
+        self._slices, off = OrderedDict(), 0
+        for k, v in self._host_init.items():
             off = (off + 3) // 4 * 4
-            views[k] = flat[off:off + n].view(v.shape)
-            self._slices[k] = (off, n)
-            off += n
+            if v.dim() == 2:
+                ld = (v.shape[1] + 3) // 4 * 4
+                self._slices[k] = (off, v.shape[0], v.shape[1], ld)
+                off += v.shape[0] * ld
+            else:
+                self._slices[k] = (off, v.numel())
+                off += v.numel()
         assert (off + 3) // 4 * 4 == flat.numel(), (off, flat.numel())
-        self._views = views
+        self._views = OrderedDict((k, self.view_of(flat, k)) for k in self._host_init)
         self.load_state_dict(self._host_init, set_std=False)
         self._host_init = None
+
+    def view_of(self, flat, key):
+        """The tensor `key` inside a flat vector laid out like the parameter vector (params, grads, Adam moments)."""
+        sl = self._slices[key]
+        if len(sl) == 2:
+            return flat[sl[0]:sl[0] + sl[1]]
+        off, rows, cols, ld = sl
+        return flat[off:off + rows * ld].view(rows, ld)[:, :cols]
 
     @property
     def std(self):
@@ -295,21 +307,21 @@ class PPO:
     def optimizer_state_dict(self):
         state = {}
         step = float(self.adam_step)
-        for i, (k, v) in enumerate(self.actor_critic.state_dict().items()):
-            off, n = self.actor_critic._slices[k]
-            state[i] = {"step": torch.tensor(step), "exp_avg": self.adam_m[off:off + n].view(v.shape).clone(),
-                        "exp_avg_sq": self.adam_v[off:off + n].view(v.shape).clone()}
+        ac = self.actor_critic
+        for i, k in enumerate(ac.state_dict()):
+            state[i] = {"step": torch.tensor(step), "exp_avg": ac.view_of(self.adam_m, k).clone(),
+                        "exp_avg_sq": ac.view_of(self.adam_v, k).clone()}
         group = {"lr": self.learning_rate, "betas": (0.9, 0.999), "eps": 1e-8, "weight_decay": 0, "amsgrad": False,
                  "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
                  "params": list(range(len(state)))}
         return {"state": state, "param_groups": [group]}
 
     def load_optimizer_state_dict(self, sd):
-        for i, (k, v) in enumerate(self.actor_critic.state_dict().items()):
-            off, n = self.actor_critic._slices[k]
+        ac = self.actor_critic
+        for i, k in enumerate(ac.state_dict()):
             if i in sd["state"]:
-                self.adam_m[off:off + n].copy_(sd["state"][i]["exp_avg"].reshape(-1).to(self.device))
-                self.adam_v[off:off + n].copy_(sd["state"][i]["exp_avg_sq"].reshape(-1).to(self.device))
+                ac.view_of(self.adam_m, k).copy_(sd["state"][i]["exp_avg"].to(self.device))
+                ac.view_of(self.adam_v, k).copy_(sd["state"][i]["exp_avg_sq"].to(self.device))
                 step = int(float(sd["state"][i]["step"]))
         if sd["state"]:
             self.ctl[3:4].view(torch.int32).fill_(step)

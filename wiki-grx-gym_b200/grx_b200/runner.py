@@ -133,7 +133,7 @@ class OnPolicyRunner:
         self.last_scalars = scalars
 
     def save(self, path, infos=None):                                                     # on_policy_runner.py:297-309
-        torch.save({"model_state_dict": {k: v.detach().cpu().clone() for k, v in self.algorithm.actor_critic.state_dict().items()},
+        torch.save({"model_state_dict": {k: v.detach().contiguous().cpu().clone() for k, v in self.algorithm.actor_critic.state_dict().items()},
                     "optimizer_state_dict": self.algorithm.optimizer_state_dict(),
                     "iter": self.current_learning_iteration, "infos": infos}, path)
 
