@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmArgs g) {
             else atomicAdd(&g.C[o], acc[i][j]);
         }
     }
-    if (EPI == 3 && blockIdx.x == 0 && t < BM && m0 + t < g.M) atomicAdd(&g.bias_out[m0 + t], bsum);
+    if (EPI == 3 && g.bias_out != nullptr && blockIdx.x == 0 && t < BM && m0 + t < g.M) atomicAdd(&g.bias_out[m0 + t], bsum);
 }
 
 template <bool A_KC, bool B_KC, int EPI>
