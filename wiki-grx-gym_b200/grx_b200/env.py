@@ -18,6 +18,7 @@ import torch
 from . import _lib as L
 from . import rng_layout as RL
 from .config import make_cfg
+from . import sharding
 from .robot import nominal_params, sample_domain_rand, task_tables
 from .terrain import Terrain
 from .urdf import builtin_model
@@ -200,7 +201,7 @@ class GRXVecEnv:
         n_total = int(cfg.env.num_envs)
         assert n_total % world_size == 0, "num_envs must divide evenly over ranks"
         self.num_envs_total, self.num_envs = n_total, n_total // world_size
-        self.env_id_offset = rank * self.num_envs
+        self.env_id_offset = sharding.env_block(rank, world_size, n_total)[0]
         self.num_obs, self.num_pri_obs, self.num_actions = cfg.env.num_obs, cfg.env.num_pri_obs, cfg.env.num_actions
         self.num_privileged_obs = self.num_pri_obs
         robot = getattr(cfg, "robot", None) or ("GR1T2" if "GR1T2" in getattr(cfg.asset, "file", getattr(cfg.asset, "name", "")) else "GR1T1")
@@ -237,8 +238,7 @@ class GRXVecEnv:
                 max_init = cfg.terrain.max_init_terrain_level if cfg.terrain.curriculum else rows - 1
                 terrain_levels = g.integers(0, max_init + 1, n_total)[self.env_id_offset:self.env_id_offset + N]
             if terrain_types is None:
-                gi = np.arange(self.env_id_offset, self.env_id_offset + N)
-                terrain_types = np.floor(gi / (n_total / cols)).astype(np.int64)
+                terrain_types = sharding.terrain_types_for(rank, world_size, n_total, cols)
             if env_origins is None:
                 env_origins = t_org[np.asarray(terrain_levels), np.asarray(terrain_types)]
         elif env_origins is None:
