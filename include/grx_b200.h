@@ -212,10 +212,24 @@ int grx_ppo_normalize_advantages(grx_ppo *ppo, void *stream);
  *   apply: KL -> adaptive LR (device scalar, no .item()), NaN-skip, global-norm clip, Adam */
 int grx_ppo_minibatch_grads(grx_ppo *ppo, const int64_t *d_indices, int32_t mb, void *stream);
 int grx_ppo_minibatch_apply(grx_ppo *ppo, void *stream);
-/* Whole PPO.update (ppo.py:215-321) for world_size == 1: epochs x minibatches of grads+apply. */
+/* Whole PPO.update (ppo.py:215-321): epochs x minibatches of grads+apply replayed from one CUDA graph.  With world_size > 1
+ * it needs the NVLink all-reduce (grx_ppo_comm_open) and must be called by every rank. */
 int grx_ppo_update(grx_ppo *ppo, const int64_t *d_indices, void *stream);
+/* Multi-GPU gradient all-reduce over NVLink peer memory (no reference counterpart: the reference is single-GPU).
+ *   grx_ppo_comm_handle: writes this rank's 64-byte cudaIpcMemHandle_t of its comm block [reduce_buf | gsum | flags];
+ *   grx_ppo_comm_open:   handles = world x 64 bytes in rank order (exchanged by the caller over any host channel); maps every
+ *                        peer's block.  All ranks must have returned from it (host barrier) before the first apply.
+ *   grx_ppo_minibatch_apply_comm: apply step whose first kernel loads this rank's slice of the gradient from every peer, sums it
+ *                        in rank order, pushes the sum into every peer's gsum and reduces the gradient norm on the way. */
+int grx_ppo_comm_handle(grx_ppo *ppo, void *out64);
+int grx_ppo_comm_open(grx_ppo *ppo, int32_t rank, int32_t world, const void *handles);
+int grx_ppo_minibatch_apply_comm(grx_ppo *ppo, void *stream);
 /* actor-only forward for play.py / get_inference_policy (actor_critic_mlp.py:209-217) */
 int grx_ppo_act_inference(grx_ppo *ppo, const float *d_obs, int32_t n, float *d_actions_out, void *stream);
+
+/* Profiling (GRX_PPO_TIMING=1 in the environment at create): mean microseconds per minibatch of the stepwise grads + apply
+ * entries, split [memset+gather, actor forward, critic forward, heads/loss, actor backward, critic backward, apply]; resets. */
+int grx_ppo_debug_timing(grx_ppo *ppo, float *out7, int32_t *count);
 
 /* Debug / parity: one dense-layer GEMM on device pointers through the fp32 SIMT kernel (use_tc = 0) or the tcgen05 TF32 kernel.
  *   variant 0: C[M,N] = A[M,K] B[N,K]^T + bias (epi 0) or elu(...) (epi 1)      — forward (mlp.py:40-41)

@@ -32,4 +32,9 @@ for rep in range(2):
         L.check(alg.lib.grx_ppo_minibatch_apply(alg._h, alg._stream()))
     e1.record()
     torch.cuda.synchronize()
+if os.environ.get("GRX_PPO_TIMING"):
+    out, cnt = (C.c_float * 7)(), C.c_int32()
+    L.check(alg.lib.grx_ppo_debug_timing(alg._h, out, C.byref(cnt)))
+    names = ["memset+gather", "actor fwd", "critic fwd", "heads", "actor bwd", "critic bwd", "apply"]
+    print("phase us/minibatch (stepwise, events):", {n: round(v, 1) for n, v in zip(names, out)}, "over", cnt.value)
 print(f"N={N} T={T} use_tc={use_tc}: {e0.elapsed_time(e1) / nmb * 1e3:.1f} us per minibatch (B={alg.mini_batch_size})", alg.minibatch_stats())

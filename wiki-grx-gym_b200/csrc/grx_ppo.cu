@@ -333,20 +333,35 @@ struct GatherArgs {
     const float *s_obs, *s_cobs, *s_act, *s_val, *s_ret, *s_adv, *s_logp, *s_mu, *s_sigma;
     float *xa, *xc, *act, *val, *ret, *adv, *logp, *mu, *sigma;
 };
-__global__ void gather_kernel(const GatherArgs g) {
+__global__ void __launch_bounds__(256) gather_kernel(const GatherArgs g) {
+    // flat element-parallel copy (a warp-per-row loop leaves the row loads of one warp serialised behind its index load)
     const int mb = g.mb_counter ? (*g.mb_counter % g.nmb) : g.mb;
     const int64_t *idx = g.indices + (size_t)mb * g.B;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, nwarp = (gridDim.x * blockDim.x) >> 5;
-    for (int r = warp; r < g.B; r += nwarp) {
-        const size_t s = (size_t)idx[r];
-        for (int i = lane; i < g.O; i += 32) g.xa[(size_t)r * g.Opad + i] = g.s_obs[s * g.O + i];
-        for (int i = lane; i < g.P; i += 32) g.xc[(size_t)r * g.Ppad + i] = g.s_cobs[s * g.P + i];
-        for (int i = lane; i < g.A; i += 32) {
-            g.act[(size_t)r * g.A + i] = g.s_act[s * g.A + i];
-            g.mu[(size_t)r * g.A + i] = g.s_mu[s * g.A + i];
-            g.sigma[(size_t)r * g.A + i] = g.s_sigma[s * g.A + i];
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+    if ((g.P & 3) == 0) {   // critic rows are 16-byte aligned in the storage and in the staging buffer: float4 copies
+        const int P4 = g.P >> 2, L4 = g.Ppad >> 2;
+        for (size_t e = tid; e < (size_t)g.B * P4; e += nth) {
+            const int r = (int)(e / P4), c = (int)(e % P4);
+            reinterpret_cast<float4 *>(g.xc)[(size_t)r * L4 + c] = __ldg(reinterpret_cast<const float4 *>(g.s_cobs) + (size_t)idx[r] * P4 + c);
         }
-        if (lane == 0) { g.val[r] = g.s_val[s]; g.ret[r] = g.s_ret[s]; g.adv[r] = g.s_adv[s]; g.logp[r] = g.s_logp[s]; }
+    } else {
+        for (size_t e = tid; e < (size_t)g.B * g.P; e += nth) {
+            const int r = (int)(e / g.P), c = (int)(e % g.P);
+            g.xc[(size_t)r * g.Ppad + c] = __ldg(g.s_cobs + (size_t)idx[r] * g.P + c);
+        }
+    }
+    for (size_t e = tid; e < (size_t)g.B * g.O; e += nth) {
+        const int r = (int)(e / g.O), c = (int)(e % g.O);
+        g.xa[(size_t)r * g.Opad + c] = __ldg(g.s_obs + (size_t)idx[r] * g.O + c);
+    }
+    for (size_t e = tid; e < (size_t)g.B * g.A; e += nth) {
+        const int r = (int)(e / g.A), c = (int)(e % g.A);
+        const size_t s = (size_t)idx[r] * g.A + c;
+        g.act[e] = __ldg(g.s_act + s); g.mu[e] = __ldg(g.s_mu + s); g.sigma[e] = __ldg(g.s_sigma + s);
+    }
+    for (size_t r = tid; r < (size_t)g.B; r += nth) {
+        const size_t s = (size_t)idx[r];
+        g.val[r] = __ldg(g.s_val + s); g.ret[r] = __ldg(g.s_ret + s); g.adv[r] = __ldg(g.s_adv + s); g.logp[r] = __ldg(g.s_logp + s);
     }
 }
 
@@ -439,78 +454,69 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(const LossArgs a) {
 //   -> dh3 = (d(out) W3) * ELU'(h3) for both nets, and the head gradients dW3 += d(out) (x) h3, db3 += d(out), db2 += colsum(dh3)
 // Replaces 2 head GEMMs + loss + 2 head dW GEMMs + 2 head dX GEMMs + 2 column-sum passes.  Memory-bound on h3 / dh3.
 // =========================================================================================================
-constexpr int HA = 16;   // max action dim for the fused path (register accumulators)
+constexpr int HEADS_H = 128;       // hidden width of the last layer on the fused path (one float4 per lane)
+constexpr int HEADS_THREADS = 384; // 12 warps per CTA, one CTA per SM (168 registers per thread: every accumulator stays in registers)
 struct HeadsArgs {
-    const float *h3a, *h3c;            // [B, H3a], [B, H3c]
+    const float *h3a, *h3c;            // [B, 128] last hidden activations of actor / critic
     float *dh3a, *dh3c;                // same shapes
     const float *W3a, *b3a, *W3c, *b3c, *std;
     float *gW3a, *gb3a, *gW3c, *gb3c, *gb2a, *gb2c, *gstd, *tail;
     const float *act, *old_mu, *old_sigma, *old_logp, *adv, *ret, *old_v;
-    int B, A, H3a, H3c;
+    int B;
     float clip, vcoef, ecoef;
     int clipped_value;
 };
-__global__ void __launch_bounds__(256) ppo_heads_kernel(const HeadsArgs a) {
-    extern __shared__ __align__(16) float hs[];   // W3a [A*H3a] | W3c [H3c] | block accumulators: gW3a [A*H3a] | gW3c [H3c] | gb2a [H3a] | gb2c [H3c] | misc [A + 6 + A]
-    const int A = a.A, Ha = a.H3a, Hc = a.H3c;
-    float *sWa = hs, *sWc = sWa + A * Ha, *aWa = sWc + Hc, *aWc = aWa + A * Ha, *ab2a = aWc + Hc, *ab2c = ab2a + Ha, *amisc = ab2c + Hc;
-    const int nacc = A * Ha + Hc + Ha + Hc + (2 * A + 6);
-    for (int i = threadIdx.x; i < A * Ha; i += blockDim.x) sWa[i] = a.W3a[i];
-    for (int i = threadIdx.x; i < Hc; i += blockDim.x) sWc[i] = a.W3c[i];
-    for (int i = threadIdx.x; i < nacc; i += blockDim.x) aWa[i] = 0.f;
+// One warp per minibatch row; a lane owns the same 4 hidden columns for the whole kernel, so its slices of W3a / W3c and all its
+// gradient accumulators live in registers.  Lane j < NA additionally owns action j (its mu_j, log-prob / KL term, d mu_j, grad std_j).
+template <int NA>
+__global__ void __launch_bounds__(HEADS_THREADS, 1) ppo_heads_kernel(const HeadsArgs a) {
+    constexpr int H = HEADS_H;
+    constexpr int NACC = NA * H + 3 * H + 2 * NA + 8;   // gW3a | gW3c | gb2a | gb2c | gb3a[NA] | gstd[NA] | gb3c, kl, cnt, surr, vl
+    __shared__ float acc[NACC];
+    for (int i = threadIdx.x; i < NACC; i += blockDim.x) acc[i] = 0.f;
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5, nwarps = gridDim.x * wpb;
+    const int c0 = lane * 4;
+    float4 wa[NA], gWa[NA];
+#pragma unroll
+    for (int j = 0; j < NA; j++) { wa[j] = *reinterpret_cast<const float4 *>(a.W3a + j * H + c0); gWa[j] = make_float4(0.f, 0.f, 0.f, 0.f); }
+    const float4 wc = *reinterpret_cast<const float4 *>(a.W3c + c0);
+    float4 gWc = make_float4(0.f, 0.f, 0.f, 0.f), g2a = gWc, g2c = gWc;
+    const bool own = lane < NA;
+    const float sg = own ? a.std[lane] : 1.f, ba = own ? a.b3a[lane] : 0.f, bc = a.b3c[0];
+    const float inv2s2 = 1.f / (2.f * sg * sg), logsg = logf(sg);
+    float gba = 0.f, gsd = 0.f, gbc = 0.f, kl_s = 0.f, surr_s = 0.f, vl_s = 0.f, cnt_s = 0.f;
     const float invB = 1.0f / (float)a.B;
-    // per-lane register accumulators over this warp's rows: lane owns columns {lane*4 + 128 k}
-    float gWa[HA][4], gWc[4], g2a[4], g2c[4], gba[HA], gstd[HA];
+    for (int r = blockIdx.x * wpb + warp; r < a.B; r += nwarps) {
+        const float4 ha = *reinterpret_cast<const float4 *>(a.h3a + (size_t)r * H + c0);
+        const float4 hc = *reinterpret_cast<const float4 *>(a.h3c + (size_t)r * H + c0);
+        float ac = 0.f, om = 0.f, os = 1.f;
+        if (own) { ac = a.act[(size_t)r * NA + lane]; om = a.old_mu[(size_t)r * NA + lane]; os = a.old_sigma[(size_t)r * NA + lane]; }
+        const float A_ = a.adv[r], olp = a.old_logp[r], R = a.ret[r], V0 = a.old_v[r];
+        // ---- heads: mu_j = W3a[j] . h3a + b, v = W3c . h3c + b   (butterfly sums; lane j keeps mu_j)
+        float v = hc.x * wc.x + hc.y * wc.y + hc.z * wc.z + hc.w * wc.w;
+        float mu = 0.f;
 #pragma unroll
-    for (int j = 0; j < HA; j++) { gba[j] = 0.f; gstd[j] = 0.f;
+        for (int j = 0; j < NA; j++) {
+            float t = ha.x * wa[j].x + ha.y * wa[j].y + ha.z * wa[j].z + ha.w * wa[j].w;
 #pragma unroll
-        for (int q = 0; q < 4; q++) gWa[j][q] = 0.f; }
-#pragma unroll
-    for (int q = 0; q < 4; q++) { gWc[q] = 0.f; g2a[q] = 0.f; g2c[q] = 0.f; }
-    float gbc = 0.f, kl_s = 0.f, surr_s = 0.f, vl_s = 0.f, cnt_s = 0.f;
-    const int c0 = lane * 4;   // Ha, Hc <= 128 on this path: one float4 per lane
-    for (int r = blockIdx.x * (blockDim.x >> 5) + warp; r < a.B; r += nwarps) {
-        float4 ha = make_float4(0.f, 0.f, 0.f, 0.f), hc = ha;
-        if (c0 < Ha) ha = *reinterpret_cast<const float4 *>(a.h3a + (size_t)r * Ha + c0);
-        if (c0 < Hc) hc = *reinterpret_cast<const float4 *>(a.h3c + (size_t)r * Hc + c0);
-        float mu[HA], v = 0.f;
-#pragma unroll
-        for (int j = 0; j < HA; j++) {
-            mu[j] = 0.f;
-            if (j < A && c0 < Ha) {
-                const float4 w = *reinterpret_cast<const float4 *>(sWa + j * Ha + c0);
-                mu[j] = ha.x * w.x + ha.y * w.y + ha.z * w.z + ha.w * w.w;
-            }
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(FULL, t, o);
+            if (lane == j) mu = t;
         }
-        if (c0 < Hc) { const float4 w = *reinterpret_cast<const float4 *>(sWc + c0); v = hc.x * w.x + hc.y * w.y + hc.z * w.z + hc.w * w.w; }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            v += __shfl_xor_sync(FULL, v, o);
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+        v += bc;
+        mu += ba;
+        // ---- losses (ppo.py:246-295), same arithmetic as ppo_loss_kernel; lane j holds the terms of action j
+        const float d = ac - mu;
+        float lp = own ? -(d * d) * inv2s2 - logsg - LOG_SQRT_2PI : 0.f;
+        float kl = own ? logf(sg / os + 1.0e-5f) + (os * os + (om - mu) * (om - mu)) * inv2s2 - 0.5f : 0.f;
 #pragma unroll
-            for (int j = 0; j < HA; j++) if (j < A) mu[j] += __shfl_xor_sync(FULL, mu[j], o);
-        }
-        v += a.b3c[0];
-        // ---- losses + output gradients (identical arithmetic to ppo_loss_kernel; every lane computes the row redundantly)
-        float lp = 0.f, kl = 0.f, dmu[HA];
-#pragma unroll
-        for (int j = 0; j < HA; j++) {
-            dmu[j] = 0.f;
-            if (j < A) {
-                mu[j] += a.b3a[j];
-                const float sg = a.std[j], d = a.act[(size_t)r * A + j] - mu[j];
-                lp += -(d * d) / (2.f * sg * sg) - logf(sg) - LOG_SQRT_2PI;
-                const float os = a.old_sigma[(size_t)r * A + j], om = a.old_mu[(size_t)r * A + j];
-                kl += logf(sg / os + 1.0e-5f) + (os * os + (om - mu[j]) * (om - mu[j])) / (2.0f * sg * sg) - 0.5f;
-            }
-        }
-        const float A_ = a.adv[r];
-        const float ratio = expf(lp - a.old_logp[r]);
+        for (int o = 16; o > 0; o >>= 1) { lp += __shfl_xor_sync(FULL, lp, o); kl += __shfl_xor_sync(FULL, kl, o); }
+        const float ratio = expf(lp - olp);
         const float s1 = -A_ * ratio, s2 = -A_ * fminf(fmaxf(ratio, 1.0f - a.clip), 1.0f + a.clip);
         const bool use1 = s1 >= s2, in_clip = ratio >= 1.0f - a.clip && ratio <= 1.0f + a.clip;
         const float dlp = (use1 || in_clip ? -A_ : 0.f) * invB * ratio;
-        const float R = a.ret[r], V0 = a.old_v[r];
         float dv, vl;
         if (a.clipped_value) {
             const float vc = V0 + fminf(fmaxf(v - V0, -a.clip), a.clip);
@@ -520,67 +526,50 @@ __global__ void __launch_bounds__(256) ppo_heads_kernel(const HeadsArgs a) {
             dv = l1 >= l2 ? 2.f * (v - R) : (inc ? 2.f * (vc - R) : 0.f);
         } else { vl = (R - v) * (R - v); dv = -2.f * (R - v); }
         dv *= a.vcoef * invB;
-        if (lane == 0) { kl_s += kl; surr_s += fmaxf(s1, s2); vl_s += vl; cnt_s += 1.f; gbc += dv; }
-        // ---- head backward
+        kl_s += kl; surr_s += fmaxf(s1, s2); vl_s += vl; cnt_s += 1.f; gbc += dv;      // identical on every lane; lane 0 publishes
+        const float dmu = own ? dlp * d / (sg * sg) : 0.f;
+        if (own) { gba += dmu; gsd += dlp * (d * d / (sg * sg * sg) - 1.0f / sg); }
+        // ---- head backward: dh3 = (d out . W3) * ELU'(h3); dW3 += d out (x) h3; db2 += dh3
         float4 da = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < HA; j++) {
-            if (j < A) {
-                const float sg = a.std[j], d = a.act[(size_t)r * A + j] - mu[j];
-                dmu[j] = dlp * d / (sg * sg);
-                if (lane == 0) { gba[j] += dmu[j]; gstd[j] += dlp * (d * d / (sg * sg * sg) - 1.0f / sg); }
-                if (c0 < Ha) {
-                    const float4 w = *reinterpret_cast<const float4 *>(sWa + j * Ha + c0);
-                    da.x += dmu[j] * w.x; da.y += dmu[j] * w.y; da.z += dmu[j] * w.z; da.w += dmu[j] * w.w;
-                    gWa[j][0] += dmu[j] * ha.x; gWa[j][1] += dmu[j] * ha.y; gWa[j][2] += dmu[j] * ha.z; gWa[j][3] += dmu[j] * ha.w;
-                }
-            }
+        for (int j = 0; j < NA; j++) {
+            const float dj = __shfl_sync(FULL, dmu, j);
+            da.x += dj * wa[j].x; da.y += dj * wa[j].y; da.z += dj * wa[j].z; da.w += dj * wa[j].w;
+            gWa[j].x += dj * ha.x; gWa[j].y += dj * ha.y; gWa[j].z += dj * ha.z; gWa[j].w += dj * ha.w;
         }
-        if (c0 < Ha) {
-            da.x *= elu_grad_from_out(ha.x); da.y *= elu_grad_from_out(ha.y); da.z *= elu_grad_from_out(ha.z); da.w *= elu_grad_from_out(ha.w);
-            *reinterpret_cast<float4 *>(a.dh3a + (size_t)r * Ha + c0) = da;
-            g2a[0] += da.x; g2a[1] += da.y; g2a[2] += da.z; g2a[3] += da.w;
-        }
-        if (c0 < Hc) {
-            const float4 w = *reinterpret_cast<const float4 *>(sWc + c0);
-            float4 dc = make_float4(dv * w.x * elu_grad_from_out(hc.x), dv * w.y * elu_grad_from_out(hc.y), dv * w.z * elu_grad_from_out(hc.z),
-                                    dv * w.w * elu_grad_from_out(hc.w));
-            *reinterpret_cast<float4 *>(a.dh3c + (size_t)r * Hc + c0) = dc;
-            g2c[0] += dc.x; g2c[1] += dc.y; g2c[2] += dc.z; g2c[3] += dc.w;
-            gWc[0] += dv * hc.x; gWc[1] += dv * hc.y; gWc[2] += dv * hc.z; gWc[3] += dv * hc.w;
-        }
+        da.x *= elu_grad_from_out(ha.x); da.y *= elu_grad_from_out(ha.y); da.z *= elu_grad_from_out(ha.z); da.w *= elu_grad_from_out(ha.w);
+        *reinterpret_cast<float4 *>(a.dh3a + (size_t)r * H + c0) = da;
+        g2a.x += da.x; g2a.y += da.y; g2a.z += da.z; g2a.w += da.w;
+        const float4 dc = make_float4(dv * wc.x * elu_grad_from_out(hc.x), dv * wc.y * elu_grad_from_out(hc.y),
+                                      dv * wc.z * elu_grad_from_out(hc.z), dv * wc.w * elu_grad_from_out(hc.w));
+        *reinterpret_cast<float4 *>(a.dh3c + (size_t)r * H + c0) = dc;
+        g2c.x += dc.x; g2c.y += dc.y; g2c.z += dc.z; g2c.w += dc.w;
+        gWc.x += dv * hc.x; gWc.y += dv * hc.y; gWc.z += dv * hc.z; gWc.w += dv * hc.w;
     }
-    // ---- block reduction in shared memory, then one global atomic per element per block
+    // ---- CTA reduction in shared memory (16 warps), then one red.global per element per CTA
+    float *aWa = acc, *aWc = aWa + NA * H, *ab2a = aWc + H, *ab2c = ab2a + H, *agba = ab2c + H, *agsd = agba + NA, *amisc = agsd + NA;
 #pragma unroll
-    for (int j = 0; j < HA; j++) {
-        if (j < A && c0 < Ha) {
-#pragma unroll
-            for (int q = 0; q < 4; q++) atomicAdd(&aWa[j * Ha + c0 + q], gWa[j][q]);
-        }
+    for (int j = 0; j < NA; j++) {
+        atomicAdd(&aWa[j * H + c0], gWa[j].x); atomicAdd(&aWa[j * H + c0 + 1], gWa[j].y);
+        atomicAdd(&aWa[j * H + c0 + 2], gWa[j].z); atomicAdd(&aWa[j * H + c0 + 3], gWa[j].w);
     }
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-        if (c0 < Hc) { atomicAdd(&aWc[c0 + q], gWc[q]); atomicAdd(&ab2c[c0 + q], g2c[q]); }
-        if (c0 < Ha) atomicAdd(&ab2a[c0 + q], g2a[q]);
-    }
-    if (lane == 0) {
-#pragma unroll
-        for (int j = 0; j < HA; j++) if (j < A) { atomicAdd(&amisc[j], gba[j]); atomicAdd(&amisc[A + 6 + j], gstd[j]); }
-        atomicAdd(&amisc[A], gbc); atomicAdd(&amisc[A + 1], kl_s); atomicAdd(&amisc[A + 2], cnt_s); atomicAdd(&amisc[A + 3], surr_s); atomicAdd(&amisc[A + 4], vl_s);
-    }
+    atomicAdd(&aWc[c0], gWc.x); atomicAdd(&aWc[c0 + 1], gWc.y); atomicAdd(&aWc[c0 + 2], gWc.z); atomicAdd(&aWc[c0 + 3], gWc.w);
+    atomicAdd(&ab2a[c0], g2a.x); atomicAdd(&ab2a[c0 + 1], g2a.y); atomicAdd(&ab2a[c0 + 2], g2a.z); atomicAdd(&ab2a[c0 + 3], g2a.w);
+    atomicAdd(&ab2c[c0], g2c.x); atomicAdd(&ab2c[c0 + 1], g2c.y); atomicAdd(&ab2c[c0 + 2], g2c.z); atomicAdd(&ab2c[c0 + 3], g2c.w);
+    if (own) { atomicAdd(&agba[lane], gba); atomicAdd(&agsd[lane], gsd); }
+    if (lane == 0) { atomicAdd(&amisc[0], gbc); atomicAdd(&amisc[1], kl_s); atomicAdd(&amisc[2], cnt_s); atomicAdd(&amisc[3], surr_s); atomicAdd(&amisc[4], vl_s); }
     __syncthreads();
-    for (int i = threadIdx.x; i < A * Ha; i += blockDim.x) atomicAdd(&a.gW3a[i], aWa[i]);
-    for (int i = threadIdx.x; i < Hc; i += blockDim.x) { atomicAdd(&a.gW3c[i], aWc[i]); atomicAdd(&a.gb2c[i], ab2c[i]); }
-    for (int i = threadIdx.x; i < Ha; i += blockDim.x) atomicAdd(&a.gb2a[i], ab2a[i]);
-    if (threadIdx.x < A) {
-        atomicAdd(&a.gb3a[threadIdx.x], amisc[threadIdx.x]);
-        float gs = amisc[A + 6 + threadIdx.x];
+    for (int i = threadIdx.x; i < NA * H; i += blockDim.x) atomicAdd(&a.gW3a[i], aWa[i]);
+    for (int i = threadIdx.x; i < H; i += blockDim.x) { atomicAdd(&a.gW3c[i], aWc[i]); atomicAdd(&a.gb2a[i], ab2a[i]); atomicAdd(&a.gb2c[i], ab2c[i]); }
+    if (threadIdx.x < NA) {
+        atomicAdd(&a.gb3a[threadIdx.x], agba[threadIdx.x]);
+        float gs = agsd[threadIdx.x];
         if (blockIdx.x == 0) gs += -a.ecoef * (1.0f / a.std[threadIdx.x]);   // d(-c_e * mean entropy)/d std_j, once per rank
         atomicAdd(&a.gstd[threadIdx.x], gs);
     }
     if (threadIdx.x == 0) {
-        atomicAdd(&a.gb3c[0], amisc[A]);
-        atomicAdd(&a.tail[0], amisc[A + 1]); atomicAdd(&a.tail[1], amisc[A + 2]); atomicAdd(&a.tail[2], amisc[A + 3]); atomicAdd(&a.tail[3], amisc[A + 4]);
+        atomicAdd(&a.gb3c[0], amisc[0]);
+        atomicAdd(&a.tail[0], amisc[1]); atomicAdd(&a.tail[1], amisc[2]); atomicAdd(&a.tail[2], amisc[3]); atomicAdd(&a.tail[3], amisc[4]);
     }
 }
 
@@ -597,7 +586,87 @@ struct Ctl {            // device control block
     float sum_value_loss, sum_surrogate_loss;   // accumulated over the update (ppo.py:308-309)
     int mb_counter;     // minibatches processed in this update (device-side so a replayed graph advances by itself)
     double sumsq;       // scratch: sum of squares of the gradient
+    int comm_epoch;     // NVLink all-reduce epochs completed (flags in peer memory are monotonic epoch numbers)
+    int comm_error;     // set when a peer did not show up within the spin budget (results of that step are invalid)
+    unsigned comm_arrive;   // scratch: blocks of allreduce_kernel that finished their slice
+    int pad_;
 };
+
+// =========================================================================================================
+// Gradient all-reduce over NVLink peer memory, fused with the gradient-norm reduction (multi-GPU).
+// Every rank maps every peer's comm block (cudaIpc): [reduce_buf | gsum | flags].  Per minibatch, ONE kernel per rank:
+//   1. ready barrier: flags[peer].ready[rank] = epoch (st.release.sys into peer memory); spin on the local ready[] row;
+//   2. two-shot: rank r owns float4 slice r of the buffer — it LOADS that slice from all W ranks' reduce_buf over NVLink, sums
+//      in rank order (every element is summed by exactly one rank, so all ranks hold bit-identical results), and STORES the
+//      sum into every rank's gsum (push all-gather); the squared norm of the slice is reduced on the way;
+//   3. the last block to finish publishes the slice's sum of squares and done[rank] = epoch to every peer.
+// prep_apply_kernel then waits for all done[] flags, adds the W partial norms in rank order and proceeds exactly as on one GPU.
+// No NCCL call, no host involvement: the kernel sits in the same CUDA graph as the rest of the minibatch.
+// =========================================================================================================
+constexpr int MAXW = 8;
+constexpr int FLAG_READY = 0, FLAG_DONE = MAXW, FLAG_SUMSQ = 2 * MAXW;   // ints; sumsq partials are doubles at int offset 16 (64-byte aligned)
+constexpr int FLAG_INTS = 2 * MAXW + 2 * MAXW;
+struct CommDev {
+    float *grads[MAXW];
+    float *gsum[MAXW];
+    int *flags[MAXW];
+    int rank, world;
+};
+__device__ __forceinline__ void st_release_sys(int *p, int v) { asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ int ld_acquire_sys(const int *p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// spin until *p >= epoch; gives up after ~2 s worth of clocks and reports through ctl->comm_error (never hangs the GPU)
+__device__ __forceinline__ void wait_flag(const int *p, int epoch, Ctl *ctl) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(p) < epoch) {
+        if (clock64() - t0 > 4000000000ll) { ctl->comm_error = 1; break; }
+        __nanosleep(64);
+    }
+}
+__global__ void __launch_bounds__(256) allreduce_kernel(const CommDev c, int n4, int nparam4, Ctl *ctl) {
+    const int epoch = ctl->comm_epoch + 1;
+    if (blockIdx.x == 0 && threadIdx.x < c.world) st_release_sys(c.flags[threadIdx.x] + FLAG_READY + c.rank, epoch);
+    if (threadIdx.x < c.world) wait_flag(c.flags[c.rank] + FLAG_READY + threadIdx.x, epoch, ctl);
+    __syncthreads();
+    const int per = (n4 + c.world - 1) / c.world, lo = c.rank * per, hi = min(n4, lo + per);
+    float ss = 0.f;
+    for (int i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) {
+        float4 s = reinterpret_cast<const float4 *>(c.grads[0])[i];
+        for (int r = 1; r < c.world; r++) {
+            const float4 v = reinterpret_cast<const float4 *>(c.grads[r])[i];
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        for (int r = 0; r < c.world; r++) reinterpret_cast<float4 *>(c.gsum[r])[i] = s;
+        if (i < nparam4) ss += s.x * s.x + s.y * s.y + s.z * s.z + s.w * s.w;   // the tail (KL / loss sums) is not part of the gradient
+    }
+    __threadfence_system();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(FULL, ss, o);
+    __shared__ float red[8];
+    __shared__ bool last;
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float x = 0.f;
+        for (int k = 0; k < 8; k++) x += red[k];
+        atomicAdd(&ctl->sumsq, (double)x);
+        __threadfence();
+        last = atomicAdd(&ctl->comm_arrive, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x < c.world) {
+        __threadfence_system();
+        const double mine = *reinterpret_cast<volatile double *>(&ctl->sumsq);
+        int *pf = c.flags[threadIdx.x];
+        reinterpret_cast<double *>(pf + FLAG_SUMSQ)[c.rank] = mine;
+        __threadfence_system();
+        st_release_sys(pf + FLAG_DONE + c.rank, epoch);
+    }
+    if (last && threadIdx.x == 0) ctl->comm_arrive = 0;
+}
 __global__ void gradnorm_kernel(const float *g, int n, Ctl *ctl) {
     float s = 0.f;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += g[i] * g[i];
@@ -618,10 +687,22 @@ struct PrepArgs {
     const float *tail, *std;
     int A, adaptive, world_size;
     float desired_kl, lr_min, lr_max, max_grad_norm, vcoef, ecoef;
+    int *comm_flags;   // this rank's flag block when the NVLink all-reduce is active, else NULL
+    int comm_rank;
 };
 __global__ void prep_apply_kernel(const PrepArgs a) {
+    if (a.comm_flags != nullptr) {   // wait until every rank has pushed its slice of the summed gradient (and its partial norm)
+        if (threadIdx.x < a.world_size) wait_flag(a.comm_flags + FLAG_DONE + threadIdx.x, a.ctl->comm_epoch + 1, a.ctl);
+        __syncwarp();
+    }
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     Ctl &c = *a.ctl;
+    if (a.comm_flags != nullptr) {
+        double t = 0.0;
+        for (int r = 0; r < a.world_size; r++) t += reinterpret_cast<const volatile double *>(a.comm_flags + FLAG_SUMSQ)[r];   // rank order: identical on every rank
+        c.sumsq = t;
+        c.comm_epoch += 1;
+    }
     const float cnt = a.tail[1];
     const float kl_mean = a.tail[0] / cnt;
     if (a.adaptive) {                                                                  // ppo.py:262-268, 207-213
@@ -695,6 +776,19 @@ struct grx_ppo {
     std::vector<void *> allocs;
     cudaGraphExec_t graph = nullptr;
     const int64_t *graph_indices = nullptr;
+    // phase timing of the stepwise minibatch entries (GRX_PPO_TIMING=1; profiling only: it synchronises after every minibatch)
+    bool timing = false;
+    cudaEvent_t tev[9] = {};
+    double tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int tcount = 0;
+    // NVLink peer-memory all-reduce (world_size > 1): comm block = [reduce_buf | gsum | flags], one cudaIpc handle per rank
+    void *comm_block = nullptr;
+    size_t comm_bytes = 0;
+    float *gsum = nullptr;
+    int *flags = nullptr;
+    bool comm_open = false;
+    CommDev comm;
+    std::vector<void *> peer_maps;
 };
 
 static int ppo_alloc(grx_ppo *p, void **ptr, size_t bytes) {
@@ -735,7 +829,16 @@ extern "C" int grx_ppo_create(const grx_ppo_cfg *cfg, int32_t device, grx_ppo **
     layout_net(p->critic, dc, off);
     p->nparam = (off + 3) & ~(size_t)3;
     const size_t TN = (size_t)p->T * p->N, MR = p->MR;
-    PALLOC(p->params, p->nparam * 4); PALLOC(p->reduce_buf, (p->nparam + TAIL) * 4); PALLOC(p->adam_m, p->nparam * 4); PALLOC(p->adam_v, p->nparam * 4);
+    PALLOC(p->params, p->nparam * 4); PALLOC(p->adam_m, p->nparam * 4); PALLOC(p->adam_v, p->nparam * 4);
+    {   // comm block: its own cudaMalloc so that one cudaIpc handle covers exactly [reduce_buf | gsum | flags]
+        const size_t nb = ((p->nparam + TAIL) * 4 + 255) & ~(size_t)255;
+        p->comm_bytes = 2 * nb + 256;
+        PALLOC(p->comm_block, p->comm_bytes);
+        p->reduce_buf = (float *)p->comm_block;
+        p->gsum = (float *)((char *)p->comm_block + nb);
+        p->flags = (int *)((char *)p->comm_block + 2 * nb);
+        memset(&p->comm, 0, sizeof(p->comm));
+    }
     PALLOC(p->s_obs, TN * p->O * 4); PALLOC(p->s_cobs, TN * p->P * 4); PALLOC(p->s_act, TN * p->A * 4); PALLOC(p->s_val, TN * 4);
     PALLOC(p->s_rew, TN * 4); PALLOC(p->s_logp, TN * 4); PALLOC(p->s_mu, TN * p->A * 4); PALLOC(p->s_sigma, TN * p->A * 4);
     PALLOC(p->s_ret, TN * 4); PALLOC(p->s_adv, TN * 4); PALLOC(p->s_done, TN);
@@ -755,6 +858,8 @@ extern "C" int grx_ppo_create(const grx_ppo_cfg *cfg, int32_t device, grx_ppo **
         c.lr = cfg->learning_rate;
         CK(cudaMemcpy(p->ctl, &c, sizeof(c), cudaMemcpyHostToDevice));
     }
+    if (const char *e = getenv("GRX_PPO_TIMING")) p->timing = atoi(e) != 0;
+    if (p->timing) for (int i = 0; i < 9; i++) CK(cudaEventCreate(&p->tev[i]));
     *out = p;
     return GRX_OK;
 }
@@ -763,6 +868,7 @@ extern "C" int grx_ppo_destroy(grx_ppo *p) {
     if (!p) return GRX_OK;
     cudaSetDevice(p->device);
     if (p->graph) cudaGraphExecDestroy(p->graph);
+    for (void *q : p->peer_maps) cudaIpcCloseMemHandle(q);
     for (void *q : p->allocs) cudaFree(q);
     delete p;
     return GRX_OK;
@@ -795,6 +901,7 @@ extern "C" int grx_ppo_get_buffer(grx_ppo *p, const char *name, grx_buffer *b) {
     if (n == "advantages") { set_buf(b, p->s_adv, GRX_F32, 3, T, N, 1); return GRX_OK; }
     if (n == "dones") { set_buf(b, p->s_done, GRX_U8, 3, T, N, 1); return GRX_OK; }
     if (n == "adv_moments") { set_buf(b, p->moments, GRX_U64, 1, 3, 1, 1); return GRX_OK; }   // 3 doubles (bit pattern)
+    if (n == "gsum") { set_buf(b, p->gsum, GRX_F32, 1, np_ + TAIL, 1, 1); return GRX_OK; }
     if (n == "ctl") { set_buf(b, p->ctl, GRX_F32, 1, sizeof(Ctl) / 4, 1, 1); return GRX_OK; }
     return grx_set_error(GRX_E_NOTFOUND, "grx_ppo_get_buffer: unknown buffer '" + n + "'");
 }
@@ -899,6 +1006,9 @@ extern "C" int grx_ppo_compute_returns(grx_ppo *p, const float *d_last_critic_ob
 
 static int minibatch_grads(grx_ppo *p, const int64_t *d_indices, int mb, bool device_counter, cudaStream_t st) {
     const int B = p->B;
+    const bool tm = p->timing && !device_counter;
+#define TMARK(i) do { if (tm) cudaEventRecord(p->tev[i], st); } while (0)
+    TMARK(0);
     CK(cudaMemsetAsync(p->reduce_buf, 0, (p->nparam + TAIL) * 4, st));
     GatherArgs g; memset(&g, 0, sizeof(g));
     g.indices = d_indices; g.mb_counter = device_counter ? &p->ctl->mb_counter : nullptr; g.mb = mb; g.nmb = p->cfg.num_mini_batches;
@@ -907,11 +1017,14 @@ static int minibatch_grads(grx_ppo *p, const int64_t *d_indices, int mb, bool de
     g.s_logp = p->s_logp; g.s_mu = p->s_mu; g.s_sigma = p->s_sigma;
     g.xa = p->xa; g.xc = p->xc; g.act = p->mb_act; g.val = p->mb_val; g.ret = p->mb_ret; g.adv = p->mb_adv; g.logp = p->mb_logp;
     g.mu = p->mb_mu; g.sigma = p->mb_sigma;
-    gather_kernel<<<592, 256, 0, st>>>(g);
+    gather_kernel<<<148 * 8, 256, 0, st>>>(g);
+    TMARK(1);
     const Net &na = p->actor, &nc = p->critic;
-    const bool fused_heads = p->A <= HA && nc.dims[4] == 1 && na.dims[3] <= 128 && nc.dims[3] <= 128 && (na.dims[3] & 3) == 0 && (nc.dims[3] & 3) == 0;
+    const bool fused_heads = p->A == 10 && nc.dims[4] == 1 && na.dims[3] == HEADS_H && nc.dims[3] == HEADS_H;   // the registered GRx policy; other shapes take the unfused path
     mlp_forward(p, na, p->xa, p->Opad, p->ha, B, fused_heads ? 3 : 4, st);             // ppo.py:244-248
+    TMARK(2);
     mlp_forward(p, nc, p->xc, p->Ppad, p->hc, B, fused_heads ? 3 : 4, st);
+    TMARK(3);
     float *gr = p->reduce_buf;
     if (fused_heads) {
         HeadsArgs a; memset(&a, 0, sizeof(a));
@@ -920,12 +1033,14 @@ static int minibatch_grads(grx_ppo *p, const int64_t *d_indices, int mb, bool de
         a.gW3a = gr + na.w[3]; a.gb3a = gr + na.b[3]; a.gW3c = gr + nc.w[3]; a.gb3c = gr + nc.b[3]; a.gb2a = gr + na.b[2]; a.gb2c = gr + nc.b[2];
         a.gstd = gr; a.tail = gr + p->nparam;
         a.act = p->mb_act; a.old_mu = p->mb_mu; a.old_sigma = p->mb_sigma; a.old_logp = p->mb_logp; a.adv = p->mb_adv; a.ret = p->mb_ret; a.old_v = p->mb_val;
-        a.B = B; a.A = p->A; a.H3a = na.dims[3]; a.H3c = nc.dims[3];
+        a.B = B;
         a.clip = p->cfg.clip_param; a.vcoef = p->cfg.value_loss_coef; a.ecoef = p->cfg.entropy_coef; a.clipped_value = p->cfg.use_clipped_value_loss;
-        const size_t sm = (size_t)(2 * (p->A * a.H3a + a.H3c) + a.H3a + a.H3c + 2 * p->A + 6) * sizeof(float);
-        ppo_heads_kernel<<<296, 256, sm, st>>>(a);
+        ppo_heads_kernel<10><<<148, HEADS_THREADS, 0, st>>>(a);
+        TMARK(4);
         mlp_backward(p, na, p->xa, p->Opad, p->ha, p->da, gr, B, 2, st);
+        TMARK(5);
         mlp_backward(p, nc, p->xc, p->Ppad, p->hc, p->dc, gr, B, 2, st);
+        TMARK(6);
     } else {
         LossArgs a; memset(&a, 0, sizeof(a));
         a.mu = p->ha[3]; a.v = p->hc[3]; a.std = p->params; a.act = p->mb_act; a.old_mu = p->mb_mu; a.old_sigma = p->mb_sigma;
@@ -934,22 +1049,51 @@ static int minibatch_grads(grx_ppo *p, const int64_t *d_indices, int mb, bool de
         a.B = B; a.A = p->A; a.clip = p->cfg.clip_param; a.vcoef = p->cfg.value_loss_coef; a.ecoef = p->cfg.entropy_coef;
         a.clipped_value = p->cfg.use_clipped_value_loss;
         ppo_loss_kernel<<<(B + 255) / 256, 256, 0, st>>>(a);
+        TMARK(4);
         mlp_backward(p, na, p->xa, p->Opad, p->ha, p->da, gr, B, 3, st);
+        TMARK(5);
         mlp_backward(p, nc, p->xc, p->Ppad, p->hc, p->dc, gr, B, 3, st);
+        TMARK(6);
     }
     if (g_launch_err != cudaSuccess) { const cudaError_t e = g_launch_err; g_launch_err = cudaSuccess; return grx_set_error(GRX_E_CUDA, std::string("tensor-core GEMM launch: ") + cudaGetErrorString(e)); }
     CK(cudaGetLastError());
     return GRX_OK;
 }
-static int minibatch_apply(grx_ppo *p, cudaStream_t st) {
-    gradnorm_kernel<<<148, 256, 0, st>>>(p->reduce_buf, (int)p->nparam, p->ctl);
+static int minibatch_apply(grx_ppo *p, cudaStream_t st, bool use_comm) {
+    const float *gsrc = p->reduce_buf;
+    if (use_comm) {   // NVLink all-reduce + norm in one kernel; the summed gradient lands in gsum on every rank
+        allreduce_kernel<<<64, 256, 0, st>>>(p->comm, (int)((p->nparam + TAIL) / 4), (int)(p->nparam / 4), p->ctl);
+        gsrc = p->gsum;
+    } else {
+        gradnorm_kernel<<<148, 256, 0, st>>>(p->reduce_buf, (int)p->nparam, p->ctl);
+    }
     PrepArgs a; memset(&a, 0, sizeof(a));
-    a.ctl = p->ctl; a.tail = p->reduce_buf + p->nparam; a.std = p->params; a.A = p->A; a.adaptive = p->cfg.adaptive_schedule;
+    a.comm_flags = use_comm ? p->flags : nullptr; a.comm_rank = p->comm.rank;
+    a.ctl = p->ctl; a.tail = gsrc + p->nparam; a.std = p->params; a.A = p->A; a.adaptive = p->cfg.adaptive_schedule;
     a.world_size = p->cfg.world_size; a.desired_kl = p->cfg.desired_kl; a.lr_min = p->cfg.learning_rate_min; a.lr_max = p->cfg.learning_rate_max;
     a.max_grad_norm = p->cfg.max_grad_norm; a.vcoef = p->cfg.value_loss_coef; a.ecoef = p->cfg.entropy_coef;
     prep_apply_kernel<<<1, 32, 0, st>>>(a);
-    adam_kernel<<<296, 256, 0, st>>>(p->params, p->reduce_buf, p->adam_m, p->adam_v, (int)p->nparam, p->ctl);
+    adam_kernel<<<296, 256, 0, st>>>(p->params, gsrc, p->adam_m, p->adam_v, (int)p->nparam, p->ctl);
     CK(cudaGetLastError());
+    if (p->timing) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(st, &cs);
+        if (cs == cudaStreamCaptureStatusNone) {
+            cudaEventRecord(p->tev[7], st);
+            CK(cudaEventSynchronize(p->tev[7]));
+            for (int i = 0; i < 7; i++) { float ms = 0.f; if (cudaEventElapsedTime(&ms, p->tev[i], p->tev[i + 1]) == cudaSuccess) p->tacc[i] += ms; }
+            p->tcount++;
+        }
+    }
+    return GRX_OK;
+}
+/* profiling: mean microseconds per minibatch of [memset+gather, actor fwd, critic fwd, heads/loss, actor bwd, critic bwd, apply] */
+extern "C" int grx_ppo_debug_timing(grx_ppo *p, float *out7, int32_t *count) {
+    if (!p || !out7) return grx_set_error(GRX_E_INVALID, "grx_ppo_debug_timing: null argument");
+    for (int i = 0; i < 7; i++) out7[i] = p->tcount ? (float)(p->tacc[i] / p->tcount * 1e3) : 0.f;
+    if (count) *count = p->tcount;
+    for (int i = 0; i < 8; i++) p->tacc[i] = 0;
+    p->tcount = 0;
     return GRX_OK;
 }
 
@@ -959,13 +1103,54 @@ extern "C" int grx_ppo_minibatch_grads(grx_ppo *p, const int64_t *d_indices, int
 }
 extern "C" int grx_ppo_minibatch_apply(grx_ppo *p, void *stream) {
     if (!p) return grx_set_error(GRX_E_INVALID, "null ppo");
-    return minibatch_apply(p, (cudaStream_t)stream);
+    return minibatch_apply(p, (cudaStream_t)stream, false);   // the caller all-reduced reduce_buf itself (NCCL path) or world_size == 1
+}
+
+// ---- NVLink all-reduce setup: exchange grx_ppo_comm_handle() blobs between the ranks (any host channel), then open them
+extern "C" int grx_ppo_comm_handle(grx_ppo *p, void *out64) {
+    if (!p || !out64) return grx_set_error(GRX_E_INVALID, "grx_ppo_comm_handle: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    CK(cudaSetDevice(p->device));
+    CK(cudaIpcGetMemHandle(&h, p->comm_block));
+    memcpy(out64, &h, sizeof(h));
+    return GRX_OK;
+}
+extern "C" int grx_ppo_comm_open(grx_ppo *p, int32_t rank, int32_t world, const void *handles) {
+    if (!p || !handles || world < 2 || world > MAXW || rank < 0 || rank >= world || world != p->cfg.world_size)
+        return grx_set_error(GRX_E_INVALID, "grx_ppo_comm_open: need 2 <= world == cfg.world_size <= 8 and 0 <= rank < world");
+    if (p->comm_open) return grx_set_error(GRX_E_STATE, "grx_ppo_comm_open: already open");
+    CK(cudaSetDevice(p->device));
+    const size_t nb = ((p->nparam + TAIL) * 4 + 255) & ~(size_t)255;
+    for (int r = 0; r < world; r++) {
+        void *base = p->comm_block;
+        if (r != rank) {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, (const char *)handles + (size_t)r * sizeof(h), sizeof(h));
+            CK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+            p->peer_maps.push_back(base);
+        }
+        p->comm.grads[r] = (float *)base;
+        p->comm.gsum[r] = (float *)((char *)base + nb);
+        p->comm.flags[r] = (int *)((char *)base + 2 * nb);
+    }
+    p->comm.rank = rank; p->comm.world = world;
+    p->comm_open = true;
+    if (p->graph) { cudaGraphExecDestroy(p->graph); p->graph = nullptr; }
+    return GRX_OK;
+}
+/* apply step of the NVLink path: all-reduce (peer memory) + norm + LR / clip + Adam; every rank must call it once per minibatch */
+extern "C" int grx_ppo_minibatch_apply_comm(grx_ppo *p, void *stream) {
+    if (!p || !p->comm_open) return grx_set_error(GRX_E_STATE, "grx_ppo_minibatch_apply_comm: call grx_ppo_comm_open first");
+    return minibatch_apply(p, (cudaStream_t)stream, true);
 }
 
 // Whole PPO.update (ppo.py:215-321): one minibatch (grads + apply) is captured once as a CUDA graph whose gather kernel
 // reads the minibatch index from the device control block, then replayed epochs x minibatches times.
 extern "C" int grx_ppo_update(grx_ppo *p, const int64_t *d_indices, void *stream) {
     if (!p || !d_indices) return grx_set_error(GRX_E_INVALID, "grx_ppo_update: null argument");
+    if (p->cfg.world_size > 1 && !p->comm_open)
+        return grx_set_error(GRX_E_STATE, "grx_ppo_update: world_size > 1 needs grx_ppo_comm_open (NVLink all-reduce) or the stepwise grads / all-reduce / apply entries");
     cudaStream_t st = (cudaStream_t)stream;
     // reset the per-update accumulators (mb_counter, loss sums); lr / Adam step persist
     CK(cudaMemsetAsync(&p->ctl->sum_value_loss, 0, 2 * sizeof(float) + sizeof(int), st));
@@ -976,7 +1161,7 @@ extern "C" int grx_ppo_update(grx_ppo *p, const int64_t *d_indices, void *stream
         cudaGraph_t gr;
         CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
         int rc = minibatch_grads(p, d_indices, 0, true, cs);
-        if (!rc) rc = minibatch_apply(p, cs);
+        if (!rc) rc = minibatch_apply(p, cs, p->comm_open);
         cudaError_t ce = cudaStreamEndCapture(cs, &gr);
         cudaStreamDestroy(cs);
         if (rc) return rc;

@@ -8,6 +8,7 @@ No CPU fallback: constructing these objects without the CUDA library / a CUDA de
 from __future__ import annotations
 
 import ctypes as C
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -189,8 +190,24 @@ class PPO:
         self._actions = torch.zeros(num_envs, c.num_actions, device=self.device)
         self.mini_batch_size = (num_envs * num_transitions_per_env) // self.num_mini_batches
         self._indices = torch.zeros(self.num_mini_batches * self.mini_batch_size, dtype=torch.int64, device=self.device)
+        self._comm = False
         if self.world_size > 1:
             self.broadcast_parameters()
+            if os.environ.get("GRX_COMM", "nvlink") == "nvlink":
+                self._open_comm()
+
+    def _open_comm(self):
+        """Map every peer's gradient block (cudaIpc over NVLink) so the per-minibatch all-reduce is one of OUR kernels inside the
+        update's CUDA graph instead of an NCCL call from the host loop.  GRX_COMM=nccl keeps the NCCL path."""
+        import torch.distributed as dist
+        h = (C.c_char * 64)()
+        L.check(self.lib.grx_ppo_comm_handle(self._h, h))
+        rank = dist.get_rank(self.process_group)
+        gathered = [None] * self.world_size
+        dist.all_gather_object(gathered, bytes(h.raw), group=self.process_group)
+        L.check(self.lib.grx_ppo_comm_open(self._h, rank, self.world_size, b"".join(gathered)))
+        dist.barrier(group=self.process_group)
+        self._comm = True
 
     def _view(self, name):
         b = L.Buffer()
@@ -276,7 +293,7 @@ class PPO:
         else:
             self._indices.copy_(indices.to(self.device, torch.int64))
         idx = C.c_void_p(self._indices.data_ptr())
-        if self.world_size == 1:
+        if self.world_size == 1 or self._comm:
             L.check(self.lib.grx_ppo_update(self._h, idx, self._stream()))
         else:
             self.ctl[11:14].zero_()
