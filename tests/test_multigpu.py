@@ -73,7 +73,7 @@ def test_nvlink_allreduce_update_equals_nccl_update():
     # a sum of two floats does not depend on the order, so the two transports agree up to the run-to-run rounding of the split-K
     # atomics inside each rank's backward (Adam turns a relative gradient wobble on a near-zero element into at most ~lr)
     for k in (2, 3):
-        d = np.abs(nv[0][k] - nc[0][k])
-        assert d.max() < 2e-3 and d.mean() < 2e-6, (k, d.max(), d.mean())
+        d, scale = np.abs(nv[0][k] - nc[0][k]), np.abs(nc[0][k]).mean()
+        assert d.max() < 2e-3 and d.mean() < 2e-2 * scale, (k, d.max(), d.mean(), scale)
     assert nv[0][4]["step"] == nc[0][4]["step"] == 8
     assert abs(nv[0][4]["lr"] - nc[0][4]["lr"]) < 1e-9

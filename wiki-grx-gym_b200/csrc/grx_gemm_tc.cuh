@@ -2,16 +2,20 @@
 //
 //   C[m,n] (op)= sum_k A(m,k) B(k,n)        fp32 in HBM, TF32 multiply, fp32 accumulate in TMEM
 //
-// One CTA per 128 x BN output tile (BN = 128 / 64 / 32; two CTAs per SM so one tile's epilogue overlaps the other's main
-// loop), 10 warps with fixed roles:
-//   warp 8, one lane  TMA producer: per 32-deep contraction chunk it arms the stage's `full` mbarrier with the byte count
-//                     (mbarrier.arrive.expect_tx) and issues cp.async.bulk.tensor.2d loads for the A and B boxes; TMA writes the
-//                     boxes straight into the UMMA canonical shared-memory layouts and zero-fills everything out of bounds
+// PERSISTENT, GROUPED kernel: one CTA per SM walks a static round-robin list of 128 x BN output tiles that may span several
+// independent problems of the same operand layout (actor + critic layer of the same depth, or all weight-gradient GEMMs of a
+// backward pass), so one launch covers both networks and the pipelines never drain between tiles.  10 warps, fixed roles:
+//   warp 8, one lane  TMA producer: runs ahead over the whole tile list; per 32-deep contraction chunk it arms the stage's `full`
+//                     mbarrier with the byte count and issues cp.async.bulk.tensor.2d loads for the A and B boxes; TMA writes
+//                     the boxes straight into the UMMA canonical shared-memory layouts and zero-fills out of bounds
 //                     (ragged M / N / K need no predication anywhere);
 //   warp 9, one lane  MMA issuer: waits `full`, issues 4 x tcgen05.mma.cta_group::1.kind::tf32 (K = 8 each) on shared-memory
-//                     descriptors, then tcgen05.commit -> the stage's `empty` mbarrier (and the accumulator barrier at the end);
-//   warps 0-7         epilogue: tcgen05.ld 32x32b.x16 from TMEM (warp w: lane quadrant w % 4, column half w / 4), then
-//                     bias / ELU / ELU' / split-K red.global.add.v4.f32, 16-byte stores.
+//                     descriptors into one of TWO TMEM accumulators, tcgen05.commit -> the stage's `empty` mbarrier, and after
+//                     the tile's last chunk -> that accumulator's `acc_full` mbarrier;
+//   warps 0-7         epilogue of tile i while the MMA warp already works on tile i+1; the warps are independent (no block
+//                     barrier): tcgen05.ld 32x32b.x32 from TMEM (lane = tile row, 32 consecutive columns = one 128-byte row
+//                     segment) -> bias / ELU / ELU' (+ bias-gradient column sums by a halving butterfly) / split-K
+//                     red.global.add.v4.f32 -> global; then `acc_empty` releases the accumulator.
 // Both operand majors are supported, so the three GEMM shapes of an MLP layer (forward X W^T, input gradient dY W, weight
 // gradient dY^T X) run on this kernel without transposed copies:
 //   A_KMAJ: A(m,k) = A[m*lda + k]  (contraction contiguous)   else  A[k*lda + m]
@@ -29,6 +33,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <mutex>
 #include <unordered_map>
@@ -36,6 +41,18 @@
 namespace tc {
 
 constexpr int TM = 128, TK = 32, NTHREADS_CTA = 320;   // 8 epilogue warps + TMA warp + MMA warp
+constexpr int MAXP = 4;                                 // problems per grouped launch
+
+// profiling stamps of CTA 0 (ns, %globaltimer): [0] entry, [1] setup done, [2] first TMA issued, [3] first stage landed,
+// [4] last MMA committed, [5] first accumulator complete (epilogue starts), [6] epilogue of the last tile done
+__device__ unsigned long long g_stamps[8];
+__device__ __forceinline__ void stamp(int i) {
+    if (blockIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        g_stamps[i] = t;
+    }
+}
 
 struct Args {
     float *C;
@@ -43,8 +60,18 @@ struct Args {
     const float *aux;    // EPI 2: same layout as C
     float *colsum;       // EPI 2, optional: colsum[n] += sum over rows of the stored C (bias gradient of the layer below)
     int M, N, K, ldc;
-    int kchunk;          // contraction elements per blockIdx.z (multiple of 32)
-    int dbg;             // profiling switches (GRX_TC_DEBUG): 1 skip MMA issue, 2 skip operand loads, 4 skip epilogue stores
+    int kchunk;          // contraction elements per split (multiple of 32)
+    int nt_m, nt_n;      // tiles along M / N
+    int tile_begin;      // first linear tile id of this problem in the group (tiles = nt_m * nt_n * splits)
+};
+struct Group {
+    Args g[MAXP];
+    int np, total_tiles;
+};
+struct Maps {
+    CUtensorMap a[MAXP], b[MAXP];
+    CUtensorMap c[MAXP];     // output, box {32 columns, 32 rows}, SWIZZLE_128B (TMA store / reduce-add)
+    CUtensorMap aux[MAXP];   // EPI 2: the activation the gradient is masked with, same box
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -65,6 +92,16 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
+// TMA: 2-D box store / reduce-add shared -> global (bulk async-group completion); out-of-bounds rows / columns are clipped
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int c0, int c1, uint32_t src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0), "r"(c1), "r"(src) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap *map, int c0, int c1, uint32_t src) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0), "r"(c1), "r"(src) : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -85,6 +122,34 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float *v) {
 #pragma unroll
     for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float *v) {
+    uint32_t r[32];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+                   "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+                   "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+// Column sums over the 32 lanes of a warp of CW per-lane values (lane = tile row) by a halving butterfly: CW - 1 (+1) shuffles
+// instead of 5 CW; afterwards lane l (l < CW, and its mirror l + 16 when CW == 16) holds the total of column l in v[0].
+template <int CW>
+__device__ __forceinline__ void warp_colsum(float *v, int lane) {
+#pragma unroll
+    for (int w = CW / 2, bit = CW / 2; w >= 1; w >>= 1, bit >>= 1) {
+        const bool up = (lane & bit) != 0;
+#pragma unroll
+        for (int i = 0; i < w; i++) {
+            const float send = up ? v[i] : v[i + w], keep = up ? v[i + w] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+        }
+    }
+    if (CW == 16) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 16);
+}
 // shared-memory matrix descriptor, version 1 (sm_100): start[0,14) LBO[16,30) SBO[32,46) (all >> 4), layout type [61,64):
 // 2 = SWIZZLE_128B (K-major tiles), 1 = SWIZZLE_128B_BASE32B (MN-major TF32 tiles)
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout_type) {
@@ -98,55 +163,79 @@ __host__ __device__ constexpr uint32_t tile_bytes(int rows) { return (uint32_t)r
 
 // EPI: 0 C = acc + bias[n] | 1 C = elu(acc + bias[n]) | 2 C = acc * ELU'(aux[m,n]) | 3 split-K: C += acc (red.global.add)
 template <bool A_KMAJ, bool B_KMAJ, int EPI, int BN, int S>
-__global__ void __launch_bounds__(NTHREADS_CTA, 2) gemm_tf32_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                                                                    const Args g) {
+__global__ void __launch_bounds__(NTHREADS_CTA, 1) gemm_tf32_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Group grp) {
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ __align__(8) unsigned long long full_bar[S], empty_bar[S], accum_bar;
+    constexpr int EPW = BN >= 64 ? 8 : 4;          // epilogue warps that own columns (BN = 32: one 32-column chunk per lane quadrant)
+    constexpr int NCH = BN >= 64 ? BN / 64 : 1;    // 32-column chunks per epilogue warp and tile
+    __shared__ __align__(8) unsigned long long full_bar[S], empty_bar[S], acc_full[2], acc_empty[2], aux_bar[8][2];
     __shared__ uint32_t tmem_slot;
-    __shared__ float colsum_s[BN];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int m0 = blockIdx.y * TM, n0 = blockIdx.x * BN;
-    const int kbeg = blockIdx.z * g.kchunk, kend = min(g.K, kbeg + g.kchunk);
-    const int nchunks = (kend - kbeg + TK - 1) / TK;
+    if (tid == 0) stamp(0);
     constexpr uint32_t a_bytes = tile_bytes(TM), b_bytes = tile_bytes(BN), stage_bytes = a_bytes + b_bytes;
     const uint32_t smem0 = (smem_u32(smem) + 1023u) & ~1023u;   // swizzle atoms need 1024-byte aligned tiles
 
     if (tid == 0) {
         for (int i = 0; i < S; i++) { mbar_init(smem_u32(&full_bar[i]), 1); mbar_init(smem_u32(&empty_bar[i]), 1); }
-        mbar_init(smem_u32(&accum_bar), 1);
+        for (int i = 0; i < 2; i++) { mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_empty[i]), EPW); }
+        for (int i = 0; i < 16; i++) mbar_init(smem_u32(&aux_bar[i >> 1][i & 1]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {   // TMEM allocation: BN fp32 accumulator columns (power of two >= 32), one warp
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(BN) : "memory");
+    if (warp == 0) {   // TMEM: two BN-column fp32 accumulators (power of two >= 32 columns), allocated by one warp
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(2 * BN) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (warp == 8 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+        for (int p = 0; p < grp.np; p++) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[p]) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b[p]) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.c[p]) : "memory");
+            if (EPI == 2) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.aux[p]) : "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
+    if (tid == 0) stamp(1);
+
+    // tile id -> (problem, m0, n0, contraction range); every role walks the same sequence t = blockIdx.x, + gridDim.x, ...
+    struct Tile { int p, m0, n0, kbeg, nchunks; };
+    auto decode = [&](int t) {
+        Tile T;
+        int p = 0;
+        while (p + 1 < grp.np && t >= grp.g[p + 1].tile_begin) p++;
+        const Args &g = grp.g[p];
+        const int local = t - g.tile_begin;
+        const int tn = local % g.nt_n, rest = local / g.nt_n, tm = rest % g.nt_m, z = rest / g.nt_m;
+        T.p = p; T.m0 = tm * TM; T.n0 = tn * BN; T.kbeg = z * g.kchunk;
+        const int kend = min(g.K, T.kbeg + g.kchunk);
+        T.nchunks = (kend - T.kbeg + TK - 1) / TK;
+        return T;
+    };
 
     if (warp == 8) {
         if (lane == 0) {   // ---- TMA producer
-            for (int kb = 0; kb < nchunks; kb++) {
-                const int st = kb % S;
-                if (kb >= S) mbar_wait(smem_u32(&empty_bar[st]), (uint32_t)(((kb / S) - 1) & 1));
-                const uint32_t ta = smem0 + (uint32_t)st * stage_bytes, tb = ta + a_bytes, bar = smem_u32(&full_bar[st]);
-                const int k0 = kbeg + kb * TK;
-                if (g.dbg & 2) { mbar_arrive(bar); continue; }
-                mbar_expect_tx(bar, stage_bytes);
-                if (A_KMAJ) tma_load_2d(ta, &map_a, k0, m0, bar);
-                else {
+            uint32_t it = 0;   // chunk counter across tiles -> stage / phase
+            for (int t = blockIdx.x; t < grp.total_tiles; t += gridDim.x) {
+                const Tile T = decode(t);
+                const CUtensorMap *ma = &maps.a[T.p], *mb = &maps.b[T.p];
+                for (int kb = 0; kb < T.nchunks; kb++, it++) {
+                    const uint32_t st = it % S;
+                    if (it >= S) mbar_wait(smem_u32(&empty_bar[st]), ((it / S) - 1) & 1);
+                    const uint32_t ta = smem0 + st * stage_bytes, tb = ta + a_bytes, bar = smem_u32(&full_bar[st]);
+                    const int k0 = T.kbeg + kb * TK;
+                    mbar_expect_tx(bar, stage_bytes);
+                    if (A_KMAJ) tma_load_2d(ta, ma, k0, T.m0, bar);
+                    else {
 #pragma unroll
-                    for (int j = 0; j < TM / 32; j++) tma_load_2d(ta + (uint32_t)j * 4096u, &map_a, m0 + 32 * j, k0, bar);
-                }
-                if (B_KMAJ) tma_load_2d(tb, &map_b, k0, n0, bar);
-                else {
+                        for (int j = 0; j < TM / 32; j++) tma_load_2d(ta + (uint32_t)j * 4096u, ma, T.m0 + 32 * j, k0, bar);
+                    }
+                    if (B_KMAJ) tma_load_2d(tb, mb, k0, T.n0, bar);
+                    else {
 #pragma unroll
-                    for (int j = 0; j < BN / 32; j++) tma_load_2d(tb + (uint32_t)j * 4096u, &map_b, n0 + 32 * j, k0, bar);
+                        for (int j = 0; j < BN / 32; j++) tma_load_2d(tb + (uint32_t)j * 4096u, mb, T.n0 + 32 * j, k0, bar);
+                    }
+                    if (it == 0) stamp(2);
                 }
             }
         }
@@ -157,84 +246,113 @@ __global__ void __launch_bounds__(NTHREADS_CTA, 2) gemm_tf32_kernel(const __grid
                                        ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
             constexpr uint32_t a_lbo = A_KMAJ ? 16u : 4096u, a_sbo = A_KMAJ ? 1024u : 512u, a_step = A_KMAJ ? 32u : 1024u, a_type = A_KMAJ ? 2u : 1u;
             constexpr uint32_t b_lbo = B_KMAJ ? 16u : 4096u, b_sbo = B_KMAJ ? 1024u : 512u, b_step = B_KMAJ ? 32u : 1024u, b_type = B_KMAJ ? 2u : 1u;
-            for (int kb = 0; kb < nchunks; kb++) {
-                const int st = kb % S;
-                mbar_wait(smem_u32(&full_bar[st]), (uint32_t)((kb / S) & 1));
-                tc_fence_after();
-                const uint32_t ta = smem0 + (uint32_t)st * stage_bytes, tb = ta + a_bytes;
+            uint32_t it = 0, ti = 0;
+            for (int t = blockIdx.x; t < grp.total_tiles; t += gridDim.x, ti++) {
+                const Tile T = decode(t);
+                const uint32_t buf = ti & 1u;
+                if (ti >= 2) { mbar_wait(smem_u32(&acc_empty[buf]), ((ti >> 1) - 1) & 1); tc_fence_after(); }   // epilogue drained this accumulator
+                const uint32_t dacc = tmem + buf * (uint32_t)BN;
+                for (int kb = 0; kb < T.nchunks; kb++, it++) {
+                    const uint32_t st = it % S;
+                    mbar_wait(smem_u32(&full_bar[st]), (it / S) & 1);
+                    tc_fence_after();
+                    if (it == 0) stamp(3);
+                    const uint32_t ta = smem0 + st * stage_bytes, tb = ta + a_bytes;
 #pragma unroll
-                for (int j = 0; j < TK / 8; j++) {
-                    const uint64_t da = smem_desc(ta + (uint32_t)j * a_step, a_lbo, a_sbo, a_type);
-                    const uint64_t db = smem_desc(tb + (uint32_t)j * b_step, b_lbo, b_sbo, b_type);
-                    if (!(g.dbg & 1)) tc_mma_tf32(tmem, da, db, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+                    for (int j = 0; j < TK / 8; j++) {
+                        const uint64_t da = smem_desc(ta + (uint32_t)j * a_step, a_lbo, a_sbo, a_type);
+                        const uint64_t db = smem_desc(tb + (uint32_t)j * b_step, b_lbo, b_sbo, b_type);
+                        tc_mma_tf32(dacc, da, db, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+                    }
+                    tc_commit(smem_u32(&empty_bar[st]));                          // frees the stage when these MMAs have read it
+                    if (kb == T.nchunks - 1) tc_commit(smem_u32(&acc_full[buf]));   // accumulator complete
                 }
-                tc_commit(smem_u32(&empty_bar[st]));                      // frees the stage when these MMAs have read it
-                if (kb == nchunks - 1) tc_commit(smem_u32(&accum_bar));   // accumulator complete
             }
+            stamp(4);
         }
     } else {
-        // ---- epilogue, two phases so that every global access is a full coalesced row segment:
-        //  1. TMEM -> registers -> shared (warp w reads TMEM lanes [32 (w%4), +32) = tile rows, column half w/4; the pipeline
-        //     stages are free by now and hold the 128 x BN fp32 tile with a 16-byte row pad: conflict-free float4 stores);
-        //  2. each warp streams 16 tile rows shared -> global with lane = 4 consecutive columns: bias / ELU / ELU' (aux read with
-        //     the same coalesced pattern) / split-K red.global.add.v4.f32.
-        if (nchunks > 0) mbar_wait(smem_u32(&accum_bar), 0);
-        tc_fence_after();
-        constexpr int PITCH = BN + 4;   // floats
-        float *tile = reinterpret_cast<float *>(smem + (smem0 - smem_u32(smem)));
-        {
-            const int quad = warp & 3, chalf = warp >> 2, r = quad * 32 + lane;
-#pragma unroll 1
-            for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 16) {
-                float v[16];
-                if (nchunks > 0) tc_ld16(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
-                else {
+        // ---- epilogue (independent warps, no block-level synchronisation): warp w owns TMEM lanes [32 (w%4), +32) = tile rows and
+        // the column half w/4.  Per 32-column chunk: tcgen05.ld 32x32b.x32 -> registers (lane = row) -> bias / ELU / ELU' ->
+        // the warp's 4 KB staging box in shared memory (128-byte rows, 16-byte units XOR-swizzled with row % 8: conflict-free
+        // and exactly the SWIZZLE_128B box layout) -> ONE TMA store (or TMA reduce-add for split-K) per chunk; ragged edges
+        // are clipped by the TMA unit.  EPI 2: the activation box is TMA-loaded into the same staging box at tile start (while
+        // the accumulator is still being produced) and overwritten in place; bias-gradient column sums by a halving butterfly.
+        if (warp < EPW) {
+            const int quad = warp & 3, chalf = warp >> 2;
+            const uint32_t stg0 = smem0 + (uint32_t)S * stage_bytes + (uint32_t)warp * (NCH * 4096u);
+            const uint32_t rowoff = (uint32_t)lane * 128u, sw = (uint32_t)(lane & 7);
+            uint32_t ti = 0;
+            for (int t = blockIdx.x; t < grp.total_tiles; t += gridDim.x, ti++) {
+                const Tile T = decode(t);
+                const Args &g = grp.g[T.p];
+                const uint32_t buf = ti & 1u;
+                const int mrow0 = T.m0 + quad * 32, ncol0 = T.n0 + chalf * (BN / 2);
+                if (lane == 0) {
+                    tma_wait_read0();   // the stores of the previous tile have finished reading the staging boxes
+                    if (EPI == 2) {
 #pragma unroll
-                    for (int i = 0; i < 16; i++) v[i] = 0.f;
-                }
-#pragma unroll
-                for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4 *>(tile + r * PITCH + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-            }
-        }
-        if (EPI == 2 && tid < BN) colsum_s[tid] = 0.f;
-        asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 epilogue warps only
-        float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);    // EPI 2: a lane always owns the same 4 columns (32 % (BN/4) == 0)
-        if (!(g.dbg & 4)) {
-            constexpr int V4 = BN / 4;                    // float4 per tile row
-#pragma unroll 1
-            for (int idx = lane; idx < 16 * V4; idx += 32) {
-                const int r = warp * 16 + idx / V4, c = (idx % V4) * 4;
-                const int m = m0 + r, n = n0 + c;
-                if (m >= g.M || n >= g.N) continue;       // N % 4 == 0: a float4 is either fully valid or fully out
-                float4 v = *reinterpret_cast<const float4 *>(tile + r * PITCH + c);
-                float *dst = g.C + (size_t)m * g.ldc + n;
-                if (EPI == 3) {
-                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-                } else {
-                    if (EPI == 0 || EPI == 1) {
-                        const float4 bb = __ldg(reinterpret_cast<const float4 *>(g.bias + n));
-                        v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
-                        if (EPI == 1) { v.x = elu_f(v.x); v.y = elu_f(v.y); v.z = elu_f(v.z); v.w = elu_f(v.w); }
-                    } else {
-                        const float4 h = *reinterpret_cast<const float4 *>(g.aux + (size_t)m * g.ldc + n);
-                        v.x *= h.x > 0.f ? 1.f : h.x + 1.f; v.y *= h.y > 0.f ? 1.f : h.y + 1.f;
-                        v.z *= h.z > 0.f ? 1.f : h.z + 1.f; v.w *= h.w > 0.f ? 1.f : h.w + 1.f;
-                        csum.x += v.x; csum.y += v.y; csum.z += v.z; csum.w += v.w;
+                        for (int ch = 0; ch < NCH; ch++) {
+                            const uint32_t bar = smem_u32(&aux_bar[warp][ch]);
+                            mbar_expect_tx(bar, 4096u);
+                            tma_load_2d(stg0 + ch * 4096u, &maps.aux[T.p], ncol0 + ch * 32, mrow0, bar);
+                        }
                     }
-                    *reinterpret_cast<float4 *>(dst) = v;
+                }
+                __syncwarp();
+                mbar_wait(smem_u32(&acc_full[buf]), (ti >> 1) & 1);
+                tc_fence_after();
+                if (ti == 0 && tid == 0) stamp(5);
+#pragma unroll 1
+                for (int ch = 0; ch < NCH; ch++) {
+                    float v[32];
+                    const int n = ncol0 + ch * 32;
+                    tc_ld32(tmem + ((uint32_t)(quad * 32) << 16) + buf * (uint32_t)BN + (uint32_t)(chalf * (BN / 2) + ch * 32), v);
+                    if (ch == NCH - 1) {   // this warp's last TMEM read of the accumulator: hand it back to the MMA warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
+                    }
+                    const uint32_t box = stg0 + ch * 4096u + rowoff;
+                    if (EPI == 2) mbar_wait(smem_u32(&aux_bar[warp][ch]), ti & 1);
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const uint32_t addr = box + ((((uint32_t)i >> 2) ^ sw) << 4);
+                        float4 x = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        if (EPI == 0 || EPI == 1) {
+                            if (n + i < g.N) {
+                                const float4 bb = __ldg(reinterpret_cast<const float4 *>(g.bias + n + i));
+                                x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
+                            }
+                            if (EPI == 1) { x.x = elu_f(x.x); x.y = elu_f(x.y); x.z = elu_f(x.z); x.w = elu_f(x.w); }
+                        } else if (EPI == 2) {
+                            float4 h;
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(h.x), "=f"(h.y), "=f"(h.z), "=f"(h.w) : "r"(addr));
+                            x.x *= h.x > 0.f ? 1.f : h.x + 1.f; x.y *= h.y > 0.f ? 1.f : h.y + 1.f;     // out-of-bounds box elements were zero-filled:
+                            x.z *= h.z > 0.f ? 1.f : h.z + 1.f; x.w *= h.w > 0.f ? 1.f : h.w + 1.f;     // the accumulator is zero there too (operands zero-filled)
+                            v[i] = x.x; v[i + 1] = x.y; v[i + 2] = x.z; v[i + 3] = x.w;
+                        }
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w) : "memory");
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (EPI == 3) tma_reduce_add_2d(&maps.c[T.p], n, mrow0, stg0 + ch * 4096u);
+                        else tma_store_2d(&maps.c[T.p], n, mrow0, stg0 + ch * 4096u);
+                        tma_commit();
+                    }
+                    if (EPI == 2 && g.colsum != nullptr) {
+                        warp_colsum<32>(v, lane);
+                        if (n + lane < g.N) atomicAdd(&g.colsum[n + lane], v[0]);
+                    }
                 }
             }
+            if (lane == 0) tma_wait_read0();
         }
-        if (EPI == 2 && g.colsum != nullptr) {            // 8 warps -> shared -> one global atomic per column per CTA
-            const int c = (lane % (BN / 4)) * 4;
-            atomicAdd(&colsum_s[c], csum.x); atomicAdd(&colsum_s[c + 1], csum.y); atomicAdd(&colsum_s[c + 2], csum.z); atomicAdd(&colsum_s[c + 3], csum.w);
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (tid < BN && n0 + tid < g.N) atomicAdd(&g.colsum[n0 + tid], colsum_s[tid]);
-        }
+        if (tid == 0) stamp(6);
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(BN) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * BN) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -304,41 +422,94 @@ inline cudaError_t get_tensor_map(const float *base, int rows, int cols, int ld,
     return cudaSuccess;
 }
 
+inline int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
 template <bool A_KMAJ, bool B_KMAJ, int EPI, int BN, int S>
-inline cudaError_t launch_bn(const Problem &p, Args g, int z, cudaStream_t st) {
-    constexpr size_t smem = (size_t)(tile_bytes(TM) + tile_bytes(BN)) * S + 1024;
-    static_assert((size_t)TM * (BN + 4) * 4 <= (size_t)(tile_bytes(TM) + tile_bytes(BN)) * S, "epilogue tile must fit in the pipeline stages");
+inline cudaError_t launch_bn(const Problem *ps, int np, const int *splits, cudaStream_t st) {
+    constexpr size_t smem = (size_t)(tile_bytes(TM) + tile_bytes(BN)) * S + (BN >= 64 ? 8 * (BN / 64) : 4) * 4096 + 1024;
+    static_assert(smem <= 227 * 1024, "shared memory budget");
     static bool attr_done = false;   // per template instantiation
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<A_KMAJ, B_KMAJ, EPI, BN, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
-    CUtensorMap ma, mb;
-    // K-major operand: matrix [extent, K] -> box {32 k, tile rows}.  MN-major operand: matrix [K, extent] -> box {32 mn, 32 k}.
-    cudaError_t e = A_KMAJ ? get_tensor_map(p.A, p.M, p.K, p.lda, TM, true, &ma) : get_tensor_map(p.A, p.K, p.M, p.lda, 32, false, &ma);
-    if (e != cudaSuccess) return e;
-    e = B_KMAJ ? get_tensor_map(p.B, p.N, p.K, p.ldb, BN, true, &mb) : get_tensor_map(p.B, p.K, p.N, p.ldb, 32, false, &mb);
-    if (e != cudaSuccess) return e;
-    dim3 grid((p.N + BN - 1) / BN, (p.M + TM - 1) / TM, z);
-    gemm_tf32_kernel<A_KMAJ, B_KMAJ, EPI, BN, S><<<grid, NTHREADS_CTA, smem, st>>>(ma, mb, g);
+    Maps maps;
+    Group grp;
+    memset(&grp, 0, sizeof(grp));
+    grp.np = np;
+    int total = 0;
+    for (int i = 0; i < np; i++) {
+        const Problem &p = ps[i];
+        // K-major operand: matrix [extent, K] -> box {32 k, tile rows}.  MN-major operand: matrix [K, extent] -> box {32 mn, 32 k}.
+        cudaError_t e = A_KMAJ ? get_tensor_map(p.A, p.M, p.K, p.lda, TM, true, &maps.a[i]) : get_tensor_map(p.A, p.K, p.M, p.lda, 32, false, &maps.a[i]);
+        if (e != cudaSuccess) return e;
+        e = B_KMAJ ? get_tensor_map(p.B, p.N, p.K, p.ldb, BN, true, &maps.b[i]) : get_tensor_map(p.B, p.K, p.N, p.ldb, 32, false, &maps.b[i]);
+        if (e != cudaSuccess) return e;
+        e = get_tensor_map(p.C, p.M, p.N, p.ldc, 32, true, &maps.c[i]);
+        if (e != cudaSuccess) return e;
+        if (EPI == 2) {
+            e = get_tensor_map(p.aux, p.M, p.N, p.ldc, 32, true, &maps.aux[i]);
+            if (e != cudaSuccess) return e;
+        } else maps.aux[i] = maps.c[i];
+        Args &g = grp.g[i];
+        g.C = p.C; g.bias = p.bias; g.aux = p.aux; g.colsum = p.colsum; g.M = p.M; g.N = p.N; g.K = p.K; g.ldc = p.ldc;
+        const int sp = splits && splits[i] > 1 ? splits[i] : 1;
+        g.kchunk = ((p.K + sp - 1) / sp + TK - 1) / TK * TK;
+        const int z = (p.K + g.kchunk - 1) / g.kchunk;
+        g.nt_m = (p.M + TM - 1) / TM; g.nt_n = (p.N + BN - 1) / BN;
+        g.tile_begin = total;
+        total += g.nt_m * g.nt_n * z;
+    }
+    for (int i = np; i < MAXP; i++) { maps.a[i] = maps.a[0]; maps.b[i] = maps.b[0]; maps.c[i] = maps.c[0]; maps.aux[i] = maps.aux[0]; grp.g[i].tile_begin = total; }
+    grp.total_tiles = total;
+    if (total == 0) return cudaSuccess;
+    const int grid = total < sm_count() ? total : sm_count();
+    gemm_tf32_kernel<A_KMAJ, B_KMAJ, EPI, BN, S><<<grid, NTHREADS_CTA, smem, st>>>(maps, grp);
     return cudaGetLastError();
+}
+
+// One launch for `np` (<= MAXP) problems of the same operand layout and epilogue.  N tile: the smallest cost of
+// rounds x bytes-per-tile (these GEMMs are bound by operand traffic from L2, and the tile list is static round-robin).
+template <bool A_KMAJ, bool B_KMAJ, int EPI>
+inline cudaError_t launch_group(const Problem *ps, int np, const int *splits, cudaStream_t st) {
+    if (np < 1 || np > MAXP) return cudaErrorInvalidValue;
+    const int sms = sm_count();
+    long best_cost = -1;
+    int best_bn = 32;
+    const int cands[3] = {128, 64, 32};
+    for (int ci = 0; ci < 3; ci++) {
+        const int bn = cands[ci];
+        long tiles = 0;
+        bool ok = true;
+        for (int i = 0; i < np; i++) {
+            const int sp = splits && splits[i] > 1 ? splits[i] : 1;
+            const int kchunk = ((ps[i].K + sp - 1) / sp + TK - 1) / TK * TK;
+            const int z = (ps[i].K + kchunk - 1) / kchunk;
+            if (bn > 32 && ps[i].N <= bn / 2) ok = false;   // mostly padding
+            tiles += (long)((ps[i].M + TM - 1) / TM) * ((ps[i].N + bn - 1) / bn) * z;
+        }
+        if (!ok && ci < 2) continue;
+        const long rounds = (tiles + sms - 1) / sms;
+        const long cost = rounds * (TM + bn + 24);   // per-tile bytes ~ (128 + BN) per k, + fixed epilogue share
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_bn = bn; }
+    }
+    if (best_bn == 128) return launch_bn<A_KMAJ, B_KMAJ, EPI, 128, 4>(ps, np, splits, st);
+    if (best_bn == 64) return launch_bn<A_KMAJ, B_KMAJ, EPI, 64, 7>(ps, np, splits, st);
+    return launch_bn<A_KMAJ, B_KMAJ, EPI, 32, 8>(ps, np, splits, st);
 }
 
 template <bool A_KMAJ, bool B_KMAJ, int EPI>
 inline cudaError_t launch(const Problem &p, int splits, cudaStream_t st) {
-    Args g;
-    g.C = p.C; g.bias = p.bias; g.aux = p.aux; g.colsum = p.colsum; g.M = p.M; g.N = p.N; g.K = p.K; g.ldc = p.ldc;
-    if (splits < 1) splits = 1;
-    { static const char *e = getenv("GRX_TC_DEBUG"); g.dbg = e ? atoi(e) : 0; }
-    g.kchunk = ((p.K + splits - 1) / splits + TK - 1) / TK * TK;
-    const int z = (p.K + g.kchunk - 1) / g.kchunk;
-    // N tile: these GEMMs are small, parallelism first: 128 only if it divides N and still yields >= ~1 CTA per SM slot
-    const long tiles_m = (p.M + TM - 1) / TM;
-    if (p.N % 128 == 0 && tiles_m * (p.N / 128) * z >= 148) return launch_bn<A_KMAJ, B_KMAJ, EPI, 128, 3>(p, g, z, st);
-    if (p.N > 32 && tiles_m * ((p.N + 63) / 64) * z >= 100) return launch_bn<A_KMAJ, B_KMAJ, EPI, 64, 4>(p, g, z, st);
-    if (p.N > 32 && p.N % 64 == 0) return launch_bn<A_KMAJ, B_KMAJ, EPI, 64, 4>(p, g, z, st);
-    return launch_bn<A_KMAJ, B_KMAJ, EPI, 32, 4>(p, g, z, st);
+    return launch_group<A_KMAJ, B_KMAJ, EPI>(&p, 1, &splits, st);
 }
 
 }  // namespace tc

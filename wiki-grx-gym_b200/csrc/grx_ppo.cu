@@ -152,29 +152,55 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float *X, int M, int 
 
 thread_local cudaError_t g_launch_err = cudaSuccess;   // first failed tensor-core launch (reported by the C entry points)
 
-// Dense-layer dispatch: tcgen05 TF32 kernel when enabled and the shape / alignment allows, else the fp32 SIMT kernel.
+// Dense-layer dispatch for a GROUP of problems with the same operand layout and epilogue (actor + critic layer of the same
+// depth; all weight gradients of a backward pass): ONE persistent tcgen05 TF32 launch when enabled and every shape / alignment
+// allows, else the fp32 SIMT kernel per problem.
 template <bool A_KC, bool B_KC, int EPI>
-void dense(const GemmArgs &g, int splits, bool use_tc, cudaStream_t st) {
-    if (use_tc) {
-        tc::Problem a;
-        a.A = g.A; a.B = g.B; a.C = g.C; a.bias = g.bias; a.aux = g.aux; a.colsum = EPI == 2 ? g.bias_out : nullptr;
-        a.M = g.M; a.N = g.N; a.K = g.K; a.lda = g.lda; a.ldb = g.ldb; a.ldc = g.ldc;
-        if (tc::supported<A_KC, B_KC>(a)) {
-            if (EPI == 3 && g.bias_out) {
-                const int rpb = 512;
-                colsum_kernel<<<dim3((g.M + 31) / 32, (g.K + rpb - 1) / rpb), 256, 0, st>>>(g.A, g.K, g.M, g.lda, rpb, g.bias_out);   // A = dY [rows, out]
+void dense_group(const GemmArgs *gs, const int *splits, int np, bool use_tc, cudaStream_t st) {
+    if (use_tc && np <= tc::MAXP) {
+        tc::Problem ps[tc::MAXP];
+        bool ok = true;
+        for (int i = 0; i < np; i++) {
+            const GemmArgs &g = gs[i];
+            tc::Problem &a = ps[i];
+            a.A = g.A; a.B = g.B; a.C = g.C; a.bias = g.bias; a.aux = g.aux; a.colsum = EPI == 2 ? g.bias_out : nullptr;
+            a.M = g.M; a.N = g.N; a.K = g.K; a.lda = g.lda; a.ldb = g.ldb; a.ldc = g.ldc;
+            ok = ok && tc::supported<A_KC, B_KC>(a);
+            if (EPI == 3) ok = ok && g.M >= 64 && g.N >= 32;   // tiny weight gradients (the output heads) stay on the SIMT kernel
+            if (EPI == 2) ok = ok && g.K >= 64;
+        }
+        if (ok) {
+            for (int i = 0; i < np; i++) {
+                const GemmArgs &g = gs[i];
+                if (EPI == 3 && g.bias_out) {
+                    const int rpb = 512;
+                    colsum_kernel<<<dim3((g.M + 31) / 32, (g.K + rpb - 1) / rpb), 256, 0, st>>>(g.A, g.K, g.M, g.lda, rpb, g.bias_out);   // A = dY [rows, out]
+                }
             }
-            const cudaError_t e = tc::launch<A_KC, B_KC, EPI>(a, splits, st);
+            const cudaError_t e = tc::launch_group<A_KC, B_KC, EPI>(ps, np, splits, st);
             if (e != cudaSuccess && g_launch_err == cudaSuccess) g_launch_err = e;
             return;
         }
     }
-    launch_gemm<A_KC, B_KC, EPI>(g, splits, st);
-    if (EPI == 2 && g.bias_out) {   // column sums of the produced gradient = bias gradient of the layer below
-        const int rpb = 512;
-        colsum_kernel<<<dim3((g.N + 31) / 32, (g.M + rpb - 1) / rpb), 256, 0, st>>>(g.C, g.M, g.N, g.ldc, rpb, g.bias_out);
+    for (int i = 0; i < np; i++) {
+        const GemmArgs &g = gs[i];
+        int sp = splits ? splits[i] : 1;
+        if (EPI == 3) {   // SIMT split-K: enough 64 x 64 tiles to fill the GPU
+            const int tiles = ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
+            sp = (2 * 148 + tiles - 1) / tiles;
+            const int maxs = (g.K + 255) / 256;
+            if (sp > maxs) sp = maxs;
+            if (sp < 1) sp = 1;
+        }
+        launch_gemm<A_KC, B_KC, EPI>(g, sp, st);
+        if (EPI == 2 && g.bias_out) {   // column sums of the produced gradient = bias gradient of the layer below
+            const int rpb = 512;
+            colsum_kernel<<<dim3((g.N + 31) / 32, (g.M + rpb - 1) / rpb), 256, 0, st>>>(g.C, g.M, g.N, g.ldc, rpb, g.bias_out);
+        }
     }
 }
+template <bool A_KC, bool B_KC, int EPI>
+void dense(const GemmArgs &g, int splits, bool use_tc, cudaStream_t st) { dense_group<A_KC, B_KC, EPI>(&g, &splits, 1, use_tc, st); }
 
 // =========================================================================================================
 // Philox4x32-10 + Box-Muller for the rollout's Normal.sample() in fast mode (actor_critic_mlp.py:192-194)
@@ -906,43 +932,63 @@ extern "C" int grx_ppo_get_buffer(grx_ppo *p, const char *name, grx_buffer *b) {
     return grx_set_error(GRX_E_NOTFOUND, "grx_ppo_get_buffer: unknown buffer '" + n + "'");
 }
 
-// MLP forward over M rows (x has row stride ldx): h[l] = elu(h[l-1] W_l^T + b_l) for l < nlayers, last of 4 without ELU (mlp.py:26-41)
-static void mlp_forward(grx_ppo *p, const Net &net, const float *x, int ldx, float *const *h, int M, int nlayers, cudaStream_t st) {
-    const float *in = x;
+// MLP forward over M rows for `nn` networks at once (x has row stride ldx): h[l] = elu(h[l-1] W_l^T + b_l) for l < nlayers, last of 4
+// without ELU (mlp.py:26-41).  Layer l of every network goes into ONE grouped launch.
+struct NetIO {
+    const Net *net;
+    const float *x;
+    int ldx;
+    float *const *h;
+    float *const *d;
+};
+static void mlp_forward(grx_ppo *p, const NetIO *io, int nn, int M, int nlayers, cudaStream_t st) {
     for (int l = 0; l < nlayers; l++) {
-        GemmArgs g; memset(&g, 0, sizeof(g));
-        g.A = in; g.B = p->params + net.w[l]; g.C = h[l]; g.bias = p->params + net.b[l];
-        g.M = M; g.N = net.dims[l + 1]; g.K = net.dims[l]; g.lda = l == 0 ? ldx : net.dims[l]; g.ldb = net.ld[l]; g.ldc = g.N;
-        if (l < 3) dense<true, true, 1>(g, 1, p->cfg.use_tensor_cores != 0, st);
-        else dense<true, true, 0>(g, 1, p->cfg.use_tensor_cores != 0, st);
-        in = h[l];
+        GemmArgs g[2];
+        for (int i = 0; i < nn; i++) {
+            const Net &net = *io[i].net;
+            memset(&g[i], 0, sizeof(GemmArgs));
+            g[i].A = l == 0 ? io[i].x : io[i].h[l - 1]; g[i].B = p->params + net.w[l]; g[i].C = io[i].h[l]; g[i].bias = p->params + net.b[l];
+            g[i].M = M; g[i].N = net.dims[l + 1]; g[i].K = net.dims[l]; g[i].lda = l == 0 ? io[i].ldx : net.dims[l]; g[i].ldb = net.ld[l]; g[i].ldc = g[i].N;
+        }
+        if (l < 3) dense_group<true, true, 1>(g, nullptr, nn, p->cfg.use_tensor_cores != 0, st);
+        else dense_group<true, true, 0>(g, nullptr, nn, p->cfg.use_tensor_cores != 0, st);
     }
 }
-// MLP backward from layer `top` down: d[top] holds dL/d(output of layer top).  Writes weight grads for l <= top, bias grads for
-// l < top (and for l == top when top == 3; with the fused heads kernel top == 2 and db_2, dW_3, db_3 are already done), and d[l-1].
-static void mlp_backward(grx_ppo *p, const Net &net, const float *x, int ldx, float *const *h, float *const *d, float *grads, int M, int top,
-                         cudaStream_t st) {
-    for (int l = top; l >= 0; l--) {
-        const float *hin = l == 0 ? x : h[l - 1];
-        {   // dW_l [out, in (padded)] += dY^T hin
-            GemmArgs g; memset(&g, 0, sizeof(g));
-            g.A = d[l]; g.B = hin; g.C = grads + net.w[l]; g.bias_out = (l == top && top == 3) ? grads + net.b[l] : nullptr;
-            g.M = net.dims[l + 1]; g.N = l == 0 ? net.ld[0] : net.dims[l]; g.K = M; g.lda = net.dims[l + 1]; g.ldb = l == 0 ? ldx : net.dims[l];
-            g.ldc = net.ld[l];
-            const bool use_tc = p->cfg.use_tensor_cores != 0 && g.M >= 64 && g.N >= 32;
-            const int tiles = use_tc ? ((g.M + 127) / 128) * ((g.N + 127) / 128) : ((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN);
-            int splits = (2 * 148 + tiles - 1) / tiles;
-            const int maxs = (M + 255) / 256;
-            if (splits > maxs) splits = maxs;
-            if (splits < 1) splits = 1;
-            dense<false, false, 3>(g, splits, use_tc, st);
+// MLP backward from layer `top` down for `nn` networks: d[top] holds dL/d(output of layer top).  First the input-gradient chain
+// d[l-1] = (d[l] W_l) * ELU'(h[l-1]) (+ db_{l-1} = column sums), one grouped launch per layer; then ALL weight gradients
+// dW_l = d[l]^T h[l-1] (split-K, accumulated with red.global.add) in grouped launches.  Bias grads: l < top from the column sums,
+// l == top only when top == 3 (with the fused heads kernel top == 2 and db_2, dW_3, db_3 are already done).
+static void mlp_backward(grx_ppo *p, const NetIO *io, int nn, float *grads, int M, int top, cudaStream_t st) {
+    const bool tcu = p->cfg.use_tensor_cores != 0;
+    for (int l = top; l >= 1; l--) {
+        GemmArgs g[2];
+        for (int i = 0; i < nn; i++) {
+            const Net &net = *io[i].net;
+            memset(&g[i], 0, sizeof(GemmArgs));
+            g[i].A = io[i].d[l]; g[i].B = p->params + net.w[l]; g[i].C = io[i].d[l - 1]; g[i].aux = io[i].h[l - 1]; g[i].bias_out = grads + net.b[l - 1];
+            g[i].M = M; g[i].N = net.dims[l]; g[i].K = net.dims[l + 1]; g[i].lda = net.dims[l + 1]; g[i].ldb = net.ld[l]; g[i].ldc = net.dims[l];
         }
-        if (l > 0) {   // d[l-1] = (dY W_l) * ELU'(h[l-1]) ; db_{l-1} += colsum(d[l-1])
-            GemmArgs g; memset(&g, 0, sizeof(g));
-            g.A = d[l]; g.B = p->params + net.w[l]; g.C = d[l - 1]; g.aux = h[l - 1]; g.bias_out = grads + net.b[l - 1];
-            g.M = M; g.N = net.dims[l]; g.K = net.dims[l + 1]; g.lda = net.dims[l + 1]; g.ldb = net.ld[l]; g.ldc = net.dims[l];
-            dense<true, false, 2>(g, 1, p->cfg.use_tensor_cores != 0 && g.K >= 64, st);
+        dense_group<true, false, 2>(g, nullptr, nn, tcu, st);
+    }
+    GemmArgs g[8];
+    int splits[8], n = 0;
+    auto flush = [&]() { if (n) dense_group<false, false, 3>(g, splits, n, tcu, st); n = 0; };
+    for (int pass = 0; pass < 2; pass++) {   // pass 0: hidden layers (wide N), pass 1: input layer (narrow N) -> separate tile shapes
+        for (int l = top; l >= 0; l--) {
+            if ((l == 0) != (pass == 1)) continue;
+            for (int i = 0; i < nn; i++) {
+                const Net &net = *io[i].net;
+                GemmArgs &a = g[n];
+                memset(&a, 0, sizeof(GemmArgs));
+                a.A = io[i].d[l]; a.B = l == 0 ? io[i].x : io[i].h[l - 1]; a.C = grads + net.w[l];
+                a.bias_out = (l == top && top == 3) ? grads + net.b[l] : nullptr;
+                a.M = net.dims[l + 1]; a.N = l == 0 ? net.ld[0] : net.dims[l]; a.K = M; a.lda = net.dims[l + 1]; a.ldb = l == 0 ? io[i].ldx : net.dims[l];
+                a.ldc = net.ld[l];
+                splits[n] = (M + 511) / 512;
+                if (++n == tc::MAXP) flush();
+            }
         }
+        flush();
     }
 }
 // stage caller-provided observation rows (any row stride >= width) into the padded, 16-byte aligned input buffers
@@ -956,8 +1002,8 @@ extern "C" int grx_ppo_act(grx_ppo *p, const float *d_obs, const float *d_critic
     cudaStream_t st = (cudaStream_t)stream;
     CK(stage_rows(p->xa, p->Opad, d_obs, p->O, p->N, st));
     CK(stage_rows(p->xc, p->Ppad, d_critic_obs, p->P, p->N, st));
-    mlp_forward(p, p->actor, p->xa, p->Opad, p->ha, p->N, 4, st);
-    mlp_forward(p, p->critic, p->xc, p->Ppad, p->hc, p->N, 4, st);
+    const NetIO io[2] = {{&p->actor, p->xa, p->Opad, p->ha, p->da}, {&p->critic, p->xc, p->Ppad, p->hc, p->dc}};
+    mlp_forward(p, io, 2, p->N, 4, st);
     ActArgs a; memset(&a, 0, sizeof(a));
     const size_t row = (size_t)t * p->N;
     a.obs = d_obs; a.critic_obs = d_critic_obs; a.mu = p->ha[3]; a.value = p->hc[3]; a.std = p->params; a.eps = d_eps;
@@ -984,7 +1030,8 @@ extern "C" int grx_ppo_compute_returns_local(grx_ppo *p, const float *d_last_cri
     if (!p || !d_last_critic_obs) return grx_set_error(GRX_E_INVALID, "grx_ppo_compute_returns: null argument");
     cudaStream_t st = (cudaStream_t)stream;
     CK(stage_rows(p->xc, p->Ppad, d_last_critic_obs, p->P, p->N, st));
-    mlp_forward(p, p->critic, p->xc, p->Ppad, p->hc, p->N, 4, st);                     // ppo.py:204
+    const NetIO io = {&p->critic, p->xc, p->Ppad, p->hc, p->dc};
+    mlp_forward(p, &io, 1, p->N, 4, st);                                               // ppo.py:204
     CK(cudaMemcpyAsync(p->last_values, p->hc[3], (size_t)p->N * 4, cudaMemcpyDeviceToDevice, st));
     CK(cudaMemsetAsync(p->moments, 0, 4 * sizeof(double), st));
     gae_kernel<<<(p->N + 31) / 32, 1024, (size_t)3 * p->T * 33 * sizeof(float), st>>>(p->s_rew, p->s_done, p->s_val, p->last_values, p->cfg.gamma, p->cfg.lam, p->s_ret, p->s_adv,
@@ -1021,9 +1068,9 @@ static int minibatch_grads(grx_ppo *p, const int64_t *d_indices, int mb, bool de
     TMARK(1);
     const Net &na = p->actor, &nc = p->critic;
     const bool fused_heads = p->A == 10 && nc.dims[4] == 1 && na.dims[3] == HEADS_H && nc.dims[3] == HEADS_H;   // the registered GRx policy; other shapes take the unfused path
-    mlp_forward(p, na, p->xa, p->Opad, p->ha, B, fused_heads ? 3 : 4, st);             // ppo.py:244-248
+    const NetIO io[2] = {{&na, p->xa, p->Opad, p->ha, p->da}, {&nc, p->xc, p->Ppad, p->hc, p->dc}};
     TMARK(2);
-    mlp_forward(p, nc, p->xc, p->Ppad, p->hc, B, fused_heads ? 3 : 4, st);
+    mlp_forward(p, io, 2, B, fused_heads ? 3 : 4, st);                                 // ppo.py:244-248
     TMARK(3);
     float *gr = p->reduce_buf;
     if (fused_heads) {
@@ -1037,9 +1084,8 @@ static int minibatch_grads(grx_ppo *p, const int64_t *d_indices, int mb, bool de
         a.clip = p->cfg.clip_param; a.vcoef = p->cfg.value_loss_coef; a.ecoef = p->cfg.entropy_coef; a.clipped_value = p->cfg.use_clipped_value_loss;
         ppo_heads_kernel<10><<<148, HEADS_THREADS, 0, st>>>(a);
         TMARK(4);
-        mlp_backward(p, na, p->xa, p->Opad, p->ha, p->da, gr, B, 2, st);
         TMARK(5);
-        mlp_backward(p, nc, p->xc, p->Ppad, p->hc, p->dc, gr, B, 2, st);
+        mlp_backward(p, io, 2, gr, B, 2, st);
         TMARK(6);
     } else {
         LossArgs a; memset(&a, 0, sizeof(a));
@@ -1050,9 +1096,8 @@ static int minibatch_grads(grx_ppo *p, const int64_t *d_indices, int mb, bool de
         a.clipped_value = p->cfg.use_clipped_value_loss;
         ppo_loss_kernel<<<(B + 255) / 256, 256, 0, st>>>(a);
         TMARK(4);
-        mlp_backward(p, na, p->xa, p->Opad, p->ha, p->da, gr, B, 3, st);
         TMARK(5);
-        mlp_backward(p, nc, p->xc, p->Ppad, p->hc, p->dc, gr, B, 3, st);
+        mlp_backward(p, io, 2, gr, B, 3, st);
         TMARK(6);
     }
     if (g_launch_err != cudaSuccess) { const cudaError_t e = g_launch_err; g_launch_err = cudaSuccess; return grx_set_error(GRX_E_CUDA, std::string("tensor-core GEMM launch: ") + cudaGetErrorString(e)); }
@@ -1179,8 +1224,17 @@ extern "C" int grx_ppo_act_inference(grx_ppo *p, const float *d_obs, int32_t n, 
     if (!p || !d_obs || !d_actions_out || n <= 0 || n > p->MR) return grx_set_error(GRX_E_INVALID, "grx_ppo_act_inference: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     CK(stage_rows(p->xa, p->Opad, d_obs, p->O, n, st));
-    mlp_forward(p, p->actor, p->xa, p->Opad, p->ha, n, 4, st);
+    const NetIO io = {&p->actor, p->xa, p->Opad, p->ha, p->da};
+    mlp_forward(p, &io, 1, n, 4, st);
     CK(cudaMemcpyAsync(d_actions_out, p->ha[3], (size_t)n * p->A * 4, cudaMemcpyDeviceToDevice, st));
+    return GRX_OK;
+}
+
+// Profiling: %globaltimer stamps (ns) of CTA 0 of the most recent tensor-core GEMM launch (see tc::g_stamps).  Synchronises.
+extern "C" int grx_gemm_debug_stamps(uint64_t *out8) {
+    if (!out8) return grx_set_error(GRX_E_INVALID, "grx_gemm_debug_stamps: null argument");
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpyFromSymbol(out8, tc::g_stamps, 8 * sizeof(uint64_t)));
     return GRX_OK;
 }
 
