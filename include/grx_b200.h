@@ -239,8 +239,9 @@ int grx_gemm_debug(int32_t variant, int32_t epi, int32_t M, int32_t N, int32_t K
                    const float *bias, const float *aux, float *bias_out, int32_t splits, int32_t use_tc, void *stream);
 
 /* Profiling: %globaltimer stamps (ns) of CTA 0 of the most recent tensor-core GEMM launch: entry, setup done, first TMA issued,
- * first stage landed, last MMA committed, first accumulator complete, epilogue done, unused.  Synchronises the device. */
-int grx_gemm_debug_stamps(uint64_t *out8);
+ * first stage landed, last MMA committed, first accumulator complete, epilogue done, unused, then epilogue detail of warp 0's
+ * first chunk: TMEM load done, staging written, proxy fence done, TMA store issued, all tiles stored.  16 values.  Synchronises. */
+int grx_gemm_debug_stamps(uint64_t *out16);
 
 #ifdef __cplusplus
 }

@@ -38,3 +38,16 @@ if os.environ.get("GRX_PPO_TIMING"):
     names = ["memset+gather", "actor fwd", "critic fwd", "heads", "actor bwd", "critic bwd", "apply"]
     print("phase us/minibatch (stepwise, events):", {n: round(v, 1) for n, v in zip(names, out)}, "over", cnt.value)
 print(f"N={N} T={T} use_tc={use_tc}: {e0.elapsed_time(e1) / nmb * 1e3:.1f} us per minibatch (B={alg.mini_batch_size})", alg.minibatch_stats())
+stamps = (C.c_uint64 * 16)()
+L.check(alg.lib.grx_gemm_debug_stamps(stamps))
+st = [int(x) for x in stamps]
+print("apply_kernel block 0 (us after entry): reduced %s  barrier %s  scalars %s  adam %s" % tuple(round((x - st[0]) / 1e3, 2) for x in st[1:5]))
+# whole update through the CUDA graph (what the runner uses): no per-launch CPU cost
+alg.update()
+torch.cuda.synchronize()
+e0.record()
+alg.update()
+e1.record()
+torch.cuda.synchronize()
+nmb_total = alg.num_learning_epochs * alg.num_mini_batches
+print(f"graph replay: {e0.elapsed_time(e1) / nmb_total * 1e3:.1f} us per minibatch over {nmb_total} minibatches")

@@ -19,13 +19,17 @@ def run(variant, epi, M, N, K, splits=1, use_tc=1, iters=20):
     for _ in range(iters): f()
     e1.record(); torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / iters * 1e3
-    stamps = (C.c_uint64 * 8)()
+    stamps = (C.c_uint64 * 16)()
     L.check(lib.grx_gemm_debug_stamps(stamps))
     st = [int(x) for x in stamps]
     rel = [round((x - st[0]) / 1e3, 2) for x in st[1:7]]
+    print("   epilogue detail (us after entry): ld %s  staged %s  fenced %s  stored %s  all_tiles %s" % tuple(round((x - st[0]) / 1e3, 2) for x in st[8:13]))
     print("   CTA0 us after entry: setup %s  tma0 %s  stage0 %s  mma_end %s  acc0 %s  epi_end %s" % tuple(rel))
     print(f"dbg={os.environ.get('GRX_TC_DEBUG','0')} variant {variant} M{M} N{N} K{K} splits{splits} tc{use_tc}: {us:.1f} us  {2*M*N*K/us/1e6:.1f} TFLOP/s")
 run(0, 1, 10485, 256, 512)
+run(0, 0, 10485, 256, 512)
+run(0, 0, 10485, 256, 32)
+run(0, 1, 10485, 256, 32)
 run(0, 1, 10485, 512, 168)
 run(1, 2, 10485, 512, 256)
 run(2, 3, 256, 512, 10485, splits=41)

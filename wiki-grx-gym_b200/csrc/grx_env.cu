@@ -389,25 +389,34 @@ __device__ __forceinline__ void mass_and_bias(WS &s, const ModelDev &m, float gr
     __syncwarp();
 }
 
-// ---- Cholesky of M in place (lower factor), right-looking, rolled: lane = (row i = lane & 15, half = lane >> 4).  The zero
-// block between the two legs stays exactly zero (no fill), which chol_solve exploits.
+// ---- Cholesky of M in place (lower factor), right-looking, in REGISTERS: lane (i = lane & 15) holds row i of M; column k of L
+// travels by warp shuffles (pivot from lane k, L[j][k] from lane j), so the factorisation is ~120 shuffle + FMA pairs with no
+// shared-memory round trips or warp barriers inside.  The zero block between the two legs stays exactly zero (no fill): those
+// updates are skipped here and chol_solve exploits the same structure.  Both half-warps compute the same rows (mirror).
 __device__ __noinline__ void cholesky(WS &s, int lane) {
-    const int i = lane & 15, half = lane >> 4;
-#pragma unroll 1
+    const int i = lane & 15;
+    float row[NV];
+#pragma unroll
+    for (int j = 0; j < NV; j++) row[j] = s.M[i][j];
+    float myinv = 0.f;
+#pragma unroll
     for (int k = 0; k < NV; k++) {
-        const float inv = rsqrtf(s.M[k][k]);           // all lanes: broadcast read of the pivot (updated by the previous step)
-        const float lik = s.M[i][k] * inv;               // column k of L (rows i >= k meaningful)
-        __syncwarp();
-        if (half == 0) {
-            if (i == k) { s.M[k][k] = s.M[k][k] * inv; s.invd[k] = inv; }
-            else if (i > k) s.M[i][k] = lik;
+        const float inv = rsqrtf(__shfl_sync(FULL, row[k], k));   // pivot (already updated by steps < k) from lane k
+        const float lik = row[k] * inv;                            // L[i][k] for i >= k (lane k: sqrt of the pivot)
+        row[k] = lik;
+        if (i == k) myinv = inv;
+#pragma unroll
+        for (int j = k + 1; j < NV; j++) {
+            if (k < CH && j >= CH && j < ND) continue;             // leg-1 column x leg-2 row: structurally zero
+            row[j] -= lik * __shfl_sync(FULL, lik, j);             // L[j][k] from lane j; meaningful for i >= j
         }
-        __syncwarp();
-        if (i > k) {                                     // trailing update of row i, columns k+1+half, step 2
-            for (int j = k + 1 + half; j <= i; j += 2) s.M[i][j] -= lik * s.M[j][k];
-        }
-        __syncwarp();
     }
+    if (lane < NV) {
+#pragma unroll
+        for (int j = 0; j < NV; j++) if (j <= i) s.M[i][j] = row[j];
+        s.invd[i] = myinv;
+    }
+    __syncwarp();
 }
 
 // x <- M^-1 x with the factor in s.M (every lane solves its own right-hand side; reads of L are warp-broadcasts)
@@ -592,22 +601,40 @@ __device__ __noinline__ void substep(WS &s, const ModelDev &m, const EnvArgs &A,
     __syncwarp();
     // ---- projected Gauss-Seidel in constraint space.  Row r is owned by lane r; every lane evaluates the row update from the
     // owner's (w, lambda) obtained with two independent shuffles, so the multiplier change d is warp-uniform without a third one.
+    // Rows are swept contact by contact (normal, then the two friction rows bounded by mu * lambda_n), then the joint limits.
     float lam = 0.f;
+    const float *Ac = &s.As[0][lane];
 #pragma unroll 1
     for (int it = 0; it < cfg.solver_iters; it++) {
-        float lam_n = 0.f;   // multiplier of the current contact's normal row (friction pyramid bound)
+        int r = 0;
 #pragma unroll 1
-        for (int r = 0; r < nrow; r++) {
+        for (int c = 0; c < nc; c++) {
+            float lim;
+            {
+                const float wr = __shfl_sync(FULL, wv, r), l0 = __shfl_sync(FULL, lam, r);
+                const float2 rc = *reinterpret_cast<const float2 *>(s.rowc[r]);
+                const float ln = fmaxf(l0 - (wr - rc.y) * rc.x, 0.f);
+                if (lane == r) lam = ln;
+                wv += Ac[r * 32] * (ln - l0);
+                lim = mu * ln;
+                r++;
+            }
+#pragma unroll
+            for (int k = 0; k < 2; k++, r++) {
+                const float wr = __shfl_sync(FULL, wv, r), l0 = __shfl_sync(FULL, lam, r);
+                const float2 rc = *reinterpret_cast<const float2 *>(s.rowc[r]);
+                const float ln = fminf(fmaxf(l0 - (wr - rc.y) * rc.x, -lim), lim);
+                if (lane == r) lam = ln;
+                wv += Ac[r * 32] * (ln - l0);
+            }
+        }
+#pragma unroll 1
+        for (; r < nrow; r++) {
             const float wr = __shfl_sync(FULL, wv, r), l0 = __shfl_sync(FULL, lam, r);
             const float2 rc = *reinterpret_cast<const float2 *>(s.rowc[r]);
-            float ln = l0 - (wr - rc.y) * rc.x;
-            const bool fric = r < 3 * nc && (r % 3) != 0;
-            const float lim = mu * lam_n;
-            ln = fric ? fminf(fmaxf(ln, -lim), lim) : fmaxf(ln, 0.f);
-            if (!fric) lam_n = ln;
-            const float d = ln - l0;
+            const float ln = fmaxf(l0 - (wr - rc.y) * rc.x, 0.f);
             if (lane == r) lam = ln;
-            wv += s.As[r][lane] * d;
+            wv += Ac[r * 32] * (ln - l0);
         }
     }
     // ---- u = u* + sum_r Y_r lam_r (lane i < NV owns component i)

@@ -45,7 +45,7 @@ constexpr int MAXP = 4;                                 // problems per grouped 
 
 // profiling stamps of CTA 0 (ns, %globaltimer): [0] entry, [1] setup done, [2] first TMA issued, [3] first stage landed,
 // [4] last MMA committed, [5] first accumulator complete (epilogue starts), [6] epilogue of the last tile done
-__device__ unsigned long long g_stamps[8];
+__device__ unsigned long long g_stamps[16];
 __device__ __forceinline__ void stamp(int i) {
     if (blockIdx.x == 0) {
         unsigned long long t;
@@ -156,8 +156,13 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo, uint
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46) |
            ((uint64_t)layout_type << 61);
 }
-// ELU on the tensor-core path: ex2.approx based exp; abs error ~1e-7, far below the TF32 operand rounding (2^-11 relative)
-__device__ __forceinline__ float elu_f(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
+// ELU on the tensor-core path: branch-free ex2.approx.ftz (no denormal fix-up code, no predicate chains); abs error ~1e-7, far
+// below the TF32 operand rounding (2^-11 relative).  For x > 0 the (possibly infinite) exponential is discarded by the select.
+__device__ __forceinline__ float elu_f(float x) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
+    return x > 0.f ? x : e - 1.f;
+}
 
 __host__ __device__ constexpr uint32_t tile_bytes(int rows) { return (uint32_t)rows * 128u; }   // rows x 32 fp32, either major
 
@@ -299,14 +304,25 @@ __global__ void __launch_bounds__(NTHREADS_CTA, 1) gemm_tf32_kernel(const __grid
                     }
                 }
                 __syncwarp();
+                float4 qb[NCH][8];   // EPI 0/1: the tile's bias slice, fetched while the accumulator is still being produced
+                if (EPI == 0 || EPI == 1) {
+#pragma unroll
+                    for (int ch = 0; ch < NCH; ch++)
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            const int nn = ncol0 + ch * 32 + 4 * i;
+                            qb[ch][i] = nn < g.N ? __ldg(reinterpret_cast<const float4 *>(g.bias + nn)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                }
                 mbar_wait(smem_u32(&acc_full[buf]), (ti >> 1) & 1);
                 tc_fence_after();
                 if (ti == 0 && tid == 0) stamp(5);
-#pragma unroll 1
+#pragma unroll
                 for (int ch = 0; ch < NCH; ch++) {
                     float v[32];
                     const int n = ncol0 + ch * 32;
                     tc_ld32(tmem + ((uint32_t)(quad * 32) << 16) + buf * (uint32_t)BN + (uint32_t)(chalf * (BN / 2) + ch * 32), v);
+                    if (ti == 0 && tid == 0 && ch == 0) stamp(8);
                     if (ch == NCH - 1) {   // this warp's last TMEM read of the accumulator: hand it back to the MMA warp
                         tc_fence_before();
                         __syncwarp();
@@ -314,31 +330,44 @@ __global__ void __launch_bounds__(NTHREADS_CTA, 1) gemm_tf32_kernel(const __grid
                     }
                     const uint32_t box = stg0 + ch * 4096u + rowoff;
                     if (EPI == 2) mbar_wait(smem_u32(&aux_bar[warp][ch]), ti & 1);
+                    // pass 1: all loads of the chunk (bias from global / activation from the staging box) are issued back to back;
+                    // interleaving them with the volatile shared stores below would serialise one memory latency per float4
+                    float4 q[8];
+                    if (EPI == 0 || EPI == 1) {
+#pragma unroll
+                        for (int i = 0; i < 8; i++) q[i] = qb[ch][i];
+                    } else if (EPI == 2) {
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            const uint32_t addr = box + (((uint32_t)i ^ sw) << 4);
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q[i].x), "=f"(q[i].y), "=f"(q[i].z), "=f"(q[i].w) : "r"(addr));
+                        }
+                    }
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
                         const uint32_t addr = box + ((((uint32_t)i >> 2) ^ sw) << 4);
                         float4 x = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
                         if (EPI == 0 || EPI == 1) {
-                            if (n + i < g.N) {
-                                const float4 bb = __ldg(reinterpret_cast<const float4 *>(g.bias + n + i));
-                                x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
-                            }
+                            const float4 bb = q[i >> 2];
+                            x.x += bb.x; x.y += bb.y; x.z += bb.z; x.w += bb.w;
                             if (EPI == 1) { x.x = elu_f(x.x); x.y = elu_f(x.y); x.z = elu_f(x.z); x.w = elu_f(x.w); }
                         } else if (EPI == 2) {
-                            float4 h;
-                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(h.x), "=f"(h.y), "=f"(h.z), "=f"(h.w) : "r"(addr));
+                            const float4 h = q[i >> 2];
                             x.x *= h.x > 0.f ? 1.f : h.x + 1.f; x.y *= h.y > 0.f ? 1.f : h.y + 1.f;     // out-of-bounds box elements were zero-filled:
                             x.z *= h.z > 0.f ? 1.f : h.z + 1.f; x.w *= h.w > 0.f ? 1.f : h.w + 1.f;     // the accumulator is zero there too (operands zero-filled)
                             v[i] = x.x; v[i + 1] = x.y; v[i + 2] = x.z; v[i + 3] = x.w;
                         }
                         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w) : "memory");
                     }
+                    if (ti == 0 && tid == 0 && ch == 0) stamp(9);
                     fence_proxy_async();
                     __syncwarp();
+                    if (ti == 0 && tid == 0 && ch == 0) stamp(10);
                     if (lane == 0) {
                         if (EPI == 3) tma_reduce_add_2d(&maps.c[T.p], n, mrow0, stg0 + ch * 4096u);
                         else tma_store_2d(&maps.c[T.p], n, mrow0, stg0 + ch * 4096u);
                         tma_commit();
+                        if (ti == 0 && tid == 0 && ch == 0) stamp(11);
                     }
                     if (EPI == 2 && g.colsum != nullptr) {
                         warp_colsum<32>(v, lane);
@@ -346,6 +375,7 @@ __global__ void __launch_bounds__(NTHREADS_CTA, 1) gemm_tf32_kernel(const __grid
                     }
                 }
             }
+            if (ti >= 1 && tid == 0) stamp(12);
             if (lane == 0) tma_wait_read0();
         }
         if (tid == 0) stamp(6);

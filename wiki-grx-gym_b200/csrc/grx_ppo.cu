@@ -366,9 +366,22 @@ __global__ void __launch_bounds__(256) gather_kernel(const GatherArgs g) {
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
     if ((g.P & 3) == 0) {   // critic rows are 16-byte aligned in the storage and in the staging buffer: float4 copies
         const int P4 = g.P >> 2, L4 = g.Ppad >> 2;
-        for (size_t e = tid; e < (size_t)g.B * P4; e += nth) {
-            const int r = (int)(e / P4), c = (int)(e % P4);
-            reinterpret_cast<float4 *>(g.xc)[(size_t)r * L4 + c] = __ldg(reinterpret_cast<const float4 *>(g.s_cobs) + (size_t)idx[r] * P4 + c);
+        const size_t tot = (size_t)g.B * P4;
+        for (size_t e0 = tid; e0 < tot; e0 += 4 * nth) {   // 4 independent row fetches in flight per thread
+            float4 v[4];
+            size_t d[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const size_t e = e0 + u * nth;
+                if (e < tot) {
+                    const int r = (int)(e / P4), c = (int)(e % P4);
+                    v[u] = __ldg(reinterpret_cast<const float4 *>(g.s_cobs) + (size_t)idx[r] * P4 + c);
+                    d[u] = (size_t)r * L4 + c;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (e0 + u * nth < tot) reinterpret_cast<float4 *>(g.xc)[d[u]] = v[u];
         }
     } else {
         for (size_t e = tid; e < (size_t)g.B * g.P; e += nth) {
@@ -496,6 +509,7 @@ struct HeadsArgs {
 // gradient accumulators live in registers.  Lane j < NA additionally owns action j (its mu_j, log-prob / KL term, d mu_j, grad std_j).
 template <int NA>
 __global__ void __launch_bounds__(HEADS_THREADS, 1) ppo_heads_kernel(const HeadsArgs a) {
+    static_assert(NA < 16, "the head butterfly reduces 16 products: NA actions + the value");
     constexpr int H = HEADS_H;
     constexpr int NACC = NA * H + 3 * H + 2 * NA + 8;   // gW3a | gW3c | gb2a | gb2c | gb3a[NA] | gstd[NA] | gb3c, kl, cnt, surr, vl
     __shared__ float acc[NACC];
@@ -513,24 +527,42 @@ __global__ void __launch_bounds__(HEADS_THREADS, 1) ppo_heads_kernel(const Heads
     const float inv2s2 = 1.f / (2.f * sg * sg), logsg = logf(sg);
     float gba = 0.f, gsd = 0.f, gbc = 0.f, kl_s = 0.f, surr_s = 0.f, vl_s = 0.f, cnt_s = 0.f;
     const float invB = 1.0f / (float)a.B;
-    for (int r = blockIdx.x * wpb + warp; r < a.B; r += nwarps) {
-        const float4 ha = *reinterpret_cast<const float4 *>(a.h3a + (size_t)r * H + c0);
-        const float4 hc = *reinterpret_cast<const float4 *>(a.h3c + (size_t)r * H + c0);
-        float ac = 0.f, om = 0.f, os = 1.f;
-        if (own) { ac = a.act[(size_t)r * NA + lane]; om = a.old_mu[(size_t)r * NA + lane]; os = a.old_sigma[(size_t)r * NA + lane]; }
-        const float A_ = a.adv[r], olp = a.old_logp[r], R = a.ret[r], V0 = a.old_v[r];
+    // software-pipelined over rows: the loads of the warp's next row are issued before the arithmetic of the current one
+    int r = blockIdx.x * wpb + warp;
+    float4 n_ha = make_float4(0.f, 0.f, 0.f, 0.f), n_hc = n_ha;
+    float n_ac = 0.f, n_om = 0.f, n_os = 1.f, n_A = 0.f, n_olp = 0.f, n_R = 0.f, n_V0 = 0.f;
+    auto fetch = [&](int rr) {
+        n_ha = *reinterpret_cast<const float4 *>(a.h3a + (size_t)rr * H + c0);
+        n_hc = *reinterpret_cast<const float4 *>(a.h3c + (size_t)rr * H + c0);
+        if (own) { n_ac = a.act[(size_t)rr * NA + lane]; n_om = a.old_mu[(size_t)rr * NA + lane]; n_os = a.old_sigma[(size_t)rr * NA + lane]; }
+        n_A = a.adv[rr]; n_olp = a.old_logp[rr]; n_R = a.ret[rr]; n_V0 = a.old_v[rr];
+    };
+    if (r < a.B) fetch(r);
+    for (; r < a.B; r += nwarps) {
+        const float4 ha = n_ha, hc = n_hc;
+        const float ac = n_ac, om = n_om, os = n_os, A_ = n_A, olp = n_olp, R = n_R, V0 = n_V0;
+        if (r + nwarps < a.B) fetch(r + nwarps);
         // ---- heads: mu_j = W3a[j] . h3a + b, v = W3c . h3c + b   (butterfly sums; lane j keeps mu_j)
-        float v = hc.x * wc.x + hc.y * wc.y + hc.z * wc.z + hc.w * wc.w;
-        float mu = 0.f;
+        // 16 partial dot products per lane (10 actions, the value, padding) reduced by a halving butterfly: 16 shuffles instead of 55;
+        // afterwards lane l (and its mirror l + 16) holds the complete sum of product l, i.e. lane j already owns mu_j
+        float t[16];
 #pragma unroll
-        for (int j = 0; j < NA; j++) {
-            float t = ha.x * wa[j].x + ha.y * wa[j].y + ha.z * wa[j].z + ha.w * wa[j].w;
+        for (int j = 0; j < 16; j++) t[j] = 0.f;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(FULL, t, o);
-            if (lane == j) mu = t;
+        for (int j = 0; j < NA; j++) t[j] = ha.x * wa[j].x + ha.y * wa[j].y + ha.z * wa[j].z + ha.w * wa[j].w;
+        t[NA] = hc.x * wc.x + hc.y * wc.y + hc.z * wc.z + hc.w * wc.w;
+#pragma unroll
+        for (int w = 8, bit = 8; w >= 1; w >>= 1, bit >>= 1) {
+            const bool up = (lane & bit) != 0;
+#pragma unroll
+            for (int i = 0; i < w; i++) {
+                const float send = up ? t[i] : t[i + w], keep = up ? t[i + w] : t[i];
+                t[i] = keep + __shfl_xor_sync(FULL, send, bit);
+            }
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+        t[0] += __shfl_xor_sync(FULL, t[0], 16);
+        float mu = own ? t[0] : 0.f;
+        float v = __shfl_sync(FULL, t[0], NA);
         v += bc;
         mu += ba;
         // ---- losses (ppo.py:246-295), same arithmetic as ppo_loss_kernel; lane j holds the terms of action j
@@ -615,7 +647,10 @@ struct Ctl {            // device control block
     int comm_epoch;     // NVLink all-reduce epochs completed (flags in peer memory are monotonic epoch numbers)
     int comm_error;     // set when a peer did not show up within the spin budget (results of that step are invalid)
     unsigned comm_arrive;   // scratch: blocks of allreduce_kernel that finished their slice
-    int pad_;
+    unsigned apply_arrive;  // scratch: grid barrier of apply_kernel (blocks that contributed their partial gradient norm)
+    unsigned apply_done;    // scratch: blocks of apply_kernel that have read the barrier results (the last one resets the scratch)
+    int pad_[3];
+    double pow1, pow2;      // beta1^step, beta2^step as running products (fp64 pow is a ~10 us dependent chain on this part)
 };
 
 // =========================================================================================================
@@ -626,7 +661,7 @@ struct Ctl {            // device control block
 //      in rank order (every element is summed by exactly one rank, so all ranks hold bit-identical results), and STORES the
 //      sum into every rank's gsum (push all-gather); the squared norm of the slice is reduced on the way;
 //   3. the last block to finish publishes the slice's sum of squares and done[rank] = epoch to every peer.
-// prep_apply_kernel then waits for all done[] flags, adds the W partial norms in rank order and proceeds exactly as on one GPU.
+// apply_kernel then waits for all done[] flags, adds the W partial norms in rank order and proceeds exactly as on one GPU.
 // No NCCL call, no host involvement: the kernel sits in the same CUDA graph as the rest of the minibatch.
 // =========================================================================================================
 constexpr int MAXW = 8;
@@ -693,79 +728,112 @@ __global__ void __launch_bounds__(256) allreduce_kernel(const CommDev c, int n4,
     }
     if (last && threadIdx.x == 0) ctl->comm_arrive = 0;
 }
-__global__ void gradnorm_kernel(const float *g, int n, Ctl *ctl) {
-    float s = 0.f;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += g[i] * g[i];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
-    __shared__ float red[32];
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        float x = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
-        if (threadIdx.x == 0) atomicAdd(&ctl->sumsq, (double)x);
-    }
-}
 struct PrepArgs {
     Ctl *ctl;
     const float *tail, *std;
     int A, adaptive, world_size;
     float desired_kl, lr_min, lr_max, max_grad_norm, vcoef, ecoef;
-    int *comm_flags;   // this rank's flag block when the NVLink all-reduce is active, else NULL
+    int *comm_flags;   // this rank's flag block when the NVLink all-reduce is active (norm partials come from the peers), else NULL
     int comm_rank;
 };
-__global__ void prep_apply_kernel(const PrepArgs a) {
-    if (a.comm_flags != nullptr) {   // wait until every rank has pushed its slice of the summed gradient (and its partial norm)
-        if (threadIdx.x < a.world_size) wait_flag(a.comm_flags + FLAG_DONE + threadIdx.x, a.ctl->comm_epoch + 1, a.ctl);
-        __syncwarp();
-    }
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// ONE kernel for the apply step (ppo.py:262-268, 297-305): gradient norm -> [grid barrier] -> adaptive LR from the mean KL,
+// NaN skip, clip coefficient, Adam bias corrections (evaluated identically by every block from the same inputs) -> Adam on the
+// block's slice; block 0 persists the control block.  The grid (<= one block per SM) is co-resident, so the barrier is an
+// arrival counter in the control block; the last block to have read the results resets the scratch for the next launch.
+// torch.optim.Adam semantics (ppo.py:81; betas 0.9/0.999, eps 1e-8, no weight decay).
+__global__ void __launch_bounds__(1024) apply_kernel(const PrepArgs a, float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m,
+                                                      float *__restrict__ v, int n) {
     Ctl &c = *a.ctl;
-    if (a.comm_flags != nullptr) {
-        double t = 0.0;
-        for (int r = 0; r < a.world_size; r++) t += reinterpret_cast<const volatile double *>(a.comm_flags + FLAG_SUMSQ)[r];   // rank order: identical on every rank
-        c.sumsq = t;
-        c.comm_epoch += 1;
+    __shared__ float red[32];
+    __shared__ double s_total;
+    if (threadIdx.x == 0) tc::stamp(0);
+    const float old_lr = c.lr;
+    const int old_step = c.step;
+    const double old_pow1 = c.pow1, old_pow2 = c.pow2;
+    float ent = 0.f;   // read std BEFORE the grid barrier: after it, other blocks' Adam may already be updating the parameters (std = params[0..A))
+    for (int j = 0; j < a.A; j++) ent += 0.5f + 0.5f * 1.8378770664093453f + logf(a.std[j]);   // ACM:160-163
+    if (a.comm_flags == nullptr) {
+        float s = 0.f;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (n >> 2); i += gridDim.x * blockDim.x) {   // n % 4 == 0, 16-byte aligned
+            const float4 x = reinterpret_cast<const float4 *>(g)[i];
+            s += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    } else if (threadIdx.x < a.world_size) {   // wait until every rank has pushed its slice of the summed gradient (and its partial norm)
+        wait_flag(a.comm_flags + FLAG_DONE + threadIdx.x, c.comm_epoch + 1, a.ctl);
     }
+    __syncthreads();
+    if (threadIdx.x == 0) tc::stamp(1);
+    if (threadIdx.x == 0) {
+        if (a.comm_flags == nullptr) {
+            float x = 0.f;
+            for (int k = 0; k < (int)(blockDim.x >> 5); k++) x += red[k];
+            atomicAdd(&c.sumsq, (double)x);
+        }
+        __threadfence();
+        atomicAdd(&c.apply_arrive, 1u);
+        while (*reinterpret_cast<volatile unsigned *>(&c.apply_arrive) < gridDim.x) __nanosleep(32);
+        __threadfence();
+        if (a.comm_flags == nullptr) s_total = *reinterpret_cast<volatile double *>(&c.sumsq);
+        else {
+            double t = 0.0;
+            for (int r = 0; r < a.world_size; r++) t += reinterpret_cast<const volatile double *>(a.comm_flags + FLAG_SUMSQ)[r];   // rank order: identical on every rank
+            s_total = t;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) tc::stamp(2);
+    // ---- control scalars, identical in every block
     const float cnt = a.tail[1];
     const float kl_mean = a.tail[0] / cnt;
+    float lr = old_lr;
     if (a.adaptive) {                                                                  // ppo.py:262-268, 207-213
-        if (kl_mean > a.desired_kl * 2.0f) c.lr = fmaxf(a.lr_min, c.lr / 1.5f);
-        else if (kl_mean < a.desired_kl / 2.0f && kl_mean > 0.0f) c.lr = fminf(a.lr_max, c.lr * 1.5f);
+        if (kl_mean > a.desired_kl * 2.0f) lr = fmaxf(a.lr_min, lr / 1.5f);
+        else if (kl_mean < a.desired_kl / 2.0f && kl_mean > 0.0f) lr = fminf(a.lr_max, lr * 1.5f);
     }
-    float ent = 0.f;
-    for (int j = 0; j < a.A; j++) ent += 0.5f + 0.5f * 1.8378770664093453f + logf(a.std[j]);   // ACM:160-163
     const float surr = a.tail[2] / cnt, vl = a.tail[3] / cnt;
     const float loss = surr + a.vcoef * vl - a.ecoef * ent;
-    c.kl_mean = kl_mean; c.loss = loss; c.value_loss = vl; c.surrogate_loss = surr;
-    c.skip = isnan(loss) ? 1 : 0;
+    const bool skip = isnan(loss);
     const float W = (float)a.world_size;
-    const float total = (float)sqrt(c.sumsq) / W;                                      // grads in reduce_buf are sums over ranks
-    c.grad_norm = total;
-    c.coef = fminf(a.max_grad_norm / (total + 1e-6f), 1.0f) / W;                       // clip_grad_norm_ (ppo.py:304)
-    c.sumsq = 0.0;
-    c.mb_counter += 1;
-    if (!c.skip) {
-        c.step += 1;
-        c.bc1 = (float)(1.0 - pow(0.9, (double)c.step));
-        c.bc2s = (float)sqrt(1.0 - pow(0.999, (double)c.step));
-        c.sum_value_loss += vl; c.sum_surrogate_loss += surr;
+    const float total = (float)sqrt(s_total) / W;                                      // grads are sums over ranks
+    const float coef = fminf(a.max_grad_norm / (total + 1e-6f), 1.0f) / W;             // clip_grad_norm_ (ppo.py:304)
+    const int step = old_step + (skip ? 0 : 1);
+    const double pow1 = skip ? old_pow1 : old_pow1 * 0.9, pow2 = skip ? old_pow2 : old_pow2 * 0.999;
+    const float bc1 = (float)(1.0 - pow1), bc2s = sqrtf((float)(1.0 - pow2));
+    if (threadIdx.x == 0) tc::stamp(3);
+    if (!skip) {
+        const float step_size = lr / bc1;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (n >> 2); i += gridDim.x * blockDim.x) {
+            const float4 g4 = reinterpret_cast<const float4 *>(g)[i];
+            float4 m4 = reinterpret_cast<float4 *>(m)[i], v4 = reinterpret_cast<float4 *>(v)[i], p4 = reinterpret_cast<float4 *>(p)[i];
+            const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
+            float *mm = &m4.x, *vv = &v4.x, *pp = &p4.x;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float gi = gg[k] * coef;
+                const float mi = 0.9f * mm[k] + (1.0f - 0.9f) * gi;
+                const float vi = 0.999f * vv[k] + (1.0f - 0.999f) * gi * gi;
+                mm[k] = mi; vv[k] = vi;
+                const float denom = sqrtf(vi) / bc2s + 1e-8f;
+                pp[k] -= step_size * (mi / denom);
+            }
+            reinterpret_cast<float4 *>(m)[i] = m4; reinterpret_cast<float4 *>(v)[i] = v4; reinterpret_cast<float4 *>(p)[i] = p4;
+        }
     }
-}
-// torch.optim.Adam (ppo.py:81; betas 0.9/0.999, eps 1e-8, no weight decay)
-__global__ void adam_kernel(float *p, const float *g, float *m, float *v, int n, const Ctl *ctl) {
-    if (ctl->skip) return;
-    const float lr = ctl->lr, coef = ctl->coef, bc1 = ctl->bc1, bc2s = ctl->bc2s;
-    const float step_size = lr / bc1;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float gi = g[i] * coef;
-        const float mi = 0.9f * m[i] + (1.0f - 0.9f) * gi;
-        const float vi = 0.999f * v[i] + (1.0f - 0.999f) * gi * gi;
-        m[i] = mi; v[i] = vi;
-        const float denom = sqrtf(vi) / bc2s + 1e-8f;
-        p[i] -= step_size * (mi / denom);
+    if (threadIdx.x == 0) tc::stamp(4);
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned done = atomicAdd(&c.apply_done, 1u);
+        if (done == gridDim.x - 1) {   // everybody has read the barrier results and the old control values: persist + reset scratch
+            c.lr = lr; c.coef = coef; c.skip = skip ? 1 : 0; c.step = step; c.bc1 = bc1; c.bc2s = bc2s; c.pow1 = pow1; c.pow2 = pow2;
+            c.kl_mean = kl_mean; c.loss = loss; c.value_loss = vl; c.surrogate_loss = surr; c.grad_norm = total;
+            c.mb_counter += 1;
+            if (!skip) { c.sum_value_loss += vl; c.sum_surrogate_loss += surr; }
+            if (a.comm_flags != nullptr) c.comm_epoch += 1;
+            c.sumsq = 0.0; c.apply_arrive = 0u; c.apply_done = 0u;
+        }
     }
 }
 
@@ -813,6 +881,7 @@ struct grx_ppo {
     float *gsum = nullptr;
     int *flags = nullptr;
     bool comm_open = false;
+    int apply_grid = 148;   // co-resident grid of apply_kernel (<= SM count)
     CommDev comm;
     std::vector<void *> peer_maps;
 };
@@ -882,7 +951,12 @@ extern "C" int grx_ppo_create(const grx_ppo_cfg *cfg, int32_t device, grx_ppo **
         CK(cudaMemcpy(p->params, s.data(), p->A * 4, cudaMemcpyHostToDevice));
         Ctl c; memset(&c, 0, sizeof(c));
         c.lr = cfg->learning_rate;
+        c.pow1 = 1.0; c.pow2 = 1.0;
         CK(cudaMemcpy(p->ctl, &c, sizeof(c), cudaMemcpyHostToDevice));
+    }
+    {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) p->apply_grid = sms;
     }
     if (const char *e = getenv("GRX_PPO_TIMING")) p->timing = atoi(e) != 0;
     if (p->timing) for (int i = 0; i < 9; i++) CK(cudaEventCreate(&p->tev[i]));
@@ -1110,15 +1184,13 @@ static int minibatch_apply(grx_ppo *p, cudaStream_t st, bool use_comm) {
         allreduce_kernel<<<64, 256, 0, st>>>(p->comm, (int)((p->nparam + TAIL) / 4), (int)(p->nparam / 4), p->ctl);
         gsrc = p->gsum;
     } else {
-        gradnorm_kernel<<<148, 256, 0, st>>>(p->reduce_buf, (int)p->nparam, p->ctl);
     }
     PrepArgs a; memset(&a, 0, sizeof(a));
     a.comm_flags = use_comm ? p->flags : nullptr; a.comm_rank = p->comm.rank;
     a.ctl = p->ctl; a.tail = gsrc + p->nparam; a.std = p->params; a.A = p->A; a.adaptive = p->cfg.adaptive_schedule;
     a.world_size = p->cfg.world_size; a.desired_kl = p->cfg.desired_kl; a.lr_min = p->cfg.learning_rate_min; a.lr_max = p->cfg.learning_rate_max;
     a.max_grad_norm = p->cfg.max_grad_norm; a.vcoef = p->cfg.value_loss_coef; a.ecoef = p->cfg.entropy_coef;
-    prep_apply_kernel<<<1, 32, 0, st>>>(a);
-    adam_kernel<<<296, 256, 0, st>>>(p->params, gsrc, p->adam_m, p->adam_v, (int)p->nparam, p->ctl);
+    apply_kernel<<<p->apply_grid, 1024, 0, st>>>(a, p->params, gsrc, p->adam_m, p->adam_v, (int)p->nparam);
     CK(cudaGetLastError());
     if (p->timing) {
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -1231,10 +1303,10 @@ extern "C" int grx_ppo_act_inference(grx_ppo *p, const float *d_obs, int32_t n, 
 }
 
 // Profiling: %globaltimer stamps (ns) of CTA 0 of the most recent tensor-core GEMM launch (see tc::g_stamps).  Synchronises.
-extern "C" int grx_gemm_debug_stamps(uint64_t *out8) {
+extern "C" int grx_gemm_debug_stamps(uint64_t *out8) {   /* 16 values */
     if (!out8) return grx_set_error(GRX_E_INVALID, "grx_gemm_debug_stamps: null argument");
     CK(cudaDeviceSynchronize());
-    CK(cudaMemcpyFromSymbol(out8, tc::g_stamps, 8 * sizeof(uint64_t)));
+    CK(cudaMemcpyFromSymbol(out8, tc::g_stamps, 16 * sizeof(uint64_t)));
     return GRX_OK;
 }
 

@@ -342,6 +342,7 @@ class PPO:
                 step = int(float(sd["state"][i]["step"]))
         if sd["state"]:
             self.ctl[3:4].view(torch.int32).fill_(step)
+            self.ctl[24:28].view(torch.float64).copy_(torch.tensor([0.9 ** step, 0.999 ** step], dtype=torch.float64))   # running beta^step
         self.learning_rate = sd["param_groups"][0]["lr"]
 
 
