@@ -25,6 +25,7 @@ N_PER_GPU, T_STEPS = 4096, 64
 METRIC, UNIT = "env-steps/sec GR1T1 rough-terrain PPO @4096 envs/GPU", "env-steps/s"
 ENV_BYTES_PER_STEP = 1794          # 530 B read + 1264 B written per env-step by the fused env kernel
 FWD_FLOP = 870144                  # per transition, actor + critic forward
+ENV_DRAM_TRAFFIC = 3.99e6          # dram__bytes_read.sum + dram__bytes_write.sum per env_step_kernel launch (profiles/r1_env_ncu_summary.txt)
 
 
 def peaks():
@@ -275,20 +276,24 @@ def run_ours(args):
         ppo_tf = ppo_flops / (learn * 1e-3) / 1e12
         dominant_env = T_STEPS * env_ms >= learn
         roof_env = {"kernel": "env_step_kernel", "bound": "hbm", "achieved": env_achieved, "peak": hbm, "unit": "GB/s", "frac": env_achieved / hbm,
-                    "traffic": None, "peak_source": which, "us_per_launch": env_ms * 1e3,
-                    "note": "1794 algorithmic B per env-step x 4096 robots per launch; the kernel is issue/latency-bound (10 substeps of "
-                            "articulated dynamics per launch), see profiles/"}
+                    "traffic": ENV_DRAM_TRAFFIC, "peak_source": which, "us_per_launch": env_ms * 1e3,
+                    "note": "1794 algorithmic B per env-step x 4096 robots per launch = 7.35 MB; measured DRAM traffic 4.0 MB per launch "
+                            "(ncu --set full, profiles/): the records stay in L2 between steps.  The kernel is issue/latency-bound (10 substeps "
+                            "of articulated dynamics per launch, ~55k warp-instructions per env-step), not bandwidth-bound"}
         roof_ppo = {"kernel": "PPO update (fwd+bwd dense layers, 200 minibatches)", "bound": "tensor", "achieved": ppo_tf, "peak": tf_sus,
                     "unit": "TFLOP/s", "frac": ppo_tf / tf_sus, "traffic": None, "peak_source": which,
                     "note": "21.75 MFLOP per transition incl. rollout forward; measured over compute_returns + update"}
         cb = cpu_port_rate(quick=True) if world == 1 else None
-        launches_per_iter = T_STEPS * (9 + 1 + 1) + 8 + 200 * 27
+        # our kernels per iteration: per policy step 3 grouped tcgen05 layers + 2 SIMT output heads + act/store + env + storage = 8;
+        # compute_returns 6; per minibatch gather + 3 forward + heads + 2 dX + 2 grouped dW + apply = 10
+        launches_per_iter = T_STEPS * 8 + 6 + 200 * 10
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
                 "config": {"workload": "GR1T1 lower-limb (registered task), rough heightfield 10x20 tiles + curriculum + domain randomisation, "
                                        f"{N_PER_GPU} envs/GPU x {T_STEPS} steps/iteration, PPO 8 epochs x 25 minibatches of 10485, live policy actions",
-                           "envs_total": n_total, "parallelism": f"dp{world} (env shards by index, one NCCL all-reduce of 436893 floats per minibatch)",
+                           "envs_total": n_total, "parallelism": f"dp{world} (env shards by index; per minibatch one all-reduce of 436893 floats over NVLink peer memory, "
+                                                          "fused with the gradient-norm reduction inside the update's CUDA graph)",
                            "l2": "per-iteration working set (rollout storage 252 MB/GPU) exceeds the 126 MB L2; no explicit flush",
                            "collection_ms": coll, "learn_ms": learn},
                 "roofline": roof_env if dominant_env else roof_ppo, "roofline_env": roof_env, "roofline_ppo": roof_ppo,

@@ -122,32 +122,36 @@ def test_mass_matrix_and_bias_match_fp64_oracle(robot):
         np.testing.assert_allclose(h, ho, rtol=2e-4, atol=2e-3)
 
 
-def test_full_size_properties():
-    """BASELINE config #2 shape: 4096 robots on the rough heightfield, fast-mode (in-kernel Philox) draws."""
+@pytest.mark.parametrize("robot,N,mesh", [("GR1T1", 4096, "heightfield"),     # BASELINE config #2
+                                          ("GR1T2", 8192, "heightfield"),     # config #3: GR1T2 + full domain randomisation
+                                          ("GR1T1", 4096, "trimesh")])        # config #5: one rank's share of the trimesh + curriculum job
+def test_full_size_properties(robot, N, mesh):
+    """BASELINE config shapes at full per-GPU size: rough terrain, curriculum, domain randomisation, fast-mode (in-kernel Philox)
+    draws; size-independent properties instead of an oracle run."""
     from grx_b200.config import make_cfg
     from grx_b200.env import GRXVecEnv
-    cfg = make_cfg("GR1T1", 4096, "heightfield")
+    cfg = make_cfg(robot, N, mesh)
     env = GRXVecEnv(cfg, sim_device="cuda:0")
     obs, pri = env.reset()
-    assert obs.shape == (4096, 39) and pri.shape == (4096, 168)
+    assert obs.shape == (N, 39) and pri.shape == (N, 168)
     g = torch.Generator(device="cuda").manual_seed(0)
     n_reset, n_steps = 0, 150
     lvl0 = env.terrain_levels.clone()
     for _ in range(n_steps):
-        a = 0.3 * torch.randn(4096, 10, device="cuda", generator=g)
+        a = 0.3 * torch.randn(N, 10, device="cuda", generator=g)
         obs, pri, rew, reset, extras = env.step(a)
         n_reset += int(reset.sum())
     torch.cuda.synchronize()
     for t in (obs, pri, rew, env.root_states, env.dof_pos, env.dof_vel):
         assert torch.isfinite(t).all()
     assert obs.abs().max() <= 100.0 and pri.abs().max() <= 100.0                       # clip_observations
-    assert 0 < n_reset < 4096 * n_steps // 4                                           # random actions: robots fall, but not at once
+    assert 0 < n_reset < N * n_steps // 4                                           # random actions: robots fall, but not at once
     assert torch.allclose(pri[:, 3:9], obs[:, 3:9], atol=0.06)                         # obs = pri[:39] + bounded noise
     noise = (obs - pri[:, :39]).abs().max(0).values.cpu().numpy()
     bound = np.array([0] * 3 + [0.05] * 3 + [0.03] * 3 + [0.04] * 10 + [0.2] * 10 + [0] * 10) + 1e-6
     assert (noise <= bound).all() and noise[3:29].min() > 0.0
     q = env.root_states[:, 3:7]
-    assert torch.allclose(q.norm(dim=1), torch.ones(4096, device="cuda"), atol=1e-4)   # integrator keeps the quaternion unit
+    assert torch.allclose(q.norm(dim=1), torch.ones(N, device="cuda"), atol=1e-4)   # integrator keeps the quaternion unit
     lim_lo = torch.tensor(env.model["dof_lower"], device="cuda", dtype=torch.float32) - 0.05
     lim_hi = torch.tensor(env.model["dof_upper"], device="cuda", dtype=torch.float32) + 0.05
     inside = ((env.dof_pos >= lim_lo) & (env.dof_pos <= lim_hi)).all(1)

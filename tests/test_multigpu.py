@@ -30,7 +30,8 @@ def _ppo_worker(rank, world, port, comm, q):
     N, T = 256, 16
     torch.manual_seed(5)
     ac = ActorCriticMLP(39, 168, 10, **tc["policy"])
-    alg = PPO(ac, device=dev, world_size=world, **dict(tc["algorithm"], num_mini_batches=4, num_learning_epochs=2))
+    alg = PPO(ac, device=dev, world_size=world, **dict(tc["algorithm"], num_mini_batches=4, num_learning_epochs=2,
+                                                         schedule="fixed"))   # fixed LR: an adaptive-KL threshold flip would make the two runs bifurcate
     alg.init_storage(N, T)
     g = torch.Generator().manual_seed(100 + rank)          # different data on every rank
     for s in range(T):
@@ -77,3 +78,4 @@ def test_nvlink_allreduce_update_equals_nccl_update():
         assert d.max() < 2e-3 and d.mean() < 2e-2 * scale, (k, d.max(), d.mean(), scale)
     assert nv[0][4]["step"] == nc[0][4]["step"] == 8
     assert abs(nv[0][4]["lr"] - nc[0][4]["lr"]) < 1e-9
+    assert abs(nv[0][4]["kl"] - nc[0][4]["kl"]) < 1e-3 and abs(nv[0][4]["grad_norm"] - nc[0][4]["grad_norm"]) < 1e-2 * nc[0][4]["grad_norm"]
