@@ -210,3 +210,25 @@ def test_runner_learns_and_checkpoints(tmp_path):
     a = pol(env2.get_observations())
     assert a.shape == (256, 10) and torch.isfinite(a).all()
     assert "Perf/total_fps" in r.last_scalars and "Episode/rew_pose_offset" in r.last_scalars
+
+
+def test_reference_jit_export_path(tmp_path):
+    """play.py's export (legged_gym/utils/helpers.py:188-201: deepcopy(actor).to('cpu') -> torch.jit.script -> save) works on our
+    policy object and the scripted module reproduces the CUDA inference path."""
+    import copy
+    from grx_b200.ppo import PPO, ActorCriticMLP
+    tc = make_train_cfg()
+    torch.manual_seed(3)
+    ac = ActorCriticMLP(39, 168, 10, **tc["policy"])
+    alg = PPO(ac, device="cuda:0", **tc["algorithm"])
+    alg.init_storage(64, 8)
+    model = copy.deepcopy(ac.actor).to("cpu")
+    scripted = torch.jit.script(model)
+    path = str(tmp_path / "policy_jit.pt")
+    scripted.save(path)
+    loaded = torch.jit.load(path)
+    obs = torch.randn(64, 39)
+    ref = loaded(obs)
+    ours = ac.act_inference(obs.cuda()).cpu()
+    assert [k for k in model.state_dict()] == [f"model.{i}.{p}" for i in (0, 2, 4, 6) for p in ("weight", "bias")]
+    np.testing.assert_allclose(ours.numpy(), ref.detach().numpy(), rtol=0, atol=5e-3)   # TF32 tensor-core layers vs fp32 torch

@@ -28,7 +28,7 @@ namespace {
 constexpr int NB = 11, ND = 10, NV = 16, CH = 5, NLMAX = 40, NSMAX = 32, NF = 2, KC = 8, KLIM = 7;
 constexpr int YS = 20;   // row stride of WS::Y (floats): 16-byte aligned and conflict-free for per-lane float4 stores
 constexpr int NREW = 24, NHMAX = 128;
-constexpr int WARPS_PER_CTA = 4;
+constexpr int WARPS_PER_CTA = 16;   // one CTA per SM; its warps re-converge at every substep so the 4 warps of a scheduler share instruction-cache lines
 constexpr int ACC_RING = 256, ACC_W = 32;   // extras["episode"] accumulators: one 32-float slot per launch, ring of 256
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -56,7 +56,7 @@ struct ModelDev {
     int torso_body;
     unsigned long long term_mask;
     int ankle_dof[2];
-    int pad_;
+    int jrot_nonident;   // bit b set: joint frame rotation of body b is not the identity (GR1T1 / GR1T2: none) -> one 3x3 product per joint saved
 };
 
 struct TerrainDev {
@@ -258,7 +258,11 @@ __device__ __noinline__ void kinematics(WS &s, const ModelDev &m, int lane) {
             const int j = 1 + leg * CH + k;
             const float q = s.rec[R_DOFPOS + j - 1], qd = s.rec[R_DOFVEL + j - 1];
             float Rj[9], Rq[9], r[3], an[3], t1[3], t2[3], t3[3], t4[3];
-            m3m(R, m.jrot[j], Rj);
+            if ((m.jrot_nonident >> j) & 1) m3m(R, m.jrot[j], Rj);
+            else {
+#pragma unroll
+                for (int i = 0; i < 9; i++) Rj[i] = R[i];
+            }
             axang2mat(m.axis[j], q, Rq);
             m3v(R, m.jpos[j], r);
             m3m(Rj, Rq, R);
@@ -326,16 +330,30 @@ __device__ __forceinline__ void mass_and_bias(WS &s, const ModelDev &m, float gr
     }
     __syncwarp();
     if (lane <= ND) {
-        // lanes 0..9: composite of the chain suffix starting at joint body lane+1; lane 10: whole robot
+        // lanes 0..9: composite of the chain suffix starting at joint body lane+1; lane 10: whole robot = base body + the two
+        // leg composites (lanes 0 and CH), fetched by shuffles so that the summation loop runs CH trips instead of NB
         int first, last;
         if (lane < ND) { first = lane + 1; last = 1 + (lane / CH) * CH + CH - 1; }
-        else { first = 0; last = NB - 1; }
+        else { first = 0; last = 0; }
         float ci[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, cw[6] = {0, 0, 0, 0, 0, 0};
         for (int b = first; b <= last; b++) {
 #pragma unroll
             for (int k = 0; k < 10; k++) ci[k] += s.bi[b][k];
 #pragma unroll
             for (int k = 0; k < 6; k++) cw[k] += s.bw[b][k];
+        }
+        {
+            const unsigned msk = (1u << (ND + 1)) - 1u;   // the lanes inside this branch
+#pragma unroll
+            for (int k = 0; k < 10; k++) {
+                const float l1 = __shfl_sync(msk, ci[k], 0), l2 = __shfl_sync(msk, ci[k], CH);
+                if (lane == ND) ci[k] += l1 + l2;
+            }
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                const float l1 = __shfl_sync(msk, cw[k], 0), l2 = __shfl_sync(msk, cw[k], CH);
+                if (lane == ND) cw[k] += l1 + l2;
+            }
         }
         if (lane < ND) {
             const int j = lane + 1;
@@ -463,6 +481,10 @@ __device__ __forceinline__ void chol_solve(const WS &s, float *x) {
 // Constraint rows: 3 per contact (<= KC contacts) then <= KLIM joint-limit rows, one lane per row (<= 31); lane 31 solves the
 // unconstrained update.  The projected Gauss-Seidel sweep runs in constraint space on the Delassus matrix A = J M^-1 J^T
 // (same iterates as the velocity-space sweep of oracle/phys_impl.h): all loops are rolled to keep the instruction footprint small.
+__device__ __forceinline__ void cta_align(int nthreads) {   // phase alignment of the CTA's warps (instruction-cache locality); no data is shared
+    if (nthreads > 0) asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+}
+
 __device__ __noinline__ void substep(WS &s, const ModelDev &m, const EnvArgs &A, const grx_task_cfg &cfg, int lane) {
     const float dt = cfg.sim_dt;
     mass_and_bias(s, m, cfg.gravity, lane);
@@ -756,7 +778,7 @@ __device__ __forceinline__ void reset_env(WS &s, const ModelDev &m, const EnvArg
 }
 
 template <bool PHYS>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) env_step_kernel(const __grid_constant__ EnvArgs A,
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 1) env_step_kernel(const __grid_constant__ EnvArgs A,
                                                                          const __grid_constant__ grx_task_cfg cfg) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ModelDev &m = *reinterpret_cast<ModelDev *>(smem_raw);
@@ -804,7 +826,12 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) env_step_kernel(const _
     float torso_q[4] = {0, 0, 0, 1};
     if (PHYS) {
 #pragma unroll 1
+        // Re-converge the CTA's warps once per substep: the substep is ~60 KB of mostly straight-line code, and with every warp
+        // of a scheduler in a different place the instruction caches thrash (ncu: 28 % of warp samples `no_instructions`);
+        // aligned warps share the fetched lines (measured 536 -> 445 us per launch).  More barriers per substep cost more than they save.
+        const int cta_valid = min(WARPS_PER_CTA, A.N - (int)blockIdx.x * WARPS_PER_CTA) * 32;   // threads that did not exit above
         for (int deci = 0; deci <= cfg.decimation; deci++) {
+            cta_align(A.dbg_M == nullptr ? cta_valid : 0);
             kinematics(s, m, lane);
             if (deci > 0 && lane < NF) {   // foot statistics of the substep just integrated (FF:79-81)
                 const int l = m.foot_link[lane], b = m.foot_body[lane];
@@ -1237,6 +1264,12 @@ extern "C" int grx_env_create(const grx_model_desc *md, const grx_task_cfg *cfg,
     m.term_mask = 0;
     for (int t = 0; t < md->nterm; t++) m.term_mask |= 1ull << md->term_links[t];
     m.ankle_dof[0] = md->ankle_dofs[0]; m.ankle_dof[1] = md->ankle_dofs[1];
+    m.jrot_nonident = 0;
+    for (int b = 0; b < NB; b++) {
+        static const float I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        for (int k = 0; k < 9; k++)
+            if (m.jrot[b][k] != I3[k]) m.jrot_nonident |= 1 << b;
+    }
     const size_t N = num_envs;
 #define ALLOC(ptr, count) CK(cudaMalloc((void **)&(ptr), (count))); CK(cudaMemset((ptr), 0, (count)))
     ALLOC(e->dmodel, sizeof(ModelDev));

@@ -42,6 +42,36 @@ class _NetView:
     def state_dict(self):
         return OrderedDict((k[len(self._name) + 1:], v) for k, v in self._owner.state_dict().items() if k.startswith(self._name + "."))
 
+    def to_module(self):
+        """A plain ``torch.nn.Module`` with the reference MLP's structure (``model = Sequential(Linear, ELU, ..., Linear)``,
+        rsl_rl/modules/mlp.py:22-42) holding a CPU copy of the current weights — what deployment code expects."""
+        return _TorchMLP(self.state_dict())
+
+    def __deepcopy__(self, memo):
+        # helpers.export_policy_as_jit does copy.deepcopy(actor_critic.actor).to('cpu') and torch.jit.script()s the result
+        # (legged_gym/utils/helpers.py:188-201): hand it a real nn.Module
+        return self.to_module()
+
+
+class _TorchMLP(torch.nn.Module):
+    def __init__(self, sd):
+        super().__init__()
+        keys = sorted({int(k.split(".")[1]) for k in sd})
+        layers = []
+        for n, i in enumerate(keys):
+            w = sd[f"model.{i}.weight"]
+            lin = torch.nn.Linear(w.shape[1], w.shape[0])
+            with torch.no_grad():
+                lin.weight.copy_(w.detach().cpu())
+                lin.bias.copy_(sd[f"model.{i}.bias"].detach().cpu())
+            layers.append(lin)
+            if n < len(keys) - 1:
+                layers.append(torch.nn.ELU())
+        self.model = torch.nn.Sequential(*layers)
+
+    def forward(self, x):
+        return self.model(x)
+
 
 class ActorCriticMLP:
     """Parameters of actor 39->512->256->128->10 / critic 168->512->256->128->1 (ELU) + per-action ``std`` as views into
