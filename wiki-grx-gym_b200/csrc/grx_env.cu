@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -28,7 +29,8 @@ namespace {
 constexpr int NB = 11, ND = 10, NV = 16, CH = 5, NLMAX = 40, NSMAX = 32, NF = 2, KC = 8, KLIM = 7;
 constexpr int YS = 20;   // row stride of WS::Y (floats): 16-byte aligned and conflict-free for per-lane float4 stores
 constexpr int NREW = 24, NHMAX = 128;
-constexpr int WARPS_PER_CTA = 16;   // one CTA per SM; its warps re-converge at every substep so the 4 warps of a scheduler share instruction-cache lines
+constexpr int WARPS_PER_CTA = 16;   // MAXIMUM warps per CTA (one CTA per SM; its warps re-converge at every substep so the warps of a scheduler share
+                                    // instruction-cache lines).  The launch picks warps_per_cta <= 16 so that the CTAs fill whole waves (see env_warps_per_cta)
 constexpr int ACC_RING = 256, ACC_W = 32;   // extras["episode"] accumulators: one 32-float slot per launch, ring of 256
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -488,7 +490,7 @@ __device__ __forceinline__ void cta_align(int nthreads) {   // phase alignment o
 __device__ __noinline__ void substep(WS &s, const ModelDev &m, const EnvArgs &A, const grx_task_cfg &cfg, int lane) {
     const float dt = cfg.sim_dt;
     mass_and_bias(s, m, cfg.gravity, lane);
-    if (A.dbg_M != nullptr && A.dbg_index == (int)(blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5))) {  // debug_dynamics: export before factorisation
+    if (A.dbg_M != nullptr && A.dbg_index == (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5))) {  // debug_dynamics: export before factorisation
         for (int i = lane; i < NV * NV; i += 32) A.dbg_M[i] = s.M[i / NV][i % NV];
         if (lane < NV) A.dbg_h[lane] = s.h[lane];
         __syncwarp();
@@ -784,7 +786,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 1) env_step_kernel(const _
     ModelDev &m = *reinterpret_cast<ModelDev *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WS &s = *reinterpret_cast<WS *>(smem_raw + ((sizeof(ModelDev) + 15) & ~15) + (size_t)warp * sizeof(WS));
-    const int e = blockIdx.x * WARPS_PER_CTA + warp;
+    const int wpc = blockDim.x >> 5;   // warps (= robots) per CTA, chosen by the launch
+    const int e = blockIdx.x * wpc + warp;
     {   // model tables -> shared memory (divergent per-body indexing would serialise on the constant bank)
         const int4 *src = reinterpret_cast<const int4 *>(A.model);
         int4 *dst = reinterpret_cast<int4 *>(&m);
@@ -829,7 +832,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 1) env_step_kernel(const _
         // Re-converge the CTA's warps once per substep: the substep is ~60 KB of mostly straight-line code, and with every warp
         // of a scheduler in a different place the instruction caches thrash (ncu: 28 % of warp samples `no_instructions`);
         // aligned warps share the fetched lines (measured 536 -> 445 us per launch).  More barriers per substep cost more than they save.
-        const int cta_valid = min(WARPS_PER_CTA, A.N - (int)blockIdx.x * WARPS_PER_CTA) * 32;   // threads that did not exit above
+        const int cta_valid = min(wpc, A.N - (int)blockIdx.x * wpc) * 32;   // threads that did not exit above
         for (int deci = 0; deci <= cfg.decimation; deci++) {
             cta_align(A.dbg_M == nullptr ? cta_valid : 0);
             kinematics(s, m, lane);
@@ -1218,9 +1221,20 @@ struct grx_env {
     int t_rows = 1, t_cols = 1;
     bool params_set = false;
     size_t smem = 0;
+    int warps_per_cta = WARPS_PER_CTA;   // robots per CTA of env_step_kernel: whole waves of one CTA per SM (env_warps_per_cta)
     uint64_t launches = 0;   // step / reset launches so far; launch k accumulates extras into ring slot k % ACC_RING
 };
 
+// One CTA per SM is resident (registers + shared memory); with w warps per CTA a launch of N robots takes ceil(N / (w * SMs)) waves.
+// Take the number of waves of the widest CTA and shrink the CTA until those waves are evenly filled (4096 robots on 148 SMs:
+// 2 waves of 14 warps instead of one wave of 16 and one 73 % full).
+static int env_warps_per_cta(int N, int sms) {
+    const int waves = (N + WARPS_PER_CTA * sms - 1) / (WARPS_PER_CTA * sms);
+    int w = (N + waves * sms - 1) / (waves * sms);
+    if (w < 1) w = 1;
+    if (w > WARPS_PER_CTA) w = WARPS_PER_CTA;
+    return w;
+}
 static size_t env_smem_bytes() { return ((sizeof(ModelDev) + 15) & ~(size_t)15) + WARPS_PER_CTA * sizeof(WS); }
 
 extern "C" int grx_env_create(const grx_model_desc *md, const grx_task_cfg *cfg, int32_t num_envs, int32_t device, grx_env **out) {
@@ -1289,6 +1303,12 @@ extern "C" int grx_env_create(const grx_model_desc *md, const grx_task_cfg *cfg,
     e->terrain.type = 0; e->terrain.rows = e->terrain.cols = 0; e->terrain.h = nullptr;
     e->terrain.hscale = 1.f; e->terrain.vscale = 1.f; e->terrain.border = 0.f; e->terrain.friction = 1.f; e->terrain.restitution = 0.f;
     e->smem = env_smem_bytes();
+    {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) sms = 148;
+        e->warps_per_cta = env_warps_per_cta(num_envs, sms);
+        if (const char *w = getenv("GRX_ENV_WARPS")) { const int v = atoi(w); if (v >= 1 && v <= WARPS_PER_CTA) e->warps_per_cta = v; }
+    }
     CK(cudaFuncSetAttribute(env_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
     CK(cudaFuncSetAttribute(env_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
     CK(cudaFuncSetAttribute(env_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
@@ -1408,8 +1428,8 @@ extern "C" int grx_env_step(grx_env *e, const float *d_actions, const float *d_u
     if (!e || !d_actions) return grx_set_error(GRX_E_INVALID, "grx_env_step: null argument");
     if (!e->params_set) return grx_set_error(GRX_E_STATE, "grx_env_step: call grx_env_set_params first");
     EnvArgs A = make_args(e, d_actions, d_uniform, delay, push, step_index);
-    const int grid = (e->N + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-    env_step_kernel<true><<<grid, WARPS_PER_CTA * 32, e->smem, (cudaStream_t)stream>>>(A, e->cfg);
+    const int wpc = e->warps_per_cta, grid = (e->N + wpc - 1) / wpc;
+    env_step_kernel<true><<<grid, wpc * 32, e->smem, (cudaStream_t)stream>>>(A, e->cfg);
     CK(cudaGetLastError());
     e->launches++;
     return GRX_OK;
@@ -1421,8 +1441,8 @@ extern "C" int grx_env_post_physics(grx_env *e, const float *d_actions, const fl
     if (!e->params_set) return grx_set_error(GRX_E_STATE, "grx_env_post_physics: call grx_env_set_params first");
     EnvArgs A = make_args(e, d_actions, d_uniform, 0.f, push, step_index);
     A.inj = *inj;
-    const int grid = (e->N + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-    env_step_kernel<false><<<grid, WARPS_PER_CTA * 32, e->smem, (cudaStream_t)stream>>>(A, e->cfg);
+    const int wpc = e->warps_per_cta, grid = (e->N + wpc - 1) / wpc;
+    env_step_kernel<false><<<grid, wpc * 32, e->smem, (cudaStream_t)stream>>>(A, e->cfg);
     CK(cudaGetLastError());
     e->launches++;
     return GRX_OK;
@@ -1472,8 +1492,8 @@ extern "C" int grx_env_debug_dynamics(grx_env *e, int32_t index, float *h_M, flo
     A.rec = tmp_rec; A.dbg_M = dM; A.dbg_h = dh; A.dbg_index = index;
     grx_task_cfg c = e->cfg;
     c.decimation = 1;
-    const int grid = (e->N + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-    env_step_kernel<true><<<grid, WARPS_PER_CTA * 32, e->smem>>>(A, c);
+    const int wpc = e->warps_per_cta, grid = (e->N + wpc - 1) / wpc;
+    env_step_kernel<true><<<grid, wpc * 32, e->smem>>>(A, c);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(h_M, dM, NV * NV * 4, cudaMemcpyDeviceToHost));
