@@ -238,6 +238,9 @@ int grx_ppo_debug_timing(grx_ppo *ppo, float *out7, int32_t *count);
 int grx_gemm_debug(int32_t variant, int32_t epi, int32_t M, int32_t N, int32_t K, const float *A, const float *B, float *C,
                    const float *bias, const float *aux, float *bias_out, int32_t splits, int32_t use_tc, void *stream);
 
+/* Test / profiling: force the macro tile of the tensor-core GEMM (row_blocks in {1, 2} x bn in {32, 64, 128, 256}; 0, 0 = cost model). */
+int grx_gemm_debug_tile(int32_t row_blocks, int32_t bn);
+
 /* Profiling: %globaltimer stamps (ns) of CTA 0 of the most recent tensor-core GEMM launch: entry, setup done, first TMA issued,
  * first stage landed, last MMA committed, first accumulator complete, epilogue done, unused, then epilogue detail of warp 0's
  * first chunk: TMEM load done, staging written, proxy fence done, TMA store issued, all tiles stored.  16 values.  Synchronises. */

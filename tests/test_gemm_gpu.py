@@ -105,3 +105,21 @@ def test_tensor_core_update_matches_simt_update():
         worst[k] = float((a - b).abs().max()) / (float(a.abs().max()) + 1e-12)
     # three TF32 layers forward and three backward: operand rounding 2^-11 per product, accumulated over both passes
     assert max(worst.values()) <= 1e-2, worst
+
+
+@pytest.mark.parametrize("tile", [(1, 32), (1, 64), (1, 128), (1, 256), (2, 128), (2, 256)])
+def test_every_macro_tile_configuration(tile):
+    """The persistent kernel's macro tiles (row blocks x BN) are normally picked by a cost model; force each one and check the
+    forward (bias + ELU, TMA store, ragged M / N), input-gradient (ELU', column sums) and split-K weight-gradient (TMA reduce-add)
+    paths against fp32 torch."""
+    from grx_b200 import _lib as L
+    lib = L.lib()
+    L.check(lib.grx_gemm_debug_tile(tile[0], tile[1]))
+    try:
+        for variant, epi, M, N, K, splits in [(0, 1, 1000, 328, 168, 1), (0, 0, 10485, 512, 40, 1), (1, 2, 777, 256, 128, 1),
+                                              (2, 3, 256, 512, 3000, 7), (2, 3, 512, 168, 2048, 4)]:
+            got, ref, _ = _run(variant, epi, M, N, K, use_tc=1, splits=splits, seed=3)
+            scale = float(ref.abs().max())
+            assert float((got - ref).abs().max()) <= TF32_RTOL * scale, (tile, variant, M, N, K, float((got - ref).abs().max()) / scale)
+    finally:
+        L.check(lib.grx_gemm_debug_tile(0, 0))

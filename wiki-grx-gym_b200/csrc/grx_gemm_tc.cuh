@@ -67,6 +67,7 @@ struct Args {
 struct Group {
     Args g[MAXP];
     int np, total_tiles;
+    int dbg;   // profiling switches (GRX_TC_DEBUG): 1 skip the MMA issue, 2 skip the operand loads (results are garbage)
 };
 struct Maps {
     CUtensorMap a[MAXP], b[MAXP];
@@ -166,17 +167,34 @@ __device__ __forceinline__ float elu_f(float x) {
 
 __host__ __device__ constexpr uint32_t tile_bytes(int rows) { return (uint32_t)rows * 128u; }   // rows x 32 fp32, either major
 
-// EPI: 0 C = acc + bias[n] | 1 C = elu(acc + bias[n]) | 2 C = acc * ELU'(aux[m,n]) | 3 split-K: C += acc (red.global.add)
-template <bool A_KMAJ, bool B_KMAJ, int EPI, int BN, int S>
+// EPI: 0 C = acc + bias[n] | 1 C = elu(acc + bias[n]) | 2 C = acc * ELU'(aux[m,n]) | 3 split-K: C += acc (TMA reduce-add)
+// Macro tile: TMT (1 or 2) row blocks of 128 x BN columns per CTA tile; all row blocks share the B tile of a stage, so operand
+// traffic per output element drops from 1/128 + 1/BN to 1/(128 TMT) + 1/BN.
+template <int TMT, int BN>
+struct TileCfg {
+    static constexpr int NACC = 2 * TMT * BN <= 512 ? 2 : 1;         // accumulator sets in TMEM (2: epilogue overlaps the next tile)
+    static constexpr int ACC_COLS = TMT * BN;
+    static constexpr int EPW = BN >= 64 ? 8 : 4;                      // epilogue warps that own columns
+    static constexpr int WCOLS = BN >= 64 ? BN / 2 : 32;              // columns per epilogue warp
+    static constexpr int NCHW = WCOLS / 32;                           // 32-column chunks per warp and row block
+    static constexpr int CT = TMT * NCHW;                             // chunks per warp and tile
+    static constexpr int NBOX = CT < 2 ? CT : 2;                      // staging boxes per warp (ring when CT > NBOX)
+    static constexpr uint32_t a_bytes = (uint32_t)TMT * 16384u, b_bytes = (uint32_t)BN * 128u, stage_bytes = a_bytes + b_bytes;
+    static constexpr uint32_t staging_bytes = (uint32_t)EPW * NBOX * 4096u, bias_bytes = (uint32_t)EPW * WCOLS * 4u;
+    static constexpr size_t smem(int S) { return (size_t)stage_bytes * S + staging_bytes + bias_bytes + 1024; }
+};
+
+template <bool A_KMAJ, bool B_KMAJ, int EPI, int TMT, int BN, int S>
 __global__ void __launch_bounds__(NTHREADS_CTA, 1) gemm_tf32_kernel(const __grid_constant__ Maps maps, const __grid_constant__ Group grp) {
+    using Cfg = TileCfg<TMT, BN>;
+    constexpr int NACC = Cfg::NACC, ACC_COLS = Cfg::ACC_COLS, EPW = Cfg::EPW, WCOLS = Cfg::WCOLS, NCHW = Cfg::NCHW, CT = Cfg::CT, NBOX = Cfg::NBOX;
+    static_assert(EPI != 2 || CT <= NBOX, "EPI 2 prefetches the activation boxes of a whole tile: needs one staging box per chunk");
     extern __shared__ __align__(1024) unsigned char smem[];
-    constexpr int EPW = BN >= 64 ? 8 : 4;          // epilogue warps that own columns (BN = 32: one 32-column chunk per lane quadrant)
-    constexpr int NCH = BN >= 64 ? BN / 64 : 1;    // 32-column chunks per epilogue warp and tile
     __shared__ __align__(8) unsigned long long full_bar[S], empty_bar[S], acc_full[2], acc_empty[2], aux_bar[8][2];
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) stamp(0);
-    constexpr uint32_t a_bytes = tile_bytes(TM), b_bytes = tile_bytes(BN), stage_bytes = a_bytes + b_bytes;
+    constexpr uint32_t a_bytes = Cfg::a_bytes, stage_bytes = Cfg::stage_bytes;
     const uint32_t smem0 = (smem_u32(smem) + 1023u) & ~1023u;   // swizzle atoms need 1024-byte aligned tiles
 
     if (tid == 0) {
@@ -185,8 +203,8 @@ __global__ void __launch_bounds__(NTHREADS_CTA, 1) gemm_tf32_kernel(const __grid
         for (int i = 0; i < 16; i++) mbar_init(smem_u32(&aux_bar[i >> 1][i & 1]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {   // TMEM: two BN-column fp32 accumulators (power of two >= 32 columns), allocated by one warp
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(2 * BN) : "memory");
+    if (warp == 0) {   // TMEM: NACC accumulator sets of TMT x BN fp32 columns (power of two >= 32 columns), allocated by one warp
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(NACC * ACC_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (warp == 8 && lane == 0) {
@@ -212,7 +230,7 @@ __global__ void __launch_bounds__(NTHREADS_CTA, 1) gemm_tf32_kernel(const __grid
         const Args &g = grp.g[p];
         const int local = t - g.tile_begin;
         const int tn = local % g.nt_n, rest = local / g.nt_n, tm = rest % g.nt_m, z = rest / g.nt_m;
-        T.p = p; T.m0 = tm * TM; T.n0 = tn * BN; T.kbeg = z * g.kchunk;
+        T.p = p; T.m0 = tm * (TM * TMT); T.n0 = tn * BN; T.kbeg = z * g.kchunk;
         const int kend = min(g.K, T.kbeg + g.kchunk);
         T.nchunks = (kend - T.kbeg + TK - 1) / TK;
         return T;
@@ -229,11 +247,14 @@ __global__ void __launch_bounds__(NTHREADS_CTA, 1) gemm_tf32_kernel(const __grid
                     if (it >= S) mbar_wait(smem_u32(&empty_bar[st]), ((it / S) - 1) & 1);
                     const uint32_t ta = smem0 + st * stage_bytes, tb = ta + a_bytes, bar = smem_u32(&full_bar[st]);
                     const int k0 = T.kbeg + kb * TK;
+                    if (grp.dbg & 2) { mbar_arrive(bar); continue; }
                     mbar_expect_tx(bar, stage_bytes);
-                    if (A_KMAJ) tma_load_2d(ta, ma, k0, T.m0, bar);
-                    else {
+                    if (A_KMAJ) {
 #pragma unroll
-                        for (int j = 0; j < TM / 32; j++) tma_load_2d(ta + (uint32_t)j * 4096u, ma, T.m0 + 32 * j, k0, bar);
+                        for (int i = 0; i < TMT; i++) tma_load_2d(ta + (uint32_t)i * 16384u, ma, k0, T.m0 + TM * i, bar);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < TMT * (TM / 32); j++) tma_load_2d(ta + (uint32_t)j * 4096u, ma, T.m0 + 32 * j, k0, bar);
                     }
                     if (B_KMAJ) tma_load_2d(tb, mb, k0, T.n0, bar);
                     else {
@@ -254,9 +275,9 @@ __global__ void __launch_bounds__(NTHREADS_CTA, 1) gemm_tf32_kernel(const __grid
             uint32_t it = 0, ti = 0;
             for (int t = blockIdx.x; t < grp.total_tiles; t += gridDim.x, ti++) {
                 const Tile T = decode(t);
-                const uint32_t buf = ti & 1u;
-                if (ti >= 2) { mbar_wait(smem_u32(&acc_empty[buf]), ((ti >> 1) - 1) & 1); tc_fence_after(); }   // epilogue drained this accumulator
-                const uint32_t dacc = tmem + buf * (uint32_t)BN;
+                const uint32_t buf = ti % NACC;
+                if (ti >= (uint32_t)NACC) { mbar_wait(smem_u32(&acc_empty[buf]), ((ti / NACC) - 1) & 1); tc_fence_after(); }   // epilogue drained this set
+                const uint32_t dacc = tmem + buf * (uint32_t)ACC_COLS;
                 for (int kb = 0; kb < T.nchunks; kb++, it++) {
                     const uint32_t st = it % S;
                     mbar_wait(smem_u32(&full_bar[st]), (it / S) & 1);
@@ -264,78 +285,87 @@ __global__ void __launch_bounds__(NTHREADS_CTA, 1) gemm_tf32_kernel(const __grid
                     if (it == 0) stamp(3);
                     const uint32_t ta = smem0 + st * stage_bytes, tb = ta + a_bytes;
 #pragma unroll
-                    for (int j = 0; j < TK / 8; j++) {
-                        const uint64_t da = smem_desc(ta + (uint32_t)j * a_step, a_lbo, a_sbo, a_type);
-                        const uint64_t db = smem_desc(tb + (uint32_t)j * b_step, b_lbo, b_sbo, b_type);
-                        tc_mma_tf32(dacc, da, db, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+                    for (int i = 0; i < TMT; i++) {
+#pragma unroll
+                        for (int j = 0; j < TK / 8; j++) {
+                            const uint64_t da = smem_desc(ta + (uint32_t)i * 16384u + (uint32_t)j * a_step, a_lbo, a_sbo, a_type);
+                            const uint64_t db = smem_desc(tb + (uint32_t)j * b_step, b_lbo, b_sbo, b_type);
+                            if (!(grp.dbg & 1)) tc_mma_tf32(dacc + (uint32_t)(i * BN), da, db, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+                        }
                     }
                     tc_commit(smem_u32(&empty_bar[st]));                          // frees the stage when these MMAs have read it
-                    if (kb == T.nchunks - 1) tc_commit(smem_u32(&acc_full[buf]));   // accumulator complete
+                    if (kb == T.nchunks - 1) tc_commit(smem_u32(&acc_full[buf]));   // accumulator set complete
                 }
             }
             stamp(4);
         }
     } else {
-        // ---- epilogue (independent warps, no block-level synchronisation): warp w owns TMEM lanes [32 (w%4), +32) = tile rows and
-        // the column half w/4.  Per 32-column chunk: tcgen05.ld 32x32b.x32 -> registers (lane = row) -> bias / ELU / ELU' ->
-        // the warp's 4 KB staging box in shared memory (128-byte rows, 16-byte units XOR-swizzled with row % 8: conflict-free
-        // and exactly the SWIZZLE_128B box layout) -> ONE TMA store (or TMA reduce-add for split-K) per chunk; ragged edges
-        // are clipped by the TMA unit.  EPI 2: the activation box is TMA-loaded into the same staging box at tile start (while
-        // the accumulator is still being produced) and overwritten in place; bias-gradient column sums by a halving butterfly.
+        // ---- epilogue (independent warps, no block-level synchronisation): warp w owns TMEM lanes [32 (w%4), +32) = rows of every
+        // row block and the column half w/4.  Per 32-column chunk: tcgen05.ld 32x32b.x32 -> registers (lane = row) -> bias / ELU /
+        // ELU' -> one of the warp's 4 KB staging boxes in shared memory (128-byte rows, 16-byte units XOR-swizzled with row % 8:
+        // conflict-free and exactly the SWIZZLE_128B box layout) -> ONE TMA store (or TMA reduce-add for split-K) per chunk;
+        // ragged edges are clipped by the TMA unit.  The boxes form a ring (a box is rewritten once the bulk group that read it
+        // has drained).  Bias slice of the tile: staged per warp in shared memory while the accumulator is still being produced.
+        // EPI 2: the activation boxes are TMA-loaded into the staging boxes at tile start and overwritten in place; bias-gradient
+        // column sums by a halving butterfly.
         if (warp < EPW) {
             const int quad = warp & 3, chalf = warp >> 2;
-            const uint32_t stg0 = smem0 + (uint32_t)S * stage_bytes + (uint32_t)warp * (NCH * 4096u);
+            const uint32_t stg0 = smem0 + (uint32_t)S * stage_bytes + (uint32_t)warp * (NBOX * 4096u);
+            const uint32_t bias0 = smem0 + (uint32_t)S * stage_bytes + Cfg::staging_bytes + (uint32_t)warp * (WCOLS * 4u);
             const uint32_t rowoff = (uint32_t)lane * 128u, sw = (uint32_t)(lane & 7);
-            uint32_t ti = 0;
+            uint32_t ti = 0, cc = 0;   // tiles / chunks processed by this warp
             for (int t = blockIdx.x; t < grp.total_tiles; t += gridDim.x, ti++) {
                 const Tile T = decode(t);
                 const Args &g = grp.g[T.p];
-                const uint32_t buf = ti & 1u;
-                const int mrow0 = T.m0 + quad * 32, ncol0 = T.n0 + chalf * (BN / 2);
-                if (lane == 0) {
-                    tma_wait_read0();   // the stores of the previous tile have finished reading the staging boxes
-                    if (EPI == 2) {
+                const uint32_t buf = ti % NACC;
+                const int ncol0 = T.n0 + chalf * WCOLS;
+                if (EPI == 2) {
+                    if (lane == 0) {
+                        tma_wait_read0();   // the stores of the previous tile have finished reading the staging boxes
 #pragma unroll
-                        for (int ch = 0; ch < NCH; ch++) {
-                            const uint32_t bar = smem_u32(&aux_bar[warp][ch]);
+                        for (int c = 0; c < CT; c++) {
+                            const uint32_t bar = smem_u32(&aux_bar[warp][c]);
                             mbar_expect_tx(bar, 4096u);
-                            tma_load_2d(stg0 + ch * 4096u, &maps.aux[T.p], ncol0 + ch * 32, mrow0, bar);
+                            tma_load_2d(stg0 + c * 4096u, &maps.aux[T.p], ncol0 + (c % NCHW) * 32, T.m0 + (c / NCHW) * TM + quad * 32, bar);
                         }
+                    }
+                } else if (EPI == 0 || EPI == 1) {
+                    if (lane < WCOLS / 4) {
+                        const int nn = ncol0 + 4 * lane;
+                        const float4 bb = nn < g.N ? __ldg(reinterpret_cast<const float4 *>(g.bias + nn)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(bias0 + 16u * lane), "f"(bb.x), "f"(bb.y), "f"(bb.z), "f"(bb.w) : "memory");
                     }
                 }
                 __syncwarp();
-                float4 qb[NCH][8];   // EPI 0/1: the tile's bias slice, fetched while the accumulator is still being produced
-                if (EPI == 0 || EPI == 1) {
-#pragma unroll
-                    for (int ch = 0; ch < NCH; ch++)
-#pragma unroll
-                        for (int i = 0; i < 8; i++) {
-                            const int nn = ncol0 + ch * 32 + 4 * i;
-                            qb[ch][i] = nn < g.N ? __ldg(reinterpret_cast<const float4 *>(g.bias + nn)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        }
-                }
-                mbar_wait(smem_u32(&acc_full[buf]), (ti >> 1) & 1);
+                mbar_wait(smem_u32(&acc_full[buf]), (ti / NACC) & 1);
                 tc_fence_after();
                 if (ti == 0 && tid == 0) stamp(5);
-#pragma unroll
-                for (int ch = 0; ch < NCH; ch++) {
+#pragma unroll 1
+                for (int c = 0; c < CT; c++, cc++) {
+                    const int rb = c / NCHW, ch = c % NCHW;
+                    const int n = ncol0 + ch * 32, mrow0 = T.m0 + rb * TM + quad * 32;
+                    const uint32_t bx = CT <= NBOX ? (uint32_t)c : cc % NBOX;
                     float v[32];
-                    const int n = ncol0 + ch * 32;
-                    tc_ld32(tmem + ((uint32_t)(quad * 32) << 16) + buf * (uint32_t)BN + (uint32_t)(chalf * (BN / 2) + ch * 32), v);
-                    if (ti == 0 && tid == 0 && ch == 0) stamp(8);
-                    if (ch == NCH - 1) {   // this warp's last TMEM read of the accumulator: hand it back to the MMA warp
+                    tc_ld32(tmem + ((uint32_t)(quad * 32) << 16) + buf * (uint32_t)ACC_COLS + (uint32_t)(rb * BN + chalf * WCOLS + ch * 32), v);
+                    if (ti == 0 && tid == 0 && c == 0) stamp(8);
+                    if (c == CT - 1) {   // this warp's last TMEM read of the accumulator set: hand it back to the MMA warp
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
                     }
-                    const uint32_t box = stg0 + ch * 4096u + rowoff;
-                    if (EPI == 2) mbar_wait(smem_u32(&aux_bar[warp][ch]), ti & 1);
-                    // pass 1: all loads of the chunk (bias from global / activation from the staging box) are issued back to back;
-                    // interleaving them with the volatile shared stores below would serialise one memory latency per float4
+                    if (EPI != 2) {      // ring: the bulk group that read this box (NBOX chunks ago) must have drained
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NBOX - 1) : "memory");
+                        __syncwarp();
+                    }
+                    const uint32_t box = stg0 + bx * 4096u + rowoff;
+                    if (EPI == 2) mbar_wait(smem_u32(&aux_bar[warp][c]), ti & 1);
+                    // pass 1: all shared loads of the chunk (bias slice / activation box) are issued back to back; interleaving them
+                    // with the volatile shared stores below would serialise one latency per float4
                     float4 q[8];
                     if (EPI == 0 || EPI == 1) {
 #pragma unroll
-                        for (int i = 0; i < 8; i++) q[i] = qb[ch][i];
+                        for (int i = 0; i < 8; i++)
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q[i].x), "=f"(q[i].y), "=f"(q[i].z), "=f"(q[i].w) : "r"(bias0 + (uint32_t)(ch * 128 + i * 16)));
                     } else if (EPI == 2) {
 #pragma unroll
                         for (int i = 0; i < 8; i++) {
@@ -359,15 +389,15 @@ __global__ void __launch_bounds__(NTHREADS_CTA, 1) gemm_tf32_kernel(const __grid
                         }
                         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w) : "memory");
                     }
-                    if (ti == 0 && tid == 0 && ch == 0) stamp(9);
+                    if (ti == 0 && tid == 0 && c == 0) stamp(9);
                     fence_proxy_async();
                     __syncwarp();
-                    if (ti == 0 && tid == 0 && ch == 0) stamp(10);
+                    if (ti == 0 && tid == 0 && c == 0) stamp(10);
                     if (lane == 0) {
-                        if (EPI == 3) tma_reduce_add_2d(&maps.c[T.p], n, mrow0, stg0 + ch * 4096u);
-                        else tma_store_2d(&maps.c[T.p], n, mrow0, stg0 + ch * 4096u);
+                        if (EPI == 3) tma_reduce_add_2d(&maps.c[T.p], n, mrow0, stg0 + bx * 4096u);
+                        else tma_store_2d(&maps.c[T.p], n, mrow0, stg0 + bx * 4096u);
                         tma_commit();
-                        if (ti == 0 && tid == 0 && ch == 0) stamp(11);
+                        if (ti == 0 && tid == 0 && c == 0) stamp(11);
                     }
                     if (EPI == 2 && g.colsum != nullptr) {
                         warp_colsum<32>(v, lane);
@@ -382,7 +412,7 @@ __global__ void __launch_bounds__(NTHREADS_CTA, 1) gemm_tf32_kernel(const __grid
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * BN) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(NACC * ACC_COLS) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -452,6 +482,16 @@ inline cudaError_t get_tensor_map(const float *base, int rows, int cols, int ld,
     return cudaSuccess;
 }
 
+// test / profiling override of the macro-tile choice: {row blocks, BN}, {0, 0} = cost model (GRX_TC_TILE=2x256 sets it at load)
+inline int *forced_tile() {
+    static int t[2] = {0, 0};
+    static bool init = false;
+    if (!init) {
+        init = true;
+        if (const char *e = getenv("GRX_TC_TILE")) { t[0] = atoi(e); const char *x = strchr(e, 'x'); t[1] = x ? atoi(x + 1) : 0; }
+    }
+    return t;
+}
 inline int sm_count() {
     static int n = 0;
     if (n == 0) {
@@ -462,13 +502,13 @@ inline int sm_count() {
     return n;
 }
 
-template <bool A_KMAJ, bool B_KMAJ, int EPI, int BN, int S>
-inline cudaError_t launch_bn(const Problem *ps, int np, const int *splits, cudaStream_t st) {
-    constexpr size_t smem = (size_t)(tile_bytes(TM) + tile_bytes(BN)) * S + (BN >= 64 ? 8 * (BN / 64) : 4) * 4096 + 1024;
-    static_assert(smem <= 227 * 1024, "shared memory budget");
+template <bool A_KMAJ, bool B_KMAJ, int EPI, int TMT, int BN, int S>
+inline cudaError_t launch_cfg(const Problem *ps, int np, const int *splits, cudaStream_t st) {
+    constexpr size_t smem = TileCfg<TMT, BN>::smem(S);
+    static_assert(smem <= 226 * 1024, "shared memory budget (227 KB per CTA minus the static barriers)");
     static bool attr_done = false;   // per template instantiation
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<A_KMAJ, B_KMAJ, EPI, BN, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel<A_KMAJ, B_KMAJ, EPI, TMT, BN, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_done = true;
     }
@@ -495,46 +535,63 @@ inline cudaError_t launch_bn(const Problem *ps, int np, const int *splits, cudaS
         const int sp = splits && splits[i] > 1 ? splits[i] : 1;
         g.kchunk = ((p.K + sp - 1) / sp + TK - 1) / TK * TK;
         const int z = (p.K + g.kchunk - 1) / g.kchunk;
-        g.nt_m = (p.M + TM - 1) / TM; g.nt_n = (p.N + BN - 1) / BN;
+        g.nt_m = (p.M + TM * TMT - 1) / (TM * TMT); g.nt_n = (p.N + BN - 1) / BN;
         g.tile_begin = total;
         total += g.nt_m * g.nt_n * z;
     }
     for (int i = np; i < MAXP; i++) { maps.a[i] = maps.a[0]; maps.b[i] = maps.b[0]; maps.c[i] = maps.c[0]; maps.aux[i] = maps.aux[0]; grp.g[i].tile_begin = total; }
     grp.total_tiles = total;
+    { static const char *e = getenv("GRX_TC_DEBUG"); grp.dbg = e ? atoi(e) : 0; }
     if (total == 0) return cudaSuccess;
     const int grid = total < sm_count() ? total : sm_count();
-    gemm_tf32_kernel<A_KMAJ, B_KMAJ, EPI, BN, S><<<grid, NTHREADS_CTA, smem, st>>>(maps, grp);
+    gemm_tf32_kernel<A_KMAJ, B_KMAJ, EPI, TMT, BN, S><<<grid, NTHREADS_CTA, smem, st>>>(maps, grp);
     return cudaGetLastError();
 }
 
-// One launch for `np` (<= MAXP) problems of the same operand layout and epilogue.  N tile: the smallest cost of
-// rounds x bytes-per-tile (these GEMMs are bound by operand traffic from L2, and the tile list is static round-robin).
+// One launch for `np` (<= MAXP) problems of the same operand layout and epilogue.  The macro tile is picked by a small cost model:
+// these GEMMs are bound by operand bytes pulled into each SM (~70 B/ns per SM through TMA, measured) and the tile list is static
+// round-robin, so cost = rounds x (operand bytes of one tile / 70 B/ns + the epilogue when it cannot overlap the next tile).
 template <bool A_KMAJ, bool B_KMAJ, int EPI>
 inline cudaError_t launch_group(const Problem *ps, int np, const int *splits, cudaStream_t st) {
     if (np < 1 || np > MAXP) return cudaErrorInvalidValue;
     const int sms = sm_count();
-    long best_cost = -1;
-    int best_bn = 32;
-    const int cands[3] = {128, 64, 32};
-    for (int ci = 0; ci < 3; ci++) {
-        const int bn = cands[ci];
+    struct Cand { int tmt, bn; };
+    static const Cand cands[6] = {{2, 256}, {2, 128}, {1, 256}, {1, 128}, {1, 64}, {1, 32}};
+    double best = -1.0;
+    int bt = 1, bb = 32;
+    for (int ci = 0; ci < 6; ci++) {
+        const int tmt = cands[ci].tmt, bn = cands[ci].bn;
+        if (EPI == 2 && (tmt > 1 || bn > 128)) continue;   // ELU' needs one staging box per chunk of the tile
         long tiles = 0;
+        double bytes = 0.0;
         bool ok = true;
         for (int i = 0; i < np; i++) {
             const int sp = splits && splits[i] > 1 ? splits[i] : 1;
             const int kchunk = ((ps[i].K + sp - 1) / sp + TK - 1) / TK * TK;
             const int z = (ps[i].K + kchunk - 1) / kchunk;
-            if (bn > 32 && ps[i].N <= bn / 2) ok = false;   // mostly padding
-            tiles += (long)((ps[i].M + TM - 1) / TM) * ((ps[i].N + bn - 1) / bn) * z;
+            if (bn > 32 && ps[i].N <= bn / 2) ok = false;                  // mostly padding along N
+            if (tmt > 1 && ps[i].M <= TM) ok = false;                      // second row block would be padding
+            const long ti = (long)((ps[i].M + TM * tmt - 1) / (TM * tmt)) * ((ps[i].N + bn - 1) / bn) * z;
+            tiles += ti;
+            bytes += (double)ti * (TM * tmt + bn) * kchunk * 4.0;
         }
-        if (!ok && ci < 2) continue;
+        if (!ok && !(tmt == 1 && bn == 32)) continue;
         const long rounds = (tiles + sms - 1) / sms;
-        const long cost = rounds * (TM + bn + 24);   // per-tile bytes ~ (128 + BN) per k, + fixed epilogue share
-        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_bn = bn; }
+        const int ct = tmt * (bn >= 64 ? bn / 64 : 1);
+        const bool overlap = 2 * tmt * bn <= 512;
+        const double t_tile = bytes / (double)tiles / 70.0 + (overlap ? 100.0 : 350.0 * ct);
+        double cost = rounds * t_tile + 350.0 * ct + 1500.0;
+        if (forced_tile()[0] == tmt && forced_tile()[1] == bn) cost = 0.0;   // profiling / test override (grx_gemm_debug_tile)
+        if (best < 0 || cost < best) { best = cost; bt = tmt; bb = bn; }
     }
-    if (best_bn == 128) return launch_bn<A_KMAJ, B_KMAJ, EPI, 128, 4>(ps, np, splits, st);
-    if (best_bn == 64) return launch_bn<A_KMAJ, B_KMAJ, EPI, 64, 7>(ps, np, splits, st);
-    return launch_bn<A_KMAJ, B_KMAJ, EPI, 32, 8>(ps, np, splits, st);
+    if (EPI != 2) {
+        if (bt == 2 && bb == 256) return launch_cfg<A_KMAJ, B_KMAJ, EPI == 2 ? 0 : EPI, 2, 256, 2>(ps, np, splits, st);
+        if (bt == 2 && bb == 128) return launch_cfg<A_KMAJ, B_KMAJ, EPI == 2 ? 0 : EPI, 2, 128, 3>(ps, np, splits, st);
+        if (bt == 1 && bb == 256) return launch_cfg<A_KMAJ, B_KMAJ, EPI == 2 ? 0 : EPI, 1, 256, 3>(ps, np, splits, st);
+    }
+    if (bb == 128) return launch_cfg<A_KMAJ, B_KMAJ, EPI, 1, 128, 4>(ps, np, splits, st);
+    if (bb == 64) return launch_cfg<A_KMAJ, B_KMAJ, EPI, 1, 64, 7>(ps, np, splits, st);
+    return launch_cfg<A_KMAJ, B_KMAJ, EPI, 1, 32, 8>(ps, np, splits, st);
 }
 
 template <bool A_KMAJ, bool B_KMAJ, int EPI>

@@ -1302,6 +1302,13 @@ extern "C" int grx_ppo_act_inference(grx_ppo *p, const float *d_obs, int32_t n, 
     return GRX_OK;
 }
 
+// Test / profiling: force the macro tile of the tensor-core GEMM ({0, 0} = cost model).  Configurations that do not apply to a launch
+// (ELU' epilogue with more than 128 x 128, padding-only tiles) fall back to the cost model.
+extern "C" int grx_gemm_debug_tile(int32_t row_blocks, int32_t bn) {
+    tc::forced_tile()[0] = row_blocks; tc::forced_tile()[1] = bn;
+    return GRX_OK;
+}
+
 // Profiling: %globaltimer stamps (ns) of CTA 0 of the most recent tensor-core GEMM launch (see tc::g_stamps).  Synchronises.
 extern "C" int grx_gemm_debug_stamps(uint64_t *out8) {   /* 16 values */
     if (!out8) return grx_set_error(GRX_E_INVALID, "grx_gemm_debug_stamps: null argument");
