@@ -54,3 +54,53 @@ def smoke_check(np_, torch):
         np_.testing.assert_allclose(pri.cpu().numpy(), o_pri.numpy(), **PHYS_TOL)
         np_.testing.assert_allclose(rew.cpu().numpy(), o_rew.numpy(), **PHYS_TOL)
     print("smoke: env step on cuda:0 matches the CPU oracle (64 envs, 2 steps)")
+    ppo_gradient_check(np_, torch, use_tc=1, atol=6e-3)
+    print("smoke: PPO minibatch (tcgen05 TF32 layers, fused heads, backward) on cuda:0 matches the CPU oracle")
+
+
+def ppo_gradient_check(np_, torch, use_tc, atol):
+    """One PPO minibatch (gather -> forward -> fused heads / losses -> backward) at the registered network width through the C ABI,
+    every gradient tensor and the KL / loss sums vs the hand-derived CPU oracle (oracle/ppo_oracle.py)."""
+    import ctypes as C
+    from grx_b200 import _lib as L
+    from grx_b200.config import make_train_cfg
+    from grx_b200.ppo import PPO, ActorCriticMLP
+    from oracle import ppo_oracle as po
+    torch.manual_seed(5)
+    tc = make_train_cfg()
+    O, P, A, N, T = 39, 168, 10, 256, 8
+    ac = ActorCriticMLP(O, P, A, **tc["policy"])
+    alg = PPO(ac, device="cuda:0", use_tensor_cores=use_tc, **dict(tc["algorithm"], num_mini_batches=2, num_learning_epochs=1))
+    alg.init_storage(N, T)
+    g = torch.Generator().manual_seed(7)
+    obs, cobs = torch.randn(T, N, O, generator=g), torch.randn(T, N, P, generator=g)
+    for s in range(T):
+        alg.act(obs[s].cuda(), cobs[s].cuda(), eps=torch.randn(N, A, generator=g).cuda())
+        alg.process_env_step((0.1 * torch.randn(N, generator=g)).cuda(), (torch.rand(N, generator=g) < 0.1).cuda(), {})
+    alg.compute_returns(torch.randn(N, P, generator=g).cuda())
+    with torch.no_grad():   # perturb the policy so that ratio != 1 and KL > 0
+        for k, v in ac.state_dict().items():
+            v.add_(0.02 * torch.randn(v.shape, generator=g).cuda() * (v.abs().mean() + 0.05))
+    p_new = {k: v.cpu().clone() for k, v in ac.state_dict().items()}
+    idx = torch.randperm(N * T, generator=g)
+    alg._indices.copy_(idx.cuda())
+    L.check(alg.lib.grx_ppo_minibatch_grads(alg._h, C.c_void_p(alg._indices.data_ptr()), 1, alg._stream()))
+    torch.cuda.synchronize()
+    st = alg.storage
+    flat = lambda x: x.cpu().flatten(0, 1)
+    sel = idx[alg.mini_batch_size:2 * alg.mini_batch_size]
+    b = dict(obs=flat(st.obs)[sel], critic_obs=flat(st.critic_obs)[sel], actions=flat(st.actions)[sel], values=flat(st.values)[sel],
+             advantages=flat(st.advantages)[sel], returns=flat(st.returns)[sel], old_log_prob=flat(st.actions_log_prob)[sel],
+             old_mu=flat(st.mu)[sel], old_sigma=flat(st.sigma)[sel])
+    stats, grads = po.minibatch_loss_and_grads(p_new, b, 0.2, 1.0, 0.01, True)
+    got = alg.grads.cpu()
+    for k in p_new:
+        gk = ac.view_of(got, k)
+        scale = float(grads[k].abs().max()) + 1e-12
+        np_.testing.assert_allclose(gk.numpy() / scale, grads[k].numpy() / scale, rtol=0, atol=atol, err_msg=k)
+    tail = alg.reduce_buf[-8:].cpu()
+    rt = 1e-3 if not use_tc else 5e-3
+    np_.testing.assert_allclose(float(tail[0] / tail[1]), float(stats["kl_mean"]), rtol=rt)
+    np_.testing.assert_allclose(float(tail[2] / tail[1]), float(stats["surrogate_loss"]), rtol=rt, atol=1e-5)
+    np_.testing.assert_allclose(float(tail[3] / tail[1]), float(stats["value_loss"]), rtol=rt)
+    alg.close()

@@ -41,7 +41,7 @@
 namespace tc {
 
 constexpr int TM = 128, TK = 32, NTHREADS_CTA = 320;   // 8 epilogue warps + TMA warp + MMA warp
-constexpr int MAXP = 4;                                 // problems per grouped launch
+constexpr int MAXP = 6;                                 // problems per grouped launch (all weight gradients of actor + critic)
 
 // profiling stamps of CTA 0 (ns, %globaltimer): [0] entry, [1] setup done, [2] first TMA issued, [3] first stage landed,
 // [4] last MMA committed, [5] first accumulator complete (epilogue starts), [6] epilogue of the last tile done

@@ -1047,23 +1047,20 @@ static void mlp_backward(grx_ppo *p, const NetIO *io, int nn, float *grads, int 
     GemmArgs g[8];
     int splits[8], n = 0;
     auto flush = [&]() { if (n) dense_group<false, false, 3>(g, splits, n, tcu, st); n = 0; };
-    for (int pass = 0; pass < 2; pass++) {   // pass 0: hidden layers (wide N), pass 1: input layer (narrow N) -> separate tile shapes
-        for (int l = top; l >= 0; l--) {
-            if ((l == 0) != (pass == 1)) continue;
-            for (int i = 0; i < nn; i++) {
-                const Net &net = *io[i].net;
-                GemmArgs &a = g[n];
-                memset(&a, 0, sizeof(GemmArgs));
-                a.A = io[i].d[l]; a.B = l == 0 ? io[i].x : io[i].h[l - 1]; a.C = grads + net.w[l];
-                a.bias_out = (l == top && top == 3) ? grads + net.b[l] : nullptr;
-                a.M = net.dims[l + 1]; a.N = l == 0 ? net.ld[0] : net.dims[l]; a.K = M; a.lda = net.dims[l + 1]; a.ldb = l == 0 ? io[i].ldx : net.dims[l];
-                a.ldc = net.ld[l];
-                splits[n] = (M + 511) / 512;
-                if (++n == tc::MAXP) flush();
-            }
+    for (int l = top; l >= 0; l--) {   // all weight gradients of both networks: one grouped launch (2 x 3 problems with the fused heads)
+        for (int i = 0; i < nn; i++) {
+            const Net &net = *io[i].net;
+            GemmArgs &a = g[n];
+            memset(&a, 0, sizeof(GemmArgs));
+            a.A = io[i].d[l]; a.B = l == 0 ? io[i].x : io[i].h[l - 1]; a.C = grads + net.w[l];
+            a.bias_out = (l == top && top == 3) ? grads + net.b[l] : nullptr;
+            a.M = net.dims[l + 1]; a.N = l == 0 ? net.ld[0] : net.dims[l]; a.K = M; a.lda = net.dims[l + 1]; a.ldb = l == 0 ? io[i].ldx : net.dims[l];
+            a.ldc = net.ld[l];
+            splits[n] = (M + 511) / 512;
+            if (++n == tc::MAXP) flush();
         }
-        flush();
     }
+    flush();
 }
 // stage caller-provided observation rows (any row stride >= width) into the padded, 16-byte aligned input buffers
 static cudaError_t stage_rows(float *dst, int ld_dst, const float *src, int width, int rows, cudaStream_t st) {
