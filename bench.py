@@ -285,8 +285,8 @@ def run_ours(args):
                     "note": "21.75 MFLOP per transition incl. rollout forward; measured over compute_returns + update"}
         cb = cpu_port_rate(quick=True) if world == 1 else None
         # our kernels per iteration: per policy step 3 grouped tcgen05 layers + 2 SIMT output heads + act/store + env + storage = 8;
-        # compute_returns 6; per minibatch gather + 3 forward + heads + 2 dX + 1 grouped dW + apply = 9 (+ the all-reduce kernel when N > 1)
-        launches_per_iter = T_STEPS * 8 + 6 + 200 * (9 + (1 if world > 1 else 0))
+        # compute_returns 6; per minibatch gather + 3 forward + heads + 2 dX + 2 grouped dW + apply = 10 (+ the all-reduce kernel when N > 1)
+        launches_per_iter = T_STEPS * 8 + 6 + 200 * (10 + (1 if world > 1 else 0))
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",

@@ -695,12 +695,17 @@ __global__ void __launch_bounds__(256) allreduce_kernel(const CommDev c, int n4,
     const int per = (n4 + c.world - 1) / c.world, lo = c.rank * per, hi = min(n4, lo + per);
     float ss = 0.f;
     for (int i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) {
-        float4 s = reinterpret_cast<const float4 *>(c.grads[0])[i];
-        for (int r = 1; r < c.world; r++) {
-            const float4 v = reinterpret_cast<const float4 *>(c.grads[r])[i];
-            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-        }
-        for (int r = 0; r < c.world; r++) reinterpret_cast<float4 *>(c.gsum[r])[i] = s;
+        float4 v[MAXW];
+#pragma unroll
+        for (int r = 0; r < MAXW; r++)   // all peer loads in flight at once (one NVLink round trip, not `world` of them)
+            if (r < c.world) v[r] = reinterpret_cast<const float4 *>(c.grads[r])[i];
+        float4 s = v[0];
+#pragma unroll
+        for (int r = 1; r < MAXW; r++)
+            if (r < c.world) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }   // rank order: bit-identical on every rank
+#pragma unroll
+        for (int r = 0; r < MAXW; r++)
+            if (r < c.world) reinterpret_cast<float4 *>(c.gsum[r])[i] = s;
         if (i < nparam4) ss += s.x * s.x + s.y * s.y + s.z * s.z + s.w * s.w;   // the tail (KL / loss sums) is not part of the gradient
     }
     __threadfence_system();
@@ -1047,20 +1052,23 @@ static void mlp_backward(grx_ppo *p, const NetIO *io, int nn, float *grads, int 
     GemmArgs g[8];
     int splits[8], n = 0;
     auto flush = [&]() { if (n) dense_group<false, false, 3>(g, splits, n, tcu, st); n = 0; };
-    for (int l = top; l >= 0; l--) {   // all weight gradients of both networks: one grouped launch (2 x 3 problems with the fused heads)
-        for (int i = 0; i < nn; i++) {
-            const Net &net = *io[i].net;
-            GemmArgs &a = g[n];
-            memset(&a, 0, sizeof(GemmArgs));
-            a.A = io[i].d[l]; a.B = l == 0 ? io[i].x : io[i].h[l - 1]; a.C = grads + net.w[l];
-            a.bias_out = (l == top && top == 3) ? grads + net.b[l] : nullptr;
-            a.M = net.dims[l + 1]; a.N = l == 0 ? net.ld[0] : net.dims[l]; a.K = M; a.lda = net.dims[l + 1]; a.ldb = l == 0 ? io[i].ldx : net.dims[l];
-            a.ldc = net.ld[l];
-            splits[n] = (M + 511) / 512;
-            if (++n == tc::MAXP) flush();
+    for (int pass = 0; pass < 2; pass++) {   // pass 0: hidden layers (wide N), pass 1: input layer (narrow N) -> their own tile shape
+        for (int l = top; l >= 0; l--) {     // (one launch for all six was measured slower: the narrow input layers drag the group to BN = 64)
+            if ((l == 0) != (pass == 1)) continue;
+            for (int i = 0; i < nn; i++) {
+                const Net &net = *io[i].net;
+                GemmArgs &a = g[n];
+                memset(&a, 0, sizeof(GemmArgs));
+                a.A = io[i].d[l]; a.B = l == 0 ? io[i].x : io[i].h[l - 1]; a.C = grads + net.w[l];
+                a.bias_out = (l == top && top == 3) ? grads + net.b[l] : nullptr;
+                a.M = net.dims[l + 1]; a.N = l == 0 ? net.ld[0] : net.dims[l]; a.K = M; a.lda = net.dims[l + 1]; a.ldb = l == 0 ? io[i].ldx : net.dims[l];
+                a.ldc = net.ld[l];
+                splits[n] = (M + 511) / 512;
+                if (++n == tc::MAXP) flush();
+            }
         }
+        flush();
     }
-    flush();
 }
 // stage caller-provided observation rows (any row stride >= width) into the padded, 16-byte aligned input buffers
 static cudaError_t stage_rows(float *dst, int ld_dst, const float *src, int width, int rows, cudaStream_t st) {
