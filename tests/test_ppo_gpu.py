@@ -194,3 +194,47 @@ def test_reference_jit_export_path(tmp_path):
     ours = ac.act_inference(obs.cuda()).cpu()
     assert [k for k in model.state_dict()] == [f"model.{i}.{p}" for i in (0, 2, 4, 6) for p in ("weight", "bias")]
     np.testing.assert_allclose(ours.numpy(), ref.detach().numpy(), rtol=0, atol=5e-3)   # TF32 tensor-core layers vs fp32 torch
+
+
+@pytest.mark.parametrize("use_tc", [0, 1])
+def test_rollout_act_registered_policy_matches_torch(use_tc):
+    """PPO.act at the registered widths takes the fast path (output heads folded into the sampling kernel): actions, stored mean /
+    sigma / log-prob / value vs a plain torch fp32 forward of the same weights (actor_critic_mlp.py:165-231, ppo.py:150-164)."""
+    from grx_b200.ppo import PPO, ActorCriticMLP
+    tc = make_train_cfg()
+    torch.manual_seed(9)
+    N, T = 333, 4
+    ac = ActorCriticMLP(39, 168, 10, **tc["policy"])
+    alg = PPO(ac, device="cuda:0", use_tensor_cores=use_tc, **tc["algorithm"])
+    alg.init_storage(N, T)
+    with torch.no_grad():
+        ac.std.copy_(torch.linspace(0.1, 0.5, 10))
+    actor, critic = ac.actor.to_module(), ac.critic.to_module()
+    g = torch.Generator().manual_seed(1)
+    tol = 1e-5 if not use_tc else 6e-3
+    for t in range(T):
+        obs, cobs, eps = torch.randn(N, 39, generator=g), torch.randn(N, 168, generator=g), torch.randn(N, 10, generator=g)
+        a = alg.act(obs.cuda(), cobs.cuda(), eps=eps.cuda()).cpu()
+        alg.process_env_step(torch.zeros(N).cuda(), torch.zeros(N, dtype=torch.bool).cuda(), {})
+        with torch.no_grad():
+            mu, v, std = actor(obs), critic(cobs), ac.std.cpu()
+        st = alg.storage
+        np.testing.assert_allclose(st.mu[t].cpu().numpy(), mu.numpy(), rtol=0, atol=tol * float(mu.abs().max()))
+        np.testing.assert_allclose(st.values[t].cpu().numpy(), v.numpy(), rtol=0, atol=tol * float(v.abs().max() + 1.0))
+        np.testing.assert_allclose(st.sigma[t].cpu().numpy(), std.expand(N, 10).numpy(), rtol=1e-6)
+        np.testing.assert_allclose(a.numpy(), (st.mu[t].cpu() + std * eps).numpy(), rtol=1e-5, atol=1e-6)   # a = mu + sigma * eps
+        np.testing.assert_array_equal(st.actions[t].cpu().numpy(), a.numpy())
+        lp = torch.distributions.Normal(st.mu[t].cpu(), std.expand(N, 10)).log_prob(a).sum(-1)
+        np.testing.assert_allclose(st.actions_log_prob[t].cpu().numpy().ravel(), lp.numpy(), rtol=1e-4, atol=1e-4)
+        np.testing.assert_array_equal(st.obs[t].cpu().numpy(), obs.numpy())
+        np.testing.assert_array_equal(st.critic_obs[t].cpu().numpy(), cobs.numpy())
+    # fast mode (in-kernel Philox): standard-normal draws
+    z = []
+    for t in range(2):
+        alg.step = 0
+        obs, cobs = torch.randn(N, 39, generator=g), torch.randn(N, 168, generator=g)
+        a = alg.act(obs.cuda(), cobs.cuda()).cpu()
+        z.append((a - alg.storage.mu[0].cpu()) / ac.std.cpu())
+    z = torch.cat(z).flatten()
+    assert abs(float(z.mean())) < 0.05 and abs(float(z.std()) - 1.0) < 0.05 and float(z.abs().max()) < 6.0
+    alg.close()

@@ -266,6 +266,77 @@ __global__ void act_sample_store_kernel(const ActArgs a) {
     for (size_t i = tid; i < (size_t)a.N * a.P; i += nth) a.s_cobs[i] = a.critic_obs[i];
 }
 
+// Rollout fast path for the registered policy (A == NA, last hidden width 128): the two output heads (mu = W3a h3a + b, V = W3c h3c + b)
+// folded into the sampling / storage kernel — one warp per env, lane = 4 hidden columns, the 11 dot products reduced by the same
+// 16-shuffle halving butterfly as ppo_heads_kernel, lane j owns action j.  Saves the two narrow SIMT GEMM launches per policy step.
+struct ActHeadsArgs {
+    const float *h3a, *h3c, *W3a, *b3a, *W3c, *b3c;
+    ActArgs a;
+};
+template <int NA>
+__global__ void __launch_bounds__(256) act_heads_kernel(const ActHeadsArgs q) {
+    constexpr int H = 128;
+    const ActArgs &a = q.a;
+    const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int c0 = lane * 4;
+    const bool own = lane < NA;
+    float4 wa[NA];
+#pragma unroll
+    for (int j = 0; j < NA; j++) wa[j] = *reinterpret_cast<const float4 *>(q.W3a + j * H + c0);
+    const float4 wc = *reinterpret_cast<const float4 *>(q.W3c + c0);
+    const float sg = own ? a.std[lane] : 1.f, ba = own ? q.b3a[lane] : 0.f, bc = q.b3c[0];
+    for (int n = warp; n < a.N; n += nwarps) {
+        const float4 ha = *reinterpret_cast<const float4 *>(q.h3a + (size_t)n * H + c0);
+        const float4 hc = *reinterpret_cast<const float4 *>(q.h3c + (size_t)n * H + c0);
+        float t[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) t[j] = 0.f;
+#pragma unroll
+        for (int j = 0; j < NA; j++) t[j] = ha.x * wa[j].x + ha.y * wa[j].y + ha.z * wa[j].z + ha.w * wa[j].w;
+        t[NA] = hc.x * wc.x + hc.y * wc.y + hc.z * wc.z + hc.w * wc.w;
+#pragma unroll
+        for (int w = 8, bit = 8; w >= 1; w >>= 1, bit >>= 1) {
+            const bool up = (lane & bit) != 0;
+#pragma unroll
+            for (int i = 0; i < w; i++) {
+                const float send = up ? t[i] : t[i + w], keep = up ? t[i + w] : t[i];
+                t[i] = keep + __shfl_xor_sync(FULL, send, bit);
+            }
+        }
+        t[0] += __shfl_xor_sync(FULL, t[0], 16);
+        const float mu = t[0] + ba;                              // lanes < NA
+        const float v = __shfl_sync(FULL, t[0], NA) + bc;
+        float z = 0.f;
+        if (own) {
+            if (a.eps) z = a.eps[(size_t)n * NA + lane];
+            else {   // same counter / pairing as act_sample_store_kernel: element j uses draw (j >> 2), Box-Muller pair (j & 2)
+                uint32_t rnd[4];
+                philox4((uint32_t)a.seed ^ 0x2545F491u, (uint32_t)(a.seed >> 32), (uint32_t)(a.env_id_offset + n), (uint32_t)a.step_index,
+                        (uint32_t)(a.step_index >> 32), (uint32_t)(lane >> 2), rnd);
+                const int r = lane & 2;
+                const float u1 = ((float)(rnd[r] >> 8) + 1.0f) * (1.0f / 16777216.0f), u2 = (float)(rnd[r + 1] >> 8) * (1.0f / 16777216.0f);
+                const float rad = sqrtf(-2.0f * logf(u1));
+                float sn, cs;
+                sincospif(2.0f * u2, &sn, &cs);
+                z = (lane & 1) ? rad * sn : rad * cs;
+            }
+        }
+        const float act = mu + sg * z, d = act - mu;
+        float lp = own ? -(d * d) / (2.f * sg * sg) - logf(sg) - LOG_SQRT_2PI : 0.f;      // ACM:205
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) lp += __shfl_xor_sync(FULL, lp, o);
+        if (own) {
+            const size_t o = (size_t)n * NA + lane;
+            a.actions_out[o] = act; a.s_act[o] = act; a.s_mu[o] = mu; a.s_sigma[o] = sg;
+        }
+        if (lane == 0) { a.s_logp[n] = lp; a.s_val[n] = v; }
+    }
+    // coalesced copies of the observation rows into the storage (grid-stride over the flat arrays)
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = tid; i < (size_t)a.N * a.O; i += nth) a.s_obs[i] = a.obs[i];
+    for (size_t i = tid; i < (size_t)a.N * a.P; i += nth) a.s_cobs[i] = a.critic_obs[i];
+}
+
 // PPO.process_env_step (ppo.py:186-194): r += gamma * V * time_out; store rewards / dones of step t
 __global__ void process_env_step_kernel(const float *rew, const uint8_t *dones, const uint8_t *time_outs, const float *values, float gamma,
                                         float *s_rew, uint8_t *s_done, int N) {
@@ -779,7 +850,11 @@ __global__ void __launch_bounds__(1024) apply_kernel(const PrepArgs a, float *__
         }
         __threadfence();
         atomicAdd(&c.apply_arrive, 1u);
-        while (*reinterpret_cast<volatile unsigned *>(&c.apply_arrive) < gridDim.x) __nanosleep(32);
+        const long long t0 = clock64();
+        while (*reinterpret_cast<volatile unsigned *>(&c.apply_arrive) < gridDim.x) {
+            if (clock64() - t0 > 4000000000ll) { c.comm_error = 2; break; }   // grid not co-resident (should not happen): never hang the GPU
+            __nanosleep(32);
+        }
         __threadfence();
         if (a.comm_flags == nullptr) s_total = *reinterpret_cast<volatile double *>(&c.sumsq);
         else {
@@ -1082,7 +1157,8 @@ extern "C" int grx_ppo_act(grx_ppo *p, const float *d_obs, const float *d_critic
     CK(stage_rows(p->xa, p->Opad, d_obs, p->O, p->N, st));
     CK(stage_rows(p->xc, p->Ppad, d_critic_obs, p->P, p->N, st));
     const NetIO io[2] = {{&p->actor, p->xa, p->Opad, p->ha, p->da}, {&p->critic, p->xc, p->Ppad, p->hc, p->dc}};
-    mlp_forward(p, io, 2, p->N, 4, st);
+    const bool fused_heads = p->A == 10 && p->critic.dims[4] == 1 && p->actor.dims[3] == HEADS_H && p->critic.dims[3] == HEADS_H;
+    mlp_forward(p, io, 2, p->N, fused_heads ? 3 : 4, st);
     ActArgs a; memset(&a, 0, sizeof(a));
     const size_t row = (size_t)t * p->N;
     a.obs = d_obs; a.critic_obs = d_critic_obs; a.mu = p->ha[3]; a.value = p->hc[3]; a.std = p->params; a.eps = d_eps;
@@ -1090,7 +1166,15 @@ extern "C" int grx_ppo_act(grx_ppo *p, const float *d_obs, const float *d_critic
     a.s_obs = p->s_obs + row * p->O; a.s_cobs = p->s_cobs + row * p->P; a.s_act = p->s_act + row * p->A; a.s_val = p->s_val + row;
     a.s_logp = p->s_logp + row; a.s_mu = p->s_mu + row * p->A; a.s_sigma = p->s_sigma + row * p->A;
     a.N = p->N; a.O = p->O; a.P = p->P; a.A = p->A; a.seed = 0x9E3779B97F4A7C15ull; a.step_index = step_index; a.env_id_offset = 0;
-    act_sample_store_kernel<<<max((p->N + 127) / 128, 592), 128, 0, st>>>(a);
+    if (fused_heads) {
+        ActHeadsArgs q;
+        q.h3a = p->ha[2]; q.h3c = p->hc[2];
+        q.W3a = p->params + p->actor.w[3]; q.b3a = p->params + p->actor.b[3]; q.W3c = p->params + p->critic.w[3]; q.b3c = p->params + p->critic.b[3];
+        q.a = a;
+        act_heads_kernel<10><<<(p->N + 7) / 8 < 1184 ? max((p->N + 7) / 8, 148) : 1184, 256, 0, st>>>(q);
+    } else {
+        act_sample_store_kernel<<<max((p->N + 127) / 128, 592), 128, 0, st>>>(a);
+    }
     CK(cudaGetLastError());
     return GRX_OK;
 }
