@@ -238,3 +238,33 @@ def test_rollout_act_registered_policy_matches_torch(use_tc):
     z = torch.cat(z).flatten()
     assert abs(float(z.mean())) < 0.05 and abs(float(z.std()) - 1.0) < 0.05 and float(z.abs().max()) < 6.0
     alg.close()
+
+
+def test_nan_loss_skips_the_optimiser_step():
+    """ppo.py:297-299: a NaN loss skips backward / step for that minibatch.  Device-side: the fused apply kernel leaves parameters,
+    Adam moments and the step counter untouched (and keeps going on the next finite minibatch)."""
+    from grx_b200.ppo import PPO, ActorCriticMLP
+    tc = make_train_cfg()
+    torch.manual_seed(2)
+    N, T = 128, 8
+    ac = ActorCriticMLP(39, 168, 10, **tc["policy"])
+    alg = PPO(ac, device="cuda:0", **dict(tc["algorithm"], num_mini_batches=2, num_learning_epochs=1))
+    alg.init_storage(N, T)
+    g = torch.Generator().manual_seed(4)
+    for t in range(T):
+        alg.act(torch.randn(N, 39, generator=g).cuda(), torch.randn(N, 168, generator=g).cuda(), eps=torch.randn(N, 10, generator=g).cuda())
+        alg.process_env_step((0.1 * torch.randn(N, generator=g)).cuda(), torch.zeros(N, dtype=torch.bool).cuda(), {})
+    alg.compute_returns(torch.randn(N, 168, generator=g).cuda())
+    before = alg.params.clone()
+    alg.storage.advantages.fill_(float("nan"))
+    alg.update(indices=torch.arange(N * T))
+    torch.cuda.synchronize()
+    st = alg.minibatch_stats()
+    assert st["skip"] == 1 and st["step"] == 0 and st["comm_error"] == 0
+    assert torch.equal(alg.params, before) and float(alg.adam_m.abs().max()) == 0.0
+    alg.storage.advantages.copy_(torch.randn(T, N, 1, generator=g).cuda())
+    alg.update(indices=torch.arange(N * T))
+    torch.cuda.synchronize()
+    st = alg.minibatch_stats()
+    assert st["skip"] == 0 and st["step"] == 2 and not torch.equal(alg.params, before) and bool(torch.isfinite(alg.params).all())
+    alg.close()

@@ -228,16 +228,28 @@ class PPO:
 
     def _open_comm(self):
         """Map every peer's gradient block (cudaIpc over NVLink) so the per-minibatch all-reduce is one of OUR kernels inside the
-        update's CUDA graph instead of an NCCL call from the host loop.  GRX_COMM=nccl keeps the NCCL path."""
+        update's CUDA graph instead of an NCCL call from the host loop.  GRX_COMM=nccl keeps the NCCL path.  If any rank cannot
+        export / map the blocks (no peer access, IPC disabled in the container) every rank falls back to the NCCL path together."""
         import torch.distributed as dist
-        h = (C.c_char * 64)()
-        L.check(self.lib.grx_ppo_comm_handle(self._h, h))
+        import warnings
         rank = dist.get_rank(self.process_group)
+        h = (C.c_char * 64)()
+        ok = self.lib.grx_ppo_comm_handle(self._h, h) == 0
+        err = "" if ok else self.lib.grx_last_error().decode()
         gathered = [None] * self.world_size
-        dist.all_gather_object(gathered, bytes(h.raw), group=self.process_group)
-        L.check(self.lib.grx_ppo_comm_open(self._h, rank, self.world_size, b"".join(gathered)))
-        dist.barrier(group=self.process_group)
-        self._comm = True
+        dist.all_gather_object(gathered, (ok, bytes(h.raw)), group=self.process_group)
+        if all(g[0] for g in gathered):
+            if self.lib.grx_ppo_comm_open(self._h, rank, self.world_size, b"".join(g[1] for g in gathered)) != 0:
+                ok, err = False, self.lib.grx_last_error().decode()
+        else:
+            ok = False
+        flag = torch.tensor([1 if ok else 0], device=self.device, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.process_group)    # also the barrier: every rank has mapped its peers
+        self._comm = bool(int(flag) == 1)
+        if not self._comm:
+            if ok:   # some other rank failed: drop our mappings' use (the C side keeps them until destroy; the graph path is simply not taken)
+                err = "a peer rank could not map the gradient blocks"
+            warnings.warn(f"grx_b200: NVLink peer-memory all-reduce unavailable ({err}); using the NCCL all-reduce path")
 
     def _view(self, name):
         b = L.Buffer()
@@ -339,7 +351,8 @@ class PPO:
     def minibatch_stats(self):
         c = self.ctl.cpu()
         return dict(lr=float(c[0]), skip=int(c[2:3].view(torch.int32)), step=int(c[3:4].view(torch.int32)), kl=float(c[6]),
-                    loss=float(c[7]), value_loss=float(c[8]), surrogate_loss=float(c[9]), grad_norm=float(c[10]))
+                    loss=float(c[7]), value_loss=float(c[8]), surrogate_loss=float(c[9]), grad_norm=float(c[10]),
+                    comm_error=int(c[17:18].view(torch.int32)))   # != 0: a peer flag / grid barrier wait timed out (results invalid)
 
     def act_inference(self, obs):
         obs = obs.to(self.device, torch.float32).contiguous()
