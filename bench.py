@@ -25,6 +25,7 @@ N_PER_GPU, T_STEPS = 4096, 64
 METRIC, UNIT = "env-steps/sec GR1T1 rough-terrain PPO @4096 envs/GPU", "env-steps/s"
 ENV_BYTES_PER_STEP = 1794          # 530 B read + 1264 B written per env-step by the fused env kernel
 FWD_FLOP = 870144                  # per transition, actor + critic forward
+PPO_DRAM_TRAFFIC_PER_MINIBATCH = 3.9e8   # sum of dram__bytes_read + write over gather, 3 fwd, heads, 2 dX, 2 dW, apply (r1k capture)
 ENV_DRAM_TRAFFIC = 3.99e6          # dram__bytes_read.sum + dram__bytes_write.sum per env_step_kernel launch (profiles/r1_env_ncu_summary.txt)
 
 
@@ -281,8 +282,11 @@ def run_ours(args):
                             "(ncu --set full, profiles/): the records stay in L2 between steps.  The kernel is issue/latency-bound (10 substeps "
                             "of articulated dynamics per launch, ~55k warp-instructions per env-step), not bandwidth-bound"}
         roof_ppo = {"kernel": "PPO update (fwd+bwd dense layers, 200 minibatches)", "bound": "tensor", "achieved": ppo_tf, "peak": tf_sus,
-                    "unit": "TFLOP/s", "frac": ppo_tf / tf_sus, "traffic": None, "peak_source": which,
-                    "note": "21.75 MFLOP per transition incl. rollout forward; measured over compute_returns + update"}
+                    "unit": "TFLOP/s", "frac": ppo_tf / tf_sus, "traffic": PPO_DRAM_TRAFFIC_PER_MINIBATCH * 200, "peak_source": which,
+                    "note": "21.75 MFLOP per transition incl. rollout forward; measured over compute_returns + update (TF32 tcgen05 layers: "
+                            "the TF32 tensor peak is half the bf16 denominator used here).  traffic = cold-cache DRAM bytes of the 9 "
+                            "kernels of one minibatch (ncu --set full, profiles/r1k_update_kernels_ncu_summary.txt) x 200; in the "
+                            "replayed graph most of it is served by the 126 MB L2"}
         cb = cpu_port_rate(quick=True) if world == 1 else None
         # our kernels per iteration: per policy step 3 grouped tcgen05 layers + 2 SIMT output heads + act/store + env + storage = 8;
         # compute_returns 6; per minibatch gather + 3 forward + heads + 2 dX + 2 grouped dW + apply = 10 (+ the all-reduce kernel when N > 1)
