@@ -76,6 +76,11 @@ struct Maps {
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// Programmatic dependent launch: a kernel launched with the programmatic-serialization attribute may start while its predecessor in
+// the stream / graph is still draining; everything before pdl_wait() (barrier init, TMEM allocation, descriptor prefetch) overlaps
+// the predecessor's tail, everything after it sees the predecessor's memory.  Both are no-ops for a normal launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok = 0;
@@ -219,6 +224,8 @@ __global__ void __launch_bounds__(NTHREADS_CTA, 1) gemm_tf32_kernel(const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_slot;
+    pdl_wait();                 // the set-up above overlapped the previous kernel's tail; its results are visible from here on
+    pdl_launch_dependents();    // let the next kernel's CTAs queue up behind ours (they block in their own pdl_wait)
     if (tid == 0) stamp(1);
 
     // tile id -> (problem, m0, n0, contraction range); every role walks the same sequence t = blockIdx.x, + gridDim.x, ...
@@ -492,6 +499,22 @@ inline int *forced_tile() {
     }
     return t;
 }
+// cudaLaunchKernelEx wrapper; pdl = launch with the programmatic stream serialization attribute (see pdl_wait)
+inline bool pdl_enabled() {
+    static const int on = [] { const char *e = getenv("GRX_PDL"); return e ? atoi(e) : 1; }();
+    return on != 0;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl && pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 inline int sm_count() {
     static int n = 0;
     if (n == 0) {
@@ -544,8 +567,7 @@ inline cudaError_t launch_cfg(const Problem *ps, int np, const int *splits, cuda
     { static const char *e = getenv("GRX_TC_DEBUG"); grp.dbg = e ? atoi(e) : 0; }
     if (total == 0) return cudaSuccess;
     const int grid = total < sm_count() ? total : sm_count();
-    gemm_tf32_kernel<A_KMAJ, B_KMAJ, EPI, TMT, BN, S><<<grid, NTHREADS_CTA, smem, st>>>(maps, grp);
-    return cudaGetLastError();
+    return launch_kernel(gemm_tf32_kernel<A_KMAJ, B_KMAJ, EPI, TMT, BN, S>, dim3(grid), dim3(NTHREADS_CTA), smem, st, true, maps, grp);
 }
 
 // One launch for `np` (<= MAXP) problems of the same operand layout and epilogue.  The macro tile is picked by a small cost model:

@@ -277,6 +277,7 @@ template <int NA>
 __global__ void __launch_bounds__(256) act_heads_kernel(const ActHeadsArgs q) {
     constexpr int H = 128;
     const ActArgs &a = q.a;
+    tc::pdl_wait();
     const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     const int c0 = lane * 4;
     const bool own = lane < NA;
@@ -432,6 +433,7 @@ struct GatherArgs {
 };
 __global__ void __launch_bounds__(256) gather_kernel(const GatherArgs g) {
     // flat element-parallel copy (a warp-per-row loop leaves the row loads of one warp serialised behind its index load)
+    tc::pdl_launch_dependents();
     const int mb = g.mb_counter ? (*g.mb_counter % g.nmb) : g.mb;
     const int64_t *idx = g.indices + (size_t)mb * g.B;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
@@ -586,6 +588,8 @@ __global__ void __launch_bounds__(HEADS_THREADS, 1) ppo_heads_kernel(const Heads
     __shared__ float acc[NACC];
     for (int i = threadIdx.x; i < NACC; i += blockDim.x) acc[i] = 0.f;
     __syncthreads();
+    tc::pdl_wait();
+    tc::pdl_launch_dependents();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5, nwarps = gridDim.x * wpb;
     const int c0 = lane * 4;
     float4 wa[NA], gWa[NA];
@@ -1171,7 +1175,7 @@ extern "C" int grx_ppo_act(grx_ppo *p, const float *d_obs, const float *d_critic
         q.h3a = p->ha[2]; q.h3c = p->hc[2];
         q.W3a = p->params + p->actor.w[3]; q.b3a = p->params + p->actor.b[3]; q.W3c = p->params + p->critic.w[3]; q.b3c = p->params + p->critic.b[3];
         q.a = a;
-        act_heads_kernel<10><<<(p->N + 7) / 8 < 1184 ? max((p->N + 7) / 8, 148) : 1184, 256, 0, st>>>(q);
+        CK(tc::launch_kernel(act_heads_kernel<10>, dim3((p->N + 7) / 8 < 1184 ? max((p->N + 7) / 8, 148) : 1184), dim3(256), 0, st, true, q));
     } else {
         act_sample_store_kernel<<<max((p->N + 127) / 128, 592), 128, 0, st>>>(a);
     }
@@ -1245,7 +1249,7 @@ static int minibatch_grads(grx_ppo *p, const int64_t *d_indices, int mb, bool de
         a.act = p->mb_act; a.old_mu = p->mb_mu; a.old_sigma = p->mb_sigma; a.old_logp = p->mb_logp; a.adv = p->mb_adv; a.ret = p->mb_ret; a.old_v = p->mb_val;
         a.B = B;
         a.clip = p->cfg.clip_param; a.vcoef = p->cfg.value_loss_coef; a.ecoef = p->cfg.entropy_coef; a.clipped_value = p->cfg.use_clipped_value_loss;
-        ppo_heads_kernel<10><<<148, HEADS_THREADS, 0, st>>>(a);
+        { const cudaError_t e = tc::launch_kernel(ppo_heads_kernel<10>, dim3(148), dim3(HEADS_THREADS), 0, st, true, a); if (e != cudaSuccess && g_launch_err == cudaSuccess) g_launch_err = e; }
         TMARK(4);
         TMARK(5);
         mlp_backward(p, io, 2, gr, B, 2, st);
