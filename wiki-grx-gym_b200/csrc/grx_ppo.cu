@@ -430,10 +430,14 @@ struct GatherArgs {
     int mb, nmb, B, O, P, A, Opad, Ppad;
     const float *s_obs, *s_cobs, *s_act, *s_val, *s_ret, *s_adv, *s_logp, *s_mu, *s_sigma;
     float *xa, *xc, *act, *val, *ret, *adv, *logp, *mu, *sigma;
+    float4 *zero;        // gradient / reduction buffer of the minibatch, cleared here (saves a memset node between apply and gather)
+    int nzero4;
 };
 __global__ void __launch_bounds__(256) gather_kernel(const GatherArgs g) {
     // flat element-parallel copy (a warp-per-row loop leaves the row loads of one warp serialised behind its index load)
+    tc::pdl_wait();                // launched as a programmatic dependent of the previous minibatch's apply kernel
     tc::pdl_launch_dependents();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < g.nzero4; i += gridDim.x * blockDim.x) g.zero[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int mb = g.mb_counter ? (*g.mb_counter % g.nmb) : g.mb;
     const int64_t *idx = g.indices + (size_t)mb * g.B;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
@@ -1223,7 +1227,6 @@ static int minibatch_grads(grx_ppo *p, const int64_t *d_indices, int mb, bool de
     const bool tm = p->timing && !device_counter;
 #define TMARK(i) do { if (tm) cudaEventRecord(p->tev[i], st); } while (0)
     TMARK(0);
-    CK(cudaMemsetAsync(p->reduce_buf, 0, (p->nparam + TAIL) * 4, st));
     GatherArgs g; memset(&g, 0, sizeof(g));
     g.indices = d_indices; g.mb_counter = device_counter ? &p->ctl->mb_counter : nullptr; g.mb = mb; g.nmb = p->cfg.num_mini_batches;
     g.B = B; g.O = p->O; g.P = p->P; g.A = p->A; g.Opad = p->Opad; g.Ppad = p->Ppad;
@@ -1231,7 +1234,8 @@ static int minibatch_grads(grx_ppo *p, const int64_t *d_indices, int mb, bool de
     g.s_logp = p->s_logp; g.s_mu = p->s_mu; g.s_sigma = p->s_sigma;
     g.xa = p->xa; g.xc = p->xc; g.act = p->mb_act; g.val = p->mb_val; g.ret = p->mb_ret; g.adv = p->mb_adv; g.logp = p->mb_logp;
     g.mu = p->mb_mu; g.sigma = p->mb_sigma;
-    gather_kernel<<<148 * 8, 256, 0, st>>>(g);
+    g.zero = reinterpret_cast<float4 *>(p->reduce_buf); g.nzero4 = (int)((p->nparam + TAIL) / 4);
+    { const cudaError_t e = tc::launch_kernel(gather_kernel, dim3(148 * 8), dim3(256), 0, st, true, g); if (e != cudaSuccess && g_launch_err == cudaSuccess) g_launch_err = e; }
     TMARK(1);
     const Net &na = p->actor, &nc = p->critic;
     const bool fused_heads = p->A == 10 && nc.dims[4] == 1 && na.dims[3] == HEADS_H && nc.dims[3] == HEADS_H;   // the registered GRx policy; other shapes take the unfused path
@@ -1283,7 +1287,9 @@ static int minibatch_apply(grx_ppo *p, cudaStream_t st, bool use_comm) {
     a.ctl = p->ctl; a.tail = gsrc + p->nparam; a.std = p->params; a.A = p->A; a.adaptive = p->cfg.adaptive_schedule;
     a.world_size = p->cfg.world_size; a.desired_kl = p->cfg.desired_kl; a.lr_min = p->cfg.learning_rate_min; a.lr_max = p->cfg.learning_rate_max;
     a.max_grad_norm = p->cfg.max_grad_norm; a.vcoef = p->cfg.value_loss_coef; a.ecoef = p->cfg.entropy_coef;
-    apply_kernel<<<p->apply_grid, 1024, 0, st>>>(a, p->params, gsrc, p->adam_m, p->adam_v, (int)p->nparam);
+    // (a normal launch: as a programmatic dependent the 1024-thread blocks queue up behind the last GEMM's CTAs and the grid barrier
+    // then waits on the stragglers — measured slower)
+    CK(tc::launch_kernel(apply_kernel, dim3(p->apply_grid), dim3(1024), 0, st, false, a, p->params, (const float *)gsrc, p->adam_m, p->adam_v, (int)p->nparam));
     CK(cudaGetLastError());
     if (p->timing) {
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -1355,8 +1361,8 @@ extern "C" int grx_ppo_minibatch_apply_comm(grx_ppo *p, void *stream) {
     return minibatch_apply(p, (cudaStream_t)stream, true);
 }
 
-// Whole PPO.update (ppo.py:215-321): one minibatch (grads + apply) is captured once as a CUDA graph whose gather kernel
-// reads the minibatch index from the device control block, then replayed epochs x minibatches times.
+// Whole PPO.update (ppo.py:215-321): one EPOCH (num_mini_batches x [grads + apply]) is captured once as a CUDA graph whose gather
+// kernels read the minibatch index from the device control block, then replayed num_learning_epochs times.
 extern "C" int grx_ppo_update(grx_ppo *p, const int64_t *d_indices, void *stream) {
     if (!p || !d_indices) return grx_set_error(GRX_E_INVALID, "grx_ppo_update: null argument");
     if (p->cfg.world_size > 1 && !p->comm_open)
@@ -1370,8 +1376,11 @@ extern "C" int grx_ppo_update(grx_ppo *p, const int64_t *d_indices, void *stream
         CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
         cudaGraph_t gr;
         CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-        int rc = minibatch_grads(p, d_indices, 0, true, cs);
-        if (!rc) rc = minibatch_apply(p, cs, p->comm_open);
+        int rc = 0;
+        for (int mb = 0; mb < p->cfg.num_mini_batches && !rc; mb++) {   // one graph = one epoch (the gather reads the device-side counter)
+            rc = minibatch_grads(p, d_indices, 0, true, cs);
+            if (!rc) rc = minibatch_apply(p, cs, p->comm_open);
+        }
         cudaError_t ce = cudaStreamEndCapture(cs, &gr);
         cudaStreamDestroy(cs);
         if (rc) return rc;
@@ -1380,8 +1389,7 @@ extern "C" int grx_ppo_update(grx_ppo *p, const int64_t *d_indices, void *stream
         cudaGraphDestroy(gr);
         p->graph_indices = d_indices;
     }
-    const int total = p->cfg.num_learning_epochs * p->cfg.num_mini_batches;
-    for (int i = 0; i < total; i++) CK(cudaGraphLaunch(p->graph, st));
+    for (int i = 0; i < p->cfg.num_learning_epochs; i++) CK(cudaGraphLaunch(p->graph, st));
     return GRX_OK;
 }
 
