@@ -745,7 +745,7 @@ struct Ctl {            // device control block
 // =========================================================================================================
 constexpr int MAXW = 8;
 constexpr int FLAG_READY = 0, FLAG_DONE = MAXW, FLAG_SUMSQ = 2 * MAXW;   // ints; sumsq partials are doubles at int offset 16 (64-byte aligned)
-constexpr int FLAG_INTS = 2 * MAXW + 2 * MAXW;
+
 struct CommDev {
     float *grads[MAXW];
     float *gsum[MAXW];
