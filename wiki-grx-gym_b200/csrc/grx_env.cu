@@ -828,11 +828,11 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 1) env_step_kernel(const _
     float foot_z = 0.f;
     float torso_q[4] = {0, 0, 0, 1};
     if (PHYS) {
-#pragma unroll 1
         // Re-converge the CTA's warps once per substep: the substep is ~60 KB of mostly straight-line code, and with every warp
         // of a scheduler in a different place the instruction caches thrash (ncu: 28 % of warp samples `no_instructions`);
         // aligned warps share the fetched lines (measured 536 -> 445 us per launch).  More barriers per substep cost more than they save.
         const int cta_valid = min(wpc, A.N - (int)blockIdx.x * wpc) * 32;   // threads that did not exit above
+#pragma unroll 1
         for (int deci = 0; deci <= cfg.decimation; deci++) {
             cta_align(A.dbg_M == nullptr ? cta_valid : 0);
             kinematics(s, m, lane);
