@@ -120,6 +120,7 @@ def main():
     scenario("plane_gr1t1", "GR1T1", 32, "plane", steps=10, seed=2)
     scenario("hf_gr1t1", "GR1T1", 32, "heightfield", steps=10, seed=3, rows=3, cols=4)
     scenario("hf_gr1t2_dr", "GR1T2", 32, "heightfield", steps=8, seed=4, rows=3, cols=4)
+    scenario("tm_gr1t1", "GR1T1", 32, "trimesh", steps=8, seed=5, rows=3, cols=4)   # mesh_type = 'trimesh' + curriculum (BASELINE config #5)
 
 
 if __name__ == "__main__":

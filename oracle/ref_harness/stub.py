@@ -115,6 +115,14 @@ class FakeGym:
     def add_triangle_mesh(self, sim, verts, tris, p):
         self.terrain = dict(trimesh=(np.array(verts).reshape(-1, 3), np.array(tris).reshape(-1, 3)),
                             border=-p.transform.p.x, friction=p.static_friction, restitution=p.restitution)
+        # The physics stand-in (like the product) resolves contacts of a trimesh terrain on the heightfield the mesh
+        # was converted from; the caller is LeggedRobot._create_trimesh (legged_robot.py:906-921), whose Terrain object holds it.
+        caller = sys._getframe(1).f_locals.get("self")
+        ter = getattr(caller, "terrain", None)
+        if ter is not None and hasattr(ter, "heightsamples"):
+            self.trimesh_as_heightfield = dict(heights=np.asarray(ter.heightsamples, dtype=np.int16), hscale=ter.cfg.horizontal_scale,
+                                               vscale=ter.cfg.vertical_scale, border=-p.transform.p.x,
+                                               friction=p.static_friction, restitution=p.restitution)
 
     # -- asset
     def load_asset(self, sim, root, file, opts):

@@ -8,7 +8,7 @@ from grx_b200.robot import task_tables
 from grx_b200.urdf import builtin_model
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-ENV_FIXTURES = ["plane64_dec1", "plane_gr1t1", "hf_gr1t1", "hf_gr1t2_dr"]
+ENV_FIXTURES = ["plane64_dec1", "plane_gr1t1", "hf_gr1t1", "hf_gr1t2_dr", "tm_gr1t1"]   # tm = mesh_type "trimesh" (BASELINE config #5)
 
 
 def load_fixture(name):
