@@ -49,3 +49,20 @@ def test_no_cpu_fallback():
     # error convention of the C ABI: negative code + message
     assert _lib.lib().grx_env_get_buffer(None, b"obs", None) == -1
     assert b"null" in _lib.lib().grx_last_error()
+
+
+def test_quat_rotate_inverse_host_helper():
+    """GRXVecEnv.base_lin_vel / base_ang_vel (what play.py logs, play.py:110-123) use a host-side restatement of
+    torch_utils.quat_rotate_inverse (torch_utils.py:72-81): check it against the rotation-matrix form R(q)^T v."""
+    import numpy as np
+    from grx_b200.env import quat_rotate_inverse
+    g = torch.Generator().manual_seed(0)
+    q = torch.randn(64, 4, generator=g, dtype=torch.float64)
+    q = q / q.norm(dim=1, keepdim=True)
+    v = torch.randn(64, 3, generator=g, dtype=torch.float64)
+    x, y, z, w = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    R = torch.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
+                     2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+                     2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], dim=1).view(-1, 3, 3)
+    want = torch.einsum("nji,nj->ni", R, v)
+    np.testing.assert_allclose(quat_rotate_inverse(q, v).numpy(), want.numpy(), atol=1e-12)

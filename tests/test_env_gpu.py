@@ -182,3 +182,28 @@ def test_standing_contact_force_balances_weight():
     assert alive.mean() > 0.7
     np.testing.assert_allclose(fz[alive], mg, rtol=0.15)
     assert abs(mg - 52.83 * 9.81) < 1.0                                               # GR1T1 mass
+
+
+def test_play_py_surface():
+    """Attributes legged_gym/scripts/play.py reads while logging (play.py:110-123): env.dt, dof_pos, dof_vel, torques, commands,
+    base_lin_vel, base_ang_vel, contact_forces[:, feet_indices, 2], cfg.control.action_scale; obs after reset come from get_observations."""
+    from grx_b200.config import make_cfg
+    from grx_b200.env import GRXVecEnv
+    cfg = make_cfg("GR1T1", 16, "plane")
+    env = GRXVecEnv(cfg, sim_device="cuda:0")
+    env.reset()
+    obs = env.get_observations()
+    for _ in range(5):
+        obs, _, rew, dones, infos = env.step(torch.zeros(16, 10, device="cuda"))
+    torch.cuda.synchronize()
+    assert abs(env.dt - 0.02) < 1e-9 and env.cfg.control.action_scale == 1.0
+    for name, shape in (("dof_pos", (16, 10)), ("dof_vel", (16, 10)), ("torques", (16, 10)), ("commands", (16, 3)),
+                        ("base_lin_vel", (16, 3)), ("base_ang_vel", (16, 3)), ("projected_gravity", (16, 3))):
+        t = getattr(env, name)
+        assert tuple(t.shape) == shape and bool(torch.isfinite(t).all()), name
+    fz = env.contact_forces[0, env.feet_indices, 2]
+    assert fz.shape == (2,) and float(env.dof_pos[0, 3].item()) == float(env.dof_pos[0, 3])
+    # obs[3:6] is the base angular velocity the kernel computed one step earlier than the live root state; the gravity direction
+    # of an upright robot is (0, 0, -1) in both
+    up = env.projected_gravity[:, 2] < -0.9
+    assert bool(up.any()) and torch.allclose(env.projected_gravity.norm(dim=1), torch.ones(16, device="cuda"), atol=1e-4)

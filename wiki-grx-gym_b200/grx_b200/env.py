@@ -145,6 +145,15 @@ def task_cfg(cfg, tables, seed=1, env_id_offset=0):
     return t
 
 
+def quat_rotate_inverse(q, v):
+    """isaacgym/torch_utils.py:72-81 (xyzw quaternions): rotate world-frame vectors v [N, 3] into the frames q [N, 4]."""
+    qw, qv = q[:, 3:4], q[:, :3]
+    a = v * (2.0 * qw ** 2 - 1.0)
+    b = torch.cross(qv, v, dim=-1) * qw * 2.0
+    c = qv * (qv * v).sum(-1, keepdim=True) * 2.0
+    return a - b + c
+
+
 class _EpisodeInfo(dict):
     """extras["episode"] (legged_robot.py:420-427) evaluated lazily from one slot of the device accumulator ring:
     building 25 0-d tensors eagerly would cost 25+ launches per step for values that are read once per iteration."""
@@ -313,6 +322,22 @@ class GRXVecEnv:
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # derived base-frame quantities the reference keeps as buffers (legged_robot.py:308-311); play.py logs them (play.py:110-123).
+    # The kernel computes them internally for obs / rewards; here they are evaluated on demand from the live root state.
+    @property
+    def base_lin_vel(self):
+        return quat_rotate_inverse(self.root_states[:, 3:7], self.root_states[:, 7:10])
+
+    @property
+    def base_ang_vel(self):
+        return quat_rotate_inverse(self.root_states[:, 3:7], self.root_states[:, 10:13])
+
+    @property
+    def projected_gravity(self):
+        g = torch.zeros(self.num_envs, 3, device=self.device)
+        g[:, 2] = -1.0
+        return quat_rotate_inverse(self.root_states[:, 3:7], g)
 
     @property
     def episode_length_buf(self):
