@@ -185,6 +185,7 @@ def run_ours(args):
     dev = f"cuda:{local}"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line (NCCL prints its version banner there otherwise)
         dist.init_process_group("nccl", device_id=torch.device(dev))
     n_total = N_PER_GPU * world
     torch.manual_seed(1)
