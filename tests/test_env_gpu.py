@@ -207,3 +207,31 @@ def test_play_py_surface():
     # of an upright robot is (0, 0, -1) in both
     up = env.projected_gravity[:, 2] < -0.9
     assert bool(up.any()) and torch.allclose(env.projected_gravity.norm(dim=1), torch.ones(16, device="cuda"), atol=1e-4)
+
+
+def test_trimesh_entry_accepts_only_the_structured_conversion():
+    """grx_env_set_terrain_trimesh (gym.add_triangle_mesh, legged_robot.py:903-924): the mesh must be the reference's structured
+    conversion of the heightfield (terrain_utils.py:286-350); anything else is rejected with GRX_E_INVALID."""
+    import ctypes as C
+    from grx_b200 import _lib as L
+    from grx_b200.config import make_cfg
+    from grx_b200.env import GRXVecEnv
+    from grx_b200.terrain import heightfield_to_trimesh
+    cfg = make_cfg("GR1T1", 16, "trimesh")
+    cfg.terrain.num_rows, cfg.terrain.num_cols, cfg.terrain.max_init_terrain_level = 2, 2, 1
+    env = GRXVecEnv(cfg, sim_device="cuda:0")                       # goes through the trimesh entry with the Terrain's own mesh
+    env.reset()
+    for _ in range(3):
+        env.step(torch.zeros(16, 10, device="cuda"))
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(env.obs_buf).all())
+    hs = np.ascontiguousarray(env.terrain.heightsamples, np.int16)
+    v, t = heightfield_to_trimesh(hs, 0.1, 0.005, 0.75)
+    args = lambda vv, tt: (env._h, vv.ctypes.data_as(L.PF), vv.shape[0], tt.ctypes.data_as(C.POINTER(C.c_uint32)), tt.shape[0],
+                           hs.ctypes.data_as(C.POINTER(C.c_int16)), hs.shape[0], hs.shape[1], C.c_float(0.1), C.c_float(0.005),
+                           C.c_float(25.0), C.c_float(1.0), C.c_float(0.0))
+    assert env.lib.grx_env_set_terrain_trimesh(*args(v, t)) == 0
+    assert env.lib.grx_env_set_terrain_trimesh(*args(v[:-1].copy(), t)) == -1                     # wrong vertex count
+    bad = v.copy(); bad[5, 2] += 0.5                                                              # a vertex off the heightfield
+    assert env.lib.grx_env_set_terrain_trimesh(*args(bad, t)) == -1
+    assert b"does not match" in env.lib.grx_last_error()

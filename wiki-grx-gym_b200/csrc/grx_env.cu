@@ -14,6 +14,7 @@
 // Topology handled by this kernel: floating base + 2 serial chains of 5 revolute joints (the registered lower-limb
 // GR1T1 / GR1T2 tasks); grx_env_create rejects anything else.
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -1343,6 +1344,28 @@ extern "C" int grx_env_set_terrain_heightfield(grx_env *e, const int16_t *sample
     e->terrain.hscale = hscale; e->terrain.vscale = vscale; e->terrain.border = border;
     e->terrain.friction = friction; e->terrain.restitution = restitution;
     return GRX_OK;
+}
+
+// Replaces gym.add_triangle_mesh (legged_robot.py:903-924).  The mesh the reference uploads is the structured conversion of its
+// heightfield (terrain_utils.convert_heightfield_to_trimesh: one vertex per sample, two triangles per cell, steep-edge vertices
+// snapped sideways by one cell); contacts are resolved on that heightfield (cells split along the mesh's diagonal),
+// so the entry checks that the mesh IS such a conversion of `samples` and rejects arbitrary meshes.
+extern "C" int grx_env_set_terrain_trimesh(grx_env *e, const float *vertices, int32_t nv, const uint32_t *triangles, int32_t nt,
+                                           const int16_t *samples, int32_t rows, int32_t cols, float hscale, float vscale, float border,
+                                           float friction, float restitution) {
+    if (!e || !vertices || !triangles || !samples || rows < 2 || cols < 2)
+        return grx_set_error(GRX_E_INVALID, "grx_env_set_terrain_trimesh: bad arguments");
+    if ((long long)nv != (long long)rows * cols || (long long)nt != 2ll * (rows - 1) * (cols - 1))
+        return grx_set_error(GRX_E_INVALID, "grx_env_set_terrain_trimesh: not the structured conversion of the heightfield (need nv == rows*cols, nt == 2(rows-1)(cols-1))");
+    for (long long i = 0; i < (long long)nv; i++) {
+        const float z = vertices[3 * i + 2], want = (float)samples[i] * vscale;
+        const float x0 = (float)(i / cols) * hscale, y0 = (float)(i % cols) * hscale;
+        if (fabsf(z - want) > 1e-4f + 1e-6f * fabsf(want) || fabsf(vertices[3 * i] - x0) > 1.001f * hscale || fabsf(vertices[3 * i + 1] - y0) > 1.001f * hscale)
+            return grx_set_error(GRX_E_INVALID, "grx_env_set_terrain_trimesh: vertex " + std::to_string(i) + " does not match the heightfield sample grid");
+    }
+    for (int k = 0; k < 6 && k < 3 * nt; k++)
+        if (triangles[k] >= (uint32_t)nv) return grx_set_error(GRX_E_INVALID, "grx_env_set_terrain_trimesh: triangle index out of range");
+    return grx_env_set_terrain_heightfield(e, samples, rows, cols, hscale, vscale, border, friction, restitution);
 }
 
 extern "C" int grx_env_set_params(grx_env *e, const float *friction, const float *restitution, const float *motor_strength,

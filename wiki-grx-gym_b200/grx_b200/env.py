@@ -271,9 +271,21 @@ class GRXVecEnv:
         tc = cfg.terrain
         if rough:
             hs = np.ascontiguousarray(terrain["heights"], np.int16)
-            L.check(self.lib.grx_env_set_terrain_heightfield(self._h, hs.ctypes.data_as(C.POINTER(C.c_int16)), hs.shape[0], hs.shape[1],
-                                                             C.c_float(tc.horizontal_scale), C.c_float(tc.vertical_scale),
-                                                             C.c_float(tc.border_size), C.c_float(tc.static_friction), C.c_float(tc.restitution)))
+            scal = (C.c_float(tc.horizontal_scale), C.c_float(tc.vertical_scale), C.c_float(tc.border_size),
+                    C.c_float(tc.static_friction), C.c_float(tc.restitution))
+            if tc.mesh_type == "trimesh":                                               # legged_robot.py:903-924 (_create_trimesh)
+                if self.terrain is not None and getattr(self.terrain, "vertices", None) is not None:
+                    verts, tris = self.terrain.vertices, self.terrain.triangles
+                else:
+                    from .terrain import heightfield_to_trimesh
+                    verts, tris = heightfield_to_trimesh(hs, tc.horizontal_scale, tc.vertical_scale, tc.slope_treshold)
+                verts = np.ascontiguousarray(verts, np.float32)
+                tris = np.ascontiguousarray(tris, np.uint32)
+                L.check(self.lib.grx_env_set_terrain_trimesh(self._h, verts.ctypes.data_as(L.PF), verts.shape[0],
+                                                             tris.ctypes.data_as(C.POINTER(C.c_uint32)), tris.shape[0],
+                                                             hs.ctypes.data_as(C.POINTER(C.c_int16)), hs.shape[0], hs.shape[1], *scal))
+            else:
+                L.check(self.lib.grx_env_set_terrain_heightfield(self._h, hs.ctypes.data_as(C.POINTER(C.c_int16)), hs.shape[0], hs.shape[1], *scal))
         else:
             L.check(self.lib.grx_env_set_terrain_plane(self._h, C.c_float(tc.static_friction), C.c_float(tc.restitution)))
         fr, p_fr = _f32p(params["friction"]); rs, p_rs = _f32p(params["restitution"])
