@@ -106,6 +106,10 @@ int grx_version(void);
 /* sizeof() of {grx_buffer, grx_model_desc, grx_task_cfg, grx_injected_physics, grx_ppo_cfg}, for FFI bindings to self-check their layouts */
 int grx_abi_sizes(int32_t *out, int32_t n);
 
+/* Launch accounting (bench.py's `gpu_launches`): kernels this library has launched in the calling process so far; a CUDA-graph
+ * replay counts its kernel nodes. */
+uint64_t grx_debug_launch_count(void);
+
 /* ---- environment -------------------------------------------------------------------------------------------- */
 int grx_env_create(const grx_model_desc *model, const grx_task_cfg *cfg, int32_t num_envs, int32_t device, grx_env **out);
 int grx_env_destroy(grx_env *env);
@@ -178,6 +182,12 @@ int grx_env_step_host(grx_env *env, const float *h_actions, float delay, int32_t
  * of env `index` for its current state, computed by the same device code the step uses.  Host output pointers. */
 int grx_env_debug_dynamics(grx_env *env, int32_t index, float *h_M, float *h_h);
 
+/* Debug / parity: export, for every env and substep of the following steps, the ACTIVE-SET SIGNATURE of the dynamics (a 64-bit hash of
+ * the discrete decisions: which contact spheres were accepted, the terrain triangle under each, the restitution branch, which joint
+ * limits were active and on which side) into the device buffer "active_sig" [N, 16] u64.  oracle/phys_impl.h computes the same hash, so a
+ * row that differs from the oracle beyond rounding can be attributed to a differing decision (contact-threshold flip) or flagged. */
+int grx_env_debug_active_sig(grx_env *env, int32_t enable);
+
 #define GRX_RNG_K 68 /* == grx_b200/rng_layout.py K */
 
 /* ---- PPO ---------------------------------------------------------------------------------------------------- */
@@ -192,6 +202,11 @@ typedef struct {
     float init_noise_std;
     int32_t use_tensor_cores;                /* 1: tcgen05 kind::tf32 GEMMs for the dense layers, 0: fp32 SIMT GEMMs */
     int32_t world_size;                      /* gradient / KL sums are divided by this after the caller's all-reduce */
+    int32_t env_id_offset;                   /* global index of local env 0: the rollout's Normal.sample() stream is keyed by
+                                              * (seed, global env id, step) so W shards draw what one GPU with all envs would */
+    int32_t comm_timeout_ms;                 /* NVLink all-reduce: give up waiting for a peer after this long (0 = 10000) and report
+                                              * through the control block (`comm_error`); the optimiser step is then NOT applied */
+    uint64_t seed;                           /* Philox key of the action noise (fast mode, d_eps == NULL); the task seed */
 } grx_ppo_cfg;
 
 typedef struct grx_ppo grx_ppo;
@@ -200,7 +215,9 @@ int grx_ppo_create(const grx_ppo_cfg *cfg, int32_t device, grx_ppo **out);
 int grx_ppo_destroy(grx_ppo *ppo);
 /* views: params grads adam_m adam_v (flat, reference state_dict order: std, actor.model.{0,2,4,6}.{weight,bias},
  * critic...), obs critic_obs actions values rewards dones actions_log_prob mu sigma returns advantages,
- * lr kl_mean stats (device scalars), reduce_buf (grads + [kl_sum, count, nan] tail; what the caller all-reduces) */
+ * reduce_buf (grads + [kl_sum, count, surrogate_sum, value_loss_sum] tail; what the caller all-reduces), gsum, adv_moments,
+ * ctl (device control block: lr, clip coefficient, skip, Adam step, ..., comm_error), mb_log [epochs*minibatches, 4] =
+ * (mean KL, learning rate, loss, gradient norm) of every minibatch of the most recent update (ppo.py:262-268, 308-309) */
 int grx_ppo_get_buffer(grx_ppo *ppo, const char *name, grx_buffer *out);
 /* PPO.act (ppo.py:144-171) for rollout step t: actor+critic forward, a = mu + sigma*eps, log-prob; everything stored
  * into row t of the rollout storage (base_storage.py:80-100).  d_eps [N, A] standard normal draws or NULL (Philox). */

@@ -165,6 +165,7 @@ class EnvOracle:
         out = self.phys.step(root, q, qd, actions.numpy(), self.last_actions.numpy(), float(delay), self.motor_strength,
                              self.base_inertial, self.friction, self.restitution)
         t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+        self.last_active_sig = out["active_sig"]          # [N, decimation] uint64 (compared with the CUDA kernel's by the parity tests)
         return dict(torques=t(out["torques"]), foot_state=t(out["link_state"][:, self.feet]),
                     torso_quat=t(out["link_state"][:, self.torso[0], 3:7]),
                     contact_forces=t(out["contact_force"]), avg_feet_contact_force=t(out["avg_foot_force"]),
@@ -201,6 +202,7 @@ class EnvOracle:
         cfg, N, dt = self.cfg, self.N, self.dt
         rw = cfg.rewards
         contact_forces = ph["contact_forces"]
+        self.contact_forces = contact_forces            # kept for the parity tests (net_contact_force tensor, LR:267)
         self.torques = ph["torques"]
         self.common_step_counter += 1                                                  # LR:281-282
         self.episode_length_buf += 1

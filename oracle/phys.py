@@ -131,13 +131,15 @@ class PhysOracle:
         out = dict(torques=np.zeros((N, self.nd), r), link_state=np.zeros((N, self.nl, 13), r),
                    contact_force=np.zeros((N, self.nl, 3), r), avg_foot_force=np.zeros((N, self.nf), r),
                    avg_foot_linvel=np.zeros((N, self.nf, 3), r), avg_foot_angvel=np.zeros((N, self.nf, 3), r))
-        fn = getattr(lib(), "grx_oracle_physics_step" + self.sfx)
+        out["active_sig"] = np.zeros((N, int(self.sim["decimation"])), np.uint64)   # active-set signature per substep (phys_impl.h substep)
+        fn = getattr(lib(), "grx_oracle_physics_step_sig" + self.sfx)
         fn.restype = C.c_int
         err = fn(C.byref(self.m), C.byref(self.t), C.byref(self.s), C.c_int(N), self._p(root), self._p(dof_pos),
                  self._p(dof_vel), self._p(actions), self._p(last_actions), self.real(delay), self._p(motor_strength),
                  self._p(base_inertial), self._p(friction), self._p(restitution), self._p(out["torques"]),
                  self._p(out["link_state"]), self._p(out["contact_force"]), self._p(out["avg_foot_force"]),
-                 self._p(out["avg_foot_linvel"]), self._p(out["avg_foot_angvel"]))
+                 self._p(out["avg_foot_linvel"]), self._p(out["avg_foot_angvel"]),
+                 out["active_sig"].ctypes.data_as(C.POINTER(C.c_uint64)))
         if err:
             raise RuntimeError(f"physics oracle failed (code {err})")
         return out

@@ -113,8 +113,15 @@ static inline void FN(axang2mat)(const REAL *a, REAL th, REAL *R) {
 /* ---- terrain query: height and unit normal of the piecewise-linear surface under (x, y).
  * Heightfield cells are split along the (i,j)-(i+1,j+1) diagonal, the same split the
  * reference's trimesh conversion uses (isaacgym/terrain_utils.py:333-348). */
-static inline void FN(terrain_query)(const FN(Terrain) *t, REAL x, REAL y, REAL *h, REAL *n) {
-    if (t->type == 0) { *h = 0; n[0] = 0; n[1] = 0; n[2] = 1; return; }
+/* splitmix64 finaliser: item hash of the active-set signature (same function in grx_env.cu) */
+static inline unsigned long long FN(mix64)(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+static inline void FN(terrain_query)(const FN(Terrain) *t, REAL x, REAL y, REAL *h, REAL *n, int *cell) {
+    if (t->type == 0) { *h = 0; n[0] = 0; n[1] = 0; n[2] = 1; cell[0] = cell[1] = cell[2] = 0; return; }
     REAL gx = (x + t->border) / t->hscale, gy = (y + t->border) / t->hscale;
     REAL fi = FLOOR(gx), fj = FLOOR(gy);
     int i = (int)fi, j = (int)fj;
@@ -127,6 +134,7 @@ static inline void FN(terrain_query)(const FN(Terrain) *t, REAL x, REAL y, REAL 
     REAL dhx, dhy;
     if (fx >= fy) { dhx = h10 - h00; dhy = h11 - h10; }
     else          { dhx = h11 - h01; dhy = h01 - h00; }
+    cell[0] = i; cell[1] = j; cell[2] = fx >= fy ? 0 : 1;
     *h = h00 + dhx * fx + dhy * fy;
     REAL sx = -dhx / t->hscale, sy = -dhy / t->hscale;
     REAL inv = 1 / SQRT(sx * sx + sy * sy + 1);
@@ -301,9 +309,15 @@ typedef struct {
     int count;
 } FN(Contacts);
 
-/* One dt: state (root, q, qd) advanced in place given joint torques tau.  cf_out[nl*3] = net contact force per URDF link. */
+/* One dt: state (root, q, qd) advanced in place given joint torques tau.  cf_out[nl*3] = net contact force per URDF link.
+ * sig (nullable): ACTIVE-SET SIGNATURE of the substep = wrapping sum of mix64(item) over the discrete decisions the step takes:
+ *   per accepted contact  item = 1<<56 | sphere s | cell i << 6 | cell j << 18 | triangle << 30 | bounce branch << 31 | y-tangent << 32
+ *   per joint-limit row   item = 2<<56 | joint j | (upper ? 1 : 0) << 6
+ * Two implementations that took the same decisions must agree to rounding; a differing signature explains a differing row
+ * (tests/test_env_gpu.py::test_full_step_matches_oracle). */
 static int FN(substep)(const FN(Model) *M, const FN(Terrain) *T, const FN(SimCfg) *cfg, const REAL *binert, REAL mu_env, REAL rest_env,
-                       REAL *root, REAL *q, REAL *qd, const REAL *tau, const FN(Kin) *K, REAL *cf_out) {
+                       REAL *root, REAL *q, REAL *qd, const REAL *tau, const FN(Kin) *K, REAL *cf_out, unsigned long long *sig) {
+    unsigned long long sg = 0;
     const int nd = M->nd, nv = nd + 6;
     const REAL dt = cfg->dt;
     REAL Mq[MAXV * MAXV], h[MAXV], u[MAXV], rhs[MAXV];
@@ -322,16 +336,18 @@ static int FN(substep)(const FN(Model) *M, const FN(Terrain) *T, const FN(SimCfg
     for (int s = 0; s < M->ns && C.count < cfg->max_contacts; s++) {
         int b = M->sph_body[s];
         REAL xs[3], hgt, n[3];
+        int cell[3];
         FN(m3v)(K->R[b], M->sph_pos + 3 * s, xs);
         for (int k = 0; k < 3; k++) xs[k] += K->o[b][k];
-        FN(terrain_query)(T, xs[0], xs[1], &hgt, n);
+        FN(terrain_query)(T, xs[0], xs[1], &hgt, n, cell);
         REAL d = (xs[2] - hgt) * n[2] - M->sph_rad[s];
         if (!(d < cfg->contact_offset)) continue;
         int c = C.count++;
         C.link[c] = M->sph_link[s];
         REAL xc[3] = {xs[0] - n[0] * M->sph_rad[s], xs[1] - n[1] * M->sph_rad[s], xs[2] - n[2] * M->sph_rad[s]};
         /* tangent frame: t1 = normalised projection of world x (or y if n ~ x) */
-        const REAL *e = (n[0] > (REAL)0.9 || n[0] < (REAL)-0.9) ? ey : ex;
+        const int usey = (n[0] > (REAL)0.9 || n[0] < (REAL)-0.9);
+        const REAL *e = usey ? ey : ex;
         REAL dn = FN(v3dot)(e, n), t1[3] = {e[0] - dn * n[0], e[1] - dn * n[1], e[2] - dn * n[2]};
         REAL inv = 1 / SQRT(FN(v3dot)(t1, t1)); for (int k = 0; k < 3; k++) t1[k] *= inv;
         REAL t2[3]; FN(v3cross)(n, t1, t2);
@@ -344,7 +360,10 @@ static int FN(substep)(const FN(Model) *M, const FN(Terrain) *T, const FN(SimCfg
         REAL target;
         if (d > 0) target = -d / dt;
         else { target = -d * cfg->erp / dt; if (target > cfg->max_depen_vel) target = cfg->max_depen_vel; }
-        if (vn0 < -cfg->bounce_threshold && -rest * vn0 > target) target = -rest * vn0;
+        const int bounce = (vn0 < -cfg->bounce_threshold && -rest * vn0 > target);
+        if (bounce) target = -rest * vn0;
+        sg += FN(mix64)((1ull << 56) | (unsigned long long)s | ((unsigned long long)cell[0] << 6) | ((unsigned long long)cell[1] << 18) |
+                        ((unsigned long long)cell[2] << 30) | ((unsigned long long)bounce << 31) | ((unsigned long long)usey << 32));
         bias[3 * c] = target; bias[3 * c + 1] = 0; bias[3 * c + 2] = 0;
     }
     int nrows = 3 * C.count;
@@ -361,6 +380,7 @@ static int FN(substep)(const FN(Model) *M, const FN(Terrain) *T, const FN(SimCfg
             for (int i = 0; i < nv; i++) J[r][i] = 0;
             J[r][j] = sgn; bias[r] = tgt;
             lim_joint[nlim] = j; lim_sign[nlim] = sgn; lim_lam[nlim] = 0; nlim++;
+            sg += FN(mix64)((2ull << 56) | (unsigned long long)j | ((unsigned long long)(sgn < 0 ? 1 : 0) << 6));
         }
     }
     int ntot = nrows + nlim;
@@ -393,6 +413,7 @@ static int FN(substep)(const FN(Model) *M, const FN(Terrain) *T, const FN(SimCfg
         }
     }
     (void)lim_joint; (void)lim_sign;
+    if (sig) *sig = sg;
     /* ---- contact force report (impulse / dt), per URDF link, world frame, force ON the body */
     for (int i = 0; i < M->nl * 3; i++) cf_out[i] = 0;
     for (int c = 0; c < C.count; c++)
@@ -440,12 +461,12 @@ static void FN(link_state)(const FN(Model) *M, const FN(Kin) *K, int l, REAL *ou
  *   outputs: torques (last substep), link_state [N,nl,13] and contact_force [N,nl,3] after the last substep,
  *            avg_foot_force [N,nf], avg_foot_linvel / avg_foot_angvel [N,nf,3] (means of |.| over substeps, FF:79-88)
  */
-int FN(grx_oracle_physics_step)(const FN(Model) *M, const FN(Terrain) *T, const FN(SimCfg) *cfg, int N,
+static int FN(physics_step_impl)(const FN(Model) *M, const FN(Terrain) *T, const FN(SimCfg) *cfg, int N,
                                 REAL *root, REAL *dof_pos, REAL *dof_vel,
                                 const REAL *actions, const REAL *last_actions, REAL delay,
                                 const REAL *motor_strength, const REAL *base_inertial, const REAL *friction, const REAL *restitution,
                                 REAL *torques, REAL *link_state, REAL *contact_force,
-                                REAL *avg_foot_force, REAL *avg_foot_linvel, REAL *avg_foot_angvel) {
+                                REAL *avg_foot_force, REAL *avg_foot_linvel, REAL *avg_foot_angvel, unsigned long long *active_sig) {
     const int nd = M->nd, nl = M->nl, nf = M->nf;
     int err = 0;
     if (M->nb > MAXB || nd + 6 > MAXV || cfg->max_contacts > MAXC) return 2;
@@ -467,7 +488,8 @@ int FN(grx_oracle_physics_step)(const FN(Model) *M, const FN(Terrain) *T, const 
                 if (t > lim) t = lim; if (t < -lim) t = -lim;
                 tq[j] = t;
             }
-            err |= FN(substep)(M, T, cfg, bin, friction[e], restitution[e], rt, q, qd, tq, &K, cf);
+            err |= FN(substep)(M, T, cfg, bin, friction[e], restitution[e], rt, q, qd, tq, &K, cf,
+                               active_sig ? active_sig + (size_t)e * cfg->decimation + deci : (unsigned long long *)0);
             FN(kinematics)(M, bin, rt, q, qd, &K);
             for (int f = 0; f < nf; f++) {
                 int l = M->foot_links[f];
@@ -488,6 +510,27 @@ int FN(grx_oracle_physics_step)(const FN(Model) *M, const FN(Terrain) *T, const 
     return err;
 }
 
+int FN(grx_oracle_physics_step)(const FN(Model) *M, const FN(Terrain) *T, const FN(SimCfg) *cfg, int N,
+                                REAL *root, REAL *dof_pos, REAL *dof_vel,
+                                const REAL *actions, const REAL *last_actions, REAL delay,
+                                const REAL *motor_strength, const REAL *base_inertial, const REAL *friction, const REAL *restitution,
+                                REAL *torques, REAL *link_state, REAL *contact_force,
+                                REAL *avg_foot_force, REAL *avg_foot_linvel, REAL *avg_foot_angvel) {
+    return FN(physics_step_impl)(M, T, cfg, N, root, dof_pos, dof_vel, actions, last_actions, delay, motor_strength, base_inertial, friction,
+                                 restitution, torques, link_state, contact_force, avg_foot_force, avg_foot_linvel, avg_foot_angvel,
+                                 (unsigned long long *)0);
+}
+/* same, also reporting the active-set signature of every substep: active_sig [N, decimation] */
+int FN(grx_oracle_physics_step_sig)(const FN(Model) *M, const FN(Terrain) *T, const FN(SimCfg) *cfg, int N,
+                                    REAL *root, REAL *dof_pos, REAL *dof_vel,
+                                    const REAL *actions, const REAL *last_actions, REAL delay,
+                                    const REAL *motor_strength, const REAL *base_inertial, const REAL *friction, const REAL *restitution,
+                                    REAL *torques, REAL *link_state, REAL *contact_force,
+                                    REAL *avg_foot_force, REAL *avg_foot_linvel, REAL *avg_foot_angvel, unsigned long long *active_sig) {
+    return FN(physics_step_impl)(M, T, cfg, N, root, dof_pos, dof_vel, actions, last_actions, delay, motor_strength, base_inertial, friction,
+                                 restitution, torques, link_state, contact_force, avg_foot_force, avg_foot_linvel, avg_foot_angvel, active_sig);
+}
+
 /* One simulate() call (dt) with given joint torques for N envs: what FakeGym.simulate() of the reference
  * harness calls (oracle/ref_harness), i.e. the stand-in for gym.simulate + refresh_* (legged_robot_fftai.py:67-76). */
 int FN(grx_oracle_substep)(const FN(Model) *M, const FN(Terrain) *T, const FN(SimCfg) *cfg, int N,
@@ -504,7 +547,7 @@ int FN(grx_oracle_substep)(const FN(Model) *M, const FN(Terrain) *T, const FN(Si
         REAL cf[MAXB * 4 * 3];
         FN(Kin) K;
         FN(kinematics)(M, bin, rt, q, qd, &K);
-        err |= FN(substep)(M, T, cfg, bin, friction[e], restitution[e], rt, q, qd, tau + nd * e, &K, cf);
+        err |= FN(substep)(M, T, cfg, bin, friction[e], restitution[e], rt, q, qd, tau + nd * e, &K, cf, (unsigned long long *)0);
         FN(kinematics)(M, bin, rt, q, qd, &K);
         for (int l = 0; l < nl; l++) {
             FN(link_state)(M, &K, l, link_state + (size_t)(e * nl + l) * 13);

@@ -54,3 +54,20 @@ def init_state(fx):
 def step_items(fx, t, group):
     pre = f"step{t:02d}/{group}/"
     return {k[len(pre):]: v for k, v in fx.items() if k.startswith(pre)}
+
+
+def wide_inputs(seed, N, T, O, P, A):
+    """Inputs of the registered-width fixture, regenerated (not stored) by the test from the same CPU generator stream; the fixture keeps
+    a SHA-256 of them so that a drifting generator fails loudly instead of silently comparing different rollouts."""
+    import hashlib
+    import torch
+    g = torch.Generator().manual_seed(seed + 100)
+    d = dict(eps=torch.randn(T, N, A, generator=g), obs=torch.randn(T, N, O, generator=g), critic_obs=torch.randn(T, N, P, generator=g),
+             rewards=0.1 * torch.randn(T, N, generator=g), dones=torch.rand(T, N, generator=g) < 0.05)
+    d["time_outs"] = d["dones"] & (torch.rand(T, N, generator=g) < 0.5)
+    d["last_critic_obs"] = torch.randn(N, P, generator=g)
+    d["indices"] = torch.randperm(N * T, generator=g)
+    h = hashlib.sha256()
+    for k in sorted(d):
+        h.update(d[k].numpy().tobytes())
+    return d, h.hexdigest()

@@ -8,6 +8,8 @@ POST_TOL = dict(rtol=1e-5, atol=3e-6)
 # full step incl. 10 substeps of our dynamics spec: CUDA fp32 (Delassus-space PGS, branch-sparse Cholesky, fused multiply-add)
 # vs the C oracle in fp32 (velocity-space PGS, dense Cholesky, no contraction) — same equations, different rounding
 PHYS_TOL = dict(rtol=2e-3, atol=2e-3)
+PHYS_VEL_TOL = dict(rtol=5e-3, atol=5e-3)       # joint rates (rad/s, magnitudes up to ~10): velocity-level solve output
+PHYS_FORCE_TOL = dict(rtol=2e-2, atol=0.5)      # net contact forces (N, magnitudes ~500): impulse / dt of a 4-sweep PGS
 
 
 def make_gpu_env(fx, **kw):

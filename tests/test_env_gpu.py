@@ -10,7 +10,7 @@ import pytest
 import torch
 
 from golden_util import ENV_FIXTURES, load_fixture, step_items
-from parity_util import PHYS_TOL, POST_TOL, make_gpu_env
+from parity_util import PHYS_FORCE_TOL, PHYS_TOL, PHYS_VEL_TOL, POST_TOL, make_gpu_env
 
 pytestmark = pytest.mark.gpu
 
@@ -66,35 +66,67 @@ def test_post_physics_matches_reference(name):
     assert n_reset >= 3
 
 
-@pytest.mark.parametrize("name", ENV_FIXTURES)
-def test_full_step_matches_oracle(name):
-    """The whole fused step (PD torque -> dynamics -> contact -> integrate x decimation -> post-physics) vs the golden
-    trajectory, restarted from the golden state before every step so fp32 rounding does not accumulate chaotically."""
+def _full_step_compare(name, report):
+    """Teacher-forced whole fused step (PD torque -> dynamics -> contact -> integrate x decimation -> post-physics) vs the C oracle run
+    live on the same golden state, with ACTIVE-SET ATTRIBUTION: both sides export, per env and substep, a hash of the discrete decisions
+    of the dynamics (accepted contact spheres, terrain triangle under each, restitution branch, active joint limits).
+      * envs whose signatures agree on every substep took the same decisions: every output must agree within the stated fp32 tolerance;
+      * envs whose signatures differ made a different contact / limit decision at a threshold (legitimate under different rounding:
+        Delassus-space vs velocity-space PGS, sparse vs dense Cholesky, FMA contraction): they are COUNTED and bounded, not compared.
+    No env may differ without a differing signature."""
+    from golden_util import init_state
+    from parity_util import make_oracle_env
     fx = load_fixture(name)
     env = make_gpu_env(fx)[0]
-    dev = env.device
-    N = env.num_envs
-    bad_rows = 0
+    ora = make_oracle_env(fx)
+    sig = env.debug_active_sig(True)
+    dev, N, dec = env.device, env.num_envs, int(fx["meta/decimation"])
+    n_flip = 0
     for t in range(int(fx["meta/steps"])):
         pre = f"step{t:02d}/"
-        if t > 0:
-            env.load_state(step_items(fx, t - 1, "state"))
-        U = torch.from_numpy(fx[pre + "U"]).to(dev)
-        obs, pri, rew, reset, _ = env.step(torch.from_numpy(fx[pre + "actions"]).to(dev), U=U, delay=float(fx[pre + "delay"]))
+        st = init_state(fx) if t == 0 else step_items(fx, t - 1, "state")
+        env.load_state(st); ora.load_state(st)
+        a, U, delay = fx[pre + "actions"], fx[pre + "U"], float(fx[pre + "delay"])
+        obs, pri, rew, reset, _ = env.step(torch.from_numpy(a).to(dev), U=torch.from_numpy(U).to(dev), delay=delay)
         torch.cuda.synchronize()
-        out, ph = step_items(fx, t, "out"), step_items(fx, t, "phys")
-        # contact on/off decisions near a threshold may legitimately flip under different rounding: tolerate a few envs
-        ok = np.ones(N, bool)
-        ok &= reset.cpu().numpy() == out["reset_buf"].astype(bool)
-        ok &= np.isclose(env.torques.cpu().numpy(), out["torques"], **PHYS_TOL).all(1)
-        ok &= np.isclose(obs.cpu().numpy(), out["obs_buf"], **PHYS_TOL).all(1)
-        ok &= np.isclose(pri.cpu().numpy(), out["pri_obs_buf"], rtol=5e-3, atol=5e-3).all(1)
-        ok &= np.isclose(rew.cpu().numpy(), out["rew_buf"], **PHYS_TOL)
-        cf = env.contact_forces.cpu().numpy()
-        ok &= np.isclose(cf, ph["contact_forces"], rtol=2e-2, atol=0.5).all((1, 2))
-        bad_rows += int((~ok).sum())
-        assert (~ok).sum() <= max(1, N // 16), f"{name} t={t}: {(~ok).sum()} of {N} envs differ: {np.nonzero(~ok)[0]}"
-    assert bad_rows <= int(fx["meta/steps"]) * max(1, N // 32)
+        o_obs, o_pri, o_rew, o_reset, _ = ora.step(a, U, delay)
+        same = (sig[:, :dec].cpu().numpy().view(np.uint64) == ora.last_active_sig).all(1)
+        n_flip += int((~same).sum())
+        msg = f"{name} t={t}"
+        assert (~same).sum() <= max(1, N // 16), f"{msg}: {(~same).sum()} of {N} envs took a different contact/limit decision"
+        for nm, got, ref, tol in (("torques", env.torques, ora.torques, PHYS_TOL), ("obs", obs, o_obs, PHYS_TOL), ("pri_obs", pri, o_pri, PHYS_TOL),
+                                  ("rew", rew, o_rew, PHYS_TOL), ("root_states", env.root_states, ora.root_states, PHYS_TOL),
+                                  ("dof_pos", env.dof_pos, ora.dof_pos, PHYS_TOL), ("dof_vel", env.dof_vel, ora.dof_vel, PHYS_VEL_TOL),
+                                  ("contact_forces", env.contact_forces, ora.contact_forces, PHYS_FORCE_TOL)):
+            g_, r_ = got.cpu().numpy()[same], np.asarray(ref.numpy() if hasattr(ref, "numpy") else ref)[same]
+            report.setdefault(nm, 0.0)
+            report[nm] = max(report[nm], float(np.abs(g_ - r_).max()) if g_.size else 0.0)
+            np.testing.assert_allclose(g_, r_, err_msg=f"{msg} {nm} (envs with identical active sets)", **tol)
+        np.testing.assert_array_equal(reset.cpu().numpy()[same], o_reset.numpy()[same], err_msg=msg)
+        for tns in (obs, pri, rew, env.root_states):                                      # the flipped envs still hold sane values
+            assert bool(torch.isfinite(tns).all())
+    report["flipped_env_steps"] = n_flip
+    report["env_steps"] = N * int(fx["meta/steps"])
+    return report
+
+
+@pytest.mark.parametrize("name", ENV_FIXTURES)
+def test_full_step_matches_oracle(name):
+    rep = _full_step_compare(name, {})
+    print(f"{name}: max |CUDA - C oracle| over envs with identical active sets: "
+          + ", ".join(f"{k} {v:.2e}" for k, v in rep.items() if k not in ("flipped_env_steps", "env_steps"))
+          + f"; {rep['flipped_env_steps']} of {rep['env_steps']} env-steps took a different contact/limit decision")
+    assert rep["flipped_env_steps"] <= rep["env_steps"] // 32
+
+
+def test_single_substep_error():
+    """Per-SUBSTEP error (fixture plane64_dec1: decimation 1, one 2 ms substep per policy step) reported separately from the
+    10-substep error above; stated bound 2e-4 abs on the state, an order of magnitude below the per-policy-step tolerance."""
+    rep = _full_step_compare("plane64_dec1", {})
+    print("single substep: " + ", ".join(f"{k} {v:.2e}" for k, v in rep.items()))
+    for k in ("root_states", "dof_pos", "obs"):
+        assert rep[k] < 2e-4, (k, rep[k])
+    assert rep["dof_vel"] < 2e-3
 
 
 @pytest.mark.parametrize("robot", ["GR1T1", "GR1T2"])
@@ -235,3 +267,32 @@ def test_trimesh_entry_accepts_only_the_structured_conversion():
     bad = v.copy(); bad[5, 2] += 0.5                                                              # a vertex off the heightfield
     assert env.lib.grx_env_set_terrain_trimesh(*args(bad, t)) == -1
     assert b"does not match" in env.lib.grx_last_error()
+
+
+def test_step_host_equals_device_step():
+    """grx_env_step_host (H2D actions -> fused step -> D2H obs / privileged obs / rewards / resets -> stream sync, the host-buffer
+    entry a non-torch caller of VecEnv.step uses, timed by bench.py as e2e.env_step_host) returns exactly what the device-pointer
+    entry grx_env_step leaves in the device buffers for the same state, actions, delay and step index."""
+    import ctypes as C
+    from grx_b200 import _lib as L
+    from grx_b200.config import make_cfg
+    from grx_b200.env import GRXVecEnv
+    N = 300
+    envs = [GRXVecEnv(make_cfg("GR1T1", N, "plane"), sim_device="cuda:0") for _ in range(2)]
+    for e in envs:
+        e.reset()
+    g = torch.Generator().manual_seed(6)
+    h_o, h_p = np.zeros((N, 39), np.float32), np.zeros((N, 168), np.float32)
+    h_r, h_d = np.zeros(N, np.float32), np.zeros(N, np.uint8)
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    for t in range(12):
+        a = (0.3 * torch.randn(N, 10, generator=g)).numpy()
+        idx = 1000 + t
+        L.check(envs[0].lib.grx_env_step_host(envs[0]._h, P(a), C.c_float(3.0), 0, C.c_uint64(idx), P(h_o), P(h_p), P(h_r), P(h_d), None))
+        L.check(envs[1].lib.grx_env_step(envs[1]._h, C.c_void_p(torch.from_numpy(a).cuda().data_ptr()), None, C.c_float(3.0), 0, C.c_uint64(idx), None))
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(h_o, envs[1].obs_buf.cpu().numpy())
+        np.testing.assert_array_equal(h_p, envs[1].pri_obs_buf.cpu().numpy())
+        np.testing.assert_array_equal(h_r, envs[1].rew_buf.cpu().numpy())
+        np.testing.assert_array_equal(h_d, envs[1]._reset_u8.cpu().numpy())
+    assert np.isfinite(h_o).all() and np.abs(h_o).max() > 0

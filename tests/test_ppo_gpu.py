@@ -268,3 +268,141 @@ def test_nan_loss_skips_the_optimiser_step():
     st = alg.minibatch_stats()
     assert st["skip"] == 0 and st["step"] == 2 and not torch.equal(alg.params, before) and bool(torch.isfinite(alg.params).all())
     alg.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The BENCHMARKED path (tcgen05 TF32 layers + fused heads kernels + CUDA-graph epoch with the device-side minibatch counter)
+# pinned to the unmodified rsl_rl at the REGISTERED width 512/256/128 (tests/golden/ppo_wide.npz: N=256, T=16, 4 minibatches x 2 epochs,
+# adaptive-KL schedule exercising x1.5, hold and /1.5).  Inputs and initial weights are regenerated from their seeds (checked by hash /
+# by test_init_matches_reference_generator_stream).
+#
+# Stated tolerance of the TF32 path vs fp32 rsl_rl (operands rounded to 10-bit mantissas, fp32 accumulate, split-K atomics):
+#   values / returns 5e-3 abs, normalised advantages 1e-2, log-prob 1e-5 (no GEMM between mu and log-prob of the stored action),
+#   per-minibatch mean KL 2 % + 2e-5, LR sequence exact, mean losses 2 %,
+#   update direction: ||dW_ours - dW_ref|| / ||dW_ref|| < 10 % per tensor (Adam normalises every element's step to ~lr, so an element
+#   whose tiny gradient changes sign under TF32 rounding moves by up to 2 lr per step; the norm ratio bounds the share of such elements),
+#   Adam moments (every 8th element): first moment 5 % of its RMS, second 10 %.
+# ---------------------------------------------------------------------------------------------------------------------
+def _wide_setup(use_tc=1):
+    from golden_util import wide_inputs
+    from grx_b200.ppo import PPO, ActorCriticMLP
+    fx = dict(np.load(os.path.join(GOLDEN, "ppo_wide.npz")))
+    N, T, nmb, nep, O, P, A = [int(v) for v in fx["meta/dims"]]
+    d, digest = wide_inputs(int(fx["meta/seed"]), N, T, O, P, A)
+    assert digest == str(fx["meta/inputs_sha256"]), "torch CPU generator stream differs from the one the fixture was made with"
+    tc = make_train_cfg()
+    torch.manual_seed(int(fx["meta/seed"]))
+    ac = ActorCriticMLP(O, P, A, **tc["policy"])                     # same nn.Linear init stream as rsl_rl's constructor
+    alg = PPO(ac, device="cuda:0", use_tensor_cores=use_tc,
+              **dict(tc["algorithm"], num_mini_batches=nmb, num_learning_epochs=nep, learning_rate=float(fx["meta/lr0"])))
+    alg.init_storage(N, T)
+    init = {k: v.detach().cpu().clone() for k, v in ac.state_dict().items()}
+    for t in range(T):
+        alg.act(d["obs"][t].cuda(), d["critic_obs"][t].cuda(), eps=d["eps"][t].cuda())
+        alg.process_env_step(d["rewards"][t].cuda(), d["dones"][t].cuda(), {"time_outs": d["time_outs"][t].cuda()})
+    alg.compute_returns(d["last_critic_obs"].cuda())
+    torch.cuda.synchronize()
+    return fx, d, alg, ac, init, (N, T, nmb, nep)
+
+
+def _wide_check_final(fx, alg, ac, init):
+    worst = 0.0
+    for key, v in ac.state_dict().items():
+        ref, w0 = fx["final/" + key], init[key].numpy()
+        dref, dours = ref - w0, v.cpu().numpy() - w0
+        rel = np.linalg.norm(dours - dref) / (np.linalg.norm(dref) + 1e-30)
+        worst = max(worst, rel)
+        assert rel < 0.10, f"{key}: update differs from rsl_rl by {rel:.3f} of its norm"
+        assert np.abs(dours - dref).max() < 2.5e-3, key      # <= 2 lr per step x 8 steps
+    osd = alg.optimizer_state_dict()["state"]
+    for i, key in enumerate(ac.state_dict()):
+        m8, v8 = osd[i]["exp_avg"].cpu().numpy().ravel()[::8], osd[i]["exp_avg_sq"].cpu().numpy().ravel()[::8]
+        rm, rv = fx["adam_m8/" + key], fx["adam_v8/" + key]
+        np.testing.assert_allclose(m8, rm, rtol=0, atol=0.05 * float(np.sqrt((rm ** 2).mean())) + 1e-12, err_msg="m " + key)
+        np.testing.assert_allclose(v8, rv, rtol=0.10, atol=0.02 * float(rv.mean()) + 1e-20, err_msg="v " + key)
+    assert alg.adam_step == int(fx["adam_step"])
+    return worst
+
+
+def test_wide_rollout_matches_rsl_rl_tensor_core_path():
+    fx, d, alg, ac, init, _ = _wide_setup(1)
+    st = alg.storage
+    np.testing.assert_allclose(st.values.cpu().numpy(), fx["storage/values"], rtol=0, atol=5e-3)
+    np.testing.assert_allclose(st.returns.cpu().numpy(), fx["storage/returns"], rtol=0, atol=5e-3)
+    np.testing.assert_allclose(st.advantages.cpu().numpy(), fx["storage/advantages"], rtol=0, atol=1e-2)
+    np.testing.assert_allclose(st.actions_log_prob.cpu().numpy(), fx["storage/actions_log_prob"], rtol=1e-5, atol=2e-5)
+    alg.close()
+
+
+@pytest.mark.parametrize("use_tc", [1, 0])
+def test_wide_graph_update_matches_rsl_rl(use_tc):
+    """grx_ppo_update (CUDA-graph epoch x 2, device-side minibatch counter, tcgen05 layers + ppo_heads_kernel<10>) over 8 minibatches:
+    KL / LR sequence from the device log, mean losses, final weights, Adam moments vs the unmodified rsl_rl."""
+    fx, d, alg, ac, init, (N, T, nmb, nep) = _wide_setup(use_tc)
+    mvl, msl = alg.update(indices=d["indices"][: alg._indices.numel()])
+    torch.cuda.synchronize()
+    log, ref = alg.mb_log.cpu().numpy(), fx["update/kl_lr"]
+    assert log.shape[0] == nmb * nep == ref.shape[0]
+    np.testing.assert_allclose(log[:, 1], ref[:, 1], rtol=1e-6, err_msg="learning-rate sequence")
+    np.testing.assert_allclose(log[:, 0], ref[:, 0], rtol=2e-2 if use_tc else 2e-3, atol=2e-5, err_msg="per-minibatch mean KL")
+    np.testing.assert_allclose([float(mvl), float(msl)], fx["update/mean_losses"], rtol=2e-2, atol=2e-4)
+    worst = _wide_check_final(fx, alg, ac, init)
+    print(f"wide fixture, use_tc={use_tc}: worst per-tensor relative update error {worst:.4f}")
+    alg.close()
+
+
+def test_wide_stepwise_update_matches_rsl_rl_tensor_core_path():
+    """The same update through the stepwise grads / apply entries (what the NCCL multi-GPU path uses), minibatch by minibatch."""
+    import ctypes as C
+    from grx_b200 import _lib as L
+    fx, d, alg, ac, init, (N, T, nmb, nep) = _wide_setup(1)
+    alg._indices.copy_(d["indices"][: alg._indices.numel()].cuda())
+    ref, k = fx["update/kl_lr"], 0
+    for ep in range(nep):
+        for mb in range(nmb):
+            L.check(alg.lib.grx_ppo_minibatch_grads(alg._h, C.c_void_p(alg._indices.data_ptr()), mb, alg._stream()))
+            L.check(alg.lib.grx_ppo_minibatch_apply(alg._h, alg._stream()))
+            s = alg.minibatch_stats()
+            np.testing.assert_allclose(s["kl"], ref[k, 0], rtol=2e-2, atol=2e-5, err_msg=f"kl at minibatch {k}")
+            np.testing.assert_allclose(s["lr"], ref[k, 1], rtol=1e-6, err_msg=f"lr at minibatch {k}")
+            k += 1
+    _wide_check_final(fx, alg, ac, init)
+    alg.close()
+
+
+def test_act_noise_is_keyed_by_global_env_id():
+    """RNG streams keyed by global env id.  Two shards (env_id_offset 0 / 96) of a 192-env job draw, in fast mode
+    (in-kernel Philox), exactly the eps the single 192-env PPO draws for the same global envs at the same step; a different task seed
+    or step gives a different stream."""
+    from grx_b200.ppo import PPO, ActorCriticMLP
+    tc = make_train_cfg()
+    N, T, W = 192, 2, 2
+
+    def make(n, off, seed=7):
+        torch.manual_seed(21)
+        ac = ActorCriticMLP(39, 168, 10, **tc["policy"])
+        alg = PPO(ac, device="cuda:0", seed=seed, env_id_offset=off, **tc["algorithm"])
+        alg.init_storage(n, T)
+        return alg, ac
+    g = torch.Generator().manual_seed(2)
+    obs, cobs = torch.randn(N, 39, generator=g).cuda(), torch.randn(N, 168, generator=g).cuda()
+    big, bac = make(N, 0)
+
+    def eps_of(alg, ac, o, c):
+        a = alg.act(o.contiguous(), c.contiguous()).clone()
+        z = (a - alg.storage.mu[alg.step]) / ac.std
+        alg.process_env_step(torch.zeros(o.shape[0], device="cuda"), torch.zeros(o.shape[0], dtype=torch.bool, device="cuda"), {})
+        return z
+    zb = [eps_of(big, bac, obs, cobs) for _ in range(T)]
+    assert not torch.allclose(zb[0], zb[1])                                           # the step index advances the stream
+    for r in range(W):
+        sl = slice(r * N // W, (r + 1) * N // W)
+        sh, sac = make(N // W, r * N // W)
+        for t in range(T):
+            zs = eps_of(sh, sac, obs[sl], cobs[sl])
+            assert torch.allclose(zs, zb[t][sl], atol=2e-4), f"rank {r} step {t}: shard noise differs from the global stream"
+        sh.close()
+    assert not torch.allclose(zb[0][: N // W], zb[0][N // W:])                        # ranks do not duplicate each other's noise
+    other, oac = make(N, 0, seed=8)
+    assert not torch.allclose(eps_of(other, oac, obs, cobs), zb[0])                   # the task seed selects the stream
+    big.close(); other.close()

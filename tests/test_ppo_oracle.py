@@ -87,3 +87,32 @@ def test_hand_backward_equals_autograd():
     assert abs(float(loss) - float(stats["loss"])) < 1e-5
     for k in p:
         np.testing.assert_allclose(g[k].numpy(), pa[k].grad.numpy(), rtol=2e-3, atol=2e-6, err_msg=k)
+
+
+@pytest.mark.parametrize("name", ["small", "small_hot"])
+def test_autograd_port_matches_rsl_rl(name):
+    """oracle/ppo_autograd.py (the CPU baseline arm of bench.py: nn.Module + autograd + torch.optim.Adam, as rsl_rl runs) reproduces
+    the unmodified rsl_rl update: KL / LR sequence and final weights."""
+    from oracle import ppo_autograd as pa
+    fx, t = _load(name)
+    N, T, nmb, nep, O, P, A = [int(v) for v in fx["meta/dims"]]
+    hidden = [int(v) for v in fx["meta/hidden"]]
+    ac = pa.ActorCritic(O, P, A, hidden, hidden)
+    ac.load_state_dict({k[len("init/"):]: t(k) for k in fx if k.startswith("init/")})
+    cfg = make_train_cfg()["algorithm"]
+    step = pa.PPOStep(ac, clip=cfg["clip_param"], vcoef=cfg["value_loss_coef"], ecoef=cfg["entropy_coef"], lr=float(fx["meta/lr0"]),
+                      lr_min=cfg["learning_rate_min"], lr_max=cfg["learning_rate_max"], desired_kl=cfg["desired_kl"], max_grad_norm=cfg["max_grad_norm"])
+    flat = lambda k: t(k).flatten(0, 1)
+    st = dict(obs=flat("roll/obs"), critic_obs=flat("roll/critic_obs"), actions=flat("storage/actions"), values=flat("storage/values"),
+              advantages=flat("storage/advantages"), returns=flat("storage/returns"), old_log_prob=flat("storage/actions_log_prob"),
+              old_mu=flat("storage/mu"), old_sigma=flat("storage/sigma"))
+    idx, B = t("update/indices"), (N * T) // nmb
+    for ep in range(nep):
+        for mb in range(nmb):
+            sel = idx[mb * B:(mb + 1) * B]
+            step.minibatch({k: v[sel] for k, v in st.items()})
+    ref = fx["update/kl_lr"]
+    np.testing.assert_allclose([k for k, _ in step.kl_log], ref[:, 0], rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose([l for _, l in step.kl_log], ref[:, 1], rtol=1e-12)
+    for k, v in ac.state_dict().items():
+        np.testing.assert_allclose(v.numpy(), fx["final/" + k], rtol=1e-4, atol=1e-6, err_msg=k)

@@ -24,6 +24,10 @@
 #include <vector>
 
 #include "grx_b200.h"
+#include "grx_count.h"
+
+std::atomic<unsigned long long> g_grx_launches{0};
+extern "C" uint64_t grx_debug_launch_count(void) { return (uint64_t)g_grx_launches.load(); }
 
 namespace {
 
@@ -32,6 +36,7 @@ constexpr int YS = 20;   // row stride of WS::Y (floats): 16-byte aligned and co
 constexpr int NREW = 24, NHMAX = 128;
 constexpr int WARPS_PER_CTA = 16;   // MAXIMUM warps per CTA (one CTA per SM; its warps re-converge at every substep so the warps of a scheduler share
                                     // instruction-cache lines).  The launch picks warps_per_cta <= 16 so that the CTAs fill whole waves (see env_warps_per_cta)
+constexpr int SIG_STRIDE = 16;               // substep slots per env in the active-set signature export (decimation <= 16)
 constexpr int ACC_RING = 256, ACC_W = 32;   // extras["episode"] accumulators: one 32-float slot per launch, ring of 256
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -87,6 +92,8 @@ struct EnvArgs {
     grx_injected_physics inj;
     float *dbg_M, *dbg_h;  // debug_dynamics
     int dbg_index;
+    unsigned long long *dbg_sig;   // [N, dbg_sig_stride] active-set signature per substep, or nullptr (grx_env_debug_active_sig)
+    int dbg_sig_stride;
 };
 
 // per-warp shared-memory workspace
@@ -226,8 +233,16 @@ struct Draw {
 };
 
 // ---- terrain query (oracle/phys_impl.h terrain_query)
-__device__ __forceinline__ void terrain_query(const TerrainDev &t, float x, float y, float &h, float *n) {
-    if (t.type == 0) { h = 0; n[0] = 0; n[1] = 0; n[2] = 1; return; }
+// splitmix64 finaliser: item hash of the active-set signature (same function in oracle/phys_impl.h)
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+// cell (debug signature only): grid cell (i, j) and which of its two triangles the query landed in
+__device__ __forceinline__ void terrain_query(const TerrainDev &t, float x, float y, float &h, float *n, int *cell) {
+    if (t.type == 0) { h = 0; n[0] = 0; n[1] = 0; n[2] = 1; cell[0] = cell[1] = cell[2] = 0; return; }
     float gx = (x + t.border) / t.hscale, gy = (y + t.border) / t.hscale;
     int i = (int)floorf(gx), j = (int)floorf(gy);
     if (i < 0) { i = 0; gx = 0; }
@@ -241,6 +256,7 @@ __device__ __forceinline__ void terrain_query(const TerrainDev &t, float x, floa
     float dhx, dhy;
     if (fx >= fy) { dhx = h10 - h00; dhy = h11 - h10; }
     else { dhx = h11 - h01; dhy = h01 - h00; }
+    cell[0] = i; cell[1] = j; cell[2] = fx >= fy ? 0 : 1;
     h = h00 + dhx * fx + dhy * fy;
     float sx = -dhx / t.hscale, sy = -dhy / t.hscale;
     float inv = 1.0f / sqrtf(sx * sx + sy * sy + 1.0f);
@@ -488,7 +504,7 @@ __device__ __forceinline__ void cta_align(int nthreads) {   // phase alignment o
     if (nthreads > 0) asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
 }
 
-__device__ __noinline__ void substep(WS &s, const ModelDev &m, const EnvArgs &A, const grx_task_cfg &cfg, int lane) {
+__device__ __noinline__ void substep(WS &s, const ModelDev &m, const EnvArgs &A, const grx_task_cfg &cfg, int lane, int env, int deci) {
     const float dt = cfg.sim_dt;
     mass_and_bias(s, m, cfg.gravity, lane);
     if (A.dbg_M != nullptr && A.dbg_index == (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5))) {  // debug_dynamics: export before factorisation
@@ -502,6 +518,8 @@ __device__ __noinline__ void substep(WS &s, const ModelDev &m, const EnvArgs &A,
     bool act = false;
     float n[3] = {0, 0, 1}, xs[3] = {0, 0, 0}, dist = 0, rad = 0;
     int sb = 0;
+    int cell[3] = {0, 0, 0};
+    unsigned long long sig_item = 0ull;   // this lane's contribution to the active-set signature (debug export, see phys_impl.h substep)
     if (lane < m.ns) {
         sb = m.sph_body[lane];
         rad = m.sph_rad[lane];
@@ -509,7 +527,7 @@ __device__ __noinline__ void substep(WS &s, const ModelDev &m, const EnvArgs &A,
 #pragma unroll
         for (int k = 0; k < 3; k++) xs[k] += s.o[sb][k];
         float hgt;
-        terrain_query(A.terrain, xs[0], xs[1], hgt, n);
+        terrain_query(A.terrain, xs[0], xs[1], hgt, n, cell);
         dist = (xs[2] - hgt) * n[2] - rad;
         act = dist < cfg.contact_offset;
     }
@@ -537,7 +555,10 @@ __device__ __noinline__ void substep(WS &s, const ModelDev &m, const EnvArgs &A,
         float target;
         if (dist > 0) target = -dist / dt;
         else { target = -dist * cfg.erp / dt; if (target > cfg.max_depen_vel) target = cfg.max_depen_vel; }
-        if (vn0 < -cfg.bounce_threshold && -rest * vn0 > target) target = -rest * vn0;
+        const bool bounce = vn0 < -cfg.bounce_threshold && -rest * vn0 > target;
+        if (bounce) target = -rest * vn0;
+        sig_item = mix64((1ull << 56) | (unsigned long long)lane | ((unsigned long long)cell[0] << 6) | ((unsigned long long)cell[1] << 18) |
+                         ((unsigned long long)cell[2] << 30) | ((unsigned long long)(bounce ? 1 : 0) << 31) | ((unsigned long long)(usey ? 1 : 0) << 32));
 #pragma unroll
         for (int k = 0; k < 3; k++) { s.cfr[rank][k] = n[k]; s.cfr[rank][3 + k] = t1[k]; s.cfr[rank][6 + k] = t2[k]; s.cpt[rank][k] = xc[k]; }
         s.cpt[rank][3] = target;
@@ -554,7 +575,19 @@ __device__ __noinline__ void substep(WS &s, const ModelDev &m, const EnvArgs &A,
     const unsigned lbal = __ballot_sync(FULL, lsgn != 0.f);
     const int lrank = __popc(lbal & ((1u << lane) - 1u));
     const int nlim = min(__popc(lbal), KLIM);
-    if (lsgn != 0.f && lrank < KLIM) { s.limj[lrank] = lane; s.lims[lrank] = lsgn; s.limt[lrank] = ltgt; }
+    if (lsgn != 0.f && lrank < KLIM) {
+        s.limj[lrank] = lane; s.lims[lrank] = lsgn; s.limt[lrank] = ltgt;
+        sig_item += mix64((2ull << 56) | (unsigned long long)lane | ((unsigned long long)(lsgn < 0.f ? 1 : 0) << 6));
+    }
+    if (A.dbg_sig != nullptr) {   // debug export of the discrete decisions of this substep (parity tests)
+        unsigned long long tot = sig_item;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned l2 = __shfl_xor_sync(FULL, (unsigned)tot, o), h2 = __shfl_xor_sync(FULL, (unsigned)(tot >> 32), o);
+            tot += ((unsigned long long)h2 << 32) | l2;
+        }
+        if (lane == 0) A.dbg_sig[(size_t)env * A.dbg_sig_stride + deci] = tot;
+    }
     __syncwarp();
     const int nrow = 3 * nc + nlim;  // <= 31
     // ---- build row lane's Jacobian, solve Y = M^-1 J^T ; lane 31 solves the unconstrained update
@@ -857,7 +890,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 1) env_step_kernel(const _
                 s.tau[lane] = fminf(fmaxf(t, -lim), lim);
             }
             __syncwarp();
-            substep(s, m, A, cfg, lane);
+            substep(s, m, A, cfg, lane, e, deci);
         }
         if (A.dbg_M != nullptr) return;
         const float invd = 1.0f / (float)cfg.decimation;
@@ -1216,6 +1249,7 @@ struct grx_env {
     float *rec = nullptr, *cst = nullptr, *obs = nullptr, *pri_obs = nullptr, *rew = nullptr, *torques = nullptr;
     float *contact_forces = nullptr, *foot_state = nullptr, *episode_accum = nullptr, *terrain_origins = nullptr;
     float *actions_stage = nullptr;
+    unsigned long long *active_sig = nullptr;   // debug export, allocated by grx_env_debug_active_sig
     unsigned char *reset = nullptr, *time_out = nullptr;
     short *heights = nullptr;
     TerrainDev terrain;
@@ -1321,7 +1355,7 @@ extern "C" int grx_env_destroy(grx_env *e) {
     if (!e) return GRX_OK;
     cudaSetDevice(e->device);
     void *ptrs[] = {e->dmodel, e->rec, e->cst, e->obs, e->pri_obs, e->rew, e->torques, e->contact_forces, e->foot_state,
-                    e->episode_accum, e->terrain_origins, e->actions_stage, e->reset, e->time_out, e->heights};
+                    e->episode_accum, e->terrain_origins, e->actions_stage, e->reset, e->time_out, e->heights, e->active_sig};
     for (void *p : ptrs) if (p) cudaFree(p);
     delete e;
     return GRX_OK;
@@ -1430,6 +1464,10 @@ extern "C" int grx_env_get_buffer(grx_env *e, const char *name, grx_buffer *b) {
     if (n == "foot_state") { set_buf(b, e->foot_state, GRX_F32, 3, N, NF, 13, NF * 13, 13, 1); return GRX_OK; }
     if (n == "episode_accum") { set_buf(b, e->episode_accum, GRX_F32, 2, ACC_RING, ACC_W, 1, ACC_W, 1, 1); return GRX_OK; }
     if (n == "params") { set_buf(b, e->cst, GRX_F32, 2, N, CST_F, 1, CST_F, 1, 1); return GRX_OK; }
+    if (n == "active_sig") {
+        if (!e->active_sig) return grx_set_error(GRX_E_STATE, "grx_env_get_buffer: call grx_env_debug_active_sig(env, 1) first");
+        set_buf(b, e->active_sig, GRX_U64, 2, N, SIG_STRIDE, 1, SIG_STRIDE, 1, 1); return GRX_OK;
+    }
     return grx_set_error(GRX_E_NOTFOUND, "grx_env_get_buffer: unknown buffer '" + n + "'");
 }
 
@@ -1443,6 +1481,7 @@ static EnvArgs make_args(grx_env *e, const float *d_actions, const float *d_unif
     A.episode_accum = e->episode_accum + (size_t)(e->launches % ACC_RING) * ACC_W;
     A.episode_accum_next = e->episode_accum + (size_t)((e->launches + 1) % ACC_RING) * ACC_W;
     A.reset = e->reset; A.time_out = e->time_out;
+    A.dbg_sig = e->active_sig; A.dbg_sig_stride = SIG_STRIDE;
     return A;
 }
 
@@ -1452,6 +1491,7 @@ extern "C" int grx_env_step(grx_env *e, const float *d_actions, const float *d_u
     if (!e->params_set) return grx_set_error(GRX_E_STATE, "grx_env_step: call grx_env_set_params first");
     EnvArgs A = make_args(e, d_actions, d_uniform, delay, push, step_index);
     const int wpc = e->warps_per_cta, grid = (e->N + wpc - 1) / wpc;
+    grx_count_launch();
     env_step_kernel<true><<<grid, wpc * 32, e->smem, (cudaStream_t)stream>>>(A, e->cfg);
     CK(cudaGetLastError());
     e->launches++;
@@ -1465,6 +1505,7 @@ extern "C" int grx_env_post_physics(grx_env *e, const float *d_actions, const fl
     EnvArgs A = make_args(e, d_actions, d_uniform, 0.f, push, step_index);
     A.inj = *inj;
     const int wpc = e->warps_per_cta, grid = (e->N + wpc - 1) / wpc;
+    grx_count_launch();
     env_step_kernel<false><<<grid, wpc * 32, e->smem, (cudaStream_t)stream>>>(A, e->cfg);
     CK(cudaGetLastError());
     e->launches++;
@@ -1478,6 +1519,7 @@ extern "C" int grx_env_reset_idx(grx_env *e, const int32_t *d_ids, int32_t n, co
     if (n == 0) return GRX_OK;                                                        // LR:387-388
     EnvArgs A = make_args(e, nullptr, d_uniform, 0.f, 0, step_index);
     const int grid = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    grx_count_launch();
     env_reset_kernel<<<grid, WARPS_PER_CTA * 32, e->smem, (cudaStream_t)stream>>>(A, e->cfg, d_ids, n, curriculum_active);
     CK(cudaGetLastError());
     e->launches++;
@@ -1502,6 +1544,21 @@ extern "C" int grx_env_step_host(grx_env *e, const float *h_actions, float delay
     return GRX_OK;
 }
 
+// Debug / parity: switch the per-substep active-set signature export on (allocates [N, 16] u64, buffer name "active_sig") or off.
+extern "C" int grx_env_debug_active_sig(grx_env *e, int32_t enable) {
+    if (!e) return grx_set_error(GRX_E_INVALID, "null env");
+    CK(cudaSetDevice(e->device));
+    if (enable && e->cfg.decimation > SIG_STRIDE) return grx_set_error(GRX_E_INVALID, "grx_env_debug_active_sig: decimation > 16");
+    if (enable && !e->active_sig) {
+        CK(cudaMalloc((void **)&e->active_sig, (size_t)e->N * SIG_STRIDE * 8));
+        CK(cudaMemset(e->active_sig, 0, (size_t)e->N * SIG_STRIDE * 8));
+    } else if (!enable && e->active_sig) {
+        CK(cudaDeviceSynchronize());
+        cudaFree(e->active_sig); e->active_sig = nullptr;
+    }
+    return GRX_OK;
+}
+
 extern "C" int grx_env_debug_dynamics(grx_env *e, int32_t index, float *h_M, float *h_h) {
     if (!e || !h_M || !h_h || index < 0 || index >= e->N) return grx_set_error(GRX_E_INVALID, "grx_env_debug_dynamics: bad argument");
     if (!e->params_set) return grx_set_error(GRX_E_STATE, "grx_env_debug_dynamics: call grx_env_set_params first");
@@ -1516,6 +1573,7 @@ extern "C" int grx_env_debug_dynamics(grx_env *e, int32_t index, float *h_M, flo
     grx_task_cfg c = e->cfg;
     c.decimation = 1;
     const int wpc = e->warps_per_cta, grid = (e->N + wpc - 1) / wpc;
+    grx_count_launch();
     env_step_kernel<true><<<grid, wpc * 32, e->smem>>>(A, c);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());

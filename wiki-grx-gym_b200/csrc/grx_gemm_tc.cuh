@@ -38,6 +38,8 @@
 #include <mutex>
 #include <unordered_map>
 
+#include "grx_count.h"
+
 namespace tc {
 
 constexpr int TM = 128, TK = 32, NTHREADS_CTA = 320;   // 8 epilogue warps + TMA warp + MMA warp
@@ -513,6 +515,7 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl && pdl_enabled() ? 1 : 0;
+    grx_count_launch();
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 inline int sm_count() {

@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "grx_b200.h"
+#include "grx_count.h"
 #include "grx_gemm_tc.cuh"
 
 int grx_set_error(int code, const std::string &msg);   // grx_env.cu
@@ -129,6 +130,7 @@ void launch_gemm(const GemmArgs &g, int splits, cudaStream_t st) {
     a.kchunk = ((g.K + splits - 1) / splits + BK - 1) / BK * BK;
     const int z = (g.K + a.kchunk - 1) / a.kchunk;
     dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, z);
+    grx_count_launch();
     gemm_kernel<A_KC, B_KC, EPI><<<grid, 256, 0, st>>>(a);
 }
 
@@ -174,6 +176,7 @@ void dense_group(const GemmArgs *gs, const int *splits, int np, bool use_tc, cud
                 const GemmArgs &g = gs[i];
                 if (EPI == 3 && g.bias_out) {
                     const int rpb = 512;
+                    grx_count_launch();
                     colsum_kernel<<<dim3((g.M + 31) / 32, (g.K + rpb - 1) / rpb), 256, 0, st>>>(g.A, g.K, g.M, g.lda, rpb, g.bias_out);   // A = dY [rows, out]
                 }
             }
@@ -195,6 +198,7 @@ void dense_group(const GemmArgs *gs, const int *splits, int np, bool use_tc, cud
         launch_gemm<A_KC, B_KC, EPI>(g, sp, st);
         if (EPI == 2 && g.bias_out) {   // column sums of the produced gradient = bias gradient of the layer below
             const int rpb = 512;
+            grx_count_launch();
             colsum_kernel<<<dim3((g.N + 31) / 32, (g.M + rpb - 1) / rpb), 256, 0, st>>>(g.C, g.M, g.N, g.ldc, rpb, g.bias_out);
         }
     }
@@ -758,18 +762,24 @@ __device__ __forceinline__ int ld_acquire_sys(const int *p) {
     asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// spin until *p >= epoch; gives up after ~2 s worth of clocks and reports through ctl->comm_error (never hangs the GPU)
-__device__ __forceinline__ void wait_flag(const int *p, int epoch, Ctl *ctl) {
-    const long long t0 = clock64();
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// spin until *p >= epoch; gives up after `budget_ns` (cfg.comm_timeout_ms) and reports through ctl->comm_error, which is STICKY:
+// apply_kernel does not touch the parameters once it is set and the host raises (grx_ppo_update / grx_ppo_check) — never hangs the GPU
+__device__ __forceinline__ void wait_flag(const int *p, int epoch, Ctl *ctl, unsigned long long budget_ns) {
+    const unsigned long long t0 = global_ns();
     while (ld_acquire_sys(p) < epoch) {
-        if (clock64() - t0 > 4000000000ll) { ctl->comm_error = 1; break; }
+        if (global_ns() - t0 > budget_ns) { atomicExch(&ctl->comm_error, 1); break; }
         __nanosleep(64);
     }
 }
-__global__ void __launch_bounds__(256) allreduce_kernel(const CommDev c, int n4, int nparam4, Ctl *ctl) {
+__global__ void __launch_bounds__(256) allreduce_kernel(const CommDev c, int n4, int nparam4, Ctl *ctl, unsigned long long budget_ns) {
     const int epoch = ctl->comm_epoch + 1;
     if (blockIdx.x == 0 && threadIdx.x < c.world) st_release_sys(c.flags[threadIdx.x] + FLAG_READY + c.rank, epoch);
-    if (threadIdx.x < c.world) wait_flag(c.flags[c.rank] + FLAG_READY + threadIdx.x, epoch, ctl);
+    if (threadIdx.x < c.world) wait_flag(c.flags[c.rank] + FLAG_READY + threadIdx.x, epoch, ctl, budget_ns);
     __syncthreads();
     const int per = (n4 + c.world - 1) / c.world, lo = c.rank * per, hi = min(n4, lo + per);
     float ss = 0.f;
@@ -819,6 +829,9 @@ struct PrepArgs {
     float desired_kl, lr_min, lr_max, max_grad_norm, vcoef, ecoef;
     int *comm_flags;   // this rank's flag block when the NVLink all-reduce is active (norm partials come from the peers), else NULL
     int comm_rank;
+    unsigned long long budget_ns;   // peer-flag wait budget
+    float *mb_log;     // [mb_log_cap][4] = (kl_mean, lr, loss, grad_norm) of minibatch ctl.mb_counter of this update (what ppo.py:262-268, 308-309 would log)
+    int mb_log_cap;
 };
 // ONE kernel for the apply step (ppo.py:262-268, 297-305): gradient norm -> [grid barrier] -> adaptive LR from the mean KL,
 // NaN skip, clip coefficient, Adam bias corrections (evaluated identically by every block from the same inputs) -> Adam on the
@@ -830,6 +843,7 @@ __global__ void __launch_bounds__(1024) apply_kernel(const PrepArgs a, float *__
     Ctl &c = *a.ctl;
     __shared__ float red[32];
     __shared__ double s_total;
+    __shared__ int s_comm_bad;
     if (threadIdx.x == 0) tc::stamp(0);
     const float old_lr = c.lr;
     const int old_step = c.step;
@@ -846,7 +860,7 @@ __global__ void __launch_bounds__(1024) apply_kernel(const PrepArgs a, float *__
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
         if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
     } else if (threadIdx.x < a.world_size) {   // wait until every rank has pushed its slice of the summed gradient (and its partial norm)
-        wait_flag(a.comm_flags + FLAG_DONE + threadIdx.x, c.comm_epoch + 1, a.ctl);
+        wait_flag(a.comm_flags + FLAG_DONE + threadIdx.x, c.comm_epoch + 1, a.ctl, a.budget_ns);
     }
     __syncthreads();
     if (threadIdx.x == 0) tc::stamp(1);
@@ -860,7 +874,7 @@ __global__ void __launch_bounds__(1024) apply_kernel(const PrepArgs a, float *__
         atomicAdd(&c.apply_arrive, 1u);
         const long long t0 = clock64();
         while (*reinterpret_cast<volatile unsigned *>(&c.apply_arrive) < gridDim.x) {
-            if (clock64() - t0 > 4000000000ll) { c.comm_error = 2; break; }   // grid not co-resident (should not happen): never hang the GPU
+            if (clock64() - t0 > 8000000000ll) { atomicExch(&c.comm_error, 2); break; }   // grid not co-resident (should not happen): never hang the GPU
             __nanosleep(32);
         }
         __threadfence();
@@ -870,6 +884,9 @@ __global__ void __launch_bounds__(1024) apply_kernel(const PrepArgs a, float *__
             for (int r = 0; r < a.world_size; r++) t += reinterpret_cast<const volatile double *>(a.comm_flags + FLAG_SUMSQ)[r];   // rank order: identical on every rank
             s_total = t;
         }
+        // sticky: a peer-flag / grid-barrier wait that timed out (now or in an earlier minibatch) leaves the summed gradient undefined.
+        // Every block reads the flag after the grid barrier, so all of them take the same decision: do not touch the parameters.
+        s_comm_bad = *reinterpret_cast<volatile int *>(&c.comm_error);
     }
     __syncthreads();
     if (threadIdx.x == 0) tc::stamp(2);
@@ -883,7 +900,7 @@ __global__ void __launch_bounds__(1024) apply_kernel(const PrepArgs a, float *__
     }
     const float surr = a.tail[2] / cnt, vl = a.tail[3] / cnt;
     const float loss = surr + a.vcoef * vl - a.ecoef * ent;
-    const bool skip = isnan(loss);
+    const bool skip = isnan(loss) || s_comm_bad != 0;
     const float W = (float)a.world_size;
     const float total = (float)sqrt(s_total) / W;                                      // grads are sums over ranks
     const float coef = fminf(a.max_grad_norm / (total + 1e-6f), 1.0f) / W;             // clip_grad_norm_ (ppo.py:304)
@@ -917,6 +934,10 @@ __global__ void __launch_bounds__(1024) apply_kernel(const PrepArgs a, float *__
         if (done == gridDim.x - 1) {   // everybody has read the barrier results and the old control values: persist + reset scratch
             c.lr = lr; c.coef = coef; c.skip = skip ? 1 : 0; c.step = step; c.bc1 = bc1; c.bc2s = bc2s; c.pow1 = pow1; c.pow2 = pow2;
             c.kl_mean = kl_mean; c.loss = loss; c.value_loss = vl; c.surrogate_loss = surr; c.grad_norm = total;
+            if (a.mb_log != nullptr && c.mb_counter >= 0 && c.mb_counter < a.mb_log_cap) {
+                float *row = a.mb_log + 4 * c.mb_counter;
+                row[0] = kl_mean; row[1] = lr; row[2] = loss; row[3] = total;
+            }
             c.mb_counter += 1;
             if (!skip) { c.sum_value_loss += vl; c.sum_surrogate_loss += surr; }
             if (a.comm_flags != nullptr) c.comm_epoch += 1;
@@ -955,9 +976,12 @@ struct grx_ppo {
           *mb_mu = nullptr, *mb_sigma = nullptr, *last_values = nullptr;
     double *moments = nullptr;
     Ctl *ctl = nullptr;
+    float *mb_log = nullptr;   // per-minibatch (kl, lr, loss, grad norm) of the current update
+    int mb_log_cap = 0;
     std::vector<void *> allocs;
     cudaGraphExec_t graph = nullptr;
     const int64_t *graph_indices = nullptr;
+    unsigned long long graph_kernels = 0;   // kernel nodes of one epoch graph
     // phase timing of the stepwise minibatch entries (GRX_PPO_TIMING=1; profiling only: it synchronises after every minibatch)
     bool timing = false;
     cudaEvent_t tev[9] = {};
@@ -970,6 +994,7 @@ struct grx_ppo {
     int *flags = nullptr;
     bool comm_open = false;
     int apply_grid = 148;   // co-resident grid of apply_kernel (<= SM count)
+    unsigned long long comm_budget_ns = 10000000000ull;   // cfg.comm_timeout_ms (GRX_COMM_TIMEOUT_MS overrides)
     CommDev comm;
     std::vector<void *> peer_maps;
 };
@@ -1033,6 +1058,8 @@ extern "C" int grx_ppo_create(const grx_ppo_cfg *cfg, int32_t device, grx_ppo **
     PALLOC(p->mb_ret, MR * 4); PALLOC(p->mb_adv, MR * 4); PALLOC(p->mb_logp, MR * 4); PALLOC(p->mb_mu, MR * p->A * 4);
     PALLOC(p->mb_sigma, MR * p->A * 4); PALLOC(p->last_values, (size_t)p->N * 4);
     PALLOC(p->moments, 4 * sizeof(double)); PALLOC(p->ctl, sizeof(Ctl));
+    p->mb_log_cap = cfg->num_learning_epochs * cfg->num_mini_batches;
+    PALLOC(p->mb_log, (size_t)p->mb_log_cap * 4 * sizeof(float));
     CK(cudaFuncSetAttribute(gae_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * GAE_TMAX * 33 * (int)sizeof(float)));
     {   // std = init_noise_std (ACM:79-82); weights are loaded by the host (same nn.Linear init stream as the reference); lr
         std::vector<float> s(p->A, cfg->init_noise_std);
@@ -1046,6 +1073,8 @@ extern "C" int grx_ppo_create(const grx_ppo_cfg *cfg, int32_t device, grx_ppo **
         int sms = 0;
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) p->apply_grid = sms;
     }
+    if (cfg->comm_timeout_ms > 0) p->comm_budget_ns = (unsigned long long)cfg->comm_timeout_ms * 1000000ull;
+    if (const char *e = getenv("GRX_COMM_TIMEOUT_MS")) { const long v = atol(e); if (v > 0) p->comm_budget_ns = (unsigned long long)v * 1000000ull; }
     if (const char *e = getenv("GRX_PPO_TIMING")) p->timing = atoi(e) != 0;
     if (p->timing) for (int i = 0; i < 9; i++) CK(cudaEventCreate(&p->tev[i]));
     *out = p;
@@ -1091,6 +1120,7 @@ extern "C" int grx_ppo_get_buffer(grx_ppo *p, const char *name, grx_buffer *b) {
     if (n == "adv_moments") { set_buf(b, p->moments, GRX_U64, 1, 3, 1, 1); return GRX_OK; }   // 3 doubles (bit pattern)
     if (n == "gsum") { set_buf(b, p->gsum, GRX_F32, 1, np_ + TAIL, 1, 1); return GRX_OK; }
     if (n == "ctl") { set_buf(b, p->ctl, GRX_F32, 1, sizeof(Ctl) / 4, 1, 1); return GRX_OK; }
+    if (n == "mb_log") { set_buf(b, p->mb_log, GRX_F32, 2, p->mb_log_cap, 4, 1); return GRX_OK; }
     return grx_set_error(GRX_E_NOTFOUND, "grx_ppo_get_buffer: unknown buffer '" + n + "'");
 }
 
@@ -1173,7 +1203,7 @@ extern "C" int grx_ppo_act(grx_ppo *p, const float *d_obs, const float *d_critic
     a.actions_out = d_actions_out;
     a.s_obs = p->s_obs + row * p->O; a.s_cobs = p->s_cobs + row * p->P; a.s_act = p->s_act + row * p->A; a.s_val = p->s_val + row;
     a.s_logp = p->s_logp + row; a.s_mu = p->s_mu + row * p->A; a.s_sigma = p->s_sigma + row * p->A;
-    a.N = p->N; a.O = p->O; a.P = p->P; a.A = p->A; a.seed = 0x9E3779B97F4A7C15ull; a.step_index = step_index; a.env_id_offset = 0;
+    a.N = p->N; a.O = p->O; a.P = p->P; a.A = p->A; a.seed = p->cfg.seed ^ 0x9E3779B97F4A7C15ull; a.step_index = step_index; a.env_id_offset = p->cfg.env_id_offset;   // Philox key (task seed), counter (GLOBAL env id, step)
     if (fused_heads) {
         ActHeadsArgs q;
         q.h3a = p->ha[2]; q.h3c = p->hc[2];
@@ -1181,6 +1211,7 @@ extern "C" int grx_ppo_act(grx_ppo *p, const float *d_obs, const float *d_critic
         q.a = a;
         CK(tc::launch_kernel(act_heads_kernel<10>, dim3((p->N + 7) / 8 < 1184 ? max((p->N + 7) / 8, 148) : 1184), dim3(256), 0, st, true, q));
     } else {
+        grx_count_launch();
         act_sample_store_kernel<<<max((p->N + 127) / 128, 592), 128, 0, st>>>(a);
     }
     CK(cudaGetLastError());
@@ -1191,6 +1222,7 @@ extern "C" int grx_ppo_process_env_step(grx_ppo *p, const float *d_rewards, cons
                                         void *stream) {
     if (!p || !d_rewards || !d_dones || t < 0 || t >= p->T) return grx_set_error(GRX_E_INVALID, "grx_ppo_process_env_step: bad argument");
     const size_t row = (size_t)t * p->N;
+    grx_count_launch();
     process_env_step_kernel<<<(p->N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_rewards, d_dones, d_time_outs, p->s_val + row, p->cfg.gamma,
                                                                                    p->s_rew + row, p->s_done + row, p->N);
     CK(cudaGetLastError());
@@ -1205,6 +1237,7 @@ extern "C" int grx_ppo_compute_returns_local(grx_ppo *p, const float *d_last_cri
     mlp_forward(p, &io, 1, p->N, 4, st);                                               // ppo.py:204
     CK(cudaMemcpyAsync(p->last_values, p->hc[3], (size_t)p->N * 4, cudaMemcpyDeviceToDevice, st));
     CK(cudaMemsetAsync(p->moments, 0, 4 * sizeof(double), st));
+    grx_count_launch();
     gae_kernel<<<(p->N + 31) / 32, 1024, (size_t)3 * p->T * 33 * sizeof(float), st>>>(p->s_rew, p->s_done, p->s_val, p->last_values, p->cfg.gamma, p->cfg.lam, p->s_ret, p->s_adv,
                                                   p->moments, p->T, p->N);
     CK(cudaGetLastError());
@@ -1212,6 +1245,7 @@ extern "C" int grx_ppo_compute_returns_local(grx_ppo *p, const float *d_last_cri
 }
 extern "C" int grx_ppo_normalize_advantages(grx_ppo *p, void *stream) {
     if (!p) return grx_set_error(GRX_E_INVALID, "null ppo");
+    grx_count_launch();
     normalize_adv_kernel<<<296, 256, 0, (cudaStream_t)stream>>>(p->s_adv, p->moments, (size_t)p->T * p->N);
     CK(cudaGetLastError());
     return GRX_OK;
@@ -1265,6 +1299,7 @@ static int minibatch_grads(grx_ppo *p, const int64_t *d_indices, int mb, bool de
         a.dmu = p->da[3]; a.dv = p->dc[3]; a.gstd = gr; a.tail = gr + p->nparam;
         a.B = B; a.A = p->A; a.clip = p->cfg.clip_param; a.vcoef = p->cfg.value_loss_coef; a.ecoef = p->cfg.entropy_coef;
         a.clipped_value = p->cfg.use_clipped_value_loss;
+        grx_count_launch();
         ppo_loss_kernel<<<(B + 255) / 256, 256, 0, st>>>(a);
         TMARK(4);
         TMARK(5);
@@ -1278,12 +1313,14 @@ static int minibatch_grads(grx_ppo *p, const int64_t *d_indices, int mb, bool de
 static int minibatch_apply(grx_ppo *p, cudaStream_t st, bool use_comm) {
     const float *gsrc = p->reduce_buf;
     if (use_comm) {   // NVLink all-reduce + norm in one kernel; the summed gradient lands in gsum on every rank
-        allreduce_kernel<<<64, 256, 0, st>>>(p->comm, (int)((p->nparam + TAIL) / 4), (int)(p->nparam / 4), p->ctl);
+        grx_count_launch();
+        allreduce_kernel<<<64, 256, 0, st>>>(p->comm, (int)((p->nparam + TAIL) / 4), (int)(p->nparam / 4), p->ctl, p->comm_budget_ns);
         gsrc = p->gsum;
     } else {
     }
     PrepArgs a; memset(&a, 0, sizeof(a));
-    a.comm_flags = use_comm ? p->flags : nullptr; a.comm_rank = p->comm.rank;
+    a.comm_flags = use_comm ? p->flags : nullptr; a.comm_rank = p->comm.rank; a.budget_ns = p->comm_budget_ns;
+    a.mb_log = p->mb_log; a.mb_log_cap = p->mb_log_cap;
     a.ctl = p->ctl; a.tail = gsrc + p->nparam; a.std = p->params; a.A = p->A; a.adaptive = p->cfg.adaptive_schedule;
     a.world_size = p->cfg.world_size; a.desired_kl = p->cfg.desired_kl; a.lr_min = p->cfg.learning_rate_min; a.lr_max = p->cfg.learning_rate_max;
     a.max_grad_norm = p->cfg.max_grad_norm; a.vcoef = p->cfg.value_loss_coef; a.ecoef = p->cfg.entropy_coef;
@@ -1375,6 +1412,7 @@ extern "C" int grx_ppo_update(grx_ppo *p, const int64_t *d_indices, void *stream
         cudaStream_t cs;
         CK(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
         cudaGraph_t gr;
+        const unsigned long long before_capture = g_grx_launches.load();
         CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
         int rc = 0;
         for (int mb = 0; mb < p->cfg.num_mini_batches && !rc; mb++) {   // one graph = one epoch (the gather reads the device-side counter)
@@ -1383,13 +1421,15 @@ extern "C" int grx_ppo_update(grx_ppo *p, const int64_t *d_indices, void *stream
         }
         cudaError_t ce = cudaStreamEndCapture(cs, &gr);
         cudaStreamDestroy(cs);
+        p->graph_kernels = g_grx_launches.load() - before_capture;   // recorded, not executed: counted per replay below
+        g_grx_launches.store(before_capture);
         if (rc) return rc;
         CK(ce);
         CK(cudaGraphInstantiate(&p->graph, gr, 0));
         cudaGraphDestroy(gr);
         p->graph_indices = d_indices;
     }
-    for (int i = 0; i < p->cfg.num_learning_epochs; i++) CK(cudaGraphLaunch(p->graph, st));
+    for (int i = 0; i < p->cfg.num_learning_epochs; i++) { CK(cudaGraphLaunch(p->graph, st)); grx_count_launch(p->graph_kernels); }
     return GRX_OK;
 }
 

@@ -66,7 +66,8 @@ class PPOCfg(C.Structure):
                 ("num_mini_batches", I32), ("clip_param", F), ("gamma", F), ("lam", F), ("value_loss_coef", F),
                 ("entropy_coef", F), ("learning_rate", F), ("learning_rate_min", F), ("learning_rate_max", F),
                 ("desired_kl", F), ("max_grad_norm", F), ("adaptive_schedule", I32), ("use_clipped_value_loss", I32),
-                ("init_noise_std", F), ("use_tensor_cores", I32), ("world_size", I32)]
+                ("init_noise_std", F), ("use_tensor_cores", I32), ("world_size", I32),
+                ("env_id_offset", I32), ("comm_timeout_ms", I32), ("seed", U64)]
 
 
 class GrxError(RuntimeError):
@@ -86,6 +87,7 @@ def lib():
         _lib.grx_last_error.restype = C.c_char_p
         _lib.grx_env_accum_slot.restype = C.c_int64
         _lib.grx_env_accum_slot.argtypes = [C.c_void_p]
+        _lib.grx_debug_launch_count.restype = C.c_uint64
         sizes = (I32 * 5)()
         _lib.grx_abi_sizes(sizes, 5)
         want = [C.sizeof(Buffer), C.sizeof(ModelDesc), C.sizeof(TaskCfg), C.sizeof(InjectedPhysics), C.sizeof(PPOCfg)]
@@ -99,9 +101,9 @@ def check(rc):
         raise GrxError(f"grx error {rc}: {lib().grx_last_error().decode()}")
 
 
-EXPORTED = ["grx_last_error", "grx_version", "grx_abi_sizes", "grx_env_create", "grx_env_destroy",
+EXPORTED = ["grx_last_error", "grx_version", "grx_abi_sizes", "grx_debug_launch_count", "grx_env_create", "grx_env_destroy",
             "grx_env_set_terrain_plane", "grx_env_set_terrain_heightfield", "grx_env_set_terrain_trimesh", "grx_env_set_params", "grx_env_get_buffer",
-            "grx_env_step", "grx_env_reset_idx", "grx_env_accum_slot", "grx_env_post_physics", "grx_env_step_host", "grx_env_debug_dynamics",
+            "grx_env_step", "grx_env_reset_idx", "grx_env_accum_slot", "grx_env_post_physics", "grx_env_step_host", "grx_env_debug_dynamics", "grx_env_debug_active_sig",
             "grx_ppo_create", "grx_ppo_destroy", "grx_ppo_get_buffer", "grx_ppo_act", "grx_ppo_process_env_step",
             "grx_ppo_compute_returns", "grx_ppo_compute_returns_local", "grx_ppo_normalize_advantages",
             "grx_ppo_minibatch_grads", "grx_ppo_minibatch_apply", "grx_ppo_update", "grx_ppo_comm_handle", "grx_ppo_comm_open",

@@ -26,8 +26,8 @@ from .urdf import builtin_model
 REWARD_NAMES = list(L._SIGMAS[:21]) + ["on_the_air", "pose_offset", "stand_still"]   # alphabetical
 assert REWARD_NAMES == sorted(REWARD_NAMES) and len(REWARD_NAMES) == 24
 
-_TORCH_DT = {0: torch.float32, 3: torch.uint8, 4: torch.int16, 5: torch.int32}
-_TYPESTR = {0: "<f4", 3: "|u1", 4: "<i2", 5: "<i4"}
+_TORCH_DT = {0: torch.float32, 2: torch.int64, 3: torch.uint8, 4: torch.int16, 5: torch.int32}
+_TYPESTR = {0: "<f4", 2: "<i8", 3: "|u1", 4: "<i2", 5: "<i4"}   # u64 buffers are exposed as int64 bit patterns (torch has no uint64 arithmetic)
 
 
 class _DevArray:
@@ -35,7 +35,7 @@ class _DevArray:
 
     def __init__(self, buf: L.Buffer, owner):
         nd = buf.ndim
-        item = {0: 4, 3: 1, 4: 2, 5: 4}[buf.dtype]
+        item = {0: 4, 2: 8, 3: 1, 4: 2, 5: 4}[buf.dtype]
         self.owner = owner
         self.__cuda_array_interface__ = {
             "shape": tuple(int(buf.dims[i]) for i in range(nd)),
@@ -84,6 +84,11 @@ def task_cfg(cfg, tables, seed=1, env_id_offset=0):
     (legged_robot.py:91-104), _prepare_reward_function (:840-866) and compute_noise_scale_vec_profile
     (gr1t1.py:315-336) derive at construction."""
     t = L.TaskCfg()
+    # options of the reference the fused kernel does not implement must not be silently ignored
+    if getattr(cfg.control, "control_type", "P") != "P":
+        raise L.GrxError(f"control_type={cfg.control.control_type!r}: the fused kernel implements the 'P' law of the registered GRx tasks (legged_robot.py:691-700)")
+    if getattr(cfg.rewards, "only_positive_rewards", False):
+        raise L.GrxError("rewards.only_positive_rewards=True is not implemented (registered GRx tasks: False, gr1t1_config.py:188)")
     px = cfg.sim.physx
     t.sim_dt, t.gravity = cfg.sim.dt, cfg.sim.gravity[2]
     t.contact_offset, t.bounce_threshold, t.max_depen_vel = px.contact_offset, px.bounce_threshold_velocity, px.max_depenetration_velocity
@@ -155,12 +160,14 @@ def quat_rotate_inverse(q, v):
 
 
 class _EpisodeInfo(dict):
-    """extras["episode"] (legged_robot.py:420-427) evaluated lazily from one slot of the device accumulator ring:
-    building 25 0-d tensors eagerly would cost 25+ launches per step for values that are read once per iteration."""
+    """extras["episode"] (legged_robot.py:420-427) evaluated lazily from the device accumulator ring: building 25 0-d tensors eagerly
+    would cost 25+ launches per step for values that are read once per iteration.  On a step where nothing reset, the reference leaves
+    the PREVIOUS non-empty dict in extras (reset_idx returns early, legged_robot.py:387-388); evaluating lazily, the same is obtained by
+    walking the ring back from this launch's slot to the most recent slot with a non-zero reset count (ring = 256 launches deep)."""
 
-    def __init__(self, slot_view, names, inv_len_s, num_envs_total, curriculum):
+    def __init__(self, ring, slot, names, inv_len_s, num_envs_total, curriculum):
         super().__init__()
-        self._v, self._names, self._s, self._n = slot_view, names, inv_len_s, num_envs_total
+        self._ring, self._slot, self._names, self._s, self._n = ring, slot, names, inv_len_s, num_envs_total
         keys = ["rew_" + n for n in names] + (["terrain_level"] if curriculum else [])
         for k in keys:
             dict.__setitem__(self, k, None)
@@ -168,12 +175,17 @@ class _EpisodeInfo(dict):
 
     def _fill(self):
         if not self._done:
-            v = self._v.clone()
-            cnt = torch.clamp(v[24], min=1.0)
-            for i, n in enumerate(self._names):
-                dict.__setitem__(self, "rew_" + n, v[i] / cnt * self._s)
+            ring = self._ring.clone()
+            n = ring.shape[0]
+            order = (self._slot - torch.arange(n, device=ring.device)) % n            # this slot, the previous one, ...
+            cnts = ring[order, 24]
+            nz = torch.nonzero(cnts > 0)
+            src = ring[order[nz[0, 0]]] if nz.numel() else ring[self._slot]
+            cnt = torch.clamp(src[24], min=1.0)
+            for i, nme in enumerate(self._names):
+                dict.__setitem__(self, "rew_" + nme, src[i] / cnt * self._s)
             if "terrain_level" in self.keys():
-                dict.__setitem__(self, "terrain_level", v[25] / self._n)
+                dict.__setitem__(self, "terrain_level", ring[self._slot][25] / self._n)   # computed on every step (legged_robot.py:427 runs with the resets; the level sum is over ALL envs)
             self._done = True
 
     def __getitem__(self, k):
@@ -415,7 +427,7 @@ class GRXVecEnv:
         if self.sync_extras:   # reference-exact staleness: rebuild only when something reset; costs a host sync
             if not from_reset and not bool(self._reset_u8.any()):
                 return
-        self.extras["episode"] = _EpisodeInfo(self._accum[slot], self.reward_names, 1.0 / self.max_episode_length_s,
+        self.extras["episode"] = _EpisodeInfo(self._accum, slot, self.reward_names, 1.0 / self.max_episode_length_s,
                                               float(self.num_envs), bool(self.cfg.terrain.curriculum))
         if self.cfg.env.send_timeouts:
             self.extras["time_outs"] = self.time_out_buf
@@ -451,6 +463,13 @@ class GRXVecEnv:
         torch.cuda.synchronize(self.device)
         self._publish_extras(False)
         return self.obs_buf, self.pri_obs_buf, self.rew_buf, self.reset_buf, self.extras
+
+    def debug_active_sig(self, enable=True):
+        """Parity tests: export the per-substep active-set signature (include/grx_b200.h grx_env_debug_active_sig); returns the
+        [N, 16] int64 view (bit patterns of the u64 hashes) or None when switched off."""
+        L.check(self.lib.grx_env_debug_active_sig(self._h, int(bool(enable))))
+        self.active_sig = self._view("active_sig") if enable else None
+        return self.active_sig
 
     def debug_dynamics(self, index):
         nv = self.model["nd"] + 6

@@ -78,12 +78,18 @@ class ActorCriticMLP:
     one flat device vector laid out in the reference's state_dict order (SURVEY.md §5 checkpoint row)."""
 
     def __init__(self, actor_num_input, critic_num_input, actor_num_output, actor_hidden_dims=(512, 256, 128),
-                 critic_hidden_dims=(512, 256, 128), activation="elu", init_noise_std=1.0, fixed_std=False,
-                 set_std=True, set_noise_std=1.0, **kwargs):
+                 critic_hidden_dims=(512, 256, 128), activation="elu", fixed_std=False, init_noise_std=1.0,
+                 set_std=True, set_noise_std=1.0, actor_output_activation=None, critic_output_activation=None, **kwargs):
+        # positional order == actor_critic_mlp.py:12-25
         if activation != "elu" or len(actor_hidden_dims) != 3 or len(critic_hidden_dims) != 3:
             raise L.GrxError("the CUDA policy implements the registered architecture: 3 hidden layers, ELU")
         if fixed_std:
             raise L.GrxError("fixed_std=True is not implemented (registered tasks use fixed_std=False, gr1t1_config.py:345)")
+        if actor_output_activation is not None or critic_output_activation is not None:
+            raise L.GrxError("output activations are not implemented (registered tasks use None)")
+        if kwargs:   # actor_critic_mlp.py:45-47 prints and ignores
+            import warnings
+            warnings.warn("ActorCritic.__init__ got unexpected arguments, which will be ignored: " + str(list(kwargs.keys())))
         self.num_actor_input, self.num_critic_input, self.num_actor_output = actor_num_input, critic_num_input, actor_num_output
         self.actor_hidden_dims, self.critic_hidden_dims = list(actor_hidden_dims), list(critic_hidden_dims)
         self.init_noise_std, self.set_std, self.set_noise_std = init_noise_std, set_std, set_noise_std
@@ -166,11 +172,20 @@ class PPO:
     """Same constructor arguments and methods as rsl_rl's PPO (ppo.py:24-110)."""
 
     def __init__(self, actor_critic, num_learning_epochs=1, num_mini_batches=1, clip_param=0.2, gamma=0.998, lam=0.95,
-                 value_loss_coef=1.0, entropy_coef=0.0, learning_rate=1e-3, learning_rate_min=1e-5, learning_rate_max=1e-3,
+                 value_loss_coef=1.0, entropy_coef=0.0, learning_rate=1e-3, learning_rate_min=1e-5, learning_rate_max=1e-2,
                  max_grad_norm=1.0, use_clipped_value_loss=True, schedule="fixed", desired_kl=0.01, device="cuda:0",
-                 storage_class="RolloutStorage", use_tensor_cores=1, world_size=1, process_group=None, **kwargs):
+                 storage_class="RolloutStorage", use_tensor_cores=1, world_size=1, process_group=None, seed=1, env_id_offset=0,
+                 comm_timeout_ms=0, weight_decay=0.0, **kwargs):
+        """seed / env_id_offset: the task seed and the global index of this rank's env 0 — the action-noise stream of ``act`` is keyed by
+        (seed, global env id, step), so W ranks draw exactly what one GPU holding all envs would."""
         if not torch.cuda.is_available():
             raise L.GrxError("PPO needs a CUDA device (no CPU fallback)")
+        if weight_decay:
+            raise L.GrxError("weight_decay != 0 is not implemented by the fused Adam kernel (the registered tasks use 0, ppo.py:81)")
+        if kwargs:   # ppo.py:98-102 prints the unexpected arguments and ignores them; do the same, loudly
+            import warnings
+            warnings.warn("PPO.__init__ got unexpected arguments, which will be ignored: " + str(list(kwargs.keys())))
+        self.seed, self.env_id_offset, self.comm_timeout_ms = int(seed), int(env_id_offset), int(comm_timeout_ms)
         self.lib = L.lib()
         self.device = torch.device(device)
         self.actor_critic = actor_critic
@@ -204,6 +219,7 @@ class PPO:
         c.adaptive_schedule = int(self.desired_kl is not None and self.schedule == "adaptive")   # ppo.py:253
         c.use_clipped_value_loss = int(self.use_clipped_value_loss)
         c.init_noise_std, c.use_tensor_cores, c.world_size = ac.init_noise_std, int(self.use_tensor_cores), self.world_size
+        c.seed, c.env_id_offset, c.comm_timeout_ms = self.seed, self.env_id_offset, self.comm_timeout_ms
         self._cfg = c
         self._h = C.c_void_p()
         dev = self.device.index if self.device.index is not None else torch.cuda.current_device()
@@ -213,6 +229,7 @@ class PPO:
         self.params, self.grads, self.reduce_buf = v("params"), v("grads"), v("reduce_buf")
         self.adam_m, self.adam_v = v("adam_m"), v("adam_v")
         self.ctl = v("ctl")
+        self.mb_log = v("mb_log")       # [epochs * minibatches, 4]: (mean KL, lr, loss, grad norm) per minibatch of the last update
         self.storage = _Storage({k: v(k) for k in ("obs", "critic_obs", "actions", "values", "rewards", "dones",
                                                    "actions_log_prob", "mu", "sigma", "returns", "advantages")})
         self._moments = v("adv_moments").view(torch.float64)
@@ -221,7 +238,12 @@ class PPO:
         self.mini_batch_size = (num_envs * num_transitions_per_env) // self.num_mini_batches
         self._indices = torch.zeros(self.num_mini_batches * self.mini_batch_size, dtype=torch.int64, device=self.device)
         self._comm = False
-        if self.world_size > 1:
+        self._err_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._err_event = None
+        # world_size > 1 with an initialised process group: we own the collectives (weights broadcast now; per minibatch the in-graph
+        # NVLink all-reduce, or NCCL with GRX_COMM=nccl).  Without one the caller drives them through the stepwise entries.
+        self._dist = self.world_size > 1 and torch.distributed.is_available() and torch.distributed.is_initialized()
+        if self._dist:
             self.broadcast_parameters()
             if os.environ.get("GRX_COMM", "nvlink") == "nvlink":
                 self._open_comm()
@@ -314,6 +336,9 @@ class PPO:
         p = C.c_void_p(last_critic_obs.data_ptr())
         if self.world_size == 1:
             L.check(self.lib.grx_ppo_compute_returns(self._h, p, self._stream()))
+        elif not self._dist:
+            raise L.GrxError("world_size > 1 without torch.distributed: call grx_ppo_compute_returns_local, all-reduce `adv_moments`, "
+                             "then grx_ppo_normalize_advantages yourself")
         else:   # global advantage statistics: one 3-double all-reduce per iteration
             L.check(self.lib.grx_ppo_compute_returns_local(self._h, p, self._stream()))
             torch.distributed.all_reduce(self._moments[:3], group=self.process_group)
@@ -329,7 +354,22 @@ class PPO:
         self._indices.copy_(torch.randperm(n, device=self.device))
         return self._indices
 
+    def check_comm(self, wait=False):
+        """Raise if a peer-flag / grid-barrier wait of the in-graph NVLink all-reduce timed out (ctl.comm_error, sticky: the device
+        skips every optimiser step from then on, so the replicas never diverge silently).  The flag travels to pinned host memory
+        asynchronously after every update; without ``wait`` only an already finished copy is inspected (no host sync)."""
+        if self._err_event is None:
+            return
+        if wait:
+            self._err_event.synchronize()
+        if self._err_event.query() and int(self._err_host[0]) != 0:
+            code = int(self._err_host[0])
+            raise L.GrxError(f"grx_b200: multi-GPU gradient all-reduce failed (comm_error={code}: "
+                             + ("a peer rank did not arrive within comm_timeout_ms" if code == 1 else "apply grid barrier timed out")
+                             + "); optimiser steps were skipped from that minibatch on — restart from the last checkpoint")
+
     def update(self, indices=None):                                                     # ppo.py:215-321
+        self.check_comm()
         if indices is None:
             indices = self.draw_indices()
         else:
@@ -337,6 +377,9 @@ class PPO:
         idx = C.c_void_p(self._indices.data_ptr())
         if self.world_size == 1 or self._comm:
             L.check(self.lib.grx_ppo_update(self._h, idx, self._stream()))
+        elif not self._dist:
+            raise L.GrxError("world_size > 1 without torch.distributed: drive grx_ppo_minibatch_grads / all-reduce(reduce_buf) / "
+                             "grx_ppo_minibatch_apply yourself")
         else:
             self.ctl[11:14].zero_()
             for _ in range(self.num_learning_epochs):
@@ -344,6 +387,10 @@ class PPO:
                     L.check(self.lib.grx_ppo_minibatch_grads(self._h, idx, mb, self._stream()))
                     torch.distributed.all_reduce(self.reduce_buf, group=self.process_group)   # ONE all-reduce per minibatch
                     L.check(self.lib.grx_ppo_minibatch_apply(self._h, self._stream()))
+        if self.world_size > 1:   # comm_error -> pinned host memory, inspected by the next check_comm() (no sync here)
+            self._err_host.copy_(self.ctl[17:18].view(torch.int32), non_blocking=True)
+            self._err_event = torch.cuda.Event()
+            self._err_event.record()
         n = self.num_learning_epochs * self.num_mini_batches
         self.last_losses = self.ctl[11:13] / n                                          # device tensor; ppo.py:314-316
         return _LazyFloat(self.last_losses, 0), _LazyFloat(self.last_losses, 1)
@@ -374,7 +421,8 @@ class PPO:
         group = {"lr": self.learning_rate, "betas": (0.9, 0.999), "eps": 1e-8, "weight_decay": 0, "amsgrad": False,
                  "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
                  "params": list(range(len(state)))}
-        return {"state": state, "param_groups": [group]}
+        # extra top-level key (torch.optim.Optimizer.load_state_dict reads only "state" / "param_groups"): counters of our RNG streams
+        return {"state": state, "param_groups": [group], "grx_b200": {"act_counter": int(self._act_counter)}}
 
     def load_optimizer_state_dict(self, sd):
         ac = self.actor_critic
@@ -387,6 +435,7 @@ class PPO:
             self.ctl[3:4].view(torch.int32).fill_(step)
             self.ctl[24:28].view(torch.float64).copy_(torch.tensor([0.9 ** step, 0.999 ** step], dtype=torch.float64))   # running beta^step
         self.learning_rate = sd["param_groups"][0]["lr"]
+        self._act_counter = int(sd.get("grx_b200", {}).get("act_counter", self._act_counter))
 
 
 class _Storage:

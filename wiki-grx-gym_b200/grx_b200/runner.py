@@ -27,8 +27,11 @@ class OnPolicyRunner:
         self.env = env
         critic_in = env.num_pri_obs if env.num_pri_obs is not None else env.num_obs       # on_policy_runner.py:71-76
         actor_critic = ActorCriticMLP(env.num_obs, critic_in, env.num_actions, **self.policy_cfg)
+        # the action-noise stream is keyed by (task seed, GLOBAL env id, step): sharded ranks draw what one big env would
+        rng_kw = dict(seed=int(getattr(getattr(env, "cfg", None), "seed", 1)), env_id_offset=int(getattr(env, "env_id_offset", 0)))
+        rng_kw.update({k: self.algorithm_cfg.pop(k) for k in ("seed", "env_id_offset") if k in self.algorithm_cfg})
         self.algorithm = PPO(actor_critic=actor_critic, device=device, world_size=world_size, process_group=process_group,
-                             **self.algorithm_cfg)
+                             **rng_kw, **self.algorithm_cfg)
         self.alg = self.algorithm
         self.num_steps_per_env = self.cfg["num_steps_per_env"]
         self.save_interval = self.cfg["save_interval"]
@@ -133,6 +136,7 @@ class OnPolicyRunner:
         self.last_scalars = scalars
 
     def save(self, path, infos=None):                                                     # on_policy_runner.py:297-309
+        self.algorithm.check_comm(wait=True)   # never checkpoint replicas that stopped stepping because a peer went missing
         torch.save({"model_state_dict": {k: v.detach().contiguous().cpu().clone() for k, v in self.algorithm.actor_critic.state_dict().items()},
                     "optimizer_state_dict": self.algorithm.optimizer_state_dict(),
                     "iter": self.current_learning_iteration, "infos": infos}, path)
