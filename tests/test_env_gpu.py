@@ -10,7 +10,7 @@ import pytest
 import torch
 
 from golden_util import ENV_FIXTURES, load_fixture, step_items
-from parity_util import PHYS_FORCE_TOL, PHYS_TOL, PHYS_VEL_TOL, POST_TOL, make_gpu_env
+from parity_util import OBS_VEL_COLS, PHYS_FORCE_TOL, PHYS_TOL, PHYS_TORQUE_TOL, PHYS_VEL_TOL, POST_TOL, PRI_VEL_COLS, make_gpu_env
 
 pytestmark = pytest.mark.gpu
 
@@ -94,14 +94,20 @@ def _full_step_compare(name, report):
         n_flip += int((~same).sum())
         msg = f"{name} t={t}"
         assert (~same).sum() <= max(1, N // 16), f"{msg}: {(~same).sum()} of {N} envs took a different contact/limit decision"
-        for nm, got, ref, tol in (("torques", env.torques, ora.torques, PHYS_TOL), ("obs", obs, o_obs, PHYS_TOL), ("pri_obs", pri, o_pri, PHYS_TOL),
+        for nm, got, ref, tol in (("torques", env.torques, ora.torques, PHYS_TORQUE_TOL), ("obs", obs, o_obs, PHYS_TOL), ("pri_obs", pri, o_pri, PHYS_TOL),
                                   ("rew", rew, o_rew, PHYS_TOL), ("root_states", env.root_states, ora.root_states, PHYS_TOL),
                                   ("dof_pos", env.dof_pos, ora.dof_pos, PHYS_TOL), ("dof_vel", env.dof_vel, ora.dof_vel, PHYS_VEL_TOL),
                                   ("contact_forces", env.contact_forces, ora.contact_forces, PHYS_FORCE_TOL)):
             g_, r_ = got.cpu().numpy()[same], np.asarray(ref.numpy() if hasattr(ref, "numpy") else ref)[same]
-            report.setdefault(nm, 0.0)
-            report[nm] = max(report[nm], float(np.abs(g_ - r_).max()) if g_.size else 0.0)
-            np.testing.assert_allclose(g_, r_, err_msg=f"{msg} {nm} (envs with identical active sets)", **tol)
+            if g_.size:
+                err = np.abs(g_ - r_)
+                report[nm] = max(report.get(nm, 0.0), float(err.max()))
+                # worst error in units of the stated tolerance (<= 1 passes); all quantities are reported before anything fails
+                bound = tol["atol"] + tol["rtol"] * np.abs(r_)
+                vel_cols = {"obs": OBS_VEL_COLS, "pri_obs": PRI_VEL_COLS, "root_states": list(range(7, 13))}.get(nm)
+                if vel_cols is not None:   # velocity columns of a mixed array carry the velocity tolerance
+                    bound[:, vel_cols] = PHYS_VEL_TOL["atol"] + PHYS_VEL_TOL["rtol"] * np.abs(r_[:, vel_cols])
+                report["tolfrac/" + nm] = max(report.get("tolfrac/" + nm, 0.0), float((err / bound).max()))
         np.testing.assert_array_equal(reset.cpu().numpy()[same], o_reset.numpy()[same], err_msg=msg)
         for tns in (obs, pri, rew, env.root_states):                                      # the flipped envs still hold sane values
             assert bool(torch.isfinite(tns).all())
@@ -113,20 +119,22 @@ def _full_step_compare(name, report):
 @pytest.mark.parametrize("name", ENV_FIXTURES)
 def test_full_step_matches_oracle(name):
     rep = _full_step_compare(name, {})
-    print(f"{name}: max |CUDA - C oracle| over envs with identical active sets: "
-          + ", ".join(f"{k} {v:.2e}" for k, v in rep.items() if k not in ("flipped_env_steps", "env_steps"))
+    print(f"\n{name}: max |CUDA - C oracle| over envs with identical active sets: "
+          + ", ".join(f"{k} {v:.2e} ({rep['tolfrac/' + k]:.2f} of tol)" for k, v in rep.items() if "/" not in k and k not in ("flipped_env_steps", "env_steps"))
           + f"; {rep['flipped_env_steps']} of {rep['env_steps']} env-steps took a different contact/limit decision")
     assert rep["flipped_env_steps"] <= rep["env_steps"] // 32
+    bad = {k: v for k, v in rep.items() if k.startswith("tolfrac/") and v > 1.0}
+    assert not bad, f"{name}: envs with IDENTICAL active sets differ beyond the stated tolerance: {bad}" 
 
 
 def test_single_substep_error():
     """Per-SUBSTEP error (fixture plane64_dec1: decimation 1, one 2 ms substep per policy step) reported separately from the
     10-substep error above; stated bound 2e-4 abs on the state, an order of magnitude below the per-policy-step tolerance."""
     rep = _full_step_compare("plane64_dec1", {})
-    print("single substep: " + ", ".join(f"{k} {v:.2e}" for k, v in rep.items()))
-    for k in ("root_states", "dof_pos", "obs"):
-        assert rep[k] < 2e-4, (k, rep[k])
-    assert rep["dof_vel"] < 2e-3
+    print("\nsingle substep: " + ", ".join(f"{k} {v:.2e}" for k, v in rep.items() if "/" not in k))
+    for k in ("root_states", "dof_pos"):
+        assert rep[k] < 5e-5, (k, rep[k])               # measured 5e-6 / 3e-7
+    assert rep["dof_vel"] < 1e-3 and rep["obs"] < 1e-3   # measured 1.7e-4 (joint rates and their observation columns)
 
 
 @pytest.mark.parametrize("robot", ["GR1T1", "GR1T2"])
