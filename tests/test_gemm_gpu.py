@@ -123,3 +123,52 @@ def test_every_macro_tile_configuration(tile):
             assert float((got - ref).abs().max()) <= TF32_RTOL * scale, (tile, variant, M, N, K, float((got - ref).abs().max()) / scale)
     finally:
         L.check(lib.grx_gemm_debug_tile(0, 0))
+
+
+@pytest.mark.parametrize("M,store", [(4096, False), (10485, True), (333, True), (128, False)])
+def test_chained_forward_equals_layerwise(M, store):
+    """The three hidden layers as ONE chained tcgen05 kernel (csrc/grx_mlp_chain.cuh: activations handed from the epilogue warps to the
+    MMA warp as shared-memory A operands) == the same layers as three grouped GEMM launches (same K order on the tensor core, same bias /
+    ELU arithmetic: bit-identical is expected, 1e-6 relative allowed), and == torch fp32 within the TF32 tolerance.  store=False is the
+    rollout variant (only the last hidden layer is written to HBM)."""
+    from grx_b200 import _lib as L
+    from grx_b200.config import make_train_cfg
+    from grx_b200.ppo import PPO, ActorCriticMLP
+    lib = L.lib()
+    tc = make_train_cfg()
+    torch.manual_seed(31)
+    N, T = (M, 4) if not store else (M * 4 // 4, 4)           # update path: minibatch of N*T/4 = M rows
+    ac = ActorCriticMLP(39, 168, 10, **tc["policy"])
+    alg = PPO(ac, device="cuda:0", **dict(tc["algorithm"], num_mini_batches=4, num_learning_epochs=1))
+    alg.init_storage(N, T)
+    g = torch.Generator().manual_seed(M)
+    obs, cobs, eps = torch.randn(N, 39, generator=g).cuda(), torch.randn(N, 168, generator=g).cuda(), torch.randn(N, 10, generator=g).cuda()
+    adv, idx = torch.randn(T, N, 1, generator=g).cuda(), torch.randperm(N * T, generator=g).cuda()
+    res = {}
+    for fused in (1, 0):
+        old = lib.grx_ppo_debug_fused(fused)
+        alg.step = 0
+        if not store:   # rollout: PPO.act
+            a = alg.act(obs, cobs, eps=eps).clone()
+            res[fused] = (a, alg.storage.mu[0].clone(), alg.storage.values[0].clone(), alg.storage.actions_log_prob[0].clone())
+        else:           # update: one minibatch's forward + backward through the stepwise entry
+            for t in range(T):
+                alg.act(obs, cobs, eps=eps)
+                alg.process_env_step(torch.zeros(N, device="cuda"), torch.zeros(N, dtype=torch.bool, device="cuda"), {})
+            alg.compute_returns(cobs)
+            alg.storage.advantages.copy_(adv)
+            alg._indices.copy_(idx)
+            import ctypes as C
+            L.check(lib.grx_ppo_minibatch_grads(alg._h, C.c_void_p(alg._indices.data_ptr()), 2, alg._stream()))
+            res[fused] = (alg.grads.clone(), alg.reduce_buf[-8:].clone())
+        torch.cuda.synchronize()
+        assert alg.minibatch_stats()["chain_error"] == 0, "a barrier wait inside the chained kernel timed out"
+        lib.grx_ppo_debug_fused(old)
+    for x, y in zip(res[1], res[0]):
+        scale = float(y.abs().max()) + 1e-30
+        assert float((x - y).abs().max()) <= 1e-5 * scale, (M, store, float((x - y).abs().max()), scale)
+    if not store:   # and against plain torch fp32
+        with torch.no_grad():
+            mu = ac.actor.to_module()(obs.cpu())
+        np.testing.assert_allclose(res[1][1].cpu().numpy(), mu.numpy(), rtol=0, atol=6e-3 * float(mu.abs().max()))
+    alg.close()

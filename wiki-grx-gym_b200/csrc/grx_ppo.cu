@@ -19,6 +19,7 @@
 #include "grx_b200.h"
 #include "grx_count.h"
 #include "grx_gemm_tc.cuh"
+#include "grx_mlp_chain.cuh"
 
 int grx_set_error(int code, const std::string &msg);   // grx_env.cu
 
@@ -732,7 +733,8 @@ struct Ctl {            // device control block
     unsigned comm_arrive;   // scratch: blocks of allreduce_kernel that finished their slice
     unsigned apply_arrive;  // scratch: grid barrier of apply_kernel (blocks that contributed their partial gradient norm)
     unsigned apply_done;    // scratch: blocks of apply_kernel that have read the barrier results (the last one resets the scratch)
-    int pad_[3];
+    int chain_error;        // set by the chained-layer kernels (grx_mlp_chain.cuh) when a barrier wait timed out (protocol error; results invalid)
+    int pad_[2];
     double pow1, pow2;      // beta1^step, beta2^step as running products (fp64 pow is a ~10 us dependent chain on this part)
 };
 
@@ -1133,8 +1135,29 @@ struct NetIO {
     float *const *h;
     float *const *d;
 };
-static void mlp_forward(grx_ppo *p, const NetIO *io, int nn, int M, int nlayers, cudaStream_t st) {
-    for (int l = 0; l < nlayers; l++) {
+static void mlp_forward(grx_ppo *p, const NetIO *io, int nn, int M, int nlayers, cudaStream_t st, bool store_hidden = true) {
+    int l0 = 0;
+    if (p->cfg.use_tensor_cores != 0 && tc::chain::fwd_enabled() && nlayers >= 3 && nn <= 2) {
+        // registered widths: the three hidden layers as ONE chained tcgen05 kernel (grx_mlp_chain.cuh); activations stay on chip between layers
+        tc::chain::FwdProblem ps[2];
+        bool ok = true;
+        for (int i = 0; i < nn; i++) {
+            const Net &net = *io[i].net;
+            ok = ok && net.dims[1] == tc::chain::D1 && net.dims[2] == tc::chain::D2 && net.dims[3] == tc::chain::D3;
+            tc::chain::FwdProblem &q = ps[i];
+            q.X = io[i].x; q.K0 = net.dims[0]; q.ldx = io[i].ldx;
+            q.W0 = p->params + net.w[0]; q.b0 = p->params + net.b[0]; q.ld0 = net.ld[0];
+            q.W1 = p->params + net.w[1]; q.b1 = p->params + net.b[1];
+            q.W2 = p->params + net.w[2]; q.b2 = p->params + net.b[2];
+            q.H1 = io[i].h[0]; q.H2 = io[i].h[1]; q.H3 = io[i].h[2];
+        }
+        if (ok && tc::chain::fwd_supported(ps, nn)) {
+            const cudaError_t e = tc::chain::launch_fwd(ps, nn, M, store_hidden, &p->ctl->chain_error, st);
+            if (e != cudaSuccess && g_launch_err == cudaSuccess) g_launch_err = e;
+            l0 = 3;
+        }
+    }
+    for (int l = l0; l < nlayers; l++) {
         GemmArgs g[2];
         for (int i = 0; i < nn; i++) {
             const Net &net = *io[i].net;
@@ -1196,7 +1219,7 @@ extern "C" int grx_ppo_act(grx_ppo *p, const float *d_obs, const float *d_critic
     CK(stage_rows(p->xc, p->Ppad, d_critic_obs, p->P, p->N, st));
     const NetIO io[2] = {{&p->actor, p->xa, p->Opad, p->ha, p->da}, {&p->critic, p->xc, p->Ppad, p->hc, p->dc}};
     const bool fused_heads = p->A == 10 && p->critic.dims[4] == 1 && p->actor.dims[3] == HEADS_H && p->critic.dims[3] == HEADS_H;
-    mlp_forward(p, io, 2, p->N, fused_heads ? 3 : 4, st);
+    mlp_forward(p, io, 2, p->N, fused_heads ? 3 : 4, st, false);   // rollout: only the last hidden layer leaves the chip
     ActArgs a; memset(&a, 0, sizeof(a));
     const size_t row = (size_t)t * p->N;
     a.obs = d_obs; a.critic_obs = d_critic_obs; a.mu = p->ha[3]; a.value = p->hc[3]; a.std = p->params; a.eps = d_eps;
@@ -1234,7 +1257,7 @@ extern "C" int grx_ppo_compute_returns_local(grx_ppo *p, const float *d_last_cri
     cudaStream_t st = (cudaStream_t)stream;
     CK(stage_rows(p->xc, p->Ppad, d_last_critic_obs, p->P, p->N, st));
     const NetIO io = {&p->critic, p->xc, p->Ppad, p->hc, p->dc};
-    mlp_forward(p, &io, 1, p->N, 4, st);                                               // ppo.py:204
+    mlp_forward(p, &io, 1, p->N, 4, st, false);                                        // ppo.py:204
     CK(cudaMemcpyAsync(p->last_values, p->hc[3], (size_t)p->N * 4, cudaMemcpyDeviceToDevice, st));
     CK(cudaMemsetAsync(p->moments, 0, 4 * sizeof(double), st));
     grx_count_launch();
@@ -1438,9 +1461,16 @@ extern "C" int grx_ppo_act_inference(grx_ppo *p, const float *d_obs, int32_t n, 
     cudaStream_t st = (cudaStream_t)stream;
     CK(stage_rows(p->xa, p->Opad, d_obs, p->O, n, st));
     const NetIO io = {&p->actor, p->xa, p->Opad, p->ha, p->da};
-    mlp_forward(p, &io, 1, n, 4, st);
+    mlp_forward(p, &io, 1, n, 4, st, false);
     CK(cudaMemcpyAsync(d_actions_out, p->ha[3], (size_t)n * p->A * 4, cudaMemcpyDeviceToDevice, st));
     return GRX_OK;
+}
+
+// Test / profiling: switch the chained-layer kernels (grx_mlp_chain.cuh) on / off at run time; returns the previous setting of the forward chain.
+extern "C" int grx_ppo_debug_fused(int32_t fwd_chain) {
+    const int old = tc::chain::fwd_flag();
+    if (fwd_chain >= 0) tc::chain::fwd_flag() = fwd_chain;
+    return old;
 }
 
 // Test / profiling: force the macro tile of the tensor-core GEMM ({0, 0} = cost model).  Configurations that do not apply to a launch

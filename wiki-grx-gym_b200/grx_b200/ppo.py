@@ -399,7 +399,8 @@ class PPO:
         c = self.ctl.cpu()
         return dict(lr=float(c[0]), skip=int(c[2:3].view(torch.int32)), step=int(c[3:4].view(torch.int32)), kl=float(c[6]),
                     loss=float(c[7]), value_loss=float(c[8]), surrogate_loss=float(c[9]), grad_norm=float(c[10]),
-                    comm_error=int(c[17:18].view(torch.int32)))   # != 0: a peer flag / grid barrier wait timed out (results invalid)
+                    comm_error=int(c[17:18].view(torch.int32)),   # != 0: a peer flag / grid barrier wait timed out (results invalid)
+                    chain_error=int(c[21:22].view(torch.int32)))  # != 0: a barrier wait inside a chained-layer kernel timed out (protocol bug)
 
     def act_inference(self, obs):
         obs = obs.to(self.device, torch.float32).contiguous()
