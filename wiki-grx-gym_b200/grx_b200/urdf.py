@@ -230,6 +230,30 @@ def base_inertial_for(model, mass_scale=1.0, com_offset=(0.0, 0.0, 0.0)):
     return m, c, _sym6(I)
 
 
+def base_inertials_batch(model, mass_scale, com_offset):
+    """``base_inertial_for`` for N envs at once (no Python loop over envs): mass_scale [N], com_offset [N, 3] -> [N, 10] rows
+    (mass, com xyz, inertia xx yy zz xy xz yz about the composite COM).  Same arithmetic, vectorised (parallel-axis theorem per part)."""
+    mass_scale, com_offset = np.asarray(mass_scale, np.float64), np.asarray(com_offset, np.float64)
+    N = mass_scale.shape[0]
+    r, s = model["root_link_inertial"], model["root_rest_inertial"]
+    m1 = r[0] * mass_scale                                               # [N]
+    c1 = r[1:4][None, :] + com_offset                                    # [N, 3]
+    I1 = sym6_to_mat(r[4:10])[None, :, :] * mass_scale[:, None, None]    # [N, 3, 3]
+    m2, c2, I2 = float(s[0]), s[1:4][None, :], sym6_to_mat(s[4:10])[None, :, :]
+    m = m1 + m2
+    c = (m1[:, None] * c1 + m2 * c2) / m[:, None]
+    eye = np.eye(3)[None, :, :]
+
+    def shifted(pm, pc, pI):
+        d = pc - c
+        return pI + np.asarray(pm).reshape(-1, 1, 1) * ((d * d).sum(1)[:, None, None] * eye - d[:, :, None] * d[:, None, :])
+    I = shifted(m1, c1, I1) + (shifted(np.full(N, m2), np.broadcast_to(c2, (N, 3)), I2) if m2 > 0 else 0.0)
+    out = np.zeros((N, 10))
+    out[:, 0], out[:, 1:4] = m, c
+    out[:, 4], out[:, 5], out[:, 6], out[:, 7], out[:, 8], out[:, 9] = I[:, 0, 0], I[:, 1, 1], I[:, 2, 2], I[:, 0, 1], I[:, 0, 2], I[:, 1, 2]
+    return out
+
+
 MODEL_KEYS = ("parent", "jpos", "jrot", "axis", "mass", "com", "inertia", "root_link_inertial",
               "root_rest_inertial", "dof_lower", "dof_upper", "dof_effort", "dof_velocity", "link_body",
               "link_pos", "link_rot", "sph_body", "sph_link", "sph_pos", "sph_rad")
