@@ -32,17 +32,21 @@ extern "C" {
 #define GRX_E_NOTFOUND (-3) /* unknown buffer name */
 #define GRX_E_STATE (-4)    /* call order violated (e.g. step before set_params) */
 
-/* dtype codes follow GymTensor.h:20-27 (fp32, u32, u64, u8, i16) extended with i32 */
-enum { GRX_F32 = 0, GRX_U32 = 1, GRX_U64 = 2, GRX_U8 = 3, GRX_I16 = 4, GRX_I32 = 5 };
+/* dtype codes == carb::gym::GymTensorDataType (GymTensor.h:20-27: None 0, Fp32 1, Uint32 2, Uint64 3, Uint8 4, Int16 5), extended with
+ * Int32 6 and Int64 7 */
+enum { GRX_NONE = 0, GRX_F32 = 1, GRX_U32 = 2, GRX_U64 = 3, GRX_U8 = 4, GRX_I16 = 5, GRX_I32 = 6, GRX_I64 = 7 };
+#define GRX_MAX_DIMS 8 /* == GYM_TENSOR_MAX_DIMENSIONS (GymTensor.h:11) */
 
-/* Non-owning description of a device buffer (same role as GymTensor; adds element strides because
- * per-env state lives in one array-of-records and is exported as strided views). */
+/* Non-owning description of a device buffer: the fields of carb::gym::GymTensor (GymTensor.h:32-41: device, dtype, numDims, dims[8], data,
+ * ownData) plus element strides, because per-env state lives in one array-of-records and is exported as strided views. */
 typedef struct {
-    void *data;
-    int32_t dtype;
+    int32_t device;     /* CUDA device ordinal (GymTensor::device; never -1: there is no CPU pipeline) */
+    int32_t dtype;      /* GRX_* */
     int32_t ndim;
-    int64_t dims[4];
-    int64_t strides[4]; /* in elements */
+    int32_t own_data;   /* always 0: views stay valid for the lifetime of the env / ppo object (GymTensor::ownData == false, gymtorch.cpp:163-166) */
+    int64_t dims[GRX_MAX_DIMS];
+    int64_t strides[GRX_MAX_DIMS]; /* in elements */
+    void *data;
 } grx_buffer;
 
 /* Flat dynamic model (host pointers, copied at create).  Produced by grx_b200/urdf.py + robot.py from the URDF
@@ -136,8 +140,12 @@ int grx_env_set_params(grx_env *env, const float *friction, const float *restitu
 
 /* zero-copy views of device state, by name (what acquire_*_tensor + gymtorch.wrap_tensor give, legged_robot.py:110-135):
  * root_states dof_pos dof_vel last_dof_vel last_actions last_last_actions commands base_heights_offset feet_air_time
- * feet_land_time feet_contact_last episode_length terrain_levels terrain_types env_origins episode_sums
- * obs pri_obs rew reset time_out torques contact_forces foot_state episode_accum params records */
+ * feet_land_time feet_contact_last episode_length (i32, the live counter) terrain_levels terrain_types env_origins episode_sums
+ * obs pri_obs rew reset time_out torques contact_forces foot_state episode_accum params records active_sig
+ * Compat exports, switched on by the FIRST request and refreshed by every following step (they cost extra stores per step):
+ *   rigid_body_states [N, nl, 13]  pos3 quat4(xyzw) linvel3 angvel3 of every URDF link (acquire_rigid_body_state_tensor, legged_robot.py:135)
+ *   dof_state         [N, nd, 2]   interleaved (pos, vel) mirror of the DOF state (acquire_dof_state_tensor, legged_robot.py:122-125); read-only
+ *   episode_length_i64 [N]         int64 mirror of the episode counter (the reference buffer's dtype, base_task.py:71-72) */
 int grx_env_get_buffer(grx_env *env, const char *name, grx_buffer *out);
 
 /* One policy step = legged_robot.py:222-246 with the GR1T1 MRO: action clip, `decimation` substeps of

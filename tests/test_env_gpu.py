@@ -304,3 +304,42 @@ def test_step_host_equals_device_step():
         np.testing.assert_array_equal(h_r, envs[1].rew_buf.cpu().numpy())
         np.testing.assert_array_equal(h_d, envs[1]._reset_u8.cpu().numpy())
     assert np.isfinite(h_o).all() and np.abs(h_o).max() > 0
+
+
+def test_compat_exports_rigid_body_states_dof_state_episode_length():
+    """SURVEY §8(b) lists rigid_body_states / dof_state among the tensors the boundary exports (legged_robot.py:110-135).  They are compat
+    exports (off until first requested): rigid_body_states [N, 37, 13] must agree with the C oracle's link states of the same post-physics
+    state and contain the feet rows the kernel reports separately; dof_state is the interleaved (pos, vel) mirror; episode_length_buf is
+    int64 like the reference buffer (base_task.py:71-72) and follows the live counter."""
+    from grx_b200.config import make_cfg
+    from grx_b200.env import GRXVecEnv
+    from grx_b200.robot import nominal_params
+    from grx_b200.urdf import builtin_model
+    from oracle.phys import PhysOracle
+    N = 64
+    cfg = make_cfg("GR1T1", N, "plane")
+    cfg.noise.add_noise = False
+    model = builtin_model("GR1T1")
+    env = GRXVecEnv(cfg, sim_device="cuda:0", params=nominal_params(model, N))
+    env.reset()
+    rbs, ds, ep = env.rigid_body_states, env.dof_state, env.episode_length_buf        # first access switches the exports on
+    assert rbs.shape == (N, len(model["link_names"]), 13) and ds.shape == (N, 10, 2) and ep.dtype == torch.int64
+    g = torch.Generator().manual_seed(2)
+    for t in range(6):
+        pre = ep.clone()
+        obs, pri, rew, reset, _ = env.step((0.2 * torch.randn(N, 10, generator=g)).cuda(), delay=2.0)
+        torch.cuda.synchronize()
+        alive = ~reset
+        assert bool((ep[alive] == pre[alive] + 1).all()) and bool((ep[reset] == 0).all())       # int64 mirror follows the counter
+        assert torch.equal(ep, env._episode_length.to(torch.int64))
+        assert torch.equal(ds[..., 0], env.dof_pos) and torch.equal(ds[..., 1], env.dof_vel)
+        np.testing.assert_allclose(rbs[:, env.feet_indices].cpu().numpy(), env.foot_state.cpu().numpy(), rtol=1e-6, atol=1e-6)
+        # against the oracle's forward kinematics of the same state (envs that did not reset: their records still hold the post-physics state)
+        ora = PhysOracle(model, env.tables, None, dtype=np.float64)
+        a = alive.cpu().numpy()
+        ls = ora.link_states(env.root_states.cpu().numpy()[a], env.dof_pos.cpu().numpy()[a], env.dof_vel.cpu().numpy()[a], env.params["base_inertial"][a])
+        got = rbs.cpu().numpy()[a]
+        np.testing.assert_allclose(got[..., :3], ls[..., :3], rtol=0, atol=2e-5)
+        np.testing.assert_allclose(got[..., 7:], ls[..., 7:], rtol=1e-4, atol=2e-4)
+        dot = np.abs((got[..., 3:7] * ls[..., 3:7]).sum(-1))                          # same rotation up to quaternion sign
+        assert (dot > 1 - 1e-5).all()

@@ -92,6 +92,10 @@ struct EnvArgs {
     grx_injected_physics inj;
     float *dbg_M, *dbg_h;  // debug_dynamics
     int dbg_index;
+    float *rigid_body_states, *dof_state;   // compat exports or nullptr
+    long long *ep_len64;
+    const int *link_body;                   // [nl] per-link tables (global memory; only read when rigid_body_states is exported)
+    const float *link_pos, *link_rot;       // [nl, 3] [nl, 9]
     unsigned long long *dbg_sig;   // [N, dbg_sig_stride] active-set signature per substep, or nullptr (grx_env_debug_active_sig)
     int dbg_sig_stride;
 };
@@ -900,6 +904,25 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 1) env_step_kernel(const _
         float Rt[9];
         m3m(s.R[m.torso_body], m.torso_rot, Rt);
         mat2quat(Rt, torso_q);
+        if (A.rigid_body_states != nullptr) {   // compat export: every URDF link's state after the last substep (refresh_rigid_body_state_tensor, FF:75)
+            for (int l = lane; l < m.nl; l += 32) {
+                const int b = __ldg(A.link_body + l);
+                float lp[3], lr[9], r[3], t[3], Rl[9], ql[4];
+#pragma unroll
+                for (int k = 0; k < 3; k++) lp[k] = __ldg(A.link_pos + 3 * l + k);
+#pragma unroll
+                for (int k = 0; k < 9; k++) lr[k] = __ldg(A.link_rot + 9 * l + k);
+                m3v(s.R[b], lp, r);
+                cross3(s.w[b], r, t);
+                m3m(s.R[b], lr, Rl);
+                mat2quat(Rl, ql);
+                float *o = A.rigid_body_states + ((size_t)e * m.nl + l) * 13;
+#pragma unroll
+                for (int k = 0; k < 3; k++) { o[k] = s.o[b][k] + r[k]; o[7 + k] = s.vo[b][k] + t[k]; o[10 + k] = s.w[b][k]; }
+#pragma unroll
+                for (int k = 0; k < 4; k++) o[3 + k] = ql[k];
+            }
+        }
         if (A.foot_state != nullptr && lane < NF) {   // compat export: feet link states (play.py / tests)
             float *fs = A.foot_state + ((size_t)e * NF + lane) * 13;
             const int b = m.foot_body[lane];
@@ -1182,6 +1205,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 1) env_step_kernel(const _
     }
     if (A.contact_forces != nullptr)
         for (int i = lane; i < m.nl * 3; i += 32) A.contact_forces[(size_t)e * m.nl * 3 + i] = s.cf[i];
+    if (A.dof_state != nullptr && lane < nd) {   // compat export: interleaved (pos, vel), post-reset like the reference's dof_state after reset_idx
+        reinterpret_cast<float2 *>(A.dof_state)[(size_t)e * nd + lane] = make_float2(rec[R_DOFPOS + lane], rec[R_DOFVEL + lane]);
+    }
+    if (A.ep_len64 != nullptr && lane == 0) A.ep_len64[e] = (long long)ep_len;
     __syncwarp();
     fence_async_smem();   // generic-proxy writes to smem -> visible to the bulk-copy (async) proxy
     __syncwarp();
@@ -1250,6 +1277,10 @@ struct grx_env {
     float *contact_forces = nullptr, *foot_state = nullptr, *episode_accum = nullptr, *terrain_origins = nullptr;
     float *actions_stage = nullptr;
     unsigned long long *active_sig = nullptr;   // debug export, allocated by grx_env_debug_active_sig
+    float *rigid_body_states = nullptr, *dof_state = nullptr;   // compat exports (allocated on first grx_env_get_buffer request)
+    long long *ep_len64 = nullptr;
+    int *d_link_body = nullptr;                                  // per-link tables for the rigid_body_states export
+    float *d_link_pos = nullptr, *d_link_rot = nullptr;
     unsigned char *reset = nullptr, *time_out = nullptr;
     short *heights = nullptr;
     TerrainDev terrain;
@@ -1330,6 +1361,10 @@ extern "C" int grx_env_create(const grx_model_desc *md, const grx_task_cfg *cfg,
     ALLOC(e->terrain_origins, 3 * 4);
 #undef ALLOC
     CK(cudaMemcpy(e->dmodel, &m, sizeof(ModelDev), cudaMemcpyHostToDevice));
+    CK(cudaMalloc((void **)&e->d_link_body, (size_t)md->nl * 4)); CK(cudaMalloc((void **)&e->d_link_pos, (size_t)md->nl * 12)); CK(cudaMalloc((void **)&e->d_link_rot, (size_t)md->nl * 36));
+    CK(cudaMemcpy(e->d_link_body, md->link_body, (size_t)md->nl * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->d_link_pos, md->link_pos, (size_t)md->nl * 12, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->d_link_rot, md->link_rot, (size_t)md->nl * 36, cudaMemcpyHostToDevice));
     {   // identity root quaternion
         std::vector<float> h(N * REC_F, 0.f);
         for (size_t i = 0; i < N; i++) h[i * REC_F + R_ROOT + 6] = 1.f;
@@ -1355,7 +1390,8 @@ extern "C" int grx_env_destroy(grx_env *e) {
     if (!e) return GRX_OK;
     cudaSetDevice(e->device);
     void *ptrs[] = {e->dmodel, e->rec, e->cst, e->obs, e->pri_obs, e->rew, e->torques, e->contact_forces, e->foot_state,
-                    e->episode_accum, e->terrain_origins, e->actions_stage, e->reset, e->time_out, e->heights, e->active_sig};
+                    e->episode_accum, e->terrain_origins, e->actions_stage, e->reset, e->time_out, e->heights, e->active_sig,
+                    e->rigid_body_states, e->dof_state, e->ep_len64, e->d_link_body, e->d_link_pos, e->d_link_rot};
     for (void *p : ptrs) if (p) cudaFree(p);
     delete e;
     return GRX_OK;
@@ -1433,16 +1469,20 @@ extern "C" int grx_env_set_params(grx_env *e, const float *friction, const float
     return GRX_OK;
 }
 
+static int g_buf_device = 0;   // device ordinal stamped into the descriptors built by set_buf (set by the get_buffer entries)
 static void set_buf(grx_buffer *b, void *data, int dtype, int ndim, int64_t d0, int64_t d1, int64_t d2, int64_t s0, int64_t s1, int64_t s2) {
+    b->device = g_buf_device; b->own_data = 0;
     b->data = data; b->dtype = dtype; b->ndim = ndim;
-    b->dims[0] = d0; b->dims[1] = d1; b->dims[2] = d2; b->dims[3] = 1;
-    b->strides[0] = s0; b->strides[1] = s1; b->strides[2] = s2; b->strides[3] = 1;
+    for (int i = 0; i < GRX_MAX_DIMS; i++) { b->dims[i] = 1; b->strides[i] = 1; }
+    b->dims[0] = d0; b->dims[1] = d1; b->dims[2] = d2;
+    b->strides[0] = s0; b->strides[1] = s1; b->strides[2] = s2;
 }
 
 extern "C" int grx_env_get_buffer(grx_env *e, const char *name, grx_buffer *b) {
     if (!e || !name || !b) return grx_set_error(GRX_E_INVALID, "grx_env_get_buffer: null argument");
     const int64_t N = e->N;
     const std::string n(name);
+    g_buf_device = e->device;
     struct RecView { const char *name; int off, width, dtype; };
     static const RecView views[] = {
         {"root_states", R_ROOT, 13, GRX_F32}, {"dof_pos", R_DOFPOS, ND, GRX_F32}, {"dof_vel", R_DOFVEL, ND, GRX_F32},
@@ -1464,6 +1504,20 @@ extern "C" int grx_env_get_buffer(grx_env *e, const char *name, grx_buffer *b) {
     if (n == "foot_state") { set_buf(b, e->foot_state, GRX_F32, 3, N, NF, 13, NF * 13, 13, 1); return GRX_OK; }
     if (n == "episode_accum") { set_buf(b, e->episode_accum, GRX_F32, 2, ACC_RING, ACC_W, 1, ACC_W, 1, 1); return GRX_OK; }
     if (n == "params") { set_buf(b, e->cst, GRX_F32, 2, N, CST_F, 1, CST_F, 1, 1); return GRX_OK; }
+    if (n == "rigid_body_states" || n == "dof_state" || n == "episode_length_i64") {   // compat exports: allocated + switched on by the first request
+        CK(cudaSetDevice(e->device));
+        if (n == "rigid_body_states") {
+            if (!e->rigid_body_states) { CK(cudaMalloc((void **)&e->rigid_body_states, (size_t)N * e->nl * 13 * 4)); CK(cudaMemset(e->rigid_body_states, 0, (size_t)N * e->nl * 13 * 4)); }
+            set_buf(b, e->rigid_body_states, GRX_F32, 3, N, e->nl, 13, (int64_t)e->nl * 13, 13, 1);
+        } else if (n == "dof_state") {
+            if (!e->dof_state) { CK(cudaMalloc((void **)&e->dof_state, (size_t)N * ND * 2 * 4)); CK(cudaMemset(e->dof_state, 0, (size_t)N * ND * 2 * 4)); }
+            set_buf(b, e->dof_state, GRX_F32, 3, N, ND, 2, ND * 2, 2, 1);
+        } else {
+            if (!e->ep_len64) { CK(cudaMalloc((void **)&e->ep_len64, (size_t)N * 8)); CK(cudaMemset(e->ep_len64, 0, (size_t)N * 8)); }
+            set_buf(b, e->ep_len64, GRX_I64, 1, N, 1, 1, 1, 1, 1);
+        }
+        return GRX_OK;
+    }
     if (n == "active_sig") {
         if (!e->active_sig) return grx_set_error(GRX_E_STATE, "grx_env_get_buffer: call grx_env_debug_active_sig(env, 1) first");
         set_buf(b, e->active_sig, GRX_U64, 2, N, SIG_STRIDE, 1, SIG_STRIDE, 1, 1); return GRX_OK;
@@ -1482,6 +1536,8 @@ static EnvArgs make_args(grx_env *e, const float *d_actions, const float *d_unif
     A.episode_accum_next = e->episode_accum + (size_t)((e->launches + 1) % ACC_RING) * ACC_W;
     A.reset = e->reset; A.time_out = e->time_out;
     A.dbg_sig = e->active_sig; A.dbg_sig_stride = SIG_STRIDE;
+    A.rigid_body_states = e->rigid_body_states; A.dof_state = e->dof_state; A.ep_len64 = e->ep_len64;
+    A.link_body = e->d_link_body; A.link_pos = e->d_link_pos; A.link_rot = e->d_link_rot;
     return A;
 }
 

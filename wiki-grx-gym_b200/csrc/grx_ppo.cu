@@ -1093,15 +1093,19 @@ extern "C" int grx_ppo_destroy(grx_ppo *p) {
     return GRX_OK;
 }
 
+static int g_ppo_buf_device = 0;
 static void set_buf(grx_buffer *b, void *data, int dtype, int ndim, int64_t d0, int64_t d1, int64_t d2) {
+    b->device = g_ppo_buf_device; b->own_data = 0;
     b->data = data; b->dtype = dtype; b->ndim = ndim;
-    b->dims[0] = d0; b->dims[1] = d1; b->dims[2] = d2; b->dims[3] = 1;
-    b->strides[0] = d1 * d2; b->strides[1] = d2; b->strides[2] = 1; b->strides[3] = 1;
+    for (int i = 0; i < GRX_MAX_DIMS; i++) { b->dims[i] = 1; b->strides[i] = 1; }
+    b->dims[0] = d0; b->dims[1] = d1; b->dims[2] = d2;
+    b->strides[0] = d1 * d2; b->strides[1] = d2; b->strides[2] = 1;
 }
 
 extern "C" int grx_ppo_get_buffer(grx_ppo *p, const char *name, grx_buffer *b) {
     if (!p || !name || !b) return grx_set_error(GRX_E_INVALID, "grx_ppo_get_buffer: null argument");
     const std::string n(name);
+    g_ppo_buf_device = p->device;
     const int64_t T = p->T, N = p->N, np_ = (int64_t)p->nparam;
     if (n == "params") { set_buf(b, p->params, GRX_F32, 1, np_, 1, 1); return GRX_OK; }
     if (n == "grads") { set_buf(b, p->reduce_buf, GRX_F32, 1, np_, 1, 1); return GRX_OK; }

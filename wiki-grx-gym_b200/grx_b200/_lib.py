@@ -12,8 +12,12 @@ F, I32, I64, U64, P = C.c_float, C.c_int32, C.c_int64, C.c_uint64, C.c_void_p
 PF, PI = C.POINTER(C.c_float), C.POINTER(C.c_int32)
 
 
-class Buffer(C.Structure):
-    _fields_ = [("data", P), ("dtype", I32), ("ndim", I32), ("dims", I64 * 4), ("strides", I64 * 4)]
+class Buffer(C.Structure):   # == grx_buffer: carb::gym::GymTensor's fields + element strides
+    _fields_ = [("device", I32), ("dtype", I32), ("ndim", I32), ("own_data", I32), ("dims", I64 * 8), ("strides", I64 * 8), ("data", P)]
+
+
+# dtype codes == GymTensorDataType (GymTensor.h:20-27) + Int32 / Int64
+DT_NONE, DT_F32, DT_U32, DT_U64, DT_U8, DT_I16, DT_I32, DT_I64 = range(8)
 
 
 class ModelDesc(C.Structure):

@@ -26,8 +26,9 @@ from .urdf import builtin_model
 REWARD_NAMES = list(L._SIGMAS[:21]) + ["on_the_air", "pose_offset", "stand_still"]   # alphabetical
 assert REWARD_NAMES == sorted(REWARD_NAMES) and len(REWARD_NAMES) == 24
 
-_TORCH_DT = {0: torch.float32, 2: torch.int64, 3: torch.uint8, 4: torch.int16, 5: torch.int32}
-_TYPESTR = {0: "<f4", 2: "<i8", 3: "|u1", 4: "<i2", 5: "<i4"}   # u64 buffers are exposed as int64 bit patterns (torch has no uint64 arithmetic)
+# grx_buffer.dtype (GymTensorDataType codes + Int32 / Int64) -> numpy typestr; u64 buffers are exposed as int64 bit patterns (torch has no uint64 arithmetic)
+_TYPESTR = {L.DT_F32: "<f4", L.DT_U32: "<i4", L.DT_U64: "<i8", L.DT_U8: "|u1", L.DT_I16: "<i2", L.DT_I32: "<i4", L.DT_I64: "<i8"}
+_ITEMSIZE = {L.DT_F32: 4, L.DT_U32: 4, L.DT_U64: 8, L.DT_U8: 1, L.DT_I16: 2, L.DT_I32: 4, L.DT_I64: 8}
 
 
 class _DevArray:
@@ -35,7 +36,7 @@ class _DevArray:
 
     def __init__(self, buf: L.Buffer, owner):
         nd = buf.ndim
-        item = {0: 4, 2: 8, 3: 1, 4: 2, 5: 4}[buf.dtype]
+        item = _ITEMSIZE[buf.dtype]
         self.owner = owner
         self.__cuda_array_interface__ = {
             "shape": tuple(int(buf.dims[i]) for i in range(nd)),
@@ -319,6 +320,7 @@ class GRXVecEnv:
         self.commands, self.base_heights_offset = v("commands"), v("base_heights_offset")
         self.feet_air_time, self.feet_land_time, self.feet_contact_last = v("feet_air_time"), v("feet_land_time"), v("feet_contact_last")
         self._episode_length = v("episode_length").squeeze(1)
+        self._episode_length_i64 = self._rigid_body_states = self._dof_state = None   # compat exports, created on first access
         self.terrain_levels, self.terrain_types = v("terrain_levels").squeeze(1), v("terrain_types").squeeze(1)
         self.env_origins, self.episode_sums_buf = v("env_origins"), v("episode_sums")
         self.obs_buf, self.pri_obs_buf, self.rew_buf = v("obs"), v("pri_obs"), v("rew")
@@ -365,11 +367,34 @@ class GRXVecEnv:
 
     @property
     def episode_length_buf(self):
-        return self._episode_length
+        """int64 [N] like the reference buffer (base_task.py:71-72): a device mirror the kernel refreshes every step from the live int32
+        counter inside the state record.  Whole-tensor assignment (what OnPolicyRunner.learn does) goes through the setter."""
+        if self._episode_length_i64 is None:
+            self._episode_length_i64 = self._view("episode_length_i64")
+            self._episode_length_i64.copy_(self._episode_length)
+        return self._episode_length_i64
 
     @episode_length_buf.setter
     def episode_length_buf(self, value):   # OnPolicyRunner.learn assigns a new tensor (on_policy_runner.py:125-127)
-        self._episode_length.copy_(torch.as_tensor(value).to(self._episode_length.dtype))
+        v = torch.as_tensor(value).to(self.device)
+        self._episode_length.copy_(v.to(self._episode_length.dtype))
+        if self._episode_length_i64 is not None:
+            self._episode_length_i64.copy_(v.to(torch.int64))
+
+    @property
+    def rigid_body_states(self):
+        """[N, num_bodies, 13] world state of every URDF link (legged_robot.py:135) — compat export, switched on by the first access and
+        refreshed by every following step (like the reference's tensor it is stale between a reset and the next step)."""
+        if self._rigid_body_states is None:
+            self._rigid_body_states = self._view("rigid_body_states")
+        return self._rigid_body_states
+
+    @property
+    def dof_state(self):
+        """[N, num_dof, 2] interleaved (pos, vel) mirror (legged_robot.py:122-125) — compat export, read-only: the live state is dof_pos / dof_vel."""
+        if self._dof_state is None:
+            self._dof_state = self._view("dof_state")
+        return self._dof_state
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -440,7 +465,7 @@ class GRXVecEnv:
         for k in self.CARRIED:
             dst = getattr(self, k)
             dst.copy_(torch.as_tensor(np.asarray(d[k]).astype(np.float32)).reshape(dst.shape).to(self.device))
-        self._episode_length.copy_(torch.as_tensor(np.asarray(d["episode_length_buf"]).astype(np.int32)).to(self.device))
+        self.episode_length_buf = torch.as_tensor(np.asarray(d["episode_length_buf"]).astype(np.int64))
         self.episode_sums_buf.copy_(torch.as_tensor(np.asarray(d["episode_sums"], np.float32)).to(self.device))
         self.common_step_counter = int(d["common_step_counter"])
         if self.custom_origins and "terrain_levels" in d:

@@ -276,8 +276,8 @@ class PPO:
     def _view(self, name):
         b = L.Buffer()
         L.check(self.lib.grx_ppo_get_buffer(self._h, name.encode(), C.byref(b)))
-        if b.dtype == 2:   # u64 bit patterns of doubles
-            b.dtype = 5
+        if b.dtype == L.DT_U64:   # u64 bit patterns of doubles -> int32 pairs, re-viewed as float64 by the caller
+            b.dtype = L.DT_I32
             b.dims[0] *= 2
         return torch.as_tensor(_DevArray(b, self), device=self.device)
 
