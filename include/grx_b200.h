@@ -282,6 +282,9 @@ int grx_gemm_debug_tile(int32_t row_blocks, int32_t bn);
  * first stage landed, last MMA committed, first accumulator complete, epilogue done, unused, then epilogue detail of warp 0's
  * first chunk: TMEM load done, staging written, proxy fence done, TMA store issued, all tiles stored.  16 values.  Synchronises. */
 int grx_gemm_debug_stamps(uint64_t *out16);
+/* Profiling: the same 16 values + 16 more; [16..23] = the gradient all-reduce kernel of the most recent minibatch, per phase: entry, ready
+ * barrier passed, slices reduced and pushed, done flags published.  Synchronises. */
+int grx_debug_stamps32(uint64_t *out32);
 
 #ifdef __cplusplus
 }

@@ -47,7 +47,7 @@ constexpr int MAXP = 6;                                 // problems per grouped 
 
 // profiling stamps of CTA 0 (ns, %globaltimer): [0] entry, [1] setup done, [2] first TMA issued, [3] first stage landed,
 // [4] last MMA committed, [5] first accumulator complete (epilogue starts), [6] epilogue of the last tile done
-__device__ unsigned long long g_stamps[16];
+__device__ unsigned long long g_stamps[32];   // [16..23]: allreduce_kernel, phase * 4 + {entry, ready barrier passed, slices reduced + pushed, done flags published}
 __device__ __forceinline__ void stamp(int i) {
     if (blockIdx.x == 0) {
         unsigned long long t;

@@ -750,7 +750,17 @@ struct Ctl {            // device control block
 // No NCCL call, no host involvement: the kernel sits in the same CUDA graph as the rest of the minibatch.
 // =========================================================================================================
 constexpr int MAXW = 8;
-constexpr int FLAG_READY = 0, FLAG_DONE = MAXW, FLAG_SUMSQ = 2 * MAXW;   // ints; sumsq partials are doubles at int offset 16 (64-byte aligned)
+// flag block of a rank, per PHASE (two phases per minibatch, see allreduce_kernel), offsets in ints:
+//   ready[8]                 epoch numbers written by every peer ("my gradients of this phase are final")
+//   done counter (1 uint)    every CTA of every rank's allreduce_kernel adds 1 after pushing its slice: monotonic, target = epoch * NBLK * world
+//   sumsq partials           [world][NBLK] doubles: squared norm of the slice a CTA reduced (summed in a fixed order by apply_kernel)
+constexpr int NPHASE = 2, AR_NBLK = 128;   // CTAs of allreduce_kernel (every phase)
+constexpr int FLAG_READY = 0, FLAG_DONE = 16, FLAG_SUMSQ = 32, FLAG_PHASE = 32 + 2 * MAXW * AR_NBLK;
+constexpr size_t FLAG_BYTES = (size_t)NPHASE * FLAG_PHASE * 4;
+constexpr int MAXRANGE = 4;
+struct Ranges {         // float4 index ranges [lo, hi) of the gradient block one all-reduce phase covers
+    int lo[MAXRANGE], hi[MAXRANGE], n;
+};
 
 struct CommDev {
     float *grads[MAXW];
@@ -773,56 +783,55 @@ __device__ __forceinline__ unsigned long long global_ns() {
 // apply_kernel does not touch the parameters once it is set and the host raises (grx_ppo_update / grx_ppo_check) — never hangs the GPU
 __device__ __forceinline__ void wait_flag(const int *p, int epoch, Ctl *ctl, unsigned long long budget_ns) {
     const unsigned long long t0 = global_ns();
-    while (ld_acquire_sys(p) < epoch) {
+    while ((int)((unsigned)ld_acquire_sys(p) - (unsigned)epoch) < 0) {   // wrap-safe: the done counters grow by CTAs x ranks per minibatch
         if (global_ns() - t0 > budget_ns) { atomicExch(&ctl->comm_error, 1); break; }
         __nanosleep(64);
     }
 }
-__global__ void __launch_bounds__(256) allreduce_kernel(const CommDev c, int n4, int nparam4, Ctl *ctl, unsigned long long budget_ns) {
+__global__ void __launch_bounds__(256) allreduce_kernel(const CommDev c, const Ranges rg, int phase, int nparam4, Ctl *ctl, unsigned long long budget_ns) {
     const int epoch = ctl->comm_epoch + 1;
-    if (blockIdx.x == 0 && threadIdx.x < c.world) st_release_sys(c.flags[threadIdx.x] + FLAG_READY + c.rank, epoch);
-    if (threadIdx.x < c.world) wait_flag(c.flags[c.rank] + FLAG_READY + threadIdx.x, epoch, ctl, budget_ns);
+    const int fo = phase * FLAG_PHASE;
+    if (threadIdx.x == 0) tc::stamp(16 + 4 * phase);
+    if (blockIdx.x == 0 && threadIdx.x < c.world) st_release_sys(c.flags[threadIdx.x] + fo + FLAG_READY + c.rank, epoch);
+    if (threadIdx.x < c.world) wait_flag(c.flags[c.rank] + fo + FLAG_READY + threadIdx.x, epoch, ctl, budget_ns);
     __syncthreads();
-    const int per = (n4 + c.world - 1) / c.world, lo = c.rank * per, hi = min(n4, lo + per);
+    if (threadIdx.x == 0) tc::stamp(17 + 4 * phase);
     float ss = 0.f;
-    for (int i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) {
-        float4 v[MAXW];
+    for (int q = 0; q < rg.n; q++) {
+        const int len = rg.hi[q] - rg.lo[q], per = (len + c.world - 1) / c.world;
+        const int lo = rg.lo[q] + c.rank * per, hi = min(rg.hi[q], lo + per);
+        for (int i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) {
+            float4 v[MAXW];
 #pragma unroll
-        for (int r = 0; r < MAXW; r++)   // all peer loads in flight at once (one NVLink round trip, not `world` of them)
-            if (r < c.world) v[r] = reinterpret_cast<const float4 *>(c.grads[r])[i];
-        float4 s = v[0];
+            for (int r = 0; r < MAXW; r++)   // all peer loads in flight at once (one NVLink round trip, not `world` of them)
+                if (r < c.world) v[r] = reinterpret_cast<const float4 *>(c.grads[r])[i];
+            float4 s = v[0];
 #pragma unroll
-        for (int r = 1; r < MAXW; r++)
-            if (r < c.world) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }   // rank order: bit-identical on every rank
+            for (int r = 1; r < MAXW; r++)
+                if (r < c.world) { s.x += v[r].x; s.y += v[r].y; s.z += v[r].z; s.w += v[r].w; }   // rank order: bit-identical on every rank
 #pragma unroll
-        for (int r = 0; r < MAXW; r++)
-            if (r < c.world) reinterpret_cast<float4 *>(c.gsum[r])[i] = s;
-        if (i < nparam4) ss += s.x * s.x + s.y * s.y + s.z * s.z + s.w * s.w;   // the tail (KL / loss sums) is not part of the gradient
+            for (int r = 0; r < MAXW; r++)
+                if (r < c.world) reinterpret_cast<float4 *>(c.gsum[r])[i] = s;
+            if (i < nparam4) ss += s.x * s.x + s.y * s.y + s.z * s.z + s.w * s.w;   // the tail (KL / loss sums) is not part of the gradient
+        }
     }
-    __threadfence_system();
+    // publication, per CTA (no last-block chain): squared-norm partial of this CTA's slice -> every rank's partial table; then ONE system fence by
+    // thread 0 (cumulative over the CTA's stores through the block barrier) and one remote add on every rank's done counter
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(FULL, ss, o);
     __shared__ float red[8];
-    __shared__ bool last;
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
     __syncthreads();
     if (threadIdx.x == 0) {
-        float x = 0.f;
-        for (int k = 0; k < 8; k++) x += red[k];
-        atomicAdd(&ctl->sumsq, (double)x);
-        __threadfence();
-        last = atomicAdd(&ctl->comm_arrive, 1u) == gridDim.x - 1;
-    }
-    __syncthreads();
-    if (last && threadIdx.x < c.world) {
+        tc::stamp(18 + 4 * phase);
+        double x = 0.0;
+        for (int k = 0; k < 8; k++) x += (double)red[k];
+        for (int r = 0; r < c.world; r++) reinterpret_cast<double *>(c.flags[r] + fo + FLAG_SUMSQ)[c.rank * AR_NBLK + blockIdx.x] = x;
         __threadfence_system();
-        const double mine = *reinterpret_cast<volatile double *>(&ctl->sumsq);
-        int *pf = c.flags[threadIdx.x];
-        reinterpret_cast<double *>(pf + FLAG_SUMSQ)[c.rank] = mine;
-        __threadfence_system();
-        st_release_sys(pf + FLAG_DONE + c.rank, epoch);
+        for (int r = 0; r < c.world; r++)
+            asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(c.flags[r] + fo + FLAG_DONE), "r"(1u) : "memory");
+        tc::stamp(19 + 4 * phase);
     }
-    if (last && threadIdx.x == 0) ctl->comm_arrive = 0;
 }
 struct PrepArgs {
     Ctl *ctl;
@@ -844,7 +853,7 @@ __global__ void __launch_bounds__(1024) apply_kernel(const PrepArgs a, float *__
                                                       float *__restrict__ v, int n) {
     Ctl &c = *a.ctl;
     __shared__ float red[32];
-    __shared__ double s_total;
+    __shared__ double s_total, s_norm;
     __shared__ int s_comm_bad;
     if (threadIdx.x == 0) tc::stamp(0);
     const float old_lr = c.lr;
@@ -861,11 +870,23 @@ __global__ void __launch_bounds__(1024) apply_kernel(const PrepArgs a, float *__
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
         if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-    } else if (threadIdx.x < a.world_size) {   // wait until every rank has pushed its slice of the summed gradient (and its partial norm)
-        wait_flag(a.comm_flags + FLAG_DONE + threadIdx.x, c.comm_epoch + 1, a.ctl, a.budget_ns);
+    } else if (threadIdx.x < NPHASE) {   // wait until every CTA of every rank has pushed its slice of the summed gradient (and its partial norm), both phases
+        wait_flag(a.comm_flags + threadIdx.x * FLAG_PHASE + FLAG_DONE, (c.comm_epoch + 1) * AR_NBLK * a.world_size, a.ctl, a.budget_ns);
     }
     __syncthreads();
     if (threadIdx.x == 0) tc::stamp(1);
+    if (a.comm_flags != nullptr && threadIdx.x < 32) {   // squared norm = sum of the per-CTA partials of all ranks and phases, in an order that is the same everywhere
+        const int per_phase = a.world_size * AR_NBLK;
+        double t = 0.0;
+        for (int ph = 0; ph < NPHASE; ph++) {
+            const volatile double *tab = reinterpret_cast<const volatile double *>(a.comm_flags + ph * FLAG_PHASE + FLAG_SUMSQ);
+            for (int i = threadIdx.x; i < per_phase; i += 32) t += tab[i];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(FULL, t, o);
+        if (threadIdx.x == 0) s_norm = t;
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
         if (a.comm_flags == nullptr) {
             float x = 0.f;
@@ -882,9 +903,7 @@ __global__ void __launch_bounds__(1024) apply_kernel(const PrepArgs a, float *__
         __threadfence();
         if (a.comm_flags == nullptr) s_total = *reinterpret_cast<volatile double *>(&c.sumsq);
         else {
-            double t = 0.0;
-            for (int r = 0; r < a.world_size; r++) t += reinterpret_cast<const volatile double *>(a.comm_flags + FLAG_SUMSQ)[r];   // rank order: identical on every rank
-            s_total = t;
+            s_total = s_norm;   // summed below by warp 0 in a fixed order
         }
         // sticky: a peer-flag / grid-barrier wait that timed out (now or in an earlier minibatch) leaves the summed gradient undefined.
         // Every block reads the flag after the grid barrier, so all of them take the same decision: do not touch the parameters.
@@ -999,6 +1018,13 @@ struct grx_ppo {
     unsigned long long comm_budget_ns = 10000000000ull;   // cfg.comm_timeout_ms (GRX_COMM_TIMEOUT_MS overrides)
     CommDev comm;
     std::vector<void *> peer_maps;
+    // the all-reduce runs in two phases so that most of it hides behind the last weight-gradient launch:
+    //   phase 0 = every gradient that is final once the hidden-layer weight gradients are done (all but the two input-layer matrices) + the KL / loss tail,
+    //   phase 1 = the input-layer weight gradients (24 % of the bytes)
+    Ranges phase_ranges[NPHASE];
+    cudaStream_t side = nullptr;           // phase 0 is forked onto this stream (inside the update's CUDA graph: a parallel branch)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool phase0_launched = false;
 };
 
 static int ppo_alloc(grx_ppo *p, void **ptr, size_t bytes) {
@@ -1038,11 +1064,19 @@ extern "C" int grx_ppo_create(const grx_ppo_cfg *cfg, int32_t device, grx_ppo **
     layout_net(p->actor, da, off);
     layout_net(p->critic, dc, off);
     p->nparam = (off + 3) & ~(size_t)3;
+    {   // all-reduce phases (float4 index ranges of the gradient block)
+        const int aw_lo = (int)(p->actor.w[0] / 4), aw_hi = (int)((p->actor.w[0] + (size_t)p->actor.dims[1] * p->actor.ld[0]) / 4);
+        const int cw_lo = (int)(p->critic.w[0] / 4), cw_hi = (int)((p->critic.w[0] + (size_t)p->critic.dims[1] * p->critic.ld[0]) / 4);
+        const int n4 = (int)((p->nparam + TAIL) / 4);
+        Ranges &r0 = p->phase_ranges[0], &r1 = p->phase_ranges[1];
+        r0.n = 3; r0.lo[0] = 0; r0.hi[0] = aw_lo; r0.lo[1] = aw_hi; r0.hi[1] = cw_lo; r0.lo[2] = cw_hi; r0.hi[2] = n4;
+        r1.n = 2; r1.lo[0] = aw_lo; r1.hi[0] = aw_hi; r1.lo[1] = cw_lo; r1.hi[1] = cw_hi;
+    }
     const size_t TN = (size_t)p->T * p->N, MR = p->MR;
     PALLOC(p->params, p->nparam * 4); PALLOC(p->adam_m, p->nparam * 4); PALLOC(p->adam_v, p->nparam * 4);
     {   // comm block: its own cudaMalloc so that one cudaIpc handle covers exactly [reduce_buf | gsum | flags]
         const size_t nb = ((p->nparam + TAIL) * 4 + 255) & ~(size_t)255;
-        p->comm_bytes = 2 * nb + 256;
+        p->comm_bytes = 2 * nb + FLAG_BYTES;
         PALLOC(p->comm_block, p->comm_bytes);
         p->reduce_buf = (float *)p->comm_block;
         p->gsum = (float *)((char *)p->comm_block + nb);
@@ -1087,6 +1121,9 @@ extern "C" int grx_ppo_destroy(grx_ppo *p) {
     if (!p) return GRX_OK;
     cudaSetDevice(p->device);
     if (p->graph) cudaGraphExecDestroy(p->graph);
+    if (p->side) cudaStreamDestroy(p->side);
+    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+    if (p->ev_join) cudaEventDestroy(p->ev_join);
     for (void *q : p->peer_maps) cudaIpcCloseMemHandle(q);
     for (void *q : p->allocs) cudaFree(q);
     delete p;
@@ -1177,7 +1214,11 @@ static void mlp_forward(grx_ppo *p, const NetIO *io, int nn, int M, int nlayers,
 // d[l-1] = (d[l] W_l) * ELU'(h[l-1]) (+ db_{l-1} = column sums), one grouped launch per layer; then ALL weight gradients
 // dW_l = d[l]^T h[l-1] (split-K, accumulated with red.global.add) in grouped launches.  Bias grads: l < top from the column sums,
 // l == top only when top == 3 (with the fused heads kernel top == 2 and db_2, dW_3, db_3 are already done).
-static void mlp_backward(grx_ppo *p, const NetIO *io, int nn, float *grads, int M, int top, cudaStream_t st) {
+static void launch_allreduce_phase(grx_ppo *p, int phase, cudaStream_t st) {
+    grx_count_launch();
+    allreduce_kernel<<<AR_NBLK, 256, 0, st>>>(p->comm, p->phase_ranges[phase], phase, (int)(p->nparam / 4), p->ctl, p->comm_budget_ns);
+}
+static void mlp_backward(grx_ppo *p, const NetIO *io, int nn, float *grads, int M, int top, cudaStream_t st, bool overlap_comm = false) {
     const bool tcu = p->cfg.use_tensor_cores != 0;
     for (int l = top; l >= 1; l--) {
         GemmArgs g[2];
@@ -1208,6 +1249,17 @@ static void mlp_backward(grx_ppo *p, const NetIO *io, int nn, float *grads, int 
             }
         }
         flush();
+        if (overlap_comm) {
+            if (pass == 0) {   // fork: phase 0 of the gradient all-reduce runs beside the input-layer weight-gradient launch (64 small CTAs fit next to the GEMM's one CTA per SM)
+                cudaEventRecord(p->ev_fork, st);
+                cudaStreamWaitEvent(p->side, p->ev_fork, 0);
+                launch_allreduce_phase(p, 0, p->side);
+                cudaEventRecord(p->ev_join, p->side);
+                p->phase0_launched = true;
+            } else {
+                cudaStreamWaitEvent(st, p->ev_join, 0);   // join
+            }
+        }
     }
 }
 // stage caller-provided observation rows (any row stride >= width) into the padded, 16-byte aligned input buffers
@@ -1283,7 +1335,7 @@ extern "C" int grx_ppo_compute_returns(grx_ppo *p, const float *d_last_critic_ob
     return grx_ppo_normalize_advantages(p, stream);
 }
 
-static int minibatch_grads(grx_ppo *p, const int64_t *d_indices, int mb, bool device_counter, cudaStream_t st) {
+static int minibatch_grads(grx_ppo *p, const int64_t *d_indices, int mb, bool device_counter, cudaStream_t st, bool overlap_comm = false) {
     const int B = p->B;
     const bool tm = p->timing && !device_counter;
 #define TMARK(i) do { if (tm) cudaEventRecord(p->tev[i], st); } while (0)
@@ -1317,7 +1369,7 @@ static int minibatch_grads(grx_ppo *p, const int64_t *d_indices, int mb, bool de
         { const cudaError_t e = tc::launch_kernel(ppo_heads_kernel<10>, dim3(148), dim3(HEADS_THREADS), 0, st, true, a); if (e != cudaSuccess && g_launch_err == cudaSuccess) g_launch_err = e; }
         TMARK(4);
         TMARK(5);
-        mlp_backward(p, io, 2, gr, B, 2, st);
+        mlp_backward(p, io, 2, gr, B, 2, st, overlap_comm);
         TMARK(6);
     } else {
         LossArgs a; memset(&a, 0, sizeof(a));
@@ -1330,20 +1382,24 @@ static int minibatch_grads(grx_ppo *p, const int64_t *d_indices, int mb, bool de
         ppo_loss_kernel<<<(B + 255) / 256, 256, 0, st>>>(a);
         TMARK(4);
         TMARK(5);
-        mlp_backward(p, io, 2, gr, B, 3, st);
+        mlp_backward(p, io, 2, gr, B, 3, st, overlap_comm);
         TMARK(6);
     }
     if (g_launch_err != cudaSuccess) { const cudaError_t e = g_launch_err; g_launch_err = cudaSuccess; return grx_set_error(GRX_E_CUDA, std::string("tensor-core GEMM launch: ") + cudaGetErrorString(e)); }
     CK(cudaGetLastError());
     return GRX_OK;
 }
+static bool overlap_enabled() {   // GRX_COMM_OVERLAP=0: both all-reduce phases after the last backward launch (profiling / A-B comparison)
+    static const int on = [] { const char *e = getenv("GRX_COMM_OVERLAP"); return e ? atoi(e) : 1; }();
+    return on != 0;
+}
 static int minibatch_apply(grx_ppo *p, cudaStream_t st, bool use_comm) {
     const float *gsrc = p->reduce_buf;
-    if (use_comm) {   // NVLink all-reduce + norm in one kernel; the summed gradient lands in gsum on every rank
-        grx_count_launch();
-        allreduce_kernel<<<64, 256, 0, st>>>(p->comm, (int)((p->nparam + TAIL) / 4), (int)(p->nparam / 4), p->ctl, p->comm_budget_ns);
+    if (use_comm) {   // NVLink all-reduce + norm; the summed gradient lands in gsum on every rank
+        if (!p->phase0_launched) launch_allreduce_phase(p, 0, st);   // not forked by minibatch_grads (stepwise entry): both phases back to back
+        launch_allreduce_phase(p, 1, st);
+        p->phase0_launched = false;
         gsrc = p->gsum;
-    } else {
     }
     PrepArgs a; memset(&a, 0, sizeof(a));
     a.comm_flags = use_comm ? p->flags : nullptr; a.comm_rank = p->comm.rank; a.budget_ns = p->comm_budget_ns;
@@ -1415,6 +1471,11 @@ extern "C" int grx_ppo_comm_open(grx_ppo *p, int32_t rank, int32_t world, const 
         p->comm.flags[r] = (int *)((char *)base + 2 * nb);
     }
     p->comm.rank = rank; p->comm.world = world;
+    if (!p->side) {
+        CK(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+    }
     p->comm_open = true;
     if (p->graph) { cudaGraphExecDestroy(p->graph); p->graph = nullptr; }
     return GRX_OK;
@@ -1443,7 +1504,7 @@ extern "C" int grx_ppo_update(grx_ppo *p, const int64_t *d_indices, void *stream
         CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
         int rc = 0;
         for (int mb = 0; mb < p->cfg.num_mini_batches && !rc; mb++) {   // one graph = one epoch (the gather reads the device-side counter)
-            rc = minibatch_grads(p, d_indices, 0, true, cs);
+            rc = minibatch_grads(p, d_indices, 0, true, cs, p->comm_open && overlap_enabled());
             if (!rc) rc = minibatch_apply(p, cs, p->comm_open);
         }
         cudaError_t ce = cudaStreamEndCapture(cs, &gr);
@@ -1489,6 +1550,14 @@ extern "C" int grx_gemm_debug_stamps(uint64_t *out8) {   /* 16 values */
     if (!out8) return grx_set_error(GRX_E_INVALID, "grx_gemm_debug_stamps: null argument");
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpyFromSymbol(out8, tc::g_stamps, 16 * sizeof(uint64_t)));
+    return GRX_OK;
+}
+// Profiling: all 32 stamps; [16..23] = allreduce_kernel of the most recent minibatch: per phase {entry, ready barrier passed, slices reduced
+// and pushed, done flags published}.  Synchronises.
+extern "C" int grx_debug_stamps32(uint64_t *out32) {
+    if (!out32) return grx_set_error(GRX_E_INVALID, "grx_debug_stamps32: null argument");
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpyFromSymbol(out32, tc::g_stamps, 32 * sizeof(uint64_t)));
     return GRX_OK;
 }
 
