@@ -32,10 +32,12 @@ extern "C" uint64_t grx_debug_launch_count(void) { return (uint64_t)g_grx_launch
 namespace {
 
 constexpr int NB = 11, ND = 10, NV = 16, CH = 5, NLMAX = 40, NSMAX = 32, NF = 2, KC = 8, KLIM = 7;
-constexpr int YS = 20;   // row stride of WS::Y (floats): 16-byte aligned and conflict-free for per-lane float4 stores
+constexpr int YS = 16;   // row stride of WS::Y (floats); the four float4 slots of a row are XOR-swizzled with (row >> 1) & 3 (conflict-free per-lane float4 stores)
+constexpr int ASP = 31;  // pitch of the Delassus block: 31 rows x 31 columns (at most 31 constraint rows; lane 31 solves the unconstrained update)
 constexpr int NREW = 24, NHMAX = 128;
-constexpr int WARPS_PER_CTA = 16;   // MAXIMUM warps per CTA (one CTA per SM; its warps re-converge at every substep so the warps of a scheduler share
-                                    // instruction-cache lines).  The launch picks warps_per_cta <= 16 so that the CTAs fill whole waves (see env_warps_per_cta)
+constexpr int WARPS_PER_CTA = 16;   // warps per CTA of the 128-register build and of the reset kernel (one CTA per SM; its warps re-converge at every substep so
+                                    // the warps of a scheduler share instruction-cache lines).  The launch picks warps_per_cta so that the CTAs fill whole waves
+constexpr int WARPS_PER_CTA_WIDE = 28;   // the 72-register build: 4096 robots on 148 SMs = ONE wave of 28 warps per SM (needs sizeof(WS) <= 8.1 KB)
 constexpr int SIG_STRIDE = 16;               // substep slots per env in the active-set signature export (decimation <= 16)
 constexpr int ACC_RING = 256, ACC_W = 32;   // extras["episode"] accumulators: one 32-float slot per launch, ring of 256
 constexpr unsigned FULL = 0xffffffffu;
@@ -104,13 +106,19 @@ struct EnvArgs {
 struct alignas(16) WS {
     float rec[REC_F];
     float cst[CST_F];
-    float R[NB][9], o[NB][3], a[NB][3], c[NB][3], Iw[NB][6], w[NB][3], vo[NB][3], al[NB][3], ao[NB][3];
-    float bi[NB][10], bw[NB][6];
-    float S[ND][6], F[ND][6];
-    float M[NV][NV + 1];
+    // Lifetimes inside a substep: kinematics (R .. ao) and the mass-matrix scratch (bi .. M) are dead once the constraint Jacobians have been
+    // built and M^-1 applied; the Delassus block As is written after that and read only by the Gauss-Seidel sweep -> they share storage.
+    union {
+        struct {
+            float R[NB][9], o[NB][3], a[NB][3], c[NB][3], Iw[NB][6], w[NB][3], vo[NB][3], al[NB][3], ao[NB][3];
+            float bi[NB][10], bw[NB][6];
+            float S[ND][6], F[ND][6];
+            float M[NV][NV + 1];
+        };
+        float As[ASP * ASP + 3];   // Delassus matrix, As[r * ASP + c] = J_c . Y_r (symmetric); after the physics: measured heights + obs staging
+    };
     float invd[NV], h[NV], u[NV], tau[NV];
-    float Y[32][YS];     // M^-1 J^T, one row per constraint; after the physics: privileged-observation row staging (bulk-stored)
-    float As[32][32];    // Delassus matrix, As[r][c] = J_c . Y_r (symmetric); after the physics: measured heights + obs staging
+    float Y[32][YS];     // M^-1 J^T, one row per constraint (swizzled, see y_slot); after the physics: privileged-observation row staging (bulk-stored)
     float rowc[32][2];   // 1 / A_rr, bias
     float cfr[KC][9];    // contact frame n, t1, t2
     float cpt[KC][4];    // contact point xyz, target velocity
@@ -122,6 +130,10 @@ struct alignas(16) WS {
     unsigned long long mbar;
 };
 static_assert(sizeof(float) * 32 * YS >= 168 * 4, "pri_obs staging aliases Y");
+static_assert(sizeof(float) * (NB * (9 + 7 * 3 + 6) + NB * 16 + ND * 12 + NV * (NV + 1)) >= sizeof(float) * ASP * ASP, "the Delassus block fits over the dead dynamics scratch");
+static_assert(ASP * ASP >= NHMAX + 64, "heights + obs staging alias the Delassus block");
+static_assert(sizeof(WS) <= 8128, "28 warps per CTA need the per-warp workspace to stay near 8 KB");
+__device__ __forceinline__ int y_slot(int row, int i4) { return (i4 ^ ((row >> 1) & 3)) << 2; }   // float offset of float4 slot i4 of row `row` in WS::Y
 
 __device__ __forceinline__ void cross3(const float *a, const float *b, float *o) {
     float x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
@@ -268,6 +280,7 @@ __device__ __forceinline__ void terrain_query(const TerrainDev &t, float x, floa
 }
 
 // ---- forward kinematics + body velocities + velocity-product accelerations; lane b < NB owns body b and walks its own chain
+template <int MAXW>   // (a separate copy per kernel build: its register allocation follows that build's launch bounds)
 __device__ __noinline__ void kinematics(WS &s, const ModelDev &m, int lane) {
     if (lane < NB) {
         const float *rt = s.rec + R_ROOT;
@@ -434,6 +447,7 @@ __device__ __forceinline__ void mass_and_bias(WS &s, const ModelDev &m, float gr
 // travels by warp shuffles (pivot from lane k, L[j][k] from lane j), so the factorisation is ~120 shuffle + FMA pairs with no
 // shared-memory round trips or warp barriers inside.  The zero block between the two legs stays exactly zero (no fill): those
 // updates are skipped here and chol_solve exploits the same structure.  Both half-warps compute the same rows (mirror).
+template <int MAXW>
 __device__ __noinline__ void cholesky(WS &s, int lane) {
     const int i = lane & 15;
     float row[NV];
@@ -508,6 +522,7 @@ __device__ __forceinline__ void cta_align(int nthreads) {   // phase alignment o
     if (nthreads > 0) asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
 }
 
+template <int MAXW>
 __device__ __noinline__ void substep(WS &s, const ModelDev &m, const EnvArgs &A, const grx_task_cfg &cfg, int lane, int env, int deci) {
     const float dt = cfg.sim_dt;
     mass_and_bias(s, m, cfg.gravity, lane);
@@ -516,7 +531,7 @@ __device__ __noinline__ void substep(WS &s, const ModelDev &m, const EnvArgs &A,
         if (lane < NV) A.dbg_h[lane] = s.h[lane];
         __syncwarp();
     }
-    cholesky(s, lane);
+    cholesky<MAXW>(s, lane);
     const float mu = 0.5f * (s.cst[C_FRIC] + A.terrain.friction), rest = 0.5f * (s.cst[C_REST] + A.terrain.restitution);
     // ---- contact detection: lane = sphere
     bool act = false;
@@ -636,7 +651,7 @@ __device__ __noinline__ void substep(WS &s, const ModelDev &m, const EnvArgs &A,
         for (int i = 0; i < NV; i++) arr += J[i] * x[i];
         invA = 1.0f / arr;
 #pragma unroll
-        for (int i = 0; i < NV; i += 4) *reinterpret_cast<float4 *>(&s.Y[lane][i]) = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
+        for (int i = 0; i < NV; i += 4) *reinterpret_cast<float4 *>(&s.Y[lane][y_slot(lane, i >> 2)]) = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
         s.rowc[lane][0] = invA;
         s.rowc[lane][1] = bias;
     }
@@ -655,17 +670,17 @@ __device__ __noinline__ void substep(WS &s, const ModelDev &m, const EnvArgs &A,
         float acc = 0.f;
 #pragma unroll
         for (int i = 0; i < NV; i += 4) {
-            const float4 y = *reinterpret_cast<const float4 *>(&s.Y[r][i]);
+            const float4 y = *reinterpret_cast<const float4 *>(&s.Y[r][y_slot(r, i >> 2)]);
             acc += J[i] * y.x + J[i + 1] * y.y + J[i + 2] * y.z + J[i + 3] * y.w;
         }
-        s.As[r][lane] = acc;
+        if (lane < ASP) s.As[r * ASP + lane] = acc;
     }
     __syncwarp();
     // ---- projected Gauss-Seidel in constraint space.  Row r is owned by lane r; every lane evaluates the row update from the
     // owner's (w, lambda) obtained with two independent shuffles, so the multiplier change d is warp-uniform without a third one.
     // Rows are swept contact by contact (normal, then the two friction rows bounded by mu * lambda_n), then the joint limits.
     float lam = 0.f;
-    const float *Ac = &s.As[0][lane];
+    const float *Ac = &s.As[min(lane, ASP - 1)];
 #pragma unroll 1
     for (int it = 0; it < cfg.solver_iters; it++) {
         int r = 0;
@@ -677,7 +692,7 @@ __device__ __noinline__ void substep(WS &s, const ModelDev &m, const EnvArgs &A,
                 const float2 rc = *reinterpret_cast<const float2 *>(s.rowc[r]);
                 const float ln = fmaxf(l0 - (wr - rc.y) * rc.x, 0.f);
                 if (lane == r) lam = ln;
-                wv += Ac[r * 32] * (ln - l0);
+                wv += Ac[r * ASP] * (ln - l0);
                 lim = mu * ln;
                 r++;
             }
@@ -687,7 +702,7 @@ __device__ __noinline__ void substep(WS &s, const ModelDev &m, const EnvArgs &A,
                 const float2 rc = *reinterpret_cast<const float2 *>(s.rowc[r]);
                 const float ln = fminf(fmaxf(l0 - (wr - rc.y) * rc.x, -lim), lim);
                 if (lane == r) lam = ln;
-                wv += Ac[r * 32] * (ln - l0);
+                wv += Ac[r * ASP] * (ln - l0);
             }
         }
 #pragma unroll 1
@@ -696,7 +711,7 @@ __device__ __noinline__ void substep(WS &s, const ModelDev &m, const EnvArgs &A,
             const float2 rc = *reinterpret_cast<const float2 *>(s.rowc[r]);
             const float ln = fmaxf(l0 - (wr - rc.y) * rc.x, 0.f);
             if (lane == r) lam = ln;
-            wv += Ac[r * 32] * (ln - l0);
+            wv += Ac[r * ASP] * (ln - l0);
         }
     }
     // ---- u = u* + sum_r Y_r lam_r (lane i < NV owns component i)
@@ -704,7 +719,7 @@ __device__ __noinline__ void substep(WS &s, const ModelDev &m, const EnvArgs &A,
 #pragma unroll 1
     for (int r = 0; r < nrow; r++) {
         const float lr = __shfl_sync(FULL, lam, r);
-        if (lane < NV) unew += s.Y[r][lane] * lr;
+        if (lane < NV) unew += s.Y[r][y_slot(r, lane >> 2) + (lane & 3)] * lr;
     }
     for (int i = lane; i < m.nl * 3; i += 32) s.cf[i] = 0.f;
     __syncwarp();
@@ -817,9 +832,10 @@ __device__ __forceinline__ void reset_env(WS &s, const ModelDev &m, const EnvArg
     __syncwarp();
 }
 
-template <bool PHYS>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 1) env_step_kernel(const __grid_constant__ EnvArgs A,
-                                                                         const __grid_constant__ grx_task_cfg cfg) {
+// MAXW: warps per CTA the build is compiled for — 16 (128 registers per thread) or 28 (72 registers: one wave for 4096 robots on 148 SMs)
+template <bool PHYS, int MAXW>
+__global__ void __launch_bounds__(MAXW * 32, 1) env_step_kernel(const __grid_constant__ EnvArgs A,
+                                                                const __grid_constant__ grx_task_cfg cfg) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ModelDev &m = *reinterpret_cast<ModelDev *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -873,7 +889,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 1) env_step_kernel(const _
 #pragma unroll 1
         for (int deci = 0; deci <= cfg.decimation; deci++) {
             cta_align(A.dbg_M == nullptr ? cta_valid : 0);
-            kinematics(s, m, lane);
+            kinematics<MAXW>(s, m, lane);
             if (deci > 0 && lane < NF) {   // foot statistics of the substep just integrated (FF:79-81)
                 const int l = m.foot_link[lane], b = m.foot_body[lane];
                 float r[3], t[3];
@@ -894,7 +910,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 1) env_step_kernel(const _
                 s.tau[lane] = fminf(fmaxf(t, -lim), lim);
             }
             __syncwarp();
-            substep(s, m, A, cfg, lane, e, deci);
+            substep<MAXW>(s, m, A, cfg, lane, e, deci);
         }
         if (A.dbg_M != nullptr) return;
         const float invd = 1.0f / (float)cfg.decimation;
@@ -971,7 +987,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 1) env_step_kernel(const _
     }
     __syncwarp();
     // ---- _get_heights (legged_robot.py:1235-1274): trunc-to-int grid index, min of 3 samples
-    float *mh = &s.As[0][0];   // [num_height_points] (the Delassus block is dead after the physics)
+    float *mh = &s.As[0];   // [num_height_points] (the Delassus block is dead after the physics)
     const int H = cfg.num_height_points;
     if (cfg.measure_heights && A.terrain.type != 0) {
         float qz = base_quat[2], qw = base_quat[3];
@@ -1155,7 +1171,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 1) env_step_kernel(const _
     }
     bsum = warp_sum(bsum);
     const float bho = bsum / (float)H;
-    float *ob = &s.As[0][0] + NHMAX;   // unclipped, noise-free obs staging [num_obs]
+    float *ob = &s.As[0] + NHMAX;   // unclipped, noise-free obs staging [num_obs]
     if (lane < 3) {
         ob[lane] = rec[R_CMD + lane] * 1.0f;                                         // commands * commands_scale (ones, G1:125)
         ob[3 + lane] = w_b[lane] * cfg.obs_scale_ang_vel;
@@ -1294,14 +1310,18 @@ struct grx_env {
 // One CTA per SM is resident (registers + shared memory); with w warps per CTA a launch of N robots takes ceil(N / (w * SMs)) waves.
 // Take the number of waves of the widest CTA and shrink the CTA until those waves are evenly filled (4096 robots on 148 SMs:
 // 2 waves of 14 warps instead of one wave of 16 and one 73 % full).
-static int env_warps_per_cta(int N, int sms) {
-    const int waves = (N + WARPS_PER_CTA * sms - 1) / (WARPS_PER_CTA * sms);
+static int env_warps_per_cta(int N, int sms, int maxw) {
+    const int waves = (N + maxw * sms - 1) / (maxw * sms);
     int w = (N + waves * sms - 1) / (waves * sms);
     if (w < 1) w = 1;
-    if (w > WARPS_PER_CTA) w = WARPS_PER_CTA;
+    if (w > maxw) w = maxw;
     return w;
 }
-static size_t env_smem_bytes() { return ((sizeof(ModelDev) + 15) & ~(size_t)15) + WARPS_PER_CTA * sizeof(WS); }
+static size_t env_smem_bytes(int warps) { return ((sizeof(ModelDev) + 15) & ~(size_t)15) + (size_t)warps * sizeof(WS); }
+// The two builds of the step kernel: <= 16 warps per CTA at 128 registers per thread, or <= 28 warps at 72 registers (more spills, but
+// twice the warps to hide latency with and HALF THE WAVES: 4096 robots = one wave of 28 warps per SM instead of two of 14).
+template <bool PHYS>
+static void launch_env_step(const grx_env *e, const EnvArgs &A, const grx_task_cfg &cfg, cudaStream_t st);
 
 extern "C" int grx_env_create(const grx_model_desc *md, const grx_task_cfg *cfg, int32_t num_envs, int32_t device, grx_env **out) {
     if (!md || !cfg || !out || num_envs <= 0) return grx_set_error(GRX_E_INVALID, "grx_env_create: null argument or num_envs <= 0");
@@ -1372,18 +1392,33 @@ extern "C" int grx_env_create(const grx_model_desc *md, const grx_task_cfg *cfg,
     }
     e->terrain.type = 0; e->terrain.rows = e->terrain.cols = 0; e->terrain.h = nullptr;
     e->terrain.hscale = 1.f; e->terrain.vscale = 1.f; e->terrain.border = 0.f; e->terrain.friction = 1.f; e->terrain.restitution = 0.f;
-    e->smem = env_smem_bytes();
     {
         int sms = 0;
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) sms = 148;
-        e->warps_per_cta = env_warps_per_cta(num_envs, sms);
-        if (const char *w = getenv("GRX_ENV_WARPS")) { const int v = atoi(w); if (v >= 1 && v <= WARPS_PER_CTA) e->warps_per_cta = v; }
+        // Measured on B200 (profiles/r2f_env_*): the wide build runs 4096 robots as ONE wave of 28 warps per SM in 415 us vs 424 us for two waves of
+        // 14 warps at 128 registers (IPC 2.06 vs 1.89) — but its 72-register budget spills 544 B per thread per substep, which turn into 411 MB
+        // of DRAM writes per launch (3.9 MB for the 128-register build).  +2 % is not worth 100x the memory traffic: opt-in (GRX_ENV_WIDE=1).
+        int maxw = WARPS_PER_CTA;
+        if (const char *w = getenv("GRX_ENV_WIDE")) maxw = atoi(w) ? WARPS_PER_CTA_WIDE : WARPS_PER_CTA;
+        e->warps_per_cta = env_warps_per_cta(num_envs, sms, maxw);
+        if (const char *w = getenv("GRX_ENV_WARPS")) { const int v = atoi(w); if (v >= 1 && v <= WARPS_PER_CTA_WIDE) e->warps_per_cta = v; }
     }
-    CK(cudaFuncSetAttribute(env_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
-    CK(cudaFuncSetAttribute(env_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
-    CK(cudaFuncSetAttribute(env_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+    e->smem = env_smem_bytes(e->warps_per_cta > WARPS_PER_CTA ? WARPS_PER_CTA_WIDE : WARPS_PER_CTA);
+    CK((cudaFuncSetAttribute(env_step_kernel<true, WARPS_PER_CTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env_smem_bytes(WARPS_PER_CTA))));
+    CK((cudaFuncSetAttribute(env_step_kernel<false, WARPS_PER_CTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env_smem_bytes(WARPS_PER_CTA))));
+    CK((cudaFuncSetAttribute(env_step_kernel<true, WARPS_PER_CTA_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env_smem_bytes(WARPS_PER_CTA_WIDE))));
+    CK((cudaFuncSetAttribute(env_step_kernel<false, WARPS_PER_CTA_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env_smem_bytes(WARPS_PER_CTA_WIDE))));
+    CK(cudaFuncSetAttribute(env_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env_smem_bytes(WARPS_PER_CTA)));
     *out = e;
     return GRX_OK;
+}
+
+template <bool PHYS>
+static void launch_env_step(const grx_env *e, const EnvArgs &A, const grx_task_cfg &cfg, cudaStream_t st) {
+    const int wpc = e->warps_per_cta, grid = (e->N + wpc - 1) / wpc;
+    grx_count_launch();
+    if (wpc > WARPS_PER_CTA) env_step_kernel<PHYS, WARPS_PER_CTA_WIDE><<<grid, wpc * 32, env_smem_bytes(wpc), st>>>(A, cfg);
+    else env_step_kernel<PHYS, WARPS_PER_CTA><<<grid, wpc * 32, env_smem_bytes(wpc), st>>>(A, cfg);
 }
 
 extern "C" int grx_env_destroy(grx_env *e) {
@@ -1546,9 +1581,7 @@ extern "C" int grx_env_step(grx_env *e, const float *d_actions, const float *d_u
     if (!e || !d_actions) return grx_set_error(GRX_E_INVALID, "grx_env_step: null argument");
     if (!e->params_set) return grx_set_error(GRX_E_STATE, "grx_env_step: call grx_env_set_params first");
     EnvArgs A = make_args(e, d_actions, d_uniform, delay, push, step_index);
-    const int wpc = e->warps_per_cta, grid = (e->N + wpc - 1) / wpc;
-    grx_count_launch();
-    env_step_kernel<true><<<grid, wpc * 32, e->smem, (cudaStream_t)stream>>>(A, e->cfg);
+    launch_env_step<true>(e, A, e->cfg, (cudaStream_t)stream);
     CK(cudaGetLastError());
     e->launches++;
     return GRX_OK;
@@ -1560,9 +1593,7 @@ extern "C" int grx_env_post_physics(grx_env *e, const float *d_actions, const fl
     if (!e->params_set) return grx_set_error(GRX_E_STATE, "grx_env_post_physics: call grx_env_set_params first");
     EnvArgs A = make_args(e, d_actions, d_uniform, 0.f, push, step_index);
     A.inj = *inj;
-    const int wpc = e->warps_per_cta, grid = (e->N + wpc - 1) / wpc;
-    grx_count_launch();
-    env_step_kernel<false><<<grid, wpc * 32, e->smem, (cudaStream_t)stream>>>(A, e->cfg);
+    launch_env_step<false>(e, A, e->cfg, (cudaStream_t)stream);
     CK(cudaGetLastError());
     e->launches++;
     return GRX_OK;
@@ -1576,7 +1607,7 @@ extern "C" int grx_env_reset_idx(grx_env *e, const int32_t *d_ids, int32_t n, co
     EnvArgs A = make_args(e, nullptr, d_uniform, 0.f, 0, step_index);
     const int grid = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     grx_count_launch();
-    env_reset_kernel<<<grid, WARPS_PER_CTA * 32, e->smem, (cudaStream_t)stream>>>(A, e->cfg, d_ids, n, curriculum_active);
+    env_reset_kernel<<<grid, WARPS_PER_CTA * 32, env_smem_bytes(WARPS_PER_CTA), (cudaStream_t)stream>>>(A, e->cfg, d_ids, n, curriculum_active);
     CK(cudaGetLastError());
     e->launches++;
     return GRX_OK;
@@ -1628,9 +1659,7 @@ extern "C" int grx_env_debug_dynamics(grx_env *e, int32_t index, float *h_M, flo
     A.rec = tmp_rec; A.dbg_M = dM; A.dbg_h = dh; A.dbg_index = index;
     grx_task_cfg c = e->cfg;
     c.decimation = 1;
-    const int wpc = e->warps_per_cta, grid = (e->N + wpc - 1) / wpc;
-    grx_count_launch();
-    env_step_kernel<true><<<grid, wpc * 32, e->smem>>>(A, c);
+    launch_env_step<true>(e, A, c, nullptr);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(h_M, dM, NV * NV * 4, cudaMemcpyDeviceToHost));
