@@ -144,6 +144,11 @@ class CpuArm:
         consts.update(env_origins=ter.env_origins[levels, types], terrain_origins=ter.env_origins, terrain_levels=levels, terrain_types=types)
         terrain = dict(heights=ter.heightsamples, hscale=cfg.terrain.horizontal_scale, vscale=cfg.terrain.vertical_scale,
                        border=float(cfg.terrain.border_size), friction=1.0, restitution=0.0)
+        if cf["mesh"] == "trimesh":   # structured trimesh: the vertex shifts of the reference's conversion (top-surface contact, as the CUDA arm)
+            from grx_b200.terrain import heightfield_to_trimesh
+            from oracle.phys import moves_from_vertices
+            verts, _ = heightfield_to_trimesh(ter.heightsamples, cfg.terrain.horizontal_scale, cfg.terrain.vertical_scale, cfg.terrain.slope_treshold)
+            terrain["moves"] = moves_from_vertices(verts, ter.heightsamples.shape[0], ter.heightsamples.shape[1], cfg.terrain.horizontal_scale)
         phys = PhysOracle(model, tables, terrain, dtype=np.float32)
         self.env = EnvOracle(cfg, tables, consts, phys, terrain)
         self.env.root_states[:, :3] = torch.as_tensor(consts["env_origins"], dtype=torch.float32) + torch.tensor([0.0, 0.0, 0.95])

@@ -125,12 +125,18 @@ int grx_env_set_terrain_heightfield(grx_env *env, const int16_t *samples, int32_
                                     float vscale, float border, float friction, float restitution);
 
 /* replaces gym.add_triangle_mesh (legged_robot.py:903-924): vertices [nv, 3] fp32 / triangles [nt, 3] u32 exactly as
- * terrain_utils.convert_heightfield_to_trimesh (terrain_utils.py:286-350) produces them from `samples`.  Contacts are resolved on
- * that heightfield (cells split along the mesh's diagonal); the mesh is checked to be this structured conversion (one vertex per
- * sample within one cell of its grid position, heights == samples * vscale) and anything else is rejected with GRX_E_INVALID. */
+ * terrain_utils.convert_heightfield_to_trimesh (terrain_utils.py:286-350) produces them from `samples`.  The mesh is checked to be this structured
+ * conversion — every vertex (height == sample * vscale, x / y an integral shift of at most one cell from its grid position) and every triangle
+ * (the two index triples of its cell) — anything else is rejected with GRX_E_INVALID.  Contacts are resolved on the mesh's TOP SURFACE: the
+ * sample grid with the shifted vertices of the steep-edge snapping (flat treads + vertical walls instead of the heightfield's ramps); a
+ * vertical wall carries no lateral contact. */
 int grx_env_set_terrain_trimesh(grx_env *env, const float *vertices, int32_t nv, const uint32_t *triangles, int32_t nt,
                                 const int16_t *samples, int32_t rows, int32_t cols, float hscale, float vscale, float border,
                                 float friction, float restitution);
+/* The same terrain built on the device from the sample grid alone (the vertex snapping of terrain_utils.py:315-328 as a kernel; bit-identical
+ * shifts, buffer "terrain_moves"): what GRXVecEnv uses for mesh_type = 'trimesh' instead of materialising the 2.7 M-vertex host mesh. */
+int grx_env_set_terrain_trimesh_hf(grx_env *env, const int16_t *samples, int32_t rows, int32_t cols, float hscale, float vscale,
+                                   float border, float slope_threshold, float friction, float restitution);
 
 /* per-env parameters (host pointers): replaces the O(num_envs) create_actor loop, legged_robot.py:1008-1082.
  * terrain_* may be NULL when custom_origins == 0.  terrain_origins = [t_rows, t_cols, 3]. */

@@ -30,6 +30,28 @@ def lib():
     return _LIB
 
 
+def near_moved_cells(moves):
+    """[rows, cols] uint8: 1 where any vertex of the 3 x 3 cells around cell (i, j) — vertices (i-1 .. i+2, j-1 .. j+2) — is shifted."""
+    m = (np.asarray(moves) != 0).any(-1)
+    R, Cc = m.shape
+    pad = np.zeros((R + 3, Cc + 3), bool)
+    pad[1:R + 1, 1:Cc + 1] = m
+    out = np.zeros((R, Cc), bool)
+    for a in range(4):
+        for b in range(4):
+            out |= pad[a:a + R, b:b + Cc]
+    return np.ascontiguousarray(out.astype(np.uint8))
+
+
+def moves_from_vertices(vertices, rows, cols, hscale):
+    """Vertex shifts (in cells) of a structured trimesh [rows * cols, 3] relative to its sample grid: the reference's steep-edge snapping."""
+    v = np.asarray(vertices, np.float64).reshape(rows, cols, 3)
+    gi, gj = np.meshgrid(np.arange(rows), np.arange(cols), indexing="ij")
+    mx, my = np.rint(v[..., 0] / hscale - gi), np.rint(v[..., 1] / hscale - gj)
+    assert np.abs(mx).max() <= 1 and np.abs(my).max() <= 1
+    return np.stack([mx, my], -1).astype(np.int8)
+
+
 def _mk_structs(real):
     P = C.POINTER(real)
     PI = C.POINTER(C.c_int)
@@ -44,7 +66,8 @@ def _mk_structs(real):
 
     class Terrain(C.Structure):
         _fields_ = [("type", C.c_int), ("rows", C.c_int), ("cols", C.c_int), ("heights", C.POINTER(C.c_short)),
-                    ("hscale", real), ("vscale", real), ("border", real), ("friction", real), ("restitution", real)]
+                    ("hscale", real), ("vscale", real), ("border", real), ("friction", real), ("restitution", real),
+                    ("moves", C.POINTER(C.c_byte)), ("near_moved", C.POINTER(C.c_ubyte))]
 
     class SimCfg(C.Structure):
         _fields_ = [("dt", real), ("gravity", real), ("contact_offset", real), ("bounce_threshold", real),
@@ -94,6 +117,13 @@ class PhysOracle:
             self._keep.append(hs)
             t.type, t.rows, t.cols = 1, hs.shape[0], hs.shape[1]
             t.heights = hs.ctypes.data_as(C.POINTER(C.c_short))
+            if terrain.get("moves") is not None:   # structured trimesh: vertex shifts of the steep-edge snapping + the cells that can see a shifted vertex
+                mv = np.ascontiguousarray(terrain["moves"], dtype=np.int8)
+                assert mv.shape == hs.shape + (2,)
+                near = near_moved_cells(mv)
+                self._keep += [mv, near]
+                t.type = 2
+                t.moves, t.near_moved = mv.ctypes.data_as(C.POINTER(C.c_byte)), near.ctypes.data_as(C.POINTER(C.c_ubyte))
             t.hscale, t.vscale, t.border = terrain["hscale"], terrain["vscale"], terrain["border"]
             t.friction, t.restitution = terrain.get("friction", 1.0), terrain.get("restitution", 0.0)
         self.t = t

@@ -46,11 +46,13 @@ typedef struct {
 } FN(Model);
 
 typedef struct {
-    int type;                    /* 0 plane z=0, 1 heightfield */
+    int type;                    /* 0 plane z=0, 1 heightfield, 2 structured trimesh (heightfield + snapped vertices) */
     int rows, cols;              /* heightfield samples [rows, cols], x = row axis */
     const short *heights;        /* int16 */
     REAL hscale, vscale, border; /* world x = row*hscale - border */
     REAL friction, restitution;
+    const signed char *moves;    /* type 2: [rows, cols, 2] vertex shifts (cells) of the reference's steep-edge snapping, terrain_utils.py:315-328 */
+    const unsigned char *near_moved; /* type 2: [rows, cols] != 0 where a vertex within the 3 x 3 cells around cell (i, j) is shifted */
 } FN(Terrain);
 
 typedef struct {
@@ -139,6 +141,40 @@ static inline void FN(terrain_query)(const FN(Terrain) *t, REAL x, REAL y, REAL 
     REAL sx = -dhx / t->hscale, sy = -dhy / t->hscale;
     REAL inv = 1 / SQRT(sx * sx + sy * sy + 1);
     n[0] = sx * inv; n[1] = sy * inv; n[2] = inv;
+    if (t->type != 2 || !t->near_moved[i * t->cols + j]) return;
+    /* Structured trimesh (gym.add_triangle_mesh of terrain_utils.convert_heightfield_to_trimesh, terrain_utils.py:286-350): vertices next to a
+     * steep edge are shifted sideways by one cell, which turns the ramp of the heightfield into a flat tread + a vertical wall.  The top
+     * surface under (x, y): of the triangles of the 3 x 3 cells around the nominal cell whose PROJECTION contains the point (vertical walls
+     * project to nothing), the highest one.  Vertex (vi, vj) sits at grid coordinates (vi + mx, vj + my). */
+    REAL best = (REAL)-1e30;
+    for (int di = -1; di <= 1; di++) for (int dj = -1; dj <= 1; dj++) {
+        const int ci = i + di, cj = j + dj;
+        if (ci < 0 || cj < 0 || ci > t->rows - 2 || cj > t->cols - 2) continue;
+        REAL P[4][3];   /* P00 P10 P01 P11 */
+        for (int v = 0; v < 4; v++) {
+            const int vi = ci + (v & 1), vj = cj + (v >> 1), id = vi * t->cols + vj;
+            P[v][0] = (REAL)(vi + t->moves[2 * id]); P[v][1] = (REAL)(vj + t->moves[2 * id + 1]); P[v][2] = t->heights[id] * t->vscale;
+        }
+        for (int k = 0; k < 2; k++) {   /* k = 0: (P00, P11, P01), k = 1: (P00, P10, P11)  (terrain_utils.py:342-347) */
+            const REAL *a = P[0], *b = k ? P[1] : P[3], *c = k ? P[3] : P[2];
+            const REAL e1x = b[0] - a[0], e1y = b[1] - a[1], e2x = c[0] - a[0], e2y = c[1] - a[1];
+            const REAL det = e1x * e2y - e2x * e1y;
+            if (FABS(det) < (REAL)1e-6) continue;
+            const REAL px = gx - a[0], py = gy - a[1];
+            const REAL u = (px * e2y - e2x * py) / det, w = (e1x * py - px * e1y) / det;
+            if (u < (REAL)-1e-5 || w < (REAL)-1e-5 || u + w > (REAL)1.00001) continue;
+            const REAL hh = a[2] + u * (b[2] - a[2]) + w * (c[2] - a[2]);
+            if (hh > best) {
+                best = hh;
+                REAL nx = (e1y * (c[2] - a[2]) - (b[2] - a[2]) * e2y) * t->hscale, ny = ((b[2] - a[2]) * e2x - e1x * (c[2] - a[2])) * t->hscale,
+                     nz = det * t->hscale * t->hscale;
+                if (nz < 0) { nx = -nx; ny = -ny; nz = -nz; }
+                const REAL il = 1 / SQRT(nx * nx + ny * ny + nz * nz);
+                *h = hh; n[0] = nx * il; n[1] = ny * il; n[2] = nz * il;
+                cell[0] = ci; cell[1] = cj; cell[2] = 2 + k;
+            }
+        }
+    }
 }
 
 typedef struct {
@@ -311,7 +347,7 @@ typedef struct {
 
 /* One dt: state (root, q, qd) advanced in place given joint torques tau.  cf_out[nl*3] = net contact force per URDF link.
  * sig (nullable): ACTIVE-SET SIGNATURE of the substep = wrapping sum of mix64(item) over the discrete decisions the step takes:
- *   per accepted contact  item = 1<<56 | sphere s | cell i << 6 | cell j << 18 | triangle << 30 | bounce branch << 31 | y-tangent << 32
+ *   per accepted contact  item = 1<<56 | sphere s | cell i << 6 | cell j << 18 | triangle (0-3) << 30 | bounce branch << 33 | y-tangent << 34
  *   per joint-limit row   item = 2<<56 | joint j | (upper ? 1 : 0) << 6
  * Two implementations that took the same decisions must agree to rounding; a differing signature explains a differing row
  * (tests/test_env_gpu.py::test_full_step_matches_oracle). */
@@ -363,7 +399,7 @@ static int FN(substep)(const FN(Model) *M, const FN(Terrain) *T, const FN(SimCfg
         const int bounce = (vn0 < -cfg->bounce_threshold && -rest * vn0 > target);
         if (bounce) target = -rest * vn0;
         sg += FN(mix64)((1ull << 56) | (unsigned long long)s | ((unsigned long long)cell[0] << 6) | ((unsigned long long)cell[1] << 18) |
-                        ((unsigned long long)cell[2] << 30) | ((unsigned long long)bounce << 31) | ((unsigned long long)usey << 32));
+                        ((unsigned long long)cell[2] << 30) | ((unsigned long long)bounce << 33) | ((unsigned long long)usey << 34));
         bias[3 * c] = target; bias[3 * c + 1] = 0; bias[3 * c + 2] = 0;
     }
     int nrows = 3 * C.count;

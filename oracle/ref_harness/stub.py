@@ -115,14 +115,18 @@ class FakeGym:
     def add_triangle_mesh(self, sim, verts, tris, p):
         self.terrain = dict(trimesh=(np.array(verts).reshape(-1, 3), np.array(tris).reshape(-1, 3)),
                             border=-p.transform.p.x, friction=p.static_friction, restitution=p.restitution)
-        # The physics stand-in (like the product) resolves contacts of a trimesh terrain on the heightfield the mesh
-        # was converted from; the caller is LeggedRobot._create_trimesh (legged_robot.py:906-921), whose Terrain object holds it.
+        # The physics stand-in (like the product) resolves contacts of a structured trimesh on its sample grid + the vertex
+        # shifts of the steep-edge snapping (top surface of the mesh; vertical walls carry no lateral contact); the caller is LeggedRobot._create_trimesh (legged_robot.py:906-921), whose Terrain object holds it.
         caller = sys._getframe(1).f_locals.get("self")
         ter = getattr(caller, "terrain", None)
         if ter is not None and hasattr(ter, "heightsamples"):
-            self.trimesh_as_heightfield = dict(heights=np.asarray(ter.heightsamples, dtype=np.int16), hscale=ter.cfg.horizontal_scale,
+            from oracle.phys import moves_from_vertices
+            hs_ = np.asarray(ter.heightsamples, dtype=np.int16)
+            self.trimesh_as_heightfield = dict(heights=hs_, hscale=ter.cfg.horizontal_scale,
                                                vscale=ter.cfg.vertical_scale, border=-p.transform.p.x,
-                                               friction=p.static_friction, restitution=p.restitution)
+                                               friction=p.static_friction, restitution=p.restitution,
+                                               # the vertex shifts of the mesh the reference actually uploaded (steep-edge snapping, terrain_utils.py:315-328)
+                                               moves=moves_from_vertices(np.array(verts).reshape(-1, 3), hs_.shape[0], hs_.shape[1], ter.cfg.horizontal_scale))
 
     # -- asset
     def load_asset(self, sim, root, file, opts):

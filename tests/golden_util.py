@@ -44,6 +44,12 @@ def setup_from_fixture(fx):
         terrain = dict(heights=fx["const/height_samples"], hscale=cfg.terrain.horizontal_scale,
                        vscale=cfg.terrain.vertical_scale, border=float(cfg.terrain.border_size),
                        friction=cfg.terrain.static_friction, restitution=cfg.terrain.restitution)
+        if str(fx["meta/mesh_type"]) == "trimesh":   # structured trimesh: the vertex shifts of the reference's conversion (terrain.py is SHA-pinned to it)
+            from grx_b200.terrain import heightfield_to_trimesh
+            from oracle.phys import moves_from_vertices
+            hs = np.asarray(fx["const/height_samples"], np.int16)
+            verts, _ = heightfield_to_trimesh(hs, cfg.terrain.horizontal_scale, cfg.terrain.vertical_scale, cfg.terrain.slope_treshold)
+            terrain["moves"] = moves_from_vertices(verts, hs.shape[0], hs.shape[1], cfg.terrain.horizontal_scale)
     return cfg, model, tables, consts, terrain
 
 

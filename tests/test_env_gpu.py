@@ -259,7 +259,7 @@ def test_trimesh_entry_accepts_only_the_structured_conversion():
     from grx_b200.terrain import heightfield_to_trimesh
     cfg = make_cfg("GR1T1", 16, "trimesh")
     cfg.terrain.num_rows, cfg.terrain.num_cols, cfg.terrain.max_init_terrain_level = 2, 2, 1
-    env = GRXVecEnv(cfg, sim_device="cuda:0")                       # goes through the trimesh entry with the Terrain's own mesh
+    env = GRXVecEnv(cfg, sim_device="cuda:0", trimesh_builder="host")   # goes through the vertex / triangle entry with the Terrain's own mesh
     env.reset()
     for _ in range(3):
         env.step(torch.zeros(16, 10, device="cuda"))
@@ -275,6 +275,37 @@ def test_trimesh_entry_accepts_only_the_structured_conversion():
     bad = v.copy(); bad[5, 2] += 0.5                                                              # a vertex off the heightfield
     assert env.lib.grx_env_set_terrain_trimesh(*args(bad, t)) == -1
     assert b"does not match" in env.lib.grx_last_error()
+    bad = v.copy(); bad[7, 0] += 0.04                                                             # a non-integral sideways shift
+    assert env.lib.grx_env_set_terrain_trimesh(*args(bad, t)) == -1
+    badt = t.copy(); badt[len(t) // 2, [1, 2]] = badt[len(t) // 2, [2, 1]]                        # one triangle in the MIDDLE with swapped indices
+    assert env.lib.grx_env_set_terrain_trimesh(*args(v, badt)) == -1 and b"structured pair" in env.lib.grx_last_error()
+    assert env.lib.grx_env_set_terrain_trimesh(*args(v, t)) == 0
+
+
+def test_device_trimesh_builder_equals_reference_conversion():
+    """grx_env_set_terrain_trimesh_hf: the steep-edge vertex snapping computed ON THE DEVICE from the int16 sample grid (one thread per
+    vertex) gives exactly the shifts of the reference's numpy conversion (terrain_utils.py:315-328 via grx_b200.terrain, SHA-pinned to the
+    reference), on a full 10 x 20-tile rough terrain; and the env built on it steps on the mesh's top surface: on a stairs tile the
+    contact height under a robot standing next to a riser is a flat tread, not the heightfield's ramp."""
+    from grx_b200.config import make_cfg
+    from grx_b200.env import GRXVecEnv
+    from grx_b200.terrain import heightfield_to_trimesh
+    cfg = make_cfg("GR1T1", 64, "trimesh")
+    env = GRXVecEnv(cfg, sim_device="cuda:0")                                       # device builder (default)
+    hs = np.ascontiguousarray(env.terrain.heightsamples, np.int16)
+    verts, _ = heightfield_to_trimesh(hs, cfg.terrain.horizontal_scale, cfg.terrain.vertical_scale, cfg.terrain.slope_treshold)
+    R, Cc = hs.shape
+    v = verts.astype(np.float64).reshape(R, Cc, 3)
+    gi, gj = np.meshgrid(np.arange(R), np.arange(Cc), indexing="ij")
+    want = np.stack([np.rint(v[..., 0] / cfg.terrain.horizontal_scale - gi), np.rint(v[..., 1] / cfg.terrain.horizontal_scale - gj)], -1).astype(np.int8)
+    got = env._view("terrain_moves").cpu().numpy().view(np.int8)
+    assert got.shape == want.shape and int((want != 0).sum()) > 1000                  # stairs / obstacles do shift vertices
+    np.testing.assert_array_equal(got, want)
+    env.reset()
+    for _ in range(5):
+        env.step(torch.zeros(64, 10, device="cuda"))
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(env.obs_buf).all())
 
 
 def test_step_host_equals_device_step():

@@ -70,9 +70,11 @@ struct ModelDev {
 };
 
 struct TerrainDev {
-    int type, rows, cols;
+    int type, rows, cols;   // 0 plane, 1 heightfield, 2 structured trimesh (heightfield + snapped vertices)
     const short *h;
     float hscale, vscale, border, friction, restitution;
+    const signed char *mv;          // type 2: [rows, cols, 2] vertex shifts (cells) of the steep-edge snapping (terrain_utils.py:315-328)
+    const unsigned char *near_mv;   // type 2: [rows, cols] != 0 where a vertex of the 3 x 3 cells around cell (i, j) is shifted
 };
 
 struct EnvArgs {
@@ -277,6 +279,43 @@ __device__ __forceinline__ void terrain_query(const TerrainDev &t, float x, floa
     float sx = -dhx / t.hscale, sy = -dhy / t.hscale;
     float inv = 1.0f / sqrtf(sx * sx + sy * sy + 1.0f);
     n[0] = sx * inv; n[1] = sy * inv; n[2] = inv;
+    if (t.type != 2 || !__ldg(t.near_mv + (size_t)i * t.cols + j)) return;
+    // Structured trimesh (gym.add_triangle_mesh of terrain_utils.convert_heightfield_to_trimesh): vertices next to a steep edge are shifted
+    // sideways by one cell — a flat tread + a vertical wall instead of the heightfield's ramp.  Top surface under (x, y) = the highest of the
+    // triangles of the 3 x 3 cells around the nominal cell whose projection contains the point (oracle/phys_impl.h terrain_query, same arithmetic).
+    float best = -1e30f;
+#pragma unroll 1
+    for (int d = 0; d < 9; d++) {
+        const int ci = i + d / 3 - 1, cj = j + d % 3 - 1;
+        if (ci < 0 || cj < 0 || ci > t.rows - 2 || cj > t.cols - 2) continue;
+        float P[4][3];   // P00 P10 P01 P11
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            const int vi = ci + (v & 1), vj = cj + (v >> 1);
+            const size_t id = (size_t)vi * t.cols + vj;
+            P[v][0] = (float)(vi + (int)__ldg(t.mv + 2 * id)); P[v][1] = (float)(vj + (int)__ldg(t.mv + 2 * id + 1)); P[v][2] = __ldg(t.h + id) * t.vscale;
+        }
+#pragma unroll
+        for (int k = 0; k < 2; k++) {   // k = 0: (P00, P11, P01), k = 1: (P00, P10, P11)
+            const float *a = P[0], *b = k ? P[1] : P[3], *c = k ? P[3] : P[2];
+            const float e1x = b[0] - a[0], e1y = b[1] - a[1], e2x = c[0] - a[0], e2y = c[1] - a[1];
+            const float det = e1x * e2y - e2x * e1y;
+            if (fabsf(det) < 1e-6f) continue;
+            const float px = gx - a[0], py = gy - a[1];
+            const float u = (px * e2y - e2x * py) / det, w = (e1x * py - px * e1y) / det;
+            if (u < -1e-5f || w < -1e-5f || u + w > 1.00001f) continue;
+            const float hh = a[2] + u * (b[2] - a[2]) + w * (c[2] - a[2]);
+            if (hh > best) {
+                best = hh;
+                float nx = (e1y * (c[2] - a[2]) - (b[2] - a[2]) * e2y) * t.hscale, ny = ((b[2] - a[2]) * e2x - e1x * (c[2] - a[2])) * t.hscale,
+                      nz = det * t.hscale * t.hscale;
+                if (nz < 0) { nx = -nx; ny = -ny; nz = -nz; }
+                const float il = 1.0f / sqrtf(nx * nx + ny * ny + nz * nz);
+                h = hh; n[0] = nx * il; n[1] = ny * il; n[2] = nz * il;
+                cell[0] = ci; cell[1] = cj; cell[2] = 2 + k;
+            }
+        }
+    }
 }
 
 // ---- forward kinematics + body velocities + velocity-product accelerations; lane b < NB owns body b and walks its own chain
@@ -577,7 +616,7 @@ __device__ __noinline__ void substep(WS &s, const ModelDev &m, const EnvArgs &A,
         const bool bounce = vn0 < -cfg.bounce_threshold && -rest * vn0 > target;
         if (bounce) target = -rest * vn0;
         sig_item = mix64((1ull << 56) | (unsigned long long)lane | ((unsigned long long)cell[0] << 6) | ((unsigned long long)cell[1] << 18) |
-                         ((unsigned long long)cell[2] << 30) | ((unsigned long long)(bounce ? 1 : 0) << 31) | ((unsigned long long)(usey ? 1 : 0) << 32));
+                         ((unsigned long long)cell[2] << 30) | ((unsigned long long)(bounce ? 1 : 0) << 33) | ((unsigned long long)(usey ? 1 : 0) << 34));
 #pragma unroll
         for (int k = 0; k < 3; k++) { s.cfr[rank][k] = n[k]; s.cfr[rank][3 + k] = t1[k]; s.cfr[rank][6 + k] = t2[k]; s.cpt[rank][k] = xc[k]; }
         s.cpt[rank][3] = target;
@@ -1235,6 +1274,36 @@ __global__ void __launch_bounds__(MAXW * 32, 1) env_step_kernel(const __grid_con
     }
 }
 
+// ---- structured-trimesh builder on the device (terrain_utils.py:315-328): per vertex, the shift (in cells) of the steep-edge snapping, straight
+// from the int16 sample grid.  The differences wrap in int16 like the reference's numpy arithmetic on the int16 array; thr = slope_threshold *
+// horizontal_scale / vertical_scale is compared in double like numpy does.  One thread per vertex.
+__global__ void trimesh_moves_kernel(const short *h, int rows, int cols, double thr, signed char *mv) {
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= rows * cols) return;
+    const int i = id / cols, j = id % cols;
+    auto H = [&](int a, int b) { return h[(size_t)a * cols + b]; };
+    auto steep = [&](short hi, short lo) { return (double)(short)(hi - lo) > thr; };   // hf[hi] - hf[lo] > thr, int16 wrap-around
+    int mx = 0, my = 0, mc = 0;
+    if (i < rows - 1 && steep(H(i + 1, j), H(i, j))) mx += 1;
+    if (i >= 1 && steep(H(i - 1, j), H(i, j))) mx -= 1;
+    if (j < cols - 1 && steep(H(i, j + 1), H(i, j))) my += 1;
+    if (j >= 1 && steep(H(i, j - 1), H(i, j))) my -= 1;
+    if (i < rows - 1 && j < cols - 1 && steep(H(i + 1, j + 1), H(i, j))) mc += 1;
+    if (i >= 1 && j >= 1 && steep(H(i - 1, j - 1), H(i, j))) mc -= 1;
+    mv[2 * (size_t)id] = (signed char)(mx + (mx == 0 ? mc : 0));
+    mv[2 * (size_t)id + 1] = (signed char)(my + (my == 0 ? mc : 0));
+}
+// per cell: does any vertex of the 3 x 3 cells around it (vertices i-1 .. i+2, j-1 .. j+2) carry a shift?
+__global__ void trimesh_near_kernel(const signed char *mv, int rows, int cols, unsigned char *near_mv) {
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= rows * cols) return;
+    const int i = id / cols, j = id % cols;
+    int any = 0;
+    for (int a = max(i - 1, 0); a <= min(i + 2, rows - 1); a++)
+        for (int b = max(j - 1, 0); b <= min(j + 2, cols - 1); b++) any |= mv[2 * ((size_t)a * cols + b)] | mv[2 * ((size_t)a * cols + b) + 1];
+    near_mv[id] = any ? 1 : 0;
+}
+
 // Host-invoked reset_idx (BaseTask.reset(), base_task.py:117-121): one warp per listed env (ids == nullptr: all envs).
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) env_reset_kernel(const __grid_constant__ EnvArgs A, const __grid_constant__ grx_task_cfg cfg,
                                                                       const int *ids, int n, int curriculum_active) {
@@ -1299,6 +1368,8 @@ struct grx_env {
     float *d_link_pos = nullptr, *d_link_rot = nullptr;
     unsigned char *reset = nullptr, *time_out = nullptr;
     short *heights = nullptr;
+    signed char *moves = nullptr;         // structured trimesh: vertex shifts
+    unsigned char *near_moved = nullptr;
     TerrainDev terrain;
     int t_rows = 1, t_cols = 1;
     bool params_set = false;
@@ -1390,7 +1461,7 @@ extern "C" int grx_env_create(const grx_model_desc *md, const grx_task_cfg *cfg,
         for (size_t i = 0; i < N; i++) h[i * REC_F + R_ROOT + 6] = 1.f;
         CK(cudaMemcpy(e->rec, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
     }
-    e->terrain.type = 0; e->terrain.rows = e->terrain.cols = 0; e->terrain.h = nullptr;
+    e->terrain.type = 0; e->terrain.rows = e->terrain.cols = 0; e->terrain.h = nullptr; e->terrain.mv = nullptr; e->terrain.near_mv = nullptr;
     e->terrain.hscale = 1.f; e->terrain.vscale = 1.f; e->terrain.border = 0.f; e->terrain.friction = 1.f; e->terrain.restitution = 0.f;
     {
         int sms = 0;
@@ -1426,7 +1497,7 @@ extern "C" int grx_env_destroy(grx_env *e) {
     cudaSetDevice(e->device);
     void *ptrs[] = {e->dmodel, e->rec, e->cst, e->obs, e->pri_obs, e->rew, e->torques, e->contact_forces, e->foot_state,
                     e->episode_accum, e->terrain_origins, e->actions_stage, e->reset, e->time_out, e->heights, e->active_sig,
-                    e->rigid_body_states, e->dof_state, e->ep_len64, e->d_link_body, e->d_link_pos, e->d_link_rot};
+                    e->rigid_body_states, e->dof_state, e->ep_len64, e->d_link_body, e->d_link_pos, e->d_link_rot, e->moves, e->near_moved};
     for (void *p : ptrs) if (p) cudaFree(p);
     delete e;
     return GRX_OK;
@@ -1446,15 +1517,35 @@ extern "C" int grx_env_set_terrain_heightfield(grx_env *e, const int16_t *sample
     CK(cudaMalloc((void **)&e->heights, (size_t)rows * cols * 2));
     CK(cudaMemcpy(e->heights, samples, (size_t)rows * cols * 2, cudaMemcpyHostToDevice));
     e->terrain.type = 1; e->terrain.rows = rows; e->terrain.cols = cols; e->terrain.h = e->heights;
+    e->terrain.mv = nullptr; e->terrain.near_mv = nullptr;
     e->terrain.hscale = hscale; e->terrain.vscale = vscale; e->terrain.border = border;
     e->terrain.friction = friction; e->terrain.restitution = restitution;
     return GRX_OK;
 }
 
-// Replaces gym.add_triangle_mesh (legged_robot.py:903-924).  The mesh the reference uploads is the structured conversion of its
-// heightfield (terrain_utils.convert_heightfield_to_trimesh: one vertex per sample, two triangles per cell, steep-edge vertices
-// snapped sideways by one cell); contacts are resolved on that heightfield (cells split along the mesh's diagonal),
-// so the entry checks that the mesh IS such a conversion of `samples` and rejects arbitrary meshes.
+// Structured trimesh = the heightfield's sample grid + per-vertex shifts (moves).  finish_trimesh uploads / derives the device tables.
+static int finish_trimesh(grx_env *e, const signed char *h_moves, double thr, int32_t rows, int32_t cols) {
+    const size_t nvx = (size_t)rows * cols;
+    if (e->moves) { cudaFree(e->moves); e->moves = nullptr; }
+    if (e->near_moved) { cudaFree(e->near_moved); e->near_moved = nullptr; }
+    CK(cudaMalloc((void **)&e->moves, 2 * nvx));
+    CK(cudaMalloc((void **)&e->near_moved, nvx));
+    const int blocks = (int)((nvx + 255) / 256);
+    if (h_moves) CK(cudaMemcpy(e->moves, h_moves, 2 * nvx, cudaMemcpyHostToDevice));
+    else { grx_count_launch(); trimesh_moves_kernel<<<blocks, 256>>>(e->heights, rows, cols, thr, e->moves); }
+    grx_count_launch();
+    trimesh_near_kernel<<<blocks, 256>>>(e->moves, rows, cols, e->near_moved);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    e->terrain.type = 2; e->terrain.mv = e->moves; e->terrain.near_mv = e->near_moved;
+    return GRX_OK;
+}
+
+// Replaces gym.add_triangle_mesh (legged_robot.py:903-924).  The mesh the reference uploads is the structured conversion of its heightfield
+// (terrain_utils.convert_heightfield_to_trimesh: one vertex per sample, two triangles per cell, steep-edge vertices shifted sideways by one
+// cell).  The entry checks that the mesh IS such a conversion of `samples` — every vertex (height, and x / y within one cell of its grid
+// position, shifts integral) and EVERY triangle (the two index triples of its cell) — and rejects arbitrary meshes; contacts are then
+// resolved on the mesh's top surface (grid + shifts, terrain_query).
 extern "C" int grx_env_set_terrain_trimesh(grx_env *e, const float *vertices, int32_t nv, const uint32_t *triangles, int32_t nt,
                                            const int16_t *samples, int32_t rows, int32_t cols, float hscale, float vscale, float border,
                                            float friction, float restitution) {
@@ -1462,15 +1553,34 @@ extern "C" int grx_env_set_terrain_trimesh(grx_env *e, const float *vertices, in
         return grx_set_error(GRX_E_INVALID, "grx_env_set_terrain_trimesh: bad arguments");
     if ((long long)nv != (long long)rows * cols || (long long)nt != 2ll * (rows - 1) * (cols - 1))
         return grx_set_error(GRX_E_INVALID, "grx_env_set_terrain_trimesh: not the structured conversion of the heightfield (need nv == rows*cols, nt == 2(rows-1)(cols-1))");
+    std::vector<signed char> mv(2 * (size_t)nv);
     for (long long i = 0; i < (long long)nv; i++) {
         const float z = vertices[3 * i + 2], want = (float)samples[i] * vscale;
-        const float x0 = (float)(i / cols) * hscale, y0 = (float)(i % cols) * hscale;
-        if (fabsf(z - want) > 1e-4f + 1e-6f * fabsf(want) || fabsf(vertices[3 * i] - x0) > 1.001f * hscale || fabsf(vertices[3 * i + 1] - y0) > 1.001f * hscale)
+        const float fx = vertices[3 * i] / hscale - (float)(i / cols), fy = vertices[3 * i + 1] / hscale - (float)(i % cols);
+        const float rx = roundf(fx), ry = roundf(fy);
+        if (fabsf(z - want) > 1e-4f + 1e-6f * fabsf(want) || fabsf(rx) > 1.f || fabsf(ry) > 1.f || fabsf(fx - rx) > 1e-3f || fabsf(fy - ry) > 1e-3f)
             return grx_set_error(GRX_E_INVALID, "grx_env_set_terrain_trimesh: vertex " + std::to_string(i) + " does not match the heightfield sample grid");
+        mv[2 * i] = (signed char)rx; mv[2 * i + 1] = (signed char)ry;
     }
-    for (int k = 0; k < 6 && k < 3 * nt; k++)
-        if (triangles[k] >= (uint32_t)nv) return grx_set_error(GRX_E_INVALID, "grx_env_set_terrain_trimesh: triangle index out of range");
-    return grx_env_set_terrain_heightfield(e, samples, rows, cols, hscale, vscale, border, friction, restitution);
+    for (long long c = 0; c < (long long)(rows - 1) * (cols - 1); c++) {   // terrain_utils.py:333-348: (ind0, ind3, ind1) and (ind0, ind2, ind3) per cell
+        const uint32_t i0 = (uint32_t)((c / (cols - 1)) * cols + c % (cols - 1)), i1 = i0 + 1, i2 = i0 + cols, i3 = i2 + 1;
+        const uint32_t *t0 = triangles + 6 * c, *t1 = t0 + 3;
+        if (t0[0] != i0 || t0[1] != i3 || t0[2] != i1 || t1[0] != i0 || t1[1] != i2 || t1[2] != i3)
+            return grx_set_error(GRX_E_INVALID, "grx_env_set_terrain_trimesh: triangles of cell " + std::to_string(c) + " are not the structured pair");
+    }
+    int rc = grx_env_set_terrain_heightfield(e, samples, rows, cols, hscale, vscale, border, friction, restitution);
+    if (rc) return rc;
+    return finish_trimesh(e, mv.data(), 0.0, rows, cols);
+}
+
+// The same terrain built ON THE DEVICE from the sample grid alone: the steep-edge snapping of terrain_utils.py:315-328 as one kernel over the
+// vertices (no 2.7 M-vertex host mesh: the reference builds 33 MB of vertices + 65 MB of indices in numpy for the default 1300 x 2100 grid).
+extern "C" int grx_env_set_terrain_trimesh_hf(grx_env *e, const int16_t *samples, int32_t rows, int32_t cols, float hscale, float vscale,
+                                              float border, float slope_threshold, float friction, float restitution) {
+    if (!e || !samples || rows < 2 || cols < 2) return grx_set_error(GRX_E_INVALID, "grx_env_set_terrain_trimesh_hf: bad arguments");
+    int rc = grx_env_set_terrain_heightfield(e, samples, rows, cols, hscale, vscale, border, friction, restitution);
+    if (rc) return rc;
+    return finish_trimesh(e, nullptr, (double)slope_threshold * (double)hscale / (double)vscale, rows, cols);
 }
 
 extern "C" int grx_env_set_params(grx_env *e, const float *friction, const float *restitution, const float *motor_strength,
@@ -1552,6 +1662,10 @@ extern "C" int grx_env_get_buffer(grx_env *e, const char *name, grx_buffer *b) {
             set_buf(b, e->ep_len64, GRX_I64, 1, N, 1, 1, 1, 1, 1);
         }
         return GRX_OK;
+    }
+    if (n == "terrain_moves") {   // structured trimesh: per-vertex shifts [rows, cols, 2] int8 (exported as u8 bit patterns)
+        if (!e->moves) return grx_set_error(GRX_E_STATE, "grx_env_get_buffer: no trimesh terrain set");
+        set_buf(b, e->moves, GRX_U8, 3, e->terrain.rows, e->terrain.cols, 2, (int64_t)e->terrain.cols * 2, 2, 1); return GRX_OK;
     }
     if (n == "active_sig") {
         if (!e->active_sig) return grx_set_error(GRX_E_STATE, "grx_env_get_buffer: call grx_env_debug_active_sig(env, 1) first");

@@ -106,7 +106,7 @@ def check(rc):
 
 
 EXPORTED = ["grx_last_error", "grx_version", "grx_abi_sizes", "grx_debug_launch_count", "grx_env_create", "grx_env_destroy",
-            "grx_env_set_terrain_plane", "grx_env_set_terrain_heightfield", "grx_env_set_terrain_trimesh", "grx_env_set_params", "grx_env_get_buffer",
+            "grx_env_set_terrain_plane", "grx_env_set_terrain_heightfield", "grx_env_set_terrain_trimesh", "grx_env_set_terrain_trimesh_hf", "grx_env_set_params", "grx_env_get_buffer",
             "grx_env_step", "grx_env_reset_idx", "grx_env_accum_slot", "grx_env_post_physics", "grx_env_step_host", "grx_env_debug_dynamics", "grx_env_debug_active_sig",
             "grx_ppo_create", "grx_ppo_destroy", "grx_ppo_get_buffer", "grx_ppo_act", "grx_ppo_process_env_step",
             "grx_ppo_compute_returns", "grx_ppo_compute_returns_local", "grx_ppo_normalize_advantages",

@@ -207,7 +207,7 @@ class GRXVecEnv:
 
     def __init__(self, cfg=None, sim_params=None, physics_engine=None, sim_device="cuda:0", headless=True, *,
                  rank=0, world_size=1, params=None, terrain=None, env_origins=None, terrain_levels=None, terrain_types=None,
-                 parity_rng=False, sync_extras=False):
+                 parity_rng=False, sync_extras=False, trimesh_builder="device"):
         """cfg: grx_b200.config.make_cfg(...) or the reference's GR1T1LowerLimbCfg()/GR1T2LowerLimbCfg() object
         (cfg.env.num_envs is the GLOBAL env count; this rank simulates the contiguous block rank*N/W..(rank+1)*N/W).
         params / terrain / env_origins...: override the sampled per-env parameters (tests)."""
@@ -287,16 +287,21 @@ class GRXVecEnv:
             scal = (C.c_float(tc.horizontal_scale), C.c_float(tc.vertical_scale), C.c_float(tc.border_size),
                     C.c_float(tc.static_friction), C.c_float(tc.restitution))
             if tc.mesh_type == "trimesh":                                               # legged_robot.py:903-924 (_create_trimesh)
-                if self.terrain is not None and getattr(self.terrain, "vertices", None) is not None:
-                    verts, tris = self.terrain.vertices, self.terrain.triangles
-                else:
-                    from .terrain import heightfield_to_trimesh
-                    verts, tris = heightfield_to_trimesh(hs, tc.horizontal_scale, tc.vertical_scale, tc.slope_treshold)
-                verts = np.ascontiguousarray(verts, np.float32)
-                tris = np.ascontiguousarray(tris, np.uint32)
-                L.check(self.lib.grx_env_set_terrain_trimesh(self._h, verts.ctypes.data_as(L.PF), verts.shape[0],
-                                                             tris.ctypes.data_as(C.POINTER(C.c_uint32)), tris.shape[0],
-                                                             hs.ctypes.data_as(C.POINTER(C.c_int16)), hs.shape[0], hs.shape[1], *scal))
+                if trimesh_builder == "device":
+                    # the steep-edge vertex snapping (terrain_utils.py:315-328) runs as a kernel over the sample grid: no host mesh
+                    L.check(self.lib.grx_env_set_terrain_trimesh_hf(self._h, hs.ctypes.data_as(C.POINTER(C.c_int16)), hs.shape[0], hs.shape[1],
+                                                                    scal[0], scal[1], scal[2], C.c_float(tc.slope_treshold), scal[3], scal[4]))
+                else:   # "host": upload the reference's own vertices / triangles (validated against the sample grid)
+                    if self.terrain is not None and getattr(self.terrain, "vertices", None) is not None:
+                        verts, tris = self.terrain.vertices, self.terrain.triangles
+                    else:
+                        from .terrain import heightfield_to_trimesh
+                        verts, tris = heightfield_to_trimesh(hs, tc.horizontal_scale, tc.vertical_scale, tc.slope_treshold)
+                    verts = np.ascontiguousarray(verts, np.float32)
+                    tris = np.ascontiguousarray(tris, np.uint32)
+                    L.check(self.lib.grx_env_set_terrain_trimesh(self._h, verts.ctypes.data_as(L.PF), verts.shape[0],
+                                                                 tris.ctypes.data_as(C.POINTER(C.c_uint32)), tris.shape[0],
+                                                                 hs.ctypes.data_as(C.POINTER(C.c_int16)), hs.shape[0], hs.shape[1], *scal))
             else:
                 L.check(self.lib.grx_env_set_terrain_heightfield(self._h, hs.ctypes.data_as(C.POINTER(C.c_int16)), hs.shape[0], hs.shape[1], *scal))
         else:
