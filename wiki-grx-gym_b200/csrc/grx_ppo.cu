@@ -432,6 +432,7 @@ __global__ void normalize_adv_kernel(float *adv, const double *moments, size_t n
 struct GatherArgs {
     const int64_t *indices;
     const int *mb_counter;   // device-side minibatch index (so the same CUDA graph replays for every minibatch), or NULL
+    int mb_off;              // added to the device counter: 1 when the gather is PREFETCHED during the previous minibatch
     int mb, nmb, B, O, P, A, Opad, Ppad;
     const float *s_obs, *s_cobs, *s_act, *s_val, *s_ret, *s_adv, *s_logp, *s_mu, *s_sigma;
     float *xa, *xc, *act, *val, *ret, *adv, *logp, *mu, *sigma;
@@ -443,7 +444,7 @@ __global__ void __launch_bounds__(256) gather_kernel(const GatherArgs g) {
     tc::pdl_wait();                // launched as a programmatic dependent of the previous minibatch's apply kernel
     tc::pdl_launch_dependents();
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < g.nzero4; i += gridDim.x * blockDim.x) g.zero[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int mb = g.mb_counter ? (*g.mb_counter % g.nmb) : g.mb;
+    const int mb = g.mb_counter ? ((*g.mb_counter + g.mb_off) % g.nmb) : g.mb;
     const int64_t *idx = g.indices + (size_t)mb * g.B;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
     if ((g.P & 3) == 0) {   // critic rows are 16-byte aligned in the storage and in the staging buffer: float4 copies
@@ -841,6 +842,8 @@ struct PrepArgs {
     int *comm_flags;   // this rank's flag block when the NVLink all-reduce is active (norm partials come from the peers), else NULL
     int comm_rank;
     unsigned long long budget_ns;   // peer-flag wait budget
+    float4 *zero;      // gradient block to clear once the step is applied (graph mode with prefetched gathers), or NULL
+    int nzero4;
     float *mb_log;     // [mb_log_cap][4] = (kl_mean, lr, loss, grad_norm) of minibatch ctl.mb_counter of this update (what ppo.py:262-268, 308-309 would log)
     int mb_log_cap;
 };
@@ -948,6 +951,8 @@ __global__ void __launch_bounds__(1024) apply_kernel(const PrepArgs a, float *__
             reinterpret_cast<float4 *>(m)[i] = m4; reinterpret_cast<float4 *>(v)[i] = v4; reinterpret_cast<float4 *>(p)[i] = p4;
         }
     }
+    if (a.zero != nullptr)   // every reader of this minibatch's gradients (this kernel; the peers' all-reduce, whose completion was awaited above) is done
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.nzero4; i += gridDim.x * blockDim.x) a.zero[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (threadIdx.x == 0) tc::stamp(4);
     if (threadIdx.x == 0) {
         __threadfence();
@@ -995,6 +1000,10 @@ struct grx_ppo {
     float *da[4] = {nullptr, nullptr, nullptr, nullptr}, *dc[4] = {nullptr, nullptr, nullptr, nullptr};     // gradients w.r.t. them
     float *xa = nullptr, *xc = nullptr, *mb_act = nullptr, *mb_val = nullptr, *mb_ret = nullptr, *mb_adv = nullptr, *mb_logp = nullptr,
           *mb_mu = nullptr, *mb_sigma = nullptr, *last_values = nullptr;
+    struct MbIn { float *xa, *xc, *act, *val, *ret, *adv, *logp, *mu, *sigma; } mbin[2] = {};   // minibatch inputs, double-buffered: the gather of
+                                                                                             // minibatch k+1 runs beside the kernels of minibatch k
+    cudaStream_t gstream = nullptr;
+    cudaEvent_t ev_gfork = nullptr, ev_gjoin = nullptr;
     double *moments = nullptr;
     Ctl *ctl = nullptr;
     float *mb_log = nullptr;   // per-minibatch (kl, lr, loss, grad norm) of the current update
@@ -1093,6 +1102,16 @@ extern "C" int grx_ppo_create(const grx_ppo_cfg *cfg, int32_t device, grx_ppo **
     PALLOC(p->xa, MR * p->Opad * 4); PALLOC(p->xc, MR * p->Ppad * 4); PALLOC(p->mb_act, MR * p->A * 4); PALLOC(p->mb_val, MR * 4);
     PALLOC(p->mb_ret, MR * 4); PALLOC(p->mb_adv, MR * 4); PALLOC(p->mb_logp, MR * 4); PALLOC(p->mb_mu, MR * p->A * 4);
     PALLOC(p->mb_sigma, MR * p->A * 4); PALLOC(p->last_values, (size_t)p->N * 4);
+    p->mbin[0] = {p->xa, p->xc, p->mb_act, p->mb_val, p->mb_ret, p->mb_adv, p->mb_logp, p->mb_mu, p->mb_sigma};
+    {   // second set (only minibatch rows)
+        const size_t Bm = (size_t)p->B;
+        grx_ppo::MbIn &m = p->mbin[1];
+        PALLOC(m.xa, Bm * p->Opad * 4); PALLOC(m.xc, Bm * p->Ppad * 4); PALLOC(m.act, Bm * p->A * 4); PALLOC(m.val, Bm * 4); PALLOC(m.ret, Bm * 4);
+        PALLOC(m.adv, Bm * 4); PALLOC(m.logp, Bm * 4); PALLOC(m.mu, Bm * p->A * 4); PALLOC(m.sigma, Bm * p->A * 4);
+    }
+    CK(cudaStreamCreateWithFlags(&p->gstream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&p->ev_gfork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&p->ev_gjoin, cudaEventDisableTiming));
     PALLOC(p->moments, 4 * sizeof(double)); PALLOC(p->ctl, sizeof(Ctl));
     p->mb_log_cap = cfg->num_learning_epochs * cfg->num_mini_batches;
     PALLOC(p->mb_log, (size_t)p->mb_log_cap * 4 * sizeof(float));
@@ -1122,6 +1141,9 @@ extern "C" int grx_ppo_destroy(grx_ppo *p) {
     cudaSetDevice(p->device);
     if (p->graph) cudaGraphExecDestroy(p->graph);
     if (p->side) cudaStreamDestroy(p->side);
+    if (p->gstream) cudaStreamDestroy(p->gstream);
+    if (p->ev_gfork) cudaEventDestroy(p->ev_gfork);
+    if (p->ev_gjoin) cudaEventDestroy(p->ev_gjoin);
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
     if (p->ev_join) cudaEventDestroy(p->ev_join);
     for (void *q : p->peer_maps) cudaIpcCloseMemHandle(q);
@@ -1335,24 +1357,34 @@ extern "C" int grx_ppo_compute_returns(grx_ppo *p, const float *d_last_critic_ob
     return grx_ppo_normalize_advantages(p, stream);
 }
 
-static int minibatch_grads(grx_ppo *p, const int64_t *d_indices, int mb, bool device_counter, cudaStream_t st, bool overlap_comm = false) {
+// minibatch rows of the rollout -> input set `set`; zero: also clear the gradient block (inline gathers; a prefetched gather runs beside the
+// previous minibatch's accumulation and must not)
+static void launch_gather(grx_ppo *p, const int64_t *d_indices, int mb, bool device_counter, int mb_off, int set, bool zero, cudaStream_t st, bool pdl) {
+    GatherArgs g; memset(&g, 0, sizeof(g));
+    const grx_ppo::MbIn &m = p->mbin[set];
+    g.indices = d_indices; g.mb_counter = device_counter ? &p->ctl->mb_counter : nullptr; g.mb_off = mb_off; g.mb = mb; g.nmb = p->cfg.num_mini_batches;
+    g.B = p->B; g.O = p->O; g.P = p->P; g.A = p->A; g.Opad = p->Opad; g.Ppad = p->Ppad;
+    g.s_obs = p->s_obs; g.s_cobs = p->s_cobs; g.s_act = p->s_act; g.s_val = p->s_val; g.s_ret = p->s_ret; g.s_adv = p->s_adv;
+    g.s_logp = p->s_logp; g.s_mu = p->s_mu; g.s_sigma = p->s_sigma;
+    g.xa = m.xa; g.xc = m.xc; g.act = m.act; g.val = m.val; g.ret = m.ret; g.adv = m.adv; g.logp = m.logp; g.mu = m.mu; g.sigma = m.sigma;
+    g.zero = reinterpret_cast<float4 *>(p->reduce_buf); g.nzero4 = zero ? (int)((p->nparam + TAIL) / 4) : 0;
+    const cudaError_t e = tc::launch_kernel(gather_kernel, dim3(148 * 8), dim3(256), 0, st, pdl, g);
+    if (e != cudaSuccess && g_launch_err == cudaSuccess) g_launch_err = e;
+}
+
+// set: which minibatch-input set the forward / backward read; gather_inline: run the gather (and clear the gradient block) first, in-stream
+static int minibatch_grads(grx_ppo *p, const int64_t *d_indices, int mb, bool device_counter, cudaStream_t st, bool overlap_comm = false, int set = 0,
+                           bool gather_inline = true) {
     const int B = p->B;
     const bool tm = p->timing && !device_counter;
 #define TMARK(i) do { if (tm) cudaEventRecord(p->tev[i], st); } while (0)
     TMARK(0);
-    GatherArgs g; memset(&g, 0, sizeof(g));
-    g.indices = d_indices; g.mb_counter = device_counter ? &p->ctl->mb_counter : nullptr; g.mb = mb; g.nmb = p->cfg.num_mini_batches;
-    g.B = B; g.O = p->O; g.P = p->P; g.A = p->A; g.Opad = p->Opad; g.Ppad = p->Ppad;
-    g.s_obs = p->s_obs; g.s_cobs = p->s_cobs; g.s_act = p->s_act; g.s_val = p->s_val; g.s_ret = p->s_ret; g.s_adv = p->s_adv;
-    g.s_logp = p->s_logp; g.s_mu = p->s_mu; g.s_sigma = p->s_sigma;
-    g.xa = p->xa; g.xc = p->xc; g.act = p->mb_act; g.val = p->mb_val; g.ret = p->mb_ret; g.adv = p->mb_adv; g.logp = p->mb_logp;
-    g.mu = p->mb_mu; g.sigma = p->mb_sigma;
-    g.zero = reinterpret_cast<float4 *>(p->reduce_buf); g.nzero4 = (int)((p->nparam + TAIL) / 4);
-    { const cudaError_t e = tc::launch_kernel(gather_kernel, dim3(148 * 8), dim3(256), 0, st, true, g); if (e != cudaSuccess && g_launch_err == cudaSuccess) g_launch_err = e; }
+    if (gather_inline) launch_gather(p, d_indices, mb, device_counter, 0, set, true, st, true);
     TMARK(1);
+    const grx_ppo::MbIn &mi = p->mbin[set];
     const Net &na = p->actor, &nc = p->critic;
     const bool fused_heads = p->A == 10 && nc.dims[4] == 1 && na.dims[3] == HEADS_H && nc.dims[3] == HEADS_H;   // the registered GRx policy; other shapes take the unfused path
-    const NetIO io[2] = {{&na, p->xa, p->Opad, p->ha, p->da}, {&nc, p->xc, p->Ppad, p->hc, p->dc}};
+    const NetIO io[2] = {{&na, mi.xa, p->Opad, p->ha, p->da}, {&nc, mi.xc, p->Ppad, p->hc, p->dc}};
     TMARK(2);
     mlp_forward(p, io, 2, B, fused_heads ? 3 : 4, st);                                 // ppo.py:244-248
     TMARK(3);
@@ -1363,7 +1395,7 @@ static int minibatch_grads(grx_ppo *p, const int64_t *d_indices, int mb, bool de
         a.W3a = p->params + na.w[3]; a.b3a = p->params + na.b[3]; a.W3c = p->params + nc.w[3]; a.b3c = p->params + nc.b[3]; a.std = p->params;
         a.gW3a = gr + na.w[3]; a.gb3a = gr + na.b[3]; a.gW3c = gr + nc.w[3]; a.gb3c = gr + nc.b[3]; a.gb2a = gr + na.b[2]; a.gb2c = gr + nc.b[2];
         a.gstd = gr; a.tail = gr + p->nparam;
-        a.act = p->mb_act; a.old_mu = p->mb_mu; a.old_sigma = p->mb_sigma; a.old_logp = p->mb_logp; a.adv = p->mb_adv; a.ret = p->mb_ret; a.old_v = p->mb_val;
+        a.act = mi.act; a.old_mu = mi.mu; a.old_sigma = mi.sigma; a.old_logp = mi.logp; a.adv = mi.adv; a.ret = mi.ret; a.old_v = mi.val;
         a.B = B;
         a.clip = p->cfg.clip_param; a.vcoef = p->cfg.value_loss_coef; a.ecoef = p->cfg.entropy_coef; a.clipped_value = p->cfg.use_clipped_value_loss;
         { const cudaError_t e = tc::launch_kernel(ppo_heads_kernel<10>, dim3(148), dim3(HEADS_THREADS), 0, st, true, a); if (e != cudaSuccess && g_launch_err == cudaSuccess) g_launch_err = e; }
@@ -1373,8 +1405,8 @@ static int minibatch_grads(grx_ppo *p, const int64_t *d_indices, int mb, bool de
         TMARK(6);
     } else {
         LossArgs a; memset(&a, 0, sizeof(a));
-        a.mu = p->ha[3]; a.v = p->hc[3]; a.std = p->params; a.act = p->mb_act; a.old_mu = p->mb_mu; a.old_sigma = p->mb_sigma;
-        a.old_logp = p->mb_logp; a.adv = p->mb_adv; a.ret = p->mb_ret; a.old_v = p->mb_val;
+        a.mu = p->ha[3]; a.v = p->hc[3]; a.std = p->params; a.act = mi.act; a.old_mu = mi.mu; a.old_sigma = mi.sigma;
+        a.old_logp = mi.logp; a.adv = mi.adv; a.ret = mi.ret; a.old_v = mi.val;
         a.dmu = p->da[3]; a.dv = p->dc[3]; a.gstd = gr; a.tail = gr + p->nparam;
         a.B = B; a.A = p->A; a.clip = p->cfg.clip_param; a.vcoef = p->cfg.value_loss_coef; a.ecoef = p->cfg.entropy_coef;
         a.clipped_value = p->cfg.use_clipped_value_loss;
@@ -1389,11 +1421,15 @@ static int minibatch_grads(grx_ppo *p, const int64_t *d_indices, int mb, bool de
     CK(cudaGetLastError());
     return GRX_OK;
 }
+static bool prefetch_enabled() {   // GRX_GATHER_PREFETCH=0: every gather in-stream at the head of its minibatch (A-B comparison)
+    static const int on = [] { const char *e = getenv("GRX_GATHER_PREFETCH"); return e ? atoi(e) : 1; }();
+    return on != 0;
+}
 static bool overlap_enabled() {   // GRX_COMM_OVERLAP=0: both all-reduce phases after the last backward launch (profiling / A-B comparison)
     static const int on = [] { const char *e = getenv("GRX_COMM_OVERLAP"); return e ? atoi(e) : 1; }();
     return on != 0;
 }
-static int minibatch_apply(grx_ppo *p, cudaStream_t st, bool use_comm) {
+static int minibatch_apply(grx_ppo *p, cudaStream_t st, bool use_comm, bool zero_grads = false) {
     const float *gsrc = p->reduce_buf;
     if (use_comm) {   // NVLink all-reduce + norm; the summed gradient lands in gsum on every rank
         if (!p->phase0_launched) launch_allreduce_phase(p, 0, st);   // not forked by minibatch_grads (stepwise entry): both phases back to back
@@ -1404,6 +1440,7 @@ static int minibatch_apply(grx_ppo *p, cudaStream_t st, bool use_comm) {
     PrepArgs a; memset(&a, 0, sizeof(a));
     a.comm_flags = use_comm ? p->flags : nullptr; a.comm_rank = p->comm.rank; a.budget_ns = p->comm_budget_ns;
     a.mb_log = p->mb_log; a.mb_log_cap = p->mb_log_cap;
+    a.zero = zero_grads ? reinterpret_cast<float4 *>(p->reduce_buf) : nullptr; a.nzero4 = (int)((p->nparam + TAIL) / 4);
     a.ctl = p->ctl; a.tail = gsrc + p->nparam; a.std = p->params; a.A = p->A; a.adaptive = p->cfg.adaptive_schedule;
     a.world_size = p->cfg.world_size; a.desired_kl = p->cfg.desired_kl; a.lr_min = p->cfg.learning_rate_min; a.lr_max = p->cfg.learning_rate_max;
     a.max_grad_norm = p->cfg.max_grad_norm; a.vcoef = p->cfg.value_loss_coef; a.ecoef = p->cfg.entropy_coef;
@@ -1503,9 +1540,26 @@ extern "C" int grx_ppo_update(grx_ppo *p, const int64_t *d_indices, void *stream
         const unsigned long long before_capture = g_grx_launches.load();
         CK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
         int rc = 0;
-        for (int mb = 0; mb < p->cfg.num_mini_batches && !rc; mb++) {   // one graph = one epoch (the gather reads the device-side counter)
-            rc = minibatch_grads(p, d_indices, 0, true, cs, p->comm_open && overlap_enabled());
-            if (!rc) rc = minibatch_apply(p, cs, p->comm_open);
+        // one graph = one epoch (the gathers read the device-side minibatch counter).  The gather of minibatch k+1 is PREFETCHED: forked onto a
+        // side branch at the start of minibatch k (into the other input set), it runs beside the dense layers of minibatch k (two of those
+        // launches leave 66 SMs idle) and is joined before apply(k) advances the counter; apply clears the gradient block instead of the gather.
+        const bool prefetch = prefetch_enabled();
+        const int nmb = p->cfg.num_mini_batches;
+        for (int mb = 0; mb < nmb && !rc; mb++) {
+            const int set = prefetch ? (mb & 1) : 0;
+            const bool inline_gather = !prefetch || mb == 0;
+            if (prefetch && mb + 1 < nmb) {
+                if (inline_gather) launch_gather(p, d_indices, 0, true, 0, set, true, cs, true);   // (minibatch 0: its own gather first, so the fork comes after it)
+                cudaEventRecord(p->ev_gfork, cs);
+                cudaStreamWaitEvent(p->gstream, p->ev_gfork, 0);
+                launch_gather(p, d_indices, 0, true, 1, set ^ 1, false, p->gstream, false);
+                cudaEventRecord(p->ev_gjoin, p->gstream);
+                rc = minibatch_grads(p, d_indices, 0, true, cs, p->comm_open && overlap_enabled(), set, false);
+                cudaStreamWaitEvent(cs, p->ev_gjoin, 0);
+            } else {
+                rc = minibatch_grads(p, d_indices, 0, true, cs, p->comm_open && overlap_enabled(), set, inline_gather);
+            }
+            if (!rc) rc = minibatch_apply(p, cs, p->comm_open, prefetch);
         }
         cudaError_t ce = cudaStreamEndCapture(cs, &gr);
         cudaStreamDestroy(cs);
