@@ -62,7 +62,8 @@ def _mk_structs(real):
                     ("dof_lower", P), ("dof_upper", P), ("dof_vel_limit", P), ("dof_effort", P),
                     ("link_body", PI), ("link_pos", P), ("link_rot", P),
                     ("sph_body", PI), ("sph_link", PI), ("sph_pos", P), ("sph_rad", P),
-                    ("foot_links", PI), ("kp", P), ("kd", P), ("default_pos", P)]
+                    ("foot_links", PI), ("kp", P), ("kd", P), ("default_pos", P),
+                    ("npairs", C.c_int), ("pair_a", PI), ("pair_b", PI)]
 
     class Terrain(C.Structure):
         _fields_ = [("type", C.c_int), ("rows", C.c_int), ("cols", C.c_int), ("heights", C.POINTER(C.c_short)),
@@ -72,7 +73,7 @@ def _mk_structs(real):
     class SimCfg(C.Structure):
         _fields_ = [("dt", real), ("gravity", real), ("contact_offset", real), ("bounce_threshold", real),
                     ("max_depen_vel", real), ("erp", real), ("solver_iters", C.c_int), ("decimation", C.c_int),
-                    ("action_scale", real), ("max_contacts", C.c_int)]
+                    ("action_scale", real), ("max_contacts", C.c_int), ("max_self_contacts", C.c_int)]
     return Model, Terrain, SimCfg
 
 
@@ -103,6 +104,9 @@ class PhysOracle:
             setattr(m, k, self._rptr(model[k]))
         m.dof_vel_limit = self._rptr(model["dof_velocity"])
         m.kp, m.kd, m.default_pos = self._rptr(ctl["kp"]), self._rptr(ctl["kd"]), self._rptr(ctl["default_pos"])
+        pairs = np.asarray(ctl.get("self_pairs", np.zeros((0, 2), np.int32)), np.int32).reshape(-1, 2)   # robot.self_collision_pairs (sphere indices in priority order)
+        m.npairs = len(pairs)
+        m.pair_a, m.pair_b = self._iptr(pairs[:, 0].copy()), self._iptr(pairs[:, 1].copy())
         self.model, self.m = model, m
         self.nd, self.nl, self.nf = m.nd, m.nl, m.nf
         t = Terrain()
@@ -129,7 +133,7 @@ class PhysOracle:
         self.t = t
         s = SimCfg()
         d = dict(dt=0.002, gravity=-9.81, contact_offset=0.01, bounce_threshold=0.5, max_depen_vel=1.0, erp=0.2,
-                 solver_iters=4, decimation=10, action_scale=1.0, max_contacts=8)
+                 solver_iters=4, decimation=10, action_scale=1.0, max_contacts=8, max_self_contacts=0)
         d.update(sim or {})
         for k, v in d.items():
             setattr(s, k, v)

@@ -43,6 +43,9 @@ typedef struct {
     const REAL *sph_pos, *sph_rad;     /* [ns*3] [ns] */
     const int *foot_links;             /* [nf] URDF-link indices of the feet */
     const REAL *kp, *kd, *default_pos; /* [nd] PD gains + default joint angles */
+    int npairs;                        /* robot self-collision (legged_robot_config.py:121 self_collisions = 0 = enabled; create_actor(...,
+                                        * collision_filter = 0), legged_robot.py:1022-1028): candidate sphere pairs, in priority order */
+    const int *pair_a, *pair_b;        /* [npairs] sphere indices (contact-priority order), bodies differ and are not parent / child */
 } FN(Model);
 
 typedef struct {
@@ -66,13 +69,15 @@ typedef struct {
     int decimation;         /* 10 */
     REAL action_scale;      /* 1.0 */
     int max_contacts;       /* 8: with <= 7 limit rows the solver has at most 31 rows = one warp lane per row + one lane for the unconstrained update */
+    int max_self_contacts;  /* 0 = robot self-collision off (the lower-limb fast kernel), else at most this many sphere-sphere contacts per substep */
 } FN(SimCfg);
 
 #define MAXB 36
 #define MAXV 40
 #define MAXC 16
+#define MAXSC 8
 #define MAXLIM 7
-#define MAXROWS (3 * MAXC + MAXV)
+#define MAXROWS (3 * (MAXC + MAXSC) + MAXV)
 
 static inline void FN(v3cross)(const REAL *a, const REAL *b, REAL *o) {
     REAL x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
@@ -339,9 +344,9 @@ static void FN(point_jac_row)(const FN(Model) *M, const FN(Kin) *K, int b, const
 }
 
 typedef struct {
-    int link[MAXC];
-    REAL n[MAXC][3], t1[MAXC][3], t2[MAXC][3];
-    REAL lam[MAXC][3];
+    int link[MAXC + MAXSC], link2[MAXC + MAXSC];   /* link2 >= 0: self-contact, the reaction goes to that link */
+    REAL n[MAXC + MAXSC][3], t1[MAXC + MAXSC][3], t2[MAXC + MAXSC][3];
+    REAL lam[MAXC + MAXSC][3];
     int count;
 } FN(Contacts);
 
@@ -379,7 +384,7 @@ static int FN(substep)(const FN(Model) *M, const FN(Terrain) *T, const FN(SimCfg
         REAL d = (xs[2] - hgt) * n[2] - M->sph_rad[s];
         if (!(d < cfg->contact_offset)) continue;
         int c = C.count++;
-        C.link[c] = M->sph_link[s];
+        C.link[c] = M->sph_link[s]; C.link2[c] = -1;
         REAL xc[3] = {xs[0] - n[0] * M->sph_rad[s], xs[1] - n[1] * M->sph_rad[s], xs[2] - n[2] * M->sph_rad[s]};
         /* tangent frame: t1 = normalised projection of world x (or y if n ~ x) */
         const int usey = (n[0] > (REAL)0.9 || n[0] < (REAL)-0.9);
@@ -401,6 +406,48 @@ static int FN(substep)(const FN(Model) *M, const FN(Terrain) *T, const FN(SimCfg
         sg += FN(mix64)((1ull << 56) | (unsigned long long)s | ((unsigned long long)cell[0] << 6) | ((unsigned long long)cell[1] << 18) |
                         ((unsigned long long)cell[2] << 30) | ((unsigned long long)bounce << 33) | ((unsigned long long)usey << 34));
         bias[3 * c] = target; bias[3 * c + 1] = 0; bias[3 * c + 2] = 0;
+    }
+    /* ---- robot self-collision: sphere-sphere contacts between non-adjacent bodies, candidate pairs in priority order; normal from sphere b to
+     * sphere a, contact point in the middle of the gap, rows = J_a - J_b (normal + 2 friction, mu = the robot's own material), same target
+     * velocity rule as the ground contacts.  Signature item = 3<<56 | pair index. */
+    {
+        int nself = 0;
+        for (int pi = 0; pi < M->npairs && nself < cfg->max_self_contacts; pi++) {
+            const int sa = M->pair_a[pi], sb = M->pair_b[pi], ba = M->sph_body[sa], bb = M->sph_body[sb];
+            REAL xa[3], xb[3];
+            FN(m3v)(K->R[ba], M->sph_pos + 3 * sa, xa); FN(m3v)(K->R[bb], M->sph_pos + 3 * sb, xb);
+            for (int k = 0; k < 3; k++) { xa[k] += K->o[ba][k]; xb[k] += K->o[bb][k]; }
+            REAL dv[3] = {xa[0] - xb[0], xa[1] - xb[1], xa[2] - xb[2]};
+            const REAL dist = SQRT(FN(v3dot)(dv, dv)), d = dist - M->sph_rad[sa] - M->sph_rad[sb];
+            if (!(d < cfg->contact_offset) || !(dist > (REAL)1e-9)) continue;
+            nself++;
+            int c = C.count++;
+            C.link[c] = M->sph_link[sa]; C.link2[c] = M->sph_link[sb];
+            REAL n[3] = {dv[0] / dist, dv[1] / dist, dv[2] / dist};
+            const REAL mid = M->sph_rad[sb] + (REAL)0.5 * d;
+            REAL xc[3] = {xb[0] + n[0] * mid, xb[1] + n[1] * mid, xb[2] + n[2] * mid};
+            const int usey = (n[0] > (REAL)0.9 || n[0] < (REAL)-0.9);
+            const REAL *e = usey ? ey : ex;
+            REAL dn = FN(v3dot)(e, n), t1[3] = {e[0] - dn * n[0], e[1] - dn * n[1], e[2] - dn * n[2]};
+            REAL inv = 1 / SQRT(FN(v3dot)(t1, t1)); for (int k = 0; k < 3; k++) t1[k] *= inv;
+            REAL t2[3]; FN(v3cross)(n, t1, t2);
+            for (int k = 0; k < 3; k++) { C.n[c][k] = n[k]; C.t1[c][k] = t1[k]; C.t2[c][k] = t2[k]; C.lam[c][k] = 0; }
+            const REAL *dirs[3] = {n, t1, t2};
+            for (int k = 0; k < 3; k++) {
+                REAL Jb[MAXV];
+                FN(point_jac_row)(M, K, ba, xc, dirs[k], J[3 * c + k]);
+                FN(point_jac_row)(M, K, bb, xc, dirs[k], Jb);
+                for (int i = 0; i < nv; i++) J[3 * c + k][i] -= Jb[i];
+            }
+            REAL vn0 = 0; for (int i = 0; i < nv; i++) vn0 += J[3 * c][i] * (i < nd ? qd[i] : root[7 + i - nd]);
+            REAL target;
+            if (d > 0) target = -d / dt;
+            else { target = -d * cfg->erp / dt; if (target > cfg->max_depen_vel) target = cfg->max_depen_vel; }
+            const int bounce = (vn0 < -cfg->bounce_threshold && -rest_env * vn0 > target);
+            if (bounce) target = -rest_env * vn0;
+            sg += FN(mix64)((3ull << 56) | (unsigned long long)pi | ((unsigned long long)bounce << 33) | ((unsigned long long)usey << 34));
+            bias[3 * c] = target; bias[3 * c + 1] = 0; bias[3 * c + 2] = 0;
+        }
     }
     int nrows = 3 * C.count;
     /* joint limit rows (speculative, predicted with the PRE-step joint rate so that all constraint rows are known
@@ -434,7 +481,7 @@ static int FN(substep)(const FN(Model) *M, const FN(Terrain) *T, const FN(SimCfg
                 REAL v = 0; for (int i = 0; i < nv; i++) v += J[r][i] * u[i];
                 REAL dl = -(v - bias[r]) / Ad[r], ln = C.lam[c][k] + dl;
                 if (k == 0) { if (ln < 0) ln = 0; }
-                else { REAL lim = mu * C.lam[c][0]; if (ln > lim) ln = lim; if (ln < -lim) ln = -lim; }
+                else { REAL lim = (C.link2[c] >= 0 ? mu_env : mu) * C.lam[c][0]; if (ln > lim) ln = lim; if (ln < -lim) ln = -lim; }
                 dl = ln - C.lam[c][k]; C.lam[c][k] = ln;
                 for (int i = 0; i < nv; i++) u[i] += Y[r][i] * dl;
             }
@@ -453,8 +500,11 @@ static int FN(substep)(const FN(Model) *M, const FN(Terrain) *T, const FN(SimCfg
     /* ---- contact force report (impulse / dt), per URDF link, world frame, force ON the body */
     for (int i = 0; i < M->nl * 3; i++) cf_out[i] = 0;
     for (int c = 0; c < C.count; c++)
-        for (int k = 0; k < 3; k++)
-            cf_out[3 * C.link[c] + k] += (C.n[c][k] * C.lam[c][0] + C.t1[c][k] * C.lam[c][1] + C.t2[c][k] * C.lam[c][2]) / dt;
+        for (int k = 0; k < 3; k++) {
+            const REAL f = (C.n[c][k] * C.lam[c][0] + C.t1[c][k] * C.lam[c][1] + C.t2[c][k] * C.lam[c][2]) / dt;
+            cf_out[3 * C.link[c] + k] += f;
+            if (C.link2[c] >= 0) cf_out[3 * C.link2[c] + k] -= f;   /* reaction on the other link of a self-contact */
+        }
     /* ---- joint velocity limit + integrate */
     for (int j = 0; j < nd; j++) {
         REAL v = u[j], vl = M->dof_vel_limit[j];
@@ -505,7 +555,7 @@ static int FN(physics_step_impl)(const FN(Model) *M, const FN(Terrain) *T, const
                                 REAL *avg_foot_force, REAL *avg_foot_linvel, REAL *avg_foot_angvel, unsigned long long *active_sig) {
     const int nd = M->nd, nl = M->nl, nf = M->nf;
     int err = 0;
-    if (M->nb > MAXB || nd + 6 > MAXV || cfg->max_contacts > MAXC) return 2;
+    if (M->nb > MAXB || nd + 6 > MAXV || cfg->max_contacts > MAXC || cfg->max_self_contacts > MAXSC) return 2;
 #pragma omp parallel for schedule(static) reduction(| : err)
     for (int e = 0; e < N; e++) {
         REAL *rt = root + 13 * e, *q = dof_pos + nd * e, *qd = dof_vel + nd * e, *tq = torques + nd * e;
@@ -626,5 +676,6 @@ int FN(grx_oracle_dynamics_terms)(const FN(Model) *M, const FN(SimCfg) *cfg, con
 #undef MAXB
 #undef MAXV
 #undef MAXC
+#undef MAXSC
 #undef MAXLIM
 #undef MAXROWS

@@ -44,6 +44,50 @@ def task_tables(model, cfg):
                 termination_links=term, ankle_dofs=ankle)
 
 
+def _axang(a, th):
+    c, s_, t = np.cos(th), np.sin(th), 1 - np.cos(th)
+    return np.array([[c + a[0] * a[0] * t, a[0] * a[1] * t - a[2] * s_, a[0] * a[2] * t + a[1] * s_],
+                     [a[1] * a[0] * t + a[2] * s_, c + a[1] * a[1] * t, a[1] * a[2] * t - a[0] * s_],
+                     [a[2] * a[0] * t - a[1] * s_, a[2] * a[1] * t + a[0] * s_, c + a[2] * a[2] * t]])
+
+
+def forward_kinematics(model, q):
+    """Body frames (R [nb, 3, 3], o [nb, 3]) of the dynamic tree with the base at the origin, joint angles q [nd] (host-side helper)."""
+    nb = model["nb"]
+    R, o = np.zeros((nb, 3, 3)), np.zeros((nb, 3))
+    R[0] = np.eye(3)
+    jrot = np.asarray(model["jrot"]).reshape(nb, 3, 3)
+    for b in range(1, nb):
+        p = int(model["parent"][b])
+        R[b] = R[p] @ jrot[b] @ _axang(np.asarray(model["axis"]).reshape(nb, 3)[b], q[b - 1])
+        o[b] = o[p] + R[p] @ np.asarray(model["jpos"]).reshape(nb, 3)[b]
+    return R, o
+
+
+def self_collision_pairs(model, tables, max_pairs=64, min_rest_gap=0.005):
+    """Candidate sphere pairs for robot self-collision (legged_robot_config.py:121 `self_collisions = 0` = enabled; every actor is created
+    with collision_filter 0, legged_robot.py:1022-1028, so all of its shapes collide with each other except those on directly connected
+    links).  Indices refer to the contact-PRIORITY order of the spheres (tables['sph_order']).  Kept: pairs on different, non-adjacent
+    dynamic bodies that are apart by more than `min_rest_gap` in the default pose (shapes that touch by construction would otherwise push the
+    robot apart at rest); ordered by that rest gap (the closest pairs — feet, shanks, hands vs thighs — first), at most `max_pairs`."""
+    order = np.asarray(tables["sph_order"])
+    body, pos, rad = np.asarray(model["sph_body"])[order], np.asarray(model["sph_pos"]).reshape(-1, 3)[order], np.asarray(model["sph_rad"])[order]
+    parent = np.asarray(model["parent"])
+    R, o = forward_kinematics(model, np.asarray(tables["default_pos"], float))
+    x = np.stack([o[b] + R[b] @ p for b, p in zip(body, pos)])
+    cand = []
+    for a in range(len(rad)):
+        for b in range(a + 1, len(rad)):
+            ba, bb = int(body[a]), int(body[b])
+            if ba == bb or parent[ba] == bb or parent[bb] == ba:
+                continue
+            gap = float(np.linalg.norm(x[a] - x[b]) - rad[a] - rad[b])
+            if gap > min_rest_gap:
+                cand.append((gap, a, b))
+    cand.sort()
+    return np.array([[a, b] for _, a, b in cand[:max_pairs]], dtype=np.int32).reshape(-1, 2)
+
+
 def sample_domain_rand(model, cfg, num_envs, rng_np, rng_torch_cpu=None):
     """Per-env randomised physical parameters, vectorised.
 
