@@ -204,6 +204,36 @@ int grx_env_debug_active_sig(grx_env *env, int32_t enable);
 
 #define GRX_RNG_K 68 /* == grx_b200/rng_layout.py K */
 
+/* ---- generic-topology dynamics (full-body 32-DOF GR1T1 / GR1T2, robot self-collision) --------------------------------------------------
+ * The fused env kernel above is specialised to the registered lower-limb tree.  grx_physg runs the same dynamics spec for ANY revolute tree
+ * with a floating base (<= 36 bodies in depth-first order, <= 32 DOF, <= 48 links, <= 32 contact spheres) incl. robot self-collision
+ * (legged_robot_config.py:121 self_collisions = 0 = enabled; create_actor(..., collision_filter = 0), legged_robot.py:1022-1028): one policy
+ * step of physics = the body of during_physics_step (legged_robot_fftai.py:51-88) — decimation x [PD torque (legged_robot.py:679-715) ->
+ * articulated dynamics -> ground / self / joint-limit constraints -> integrate] + the foot averages.  grx_physg_step has the signature of the
+ * CPU oracle's grx_oracle_physics_step on DEVICE pointers (state in place), so the two are compared call for call. */
+typedef struct {
+    float sim_dt, gravity, contact_offset, bounce_threshold, max_depen_vel, erp;
+    int32_t solver_iters, decimation;
+    float action_scale;
+    int32_t max_contacts;        /* ground contacts per robot and substep (<= 8) */
+    int32_t max_self_contacts;   /* sphere-sphere self-contacts per robot and substep (<= 4), 0 = self-collision off */
+} grx_physg_cfg;
+typedef struct grx_physg grx_physg;
+/* self_pairs: [npairs, 2] candidate sphere pairs (indices into the model's sphere arrays, priority order; grx_b200/robot.py:self_collision_pairs) */
+int grx_physg_create(const grx_model_desc *model, const int32_t *self_pairs, int32_t npairs, const grx_physg_cfg *cfg, int32_t num_envs,
+                     int32_t device, grx_physg **out);
+int grx_physg_destroy(grx_physg *p);
+int grx_physg_set_terrain_plane(grx_physg *p, float friction, float restitution);
+int grx_physg_set_terrain_heightfield(grx_physg *p, const int16_t *samples, int32_t rows, int32_t cols, float hscale, float vscale,
+                                      float border, float friction, float restitution);
+/* d_root [N,13], d_dof_pos / d_dof_vel [N,nd] advanced in place; d_actions / d_last_actions [N,nd] (already clipped), delay as in
+ * legged_robot_fftai.py:53-61; outputs: d_torques [N,nd] (last substep), d_link_state [N,nl,13], d_contact_force [N,nl,3],
+ * d_avg_foot_force [N,nf], d_avg_foot_linvel / d_avg_foot_angvel [N,nf,3]; d_active_sig [N, decimation] u64 or NULL. */
+int grx_physg_step(grx_physg *p, float *d_root, float *d_dof_pos, float *d_dof_vel, const float *d_actions, const float *d_last_actions,
+                   float delay, const float *d_motor_strength, const float *d_base_inertial, const float *d_friction,
+                   const float *d_restitution, float *d_torques, float *d_link_state, float *d_contact_force, float *d_avg_foot_force,
+                   float *d_avg_foot_linvel, float *d_avg_foot_angvel, uint64_t *d_active_sig, void *stream);
+
 /* ---- PPO ---------------------------------------------------------------------------------------------------- */
 typedef struct {
     int32_t num_envs, num_steps;             /* N (local), T */

@@ -118,6 +118,49 @@ def make_cfg(robot="GR1T1", num_envs=4096, mesh_type="plane"):
     return cfg
 
 
+def make_full_body_cfg(robot="GR1T1", num_envs=4096, mesh_type="plane"):
+    """The reference's UNREGISTERED full-body configuration (``GR1T1Cfg`` / ``GR1T2Cfg``: gr1t1_config.py:10-307, gr1t2_config.py:7-14): 32 DOF /
+    32 actions, PD gains and default angles for legs, waist, head and arms, the full-body termination list, action limits.  As upstream, its
+    reward scales are all zero except the inherited ``termination = 0`` (gr1t1_config.py:252-254) and its ``num_obs = 121`` is stale: the
+    observation layout of gr1t1.py:281-313 gives 9 + 3 * 32 = 105, which is what this object declares."""
+    cfg = make_cfg(robot, num_envs, mesh_type)
+    cfg.robot = robot + "_full"
+    d15, d30 = math.radians(15.0), math.radians(30.0)
+    dja = {}
+    for side, sgn in (("left", 1.0), ("right", -1.0)):
+        dja.update({f"{side}_hip_roll_joint": 0.0, f"{side}_hip_yaw_joint": 0.0, f"{side}_hip_pitch_joint": -d15, f"{side}_knee_pitch_joint": d30,
+                    f"{side}_ankle_pitch_joint": -d15, f"{side}_ankle_roll_joint": 0.0,
+                    f"{side}_shoulder_pitch_joint": 0.0, f"{side}_shoulder_roll_joint": 0.2 * sgn, f"{side}_shoulder_yaw_joint": 0.0,
+                    f"{side}_elbow_pitch_joint": -0.3, f"{side}_wrist_yaw_joint": 0.0, f"{side}_wrist_roll_joint": 0.0, f"{side}_wrist_pitch_joint": 0.0})
+    for j in ("waist_yaw", "waist_pitch", "waist_roll", "head_yaw", "head_pitch", "head_roll"):
+        dja[j + "_joint"] = 0.0
+    cfg.init_state.default_joint_angles = dja                                           # gr1t1_config.py:93-136
+    cfg.control.stiffness = {"hip_roll": 251.625, "hip_yaw": 362.5214, "hip_pitch": 200, "knee_pitch": 200, "ankle_pitch": 10.9805, "ankle_roll": 0.25,
+                             "waist_yaw": 362.5214, "waist_pitch": 362.5214, "waist_roll": 362.5214, "head_yaw": 10.0, "head_pitch": 10.0, "head_roll": 10.0,
+                             "shoulder_pitch": 92.85, "shoulder_roll": 92.85, "shoulder_yaw": 112.06, "elbow_pitch": 112.06,
+                             "wrist_yaw": 10.0, "wrist_roll": 10.0, "wrist_pitch": 10.0}  # gr1t1_config.py:158-168
+    cfg.control.damping = {"hip_roll": 14.72, "hip_yaw": 10.0833, "hip_pitch": 11, "knee_pitch": 11, "ankle_pitch": 0.5991, "ankle_roll": 0.01,
+                           "waist_yaw": 10.0833, "waist_pitch": 10.0833, "waist_roll": 10.0833, "head_yaw": 1.0, "head_pitch": 1.0, "head_roll": 1.0,
+                           "shoulder_pitch": 2.575, "shoulder_roll": 2.575, "shoulder_yaw": 3.1, "elbow_pitch": 3.1,
+                           "wrist_yaw": 1.0, "wrist_roll": 1.0, "wrist_pitch": 1.0}      # gr1t1_config.py:169-178
+    cfg.asset.terminate_after_contacts_on = ["imu", "torso", "head_pitch", "waist", "upper_arm", "lower_arm", "hand"]   # gr1t1_config.py:78-86
+    cfg.env.num_actions, cfg.env.num_obs = 32, 105
+    cfg.env.num_pri_obs = 105 + 8 + len(cfg.terrain.measured_points_x) * len(cfg.terrain.measured_points_y)
+    amax = np.array([0.79, 0.7, 0.7, 1.92, 0.52, 0.44, 0.09, 0.7, 0.7, 1.92, 0.52, 0.44, 1.05, 1.22, 0.7, 2.71, 0.35, 0.35,
+                     1.92, 3.27, 2.97, 2.27, 2.97, 0.61, 0.61, 1.92, 0.57, 2.97, 2.27, 2.97, 0.61, 0.61])
+    amin = np.array([-0.09, -0.7, -1.75, -0.09, -1.05, -0.44, -0.79, -0.7, -1.75, -0.09, -1.05, -0.44, -1.05, -0.52, -0.7, -2.71, -0.35, -0.52,
+                     -2.79, -0.57, -2.97, -2.27, -2.97, -0.61, -0.61, -2.79, -3.27, -2.97, -2.27, -2.97, -0.61, -0.61])   # gr1t1_config.py:282-299
+    cfg.normalization.clip_actions_max = amax + (np.abs(amax) + np.abs(amin)) * 0.01
+    cfg.normalization.clip_actions_min = amin - (np.abs(amax) + np.abs(amin)) * 0.01
+    return cfg
+
+
+def full_body_tables(model):
+    """robot.task_tables for a full-body model (urdf.builtin_model('GR1T1_full' / 'GR1T2_full'))."""
+    from .robot import task_tables
+    return task_tables(model, make_full_body_cfg("GR1T2" if "GR1T2" in str(model.get("name", "")) else "GR1T1", 4, "plane"))
+
+
 def make_train_cfg(robot="GR1T1"):
     """PPO / runner config of the registered tasks as the dict ``OnPolicyRunner`` takes
     (gr1t1_config.py:310-345, gr1t1_lower_limb_config.py:107-116, legged_robot_config.py:254-294)."""
