@@ -82,7 +82,7 @@ typedef struct {
     float cmd_range[3][2];           /* lin_vel_x, lin_vel_y, ang_vel_yaw */
     float max_push_vel_xy;
     int32_t add_noise, randomize_init_dof_pos, randomize_init_base_velocity, curriculum, custom_origins, measure_heights;
-    float noise_scale_vec[64];       /* [num_obs] */
+    float noise_scale_vec[128];      /* [num_obs] (39 lower-limb, 105 full body) */
     float obs_scale_lin_vel, obs_scale_ang_vel, obs_scale_gravity, obs_scale_dof_pos, obs_scale_dof_vel,
           obs_scale_action, obs_scale_height;
     float base_init_state[13];
@@ -202,7 +202,20 @@ int grx_env_debug_dynamics(grx_env *env, int32_t index, float *h_M, float *h_h);
  * row that differs from the oracle beyond rounding can be attributed to a differing decision (contact-threshold flip) or flagged. */
 int grx_env_debug_active_sig(grx_env *env, int32_t enable);
 
-#define GRX_RNG_K 68 /* == grx_b200/rng_layout.py K */
+#define GRX_RNG_K 68 /* == grx_b200/rng_layout.py K of the registered 10-DOF tasks; in general 28 + 4 * num_dof (grx_env_info(env, 0)) */
+
+/* Models other than the registered lower-limb tree — any floating-base revolute tree with <= 36 bodies in depth-first order, <= 32 DOF, <= 48
+ * links, <= 32 contact spheres, 2 feet: the full-body 32-DOF GR1T1 / GR1T2 of gr1t1_config.py:10-307 (num_obs = 9 + 3 * 32 = 105, num_pri_obs =
+ * 105 + 8 + H) — run behind the SAME grx_env_* entries on the generic-topology kernels (csrc/grx_phys_generic.cu); GRX_ENV_GENERIC=1 in the
+ * environment routes the lower-limb model there as well.
+ * Robot self-collision (legged_robot_config.py:121 self_collisions = 0 = enabled; create_actor(..., collision_filter = 0),
+ * legged_robot.py:1022-1028): pairs = [npairs, 2] candidate sphere pairs (indices into the model's sphere arrays, priority order;
+ * grx_b200/robot.py:self_collision_pairs), at most max_self_contacts (<= 4) sphere-sphere contacts per robot and substep.  Generic-topology
+ * envs only (GRX_E_INVALID on the specialised lower-limb kernel, which carries no self-contact rows). */
+int grx_env_set_self_collision(grx_env *env, const int32_t *pairs, int32_t npairs, int32_t max_self_contacts);
+/* Shape facts a binding needs before it allocates: what = 0 uniform draws per env and step (d_uniform row width), 1 floats per state record,
+ * 2 floats per parameter record, 3 actuated DOF, 4 = 1 when the generic-topology kernels run this env; -1 on a bad argument. */
+int64_t grx_env_info(grx_env *env, int32_t what);
 
 /* ---- generic-topology dynamics (full-body 32-DOF GR1T1 / GR1T2, robot self-collision) --------------------------------------------------
  * The fused env kernel above is specialised to the registered lower-limb tree.  grx_physg runs the same dynamics spec for ANY revolute tree

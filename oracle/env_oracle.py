@@ -65,6 +65,7 @@ class EnvOracle:
         self.cfg, self.tb, self.phys = cfg, tables, phys
         self.N = N = len(consts["friction"])
         self.nd = nd = len(tables["kp"])
+        self.L = L.layout(nd)   # slots of the uniform-draw table for this DOF count
         self.dt = cfg.control.decimation * cfg.sim.dt                                  # LR:92
         self.max_episode_length_s = cfg.env.episode_length_s
         self.max_episode_length = float(np.ceil(self.max_episode_length_s / self.dt))  # LR:101
@@ -212,11 +213,11 @@ class EnvOracle:
         base_ang_vel = quat_rotate_inverse(base_quat, self.root_states[:, 10:13])
         g_proj = quat_rotate_inverse(base_quat, self.gravity_vec)
         ids = (self.episode_length_buf % self.resample_interval == 0).nonzero(as_tuple=False).flatten()
-        self._resample_commands(ids, U, L.CMD_TIME)
+        self._resample_commands(ids, U, self.L.CMD_TIME)
         measured_heights = self._get_heights()
         if cfg.domain_rand.push_robots and (self.common_step_counter % self.push_interval == 0):   # LR:333-334, 786-797
             mv = cfg.domain_rand.max_push_vel_xy
-            self.root_states[:, 7:9] = (mv - -mv) * U[:, L.PUSH:L.PUSH + 2] + -mv
+            self.root_states[:, 7:9] = (mv - -mv) * U[:, self.L.PUSH:self.L.PUSH + 2] + -mv
         # FF:108-133
         feet_contact = contact_forces[:, self.feet, 2] > 1.0
         contact_filt = torch.logical_or(feet_contact, self.feet_contact_last)
@@ -247,22 +248,22 @@ class EnvOracle:
             if self.curriculum:
                 self._update_terrain_curriculum(env_ids, U)
             if cfg.domain_rand.randomize_init_dof_pos:                                 # LR:725-734
-                self.dof_pos[env_ids] = ((1.5 - 0.5) * U[env_ids, L.RESET_DOF:L.RESET_DOF + self.nd] + 0.5) * self.default_dof_pos
+                self.dof_pos[env_ids] = ((1.5 - 0.5) * U[env_ids, self.L.RESET_DOF:self.L.RESET_DOF + self.nd] + 0.5) * self.default_dof_pos
             else:
                 self.dof_pos[env_ids] = self.default_dof_pos
             self.dof_vel[env_ids] = 0.0
             self.root_states[env_ids] = self.base_init_state                           # LR:750-779
             self.root_states[env_ids, :3] += self.env_origins[env_ids]
             if self.custom_origins:
-                self.root_states[env_ids, :2] += (1.0 - -1.0) * U[env_ids, L.RESET_XY:L.RESET_XY + 2] + -1.0
-            yaw = ((2 * np.pi - -2 * np.pi) * U[env_ids, L.RESET_YAW:L.RESET_YAW + 1] + -2 * np.pi).squeeze(1)
+                self.root_states[env_ids, :2] += (1.0 - -1.0) * U[env_ids, self.L.RESET_XY:self.L.RESET_XY + 2] + -1.0
+            yaw = ((2 * np.pi - -2 * np.pi) * U[env_ids, self.L.RESET_YAW:self.L.RESET_YAW + 1] + -2 * np.pi).squeeze(1)
             zer = torch.zeros(len(env_ids))
             self.root_states[env_ids, 3:7] = quat_from_euler_xyz(zer, zer, yaw)
             if cfg.domain_rand.randomize_init_base_velocity:
-                self.root_states[env_ids, 7:13] = (0.5 - -0.5) * U[env_ids, L.RESET_VEL:L.RESET_VEL + 6] + -0.5
+                self.root_states[env_ids, 7:13] = (0.5 - -0.5) * U[env_ids, self.L.RESET_VEL:self.L.RESET_VEL + 6] + -0.5
             else:
                 self.root_states[env_ids, 7:13] = 0.0
-            self._resample_commands(env_ids, U, L.CMD_RESET)
+            self._resample_commands(env_ids, U, self.L.CMD_RESET)
             self.last_actions[env_ids] = 0.0
             self.last_dof_vel[env_ids] = 0.0
             self.feet_air_time[env_ids] = 0.0
@@ -290,7 +291,7 @@ class EnvOracle:
         pri = torch.cat((obs, base_lin_vel * os_.lin_vel, self.base_heights_offset.unsqueeze(1) * hm, feet_contact_f,
                          feet_height * hm, surround * hm), dim=-1)
         if cfg.noise.add_noise:                                                         # LR:478-481
-            obs = obs + (2 * U[:, L.NOISE:L.NOISE + obs.shape[1]] - 1) * self.noise_scale_vec
+            obs = obs + (2 * U[:, self.L.NOISE:self.L.NOISE + obs.shape[1]] - 1) * self.noise_scale_vec
         self.last_actions[:] = self.actions[:]                                         # LR:299-300
         self.last_dof_vel[:] = self.dof_vel[:]
         self.last_last_actions[:] = self.last_actions[:]                               # FF:94
@@ -308,7 +309,7 @@ class EnvOracle:
         move_up = distance > self.env_length / 2
         move_down = (distance < torch.norm(self.commands[env_ids, :2], dim=1) * self.max_episode_length_s * 0.5) * ~move_up
         self.terrain_levels[env_ids] += 1 * move_up - 1 * move_down
-        rnd = torch.floor(U[env_ids, L.CURRICULUM] * self.max_terrain_level).long().clamp(max=self.max_terrain_level - 1)
+        rnd = torch.floor(U[env_ids, self.L.CURRICULUM] * self.max_terrain_level).long().clamp(max=self.max_terrain_level - 1)
         self.terrain_levels[env_ids] = torch.where(self.terrain_levels[env_ids] >= self.max_terrain_level, rnd,
                                                    torch.clip(self.terrain_levels[env_ids], 0))
         self.env_origins[env_ids] = self.terrain_origins[self.terrain_levels[env_ids], self.terrain_types[env_ids]]

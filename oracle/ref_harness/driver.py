@@ -21,8 +21,28 @@ import torch
 from . import stub
 
 
+def full_body_cfg(task="GR1T1"):
+    """The reference's UNREGISTERED full-body configuration (gr1t1_config.py:10-307 GR1T1Cfg / gr1t2_config.py GR1T2Cfg: 32 DOF) made runnable:
+    its stale `num_obs = 121` replaced by what compute_observations (gr1t1.py:281-313) really produces (9 + 3 * 32 = 105; pri = 105 + 8 + 121),
+    and — because upstream leaves every full-body reward scale at zero — the reward scales of the registered lower-limb task."""
+    import legged_gym.envs  # noqa: F401
+    if task == "GR1T2":
+        from legged_gym.envs.gr1t2.gr1t2_config import GR1T2Cfg as Full
+        from legged_gym.envs.gr1t2.gr1t2_lower_limb_config import GR1T2LowerLimbCfg as Low
+    else:
+        from legged_gym.envs.gr1t1.gr1t1_config import GR1T1Cfg as Full
+        from legged_gym.envs.gr1t1.gr1t1_lower_limb_config import GR1T1LowerLimbCfg as Low
+    cfg, low = Full(), Low()
+    cfg.env.num_obs = 9 + 3 * cfg.env.num_actions
+    cfg.env.num_pri_obs = cfg.env.num_obs + 8 + len(cfg.terrain.measured_points_x) * len(cfg.terrain.measured_points_y)
+    for k in dir(low.rewards.scales):
+        if not k.startswith("_"):
+            setattr(cfg.rewards.scales, k, getattr(low.rewards.scales, k))
+    return cfg
+
+
 def make_reference_env(task="GR1T1", num_envs=64, mesh_type="plane", seed=1, mutate_cfg=None, quiet=True,
-                       terrain_rows=None, terrain_cols=None):
+                       terrain_rows=None, terrain_cols=None, full_body=False):
     """Instantiate the reference task class over FakeGym (CPU).  Returns (env, env_cfg)."""
     stub.install()
     out = io.StringIO()
@@ -30,7 +50,10 @@ def make_reference_env(task="GR1T1", num_envs=64, mesh_type="plane", seed=1, mut
         import legged_gym.envs  # noqa: F401  registers GR1T1 / GR1T2
         from legged_gym.utils.helpers import class_to_dict, parse_sim_params, set_seed
         from legged_gym.utils.task_registry import task_registry
-        env_cfg, _ = task_registry.get_cfgs(task)
+        if full_body:
+            env_cfg = full_body_cfg(task)
+        else:
+            env_cfg, _ = task_registry.get_cfgs(task)
         env_cfg = copy.deepcopy(env_cfg)
         env_cfg.env.num_envs = num_envs
         env_cfg.terrain.mesh_type = mesh_type
@@ -54,7 +77,8 @@ class _Injector:
     """Context manager replacing the generator functions by table look-ups for one env.step()."""
 
     def __init__(self, env, U, delay):
-        from grx_b200 import rng_layout as L
+        from grx_b200 import rng_layout
+        L = rng_layout.layout(env.num_actions)   # slots of the draw table for this DOF count (== the module constants for 10 DOF)
         self.env, self.U, self.delay, self.L = env, U, float(delay), L
         self.saved = []
 

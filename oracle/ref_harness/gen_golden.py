@@ -29,9 +29,10 @@ OUTPUTS = ("obs_buf", "pri_obs_buf", "rew_buf", "reset_buf", "time_out_buf", "ba
            "base_projected_gravity", "feet_height", "measured_heights", "torques")
 
 
-def scenario(name, task, num_envs, mesh_type, steps, seed, mutate_cfg=None, rows=None, cols=None):
+def scenario(name, task, num_envs, mesh_type, steps, seed, mutate_cfg=None, rows=None, cols=None, full_body=False):
     env, cfg = make_reference_env(task, num_envs, mesh_type, seed=seed, mutate_cfg=mutate_cfg, terrain_rows=rows,
-                                  terrain_cols=cols)
+                                  terrain_cols=cols, full_body=full_body)
+    K = L.layout(env.num_actions).K
     env.reset()
     g = torch.Generator().manual_seed(1000 + seed)
     N = num_envs
@@ -64,7 +65,7 @@ def scenario(name, task, num_envs, mesh_type, steps, seed, mutate_cfg=None, rows
     env.post_physics_step = hooked
     out = {("const/" + k): np.asarray(v) for k, v in consts.items() if k != "reward_names"}
     out["const/reward_names"] = np.array(consts["reward_names"])
-    out["meta/task"], out["meta/mesh_type"], out["meta/steps"] = np.array(task), np.array(mesh_type), np.array(steps)
+    out["meta/task"], out["meta/mesh_type"], out["meta/steps"] = np.array(task + ("_full" if full_body else "")), np.array(mesh_type), np.array(steps)
     out["meta/decimation"] = np.array(env.cfg.control.decimation)
     out["meta/flags"] = np.array([int(env.cfg.noise.add_noise), int(env.cfg.domain_rand.push_robots),
                                   int(env.cfg.terrain.curriculum), int(env.cfg.domain_rand.randomize_init_dof_pos),
@@ -81,7 +82,7 @@ def scenario(name, task, num_envs, mesh_type, steps, seed, mutate_cfg=None, rows
         actions[:, 3] += 0.2
         if t % 4 == 1:
             actions[0] = 5.0        # exercises the per-joint action clip
-        U = torch.rand(N, L.K, generator=g)
+        U = torch.rand(N, K, generator=g)
         delay = max(0.0, float(5 + 2 * torch.randn(1, generator=g)))
         injected_step(env, actions, U, delay)
         s = dump_state(env)
@@ -121,7 +122,14 @@ def main():
     scenario("hf_gr1t1", "GR1T1", 32, "heightfield", steps=10, seed=3, rows=3, cols=4)
     scenario("hf_gr1t2_dr", "GR1T2", 32, "heightfield", steps=8, seed=4, rows=3, cols=4)
     scenario("tm_gr1t1", "GR1T1", 32, "trimesh", steps=8, seed=5, rows=3, cols=4)   # mesh_type = 'trimesh' + curriculum (BASELINE config #5)
+    # the reference classes on the UNREGISTERED full-body 32-DOF configuration (driver.full_body_cfg), robot self-collision on
+    scenario("plane_gr1t1_full", "GR1T1", 16, "plane", steps=8, seed=6, full_body=True)
+    scenario("hf_gr1t2_full", "GR1T2", 16, "heightfield", steps=8, seed=7, rows=3, cols=4, full_body=True)
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "full":   # only the full-body fixtures
+        scenario("plane_gr1t1_full", "GR1T1", 16, "plane", steps=8, seed=6, full_body=True)
+        scenario("hf_gr1t2_full", "GR1T2", 16, "heightfield", steps=8, seed=7, rows=3, cols=4, full_body=True)
+    else:
+        main()

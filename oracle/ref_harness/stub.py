@@ -232,10 +232,17 @@ class FakeGym:
             m, c, I6 = base_inertial_for(self.model, e["mass_scale"], e["com_offset"])
             bi[i, 0], bi[i, 1:4], bi[i, 4:10] = m, c, I6
         self.base_inertial = bi
-        from grx_b200.config import make_cfg
-        from grx_b200.robot import task_tables
-        order = task_tables(self.model, make_cfg(self.model["name"]))["sph_order"]   # same contact priority as the product
-        ctl = dict(kp=np.zeros(nd), kd=np.zeros(nd), default_pos=np.zeros(nd), foot_links=[0], sph_order=order)
+        from grx_b200.config import full_body_tables, make_cfg
+        from grx_b200.robot import self_collision_pairs, task_tables
+        sim_extra = {}
+        if nd > 10:   # full-body tree: same contact priority AND the same self-collision candidate pairs as the product (legged_robot_config.py:121)
+            tb = full_body_tables(self.model)
+            ctl = dict(kp=np.zeros(nd), kd=np.zeros(nd), default_pos=np.zeros(nd), foot_links=[0], sph_order=tb["sph_order"],
+                       self_pairs=self_collision_pairs(self.model, tb))
+            sim_extra = dict(max_self_contacts=4)
+        else:
+            order = task_tables(self.model, make_cfg(self.model["name"]))["sph_order"]   # same contact priority as the product
+            ctl = dict(kp=np.zeros(nd), kd=np.zeros(nd), default_pos=np.zeros(nd), foot_links=[0], sph_order=order)
         sp = self.sim_params
         terr = self.terrain
         if terr is not None and "trimesh" in terr:
@@ -245,7 +252,7 @@ class FakeGym:
                                sim=dict(dt=sp.dt, contact_offset=sp.physx.contact_offset,
                                         bounce_threshold=sp.physx.bounce_threshold_velocity,
                                         max_depen_vel=sp.physx.max_depenetration_velocity,
-                                        solver_iters=sp.physx.num_position_iterations))
+                                        solver_iters=sp.physx.num_position_iterations, **sim_extra))
         self._refresh_links()
         return True
 

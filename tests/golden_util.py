@@ -3,12 +3,15 @@ import os
 
 import numpy as np
 
-from grx_b200.config import make_cfg
-from grx_b200.robot import task_tables
+from grx_b200.config import make_cfg, make_full_body_cfg
+from grx_b200.robot import self_collision_pairs, task_tables
 from grx_b200.urdf import builtin_model
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 ENV_FIXTURES = ["plane64_dec1", "plane_gr1t1", "hf_gr1t1", "hf_gr1t2_dr", "tm_gr1t1"]   # tm = mesh_type "trimesh" (BASELINE config #5)
+# the reference classes on the unregistered full-body 32-DOF configuration (gr1t1_config.py:10-307; oracle/ref_harness/driver.py:full_body_cfg)
+FULL_BODY_FIXTURES = ["plane_gr1t1_full", "hf_gr1t2_full"]
+MAX_SELF_CONTACTS = 4
 
 
 def load_fixture(name):
@@ -18,7 +21,7 @@ def load_fixture(name):
 def cfg_from_fixture(fx):
     task, mesh = str(fx["meta/task"]), str(fx["meta/mesh_type"])
     N = fx["const/friction"].shape[0]
-    cfg = make_cfg(task, N, mesh)
+    cfg = make_full_body_cfg(task[:-5], N, mesh) if task.endswith("_full") else make_cfg(task, N, mesh)
     cfg.control.decimation = int(fx["meta/decimation"])
     fl = fx["meta/flags"]
     cfg.noise.add_noise, cfg.domain_rand.push_robots = bool(fl[0]), bool(fl[1])
@@ -51,6 +54,18 @@ def setup_from_fixture(fx):
             verts, _ = heightfield_to_trimesh(hs, cfg.terrain.horizontal_scale, cfg.terrain.vertical_scale, cfg.terrain.slope_treshold)
             terrain["moves"] = moves_from_vertices(verts, hs.shape[0], hs.shape[1], cfg.terrain.horizontal_scale)
     return cfg, model, tables, consts, terrain
+
+
+def phys_oracle(cfg, model, tables, terrain, dtype=np.float32):
+    """The C physics oracle for a fixture's model: full-body trees run with robot self-collision (legged_robot_config.py:121), with the same
+    candidate pairs the product derives."""
+    from oracle.phys import PhysOracle
+    sim = dict(dt=cfg.sim.dt, decimation=cfg.control.decimation, action_scale=cfg.control.action_scale)
+    ctl = dict(tables)
+    if model["nd"] > 10:
+        ctl["self_pairs"] = self_collision_pairs(model, tables)
+        sim["max_self_contacts"] = MAX_SELF_CONTACTS
+    return PhysOracle(model, ctl, terrain, dtype=dtype, sim=sim)
 
 
 def init_state(fx):

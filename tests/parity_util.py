@@ -1,7 +1,7 @@
 """Shared by the GPU parity tests and __graft_entry__.smoke(): build the CUDA env from a golden fixture and compare."""
 import numpy as np
 
-from golden_util import init_state, load_fixture, setup_from_fixture, step_items  # noqa: F401
+from golden_util import init_state, load_fixture, phys_oracle, setup_from_fixture, step_items  # noqa: F401
 
 # post-physics map (the reference's own arithmetic): fp32 on both sides, different exp/sqrt implementations and summation trees
 POST_TOL = dict(rtol=1e-5, atol=3e-6)
@@ -24,11 +24,37 @@ OBS_VEL_COLS = list(range(3, 6)) + list(range(19, 29))          # base angular v
 PRI_VEL_COLS = OBS_VEL_COLS + list(range(39, 42))               # + base linear velocity
 
 
-def make_gpu_env(fx, **kw):
+def vel_cols(nd):
+    """(obs, pri_obs) columns that carry velocities for a robot with nd DOF (obs = cmd 3, ang vel 3, gravity 3, q nd, qd nd, actions nd)."""
+    o = list(range(3, 6)) + list(range(9 + nd, 9 + 2 * nd))
+    return o, o + list(range(9 + 3 * nd, 12 + 3 * nd))
+
+
+assert vel_cols(10) == (OBS_VEL_COLS, PRI_VEL_COLS)
+
+
+def make_gpu_env(fx, generic=False, **kw):
+    """generic=True routes the (lower-limb) model to the generic-topology kernels (GRX_ENV_GENERIC=1, read by grx_env_create); full-body
+    fixtures always run there."""
+    import os
     import torch
     from grx_b200.env import GRXVecEnv
+    old_env = os.environ.get("GRX_ENV_GENERIC")
+    os.environ["GRX_ENV_GENERIC"] = "1" if generic else "0"
+    try:
+        return _make_gpu_env(fx, torch, GRXVecEnv, **kw)
+    finally:
+        if old_env is None:
+            del os.environ["GRX_ENV_GENERIC"]
+        else:
+            os.environ["GRX_ENV_GENERIC"] = old_env
+
+
+def _make_gpu_env(fx, torch, GRXVecEnv, **kw):
     cfg, model, tables, consts, terrain = setup_from_fixture(fx)
     cfg.env.num_envs = len(consts["friction"])
+    if model["nd"] <= 10:
+        kw.setdefault("self_collision", False)   # the lower-limb fixtures' physics (the C oracle) ran without self-contact rows
     params = dict(friction=consts["friction"], restitution=consts["restitution"], motor_strength=consts["motor_strength"],
                   base_inertial=consts["base_inertial"])
     tkw = {}
@@ -43,10 +69,8 @@ def make_gpu_env(fx, **kw):
 
 def make_oracle_env(fx):
     from oracle.env_oracle import EnvOracle
-    from oracle.phys import PhysOracle
     cfg, model, tables, consts, terrain = setup_from_fixture(fx)
-    phys = PhysOracle(model, tables, terrain, dtype=np.float32,
-                      sim=dict(dt=cfg.sim.dt, decimation=cfg.control.decimation, action_scale=cfg.control.action_scale))
+    phys = phys_oracle(cfg, model, tables, terrain)
     env = EnvOracle(cfg, tables, consts, phys, terrain)
     env.load_state(init_state(fx))
     return env

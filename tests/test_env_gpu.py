@@ -9,8 +9,13 @@ import numpy as np
 import pytest
 import torch
 
-from golden_util import ENV_FIXTURES, load_fixture, step_items
-from parity_util import OBS_VEL_COLS, PHYS_FORCE_TOL, PHYS_TOL, PHYS_TORQUE_TOL, PHYS_VEL_TOL, POST_TOL, PRI_VEL_COLS, make_gpu_env
+from golden_util import ENV_FIXTURES, FULL_BODY_FIXTURES, load_fixture, step_items
+from parity_util import PHYS_FORCE_TOL, PHYS_TOL, PHYS_TORQUE_TOL, PHYS_VEL_TOL, POST_TOL, make_gpu_env, vel_cols
+
+# (fixture, generic): every lower-limb fixture on the specialised fused kernel AND on the generic-topology kernels (GRX_ENV_GENERIC=1: same
+# task code from grx_task.cuh, dynamics of grx_phys_generic.cu); the full-body 32-DOF fixtures (always generic)
+ENV_CASES = [(n, False) for n in ENV_FIXTURES] + [(n, True) for n in ENV_FIXTURES] + [(n, True) for n in FULL_BODY_FIXTURES]
+_case_id = lambda c: c[0] + ("-generic" if c[1] else "")
 
 pytestmark = pytest.mark.gpu
 
@@ -30,12 +35,14 @@ def _cmp_state(env, st, tol, msg):
         np.testing.assert_allclose(env.env_origins.cpu().numpy(), st["env_origins"], err_msg=msg, **tol)
 
 
-@pytest.mark.parametrize("name", ENV_FIXTURES)
-def test_post_physics_matches_reference(name):
+@pytest.mark.parametrize("case", ENV_CASES, ids=_case_id)
+def test_post_physics_matches_reference(case):
     """obs / pri_obs / rew / reset / time_out / carried state / extras of the CUDA post-physics path == the unmodified
     reference GR1T1 / GR1T2 classes (golden), given the same physics outputs and the same random draws."""
+    name, generic = case
     fx = load_fixture(name)
-    env = make_gpu_env(fx, sync_extras=True)[0]
+    env = make_gpu_env(fx, generic=generic, sync_extras=True)[0]
+    assert env.generic == generic
     dev = env.device
     n_reset = 0
     for t in range(int(fx["meta/steps"])):
@@ -66,7 +73,7 @@ def test_post_physics_matches_reference(name):
     assert n_reset >= 3
 
 
-def _full_step_compare(name, report):
+def _full_step_compare(name, report, generic=False):
     """Teacher-forced whole fused step (PD torque -> dynamics -> contact -> integrate x decimation -> post-physics) vs the C oracle run
     live on the same golden state, with ACTIVE-SET ATTRIBUTION: both sides export, per env and substep, a hash of the discrete decisions
     of the dynamics (accepted contact spheres, terrain triangle under each, restitution branch, active joint limits).
@@ -77,9 +84,11 @@ def _full_step_compare(name, report):
     from golden_util import init_state
     from parity_util import make_oracle_env
     fx = load_fixture(name)
-    env = make_gpu_env(fx)[0]
+    env = make_gpu_env(fx, generic=generic)[0]
+    assert env.generic == generic
     ora = make_oracle_env(fx)
     sig = env.debug_active_sig(True)
+    obs_vel, pri_vel = vel_cols(env.num_actions)
     dev, N, dec = env.device, env.num_envs, int(fx["meta/decimation"])
     n_flip = 0
     for t in range(int(fx["meta/steps"])):
@@ -104,9 +113,9 @@ def _full_step_compare(name, report):
                 report[nm] = max(report.get(nm, 0.0), float(err.max()))
                 # worst error in units of the stated tolerance (<= 1 passes); all quantities are reported before anything fails
                 bound = tol["atol"] + tol["rtol"] * np.abs(r_)
-                vel_cols = {"obs": OBS_VEL_COLS, "pri_obs": PRI_VEL_COLS, "root_states": list(range(7, 13))}.get(nm)
-                if vel_cols is not None:   # velocity columns of a mixed array carry the velocity tolerance
-                    bound[:, vel_cols] = PHYS_VEL_TOL["atol"] + PHYS_VEL_TOL["rtol"] * np.abs(r_[:, vel_cols])
+                vcols = {"obs": obs_vel, "pri_obs": pri_vel, "root_states": list(range(7, 13))}.get(nm)
+                if vcols is not None:   # velocity columns of a mixed array carry the velocity tolerance
+                    bound[:, vcols] = PHYS_VEL_TOL["atol"] + PHYS_VEL_TOL["rtol"] * np.abs(r_[:, vcols])
                 report["tolfrac/" + nm] = max(report.get("tolfrac/" + nm, 0.0), float((err / bound).max()))
         np.testing.assert_array_equal(reset.cpu().numpy()[same], o_reset.numpy()[same], err_msg=msg)
         for tns in (obs, pri, rew, env.root_states):                                      # the flipped envs still hold sane values
@@ -116,9 +125,10 @@ def _full_step_compare(name, report):
     return report
 
 
-@pytest.mark.parametrize("name", ENV_FIXTURES)
-def test_full_step_matches_oracle(name):
-    rep = _full_step_compare(name, {})
+@pytest.mark.parametrize("case", ENV_CASES, ids=_case_id)
+def test_full_step_matches_oracle(case):
+    name, generic = case
+    rep = _full_step_compare(name, {}, generic)
     print(f"\n{name}: max |CUDA - C oracle| over envs with identical active sets: "
           + ", ".join(f"{k} {v:.2e} ({rep['tolfrac/' + k]:.2f} of tol)" for k, v in rep.items() if "/" not in k and k not in ("flipped_env_steps", "env_steps"))
           + f"; {rep['flipped_env_steps']} of {rep['env_steps']} env-steps took a different contact/limit decision")

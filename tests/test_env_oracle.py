@@ -4,9 +4,8 @@ import numpy as np
 import pytest
 import torch
 
-from golden_util import ENV_FIXTURES, init_state, load_fixture, setup_from_fixture, step_items
+from golden_util import ENV_FIXTURES, FULL_BODY_FIXTURES, init_state, load_fixture, phys_oracle, setup_from_fixture, step_items
 from oracle.env_oracle import EnvOracle
-from oracle.phys import PhysOracle
 
 # torch CPU fp32 on both sides, same op order -> near bit-exact; physics = the same C code
 TOL = dict(rtol=1e-6, atol=1e-6)
@@ -14,14 +13,13 @@ TOL = dict(rtol=1e-6, atol=1e-6)
 
 def _make(fx):
     cfg, model, tables, consts, terrain = setup_from_fixture(fx)
-    phys = PhysOracle(model, tables, terrain, dtype=np.float32,
-                      sim=dict(dt=cfg.sim.dt, decimation=cfg.control.decimation, action_scale=cfg.control.action_scale))
+    phys = phys_oracle(cfg, model, tables, terrain)
     env = EnvOracle(cfg, tables, consts, phys, terrain)
     env.load_state(init_state(fx))
     return env
 
 
-@pytest.mark.parametrize("name", ENV_FIXTURES)
+@pytest.mark.parametrize("name", ENV_FIXTURES + FULL_BODY_FIXTURES)
 def test_full_step_matches_reference(name):
     fx = load_fixture(name)
     env = _make(fx)
@@ -52,7 +50,7 @@ def test_full_step_matches_reference(name):
     assert n_reset >= 3
 
 
-@pytest.mark.parametrize("name", ENV_FIXTURES)
+@pytest.mark.parametrize("name", ENV_FIXTURES + FULL_BODY_FIXTURES)
 def test_post_physics_only_matches_reference(name):
     """Same, but with the reference's own physics outputs injected (isolates LR/FF/G1 arithmetic)."""
     fx = load_fixture(name)
@@ -71,7 +69,7 @@ def test_post_physics_only_matches_reference(name):
         np.testing.assert_array_equal(env.reset_buf.numpy(), out["reset_buf"].astype(bool))
 
 
-@pytest.mark.parametrize("name", ENV_FIXTURES)
+@pytest.mark.parametrize("name", ENV_FIXTURES + FULL_BODY_FIXTURES)
 def test_task_tables_match_reference_constants(name):
     """PD gains / limits / body indices our host code derives == what the reference env derived (LR:176-192, 594-616, G1:18-113)."""
     fx = load_fixture(name)

@@ -26,6 +26,8 @@
 #include "grx_b200.h"
 #include "grx_count.h"
 #include "grx_terrain.cuh"
+#include "grx_task.cuh"
+#include "grx_envg.h"
 
 std::atomic<unsigned long long> g_grx_launches{0};
 extern "C" uint64_t grx_debug_launch_count(void) { return (uint64_t)g_grx_launches.load(); }
@@ -40,7 +42,6 @@ constexpr int WARPS_PER_CTA = 16;   // warps per CTA of the 128-register build a
                                     // the warps of a scheduler share instruction-cache lines).  The launch picks warps_per_cta so that the CTAs fill whole waves
 constexpr int WARPS_PER_CTA_WIDE = 28;   // the 72-register build: 4096 robots on 148 SMs = ONE wave of 28 warps per SM (needs sizeof(WS) <= 8.1 KB)
 constexpr int SIG_STRIDE = 16;               // substep slots per env in the active-set signature export (decimation <= 16)
-constexpr int ACC_RING = 256, ACC_W = 32;   // extras["episode"] accumulators: one 32-float slot per launch, ring of 256
 constexpr unsigned FULL = 0xffffffffu;
 
 // ---- per-env state record (floats; ints stored bit-wise) — 108 floats = 432 B, 16-B aligned
@@ -53,6 +54,12 @@ enum { C_MOTOR = 0, C_BI = 10, C_FRIC = 20, C_REST = 21, CST_F = 24 };
 enum { U_NOISE = 0, U_RESET_DOF = 39, U_RESET_XY = 49, U_RESET_YAW = 51, U_RESET_VEL = 52, U_CMD_TIME = 58,
        U_CMD_RESET = 61, U_PUSH = 64, U_CURRICULUM = 66 };
 static_assert(GRX_RNG_K == 68, "rng layout");
+using Lay10 = LayC<ND>;   // grx_task.cuh: the same offsets as the enums above, as a layout policy of the shared task code
+static_assert(Lay10::dofpos == R_DOFPOS && Lay10::lastlastact == R_LASTLASTACT && Lay10::cmd == R_CMD && Lay10::bho == R_BHO && Lay10::clast == R_CLAST &&
+              Lay10::eplen == R_EPLEN && Lay10::ttype == R_TTYPE && Lay10::sums == R_SUMS && Lay10::rec_f == REC_F, "record layout");
+static_assert(Lay10::c_bi == C_BI && Lay10::c_fric == C_FRIC && Lay10::c_rest == C_REST && Lay10::cst_f == CST_F, "parameter record layout");
+static_assert(Lay10::u_reset_dof == U_RESET_DOF && Lay10::u_cmd_time == U_CMD_TIME && Lay10::u_push == U_PUSH && Lay10::u_curriculum == U_CURRICULUM &&
+              Lay10::rng_k == GRX_RNG_K, "uniform-draw layout");
 
 struct ModelDev {
     float jpos[NB][3], jrot[NB][9], axis[NB][3], mass[NB], com[NB][3], inertia[NB][6];
@@ -71,32 +78,7 @@ struct ModelDev {
 };
 
 
-struct EnvArgs {
-    float *rec;
-    const float *cst;
-    const ModelDev *model;
-    TerrainDev terrain;
-    const float *terrain_origins;  // [t_rows, t_cols, 3]
-    int t_rows, t_cols;
-    int N;
-    const float *actions;
-    const float *U;  // nullable
-    float delay;
-    int push;
-    unsigned long long step_index;
-    float *obs, *pri_obs, *rew, *torques, *contact_forces, *foot_state;
-    float *episode_accum, *episode_accum_next;  // this launch's slot of the extras ring, and the slot to clear for the next launch
-    unsigned char *reset, *time_out;
-    grx_injected_physics inj;
-    float *dbg_M, *dbg_h;  // debug_dynamics
-    int dbg_index;
-    float *rigid_body_states, *dof_state;   // compat exports or nullptr
-    long long *ep_len64;
-    const int *link_body;                   // [nl] per-link tables (global memory; only read when rigid_body_states is exported)
-    const float *link_pos, *link_rot;       // [nl, 3] [nl, 9]
-    unsigned long long *dbg_sig;   // [N, dbg_sig_stride] active-set signature per substep, or nullptr (grx_env_debug_active_sig)
-    int dbg_sig_stride;
-};
+
 
 // per-warp shared-memory workspace
 struct alignas(16) WS {
@@ -178,20 +160,7 @@ __device__ __forceinline__ void sym6v(const float *S, const float *v, float *o) 
     float z = S[4] * v[0] + S[5] * v[1] + S[2] * v[2];
     o[0] = x; o[1] = y; o[2] = z;
 }
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-    return v;
-}
-// torch_utils.py:72-81 quat_rotate_inverse
-__device__ __forceinline__ void quat_rotate_inverse(const float *q, const float *v, float *o) {
-    float qw = q[3];
-    float s = 2.0f * qw * qw - 1.0f;
-    float cx[3]; cross3(q, v, cx);
-    float d = q[0] * v[0] + q[1] * v[1] + q[2] * v[2];
-#pragma unroll
-    for (int k = 0; k < 3; k++) o[k] = v[k] * s - cx[k] * qw * 2.0f + q[k] * d * 2.0f;
-}
+
 
 // ---- TMA bulk copies (1-D) + mbarrier
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -221,28 +190,7 @@ __device__ __forceinline__ void bulk_commit_wait() {
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// ---- Philox4x32-10 (counter-based draws for fast mode)
-__device__ __noinline__ void philox4(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t *out) {
-#pragma unroll
-    for (int r = 0; r < 10; r++) {
-        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
-        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-    }
-    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
-}
-struct Draw {
-    const float *U;  // row of this env or nullptr
-    uint32_t k0, k1, gid, step_lo, step_hi;
-    __device__ __forceinline__ float operator()(int slot) const {
-        if (U) return U[slot];
-        uint32_t r[4];
-        philox4(k0, k1, gid, step_lo, step_hi, (uint32_t)(slot >> 2), r);
-        return (float)(r[slot & 3] >> 8) * (1.0f / 16777216.0f);  // 24-bit mantissa uniform in [0,1), like torch.rand
-    }
-};
+
 
 // ---- terrain query (oracle/phys_impl.h terrain_query)
 // ---- forward kinematics + body velocities + velocity-product accelerations; lane b < NB owns body b and walks its own chain
@@ -730,73 +678,7 @@ __device__ __noinline__ void substep(WS &s, const ModelDev &m, const EnvArgs &A,
     __syncwarp();
 }
 
-__device__ __forceinline__ void resample_commands(WS &s, const grx_task_cfg &cfg, const Draw &draw, int base) {
-    // legged_robot.py:650-677 ((upper - lower) * u + lower; small xy commands zeroed)
-    float cx = (cfg.cmd_range[0][1] - cfg.cmd_range[0][0]) * draw(base) + cfg.cmd_range[0][0];
-    float cy = (cfg.cmd_range[1][1] - cfg.cmd_range[1][0]) * draw(base + 1) + cfg.cmd_range[1][0];
-    const float keep = sqrtf(cx * cx + cy * cy) > 0.1f ? 1.f : 0.f;
-    s.rec[R_CMD] = cx * keep;
-    s.rec[R_CMD + 1] = cy * keep;
-    s.rec[R_CMD + 2] = (cfg.cmd_range[2][1] - cfg.cmd_range[2][0]) * draw(base + 2) + cfg.cmd_range[2][0];
-}
 
-// ---- reset of one env (warp-cooperative): _update_terrain_curriculum LR:799-826, _reset_dofs LR:717-740,
-// _reset_root_states LR:742-784, _resample_commands LR:402, buffer zeroing LR:405-415 + FF:137-146, episode sums -> extras LR:420-424
-__device__ __forceinline__ void reset_env(WS &s, const ModelDev &m, const EnvArgs &A, const grx_task_cfg &cfg, const Draw &draw,
-                                          int lane, float cnorm, bool curriculum_active) {
-    float *rec = s.rec;
-    if (cfg.curriculum && curriculum_active) {
-        if (lane == 0) {
-            const float dx = rec[R_ROOT] - rec[R_ORIGIN], dy = rec[R_ROOT + 1] - rec[R_ORIGIN + 1];
-            const float distance = sqrtf(dx * dx + dy * dy);
-            const bool up = distance > cfg.terrain_env_length / 2.f;
-            const bool down = (distance < cnorm * cfg.max_episode_length_s * 0.5f) && !up;
-            int level = __float_as_int(rec[R_TLEVEL]) + (up ? 1 : 0) - (down ? 1 : 0);
-            if (level >= A.t_rows) level = min((int)floorf(draw(U_CURRICULUM) * (float)A.t_rows), A.t_rows - 1);
-            else level = max(level, 0);
-            rec[R_TLEVEL] = __int_as_float(level);
-            const int type = __float_as_int(rec[R_TTYPE]);
-            const float *org = A.terrain_origins + ((size_t)level * A.t_cols + type) * 3;
-            rec[R_ORIGIN] = org[0]; rec[R_ORIGIN + 1] = org[1]; rec[R_ORIGIN + 2] = org[2];
-        }
-        __syncwarp();
-    }
-    if (lane < ND) {                                                                  // _reset_dofs LR:717-734
-        rec[R_DOFPOS + lane] = cfg.randomize_init_dof_pos ? ((1.5f - 0.5f) * draw(U_RESET_DOF + lane) + 0.5f) * m.q0[lane] : m.q0[lane];
-        rec[R_DOFVEL + lane] = 0.f;
-        rec[R_LASTACT + lane] = 0.f;
-        rec[R_LASTDOFVEL + lane] = 0.f;
-        rec[R_LASTLASTACT + lane] = 0.f;
-    }
-    if (lane == 0) {                                                                  // _reset_root_states LR:742-779
-        float *rt = rec + R_ROOT;
-#pragma unroll
-        for (int k = 0; k < 13; k++) rt[k] = cfg.base_init_state[k];
-#pragma unroll
-        for (int k = 0; k < 3; k++) rt[k] += rec[R_ORIGIN + k];
-        if (cfg.custom_origins) {
-            rt[0] += (1.0f - -1.0f) * draw(U_RESET_XY) + -1.0f;
-            rt[1] += (1.0f - -1.0f) * draw(U_RESET_XY + 1) + -1.0f;
-        }
-        const float yaw = 12.566370614359172f * draw(U_RESET_YAW) + -6.283185307179586f;
-        float sy, cy;
-        sincosf(yaw * 0.5f, &sy, &cy);
-        rt[3] = 0.f; rt[4] = 0.f; rt[5] = sy; rt[6] = cy;
-        if (cfg.randomize_init_base_velocity) {
-#pragma unroll
-            for (int k = 0; k < 6; k++) rt[7 + k] = (0.5f - -0.5f) * draw(U_RESET_VEL + k) + -0.5f;
-        }
-        resample_commands(s, cfg, draw, U_CMD_RESET);                                 // LR:402
-        rec[R_EPLEN] = __int_as_float(0);
-    }
-    if (lane < NF) { rec[R_AIR + lane] = 0.f; rec[R_LAND + lane] = 0.f; rec[R_CLAST + lane] = 0.f; }
-    if (lane < NREW) {                                                                // extras["episode"] sums LR:420-424
-        atomicAdd(A.episode_accum + lane, rec[R_SUMS + lane]);
-        rec[R_SUMS + lane] = 0.f;
-    }
-    if (lane == NREW) atomicAdd(A.episode_accum + NREW, 1.0f);
-    __syncwarp();
-}
 
 // MAXW: warps per CTA the build is compiled for — 16 (128 registers per thread) or 28 (72 registers: one wave for 4096 robots on 148 SMs)
 template <bool PHYS, int MAXW>
@@ -934,263 +816,11 @@ __global__ void __launch_bounds__(MAXW * 32, 1) env_step_kernel(const __grid_con
     }
 
     // =====================================================================================================
-    // post_physics_step (legged_robot.py:269-305, legged_robot_fftai.py:90-133)
+    // post_physics_step (legged_robot.py:269-305, legged_robot_fftai.py:90-133) .. compute_observations: grx_task.cuh
     // =====================================================================================================
-    const float dtp = (float)cfg.decimation * cfg.sim_dt;
-    float *rec = s.rec;
-    int ep_len = __float_as_int(rec[R_EPLEN]) + 1;                                   // LR:282
-    float base_quat[4], v_b[3], w_b[3], g_b[3];
-    const float gvec[3] = {0.f, 0.f, -1.f};
-#pragma unroll
-    for (int k = 0; k < 4; k++) base_quat[k] = rec[R_ROOT + 3 + k];
-    quat_rotate_inverse(base_quat, rec + R_ROOT + 7, v_b);                           // LR:309-311
-    quat_rotate_inverse(base_quat, rec + R_ROOT + 10, w_b);
-    quat_rotate_inverse(base_quat, gvec, g_b);
-    const float root_pos[3] = {rec[R_ROOT], rec[R_ROOT + 1], rec[R_ROOT + 2]};
-    __syncwarp();
-    if (ep_len % cfg.resample_interval == 0) {                                        // LR:317-318
-        if (lane == 0) resample_commands(s, cfg, draw, U_CMD_TIME);
-    }
-    __syncwarp();
-    // ---- _get_heights (legged_robot.py:1235-1274): trunc-to-int grid index, min of 3 samples
-    float *mh = &s.As[0];   // [num_height_points] (the Delassus block is dead after the physics)
-    const int H = cfg.num_height_points;
-    if (cfg.measure_heights && A.terrain.type != 0) {
-        float qz = base_quat[2], qw = base_quat[3];
-        const float nrm = fmaxf(sqrtf(qz * qz + qw * qw), 1e-9f);
-        qz /= nrm; qw /= nrm;
-        for (int k = lane; k < H; k += 32) {
-            const float px_ = cfg.measured_points_x[k / cfg.n_points_y], py_ = cfg.measured_points_y[k % cfg.n_points_y];
-            // quat_apply with q = (0, 0, qz, qw), b = (px, py, 0): t = 2 * cross(xyz, b); out = b + w t + cross(xyz, t)
-            const float tx = -qz * py_ * 2.f, ty = qz * px_ * 2.f;
-            const float ox = px_ + qw * tx + (-qz * ty), oy = py_ + qw * ty + (qz * tx);
-            float fx = ox + root_pos[0], fy = oy + root_pos[1];
-            fx += A.terrain.border; fy += A.terrain.border;
-            long long ix = (long long)(fx / A.terrain.hscale), iy = (long long)(fy / A.terrain.hscale);
-            ix = min(max(ix, 0LL), (long long)A.terrain.rows - 2);
-            iy = min(max(iy, 0LL), (long long)A.terrain.cols - 2);
-            const short *p = A.terrain.h + (size_t)ix * A.terrain.cols + iy;
-            const short h1 = __ldg(p), h2 = __ldg(p + A.terrain.cols), h3 = __ldg(p + 1);
-            const short hm = min(min(h1, h2), h3);
-            mh[k] = (float)hm * A.terrain.vscale;
-        }
-    } else {
-        for (int k = lane; k < H; k += 32) mh[k] = 0.f;
-    }
-    __syncwarp();
-    if (A.push && lane < 2) {                                                         // LR:333-334, 786-797
-        const float mv = cfg.max_push_vel_xy;
-        rec[R_ROOT + 7 + lane] = (mv - -mv) * draw(U_PUSH + lane) + -mv;
-    }
-    // ---- feet bookkeeping (FF:108-133): lane f < NF owns foot f
-    bool contact = false, filt = false, first = false;
-    float air = 0.f, land = 0.f, fh_sum = 0.f, fxy = 0.f, fz = 0.f;
-    {
-        // sum_k (foot_z - mh[k]) for both feet, and sum_k clip(z - target - mh[k]) for the base: lanes stride over k
-        const float fz0 = __shfl_sync(FULL, foot_z, 0), fz1 = __shfl_sync(FULL, foot_z, 1);
-        float s0 = 0.f, s1 = 0.f;
-        for (int k = lane; k < H; k += 32) { s0 += fz0 - mh[k]; s1 += fz1 - mh[k]; }
-        s0 = warp_sum(s0); s1 = warp_sum(s1);
-        fh_sum = lane == 0 ? s0 : s1;
-    }
-    const float feet_h = fh_sum / (float)H;   // valid on lanes 0,1
-    if (lane < NF) {
-        const float *f = s.cf + 3 * m.foot_link[lane];
-        fz = f[2];
-        fxy = sqrtf(f[0] * f[0] + f[1] * f[1]);
-        contact = fz > 1.0f;
-        const bool lastc = rec[R_CLAST + lane] != 0.f;
-        filt = contact || lastc;
-        air = rec[R_AIR + lane];
-        first = (air > 0.f) && filt;
-        air += dtp;
-        land = (rec[R_LAND + lane] + dtp) * (contact ? 1.f : 0.f);
-    }
-    // ---- check_termination (LR:336-353)
-    bool term = false;
-    for (int l = lane; l < m.nl; l += 32) {
-        if ((m.term_mask >> l) & 1ull) {
-            const float *f = s.cf + 3 * l;
-            term |= sqrtf(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]) > 1.0f;
-        }
-    }
-    bool reset = __any_sync(FULL, term);
-    reset |= fabsf(g_b[2]) < 0.33f;
-    const bool time_out = (float)ep_len > cfg.max_episode_length;
-    reset |= time_out;
-
-    // ---- compute_reward (LR:355-375): per-DOF sums by warp reduction, then the 24 terms
-    float sa = 0, sadd = 0, sacc = 0, stor = 0, spose = 0, slpos = 0, slvel = 0, sltor = 0;
-    float q_l = 0, qd_l = 0, tau_l = 0;
-    if (lane < nd) {
-        q_l = rec[R_DOFPOS + lane]; qd_l = rec[R_DOFVEL + lane]; tau_l = s.tau[lane];
-        const float la = last_act_l, lla = rec[R_LASTLASTACT + lane], asc = cfg.action_scale;
-        const float e1 = (la - act_l) * asc, e0 = (lla - la) * asc;
-        sa = fabsf(e1);
-        sadd = fabsf(e1 - e0);
-        sacc = fabsf((qd_l - rec[R_LASTDOFVEL + lane]) / dtp);
-        stor = fabsf(tau_l);
-        spose = fabsf(q_l - m.q0[lane]);
-        float ool = -fminf(q_l - m.soft_lower[lane], 0.f);
-        ool += fmaxf(q_l - m.soft_upper[lane], 0.f);
-        slpos = fabsf(ool);
-        slvel = fminf(fmaxf(fabsf(qd_l) - m.dof_vel_limit[lane] * cfg.soft_dof_vel_limit, 0.f), 1.f);
-        sltor = fmaxf(fabsf(tau_l) - m.dof_effort[lane] * cfg.soft_torque_limit, 0.f);
-    }
-    sa = warp_sum(sa); sadd = warp_sum(sadd); sacc = warp_sum(sacc); stor = warp_sum(stor);
-    spose = warp_sum(spose); slpos = warp_sum(slpos); slvel = warp_sum(slvel); sltor = warp_sum(sltor);
-    // foot quantities broadcast to every lane
-    const float lfh = __shfl_sync(FULL, feet_h, 0), rfh = __shfl_sync(FULL, feet_h, 1);
-    const float air0 = __shfl_sync(FULL, air, 0), air1 = __shfl_sync(FULL, air, 1);
-    const float land0 = __shfl_sync(FULL, land, 0), land1 = __shfl_sync(FULL, land, 1);
-    const float ff0 = __shfl_sync(FULL, ff_acc, 0), ff1 = __shfl_sync(FULL, ff_acc, 1);
-    const float vx0 = __shfl_sync(FULL, fl_acc[0], 0), vy0 = __shfl_sync(FULL, fl_acc[1], 0);
-    const float vx1 = __shfl_sync(FULL, fl_acc[0], 1), vy1 = __shfl_sync(FULL, fl_acc[1], 1);
-    const float fxy0 = __shfl_sync(FULL, fxy, 0), fxy1 = __shfl_sync(FULL, fxy, 1);
-    const float fz0 = __shfl_sync(FULL, fz, 0), fz1 = __shfl_sync(FULL, fz, 1);
-    const unsigned cbal = __ballot_sync(FULL, contact), fbal = __ballot_sync(FULL, first);
-    const float tau_a0 = fabsf(s.tau[m.ankle_dof[0]]), tau_a1 = fabsf(s.tau[m.ankle_dof[1]]);
-    const float cmdx = rec[R_CMD], cmdy = rec[R_CMD + 1], cmdw = rec[R_CMD + 2];
-    const float cnorm = sqrtf(cmdx * cmdx + cmdy * cmdy);
-    const float nz = cnorm > 0.1f ? 1.f : 0.f;
-    float rew = 0.f;
-    if (lane == 0) {
-        float r[NREW];
-        const float bh = rec[R_BHO];   // one step stale on purpose
-        float tg[3];
-        quat_rotate_inverse(torso_q, gvec, tg);
-        const float tgt = cfg.swing_feet_height_target, q4 = tgt / 4.f;
-        const float mid0 = fabsf(air0 - cfg.feet_air_time_target / 2.f), mid1 = fabsf(air1 - cfg.feet_air_time_target / 2.f);
-        const float mn = fminf(lfh, rfh);
-        r[0] = 1.f - expf(cfg.sigma_action_diff * sa);                                                    // action_diff
-        r[1] = 1.f - expf(cfg.sigma_action_diff_diff * sadd);                                             // action_diff_diff
-        r[2] = expf(cfg.sigma_cmd_diff_ang_vel_yaw * fabsf(cmdw - w_b[2]));                               // cmd_diff_ang_vel_yaw
-        r[3] = expf(cfg.sigma_cmd_diff_base_height * (fabsf(bh) * (bh < 0.f ? 1.f : 0.f)));               // cmd_diff_base_height
-        r[4] = expf(cfg.sigma_cmd_diff_base_orient * (fabsf(g_b[0]) + fabsf(g_b[1])));                    // cmd_diff_base_orient
-        r[5] = expf(cfg.sigma_cmd_diff_lin_vel_x * fabsf(cmdx - v_b[0]));                                 // cmd_diff_lin_vel_x
-        r[6] = expf(cfg.sigma_cmd_diff_lin_vel_y * fabsf(cmdy - v_b[1]));                                 // cmd_diff_lin_vel_y
-        r[7] = expf(cfg.sigma_cmd_diff_lin_vel_z * fabsf(0.f - v_b[2]));                                  // cmd_diff_lin_vel_z
-        r[8] = expf(cfg.sigma_cmd_diff_torso_orient * (fabsf(tg[0]) + fabsf(tg[1])));                     // cmd_diff_torso_orient
-        r[9] = 1.f - expf(cfg.sigma_dof_acc_new * sacc);                                                  // dof_acc_new
-        {
-            const float el = tau_a0 * fabsf(lfh) * (lfh > tgt / 2.f ? 1.f : 0.f);
-            const float er = tau_a1 * fabsf(rfh) * (rfh > tgt / 2.f ? 1.f : 0.f);
-            r[10] = 1.f - expf(cfg.sigma_dof_tor_ankle_feet_lift_up * (el + er));                         // dof_tor_ankle_feet_lift_up
-        }
-        r[11] = 1.f - expf(cfg.sigma_dof_tor_new * stor);                                                 // dof_tor_new
-        r[12] = expf(cfg.sigma_feet_air_force * (mid0 * ff0 + mid1 * ff1)) * nz;                          // feet_air_force
-        r[13] = expf(cfg.sigma_feet_air_height * (mid0 * fabsf(lfh - mn - tgt) + mid1 * fabsf(rfh - mn - tgt))) * nz;  // feet_air_height
-        r[14] = (expf(cfg.sigma_feet_air_time * fabsf(air0 - cfg.feet_air_time_target)) * ((fbal & 1u) ? 1.f : 0.f) +
-                 expf(cfg.sigma_feet_air_time * fabsf(air1 - cfg.feet_air_time_target)) * ((fbal & 2u) ? 1.f : 0.f)) * nz;  // feet_air_time
-        {
-            const float e0 = (land0 - cfg.feet_land_time_max) * (land0 > cfg.feet_land_time_max ? 1.f : 0.f);
-            const float e1 = (land1 - cfg.feet_land_time_max) * (land1 > cfg.feet_land_time_max ? 1.f : 0.f);
-            r[15] = ((1.f - expf(cfg.sigma_feet_land_time * e0)) + (1.f - expf(cfg.sigma_feet_land_time * e1))) * nz;  // feet_land_time
-        }
-        {
-            const float cl = fabsf(lfh - q4) * (lfh < q4 ? 1.f : 0.f) / q4, cr = fabsf(rfh - q4) * (rfh < q4 ? 1.f : 0.f) / q4;
-            const float e_ = sqrtf(vx0 * vx0 + vy0 * vy0) * cl + sqrtf(vx1 * vx1 + vy1 * vy1) * cr;
-            r[16] = expf(cfg.sigma_feet_speed_xy_close_to_ground * e_);                                   // feet_speed_xy_close_to_ground
-        }
-        {
-            float el = fxy0 - cfg.feet_stumble_ratio * fabsf(fz0), er = fxy1 - cfg.feet_stumble_ratio * fabsf(fz1);
-            el = el * (el > 0.f ? 1.f : 0.f); er = er * (er > 0.f ? 1.f : 0.f);
-            r[17] = (1.f - expf(cfg.sigma_feet_stumble * el)) + (1.f - expf(cfg.sigma_feet_stumble * er));  // feet_stumble
-        }
-        r[18] = 1.f - expf(cfg.sigma_limits_dof_pos * slpos);                                             // limits_dof_pos
-        r[19] = 1.f - expf(cfg.sigma_limits_dof_tor * sltor);                                             // limits_dof_tor
-        r[20] = 1.f - expf(cfg.sigma_limits_dof_vel * slvel);                                             // limits_dof_vel
-        r[21] = (cbal & 3u) == 0u ? 1.f : 0.f;                                                            // on_the_air
-        r[22] = expf(cfg.sigma_pose_offset * spose);                                                      // pose_offset
-        r[23] = expf(cfg.sigma_stand_still * spose) * (cnorm < 0.1f ? 1.f : 0.f);                         // stand_still
-#pragma unroll
-        for (int k = 0; k < NREW; k++) {
-            const float v = r[k] * cfg.reward_scale[k];
-            rew += v;                   // alphabetical summation order (App. B-15)
-            s.rterm[k] = v;
-        }
-    }
-    __syncwarp();
-    if (lane < NREW) rec[R_SUMS + lane] += s.rterm[lane];                             // LR:366
-    __syncwarp();
-
-    // ---- reset_idx (LR:377-440, FF:137-146), curriculum (LR:799-826)
-    bool contact_for_obs = contact;
-    if (reset) {
-        reset_env(s, m, A, cfg, draw, lane, cnorm, true);
-        ep_len = 0;
-        if (lane < NF) { air = 0.f; land = 0.f; contact_for_obs = false; }
-    }
-    if (lane == 0 && cfg.curriculum) atomicAdd(A.episode_accum + NREW + 1, (float)__float_as_int(rec[R_TLEVEL]));   // LR:427
-    __syncwarp();
-
-    // ---- compute_observations (LR:442-452, FF:148-167, G1:281-313) — after the reset, with stale base quantities (App. B-2)
-    const float hm = cfg.obs_scale_height;
-    const float z_new = rec[R_ROOT + 2];
-    float bsum = 0.f;
-    float *pri = &s.Y[0][0];   // privileged-observation row staging (Y is dead after the physics)
-    const int O = cfg.num_obs;
-    for (int k = lane; k < H; k += 32) {
-        const float off = fminf(fmaxf(z_new - cfg.base_height_target - mh[k], -1.f), 1.f) * hm;
-        bsum += off;
-        pri[O + 8 + k] = off * hm;                                                    // surround_heights_offset * 5 (x25 net, App. B-7)
-    }
-    bsum = warp_sum(bsum);
-    const float bho = bsum / (float)H;
-    float *ob = &s.As[0] + NHMAX;   // unclipped, noise-free obs staging [num_obs]
-    if (lane < 3) {
-        ob[lane] = rec[R_CMD + lane] * 1.0f;                                         // commands * commands_scale (ones, G1:125)
-        ob[3 + lane] = w_b[lane] * cfg.obs_scale_ang_vel;
-        ob[6 + lane] = g_b[lane] * cfg.obs_scale_gravity;
-    }
-    if (lane < nd) {
-        ob[9 + lane] = (rec[R_DOFPOS + lane] - m.q0[lane]) * cfg.obs_scale_dof_pos;
-        ob[9 + nd + lane] = rec[R_DOFVEL + lane] * cfg.obs_scale_dof_vel;
-        ob[9 + 2 * nd + lane] = act_l * cfg.obs_scale_action;
-    }
-    __syncwarp();
-    const float co = cfg.clip_observations;
-    for (int i = lane; i < O; i += 32) {
-        const float v = ob[i];
-        pri[i] = fminf(fmaxf(v, -co), co);                                            // privileged obs embeds the noise-free obs
-        float vn = v;
-        if (cfg.add_noise) vn += (2.f * draw(U_NOISE + i) - 1.f) * cfg.noise_scale_vec[i];   // LR:478-481
-        A.obs[(size_t)e * O + i] = fminf(fmaxf(vn, -co), co);                        // LR:240-241
-    }
-    if (lane < 3) pri[O + lane] = fminf(fmaxf(v_b[lane] * cfg.obs_scale_lin_vel, -co), co);
-    if (lane == 3) pri[O + 3] = fminf(fmaxf(bho * hm, -co), co);
-    if (lane < NF) {
-        pri[O + 4 + lane] = contact_for_obs ? 1.f : 0.f;
-        pri[O + 6 + lane] = fminf(fmaxf(feet_h * hm, -co), co);
-    }
-    __syncwarp();
-    for (int k = lane; k < H; k += 32) pri[O + 8 + k] = fminf(fmaxf(pri[O + 8 + k], -co), co);
-
-    // ---- carry-over (LR:299-300, FF:94-97) and outputs
-    if (lane < nd) {
-        rec[R_LASTACT + lane] = act_l;
-        rec[R_LASTLASTACT + lane] = act_l;                                            // == last_actions (App. B-1)
-        rec[R_LASTDOFVEL + lane] = rec[R_DOFVEL + lane];
-        A.torques[(size_t)e * nd + lane] = s.tau[lane];
-    }
-    if (lane < NF) {
-        rec[R_AIR + lane] = air * (filt ? 0.f : 1.f);
-        rec[R_LAND + lane] = land;
-        rec[R_CLAST + lane] = contact_for_obs ? 1.f : 0.f;
-    }
-    if (lane == 0) {
-        rec[R_BHO] = bho;
-        rec[R_EPLEN] = __int_as_float(ep_len);
-        A.rew[e] = rew;
-        A.reset[e] = reset ? 1 : 0;
-        A.time_out[e] = time_out ? 1 : 0;
-    }
-    if (A.contact_forces != nullptr)
-        for (int i = lane; i < m.nl * 3; i += 32) A.contact_forces[(size_t)e * m.nl * 3 + i] = s.cf[i];
-    if (A.dof_state != nullptr && lane < nd) {   // compat export: interleaved (pos, vel), post-reset like the reference's dof_state after reset_idx
-        reinterpret_cast<float2 *>(A.dof_state)[(size_t)e * nd + lane] = make_float2(rec[R_DOFPOS + lane], rec[R_DOFVEL + lane]);
-    }
-    if (A.ep_len64 != nullptr && lane == 0) A.ep_len64[e] = (long long)ep_len;
+    // scratch: measured heights + the noise-free obs over the Delassus block, the privileged-observation row over Y (both dead after the physics)
+    task_post_physics(s.rec, Lay10(), m, A, cfg, draw, lane, e, act_l, last_act_l, ff_acc, fl_acc, foot_z, torso_q, s.tau, s.cf, &s.As[0],
+                      &s.As[0] + NHMAX, &s.Y[0][0], s.rterm);
     __syncwarp();
     fence_async_smem();   // generic-proxy writes to smem -> visible to the bulk-copy (async) proxy
     __syncwarp();
@@ -1258,7 +888,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) env_reset_kernel(const __g
     draw.gid = (uint32_t)(cfg.env_id_offset + e);
     draw.step_lo = (uint32_t)A.step_index; draw.step_hi = (uint32_t)(A.step_index >> 32);
     const float cx = s.rec[R_CMD], cy = s.rec[R_CMD + 1];
-    reset_env(s, m, A, cfg, draw, lane, sqrtf(cx * cx + cy * cy), curriculum_active != 0);
+    reset_env(s.rec, Lay10(), m, A, cfg, draw, lane, sqrtf(cx * cx + cy * cy), curriculum_active != 0);
     if (lane == 0 && cfg.curriculum) atomicAdd(A.episode_accum + NREW + 1, (float)__float_as_int(s.rec[R_TLEVEL]));
     for (int i = lane; i < REC_F; i += 32) g[i] = s.rec[i];
 }
@@ -1303,6 +933,11 @@ struct grx_env {
     size_t smem = 0;
     int warps_per_cta = WARPS_PER_CTA;   // robots per CTA of env_step_kernel: whole waves of one CTA per SM (env_warps_per_cta)
     uint64_t launches = 0;   // step / reset launches so far; launch k accumulates extras into ring slot k % ACC_RING
+    // Record layout of this env (grx_task.cuh) and, for every model that is not the registered lower-limb tree, the generic-topology kernels'
+    // handle (grx_envg.h; e.g. the full-body 32-DOF GR1T1 / GR1T2 with robot self-collision)
+    LayR lay;
+    int nd = ND;
+    void *g = nullptr;
 };
 
 // One CTA per SM is resident (registers + shared memory); with w warps per CTA a launch of N robots takes ceil(N / (w * SMs)) waves.
@@ -1323,33 +958,40 @@ static void launch_env_step(const grx_env *e, const EnvArgs &A, const grx_task_c
 
 extern "C" int grx_env_create(const grx_model_desc *md, const grx_task_cfg *cfg, int32_t num_envs, int32_t device, grx_env **out) {
     if (!md || !cfg || !out || num_envs <= 0) return grx_set_error(GRX_E_INVALID, "grx_env_create: null argument or num_envs <= 0");
+    // The registered lower-limb tree (floating base + 2 chains of 5) runs on the specialised fused kernel; every other revolute tree (<= 36
+    // bodies / 32 DOF: the full-body GR1T1 / GR1T2) — or every model, with GRX_ENV_GENERIC=1 — on the generic-topology kernels.
     static const int want_parent[NB] = {-1, 0, 1, 2, 3, 4, 0, 6, 7, 8, 9};
-    if (md->nb != NB || md->nd != ND || md->nf != NF || md->nankle != 2 || md->nl > NLMAX || md->ns > NSMAX)
-        return grx_set_error(GRX_E_INVALID, "grx_env_create: this build handles the lower-limb topology only (11 bodies, 10 DOF, 2 feet, <=40 links, <=32 contact spheres)");
-    for (int b = 0; b < NB; b++)
-        if (md->parent[b] != want_parent[b]) return grx_set_error(GRX_E_INVALID, "grx_env_create: unsupported kinematic tree (need floating base + 2 chains of 5)");
-    const int H = cfg->num_height_points;
-    if (cfg->num_actions != ND || cfg->num_obs != 9 + 3 * ND || H > NHMAX || cfg->num_pri_obs != cfg->num_obs + 8 + H ||
-        H != cfg->n_points_x * cfg->n_points_y || cfg->n_points_x > 16 || cfg->n_points_y > 16 || (cfg->num_pri_obs * 4) % 16 != 0)
+    bool generic = md->nb != NB || md->nd != ND || md->nl > NLMAX || md->ns > NSMAX;
+    for (int b = 0; b < NB && !generic; b++) generic = md->parent[b] != want_parent[b];
+    if (const char *gen = getenv("GRX_ENV_GENERIC")) generic = generic || atoi(gen) != 0;
+    if (md->nf != NF || md->nankle != 2 || md->nd < 1 || md->nd > 32)
+        return grx_set_error(GRX_E_INVALID, "grx_env_create: the task needs 2 feet, 2 ankle DOF and 1..32 actuated DOF");
+    const int H = cfg->num_height_points, nd_ = md->nd;
+    if (cfg->num_actions != nd_ || cfg->num_obs != 9 + 3 * nd_ || H > NHMAX || cfg->num_pri_obs != cfg->num_obs + 8 + H ||
+        H != cfg->n_points_x * cfg->n_points_y || cfg->n_points_x > 16 || cfg->n_points_y > 16 || (!generic && (cfg->num_pri_obs * 4) % 16 != 0))
         return grx_set_error(GRX_E_INVALID, "grx_env_create: observation layout mismatch (need obs = 9+3*nd, pri_obs = obs+8+H, H <= 128)");
     if (cfg->decimation < 1 || cfg->solver_iters < 1 || cfg->resample_interval < 1)
         return grx_set_error(GRX_E_INVALID, "grx_env_create: decimation / solver_iters / resample_interval must be >= 1");
     CK(cudaSetDevice(device));
     grx_env *e = new grx_env();
-    e->N = num_envs; e->device = device; e->cfg = *cfg; e->nl = md->nl;
+    e->N = num_envs; e->device = device; e->cfg = *cfg; e->nl = md->nl; e->nd = nd_; e->lay = make_layout(nd_);
+    if (generic) {
+        int rc = grx::envg_create(md, cfg, device, &e->g);
+        if (rc) { delete e; return rc; }
+    }
     ModelDev &m = e->hmodel;
     memset(&m, 0, sizeof(m));
-    for (int b = 0; b < NB; b++) {
+    for (int b = 0; b < NB && !generic; b++) {
         memcpy(m.jpos[b], md->jpos + 3 * b, 12); memcpy(m.jrot[b], md->jrot + 9 * b, 36); memcpy(m.axis[b], md->axis + 3 * b, 12);
         m.mass[b] = md->mass[b]; memcpy(m.com[b], md->com + 3 * b, 12); memcpy(m.inertia[b], md->inertia + 6 * b, 24);
     }
-    for (int j = 0; j < ND; j++) {
+    for (int j = 0; j < ND && !generic; j++) {
         m.dof_lower[j] = md->dof_lower[j]; m.dof_upper[j] = md->dof_upper[j]; m.dof_vel_limit[j] = md->dof_vel_limit[j];
         m.dof_effort[j] = md->dof_effort[j]; m.soft_lower[j] = md->soft_lower[j]; m.soft_upper[j] = md->soft_upper[j];
         m.kp[j] = md->kp[j]; m.kd[j] = md->kd[j]; m.q0[j] = md->default_pos[j];
     }
     m.ns = md->ns; m.nl = md->nl;
-    for (int s = 0; s < md->ns; s++) {
+    for (int s = 0; s < md->ns && !generic; s++) {
         m.sph_body[s] = md->sph_body[s]; m.sph_link[s] = md->sph_link[s]; memcpy(m.sph_pos[s], md->sph_pos + 3 * s, 12);
         m.sph_rad[s] = md->sph_rad[s];
     }
@@ -1371,10 +1013,11 @@ extern "C" int grx_env_create(const grx_model_desc *md, const grx_task_cfg *cfg,
     const size_t N = num_envs;
 #define ALLOC(ptr, count) CK(cudaMalloc((void **)&(ptr), (count))); CK(cudaMemset((ptr), 0, (count)))
     ALLOC(e->dmodel, sizeof(ModelDev));
-    ALLOC(e->rec, N * REC_F * 4); ALLOC(e->cst, N * CST_F * 4);
+    const LayR &L = e->lay;
+    ALLOC(e->rec, N * L.rec_f * 4); ALLOC(e->cst, N * L.cst_f * 4);
     ALLOC(e->obs, N * cfg->num_obs * 4); ALLOC(e->pri_obs, N * cfg->num_pri_obs * 4);
-    ALLOC(e->rew, N * 4); ALLOC(e->torques, N * ND * 4); ALLOC(e->contact_forces, N * md->nl * 3 * 4);
-    ALLOC(e->foot_state, N * NF * 13 * 4); ALLOC(e->episode_accum, ACC_RING * ACC_W * 4); ALLOC(e->actions_stage, N * ND * 4);
+    ALLOC(e->rew, N * 4); ALLOC(e->torques, N * nd_ * 4); ALLOC(e->contact_forces, N * md->nl * 3 * 4);
+    ALLOC(e->foot_state, N * NF * 13 * 4); ALLOC(e->episode_accum, ACC_RING * ACC_W * 4); ALLOC(e->actions_stage, N * nd_ * 4);
     ALLOC(e->reset, N); ALLOC(e->time_out, N);
     ALLOC(e->terrain_origins, 3 * 4);
 #undef ALLOC
@@ -1384,8 +1027,8 @@ extern "C" int grx_env_create(const grx_model_desc *md, const grx_task_cfg *cfg,
     CK(cudaMemcpy(e->d_link_pos, md->link_pos, (size_t)md->nl * 12, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(e->d_link_rot, md->link_rot, (size_t)md->nl * 36, cudaMemcpyHostToDevice));
     {   // identity root quaternion
-        std::vector<float> h(N * REC_F, 0.f);
-        for (size_t i = 0; i < N; i++) h[i * REC_F + R_ROOT + 6] = 1.f;
+        std::vector<float> h(N * L.rec_f, 0.f);
+        for (size_t i = 0; i < N; i++) h[i * L.rec_f + L.root + 6] = 1.f;
         CK(cudaMemcpy(e->rec, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
     }
     e->terrain.type = 0; e->terrain.rows = e->terrain.cols = 0; e->terrain.h = nullptr; e->terrain.mv = nullptr; e->terrain.near_mv = nullptr;
@@ -1413,6 +1056,7 @@ extern "C" int grx_env_create(const grx_model_desc *md, const grx_task_cfg *cfg,
 
 template <bool PHYS>
 static void launch_env_step(const grx_env *e, const EnvArgs &A, const grx_task_cfg &cfg, cudaStream_t st) {
+    if (e->g) { grx::envg_launch_step(e->g, A, cfg, e->lay, PHYS, st); return; }
     const int wpc = e->warps_per_cta, grid = (e->N + wpc - 1) / wpc;
     grx_count_launch();
     if (wpc > WARPS_PER_CTA) env_step_kernel<PHYS, WARPS_PER_CTA_WIDE><<<grid, wpc * 32, env_smem_bytes(wpc), st>>>(A, cfg);
@@ -1426,6 +1070,7 @@ extern "C" int grx_env_destroy(grx_env *e) {
                     e->episode_accum, e->terrain_origins, e->actions_stage, e->reset, e->time_out, e->heights, e->active_sig,
                     e->rigid_body_states, e->dof_state, e->ep_len64, e->d_link_body, e->d_link_pos, e->d_link_rot, e->moves, e->near_moved};
     for (void *p : ptrs) if (p) cudaFree(p);
+    grx::envg_destroy(e->g);
     delete e;
     return GRX_OK;
 }
@@ -1517,15 +1162,17 @@ extern "C" int grx_env_set_params(grx_env *e, const float *friction, const float
         return grx_set_error(GRX_E_INVALID, "grx_env_set_params: null argument");
     CK(cudaSetDevice(e->device));
     const size_t N = e->N;
-    std::vector<float> c(N * CST_F, 0.f), r(N * REC_F);
+    const LayR &L = e->lay;
+    const int nd = e->nd;
+    std::vector<float> c(N * L.cst_f, 0.f), r(N * L.rec_f);
     CK(cudaMemcpy(r.data(), e->rec, r.size() * 4, cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < N; i++) {
-        for (int j = 0; j < ND; j++) c[i * CST_F + C_MOTOR + j] = motor_strength[i * ND + j];
-        for (int j = 0; j < 10; j++) c[i * CST_F + C_BI + j] = base_inertial[i * 10 + j];
-        c[i * CST_F + C_FRIC] = friction[i]; c[i * CST_F + C_REST] = restitution[i];
-        for (int k = 0; k < 3; k++) r[i * REC_F + R_ORIGIN + k] = env_origins[i * 3 + k];
+        for (int j = 0; j < nd; j++) c[i * L.cst_f + L.c_motor + j] = motor_strength[i * nd + j];
+        for (int j = 0; j < 10; j++) c[i * L.cst_f + L.c_bi + j] = base_inertial[i * 10 + j];
+        c[i * L.cst_f + L.c_fric] = friction[i]; c[i * L.cst_f + L.c_rest] = restitution[i];
+        for (int k = 0; k < 3; k++) r[i * L.rec_f + L.origin + k] = env_origins[i * 3 + k];
         int lv = terrain_levels ? terrain_levels[i] : 0, ty = terrain_types ? terrain_types[i] : 0;
-        memcpy(&r[i * REC_F + R_TLEVEL], &lv, 4); memcpy(&r[i * REC_F + R_TTYPE], &ty, 4);
+        memcpy(&r[i * L.rec_f + L.tlevel], &lv, 4); memcpy(&r[i * L.rec_f + L.ttype], &ty, 4);
     }
     CK(cudaMemcpy(e->cst, c.data(), c.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(e->rec, r.data(), r.size() * 4, cudaMemcpyHostToDevice));
@@ -1555,35 +1202,37 @@ extern "C" int grx_env_get_buffer(grx_env *e, const char *name, grx_buffer *b) {
     const int64_t N = e->N;
     const std::string n(name);
     g_buf_device = e->device;
+    const LayR &L = e->lay;
+    const int nd = e->nd;
     struct RecView { const char *name; int off, width, dtype; };
-    static const RecView views[] = {
-        {"root_states", R_ROOT, 13, GRX_F32}, {"dof_pos", R_DOFPOS, ND, GRX_F32}, {"dof_vel", R_DOFVEL, ND, GRX_F32},
-        {"last_dof_vel", R_LASTDOFVEL, ND, GRX_F32}, {"last_actions", R_LASTACT, ND, GRX_F32},
-        {"last_last_actions", R_LASTLASTACT, ND, GRX_F32}, {"commands", R_CMD, 3, GRX_F32},
-        {"base_heights_offset", R_BHO, 1, GRX_F32}, {"feet_air_time", R_AIR, NF, GRX_F32}, {"feet_land_time", R_LAND, NF, GRX_F32},
-        {"feet_contact_last", R_CLAST, NF, GRX_F32}, {"episode_length", R_EPLEN, 1, GRX_I32}, {"terrain_levels", R_TLEVEL, 1, GRX_I32},
-        {"terrain_types", R_TTYPE, 1, GRX_I32}, {"env_origins", R_ORIGIN, 3, GRX_F32}, {"episode_sums", R_SUMS, NREW, GRX_F32},
-        {"records", 0, REC_F, GRX_F32}};
+    const RecView views[] = {
+        {"root_states", L.root, 13, GRX_F32}, {"dof_pos", L.dofpos, nd, GRX_F32}, {"dof_vel", L.dofvel, nd, GRX_F32},
+        {"last_dof_vel", L.lastdofvel, nd, GRX_F32}, {"last_actions", L.lastact, nd, GRX_F32},
+        {"last_last_actions", L.lastlastact, nd, GRX_F32}, {"commands", L.cmd, 3, GRX_F32},
+        {"base_heights_offset", L.bho, 1, GRX_F32}, {"feet_air_time", L.air, NF, GRX_F32}, {"feet_land_time", L.land, NF, GRX_F32},
+        {"feet_contact_last", L.clast, NF, GRX_F32}, {"episode_length", L.eplen, 1, GRX_I32}, {"terrain_levels", L.tlevel, 1, GRX_I32},
+        {"terrain_types", L.ttype, 1, GRX_I32}, {"env_origins", L.origin, 3, GRX_F32}, {"episode_sums", L.sums, NREW, GRX_F32},
+        {"records", 0, L.rec_f, GRX_F32}};
     for (const RecView &v : views)
-        if (n == v.name) { set_buf(b, e->rec + v.off, v.dtype, 2, N, v.width, 1, REC_F, 1, 1); return GRX_OK; }
+        if (n == v.name) { set_buf(b, e->rec + v.off, v.dtype, 2, N, v.width, 1, L.rec_f, 1, 1); return GRX_OK; }
     if (n == "obs") { set_buf(b, e->obs, GRX_F32, 2, N, e->cfg.num_obs, 1, e->cfg.num_obs, 1, 1); return GRX_OK; }
     if (n == "pri_obs") { set_buf(b, e->pri_obs, GRX_F32, 2, N, e->cfg.num_pri_obs, 1, e->cfg.num_pri_obs, 1, 1); return GRX_OK; }
     if (n == "rew") { set_buf(b, e->rew, GRX_F32, 1, N, 1, 1, 1, 1, 1); return GRX_OK; }
     if (n == "reset") { set_buf(b, e->reset, GRX_U8, 1, N, 1, 1, 1, 1, 1); return GRX_OK; }
     if (n == "time_out") { set_buf(b, e->time_out, GRX_U8, 1, N, 1, 1, 1, 1, 1); return GRX_OK; }
-    if (n == "torques") { set_buf(b, e->torques, GRX_F32, 2, N, ND, 1, ND, 1, 1); return GRX_OK; }
+    if (n == "torques") { set_buf(b, e->torques, GRX_F32, 2, N, nd, 1, nd, 1, 1); return GRX_OK; }
     if (n == "contact_forces") { set_buf(b, e->contact_forces, GRX_F32, 3, N, e->nl, 3, (int64_t)e->nl * 3, 3, 1); return GRX_OK; }
     if (n == "foot_state") { set_buf(b, e->foot_state, GRX_F32, 3, N, NF, 13, NF * 13, 13, 1); return GRX_OK; }
     if (n == "episode_accum") { set_buf(b, e->episode_accum, GRX_F32, 2, ACC_RING, ACC_W, 1, ACC_W, 1, 1); return GRX_OK; }
-    if (n == "params") { set_buf(b, e->cst, GRX_F32, 2, N, CST_F, 1, CST_F, 1, 1); return GRX_OK; }
+    if (n == "params") { set_buf(b, e->cst, GRX_F32, 2, N, L.cst_f, 1, L.cst_f, 1, 1); return GRX_OK; }
     if (n == "rigid_body_states" || n == "dof_state" || n == "episode_length_i64") {   // compat exports: allocated + switched on by the first request
         CK(cudaSetDevice(e->device));
         if (n == "rigid_body_states") {
             if (!e->rigid_body_states) { CK(cudaMalloc((void **)&e->rigid_body_states, (size_t)N * e->nl * 13 * 4)); CK(cudaMemset(e->rigid_body_states, 0, (size_t)N * e->nl * 13 * 4)); }
             set_buf(b, e->rigid_body_states, GRX_F32, 3, N, e->nl, 13, (int64_t)e->nl * 13, 13, 1);
         } else if (n == "dof_state") {
-            if (!e->dof_state) { CK(cudaMalloc((void **)&e->dof_state, (size_t)N * ND * 2 * 4)); CK(cudaMemset(e->dof_state, 0, (size_t)N * ND * 2 * 4)); }
-            set_buf(b, e->dof_state, GRX_F32, 3, N, ND, 2, ND * 2, 2, 1);
+            if (!e->dof_state) { CK(cudaMalloc((void **)&e->dof_state, (size_t)N * nd * 2 * 4)); CK(cudaMemset(e->dof_state, 0, (size_t)N * nd * 2 * 4)); }
+            set_buf(b, e->dof_state, GRX_F32, 3, N, nd, 2, nd * 2, 2, 1);
         } else {
             if (!e->ep_len64) { CK(cudaMalloc((void **)&e->ep_len64, (size_t)N * 8)); CK(cudaMemset(e->ep_len64, 0, (size_t)N * 8)); }
             set_buf(b, e->ep_len64, GRX_I64, 1, N, 1, 1, 1, 1, 1);
@@ -1646,9 +1295,14 @@ extern "C" int grx_env_reset_idx(grx_env *e, const int32_t *d_ids, int32_t n, co
     if (!e->params_set) return grx_set_error(GRX_E_STATE, "grx_env_reset_idx: call grx_env_set_params first");
     if (n == 0) return GRX_OK;                                                        // LR:387-388
     EnvArgs A = make_args(e, nullptr, d_uniform, 0.f, 0, step_index);
-    const int grid = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-    grx_count_launch();
-    env_reset_kernel<<<grid, WARPS_PER_CTA * 32, env_smem_bytes(WARPS_PER_CTA), (cudaStream_t)stream>>>(A, e->cfg, d_ids, n, curriculum_active);
+    if (e->g) {
+        int rc = grx::envg_launch_reset(e->g, A, e->cfg, e->lay, d_ids, n, curriculum_active, (cudaStream_t)stream);
+        if (rc) return rc;
+    } else {
+        const int grid = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+        grx_count_launch();
+        env_reset_kernel<<<grid, WARPS_PER_CTA * 32, env_smem_bytes(WARPS_PER_CTA), (cudaStream_t)stream>>>(A, e->cfg, d_ids, n, curriculum_active);
+    }
     CK(cudaGetLastError());
     e->launches++;
     return GRX_OK;
@@ -1661,7 +1315,7 @@ extern "C" int grx_env_step_host(grx_env *e, const float *h_actions, float delay
     if (!e || !h_actions) return grx_set_error(GRX_E_INVALID, "grx_env_step_host: null argument");
     cudaStream_t st = (cudaStream_t)stream;
     const size_t N = e->N;
-    CK(cudaMemcpyAsync(e->actions_stage, h_actions, N * ND * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(e->actions_stage, h_actions, N * e->nd * 4, cudaMemcpyHostToDevice, st));
     int rc = grx_env_step(e, e->actions_stage, nullptr, delay, push, step_index, stream);
     if (rc) return rc;
     if (h_obs) CK(cudaMemcpyAsync(h_obs, e->obs, N * e->cfg.num_obs * 4, cudaMemcpyDeviceToHost, st));
@@ -1692,10 +1346,11 @@ extern "C" int grx_env_debug_dynamics(grx_env *e, int32_t index, float *h_M, flo
     if (!e->params_set) return grx_set_error(GRX_E_STATE, "grx_env_debug_dynamics: call grx_env_set_params first");
     CK(cudaSetDevice(e->device));
     float *tmp_rec = nullptr, *dM = nullptr, *dh = nullptr, *dact = nullptr;
-    CK(cudaMalloc((void **)&tmp_rec, (size_t)e->N * REC_F * 4));
-    CK(cudaMalloc((void **)&dM, NV * NV * 4)); CK(cudaMalloc((void **)&dh, NV * 4));
-    CK(cudaMalloc((void **)&dact, (size_t)e->N * ND * 4)); CK(cudaMemset(dact, 0, (size_t)e->N * ND * 4));
-    CK(cudaMemcpy(tmp_rec, e->rec, (size_t)e->N * REC_F * 4, cudaMemcpyDeviceToDevice));
+    const int nv = e->nd + 6;   // == NV for the lower-limb tree
+    CK(cudaMalloc((void **)&tmp_rec, (size_t)e->N * e->lay.rec_f * 4));
+    CK(cudaMalloc((void **)&dM, nv * nv * 4)); CK(cudaMalloc((void **)&dh, nv * 4));
+    CK(cudaMalloc((void **)&dact, (size_t)e->N * e->nd * 4)); CK(cudaMemset(dact, 0, (size_t)e->N * e->nd * 4));
+    CK(cudaMemcpy(tmp_rec, e->rec, (size_t)e->N * e->lay.rec_f * 4, cudaMemcpyDeviceToDevice));
     EnvArgs A = make_args(e, dact, nullptr, 0.f, 0, 0);
     A.rec = tmp_rec; A.dbg_M = dM; A.dbg_h = dh; A.dbg_index = index;
     grx_task_cfg c = e->cfg;
@@ -1703,8 +1358,8 @@ extern "C" int grx_env_debug_dynamics(grx_env *e, int32_t index, float *h_M, flo
     launch_env_step<true>(e, A, c, nullptr);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
-    CK(cudaMemcpy(h_M, dM, NV * NV * 4, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(h_h, dh, NV * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(h_M, dM, nv * nv * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(h_h, dh, nv * 4, cudaMemcpyDeviceToHost));
     cudaFree(tmp_rec); cudaFree(dM); cudaFree(dh); cudaFree(dact);
     return GRX_OK;
 }
@@ -1715,4 +1370,27 @@ extern "C" int grx_abi_sizes(int32_t *out, int32_t n) {
                           (int32_t)sizeof(grx_injected_physics), (int32_t)sizeof(grx_ppo_cfg)};
     for (int i = 0; i < n && i < 5; i++) out[i] = v[i];
     return 5;
+}
+
+// Robot self-collision (legged_robot_config.py:121 self_collisions = 0 = enabled; create_actor(..., collision_filter = 0), legged_robot.py:1022-1028):
+// candidate sphere pairs of a generic-topology env.  The specialised lower-limb kernel carries no self-contact rows -> GRX_E_INVALID there
+// (create the env with GRX_ENV_GENERIC=1 to run the lower-limb model with self-collision on the generic kernels).
+extern "C" int grx_env_set_self_collision(grx_env *e, const int32_t *pairs, int32_t npairs, int32_t max_self_contacts) {
+    if (!e) return grx_set_error(GRX_E_INVALID, "null env");
+    if (!e->g) return grx_set_error(GRX_E_INVALID, "grx_env_set_self_collision: the specialised lower-limb kernel has no self-contact rows (GRX_ENV_GENERIC=1 selects the generic kernels)");
+    return grx::envg_set_self_collision(e->g, pairs, npairs, max_self_contacts);
+}
+
+// Shape facts of an env a binding needs before it allocates: 0 = uniform draws per env and step (the K of grx_b200/rng_layout.py: 68 for 10 DOF,
+// 156 for 32), 1 = floats per state record, 2 = floats per parameter record, 3 = actuated DOF, 4 = 1 if the generic-topology kernels run it
+extern "C" int64_t grx_env_info(grx_env *e, int32_t what) {
+    if (!e) return -1;
+    switch (what) {
+        case 0: return e->lay.rng_k;
+        case 1: return e->lay.rec_f;
+        case 2: return e->lay.cst_f;
+        case 3: return e->nd;
+        case 4: return e->g ? 1 : 0;
+        default: return -1;
+    }
 }

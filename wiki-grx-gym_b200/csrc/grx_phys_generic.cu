@@ -22,6 +22,8 @@
 #include "grx_b200.h"
 #include "grx_count.h"
 #include "grx_terrain.cuh"
+#include "grx_task.cuh"
+#include "grx_envg.h"
 
 int grx_set_error(int code, const std::string &msg);   // grx_env.cu
 
@@ -53,6 +55,11 @@ struct GModel {   // device copy of the model, in global memory (read through th
     float sph_pos[GS][3], sph_rad[GS];
     int foot_link[4];
     int pair_a[GP], pair_b[GP];
+    // task tables (the env kernel only; grx_task.cuh reads them through the same member names as the lower-limb ModelDev)
+    float soft_lower[GD], soft_upper[GD];
+    unsigned long long term_mask;
+    int ankle_dof[2];
+    int torso_link;
 };
 
 struct GArgs {
@@ -604,11 +611,207 @@ __global__ void __launch_bounds__(GWARPS * 32, 1) physg_step_kernel(const __grid
     for (int i = lane; i < nl * 3; i += 32) A.contact_force[(size_t)e * nl * 3 + i] = s.cf[i];
 }
 
+
+// =========================================================================================================
+// The whole policy step for any topology (the generic counterpart of env_step_kernel in grx_env.cu): clip_actions (legged_robot_fftai.py:171-177)
+// -> decimation x [PD torque -> g_substep] with the foot averages (FF:51-88) -> the task half of grx_task.cuh.  One warp per robot.  The state
+// record stays in global memory during the physics (only root / q / qd / the previous actions are needed) and is staged over the dead
+// constraint Jacobian afterwards: J[0..127] measured heights, J[128..255] noise-free observation, J[256..] the record; Y = privileged row.
+// =========================================================================================================
+template <bool PHYS>
+__global__ void __launch_bounds__(GWARPS * 32, 1) envg_step_kernel(const __grid_constant__ EnvArgs A, const __grid_constant__ grx_task_cfg cfg,
+                                                                   const __grid_constant__ GArgs G, const __grid_constant__ LayR L) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    GWS &s = *reinterpret_cast<GWS *>(smem_raw + (size_t)warp * sizeof(GWS));
+    const GModel &m = *G.m;
+    const int e = blockIdx.x * GWARPS + warp;
+    if (blockIdx.x == 0 && threadIdx.x < ACC_W) A.episode_accum_next[threadIdx.x] = 0.f;   // nobody accumulates into the next slot during this launch
+    if (e >= A.N) return;
+    const int nd = L.nd;
+    float *grec = A.rec + (size_t)e * L.rec_f;
+    const float *gcst = A.cst + (size_t)e * L.cst_f;
+    Draw draw;
+    draw.U = A.U ? A.U + (size_t)e * L.rng_k : nullptr;
+    draw.k0 = (uint32_t)cfg.seed; draw.k1 = (uint32_t)(cfg.seed >> 32);
+    draw.gid = (uint32_t)(cfg.env_id_offset + e);
+    draw.step_lo = (uint32_t)A.step_index; draw.step_hi = (uint32_t)(A.step_index >> 32);
+
+    float act_l = 0.f, last_act_l = 0.f;
+    if (lane < nd) {   // clip_actions
+        act_l = fminf(fmaxf(A.actions[(size_t)e * nd + lane], cfg.clip_actions_min[lane]), cfg.clip_actions_max[lane]);
+        last_act_l = grec[L.lastact + lane];
+    }
+    float ff_acc = 0.f, fl_acc[3] = {0, 0, 0}, foot_z = 0.f;
+    float torso_q[4] = {0, 0, 0, 1};
+    if (PHYS) {
+        if (lane < 13) s.root[lane] = grec[L.root + lane];
+        float motor_l = 1.f;
+        if (lane < nd) { s.q[lane] = grec[L.dofpos + lane]; s.qd[lane] = grec[L.dofvel + lane]; motor_l = gcst[L.c_motor + lane]; }
+        if (lane < 10) s.bin[lane] = gcst[L.c_bi + lane];
+        __syncwarp();
+        const float mu_env = gcst[L.c_fric], rest_env = gcst[L.c_rest];
+        g_kinematics(s, m, lane);
+        for (int deci = 0; deci < cfg.decimation; deci++) {
+            if (lane < nd) {   // _compute_torques (legged_robot.py:691-713) with the action delay of FF:58-61
+                const float a = ((float)deci < A.delay) ? last_act_l : act_l;
+                float t = m.kp[lane] * (a * cfg.action_scale + m.q0[lane] - s.q[lane]) - m.kd[lane] * s.qd[lane];
+                t *= motor_l;
+                const float lim = m.dof_effort[lane];
+                s.tau[lane] = fminf(fmaxf(t, -lim), lim);
+            }
+            __syncwarp();
+            if (A.dbg_M != nullptr) {   // grx_env_debug_dynamics: mass matrix + bias of env dbg_index before the factorisation
+                g_mass_and_bias(s, m, G.cfg.gravity, lane);
+                const int nv = nd + 6;
+                if (e == A.dbg_index) {
+                    for (int i = lane; i < nv * nv; i += 32) A.dbg_M[i] = s.M[i / nv][i % nv];
+                    for (int i = lane; i < nv; i += 32) A.dbg_h[i] = s.h[i];
+                }
+                return;
+            }
+            g_substep(s, m, G, lane, mu_env, rest_env, A.dbg_sig ? A.dbg_sig + (size_t)e * A.dbg_sig_stride + deci : nullptr);
+            g_kinematics(s, m, lane);
+            if (lane < TK_NF) {   // foot statistics of the substep just integrated (FF:79-81)
+                float ls[13];
+                const int l = m.foot_link[lane];
+                g_link_state(s, m, l, ls);
+                const float *f = s.cf + 3 * l;
+                ff_acc += sqrtf(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]);
+#pragma unroll
+                for (int k = 0; k < 3; k++) fl_acc[k] += fabsf(ls[7 + k]);
+                foot_z = ls[2];
+            }
+            __syncwarp();
+        }
+        const float invd = 1.0f / (float)cfg.decimation;
+        ff_acc *= invd;
+#pragma unroll
+        for (int k = 0; k < 3; k++) fl_acc[k] *= invd;
+        {
+            float ls[13];
+            g_link_state(s, m, m.torso_link, ls);
+#pragma unroll
+            for (int k = 0; k < 4; k++) torso_q[k] = ls[3 + k];
+        }
+        if (A.rigid_body_states != nullptr) {   // compat export (refresh_rigid_body_state_tensor, FF:75)
+            for (int l = lane; l < m.nl; l += 32) {
+                float ls[13];
+                g_link_state(s, m, l, ls);
+                float *o = A.rigid_body_states + ((size_t)e * m.nl + l) * 13;
+#pragma unroll
+                for (int k = 0; k < 13; k++) o[k] = ls[k];
+            }
+        }
+        if (A.foot_state != nullptr && lane < TK_NF) {
+            float ls[13];
+            g_link_state(s, m, m.foot_link[lane], ls);
+            float *o = A.foot_state + ((size_t)e * TK_NF + lane) * 13;
+#pragma unroll
+            for (int k = 0; k < 13; k++) o[k] = ls[k];
+        }
+        __syncwarp();
+    } else {   // injected physics outputs (grx_env_post_physics)
+        if (lane < nd) s.tau[lane] = A.inj.torques[(size_t)e * nd + lane];
+        for (int i = lane; i < m.nl * 3; i += 32) s.cf[i] = A.inj.contact_forces[(size_t)e * m.nl * 3 + i];
+        if (lane < TK_NF) {
+            foot_z = A.inj.foot_state[((size_t)e * TK_NF + lane) * 13 + 2];
+            ff_acc = A.inj.avg_foot_force[(size_t)e * TK_NF + lane];
+#pragma unroll
+            for (int k = 0; k < 3; k++) fl_acc[k] = A.inj.avg_foot_linvel[((size_t)e * TK_NF + lane) * 3 + k];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) torso_q[k] = A.inj.torso_quat[(size_t)e * 4 + k];
+    }
+    float *scratch = &s.J[0][0];
+    float *mh = scratch, *ob = scratch + 128, *rec = scratch + 256, *pri = &s.Y[0][0];
+    for (int i = lane; i < L.rec_f; i += 32) rec[i] = grec[i];
+    __syncwarp();
+    if (PHYS) {
+        if (lane < 13) rec[L.root + lane] = s.root[lane];
+        if (lane < nd) { rec[L.dofpos + lane] = s.q[lane]; rec[L.dofvel + lane] = s.qd[lane]; }
+        __syncwarp();
+    }
+    task_post_physics(rec, L, m, A, cfg, draw, lane, e, act_l, last_act_l, ff_acc, fl_acc, foot_z, torso_q, s.tau, s.cf, mh, ob, pri, s.Ad);
+    __syncwarp();
+    for (int i = lane; i < L.rec_f; i += 32) grec[i] = rec[i];
+    float *gpri = A.pri_obs + (size_t)e * cfg.num_pri_obs;
+    for (int i = lane; i < cfg.num_pri_obs; i += 32) gpri[i] = pri[i];
+}
+static_assert(GROWS * GPITCH >= 256 + 16 + 6 * GD + 48 + 8 && GROWS >= TK_NREW, "post-physics scratch fits over J / Ad");
+
+// host-invoked reset_idx (legged_robot.py:377-440 as reached from BaseTask.reset()): one warp per listed env
+__global__ void __launch_bounds__(256) envg_reset_kernel(const __grid_constant__ EnvArgs A, const __grid_constant__ grx_task_cfg cfg,
+                                                         const __grid_constant__ GArgs G, const __grid_constant__ LayR L, const int *ids, int n,
+                                                         int curriculum_active) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *rec = reinterpret_cast<float *>(smem_raw) + (size_t)warp * L.rec_f;
+    const GModel &m = *G.m;
+    if (blockIdx.x == 0 && threadIdx.x < ACC_W) A.episode_accum_next[threadIdx.x] = 0.f;
+    const int w = blockIdx.x * 8 + warp;
+    if (w >= n) return;
+    const int e = ids ? ids[w] : w;
+    if (e < 0 || e >= A.N) return;
+    float *g = A.rec + (size_t)e * L.rec_f;
+    for (int i = lane; i < L.rec_f; i += 32) rec[i] = g[i];
+    __syncwarp();
+    Draw draw;
+    draw.U = A.U ? A.U + (size_t)e * L.rng_k : nullptr;
+    draw.k0 = (uint32_t)cfg.seed ^ 0x5bd1e995u; draw.k1 = (uint32_t)(cfg.seed >> 32);
+    draw.gid = (uint32_t)(cfg.env_id_offset + e);
+    draw.step_lo = (uint32_t)A.step_index; draw.step_hi = (uint32_t)(A.step_index >> 32);
+    const float cx = rec[L.cmd], cy = rec[L.cmd + 1];
+    reset_env(rec, L, m, A, cfg, draw, lane, sqrtf(cx * cx + cy * cy), curriculum_active != 0);
+    if (lane == 0 && cfg.curriculum) atomicAdd(A.episode_accum + TK_NREW + 1, (float)__float_as_int(rec[L.tlevel]));
+    __syncwarp();
+    for (int i = lane; i < L.rec_f; i += 32) g[i] = rec[i];
+}
+
 }  // namespace
 
 // =========================================================================================================
 // Host side
 // =========================================================================================================
+static bool gmodel_fits(const grx_model_desc *md, int npairs) {
+    return !(md->nb < 1 || md->nb > GB || md->nd != md->nb - 1 || md->nd > GD || md->nl > GL || md->ns > GS || md->nf > 4 || npairs > GP);
+}
+static bool build_gmodel(const grx_model_desc *md, const int32_t *self_pairs, int npairs, GModel &m, std::string &err) {
+    memset(&m, 0, sizeof(m));
+    m.nb = md->nb; m.nd = md->nd; m.nl = md->nl; m.ns = md->ns; m.nf = md->nf; m.npairs = npairs;
+    for (int b = 0; b < md->nb; b++) {
+        m.parent[b] = md->parent[b];
+        if (b > 0 && (md->parent[b] < 0 || md->parent[b] >= b)) { err = "bodies must be in depth-first order (parent index < body index)"; return false; }
+        memcpy(m.jpos[b], md->jpos + 3 * b, 12); memcpy(m.jrot[b], md->jrot + 9 * b, 36); memcpy(m.axis[b], md->axis + 3 * b, 12);
+        m.mass[b] = md->mass[b]; memcpy(m.com[b], md->com + 3 * b, 12); memcpy(m.inertia[b], md->inertia + 6 * b, 24);
+        // path base -> b and the ancestor bit mask
+        int chain[GB], n = 0;
+        for (int i = b; i >= 1; i = md->parent[i]) chain[n++] = i;
+        if (n > GDEPTH) { err = "kinematic tree deeper than 12 joints"; return false; }
+        m.depth[b] = n;
+        if (n > m.maxdepth) m.maxdepth = n;
+        for (int k = 0; k < n; k++) { m.path[b][k] = (signed char)chain[n - 1 - k]; m.anc[b] |= 1ull << (chain[k] - 1); }
+    }
+    for (int j = 0; j < md->nd; j++) {
+        m.dof_lower[j] = md->dof_lower[j]; m.dof_upper[j] = md->dof_upper[j]; m.dof_vel_limit[j] = md->dof_vel_limit[j]; m.dof_effort[j] = md->dof_effort[j];
+        m.kp[j] = md->kp[j]; m.kd[j] = md->kd[j]; m.q0[j] = md->default_pos[j];
+    }
+    for (int l = 0; l < md->nl; l++) { m.link_body[l] = md->link_body[l]; memcpy(m.link_pos[l], md->link_pos + 3 * l, 12); memcpy(m.link_rot[l], md->link_rot + 9 * l, 36); }
+    for (int s = 0; s < md->ns; s++) { m.sph_body[s] = md->sph_body[s]; m.sph_link[s] = md->sph_link[s]; memcpy(m.sph_pos[s], md->sph_pos + 3 * s, 12); m.sph_rad[s] = md->sph_rad[s]; }
+    for (int f = 0; f < md->nf; f++) m.foot_link[f] = md->foot_links[f];
+    for (int i = 0; i < npairs; i++) {
+        m.pair_a[i] = self_pairs[2 * i]; m.pair_b[i] = self_pairs[2 * i + 1];
+        if (m.pair_a[i] < 0 || m.pair_a[i] >= md->ns || m.pair_b[i] < 0 || m.pair_b[i] >= md->ns) { err = "self-collision pair out of range"; return false; }
+    }
+    // task tables
+    for (int j = 0; j < md->nd; j++) { m.soft_lower[j] = md->soft_lower ? md->soft_lower[j] : md->dof_lower[j]; m.soft_upper[j] = md->soft_upper ? md->soft_upper[j] : md->dof_upper[j]; }
+    m.term_mask = 0;
+    for (int k = 0; k < md->nterm; k++) m.term_mask |= 1ull << md->term_links[k];
+    m.ankle_dof[0] = md->nankle > 0 ? md->ankle_dofs[0] : 0; m.ankle_dof[1] = md->nankle > 1 ? md->ankle_dofs[1] : 0;
+    m.torso_link = md->torso_link;
+    return true;
+}
+
 struct grx_physg {
     int N = 0, device = 0;
     GModel hm;
@@ -627,35 +830,12 @@ extern "C" int grx_physg_create(const grx_model_desc *md, const int32_t *self_pa
     CK(cudaSetDevice(device));
     grx_physg *p = new grx_physg();
     p->N = num_envs; p->device = device; p->cfg = *cfg;
-    GModel &m = p->hm;
-    memset(&m, 0, sizeof(m));
-    m.nb = md->nb; m.nd = md->nd; m.nl = md->nl; m.ns = md->ns; m.nf = md->nf; m.npairs = npairs;
-    for (int b = 0; b < md->nb; b++) {
-        m.parent[b] = md->parent[b];
-        if (b > 0 && (md->parent[b] < 0 || md->parent[b] >= b)) { delete p; return grx_set_error(GRX_E_INVALID, "grx_physg_create: bodies must be in depth-first order (parent index < body index)"); }
-        memcpy(m.jpos[b], md->jpos + 3 * b, 12); memcpy(m.jrot[b], md->jrot + 9 * b, 36); memcpy(m.axis[b], md->axis + 3 * b, 12);
-        m.mass[b] = md->mass[b]; memcpy(m.com[b], md->com + 3 * b, 12); memcpy(m.inertia[b], md->inertia + 6 * b, 24);
-        // path base -> b and the ancestor bit mask
-        int chain[GB], n = 0;
-        for (int i = b; i >= 1; i = md->parent[i]) chain[n++] = i;
-        if (n > GDEPTH) { delete p; return grx_set_error(GRX_E_INVALID, "grx_physg_create: kinematic tree deeper than 12 joints"); }
-        m.depth[b] = n;
-        if (n > m.maxdepth) m.maxdepth = n;
-        for (int k = 0; k < n; k++) { m.path[b][k] = (signed char)chain[n - 1 - k]; m.anc[b] |= 1ull << (chain[k] - 1); }
-    }
-    for (int j = 0; j < md->nd; j++) {
-        m.dof_lower[j] = md->dof_lower[j]; m.dof_upper[j] = md->dof_upper[j]; m.dof_vel_limit[j] = md->dof_vel_limit[j]; m.dof_effort[j] = md->dof_effort[j];
-        m.kp[j] = md->kp[j]; m.kd[j] = md->kd[j]; m.q0[j] = md->default_pos[j];
-    }
-    for (int l = 0; l < md->nl; l++) { m.link_body[l] = md->link_body[l]; memcpy(m.link_pos[l], md->link_pos + 3 * l, 12); memcpy(m.link_rot[l], md->link_rot + 9 * l, 36); }
-    for (int s = 0; s < md->ns; s++) { m.sph_body[s] = md->sph_body[s]; m.sph_link[s] = md->sph_link[s]; memcpy(m.sph_pos[s], md->sph_pos + 3 * s, 12); m.sph_rad[s] = md->sph_rad[s]; }
-    for (int f = 0; f < md->nf; f++) m.foot_link[f] = md->foot_links[f];
-    for (int i = 0; i < npairs; i++) {
-        m.pair_a[i] = self_pairs[2 * i]; m.pair_b[i] = self_pairs[2 * i + 1];
-        if (m.pair_a[i] < 0 || m.pair_a[i] >= md->ns || m.pair_b[i] < 0 || m.pair_b[i] >= md->ns) { delete p; return grx_set_error(GRX_E_INVALID, "grx_physg_create: self-collision pair out of range"); }
+    {
+        std::string err;
+        if (!build_gmodel(md, self_pairs, npairs, p->hm, err)) { delete p; return grx_set_error(GRX_E_INVALID, "grx_physg_create: " + err); }
     }
     CK(cudaMalloc((void **)&p->dm, sizeof(GModel)));
-    CK(cudaMemcpy(p->dm, &m, sizeof(GModel), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(p->dm, &p->hm, sizeof(GModel), cudaMemcpyHostToDevice));
     memset(&p->terrain, 0, sizeof(p->terrain));
     p->terrain.hscale = 1.f; p->terrain.vscale = 1.f; p->terrain.friction = 1.f;
     CK(cudaFuncSetAttribute(physg_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(GWARPS * sizeof(GWS))));
@@ -706,6 +886,91 @@ extern "C" int grx_physg_step(grx_physg *p, float *d_root, float *d_dof_pos, flo
     A.avg_fl = d_avg_foot_linvel; A.avg_fa = d_avg_foot_angvel; A.sig = reinterpret_cast<unsigned long long *>(d_active_sig);
     grx_count_launch();
     physg_step_kernel<<<(p->N + GWARPS - 1) / GWARPS, GWARPS * 32, GWARPS * sizeof(GWS), (cudaStream_t)stream>>>(A);
+    CK(cudaGetLastError());
+    return GRX_OK;
+}
+
+// =========================================================================================================
+// Generic-topology env (grx_envg.h): what grx_env_* dispatches to for every model that is not the registered lower-limb tree
+// =========================================================================================================
+namespace {
+struct EnvG {
+    int device = 0;
+    GModel hm;
+    GModel *dm = nullptr;
+    grx_physg_cfg pcfg;
+};
+GArgs envg_args(const EnvG *g, const EnvArgs &A, const grx_task_cfg &cfg) {
+    GArgs G;
+    memset(&G, 0, sizeof(G));
+    G.m = g->dm; G.terrain = A.terrain; G.cfg = g->pcfg; G.N = A.N;
+    G.cfg.sim_dt = cfg.sim_dt; G.cfg.gravity = cfg.gravity; G.cfg.contact_offset = cfg.contact_offset; G.cfg.bounce_threshold = cfg.bounce_threshold;
+    G.cfg.max_depen_vel = cfg.max_depen_vel; G.cfg.erp = cfg.erp; G.cfg.solver_iters = cfg.solver_iters; G.cfg.decimation = cfg.decimation;
+    G.cfg.action_scale = cfg.action_scale;
+    return G;
+}
+}  // namespace
+
+int grx::envg_create(const grx_model_desc *md, const grx_task_cfg *cfg, int device, void **out) {
+    if (!gmodel_fits(md, 0) || md->nf != TK_NF || md->nl > GL)
+        return grx_set_error(GRX_E_INVALID, "grx_env_create: model exceeds the generic kernel's limits (<= 36 bodies in depth-first order, 32 DOF, 48 links, 32 contact spheres, 2 feet)");
+    if (md->torso_link < 0 || md->torso_link >= md->nl) return grx_set_error(GRX_E_INVALID, "grx_env_create: torso_link out of range");
+    CK(cudaSetDevice(device));
+    EnvG *g = new EnvG();
+    g->device = device;
+    std::string err;
+    if (!build_gmodel(md, nullptr, 0, g->hm, err)) { delete g; return grx_set_error(GRX_E_INVALID, "grx_env_create: " + err); }
+    memset(&g->pcfg, 0, sizeof(g->pcfg));
+    g->pcfg.max_contacts = GKC; g->pcfg.max_self_contacts = 0;
+    CK(cudaMalloc((void **)&g->dm, sizeof(GModel)));
+    CK(cudaMemcpy(g->dm, &g->hm, sizeof(GModel), cudaMemcpyHostToDevice));
+    CK(cudaFuncSetAttribute(envg_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(GWARPS * sizeof(GWS))));
+    CK(cudaFuncSetAttribute(envg_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(GWARPS * sizeof(GWS))));
+    (void)cfg;
+    *out = g;
+    return GRX_OK;
+}
+
+void grx::envg_destroy(void *h) {
+    EnvG *g = static_cast<EnvG *>(h);
+    if (!g) return;
+    cudaSetDevice(g->device);
+    if (g->dm) cudaFree(g->dm);
+    delete g;
+}
+
+int grx::envg_set_self_collision(void *h, const int32_t *pairs, int32_t npairs, int32_t max_self_contacts) {
+    EnvG *g = static_cast<EnvG *>(h);
+    if (!g || npairs < 0 || npairs > GP || (npairs > 0 && !pairs) || max_self_contacts < 0 || max_self_contacts > GKS)
+        return grx_set_error(GRX_E_INVALID, "grx_env_set_self_collision: bad arguments (<= 64 pairs, <= 4 self-contacts per substep)");
+    for (int i = 0; i < npairs; i++)
+        if (pairs[2 * i] < 0 || pairs[2 * i] >= g->hm.ns || pairs[2 * i + 1] < 0 || pairs[2 * i + 1] >= g->hm.ns)
+            return grx_set_error(GRX_E_INVALID, "grx_env_set_self_collision: pair index out of range");
+    CK(cudaSetDevice(g->device));
+    CK(cudaDeviceSynchronize());
+    for (int i = 0; i < npairs; i++) { g->hm.pair_a[i] = pairs[2 * i]; g->hm.pair_b[i] = pairs[2 * i + 1]; }
+    g->hm.npairs = npairs;
+    g->pcfg.max_self_contacts = npairs > 0 ? max_self_contacts : 0;
+    CK(cudaMemcpy(g->dm, &g->hm, sizeof(GModel), cudaMemcpyHostToDevice));
+    return GRX_OK;
+}
+
+int grx::envg_launch_step(void *h, const EnvArgs &A, const grx_task_cfg &cfg, const LayR &L, bool phys, cudaStream_t st) {
+    EnvG *g = static_cast<EnvG *>(h);
+    const GArgs G = envg_args(g, A, cfg);
+    const int grid = (A.N + GWARPS - 1) / GWARPS;
+    grx_count_launch();
+    if (phys) envg_step_kernel<true><<<grid, GWARPS * 32, GWARPS * sizeof(GWS), st>>>(A, cfg, G, L);
+    else envg_step_kernel<false><<<grid, GWARPS * 32, GWARPS * sizeof(GWS), st>>>(A, cfg, G, L);
+    CK(cudaGetLastError());
+    return GRX_OK;
+}
+
+int grx::envg_launch_reset(void *h, const EnvArgs &A, const grx_task_cfg &cfg, const LayR &L, const int *ids, int n, int curriculum_active, cudaStream_t st) {
+    EnvG *g = static_cast<EnvG *>(h);
+    const GArgs G = envg_args(g, A, cfg);
+    grx_count_launch();
+    envg_reset_kernel<<<(n + 7) / 8, 256, 8 * (size_t)L.rec_f * sizeof(float), st>>>(A, cfg, G, L, ids, n, curriculum_active);
     CK(cudaGetLastError());
     return GRX_OK;
 }

@@ -6,7 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-namespace {
+namespace grx {   // plain data shared across translation units
 
 struct TerrainDev {
     int type, rows, cols;   // 0 plane, 1 heightfield, 2 structured trimesh (heightfield + snapped vertices)
@@ -15,6 +15,11 @@ struct TerrainDev {
     const signed char *mv;          // type 2: [rows, cols, 2] vertex shifts (cells) of the steep-edge snapping (terrain_utils.py:315-328)
     const unsigned char *near_mv;   // type 2: [rows, cols] != 0 where a vertex of the 3 x 3 cells around cell (i, j) is shifted
 };
+
+}  // namespace grx
+
+namespace {
+using grx::TerrainDev;
 
 // splitmix64 finaliser: item hash of the active-set signature (same function in oracle/phys_impl.h)
 __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {

@@ -46,7 +46,7 @@ class TaskCfg(C.Structure):
                  ("cmd_range", (F * 2) * 3), ("max_push_vel_xy", F),
                  ("add_noise", I32), ("randomize_init_dof_pos", I32), ("randomize_init_base_velocity", I32),
                  ("curriculum", I32), ("custom_origins", I32), ("measure_heights", I32),
-                 ("noise_scale_vec", F * 64),
+                 ("noise_scale_vec", F * 128),
                  ("obs_scale_lin_vel", F), ("obs_scale_ang_vel", F), ("obs_scale_gravity", F), ("obs_scale_dof_pos", F),
                  ("obs_scale_dof_vel", F), ("obs_scale_action", F), ("obs_scale_height", F),
                  ("base_init_state", F * 13), ("measured_points_x", F * 16), ("measured_points_y", F * 16),
@@ -97,6 +97,8 @@ def lib():
         _lib.grx_env_accum_slot.restype = C.c_int64
         _lib.grx_env_accum_slot.argtypes = [C.c_void_p]
         _lib.grx_debug_launch_count.restype = C.c_uint64
+        _lib.grx_env_info.restype = C.c_int64
+        _lib.grx_env_info.argtypes = [C.c_void_p, C.c_int32]
         sizes = (I32 * 5)()
         _lib.grx_abi_sizes(sizes, 5)
         want = [C.sizeof(Buffer), C.sizeof(ModelDesc), C.sizeof(TaskCfg), C.sizeof(InjectedPhysics), C.sizeof(PPOCfg)]
@@ -112,7 +114,7 @@ def check(rc):
 
 EXPORTED = ["grx_last_error", "grx_version", "grx_abi_sizes", "grx_debug_launch_count", "grx_env_create", "grx_env_destroy",
             "grx_env_set_terrain_plane", "grx_env_set_terrain_heightfield", "grx_env_set_terrain_trimesh", "grx_env_set_terrain_trimesh_hf", "grx_env_set_params", "grx_env_get_buffer",
-            "grx_env_step", "grx_env_reset_idx", "grx_env_accum_slot", "grx_env_post_physics", "grx_env_step_host", "grx_env_debug_dynamics", "grx_env_debug_active_sig",
+            "grx_env_step", "grx_env_reset_idx", "grx_env_accum_slot", "grx_env_post_physics", "grx_env_step_host", "grx_env_debug_dynamics", "grx_env_debug_active_sig", "grx_env_set_self_collision", "grx_env_info",
             "grx_ppo_create", "grx_ppo_destroy", "grx_ppo_get_buffer", "grx_ppo_act", "grx_ppo_process_env_step",
             "grx_ppo_compute_returns", "grx_ppo_compute_returns_local", "grx_ppo_normalize_advantages",
             "grx_ppo_minibatch_grads", "grx_ppo_minibatch_apply", "grx_ppo_update", "grx_ppo_comm_handle", "grx_ppo_comm_open",

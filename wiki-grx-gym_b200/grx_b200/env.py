@@ -19,7 +19,7 @@ from . import _lib as L
 from . import rng_layout as RL
 from .config import make_cfg
 from . import sharding
-from .robot import nominal_params, sample_domain_rand, task_tables
+from .robot import nominal_params, sample_domain_rand, self_collision_pairs, task_tables
 from .terrain import Terrain
 from .urdf import builtin_model
 
@@ -207,9 +207,12 @@ class GRXVecEnv:
 
     def __init__(self, cfg=None, sim_params=None, physics_engine=None, sim_device="cuda:0", headless=True, *,
                  rank=0, world_size=1, params=None, terrain=None, env_origins=None, terrain_levels=None, terrain_types=None,
-                 parity_rng=False, sync_extras=False, trimesh_builder="device"):
+                 parity_rng=False, sync_extras=False, trimesh_builder="device", self_collision=None,
+                 max_self_contacts=4):
         """cfg: grx_b200.config.make_cfg(...) or the reference's GR1T1LowerLimbCfg()/GR1T2LowerLimbCfg() object
         (cfg.env.num_envs is the GLOBAL env count; this rank simulates the contiguous block rank*N/W..(rank+1)*N/W).
+        A full-body cfg (grx_b200.config.make_full_body_cfg: 32 DOF, num_obs 105) runs on the generic-topology kernels behind the same
+        calls, with robot self-collision unless cfg.asset.self_collisions != 0 or self_collision=False.
         params / terrain / env_origins...: override the sampled per-env parameters (tests)."""
         if cfg is None:
             cfg = make_cfg("GR1T1")
@@ -281,6 +284,13 @@ class GRXVecEnv:
         self._h = C.c_void_p()
         dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         L.check(self.lib.grx_env_create(C.byref(self._md), C.byref(self._tc), N, dev_index, C.byref(self._h)))
+        self.generic = bool(self.lib.grx_env_info(self._h, 4))        # generic-topology kernels (full-body 32-DOF trees; GRX_ENV_GENERIC=1)
+        self.rng_k = int(self.lib.grx_env_info(self._h, 0))          # width of a parity-mode uniform-draw row (rng_layout.layout(nd).K)
+        self.self_collision_pairs = np.zeros((0, 2), np.int32)
+        if self.generic and self_collision is not False and int(getattr(cfg.asset, "self_collisions", 0)) == 0:   # legged_robot_config.py:121: 0 = enabled
+            self.self_collision_pairs = self_collision_pairs(self.model, self.tables)
+            pr = np.ascontiguousarray(self.self_collision_pairs, np.int32)
+            L.check(self.lib.grx_env_set_self_collision(self._h, pr.ctypes.data_as(L.PI), len(pr), int(max_self_contacts)))
         tc = cfg.terrain
         if rough:
             hs = np.ascontiguousarray(terrain["heights"], np.int16)

@@ -24,3 +24,30 @@ CMD_RESET = 61
 PUSH = 64
 CURRICULUM = 66
 K = 68  # padded to a multiple of 4 floats
+
+
+class Layout:
+    """The same slot table for a robot with `nd` actuated DOF (observation width 9 + 3 nd): K = 28 + 4 nd, a multiple of 4 floats.
+    nd = 10 reproduces the module-level constants of the registered lower-limb tasks."""
+
+    def __init__(self, nd):
+        self.nd = nd
+        self.NOISE, self.NOISE_N = 0, 9 + 3 * nd
+        self.RESET_DOF = self.NOISE_N
+        self.RESET_XY = self.RESET_DOF + nd
+        self.RESET_YAW = self.RESET_XY + 2
+        self.RESET_VEL = self.RESET_YAW + 1
+        self.CMD_TIME = self.RESET_VEL + 6
+        self.CMD_RESET = self.CMD_TIME + 3
+        self.PUSH = self.CMD_RESET + 3
+        self.CURRICULUM = self.PUSH + 2
+        self.K = self.CURRICULUM + 2
+
+
+def layout(nd):
+    return Layout(nd)
+
+
+_L10 = Layout(10)
+assert (_L10.NOISE_N, _L10.RESET_DOF, _L10.RESET_XY, _L10.RESET_YAW, _L10.RESET_VEL, _L10.CMD_TIME, _L10.CMD_RESET, _L10.PUSH, _L10.CURRICULUM, _L10.K) == \
+    (NOISE_N, RESET_DOF, RESET_XY, RESET_YAW, RESET_VEL, CMD_TIME, CMD_RESET, PUSH, CURRICULUM, K)
