@@ -67,17 +67,20 @@ def measured_traffic():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe).  The sampler is started BEFORE the warm-up
+    iterations (nvidia-smi needs a few hundred ms to deliver its first line; the warm-up runs the same workload) and every line is stamped;
+    the median is taken over the samples that fall inside [begin(), end()], or — when the timed region is shorter than a few sampling
+    periods — over all samples under load since the start of the warm-up (`window` says which)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t0, self.t1 = index, [], None, None, None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -85,15 +88,25 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.monotonic(), [x.strip() for x in line.split(",")]))
+
+    def begin(self):
+        self.t0 = time.monotonic()
+
+    def end(self):
+        self.t1 = time.monotonic()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
+        inside = [r for ts, r in self.rows if self.t0 is not None and self.t0 <= ts <= (self.t1 or ts) + 0.06]
+        window = "timed region"
+        if len(inside) < 3:
+            inside, window = [r for _, r in self.rows], "warm-up + timed region (timed region shorter than 3 sampling periods)"
         sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        for r in inside:
             try:
                 sm.append(float(r[1])); mx = float(r[2])
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
@@ -102,7 +115,7 @@ class ClockSampler:
             except Exception:
                 pass
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -277,23 +290,25 @@ def run_ours(args):
         b.record()
         ev_pairs.append((a, b))
         return out
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
     for _ in range(args.warmup):
         runner.learn(1)
     barrier()
     env.step = timed_step
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     phase = []
     barrier()
     launches0 = int(lib.grx_debug_launch_count())
+    clocks.begin()
     e0.record()
     for _ in range(args.steps):
         runner.learn(1)
         phase.append(dict(runner.last_timing))
     e1.record()
     barrier()
+    clocks.end()
     launches = int(lib.grx_debug_launch_count()) - launches0
     ms = e0.elapsed_time(e1)
     clk = clocks.stop() if rank == 0 else None

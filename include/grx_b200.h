@@ -247,6 +247,41 @@ int grx_physg_step(grx_physg *p, float *d_root, float *d_dof_pos, float *d_dof_v
                    const float *d_restitution, float *d_torques, float *d_link_state, float *d_contact_force, float *d_avg_foot_force,
                    float *d_avg_foot_linvel, float *d_avg_foot_angvel, uint64_t *d_active_sig, void *stream);
 
+/* ---- terrain generation on the device ------------------------------------------------------------------------------------------
+ * Replaces the array work of Terrain.__init__ (legged_gym/utils/terrain.py:38-164) and the isaacgym/terrain_utils.py generators it calls
+ * (pyramid_sloped_terrain :74-106, random_uniform_terrain :17-51, pyramid_stairs_terrain :195-227, discrete_obstacles_terrain :109-149): ONE
+ * kernel writes the whole int16 sample grid (border included) into d_samples [tot_rows, tot_cols], a second one reduces the per-tile origin
+ * heights (terrain.py:159-163).  The numpy random stream stays on the host — grx_b200/terrain.py draws it in the reference's call order and
+ * fills the descriptors — so the grid is bit-identical to the reference's for the same np.random.seed (tests/test_terrain_gpu.py). */
+typedef struct {
+    int32_t kind;         /* 0 smooth pyramid slope, 1 rough slope (slope + random-uniform roughness), 2 pyramid stairs, 3 discrete obstacles */
+    int32_t slope_peak;   /* kinds 0/1: int(slope * (horizontal_scale / vertical_scale) * (width / 2)), terrain_utils.py:93 */
+    int32_t plat_lo, plat_hi; /* kinds 0/1: the platform corner sample x1 == y1 (:100-101); kind 3: the cleared centre platform [lo, hi) (:145-148) */
+    int32_t coarse_index; /* kind 1: which [coarse_nx, coarse_ny] block of h_coarse holds this tile's np.random.choice levels (:37) */
+    int32_t step_width, step_height, num_rings; /* kind 2: samples per step, height units per step (signed), number of rings painted (:213-226) */
+    int32_t rect_index, num_rects; /* kind 3: range of h_rects rows (start_i, start_j, width, length, height) in draw order (:135-143) */
+} grx_terrain_tile;
+typedef struct {
+    int32_t num_rows, num_cols;       /* tiles: difficulty rows x type columns (terrain.py:51) */
+    int32_t tile_width, tile_length;  /* samples per tile (width_per_env_pixels, length_per_env_pixels; must be equal, as upstream) */
+    int32_t border;                   /* samples */
+    int32_t coarse_nx, coarse_ny;     /* size of one coarse level block (random_uniform_terrain's down-sampled grid) */
+    int32_t origin_x1, origin_x2, origin_y1, origin_y2; /* centre window of the origin height (terrain.py:159-162) */
+} grx_terrain_grid;
+/* h_tiles [num_rows * num_cols] (row-major: tile (i, j) at i * num_cols + j); h_rx [tile_length] / h_ry [tile_width] = the float64 ramps of
+ * pyramid_sloped_terrain; h_up_i0 / h_up_fx [tile_length], h_up_j0 / h_up_fy [tile_width] = cell index and fraction of every fine sample in the
+ * coarse grid (interp2d, :41-48); h_coarse [num_coarse, coarse_nx, coarse_ny] int16; h_rects [num_rects_total, 5] int32.
+ * d_samples: DEVICE int16 [num_rows * tile_length + 2 border, num_cols * tile_width + 2 border]; h_origin_zmax: host int32 [num_rows * num_cols]
+ * (max sample of each tile's centre window; origin z = that * vertical_scale) or NULL.  Synchronises the stream before returning. */
+int grx_terrain_generate(const grx_terrain_grid *grid, const grx_terrain_tile *h_tiles, const double *h_rx, const double *h_ry,
+                         const int32_t *h_up_i0, const double *h_up_fx, const int32_t *h_up_j0, const double *h_up_fy,
+                         const int16_t *h_coarse, int32_t num_coarse, const int32_t *h_rects, int32_t num_rects_total,
+                         int16_t *d_samples, int32_t *h_origin_zmax, int32_t device, void *stream);
+/* grx_env_set_terrain_heightfield / _trimesh_hf with the samples already ON THE DEVICE (e.g. written by grx_terrain_generate): device-to-device
+ * copy, no host round trip.  slope_threshold < 0: heightfield; >= 0: structured trimesh built on the device (as grx_env_set_terrain_trimesh_hf). */
+int grx_env_set_terrain_device(grx_env *env, const int16_t *d_samples, int32_t rows, int32_t cols, float hscale, float vscale, float border,
+                               float slope_threshold, float friction, float restitution);
+
 /* ---- PPO ---------------------------------------------------------------------------------------------------- */
 typedef struct {
     int32_t num_envs, num_steps;             /* N (local), T */

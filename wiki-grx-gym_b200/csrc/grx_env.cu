@@ -74,6 +74,7 @@ struct ModelDev {
     int torso_body;
     unsigned long long term_mask;
     int ankle_dof[2];
+    __device__ __forceinline__ float ankle_torque(const float *tau, int side) const { return fabsf(tau[ankle_dof[side]]); }   // one ankle DOF per leg
     int jrot_nonident;   // bit b set: joint frame rotation of body b is not the identity (GR1T1 / GR1T2: none) -> one 3x3 product per joint saved
 };
 
@@ -964,8 +965,9 @@ extern "C" int grx_env_create(const grx_model_desc *md, const grx_task_cfg *cfg,
     bool generic = md->nb != NB || md->nd != ND || md->nl > NLMAX || md->ns > NSMAX;
     for (int b = 0; b < NB && !generic; b++) generic = md->parent[b] != want_parent[b];
     if (const char *gen = getenv("GRX_ENV_GENERIC")) generic = generic || atoi(gen) != 0;
-    if (md->nf != NF || md->nankle != 2 || md->nd < 1 || md->nd > 32)
-        return grx_set_error(GRX_E_INVALID, "grx_env_create: the task needs 2 feet, 2 ankle DOF and 1..32 actuated DOF");
+    generic = generic || md->nankle != 2;
+    if (md->nf != NF || (md->nankle != 2 && md->nankle != 4) || md->nd < 1 || md->nd > 32)
+        return grx_set_error(GRX_E_INVALID, "grx_env_create: the task needs 2 feet, 2 or 4 ankle DOF and 1..32 actuated DOF");
     const int H = cfg->num_height_points, nd_ = md->nd;
     if (cfg->num_actions != nd_ || cfg->num_obs != 9 + 3 * nd_ || H > NHMAX || cfg->num_pri_obs != cfg->num_obs + 8 + H ||
         H != cfg->n_points_x * cfg->n_points_y || cfg->n_points_x > 16 || cfg->n_points_y > 16 || (!generic && (cfg->num_pri_obs * 4) % 16 != 0))
@@ -1092,6 +1094,24 @@ extern "C" int grx_env_set_terrain_heightfield(grx_env *e, const int16_t *sample
     e->terrain.mv = nullptr; e->terrain.near_mv = nullptr;
     e->terrain.hscale = hscale; e->terrain.vscale = vscale; e->terrain.border = border;
     e->terrain.friction = friction; e->terrain.restitution = restitution;
+    return GRX_OK;
+}
+
+static int finish_trimesh(grx_env *e, const signed char *h_moves, double thr, int32_t rows, int32_t cols);
+
+// The same with the samples already on the device (written by grx_terrain_generate): no host round trip
+extern "C" int grx_env_set_terrain_device(grx_env *e, const int16_t *d_samples, int32_t rows, int32_t cols, float hscale, float vscale, float border,
+                                          float slope_threshold, float friction, float restitution) {
+    if (!e || !d_samples || rows < 2 || cols < 2) return grx_set_error(GRX_E_INVALID, "grx_env_set_terrain_device: bad arguments");
+    CK(cudaSetDevice(e->device));
+    if (e->heights) { cudaFree(e->heights); e->heights = nullptr; }
+    CK(cudaMalloc((void **)&e->heights, (size_t)rows * cols * 2));
+    CK(cudaMemcpy(e->heights, d_samples, (size_t)rows * cols * 2, cudaMemcpyDeviceToDevice));
+    e->terrain.type = 1; e->terrain.rows = rows; e->terrain.cols = cols; e->terrain.h = e->heights;
+    e->terrain.mv = nullptr; e->terrain.near_mv = nullptr;
+    e->terrain.hscale = hscale; e->terrain.vscale = vscale; e->terrain.border = border;
+    e->terrain.friction = friction; e->terrain.restitution = restitution;
+    if (slope_threshold >= 0.f) return finish_trimesh(e, nullptr, (double)slope_threshold * (double)hscale / (double)vscale, rows, cols);
     return GRX_OK;
 }
 

@@ -58,8 +58,14 @@ struct GModel {   // device copy of the model, in global memory (read through th
     // task tables (the env kernel only; grx_task.cuh reads them through the same member names as the lower-limb ModelDev)
     float soft_lower[GD], soft_upper[GD];
     unsigned long long term_mask;
-    int ankle_dof[2];
+    int ankle_dof[4], nankle;   // first half: left leg, second half: right leg (gr1t1.py:406-411); full body: ankle pitch + roll per leg
     int torso_link;
+    __device__ __forceinline__ float ankle_torque(const float *tau, int side) const {
+        const int half = nankle >> 1;
+        float s = 0.f;
+        for (int k = side * half; k < (side + 1) * half; k++) s += fabsf(tau[ankle_dof[k]]);
+        return s;
+    }
 };
 
 struct GArgs {
@@ -807,7 +813,8 @@ static bool build_gmodel(const grx_model_desc *md, const int32_t *self_pairs, in
     for (int j = 0; j < md->nd; j++) { m.soft_lower[j] = md->soft_lower ? md->soft_lower[j] : md->dof_lower[j]; m.soft_upper[j] = md->soft_upper ? md->soft_upper[j] : md->dof_upper[j]; }
     m.term_mask = 0;
     for (int k = 0; k < md->nterm; k++) m.term_mask |= 1ull << md->term_links[k];
-    m.ankle_dof[0] = md->nankle > 0 ? md->ankle_dofs[0] : 0; m.ankle_dof[1] = md->nankle > 1 ? md->ankle_dofs[1] : 0;
+    m.nankle = md->nankle;
+    for (int k = 0; k < md->nankle && k < 4; k++) m.ankle_dof[k] = md->ankle_dofs[k];
     m.torso_link = md->torso_link;
     return true;
 }
@@ -915,6 +922,7 @@ int grx::envg_create(const grx_model_desc *md, const grx_task_cfg *cfg, int devi
     if (!gmodel_fits(md, 0) || md->nf != TK_NF || md->nl > GL)
         return grx_set_error(GRX_E_INVALID, "grx_env_create: model exceeds the generic kernel's limits (<= 36 bodies in depth-first order, 32 DOF, 48 links, 32 contact spheres, 2 feet)");
     if (md->torso_link < 0 || md->torso_link >= md->nl) return grx_set_error(GRX_E_INVALID, "grx_env_create: torso_link out of range");
+    if (md->nankle != 2 && md->nankle != 4) return grx_set_error(GRX_E_INVALID, "grx_env_create: need 2 or 4 ankle DOF (left half, right half)");
     CK(cudaSetDevice(device));
     EnvG *g = new EnvG();
     g->device = device;

@@ -316,7 +316,7 @@ __device__ __forceinline__ void task_post_physics(float *rec, const LAY &L, cons
     const float fxy0 = __shfl_sync(TK_FULL, fxy, 0), fxy1 = __shfl_sync(TK_FULL, fxy, 1);
     const float fz0 = __shfl_sync(TK_FULL, fz, 0), fz1 = __shfl_sync(TK_FULL, fz, 1);
     const unsigned cbal = __ballot_sync(TK_FULL, contact), fbal = __ballot_sync(TK_FULL, first);
-    const float tau_a0 = fabsf(tau[m.ankle_dof[0]]), tau_a1 = fabsf(tau[m.ankle_dof[1]]);
+    const float tau_a0 = m.ankle_torque(tau, 0), tau_a1 = m.ankle_torque(tau, 1);   // sum |tau| over the left / right half of the ankle DOF (gr1t1.py:406-411)
     const float cmdx = rec[L.cmd], cmdy = rec[L.cmd + 1], cmdw = rec[L.cmd + 2];
     const float cnorm = sqrtf(cmdx * cmdx + cmdy * cmdy);
     const float nz = cnorm > 0.1f ? 1.f : 0.f;

@@ -79,6 +79,16 @@ class PhysGCfg(C.Structure):
                 ("solver_iters", I32), ("decimation", I32), ("action_scale", F), ("max_contacts", I32), ("max_self_contacts", I32)]
 
 
+class TerrainTile(C.Structure):
+    _fields_ = [("kind", I32), ("slope_peak", I32), ("plat_lo", I32), ("plat_hi", I32), ("coarse_index", I32), ("step_width", I32), ("step_height", I32),
+                ("num_rings", I32), ("rect_index", I32), ("num_rects", I32)]
+
+
+class TerrainGrid(C.Structure):
+    _fields_ = [("num_rows", I32), ("num_cols", I32), ("tile_width", I32), ("tile_length", I32), ("border", I32), ("coarse_nx", I32), ("coarse_ny", I32),
+                ("origin_x1", I32), ("origin_x2", I32), ("origin_y1", I32), ("origin_y2", I32)]
+
+
 class GrxError(RuntimeError):
     pass
 
@@ -114,7 +124,7 @@ def check(rc):
 
 EXPORTED = ["grx_last_error", "grx_version", "grx_abi_sizes", "grx_debug_launch_count", "grx_env_create", "grx_env_destroy",
             "grx_env_set_terrain_plane", "grx_env_set_terrain_heightfield", "grx_env_set_terrain_trimesh", "grx_env_set_terrain_trimesh_hf", "grx_env_set_params", "grx_env_get_buffer",
-            "grx_env_step", "grx_env_reset_idx", "grx_env_accum_slot", "grx_env_post_physics", "grx_env_step_host", "grx_env_debug_dynamics", "grx_env_debug_active_sig", "grx_env_set_self_collision", "grx_env_info",
+            "grx_env_step", "grx_env_reset_idx", "grx_env_accum_slot", "grx_env_post_physics", "grx_env_step_host", "grx_env_debug_dynamics", "grx_env_debug_active_sig", "grx_env_set_self_collision", "grx_env_info", "grx_terrain_generate", "grx_env_set_terrain_device",
             "grx_ppo_create", "grx_ppo_destroy", "grx_ppo_get_buffer", "grx_ppo_act", "grx_ppo_process_env_step",
             "grx_ppo_compute_returns", "grx_ppo_compute_returns_local", "grx_ppo_normalize_advantages",
             "grx_ppo_minibatch_grads", "grx_ppo_minibatch_apply", "grx_ppo_update", "grx_ppo_comm_handle", "grx_ppo_comm_open",

@@ -20,7 +20,7 @@ from . import rng_layout as RL
 from .config import make_cfg
 from . import sharding
 from .robot import nominal_params, sample_domain_rand, self_collision_pairs, task_tables
-from .terrain import Terrain
+from .terrain import DeviceTerrain, Terrain
 from .urdf import builtin_model
 
 REWARD_NAMES = list(L._SIGMAS[:21]) + ["on_the_air", "pose_offset", "stand_still"]   # alphabetical
@@ -208,7 +208,7 @@ class GRXVecEnv:
     def __init__(self, cfg=None, sim_params=None, physics_engine=None, sim_device="cuda:0", headless=True, *,
                  rank=0, world_size=1, params=None, terrain=None, env_origins=None, terrain_levels=None, terrain_types=None,
                  parity_rng=False, sync_extras=False, trimesh_builder="device", self_collision=None,
-                 max_self_contacts=4):
+                 max_self_contacts=4, terrain_generator="device"):
         """cfg: grx_b200.config.make_cfg(...) or the reference's GR1T1LowerLimbCfg()/GR1T2LowerLimbCfg() object
         (cfg.env.num_envs is the GLOBAL env count; this rank simulates the contiguous block rank*N/W..(rank+1)*N/W).
         A full-body cfg (grx_b200.config.make_full_body_cfg: 32 DOF, num_obs 105) runs on the generic-topology kernels behind the same
@@ -251,9 +251,15 @@ class GRXVecEnv:
         if rough and terrain is None:
             st = np.random.get_state()
             np.random.seed(seed)
-            self.terrain = Terrain(cfg.terrain, n_total)
+            # "device": the grid is generated by one kernel (grx_terrain_generate) and handed to the env without a host round trip;
+            # "host": the numpy generator (bit-identical arrays, tests/test_terrain_gpu.py)
+            if terrain_generator == "device":
+                self.terrain = DeviceTerrain(cfg.terrain, n_total, self.device)
+                terrain = dict(heights=None, heights_dev=self.terrain.heights_dev, terrain_origins=self.terrain.env_origins)
+            else:
+                self.terrain = Terrain(cfg.terrain, n_total)
+                terrain = dict(heights=self.terrain.heightsamples, terrain_origins=self.terrain.env_origins)
             np.random.set_state(st)
-            terrain = dict(heights=self.terrain.heightsamples, terrain_origins=self.terrain.env_origins)
         # ---- env origins (legged_robot.py:1163-1195), keyed by GLOBAL env index
         g = np.random.default_rng(seed + 7919)
         if rough:
@@ -292,8 +298,14 @@ class GRXVecEnv:
             pr = np.ascontiguousarray(self.self_collision_pairs, np.int32)
             L.check(self.lib.grx_env_set_self_collision(self._h, pr.ctypes.data_as(L.PI), len(pr), int(max_self_contacts)))
         tc = cfg.terrain
-        if rough:
-            hs = np.ascontiguousarray(terrain["heights"], np.int16)
+        if rough and terrain.get("heights_dev") is not None and (tc.mesh_type != "trimesh" or trimesh_builder == "device"):
+            hd = terrain["heights_dev"]
+            L.check(self.lib.grx_env_set_terrain_device(self._h, C.c_void_p(hd.data_ptr()), hd.shape[0], hd.shape[1], C.c_float(tc.horizontal_scale),
+                                                        C.c_float(tc.vertical_scale), C.c_float(tc.border_size),
+                                                        C.c_float(tc.slope_treshold if tc.mesh_type == "trimesh" else -1.0),
+                                                        C.c_float(tc.static_friction), C.c_float(tc.restitution)))
+        elif rough:
+            hs = np.ascontiguousarray(terrain["heights"] if terrain.get("heights") is not None else terrain["heights_dev"].cpu().numpy(), np.int16)
             scal = (C.c_float(tc.horizontal_scale), C.c_float(tc.vertical_scale), C.c_float(tc.border_size),
                     C.c_float(tc.static_friction), C.c_float(tc.restitution))
             if tc.mesh_type == "trimesh":                                               # legged_robot.py:903-924 (_create_trimesh)

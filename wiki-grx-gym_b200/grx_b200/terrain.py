@@ -157,6 +157,126 @@ class Terrain:
         self.env_origins[i, j] = [(i + 0.5) * self.env_length, (j + 0.5) * self.env_width, z]
 
 
+class DeviceTerrain(Terrain):
+    """The same terrain generated ON THE GPU (csrc/grx_terrain_gen.cu, C ABI grx_terrain_generate): the numpy random stream is drawn here in
+    the reference's call order (a few thousand draws, so the grid stays bit-identical to the reference's for the same np.random.seed), the
+    array arithmetic runs as one kernel over the grid.  ``heights_dev`` is the int16 CUDA tensor [tot_rows, tot_cols] (handed to the env
+    without a host round trip, grx_env_set_terrain_device); ``heightsamples`` / ``height_field_raw`` are fetched lazily for callers that
+    want the numpy array.  ``env_origins`` as in the host class.  No CPU fallback: raises without the CUDA library / a CUDA device."""
+
+    def __init__(self, cfg, num_robots, device="cuda:0"):
+        import ctypes as C
+        import torch
+        from . import _lib as L
+        self.cfg, self.num_robots, self.type = cfg, num_robots, cfg.mesh_type
+        if self.type in ("none", "plane"):
+            return
+        if not torch.cuda.is_available():
+            raise L.GrxError("DeviceTerrain needs a CUDA device (no CPU fallback; grx_b200.terrain.Terrain is the host generator)")
+        self.env_length, self.env_width = cfg.terrain_length, cfg.terrain_width
+        self.proportions = [np.sum(cfg.terrain_proportions[:i + 1]) for i in range(len(cfg.terrain_proportions))]
+        self.env_origins = np.zeros((cfg.num_rows, cfg.num_cols, 3))
+        W = self.width_per_env_pixels = int(self.env_width / cfg.horizontal_scale)
+        Lp = self.length_per_env_pixels = int(self.env_length / cfg.horizontal_scale)
+        self.border = int(cfg.border_size / cfg.horizontal_scale)
+        self.tot_cols = int(cfg.num_cols * W) + 2 * self.border
+        self.tot_rows = int(cfg.num_rows * Lp) + 2 * self.border
+        hs, vs = cfg.horizontal_scale, cfg.vertical_scale
+        tiles = (L.TerrainTile * (cfg.num_rows * cfg.num_cols))()
+        coarse, rects = [], []
+        nx, ny = int(W * hs / 0.2), int(W * hs / 0.2)                                    # random_uniform_terrain(downsampled_scale=0.2)
+
+        def draw(choice, difficulty, i, j):
+            """_make_tile (terrain.py:109-145) reduced to its random draws + integer parameters."""
+            d = tiles[i * cfg.num_cols + j]
+            slope, step_h, obst_h = difficulty * 0.4, 0.05 + 0.18 * difficulty, 0.05 + difficulty * 0.2
+            p = self.proportions
+            if choice < p[1]:
+                s = -slope if choice < p[0] / 2 else slope
+                d.kind = 0 if choice < p[0] else 1
+                d.slope_peak = int(s * (hs / vs) * (W / 2))
+                d.plat_lo = W // 2 - int(3.0 / hs / 2)
+                if d.kind == 1:
+                    lo, hi, st = int(-0.05 / vs), int(0.05 / vs), int(0.005 / vs)
+                    d.coarse_index = len(coarse)
+                    coarse.append(np.random.choice(np.arange(lo, hi + st, st), (nx, ny)))
+            elif choice < p[3]:
+                d.kind = 2
+                sw, sh = int(0.31 / hs), int((-step_h if choice < p[2] else step_h) / vs)
+                plat = int(3.0 / hs)
+                x0, x1, n = 0, W, 0
+                while (x1 - x0) > plat:
+                    x0, x1, n = x0 + sw, x1 - sw, n + 1
+                d.step_width, d.step_height, d.num_rings = sw, sh, n
+            elif choice < p[4]:
+                d.kind = 3
+                mh = int(obst_h / vs)
+                lo, hi, plat = int(1.0 / hs), int(2.0 / hs), int(3.0 / hs)
+                heights, sizes = [-mh, -mh // 2, mh // 2, mh], range(lo, hi, 4)
+                d.rect_index, d.num_rects = len(rects), 20
+                for _ in range(20):
+                    w = np.random.choice(sizes)
+                    l = np.random.choice(sizes)
+                    si = np.random.choice(range(0, W - w, 4))
+                    sj = np.random.choice(range(0, W - l, 4))
+                    rects.append((si, sj, w, l, np.random.choice(heights)))
+                d.plat_lo, d.plat_hi = (W - plat) // 2, (W + plat) // 2
+            else:
+                raise NotImplementedError("tile types beyond terrain_proportions[4] (stepping stones / gap / pit)")
+
+        if cfg.curriculum:                                                                # terrain.py:85-92 (column-major visiting order)
+            for j in range(cfg.num_cols):
+                for i in range(cfg.num_rows):
+                    draw(j / cfg.num_cols + 0.001, i / cfg.num_rows, i, j)
+        elif getattr(cfg, "selected", False):
+            raise NotImplementedError("terrain.selected is broken upstream (terrain.py:94-107) and not supported")
+        else:                                                                             # terrain.py:75-83
+            for k in range(cfg.num_rows * cfg.num_cols):
+                i, j = np.unravel_index(k, (cfg.num_rows, cfg.num_cols))
+                choice = np.random.uniform(0, 1)
+                difficulty = np.random.choice([0.5, 0.75, 0.9])
+                draw(choice, difficulty, i, j)
+        # float64 tables of pyramid_sloped_terrain / interp2d, exactly as the host generator computes them
+        cx = int(W / 2)
+        ramp = np.ascontiguousarray((cx - np.abs(cx - np.arange(W))) / cx, np.float64)
+        g = np.linspace(0, W * hs, W) / (W * hs) * (nx - 1)
+        i0 = np.clip(np.floor(g).astype(int), 0, nx - 2)
+        fx = np.ascontiguousarray(g - i0, np.float64)
+        i0 = np.ascontiguousarray(i0, np.int32)
+        co = np.ascontiguousarray(np.stack(coarse) if coarse else np.zeros((0, nx, ny)), np.int16)
+        rc = np.ascontiguousarray(np.array(rects, np.int32).reshape(-1, 5))
+        grid = L.TerrainGrid(cfg.num_rows, cfg.num_cols, W, Lp, self.border, nx, ny,
+                             int((self.env_length / 2.0 - 1) / hs), int((self.env_length / 2.0 + 1) / hs),
+                             int((self.env_width / 2.0 - 1) / hs), int((self.env_width / 2.0 + 1) / hs))
+        dev = torch.device(device)
+        self.heights_dev = torch.empty(self.tot_rows, self.tot_cols, dtype=torch.int16, device=dev)
+        zmax = np.zeros(cfg.num_rows * cfg.num_cols, np.int32)
+        PD = C.POINTER(C.c_double)
+        L.check(L.lib().grx_terrain_generate(C.byref(grid), tiles, ramp.ctypes.data_as(PD), ramp.ctypes.data_as(PD), i0.ctypes.data_as(L.PI),
+                                             fx.ctypes.data_as(PD), i0.ctypes.data_as(L.PI), fx.ctypes.data_as(PD),
+                                             co.ctypes.data_as(C.POINTER(C.c_int16)), len(co), rc.ctypes.data_as(L.PI), len(rc),
+                                             C.c_void_p(self.heights_dev.data_ptr()), zmax.ctypes.data_as(L.PI),
+                                             dev.index if dev.index is not None else torch.cuda.current_device(),
+                                             C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        for i in range(cfg.num_rows):
+            for j in range(cfg.num_cols):
+                z = np.int16(zmax[i * cfg.num_cols + j]) * vs
+                self.env_origins[i, j] = [(i + 0.5) * self.env_length, (j + 0.5) * self.env_width, z]
+        self._host = None
+
+    @property
+    def heightsamples(self):
+        if self._host is None:
+            self._host = self.heights_dev.cpu().numpy()
+        return self._host
+
+    height_field_raw = heightsamples
+
+    @property
+    def vertices(self):
+        raise AttributeError("DeviceTerrain builds the structured trimesh on the device (grx_env_set_terrain_device); use heightfield_to_trimesh(heightsamples, ...) for the host mesh")
+
+
 def heightfield_to_trimesh(hf, horizontal_scale, vertical_scale, slope_threshold=None):
     """Structured 2-triangles-per-cell mesh with the reference's steep-edge vertex snapping
     (terrain_utils.py:286-350).  Returns (vertices float32 [R*C, 3], triangles uint32 [2(R-1)(C-1), 3])."""
