@@ -5,12 +5,14 @@ One "step" = one PPO iteration of the reference's OnPolicyRunner.learn loop (on_
 64 policy steps x `envs/GPU` robots (policy forward -> fused env kernel -> storage), GAE, and the 8x25-minibatch PPO
 update.  value = N_total * 64 * K / (time of K iterations) == the reference's Perf/total_fps (on_policy_runner.py:235).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2|3|5]    # our arm (CUDA, no fallback)
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2|3|5|6]  # our arm (CUDA, no fallback)
   python bench.py --impl reference ...                                    # the reference's CPU path: the oracle port on host cores
 
 --config selects the BASELINE.json workload (default 2 == the configuration the metric is quoted on; #4 is #2 at --gpus 8):
   2: GR1T1, rough heightfield + curriculum, 4096 envs/GPU        3: GR1T2 + full domain randomisation, heightfield, 8192 envs/GPU
   5: GR1T1, trimesh terrain + curriculum, 4096 envs/GPU (quoted at --gpus 4)
+  6: (not a BASELINE config) the unregistered FULL-BODY 32-DOF GR1T1 with robot self-collision on the generic-topology
+     kernels, heightfield + curriculum, 4096 envs/GPU
 """
 import argparse
 import json
@@ -31,10 +33,29 @@ CONFIGS = {2: dict(robot="GR1T1", mesh="heightfield", envs=4096,
            3: dict(robot="GR1T2", mesh="heightfield", envs=8192,
                    name="#3 GR1T2 lower-limb, rough heightfield 10x20 tiles + curriculum + full domain randomisation"),
            5: dict(robot="GR1T1", mesh="trimesh", envs=4096,
-                   name="#5 GR1T1 lower-limb, trimesh terrain (slope_treshold 0.75) + curriculum + domain randomisation")}
+                   name="#5 GR1T1 lower-limb, trimesh terrain (slope_treshold 0.75) + curriculum + domain randomisation"),
+           6: dict(robot="GR1T1", mesh="heightfield", envs=4096, full_body=True,
+                   name="(extra, SURVEY 8-f3) GR1T1 FULL-BODY 32-DOF (gr1t1_config.py GR1T1Cfg, obs 105 / pri 234 / 32 actions) + robot self-collision, "
+                        "generic-topology kernels, rough heightfield 10x20 tiles + curriculum + domain randomisation")}
 METRIC, UNIT = "env-steps/sec GR1T1 rough-terrain PPO @4096 envs/GPU", "env-steps/s"
 ENV_BYTES_PER_STEP = 1794          # 530 B read + 1264 B written per env-step by the fused env kernel
 FWD_FLOP = 870144                  # per transition, actor + critic forward
+
+
+def shapes(c):
+    """(D, O, P, algorithmic env bytes per env-step, forward FLOP per transition) of config c: SURVEY.md §8(d)'s formulas — reads
+    4(7D + 17) + 4R + 86, writes 4(18 + 6D + O + P) + 4R + 28 with R = 24 reward terms; FLOP = 2 x MACs of actor O-512-256-128-D + critic P-512-256-128-1."""
+    D = 32 if CONFIGS[c].get("full_body") else 10
+    O, P, R = 9 + 3 * D, 9 + 3 * D + 8 + 121, 24
+    env_bytes = 4 * (7 * D + 17) + 4 * R + 86 + 4 * (18 + 6 * D + O + P) + 4 * R + 28
+    flop = 2 * (O * 512 + 512 * 256 + 256 * 128 + 128 * D + P * 512 + 512 * 256 + 256 * 128 + 128 * 1)
+    return D, O, P, env_bytes, flop
+
+
+def make_task_cfg(c, n):
+    from grx_b200.config import make_cfg, make_full_body_cfg
+    cf = CONFIGS[c]
+    return (make_full_body_cfg if cf.get("full_body") else make_cfg)(cf["robot"], n, cf["mesh"])
 
 
 def workload(c):
@@ -44,7 +65,11 @@ def workload(c):
 
 
 def metric_for(c):
-    return METRIC if c == 2 else f"env-steps/sec {CONFIGS[c]['robot']} {CONFIGS[c]['mesh']} PPO @{CONFIGS[c]['envs']} envs/GPU (BASELINE config #{c})"
+    if c == 2:
+        return METRIC
+    if CONFIGS[c].get("full_body"):
+        return f"env-steps/sec {CONFIGS[c]['robot']} full-body 32-DOF {CONFIGS[c]['mesh']} PPO @{CONFIGS[c]['envs']} envs/GPU (extra config #{c}, SURVEY 8-f3)"
+    return f"env-steps/sec {CONFIGS[c]['robot']} {CONFIGS[c]['mesh']} PPO @{CONFIGS[c]['envs']} envs/GPU (BASELINE config #{c})"
 
 
 def peaks():
@@ -145,9 +170,11 @@ class CpuArm:
         torch.set_num_threads(self.cores)
         os.environ.setdefault("OMP_NUM_THREADS", str(self.cores))
         N = self.N = cf["envs"]
-        cfg = make_cfg(cf["robot"], N, cf["mesh"])
-        model = builtin_model(cf["robot"])
+        cfg = make_task_cfg(config, N)
+        model = builtin_model(cf["robot"] + ("_full" if cf.get("full_body") else ""))
         tables = task_tables(model, cfg)
+        D, O, P, _, _ = shapes(config)
+        self.K = RL.layout(D).K
         np.random.seed(1)
         ter = Terrain(cfg.terrain, N)
         rng = np.random.default_rng(1)
@@ -162,23 +189,27 @@ class CpuArm:
             from oracle.phys import moves_from_vertices
             verts, _ = heightfield_to_trimesh(ter.heightsamples, cfg.terrain.horizontal_scale, cfg.terrain.vertical_scale, cfg.terrain.slope_treshold)
             terrain["moves"] = moves_from_vertices(verts, ter.heightsamples.shape[0], ter.heightsamples.shape[1], cfg.terrain.horizontal_scale)
-        phys = PhysOracle(model, tables, terrain, dtype=np.float32)
+        ctl, sim = dict(tables), {}
+        if cf.get("full_body"):   # robot self-collision, the same candidate pairs and contact budget as the CUDA arm
+            from grx_b200.robot import self_collision_pairs
+            ctl["self_pairs"], sim = self_collision_pairs(model, tables), dict(max_self_contacts=4)
+        phys = PhysOracle(model, ctl, terrain, dtype=np.float32, sim=sim)
         self.env = EnvOracle(cfg, tables, consts, phys, terrain)
         self.env.root_states[:, :3] = torch.as_tensor(consts["env_origins"], dtype=torch.float32) + torch.tensor([0.0, 0.0, 0.95])
         self.env.dof_pos[:] = self.env.default_dof_pos
         self.g = torch.Generator().manual_seed(0)
         tc = make_train_cfg()["algorithm"]
         torch.manual_seed(1)
-        self.ac = pa.ActorCritic(39, 168, 10)
+        self.ac = pa.ActorCritic(O, P, D)
         self.ppo = pa.PPOStep(self.ac, clip=tc["clip_param"], vcoef=tc["value_loss_coef"], ecoef=tc["entropy_coef"], lr=tc["learning_rate"],
                               lr_min=tc["learning_rate_min"], lr_max=tc["learning_rate_max"], desired_kl=tc["desired_kl"], max_grad_norm=tc["max_grad_norm"])
         self.M = N * T_STEPS // 25
         self.n_pol, self.n_mb = T_STEPS // self.SUB, 200 // self.SUB
-        self.obs = torch.zeros(N, 39)
-        self.cobs = torch.zeros(N, 168)
-        self.store = dict(obs=torch.zeros(self.n_pol, N, 39), critic_obs=torch.zeros(self.n_pol, N, 168), actions=torch.zeros(self.n_pol, N, 10),
-                          values=torch.zeros(self.n_pol, N, 1), lp=torch.zeros(self.n_pol, N, 1), mu=torch.zeros(self.n_pol, N, 10),
-                          sigma=torch.zeros(self.n_pol, N, 10), rew=torch.zeros(self.n_pol, N, 1))
+        self.obs = torch.zeros(N, O)
+        self.cobs = torch.zeros(N, P)
+        self.store = dict(obs=torch.zeros(self.n_pol, N, O), critic_obs=torch.zeros(self.n_pol, N, P), actions=torch.zeros(self.n_pol, N, D),
+                          values=torch.zeros(self.n_pol, N, 1), lp=torch.zeros(self.n_pol, N, 1), mu=torch.zeros(self.n_pol, N, D),
+                          sigma=torch.zeros(self.n_pol, N, D), rew=torch.zeros(self.n_pol, N, 1))
 
     def step(self):
         """8 policy steps x N robots + 25 minibatches of N*64/25 rows; returns seconds."""
@@ -187,7 +218,7 @@ class CpuArm:
         for s in range(self.n_pol):
             a, v, lp, mu, sg = self.ppo.act(self.obs, self.cobs)
             st["obs"][s], st["critic_obs"][s], st["actions"][s], st["values"][s], st["lp"][s, :, 0], st["mu"][s], st["sigma"][s] = self.obs, self.cobs, a, v, lp, mu, sg
-            obs, pri, rew, reset, _ = self.env.step(a, torch.rand(self.N, self.RL.K, generator=self.g), 5.0)
+            obs, pri, rew, reset, _ = self.env.step(a, torch.rand(self.N, self.K, generator=self.g), 5.0)
             self.obs, self.cobs = obs.clone(), pri.clone()
             st["rew"][s, :, 0] = rew
         # minibatch rows: the sample's own transitions, re-drawn with replacement up to the full minibatch size M
@@ -266,7 +297,7 @@ def run_ours(args):
     n_per_gpu = cf["envs"]
     n_total = n_per_gpu * world
     torch.manual_seed(1)
-    cfg = make_cfg(cf["robot"], n_total, cf["mesh"])
+    cfg = make_task_cfg(args.config, n_total)
     env = GRXVecEnv(cfg, sim_device=dev, rank=rank, world_size=world)
     tc = make_train_cfg()
     runner = OnPolicyRunner(env, tc, log_dir=None, device=dev, world_size=world)
@@ -389,20 +420,22 @@ def run_ours(args):
     if rank == 0:
         hbm, tf_sus, which = peaks()
         traffic = measured_traffic()
-        env_achieved = ENV_BYTES_PER_STEP * env.num_envs / (env_ms * 1e-3) / 1e9
+        _, _, _, env_bytes, fwd_flop = shapes(args.config)
+        env_kernel = "envg_step_kernel (generic topology)" if CONFIGS[args.config].get("full_body") else "env_step_kernel"
+        env_achieved = env_bytes * env.num_envs / (env_ms * 1e-3) / 1e9
         # dense layers of the update only: 8 epochs x (forward + backward ~ 3 x forward) per transition; the rollout's policy forward runs
         # in the collection phase and is in neither the numerator nor the time
-        ppo_flops = env.num_envs * T_STEPS * FWD_FLOP * 8 * 3
+        ppo_flops = env.num_envs * T_STEPS * fwd_flop * 8 * 3
         ppo_tf = ppo_flops / (learn * 1e-3) / 1e12
         dominant_env = coll >= learn
-        roof_env = {"kernel": "env_step_kernel", "bound": "hbm", "achieved": env_achieved, "peak": hbm, "unit": "GB/s", "frac": env_achieved / hbm,
-                    "traffic": traffic.get("env_step_kernel"), "peak_source": which, "us_per_launch": env_ms * 1e3,
-                    "note": f"1794 algorithmic B per env-step x {env.num_envs} robots per launch.  The kernel is issue/latency-bound "
+        roof_env = {"kernel": env_kernel, "bound": "hbm", "achieved": env_achieved, "peak": hbm, "unit": "GB/s", "frac": env_achieved / hbm,
+                    "traffic": traffic.get("env_step_kernel") if env_kernel == "env_step_kernel" else None, "peak_source": which, "us_per_launch": env_ms * 1e3,
+                    "note": f"{env_bytes} algorithmic B per env-step x {env.num_envs} robots per launch.  The kernel is issue/latency-bound "
                             "(10 substeps of articulated dynamics per launch, ~55k warp-instructions per env-step), not bandwidth-bound: the "
                             "HBM fraction is reported because BASELINE asks for it, the meaningful figure is us_per_launch"}
         roof_ppo = {"kernel": "PPO update dense layers (tcgen05 kind::tf32, 200 minibatches)", "bound": "tensor", "achieved": ppo_tf, "peak": tf_sus,
-                    "unit": "TFLOP/s", "frac": ppo_tf / tf_sus, "traffic": traffic.get("ppo_update_per_minibatch"), "peak_source": which,
-                    "note": "numerator = 8 epochs x 3 x 870144 FLOP per transition (update only); time = compute_returns + update (learn_ms). "
+                    "unit": "TFLOP/s", "frac": ppo_tf / tf_sus, "traffic": traffic.get("ppo_update_per_minibatch") if args.config != 6 else None, "peak_source": which,
+                    "note": f"numerator = 8 epochs x 3 x {fwd_flop} FLOP per transition (update only); time = compute_returns + update (learn_ms). "
                             "Peak = measured bf16 sustained (MEASURED_PEAKS.json); the layers run kind::tf32, whose tensor peak is half of it. "
                             "traffic = DRAM bytes of the kernels of ONE minibatch from the ncu --set full capture under profiles/"}
         cb = cpu_baseline(args.config) if world == 1 else None
