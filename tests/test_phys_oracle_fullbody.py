@@ -1,7 +1,7 @@
 """Dynamics spec GRX-dyn v1 on the FULL-BODY GR1T1 / GR1T2 trees (33 bodies, 32 revolute DOF: legs, waist, head, arms — the
-unregistered `GR1T1Cfg` / `GR1T2Cfg` models of gr1t1_config.py:10-307).  The CUDA env kernel handles the registered
-lower-limb topology only; the C oracle is topology-generic, so the spec itself is validated here on the deeper tree with the same
-physical invariants as tests/test_phys_oracle.py.  CPU only."""
+unregistered `GR1T1Cfg` / `GR1T2Cfg` models of gr1t1_config.py:10-307).  The C oracle is topology-generic; the spec itself is validated here on the
+deeper tree with the same physical invariants as tests/test_phys_oracle.py (CPU only).  The CUDA side of the full-body task (generic-topology
+kernels, csrc/grx_phys_generic.cu) is compared against this oracle in tests/test_physg_gpu.py and tests/test_env_gpu.py."""
 import numpy as np
 import pytest
 
