@@ -846,6 +846,13 @@ struct PrepArgs {
     int nzero4;
     float *mb_log;     // [mb_log_cap][4] = (kl_mean, lr, loss, grad_norm) of minibatch ctl.mb_counter of this update (what ppo.py:262-268, 308-309 would log)
     int mb_log_cap;
+    // ONE-SHOT phase 1 (the input-layer weight gradients, the last ones produced): instead of a third kernel + its push / fence / counter chain,
+    // apply_kernel itself publishes "ready", loads the phase's ranges from ALL ranks over NVLink, sums them in rank order (bit-identical on
+    // every rank) into its local gsum and takes their part of the gradient norm through its own grid barrier.
+    int one_shot;
+    CommDev comm;
+    Ranges r1;
+    float *gsum_w;     // == g, writable
 };
 // ONE kernel for the apply step (ppo.py:262-268, 297-305): gradient norm -> [grid barrier] -> adaptive LR from the mean KL,
 // NaN skip, clip coefficient, Adam bias corrections (evaluated identically by every block from the same inputs) -> Adam on the
@@ -856,7 +863,7 @@ __global__ void __launch_bounds__(1024) apply_kernel(const PrepArgs a, float *__
                                                       float *__restrict__ v, int n) {
     Ctl &c = *a.ctl;
     __shared__ float red[32];
-    __shared__ double s_total, s_norm;
+    __shared__ double s_total;
     __shared__ int s_comm_bad;
     if (threadIdx.x == 0) tc::stamp(0);
     const float old_lr = c.lr;
@@ -873,21 +880,37 @@ __global__ void __launch_bounds__(1024) apply_kernel(const PrepArgs a, float *__
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
         if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-    } else if (threadIdx.x < NPHASE) {   // wait until every CTA of every rank has pushed its slice of the summed gradient (and its partial norm), both phases
-        wait_flag(a.comm_flags + threadIdx.x * FLAG_PHASE + FLAG_DONE, (c.comm_epoch + 1) * AR_NBLK * a.world_size, a.ctl, a.budget_ns);
+    } else if (!a.one_shot) {
+        if (threadIdx.x < NPHASE)   // wait until every CTA of every rank has pushed its slice of the summed gradient (and its partial norm), both phases
+            wait_flag(a.comm_flags + threadIdx.x * FLAG_PHASE + FLAG_DONE, (c.comm_epoch + 1) * AR_NBLK * a.world_size, a.ctl, a.budget_ns);
+    } else {
+        const int epoch = c.comm_epoch + 1;
+        // this kernel is a normal (fully serialised) launch behind the last weight-gradient GEMM: this rank's input-layer gradients are final
+        if (blockIdx.x == 0 && threadIdx.x < a.world_size) st_release_sys(a.comm.flags[threadIdx.x] + FLAG_PHASE + FLAG_READY + a.comm_rank, epoch);
+        if (threadIdx.x == 0) wait_flag(a.comm_flags + FLAG_DONE, epoch * AR_NBLK * a.world_size, a.ctl, a.budget_ns);   // phase 0 pushed by everybody
+        else if ((int)threadIdx.x <= a.world_size) wait_flag(a.comm_flags + FLAG_PHASE + FLAG_READY + (threadIdx.x - 1), epoch, a.ctl, a.budget_ns);
     }
     __syncthreads();
     if (threadIdx.x == 0) tc::stamp(1);
-    if (a.comm_flags != nullptr && threadIdx.x < 32) {   // squared norm = sum of the per-CTA partials of all ranks and phases, in an order that is the same everywhere
-        const int per_phase = a.world_size * AR_NBLK;
-        double t = 0.0;
-        for (int ph = 0; ph < NPHASE; ph++) {
-            const volatile double *tab = reinterpret_cast<const volatile double *>(a.comm_flags + ph * FLAG_PHASE + FLAG_SUMSQ);
-            for (int i = threadIdx.x; i < per_phase; i += 32) t += tab[i];
+    if (a.comm_flags != nullptr && a.one_shot) {   // phase 1: pull the ranges from every rank, rank-order sum -> local gsum, squared norm of this block's share
+        float s = 0.f;
+        for (int q = 0; q < a.r1.n; q++) {
+            for (int i = a.r1.lo[q] + blockIdx.x * blockDim.x + threadIdx.x; i < a.r1.hi[q]; i += gridDim.x * blockDim.x) {
+                float4 v[MAXW];
+#pragma unroll
+                for (int r = 0; r < MAXW; r++)   // all peer loads in flight at once
+                    if (r < a.world_size) v[r] = reinterpret_cast<const float4 *>(a.comm.grads[r])[i];
+                float4 x = v[0];
+#pragma unroll
+                for (int r = 1; r < MAXW; r++)
+                    if (r < a.world_size) { x.x += v[r].x; x.y += v[r].y; x.z += v[r].z; x.w += v[r].w; }
+                reinterpret_cast<float4 *>(a.gsum_w)[i] = x;
+                s += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+            }
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(FULL, t, o);
-        if (threadIdx.x == 0) s_norm = t;
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -895,6 +918,10 @@ __global__ void __launch_bounds__(1024) apply_kernel(const PrepArgs a, float *__
             float x = 0.f;
             for (int k = 0; k < (int)(blockDim.x >> 5); k++) x += red[k];
             atomicAdd(&c.sumsq, (double)x);
+        } else if (a.one_shot) {   // this block's partial -> its slot of the LOCAL phase-1 table (every rank computes the same partials: same elements, same sums)
+            double x = 0.0;
+            for (int k = 0; k < (int)(blockDim.x >> 5); k++) x += (double)red[k];
+            reinterpret_cast<volatile double *>(a.comm_flags + FLAG_PHASE + FLAG_SUMSQ)[blockIdx.x] = x;
         }
         __threadfence();
         atomicAdd(&c.apply_arrive, 1u);
@@ -905,14 +932,30 @@ __global__ void __launch_bounds__(1024) apply_kernel(const PrepArgs a, float *__
         }
         __threadfence();
         if (a.comm_flags == nullptr) s_total = *reinterpret_cast<volatile double *>(&c.sumsq);
-        else {
-            s_total = s_norm;   // summed below by warp 0 in a fixed order
-        }
         // sticky: a peer-flag / grid-barrier wait that timed out (now or in an earlier minibatch) leaves the summed gradient undefined.
         // Every block reads the flag after the grid barrier, so all of them take the same decision: do not touch the parameters.
         s_comm_bad = *reinterpret_cast<volatile int *>(&c.comm_error);
     }
     __syncthreads();
+    if (a.comm_flags != nullptr) {
+        if (threadIdx.x < 32) {   // squared norm = sum of the partials of all ranks and phases, in an order that is the same everywhere
+            const int per_phase = a.world_size * AR_NBLK;
+            double t = 0.0;
+            for (int ph = 0; ph < NPHASE; ph++) {
+                const volatile double *tab = reinterpret_cast<const volatile double *>(a.comm_flags + ph * FLAG_PHASE + FLAG_SUMSQ);
+                const int cnt = (ph == 1 && a.one_shot) ? (int)gridDim.x : per_phase;   // one-shot phase 1: the partials of this kernel's own blocks
+                for (int i = threadIdx.x; i < cnt; i += 32) t += tab[i];
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(FULL, t, o);
+            if (threadIdx.x == 0) s_total = t;
+        }
+        // one-shot: every block of this rank is past the grid barrier, i.e. done reading the peers' gradients -> tell them (they wait for it before
+        // their gradient block is cleared / accumulated into again)
+        if (a.one_shot && blockIdx.x == 0 && threadIdx.x >= 32 && (int)threadIdx.x < 32 + a.world_size)
+            asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(a.comm.flags[threadIdx.x - 32] + FLAG_PHASE + FLAG_DONE), "r"(1u) : "memory");
+        __syncthreads();
+    }
     if (threadIdx.x == 0) tc::stamp(2);
     // ---- control scalars, identical in every block
     const float cnt = a.tail[1];
@@ -950,6 +993,10 @@ __global__ void __launch_bounds__(1024) apply_kernel(const PrepArgs a, float *__
             }
             reinterpret_cast<float4 *>(m)[i] = m4; reinterpret_cast<float4 *>(v)[i] = v4; reinterpret_cast<float4 *>(p)[i] = p4;
         }
+    }
+    if (a.comm_flags != nullptr && a.one_shot) {   // the peers' one-shot reads of this rank's input-layer gradients must be over before they are cleared or accumulated into again
+        if (threadIdx.x == 0) wait_flag(a.comm_flags + FLAG_PHASE + FLAG_DONE, (c.comm_epoch + 1) * a.world_size, a.ctl, a.budget_ns);
+        __syncthreads();
     }
     if (a.zero != nullptr)   // every reader of this minibatch's gradients (this kernel; the peers' all-reduce, whose completion was awaited above) is done
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.nzero4; i += gridDim.x * blockDim.x) a.zero[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1025,6 +1072,7 @@ struct grx_ppo {
     bool comm_open = false;
     int apply_grid = 148;   // co-resident grid of apply_kernel (<= SM count)
     unsigned long long comm_budget_ns = 10000000000ull;   // cfg.comm_timeout_ms (GRX_COMM_TIMEOUT_MS overrides)
+    bool one_shot = true;   // phase 1 of the gradient all-reduce inside apply_kernel (GRX_COMM_ONESHOT=0: as a second allreduce_kernel launch; fixed for the object's lifetime)
     CommDev comm;
     std::vector<void *> peer_maps;
     // the all-reduce runs in two phases so that most of it hides behind the last weight-gradient launch:
@@ -1131,6 +1179,7 @@ extern "C" int grx_ppo_create(const grx_ppo_cfg *cfg, int32_t device, grx_ppo **
     if (cfg->comm_timeout_ms > 0) p->comm_budget_ns = (unsigned long long)cfg->comm_timeout_ms * 1000000ull;
     if (const char *e = getenv("GRX_COMM_TIMEOUT_MS")) { const long v = atol(e); if (v > 0) p->comm_budget_ns = (unsigned long long)v * 1000000ull; }
     if (const char *e = getenv("GRX_PPO_TIMING")) p->timing = atoi(e) != 0;
+    if (const char *e = getenv("GRX_COMM_ONESHOT")) p->one_shot = atoi(e) != 0;
     if (p->timing) for (int i = 0; i < 9; i++) CK(cudaEventCreate(&p->tev[i]));
     *out = p;
     return GRX_OK;
@@ -1433,12 +1482,13 @@ static int minibatch_apply(grx_ppo *p, cudaStream_t st, bool use_comm, bool zero
     const float *gsrc = p->reduce_buf;
     if (use_comm) {   // NVLink all-reduce + norm; the summed gradient lands in gsum on every rank
         if (!p->phase0_launched) launch_allreduce_phase(p, 0, st);   // not forked by minibatch_grads (stepwise entry): both phases back to back
-        launch_allreduce_phase(p, 1, st);
+        if (!p->one_shot) launch_allreduce_phase(p, 1, st);
         p->phase0_launched = false;
         gsrc = p->gsum;
     }
     PrepArgs a; memset(&a, 0, sizeof(a));
     a.comm_flags = use_comm ? p->flags : nullptr; a.comm_rank = p->comm.rank; a.budget_ns = p->comm_budget_ns;
+    a.one_shot = use_comm && p->one_shot ? 1 : 0; a.comm = p->comm; a.r1 = p->phase_ranges[1]; a.gsum_w = p->gsum;
     a.mb_log = p->mb_log; a.mb_log_cap = p->mb_log_cap;
     a.zero = zero_grads ? reinterpret_cast<float4 *>(p->reduce_buf) : nullptr; a.nzero4 = (int)((p->nparam + TAIL) / 4);
     a.ctl = p->ctl; a.tail = gsrc + p->nparam; a.std = p->params; a.A = p->A; a.adaptive = p->cfg.adaptive_schedule;
