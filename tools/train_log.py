@@ -29,13 +29,14 @@ def main():
     ap.add_argument("--every", type=int, default=10)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--full-body", action="store_true", help="the unregistered full-body 32-DOF task (generic-topology kernels, self-collision)")
     args = ap.parse_args()
     import torch
-    from grx_b200.config import make_cfg, make_train_cfg
+    from grx_b200.config import make_cfg, make_full_body_cfg, make_train_cfg
     from grx_b200.env import GRXVecEnv
     from grx_b200.runner import OnPolicyRunner
     torch.manual_seed(args.seed)
-    cfg = make_cfg(args.robot, args.envs, args.mesh)
+    cfg = (make_full_body_cfg if args.full_body else make_cfg)(args.robot, args.envs, args.mesh)
     cfg.seed = args.seed
     env = GRXVecEnv(cfg, sim_device="cuda:0")
     tc = make_train_cfg()

@@ -594,7 +594,7 @@ inline cudaError_t launch_group(const Problem *ps, int np, const int *splits, cu
             const int sp = splits && splits[i] > 1 ? splits[i] : 1;
             const int kchunk = ((ps[i].K + sp - 1) / sp + TK - 1) / TK * TK;
             const int z = (ps[i].K + kchunk - 1) / kchunk;
-            if (bn > 32 && ps[i].N <= bn / 2) ok = false;                  // mostly padding along N
+            if (bn > 32 && ps[i].N <= bn / 2 && !(EPI == 3 && np > 4 && bn == 128)) ok = false;   // mostly padding along N (tolerated for one narrow member of a merged weight-gradient group)
             if (tmt > 1 && ps[i].M <= TM) ok = false;                      // second row block would be padding
             const long ti = (long)((ps[i].M + TM * tmt - 1) / (TM * tmt)) * ((ps[i].N + bn - 1) / bn) * z;
             tiles += ti;

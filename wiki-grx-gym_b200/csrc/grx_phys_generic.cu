@@ -328,13 +328,10 @@ __device__ void g_substep(GWS &s, const GModel &m, const GArgs &A, int lane, flo
     const float dt = cfg.sim_dt;
     g_mass_and_bias(s, m, cfg.gravity, lane);
     g_cholesky(s, nv, lane);
-    // ---- unconstrained update u* = u + dt M^-1 (tau - h)   (row GROWS - 1 of Y as scratch, solved by lane 0)
+    // ---- unconstrained update u* = u + dt M^-1 (tau - h): the right-hand side goes into row GROWS - 1 of Y and is solved further down TOGETHER with
+    // the constraint rows (one lane per right-hand side) — a lone single-lane solve here cost as much as the whole batch
     float *rhs = s.Y[GROWS - 1];
     for (int i = lane; i < nv; i += 32) rhs[i] = (i < nd ? s.tau[i] : 0.f) - s.h[i];
-    __syncwarp();
-    if (lane == 0) g_chol_solve(s, nv, rhs);
-    __syncwarp();
-    for (int i = lane; i < nv; i += 32) s.u[i] = (i < nd ? s.qd[i] : s.root[7 + i - nd]) + dt * rhs[i];
     __syncwarp();
     const float mu = 0.5f * (mu_env + A.terrain.friction), rest = 0.5f * (rest_env + A.terrain.restitution);
     unsigned long long sig_item = 0ull;
@@ -470,16 +467,22 @@ __device__ void g_substep(GWS &s, const GModel &m, const GArgs &A, int lane, flo
         }
     }
     __syncwarp();
-    // ---- Y = M^-1 J^T (one lane per row, two passes), Ad = J . Y
-    for (int r = lane; r < nrow; r += 32) {
-        float *y = s.Y[r];
-        for (int i = 0; i < nv; i++) y[i] = s.J[r][i];
-        g_chol_solve(s, nv, y);
-        float a = 0.f;
-        for (int i = 0; i < nv; i++) a += s.J[r][i] * y[i];
-        s.Ad[r] = a;
-        s.lam[r] = 0.f;
+    // ---- Y = M^-1 J^T (one lane per row, two passes), Ad = J . Y; "row" nrow = the unconstrained right-hand side (nrow <= GROWS - 1: its own row)
+    for (int r = lane; r <= nrow; r += 32) {
+        const bool con = r < nrow;
+        float *y = con ? s.Y[r] : rhs;
+        if (con)
+            for (int i = 0; i < nv; i++) y[i] = s.J[r][i];
+        g_chol_solve(s, nv, y);   // ONE call site: the lane of the right-hand side runs converged with the constraint lanes
+        if (con) {
+            float a = 0.f;
+            for (int i = 0; i < nv; i++) a += s.J[r][i] * y[i];
+            s.Ad[r] = a;
+            s.lam[r] = 0.f;
+        }
     }
+    __syncwarp();
+    for (int i = lane; i < nv; i += 32) s.u[i] = (i < nd ? s.qd[i] : s.root[7 + i - nd]) + dt * rhs[i];
     __syncwarp();
     // ---- projected Gauss-Seidel in velocity space (the oracle's sweep: contacts — normal, then 2 friction rows — then the limits)
     for (int it = 0; it < cfg.solver_iters; it++) {

@@ -753,10 +753,14 @@ struct Ctl {            // device control block
 constexpr int MAXW = 8;
 // flag block of a rank, per PHASE (two phases per minibatch, see allreduce_kernel), offsets in ints:
 //   ready[8]                 epoch numbers written by every peer ("my gradients of this phase are final")
-//   done counter (1 uint)    every CTA of every rank's allreduce_kernel adds 1 after pushing its slice: monotonic, target = epoch * NBLK * world
-//   sumsq partials           [world][NBLK] doubles: squared norm of the slice a CTA reduced (summed in a fixed order by apply_kernel)
+//   done counter (1 uint)    the last CTA of every rank's allreduce_kernel adds 1 after the rank's slices are pushed and visible: monotonic, target = epoch * world
+//                            (one-shot phase 1: every rank adds 1 once its apply_kernel has finished READING the peers' gradients: same target)
+//   ticket (1 uint)          local: CTAs of this rank's allreduce_kernel that have finished (the last one publishes and resets it)
+//   sumsq                    [world] doubles: squared norm of the slices rank r reduced (one-shot phase 1: [apply grid] local partials), summed in a fixed order by apply_kernel
+//   local partials           [NBLK] doubles: per-CTA squared norms of this rank's allreduce_kernel, added by its last CTA
 constexpr int NPHASE = 2, AR_NBLK = 128;   // CTAs of allreduce_kernel (every phase)
-constexpr int FLAG_READY = 0, FLAG_DONE = 16, FLAG_SUMSQ = 32, FLAG_PHASE = 32 + 2 * MAXW * AR_NBLK;
+constexpr int FLAG_READY = 0, FLAG_DONE = 16, FLAG_TICKET = 17, FLAG_SUMSQ = 32, FLAG_LOCAL = 32 + 2 * 256, FLAG_PHASE = FLAG_LOCAL + 2 * AR_NBLK;
+static_assert(MAXW <= 256 && 148 <= 256, "sumsq table: world entries (two-shot) or one per apply_kernel block (one-shot)");
 constexpr size_t FLAG_BYTES = (size_t)NPHASE * FLAG_PHASE * 4;
 constexpr int MAXRANGE = 4;
 struct Ranges {         // float4 index ranges [lo, hi) of the gradient block one all-reduce phase covers
@@ -816,22 +820,39 @@ __global__ void __launch_bounds__(256) allreduce_kernel(const CommDev c, const R
             if (i < nparam4) ss += s.x * s.x + s.y * s.y + s.z * s.z + s.w * s.w;   // the tail (KL / loss sums) is not part of the gradient
         }
     }
-    // publication, per CTA (no last-block chain): squared-norm partial of this CTA's slice -> every rank's partial table; then ONE system fence by
-    // thread 0 (cumulative over the CTA's stores through the block barrier) and one remote add on every rank's done counter
+    // publication: every CTA leaves the squared-norm partial of its slice in a LOCAL table, makes its pushes visible system-wide (one system
+    // fence by thread 0, cumulative over the CTA's stores through the block barrier) and takes a ticket on a local counter; the LAST CTA of the
+    // rank adds the partials in a fixed order, stores the rank's total into every rank's table and adds 1 to every rank's done counter
+    // (release: ordered after this thread's stores and, by cumulativity, after everything the tickets made visible).  Remote traffic per phase
+    // and rank: W stores + W atomics — per-CTA remote atomics (W x 128 per counter) do not scale: measured 45.6 ms per update on 8 GPUs
+    // against 38.7 ms on 2.
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(FULL, ss, o);
     __shared__ float red[8];
+    __shared__ int s_last;
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
     __syncthreads();
+    int *loc = c.flags[c.rank] + fo;
     if (threadIdx.x == 0) {
         tc::stamp(18 + 4 * phase);
         double x = 0.0;
         for (int k = 0; k < 8; k++) x += (double)red[k];
-        for (int r = 0; r < c.world; r++) reinterpret_cast<double *>(c.flags[r] + fo + FLAG_SUMSQ)[c.rank * AR_NBLK + blockIdx.x] = x;
+        reinterpret_cast<volatile double *>(loc + FLAG_LOCAL)[blockIdx.x] = x;
         __threadfence_system();
-        for (int r = 0; r < c.world; r++)
-            asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(c.flags[r] + fo + FLAG_DONE), "r"(1u) : "memory");
-        tc::stamp(19 + 4 * phase);
+        s_last = atomicAdd(reinterpret_cast<unsigned *>(loc + FLAG_TICKET), 1u) == gridDim.x - 1 ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x < 32) {
+        __threadfence();
+        double t = 0.0;
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += 32) t += reinterpret_cast<const volatile double *>(loc + FLAG_LOCAL)[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(FULL, t, o);   // fixed tree: the same total on every run
+        if ((int)threadIdx.x < c.world) {
+            reinterpret_cast<volatile double *>(c.flags[threadIdx.x] + fo + FLAG_SUMSQ)[c.rank] = t;
+            asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(c.flags[threadIdx.x] + fo + FLAG_DONE), "r"(1u) : "memory");
+        }
+        if (threadIdx.x == 0) { *reinterpret_cast<volatile unsigned *>(loc + FLAG_TICKET) = 0u; tc::stamp(19 + 4 * phase); }
     }
 }
 struct PrepArgs {
@@ -882,12 +903,12 @@ __global__ void __launch_bounds__(1024) apply_kernel(const PrepArgs a, float *__
         if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
     } else if (!a.one_shot) {
         if (threadIdx.x < NPHASE)   // wait until every CTA of every rank has pushed its slice of the summed gradient (and its partial norm), both phases
-            wait_flag(a.comm_flags + threadIdx.x * FLAG_PHASE + FLAG_DONE, (c.comm_epoch + 1) * AR_NBLK * a.world_size, a.ctl, a.budget_ns);
+            wait_flag(a.comm_flags + threadIdx.x * FLAG_PHASE + FLAG_DONE, (c.comm_epoch + 1) * a.world_size, a.ctl, a.budget_ns);
     } else {
         const int epoch = c.comm_epoch + 1;
         // this kernel is a normal (fully serialised) launch behind the last weight-gradient GEMM: this rank's input-layer gradients are final
         if (blockIdx.x == 0 && threadIdx.x < a.world_size) st_release_sys(a.comm.flags[threadIdx.x] + FLAG_PHASE + FLAG_READY + a.comm_rank, epoch);
-        if (threadIdx.x == 0) wait_flag(a.comm_flags + FLAG_DONE, epoch * AR_NBLK * a.world_size, a.ctl, a.budget_ns);   // phase 0 pushed by everybody
+        if (threadIdx.x == 0) wait_flag(a.comm_flags + FLAG_DONE, epoch * a.world_size, a.ctl, a.budget_ns);   // phase 0 pushed by everybody
         else if ((int)threadIdx.x <= a.world_size) wait_flag(a.comm_flags + FLAG_PHASE + FLAG_READY + (threadIdx.x - 1), epoch, a.ctl, a.budget_ns);
     }
     __syncthreads();
@@ -939,7 +960,7 @@ __global__ void __launch_bounds__(1024) apply_kernel(const PrepArgs a, float *__
     __syncthreads();
     if (a.comm_flags != nullptr) {
         if (threadIdx.x < 32) {   // squared norm = sum of the partials of all ranks and phases, in an order that is the same everywhere
-            const int per_phase = a.world_size * AR_NBLK;
+            const int per_phase = a.world_size;   // one total per rank
             double t = 0.0;
             for (int ph = 0; ph < NPHASE; ph++) {
                 const volatile double *tab = reinterpret_cast<const volatile double *>(a.comm_flags + ph * FLAG_PHASE + FLAG_SUMSQ);
@@ -1304,9 +1325,12 @@ static void mlp_backward(grx_ppo *p, const NetIO *io, int nn, float *grads, int 
     GemmArgs g[8];
     int splits[8], n = 0;
     auto flush = [&]() { if (n) dense_group<false, false, 3>(g, splits, n, tcu, st); n = 0; };
-    for (int pass = 0; pass < 2; pass++) {   // pass 0: hidden layers (wide N), pass 1: input layer (narrow N) -> their own tile shape
+    // GRX_DW_MERGE=1 (single GPU only: the two-launch split is what the all-reduce phase 0 overlaps with): all weight gradients in ONE grouped launch
+    static const bool merge_env = [] { const char *e = getenv("GRX_DW_MERGE"); return e && atoi(e) != 0; }();
+    const bool merge = merge_env && !overlap_comm;
+    for (int pass = 0; pass < (merge ? 1 : 2); pass++) {   // pass 0: hidden layers (wide N), pass 1: input layer (narrow N) -> their own tile shape
         for (int l = top; l >= 0; l--) {     // (one launch for all six was measured slower: the narrow input layers drag the group to BN = 64)
-            if ((l == 0) != (pass == 1)) continue;
+            if (!merge && (l == 0) != (pass == 1)) continue;
             for (int i = 0; i < nn; i++) {
                 const Net &net = *io[i].net;
                 GemmArgs &a = g[n];
