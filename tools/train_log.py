@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--out", default=None)
     ap.add_argument("--full-body", action="store_true", help="the unregistered full-body 32-DOF task (generic-topology kernels, self-collision)")
+    ap.add_argument("--no-self-collision", action="store_true", help="full body: robot self-collision off (cfg.asset.self_collisions = 1)")
     args = ap.parse_args()
     import torch
     from grx_b200.config import make_cfg, make_full_body_cfg, make_train_cfg
@@ -38,6 +39,8 @@ def main():
     torch.manual_seed(args.seed)
     cfg = (make_full_body_cfg if args.full_body else make_cfg)(args.robot, args.envs, args.mesh)
     cfg.seed = args.seed
+    if args.no_self_collision:
+        cfg.asset.self_collisions = 1   # legged_robot_config.py:121: 1 = disabled
     env = GRXVecEnv(cfg, sim_device="cuda:0")
     tc = make_train_cfg()
     tc["runner"]["save_interval"] = 10 ** 9

@@ -1325,11 +1325,12 @@ static void mlp_backward(grx_ppo *p, const NetIO *io, int nn, float *grads, int 
     GemmArgs g[8];
     int splits[8], n = 0;
     auto flush = [&]() { if (n) dense_group<false, false, 3>(g, splits, n, tcu, st); n = 0; };
-    // GRX_DW_MERGE=1 (single GPU only: the two-launch split is what the all-reduce phase 0 overlaps with): all weight gradients in ONE grouped launch
-    static const bool merge_env = [] { const char *e = getenv("GRX_DW_MERGE"); return e && atoi(e) != 0; }();
+    // Single GPU: all weight gradients in ONE grouped launch of 128-column tiles (the narrow actor input layer pads its one tile): measured 180.9 ->
+    // 174.7 us per minibatch (GRX_DW_MERGE=0 restores the two launches).  Multi-GPU keeps two launches: phase 0 of the all-reduce overlaps the second.
+    static const bool merge_env = [] { const char *e = getenv("GRX_DW_MERGE"); return e ? atoi(e) != 0 : true; }();
     const bool merge = merge_env && !overlap_comm;
     for (int pass = 0; pass < (merge ? 1 : 2); pass++) {   // pass 0: hidden layers (wide N), pass 1: input layer (narrow N) -> their own tile shape
-        for (int l = top; l >= 0; l--) {     // (one launch for all six was measured slower: the narrow input layers drag the group to BN = 64)
+        for (int l = top; l >= 0; l--) {     // (one launch for all six with the cost model free to pick BN = 64 was measured slower)
             if (!merge && (l == 0) != (pass == 1)) continue;
             for (int i = 0; i < nn; i++) {
                 const Net &net = *io[i].net;
@@ -1366,9 +1367,12 @@ extern "C" int grx_ppo_act(grx_ppo *p, const float *d_obs, const float *d_critic
                            uint64_t step_index, void *stream) {
     if (!p || !d_obs || !d_critic_obs || !d_actions_out || t < 0 || t >= p->T) return grx_set_error(GRX_E_INVALID, "grx_ppo_act: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
-    CK(stage_rows(p->xa, p->Opad, d_obs, p->O, p->N, st));
-    CK(stage_rows(p->xc, p->Ppad, d_critic_obs, p->P, p->N, st));
-    const NetIO io[2] = {{&p->actor, p->xa, p->Opad, p->ha, p->da}, {&p->critic, p->xc, p->Ppad, p->hc, p->dc}};
+    // rows that are already 16-byte aligned with a 16-byte pitch (the registered critic input: 168 floats) are read in place by TMA; the others
+    // (actor: 39 floats) are staged into the padded input buffers
+    const float *xa = p->xa, *xc = p->xc;
+    if (p->O == p->Opad && tc::aligned16(d_obs)) xa = d_obs; else CK(stage_rows(p->xa, p->Opad, d_obs, p->O, p->N, st));
+    if (p->P == p->Ppad && tc::aligned16(d_critic_obs)) xc = d_critic_obs; else CK(stage_rows(p->xc, p->Ppad, d_critic_obs, p->P, p->N, st));
+    const NetIO io[2] = {{&p->actor, xa, p->Opad, p->ha, p->da}, {&p->critic, xc, p->Ppad, p->hc, p->dc}};
     const bool fused_heads = p->A == 10 && p->critic.dims[4] == 1 && p->actor.dims[3] == HEADS_H && p->critic.dims[3] == HEADS_H;
     mlp_forward(p, io, 2, p->N, fused_heads ? 3 : 4, st, false);   // rollout: only the last hidden layer leaves the chip
     ActArgs a; memset(&a, 0, sizeof(a));
@@ -1406,8 +1410,9 @@ extern "C" int grx_ppo_process_env_step(grx_ppo *p, const float *d_rewards, cons
 extern "C" int grx_ppo_compute_returns_local(grx_ppo *p, const float *d_last_critic_obs, void *stream) {
     if (!p || !d_last_critic_obs) return grx_set_error(GRX_E_INVALID, "grx_ppo_compute_returns: null argument");
     cudaStream_t st = (cudaStream_t)stream;
-    CK(stage_rows(p->xc, p->Ppad, d_last_critic_obs, p->P, p->N, st));
-    const NetIO io = {&p->critic, p->xc, p->Ppad, p->hc, p->dc};
+    const float *xc = p->xc;
+    if (p->P == p->Ppad && tc::aligned16(d_last_critic_obs)) xc = d_last_critic_obs; else CK(stage_rows(p->xc, p->Ppad, d_last_critic_obs, p->P, p->N, st));
+    const NetIO io = {&p->critic, xc, p->Ppad, p->hc, p->dc};
     mlp_forward(p, &io, 1, p->N, 4, st, false);                                        // ppo.py:204
     CK(cudaMemcpyAsync(p->last_values, p->hc[3], (size_t)p->N * 4, cudaMemcpyDeviceToDevice, st));
     CK(cudaMemsetAsync(p->moments, 0, 4 * sizeof(double), st));
