@@ -358,6 +358,9 @@ int grx_gemm_debug(int32_t variant, int32_t epi, int32_t M, int32_t N, int32_t K
 /* Test / profiling: the three hidden layers of the registered policy run as ONE chained tcgen05 kernel per forward pass (csrc/grx_mlp_chain.cuh);
  * fwd_chain = 0 falls back to one grouped GEMM launch per layer, 1 enables, -1 only queries.  Returns the previous setting. */
 int grx_ppo_debug_fused(int32_t fwd_chain);
+/* Test / profiling: the layer-pipelined launches (several dependent dense layers in ONE persistent tcgen05 launch; GRX_LAYER_PIPE) on (1) / off (0)
+ * at run time, -1 = query; returns the previous setting. */
+int grx_ppo_debug_pipe(int32_t on);
 
 /* Test / profiling: force the macro tile of the tensor-core GEMM (row_blocks in {1, 2} x bn in {32, 64, 128, 256}; 0, 0 = cost model). */
 int grx_gemm_debug_tile(int32_t row_blocks, int32_t bn);

@@ -173,3 +173,61 @@ def test_chained_forward_equals_layerwise(M, store):
             mu = ac.actor.to_module()(obs.cpu())
         np.testing.assert_allclose(res[1][1].cpu().numpy(), mu.numpy(), rtol=0, atol=6e-3 * float(mu.abs().max()))
     alg.close()
+
+
+@pytest.mark.parametrize("M,store", [(4096, False), (10485, True), (333, True), (128, False), (700, False)])
+def test_layer_pipelined_launch_equals_layerwise(M, store):
+    """Dependent dense layers in ONE persistent launch (tc::launch_pipe: the three hidden layers of both networks of the forward pass, the two
+    wide input-gradient layers of the backward pass; a tile's loads wait on the row-block counter of the layer that produces its A operand)
+    == the same layers as one grouped launch per layer.  Same contraction order per output element, so the forward is expected bit-identical
+    (1e-6 relative allowed); the gradients additionally carry the run-to-run noise of the split-K / column-sum atomics (1e-5 of the scale,
+    as for the chained kernel above).  store=False is the rollout (PPO.act), store=True one minibatch's forward + backward."""
+    import ctypes as C
+    from grx_b200 import _lib as L
+    from grx_b200.config import make_train_cfg
+    from grx_b200.ppo import PPO, ActorCriticMLP
+    lib = L.lib()
+    lib.grx_ppo_debug_pipe.argtypes = [C.c_int32]
+    tc = make_train_cfg()
+    torch.manual_seed(37)
+    N, T = M, 4
+    ac = ActorCriticMLP(39, 168, 10, **tc["policy"])
+    alg = PPO(ac, device="cuda:0", **dict(tc["algorithm"], num_mini_batches=4, num_learning_epochs=1))
+    alg.init_storage(N, T)
+    g = torch.Generator().manual_seed(M + 1)
+    obs, cobs, eps = torch.randn(N, 39, generator=g).cuda(), torch.randn(N, 168, generator=g).cuda(), torch.randn(N, 10, generator=g).cuda()
+    adv, idx = torch.randn(T, N, 1, generator=g).cuda(), torch.randperm(N * T, generator=g).cuda()
+    res = {}
+    old_fused = lib.grx_ppo_debug_fused(0)
+    try:
+        for pipe in (1, 0, 1):
+            old = lib.grx_ppo_debug_pipe(pipe)
+            alg.step = 0
+            if not store:
+                a = alg.act(obs, cobs, eps=eps).clone()
+                out = (a, alg.storage.mu[0].clone(), alg.storage.values[0].clone(), alg.storage.actions_log_prob[0].clone())
+            else:
+                for t in range(T):
+                    alg.act(obs, cobs, eps=eps)
+                    alg.process_env_step(torch.zeros(N, device="cuda"), torch.zeros(N, dtype=torch.bool, device="cuda"), {})
+                alg.compute_returns(cobs)
+                alg.storage.advantages.copy_(adv)
+                alg._indices.copy_(idx)
+                L.check(lib.grx_ppo_minibatch_grads(alg._h, C.c_void_p(alg._indices.data_ptr()), 2, alg._stream()))
+                out = (alg.grads.clone(), alg.reduce_buf[-8:].clone())
+            torch.cuda.synchronize()
+            assert alg.minibatch_stats()["chain_error"] == 0, "a dependency wait inside the pipelined launch timed out"
+            res.setdefault(pipe, []).append(out)
+            lib.grx_ppo_debug_pipe(old)
+    finally:
+        lib.grx_ppo_debug_fused(old_fused)
+    tol = 1e-6 if not store else 1e-5
+    for run in res[1]:   # both pipelined runs (the second one starts from the counters the first one left behind) vs the layerwise run
+        for x, y in zip(run, res[0][0]):
+            scale = float(y.abs().max()) + 1e-30
+            assert float((x - y).abs().max()) <= tol * scale, (M, store, float((x - y).abs().max()), scale)
+    if not store:
+        with torch.no_grad():
+            mu = ac.actor.to_module()(obs.cpu())
+        np.testing.assert_allclose(res[1][0][1].cpu().numpy(), mu.numpy(), rtol=0, atol=6e-3 * float(mu.abs().max()))
+    alg.close()

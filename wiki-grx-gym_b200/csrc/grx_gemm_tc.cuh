@@ -65,11 +65,19 @@ struct Args {
     int kchunk;          // contraction elements per split (multiple of 32)
     int nt_m, nt_n;      // tiles along M / N
     int tile_begin;      // first linear tile id of this problem in the group (tiles = nt_m * nt_n * splits)
+    // layer pipelining inside ONE launch (launch_pipe): problem `dep` (an earlier member of the group, or -1) produces this problem's A operand;
+    // a tile of row block tm may load A once sync[dep][tm] has reached `need` (= column tiles of dep x its epilogue warps); `signal` != 0:
+    // every epilogue warp adds 1 to sync[this][tm] when its stores of a tile have completed
+    int dep, need, signal;
 };
+constexpr int SYNC_RB = 256;                          // row-block counters per problem
+constexpr int SYNC_INTS = MAXP * SYNC_RB + 4;         // + exit counter
 struct Group {
     Args g[MAXP];
     int np, total_tiles;
     int dbg;   // profiling switches (GRX_TC_DEBUG): 1 skip the MMA issue, 2 skip the operand loads (results are garbage)
+    int *sync; // launch_pipe: [MAXP][SYNC_RB] row-block counters + exit counter (all zero between launches: the last CTA to leave clears them), else NULL
+    int *err;  // set to 3 when a dependency wait timed out (protocol error; results invalid)
 };
 struct Maps {
     CUtensorMap a[MAXP], b[MAXP];
@@ -231,7 +239,7 @@ __global__ void __launch_bounds__(NTHREADS_CTA, 1) gemm_tf32_kernel(const __grid
     if (tid == 0) stamp(1);
 
     // tile id -> (problem, m0, n0, contraction range); every role walks the same sequence t = blockIdx.x, + gridDim.x, ...
-    struct Tile { int p, m0, n0, kbeg, nchunks; };
+    struct Tile { int p, m0, n0, kbeg, nchunks, tm; };
     auto decode = [&](int t) {
         Tile T;
         int p = 0;
@@ -239,7 +247,7 @@ __global__ void __launch_bounds__(NTHREADS_CTA, 1) gemm_tf32_kernel(const __grid
         const Args &g = grp.g[p];
         const int local = t - g.tile_begin;
         const int tn = local % g.nt_n, rest = local / g.nt_n, tm = rest % g.nt_m, z = rest / g.nt_m;
-        T.p = p; T.m0 = tm * (TM * TMT); T.n0 = tn * BN; T.kbeg = z * g.kchunk;
+        T.p = p; T.m0 = tm * (TM * TMT); T.n0 = tn * BN; T.kbeg = z * g.kchunk; T.tm = tm;
         const int kend = min(g.K, T.kbeg + g.kchunk);
         T.nchunks = (kend - T.kbeg + TK - 1) / TK;
         return T;
@@ -251,6 +259,19 @@ __global__ void __launch_bounds__(NTHREADS_CTA, 1) gemm_tf32_kernel(const __grid
             for (int t = blockIdx.x; t < grp.total_tiles; t += gridDim.x) {
                 const Tile T = decode(t);
                 const CUtensorMap *ma = &maps.a[T.p], *mb = &maps.b[T.p];
+                if (grp.g[T.p].dep >= 0) {   // layer pipelining: the rows of A this tile reads are outputs of an earlier problem of this launch
+                    const int *cnt = grp.sync + grp.g[T.p].dep * SYNC_RB + T.tm;
+                    const int need = grp.g[T.p].need;
+                    const long long t0 = clock64();
+                    for (;;) {
+                        int v;
+                        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
+                        if (v >= need) break;
+                        if (clock64() - t0 > 6000000000ll) { atomicExch(grp.err, 3); break; }   // never hang the GPU; the host raises on the flag
+                        __nanosleep(32);
+                    }
+                    asm volatile("fence.proxy.async;" ::: "memory");   // the producers' stores (seen through the acquire) before this thread's TMA reads
+                }
                 for (int kb = 0; kb < T.nchunks; kb++, it++) {
                     const uint32_t st = it % S;
                     if (it >= S) mbar_wait(smem_u32(&empty_bar[st]), ((it / S) - 1) & 1);
@@ -323,10 +344,32 @@ __global__ void __launch_bounds__(NTHREADS_CTA, 1) gemm_tf32_kernel(const __grid
             const uint32_t bias0 = smem0 + (uint32_t)S * stage_bytes + Cfg::staging_bytes + (uint32_t)warp * (WCOLS * 4u);
             const uint32_t rowoff = (uint32_t)lane * 128u, sw = (uint32_t)(lane & 7);
             uint32_t ti = 0, cc = 0;   // tiles / chunks processed by this warp
+            // layer pipelining: a finished tile is SIGNALLED (its row-block counter incremented) only once its bulk stores have completed.  Waiting
+            // for that right after the tile would put one store latency per tile on the epilogue's critical path, so the signal lags: it is sent after
+            // the first chunk of the warp's next tile has been committed (wait_group 1: everything but the newest group has completed) — or at once
+            // when that next tile's accumulator is not ready yet (the warp would idle anyway; this also keeps the protocol free of cycles: a
+            // pending signal never waits on a tile that may itself depend on it).
+            int *pend = nullptr;
+            auto flush_pending = [&](bool all) {
+                if (pend != nullptr && lane == 0) {
+                    if (all) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                    else asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    __threadfence();
+                    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(pend), "r"(1) : "memory");
+                }
+                pend = nullptr;
+            };
             for (int t = blockIdx.x; t < grp.total_tiles; t += gridDim.x, ti++) {
                 const Tile T = decode(t);
                 const Args &g = grp.g[T.p];
                 const uint32_t buf = ti % NACC;
+                if (pend != nullptr) {   // accumulator of this tile not complete yet -> use the idle time to publish the previous tile
+                    uint32_t ready = 0;
+                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                                 : "=r"(ready) : "r"(smem_u32(&acc_full[buf])), "r"((ti / NACC) & 1) : "memory");
+                    if (!ready) flush_pending(true);
+                }
                 const int ncol0 = T.n0 + chalf * WCOLS;
                 if (EPI == 2) {
                     if (lane == 0) {
@@ -412,8 +455,11 @@ __global__ void __launch_bounds__(NTHREADS_CTA, 1) gemm_tf32_kernel(const __grid
                         warp_colsum<32>(v, lane);
                         if (n + lane < g.N) atomicAdd(&g.colsum[n + lane], v[0]);
                     }
+                    if (c == 0 && pend != nullptr) flush_pending(false);   // the previous tile's groups are all older than the one just committed
                 }
+                if (g.signal) pend = grp.sync + T.p * SYNC_RB + T.tm;
             }
+            flush_pending(true);
             if (ti >= 1 && tid == 0) stamp(12);
             if (lane == 0) tma_wait_read0();
         }
@@ -422,6 +468,18 @@ __global__ void __launch_bounds__(NTHREADS_CTA, 1) gemm_tf32_kernel(const __grid
     tc_fence_before();
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(NACC * ACC_COLS) : "memory");
+    if (grp.sync != nullptr) {   // layer pipelining: the last CTA to leave clears the counters for the next launch (which touches them only after its pdl_wait)
+        __shared__ int s_last;
+        if (tid == 0) {
+            __threadfence();
+            s_last = atomicAdd(reinterpret_cast<unsigned *>(grp.sync + MAXP * SYNC_RB), 1u) == gridDim.x - 1 ? 1 : 0;
+        }
+        __syncthreads();
+        if (s_last) {
+            for (int i = tid; i < grp.np * SYNC_RB; i += NTHREADS_CTA) grp.sync[i] = 0;
+            if (tid == 0) grp.sync[MAXP * SYNC_RB] = 0;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -529,7 +587,7 @@ inline int sm_count() {
 }
 
 template <bool A_KMAJ, bool B_KMAJ, int EPI, int TMT, int BN, int S>
-inline cudaError_t launch_cfg(const Problem *ps, int np, const int *splits, cudaStream_t st) {
+inline cudaError_t launch_cfg(const Problem *ps, int np, const int *splits, cudaStream_t st, const int *deps = nullptr, int *sync = nullptr, int *err = nullptr) {
     constexpr size_t smem = TileCfg<TMT, BN>::smem(S);
     static_assert(smem <= 226 * 1024, "shared memory budget (227 KB per CTA minus the static barriers)");
     static bool attr_done = false;   // per template instantiation
@@ -564,8 +622,20 @@ inline cudaError_t launch_cfg(const Problem *ps, int np, const int *splits, cuda
         g.nt_m = (p.M + TM * TMT - 1) / (TM * TMT); g.nt_n = (p.N + BN - 1) / BN;
         g.tile_begin = total;
         total += g.nt_m * g.nt_n * z;
+        g.dep = -1; g.need = 0; g.signal = 0;
     }
-    for (int i = np; i < MAXP; i++) { maps.a[i] = maps.a[0]; maps.b[i] = maps.b[0]; maps.c[i] = maps.c[0]; maps.aux[i] = maps.aux[0]; grp.g[i].tile_begin = total; }
+    grp.sync = nullptr; grp.err = err;
+    if (deps != nullptr && sync != nullptr) {   // layer pipelining (launch_pipe): deps[i] < i
+        grp.sync = sync;
+        for (int i = 0; i < np; i++) {
+            if (deps[i] < 0) continue;
+            if (deps[i] >= i || grp.g[i].nt_m != grp.g[deps[i]].nt_m || grp.g[i].nt_m > SYNC_RB || (splits && splits[i] > 1)) return cudaErrorInvalidValue;
+            grp.g[i].dep = deps[i];
+            grp.g[i].need = grp.g[deps[i]].nt_n * TileCfg<TMT, BN>::EPW;
+            grp.g[deps[i]].signal = 1;
+        }
+    }
+    for (int i = np; i < MAXP; i++) { maps.a[i] = maps.a[0]; maps.b[i] = maps.b[0]; maps.c[i] = maps.c[0]; maps.aux[i] = maps.aux[0]; grp.g[i].tile_begin = total; grp.g[i].dep = -1; }
     grp.total_tiles = total;
     { static const char *e = getenv("GRX_TC_DEBUG"); grp.dbg = e ? atoi(e) : 0; }
     if (total == 0) return cudaSuccess;
@@ -617,6 +687,33 @@ inline cudaError_t launch_group(const Problem *ps, int np, const int *splits, cu
     if (bb == 128) return launch_cfg<A_KMAJ, B_KMAJ, EPI, 1, 128, 4>(ps, np, splits, st);
     if (bb == 64) return launch_cfg<A_KMAJ, B_KMAJ, EPI, 1, 64, 7>(ps, np, splits, st);
     return launch_cfg<A_KMAJ, B_KMAJ, EPI, 1, 32, 8>(ps, np, splits, st);
+}
+
+// Layer pipelining: several DEPENDENT layers (problem i reads, as its A operand, the output of problem deps[i] < i; equal M) in ONE persistent
+// launch.  The static tile list is ordered by problem, every CTA walks it in order, and a tile's loads wait on the row-block counter of the
+// producing problem — so layer l + 1 starts on the row blocks that are complete while the stragglers of layer l finish, and the launch gap,
+// the set-up, the first TMA round trip and the un-overlapped last epilogue are paid once per CHAIN instead of once per layer (measured: one
+// launch boundary ~ 6 us inside the update's graph).  One tile shape for the whole chain: 2 x 128 rows x 128 columns (bias / ELU epilogues),
+// 1 x 128 x 128 (ELU' epilogue).  Requires every CTA to be co-resident (grid <= SM count, one CTA per SM: true for this kernel).
+inline int &pipe_flag() {
+    static int on = [] { const char *e = getenv("GRX_LAYER_PIPE"); return e ? atoi(e) : 3; }();   // bit 0: forward chains, bit 1: input-gradient chains
+    return on;
+}
+template <bool A_KMAJ, bool B_KMAJ, int EPI>
+inline bool pipe_supported(const Problem *ps, int np, const int *deps) {
+    if (np < 2 || np > MAXP || pipe_flag() == 0) return false;
+    for (int i = 0; i < np; i++) {
+        if (!supported<A_KMAJ, B_KMAJ>(ps[i]) || ps[i].N < 65 || ps[i].M != ps[0].M) return false;
+        if (deps[i] >= i) return false;
+        if (EPI == 2 && ps[i].K < 64) return false;
+    }
+    return (ps[0].M + TM - 1) / TM <= SYNC_RB;
+}
+template <bool A_KMAJ, bool B_KMAJ, int EPI>
+inline cudaError_t launch_pipe(const Problem *ps, int np, const int *deps, int *sync, int *err, cudaStream_t st) {
+    if (EPI == 2) return launch_cfg<A_KMAJ, B_KMAJ, EPI, 1, 128, 4>(ps, np, nullptr, st, deps, sync, err);
+    if (ps[0].M > TM) return launch_cfg<A_KMAJ, B_KMAJ, EPI == 2 ? 0 : EPI, 2, 128, 3>(ps, np, nullptr, st, deps, sync, err);
+    return launch_cfg<A_KMAJ, B_KMAJ, EPI, 1, 128, 4>(ps, np, nullptr, st, deps, sync, err);
 }
 
 template <bool A_KMAJ, bool B_KMAJ, int EPI>

@@ -207,6 +207,24 @@ void dense_group(const GemmArgs *gs, const int *splits, int np, bool use_tc, cud
 template <bool A_KC, bool B_KC, int EPI>
 void dense(const GemmArgs &g, int splits, bool use_tc, cudaStream_t st) { dense_group<A_KC, B_KC, EPI>(&g, &splits, 1, use_tc, st); }
 
+// A CHAIN of dependent layers (gs[i] reads the output of gs[deps[i]], deps[i] < i or -1) as ONE layer-pipelined tcgen05 launch
+// (tc::launch_pipe).  Returns false when the chain does not qualify (then the caller launches layer by layer).
+template <bool A_KC, bool B_KC, int EPI>
+bool dense_pipe(const GemmArgs *gs, const int *deps, int np, bool use_tc, int *sync, int *err, cudaStream_t st) {
+    if (!use_tc || sync == nullptr || np > tc::MAXP) return false;
+    tc::Problem ps[tc::MAXP];
+    for (int i = 0; i < np; i++) {
+        const GemmArgs &g = gs[i];
+        tc::Problem &a = ps[i];
+        a.A = g.A; a.B = g.B; a.C = g.C; a.bias = g.bias; a.aux = g.aux; a.colsum = EPI == 2 ? g.bias_out : nullptr;
+        a.M = g.M; a.N = g.N; a.K = g.K; a.lda = g.lda; a.ldb = g.ldb; a.ldc = g.ldc;
+    }
+    if (!tc::pipe_supported<A_KC, B_KC, EPI>(ps, np, deps)) return false;
+    const cudaError_t e = tc::launch_pipe<A_KC, B_KC, EPI>(ps, np, deps, sync, err, st);
+    if (e != cudaSuccess && g_launch_err == cudaSuccess) g_launch_err = e;
+    return true;
+}
+
 // =========================================================================================================
 // Philox4x32-10 + Box-Muller for the rollout's Normal.sample() in fast mode (actor_critic_mlp.py:192-194)
 // =========================================================================================================
@@ -1093,6 +1111,7 @@ struct grx_ppo {
     bool comm_open = false;
     int apply_grid = 148;   // co-resident grid of apply_kernel (<= SM count)
     unsigned long long comm_budget_ns = 10000000000ull;   // cfg.comm_timeout_ms (GRX_COMM_TIMEOUT_MS overrides)
+    int *pipe_sync = nullptr;   // row-block counters of the layer-pipelined launches (tc::launch_pipe), zero between launches
     bool one_shot = true;   // phase 1 of the gradient all-reduce inside apply_kernel (GRX_COMM_ONESHOT=0: as a second allreduce_kernel launch; fixed for the object's lifetime)
     CommDev comm;
     std::vector<void *> peer_maps;
@@ -1171,6 +1190,7 @@ extern "C" int grx_ppo_create(const grx_ppo_cfg *cfg, int32_t device, grx_ppo **
     PALLOC(p->xa, MR * p->Opad * 4); PALLOC(p->xc, MR * p->Ppad * 4); PALLOC(p->mb_act, MR * p->A * 4); PALLOC(p->mb_val, MR * 4);
     PALLOC(p->mb_ret, MR * 4); PALLOC(p->mb_adv, MR * 4); PALLOC(p->mb_logp, MR * 4); PALLOC(p->mb_mu, MR * p->A * 4);
     PALLOC(p->mb_sigma, MR * p->A * 4); PALLOC(p->last_values, (size_t)p->N * 4);
+    PALLOC(p->pipe_sync, (size_t)tc::SYNC_INTS * 4);
     p->mbin[0] = {p->xa, p->xc, p->mb_act, p->mb_val, p->mb_ret, p->mb_adv, p->mb_logp, p->mb_mu, p->mb_sigma};
     {   // second set (only minibatch rows)
         const size_t Bm = (size_t)p->B;
@@ -1290,14 +1310,23 @@ static void mlp_forward(grx_ppo *p, const NetIO *io, int nn, int M, int nlayers,
             l0 = 3;
         }
     }
+    auto layer_args = [&](int l, int i, GemmArgs &g) {
+        const Net &net = *io[i].net;
+        memset(&g, 0, sizeof(GemmArgs));
+        g.A = l == 0 ? io[i].x : io[i].h[l - 1]; g.B = p->params + net.w[l]; g.C = io[i].h[l]; g.bias = p->params + net.b[l];
+        g.M = M; g.N = net.dims[l + 1]; g.K = net.dims[l]; g.lda = l == 0 ? io[i].ldx : net.dims[l]; g.ldb = net.ld[l]; g.ldc = g.N;
+    };
+    const int nhid = nlayers < 3 ? nlayers : 3;   // layers with the bias + ELU epilogue
+    if (l0 == 0 && nhid >= 2 && nn * nhid <= tc::MAXP && (tc::pipe_flag() & 1)) {   // the hidden layers of all networks as ONE layer-pipelined launch (tc::launch_pipe)
+        GemmArgs g[tc::MAXP];
+        int deps[tc::MAXP];
+        for (int l = 0; l < nhid; l++)
+            for (int i = 0; i < nn; i++) { layer_args(l, i, g[l * nn + i]); deps[l * nn + i] = l == 0 ? -1 : (l - 1) * nn + i; }
+        if (dense_pipe<true, true, 1>(g, deps, nn * nhid, p->cfg.use_tensor_cores != 0, p->pipe_sync, &p->ctl->chain_error, st)) l0 = nhid;
+    }
     for (int l = l0; l < nlayers; l++) {
         GemmArgs g[2];
-        for (int i = 0; i < nn; i++) {
-            const Net &net = *io[i].net;
-            memset(&g[i], 0, sizeof(GemmArgs));
-            g[i].A = l == 0 ? io[i].x : io[i].h[l - 1]; g[i].B = p->params + net.w[l]; g[i].C = io[i].h[l]; g[i].bias = p->params + net.b[l];
-            g[i].M = M; g[i].N = net.dims[l + 1]; g[i].K = net.dims[l]; g[i].lda = l == 0 ? io[i].ldx : net.dims[l]; g[i].ldb = net.ld[l]; g[i].ldc = g[i].N;
-        }
+        for (int i = 0; i < nn; i++) layer_args(l, i, g[i]);
         if (l < 3) dense_group<true, true, 1>(g, nullptr, nn, p->cfg.use_tensor_cores != 0, st);
         else dense_group<true, true, 0>(g, nullptr, nn, p->cfg.use_tensor_cores != 0, st);
     }
@@ -1312,14 +1341,29 @@ static void launch_allreduce_phase(grx_ppo *p, int phase, cudaStream_t st) {
 }
 static void mlp_backward(grx_ppo *p, const NetIO *io, int nn, float *grads, int M, int top, cudaStream_t st, bool overlap_comm = false) {
     const bool tcu = p->cfg.use_tensor_cores != 0;
-    for (int l = top; l >= 1; l--) {
-        GemmArgs g[2];
-        for (int i = 0; i < nn; i++) {
-            const Net &net = *io[i].net;
-            memset(&g[i], 0, sizeof(GemmArgs));
-            g[i].A = io[i].d[l]; g[i].B = p->params + net.w[l]; g[i].C = io[i].d[l - 1]; g[i].aux = io[i].h[l - 1]; g[i].bias_out = grads + net.b[l - 1];
-            g[i].M = M; g[i].N = net.dims[l]; g[i].K = net.dims[l + 1]; g[i].lda = net.dims[l + 1]; g[i].ldb = net.ld[l]; g[i].ldc = net.dims[l];
+    auto dx_args = [&](int l, int i, GemmArgs &g) {
+        const Net &net = *io[i].net;
+        memset(&g, 0, sizeof(GemmArgs));
+        g.A = io[i].d[l]; g.B = p->params + net.w[l]; g.C = io[i].d[l - 1]; g.aux = io[i].h[l - 1]; g.bias_out = grads + net.b[l - 1];
+        g.M = M; g.N = net.dims[l]; g.K = net.dims[l + 1]; g.lda = net.dims[l + 1]; g.ldb = net.ld[l]; g.ldc = net.dims[l];
+    };
+    int ltop = top;
+    if (top >= 2 && top <= 3 && nn * 2 <= tc::MAXP && (tc::pipe_flag() & 2)) {   // the two widest input-gradient layers (l = 2 -> 1) as ONE layer-pipelined launch; l = 3 (heads, K < 64) stays apart
+        if (top == 3) {
+            GemmArgs g3[2];
+            for (int i = 0; i < nn; i++) dx_args(3, i, g3[i]);
+            dense_group<true, false, 2>(g3, nullptr, nn, tcu, st);
         }
+        GemmArgs g[tc::MAXP];
+        int deps[tc::MAXP];
+        for (int s = 0; s < 2; s++)
+            for (int i = 0; i < nn; i++) { dx_args(2 - s, i, g[s * nn + i]); deps[s * nn + i] = s == 0 ? -1 : i; }
+        if (dense_pipe<true, false, 2>(g, deps, nn * 2, tcu, p->pipe_sync, &p->ctl->chain_error, st)) ltop = 0;
+        else if (top == 3) ltop = 2;
+    }
+    for (int l = ltop; l >= 1; l--) {
+        GemmArgs g[2];
+        for (int i = 0; i < nn; i++) dx_args(l, i, g[i]);
         dense_group<true, false, 2>(g, nullptr, nn, tcu, st);
     }
     GemmArgs g[8];
@@ -1668,6 +1712,14 @@ extern "C" int grx_ppo_act_inference(grx_ppo *p, const float *d_obs, int32_t n, 
 extern "C" int grx_ppo_debug_fused(int32_t fwd_chain) {
     const int old = tc::chain::fwd_flag();
     if (fwd_chain >= 0) tc::chain::fwd_flag() = fwd_chain;
+    return old;
+}
+
+// Test / profiling: layer-pipelined dense-layer launches (tc::launch_pipe) on / off at run time; returns the previous setting.  A captured update
+// graph keeps the setting it was captured with.
+extern "C" int grx_ppo_debug_pipe(int32_t on) {
+    const int old = tc::pipe_flag();
+    if (on >= 0) tc::pipe_flag() = on;
     return old;
 }
 
