@@ -200,7 +200,7 @@ def test_layer_pipelined_launch_equals_layerwise(M, store):
     res = {}
     old_fused = lib.grx_ppo_debug_fused(0)
     try:
-        for pipe in (1, 0, 1):
+        for pipe in (3, 0, 3):   # 3 = forward AND input-gradient chains pipelined
             old = lib.grx_ppo_debug_pipe(pipe)
             alg.step = 0
             if not store:
@@ -222,12 +222,12 @@ def test_layer_pipelined_launch_equals_layerwise(M, store):
     finally:
         lib.grx_ppo_debug_fused(old_fused)
     tol = 1e-6 if not store else 1e-5
-    for run in res[1]:   # both pipelined runs (the second one starts from the counters the first one left behind) vs the layerwise run
+    for run in res[3]:   # both pipelined runs (the second one starts from the counters the first one left behind) vs the layerwise run
         for x, y in zip(run, res[0][0]):
             scale = float(y.abs().max()) + 1e-30
             assert float((x - y).abs().max()) <= tol * scale, (M, store, float((x - y).abs().max()), scale)
     if not store:
         with torch.no_grad():
             mu = ac.actor.to_module()(obs.cpu())
-        np.testing.assert_allclose(res[1][0][1].cpu().numpy(), mu.numpy(), rtol=0, atol=6e-3 * float(mu.abs().max()))
+        np.testing.assert_allclose(res[3][0][1].cpu().numpy(), mu.numpy(), rtol=0, atol=6e-3 * float(mu.abs().max()))
     alg.close()

@@ -692,11 +692,14 @@ inline cudaError_t launch_group(const Problem *ps, int np, const int *splits, cu
 // Layer pipelining: several DEPENDENT layers (problem i reads, as its A operand, the output of problem deps[i] < i; equal M) in ONE persistent
 // launch.  The static tile list is ordered by problem, every CTA walks it in order, and a tile's loads wait on the row-block counter of the
 // producing problem — so layer l + 1 starts on the row blocks that are complete while the stragglers of layer l finish, and the launch gap,
-// the set-up, the first TMA round trip and the un-overlapped last epilogue are paid once per CHAIN instead of once per layer (measured: one
-// launch boundary ~ 6 us inside the update's graph).  One tile shape for the whole chain: 2 x 128 rows x 128 columns (bias / ELU epilogues),
+// the set-up, the first TMA round trip and the un-overlapped last epilogue are paid once per CHAIN instead of once per layer.  Measured gain: small
+// (see pipe_flag) — with programmatic dependent launch the per-layer boundary is already mostly hidden, and the chain's own tail (the last tiles
+// of layer l + 1 wait for the last tiles of layer l) replaces it.  One tile shape for the whole chain: 2 x 128 rows x 128 columns (bias / ELU epilogues),
 // 1 x 128 x 128 (ELU' epilogue).  Requires every CTA to be co-resident (grid <= SM count, one CTA per SM: true for this kernel).
 inline int &pipe_flag() {
-    static int on = [] { const char *e = getenv("GRX_LAYER_PIPE"); return e ? atoi(e) : 3; }();   // bit 0: forward chains, bit 1: input-gradient chains
+    // bit 0: forward chains, bit 1: input-gradient chains.  Measured per minibatch of the update graph (profiles/r2r_pipe_variants.txt): none 176.4 us,
+    // input-gradient chain 175.0, forward chain 180.5 (its one tile shape costs layer 2 the 2 x 256 macro tile), both 178.8 -> default 2.
+    static int on = [] { const char *e = getenv("GRX_LAYER_PIPE"); return e ? atoi(e) : 2; }();
     return on;
 }
 template <bool A_KMAJ, bool B_KMAJ, int EPI>
