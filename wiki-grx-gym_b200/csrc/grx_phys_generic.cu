@@ -39,7 +39,7 @@ namespace {
 constexpr int GB = 36, GD = 32, GV = 38, GS = 32, GL = 48, GP = 64, GDEPTH = 12;
 constexpr int GKC = 8, GKS = 4, GKL = 8, GROWS = 3 * (GKC + GKS) + GKL;   // 44 constraint rows at most
 constexpr int GPITCH = 41;            // row pitch of J / Y (odd: per-lane rows stay conflict-free)
-constexpr int GWARPS = 7;             // warps (robots) per CTA
+constexpr int GWARPS = 10;            // warps (robots) per CTA at most: 10 x 22.2 KB of workspace fit the 227 KB of an SM (4096 robots on 148 SMs = 3 waves)
 constexpr unsigned FULL = 0xffffffffu;
 
 struct GModel {   // device copy of the model, in global memory (read through the read-only path)
@@ -80,20 +80,33 @@ struct GArgs {
     unsigned long long *sig;
 };
 
+// Lower triangle of the symmetric (nv x nv) mass matrix / its Cholesky factor, packed by rows: element (i, j), i >= j
+__device__ __forceinline__ int tri(int i, int j) { return ((i * (i + 1)) >> 1) + j; }
+
 struct alignas(16) GWS {
     float root[16], q[GD], qd[GD], tau[GD], bin[12];
-    float R[GB][9], o[GB][3], a[GB][3], c[GB][3], w[GB][3], vo[GB][3], al[GB][3], ao[GB][3], Iw[GB][6];
-    float sub[GB][16];                   // per body, then subtree: mass, first moment 3, inertia 6, bias force 3, bias moment 3
-    float Sl[GB][3], Sa[GB][3], Ff[GB][3], Fn[GB][3];
-    float M[GV][GV + 1];
+    // Lifetimes inside a substep: the kinematics arrays are dead once the constraint Jacobians have been built, the composite / joint-space
+    // scratch once the mass matrix exists; Y = M^-1 J^T is written after both (the right-hand side row Y[GROWS - 1] lands on `sub`, which is
+    // dead after g_mass_and_bias) -> they share storage (9.2 KB vs 7.2 KB).
+    union {
+        struct {
+            float R[GB][9], o[GB][3], a[GB][3], c[GB][3], w[GB][3], vo[GB][3], al[GB][3], ao[GB][3], Iw[GB][6];
+            float sub[GB][16];                   // per body, then subtree: mass, first moment 3, inertia 6, bias force 3, bias moment 3
+            float Sl[GB][3], Sa[GB][3], Ff[GB][3], Fn[GB][3];
+        };
+        float Y[GROWS][GPITCH];
+    };
+    float M[GV * (GV + 1) / 2];           // packed lower triangle, see tri()
     float h[GV + 2], u[GV + 2];
-    float J[GROWS][GPITCH], Y[GROWS][GPITCH];
+    float J[GROWS][GPITCH];
     float Ad[GROWS], bias[GROWS], lam[GROWS];
     float cfr[GKC + GKS][9], cpt[GKC + GKS][4];
     int cbody[GKC + GKS], cbody2[GKC + GKS], clink[GKC + GKS], clink2[GKC + GKS];
     float cf[GL * 3];
     float facc[4][8];                    // per foot: sum |F|, sum |v| 3, sum |w| 3
 };
+static_assert(sizeof(float) * GB * (9 + 7 * 3 + 6) <= sizeof(float) * (GROWS - 1) * GPITCH, "the right-hand side row Y[GROWS - 1] must not land on the kinematics arrays (live until the Jacobians are built)");
+static_assert(GWARPS * sizeof(GWS) <= 232448, "shared memory per CTA");
 
 __device__ __forceinline__ void cross3(const float *a, const float *b, float *o) {
     float x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
@@ -194,7 +207,7 @@ __device__ void g_kinematics(GWS &s, const GModel &m, int lane) {
 // ---- mass matrix (internal order: joints, base linear, base angular) + bias vector (oracle mass_and_bias())
 __device__ void g_mass_and_bias(GWS &s, const GModel &m, float gravity, int lane) {
     const int nb = m.nb, nd = m.nd, nv = nd + 6;
-    for (int i = lane; i < GV * (GV + 1); i += 32) (&s.M[0][0])[i] = 0.0f;
+    for (int i = lane; i < GV * (GV + 1) / 2; i += 32) s.M[i] = 0.0f;
     for (int b = lane; b < nb; b += 32) {
         const float mass = b == 0 ? s.bin[0] : m.mass[b];
         float r[3], rc[3];
@@ -242,12 +255,12 @@ __device__ void g_mass_and_bias(GWS &s, const GModel &m, float gravity, int lane
     for (int j = 1 + lane; j < nb; j += 32) {
         for (int i = j; i >= 1; i = m.parent[i]) {   // i ancestor-or-self of j
             const float v = dot3(s.Sl[i], s.Ff[j]) + dot3(s.Sa[i], s.Fn[j]);
-            s.M[i - 1][j - 1] = v; s.M[j - 1][i - 1] = v;
+            s.M[tri(j - 1, i - 1)] = v;   // i is an ancestor of (or) j: i <= j
         }
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-            s.M[nd + k][j - 1] = s.Ff[j][k]; s.M[j - 1][nd + k] = s.Ff[j][k];
-            s.M[nd + 3 + k][j - 1] = s.Fn[j][k]; s.M[j - 1][nd + 3 + k] = s.Fn[j][k];
+            s.M[tri(nd + k, j - 1)] = s.Ff[j][k];
+            s.M[tri(nd + 3 + k, j - 1)] = s.Fn[j][k];
         }
     }
     if (lane == 0) {
@@ -255,13 +268,13 @@ __device__ void g_mass_and_bias(GWS &s, const GModel &m, float gravity, int lane
         const float mm = ci[0], *hh = ci + 1, *I = ci + 4;
         const int L = nd, A = nd + 3;
         const float hx[9] = {0, -hh[2], hh[1], hh[2], 0, -hh[0], -hh[1], hh[0], 0};
-        for (int k = 0; k < 3; k++) s.M[L + k][L + k] = mm;
+        for (int k = 0; k < 3; k++) s.M[tri(L + k, L + k)] = mm;
         for (int i = 0; i < 3; i++)
-            for (int j = 0; j < 3; j++) { s.M[A + i][L + j] = hx[3 * i + j]; s.M[L + j][A + i] = hx[3 * i + j]; }
-        s.M[A][A] = I[0]; s.M[A + 1][A + 1] = I[1]; s.M[A + 2][A + 2] = I[2];
-        s.M[A][A + 1] = s.M[A + 1][A] = I[3];
-        s.M[A][A + 2] = s.M[A + 2][A] = I[4];
-        s.M[A + 1][A + 2] = s.M[A + 2][A + 1] = I[5];
+            for (int j = 0; j < 3; j++) s.M[tri(A + i, L + j)] = hx[3 * i + j];
+        s.M[tri(A, A)] = I[0]; s.M[tri(A + 1, A + 1)] = I[1]; s.M[tri(A + 2, A + 2)] = I[2];
+        s.M[tri(A + 1, A)] = I[3];
+        s.M[tri(A + 2, A)] = I[4];
+        s.M[tri(A + 2, A + 1)] = I[5];
         for (int k = 0; k < 6; k++) s.h[L + k] = ci[10 + k];
     }
     (void)nv;
@@ -271,13 +284,14 @@ __device__ void g_mass_and_bias(GWS &s, const GModel &m, float gravity, int lane
 // ---- dense Cholesky in shared memory (lower factor in place), right-looking; lane owns rows lane, lane + 32
 __device__ void g_cholesky(GWS &s, int n, int lane) {
     for (int k = 0; k < n; k++) {
-        const float piv = sqrtf(s.M[k][k]);
+        const float piv = sqrtf(s.M[tri(k, k)]);
         __syncwarp();
-        for (int i = k + lane; i < n; i += 32) s.M[i][k] = i == k ? piv : s.M[i][k] / piv;
+        for (int i = k + lane; i < n; i += 32) s.M[tri(i, k)] = i == k ? piv : s.M[tri(i, k)] / piv;
         __syncwarp();
         for (int i = k + 1 + lane; i < n; i += 32) {
-            const float lik = s.M[i][k];
-            for (int j = k + 1; j <= i; j++) s.M[i][j] -= lik * s.M[j][k];
+            const float lik = s.M[tri(i, k)];
+            float *row = s.M + tri(i, 0);
+            for (int j = k + 1; j <= i; j++) row[j] -= lik * s.M[tri(j, k)];
         }
         __syncwarp();
     }
@@ -286,13 +300,14 @@ __device__ void g_cholesky(GWS &s, int n, int lane) {
 __device__ void g_chol_solve(const GWS &s, int n, float *x) {
     for (int i = 0; i < n; i++) {
         float t = x[i];
-        for (int p = 0; p < i; p++) t -= s.M[i][p] * x[p];
-        x[i] = t / s.M[i][i];
+        const float *row = s.M + tri(i, 0);
+        for (int p = 0; p < i; p++) t -= row[p] * x[p];
+        x[i] = t / row[i];
     }
     for (int i = n - 1; i >= 0; i--) {
         float t = x[i];
-        for (int p = i + 1; p < n; p++) t -= s.M[p][i] * x[p];
-        x[i] = t / s.M[i][i];
+        for (int p = i + 1; p < n; p++) t -= s.M[tri(p, i)] * x[p];
+        x[i] = t / s.M[tri(i, i)];
     }
 }
 
@@ -562,7 +577,7 @@ __global__ void __launch_bounds__(GWARPS * 32, 1) physg_step_kernel(const __grid
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     GWS &s = *reinterpret_cast<GWS *>(smem_raw + (size_t)warp * sizeof(GWS));
     const GModel &m = *A.m;
-    const int e = blockIdx.x * GWARPS + warp;
+    const int e = blockIdx.x * (blockDim.x >> 5) + warp;
     if (e >= A.N) return;
     const int nd = m.nd, nl = m.nl, nf = m.nf;
     if (lane < 13) s.root[lane] = A.root[(size_t)e * 13 + lane];
@@ -634,7 +649,7 @@ __global__ void __launch_bounds__(GWARPS * 32, 1) envg_step_kernel(const __grid_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     GWS &s = *reinterpret_cast<GWS *>(smem_raw + (size_t)warp * sizeof(GWS));
     const GModel &m = *G.m;
-    const int e = blockIdx.x * GWARPS + warp;
+    const int e = blockIdx.x * (blockDim.x >> 5) + warp;
     if (blockIdx.x == 0 && threadIdx.x < ACC_W) A.episode_accum_next[threadIdx.x] = 0.f;   // nobody accumulates into the next slot during this launch
     if (e >= A.N) return;
     const int nd = L.nd;
@@ -674,7 +689,7 @@ __global__ void __launch_bounds__(GWARPS * 32, 1) envg_step_kernel(const __grid_
                 g_mass_and_bias(s, m, G.cfg.gravity, lane);
                 const int nv = nd + 6;
                 if (e == A.dbg_index) {
-                    for (int i = lane; i < nv * nv; i += 32) A.dbg_M[i] = s.M[i / nv][i % nv];
+                    for (int i = lane; i < nv * nv; i += 32) { const int r = i / nv, c2 = i % nv; A.dbg_M[i] = s.M[r >= c2 ? tri(r, c2) : tri(c2, r)]; }
                     for (int i = lane; i < nv; i += 32) A.dbg_h[i] = s.h[i];
                 }
                 return;
@@ -782,6 +797,14 @@ __global__ void __launch_bounds__(256) envg_reset_kernel(const __grid_constant__
 // =========================================================================================================
 // Host side
 // =========================================================================================================
+// One CTA per SM is resident (shared memory): take the number of waves of the widest CTA and shrink the CTA until those waves are evenly filled
+static int g_warps_per_cta(int N) {
+    static int sms = 0;
+    if (sms == 0) { int dev = 0; cudaGetDevice(&dev); if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148; }
+    const int waves = (N + GWARPS * sms - 1) / (GWARPS * sms);
+    int w = (N + waves * sms - 1) / (waves * sms);
+    return w < 1 ? 1 : (w > GWARPS ? GWARPS : w);
+}
 static bool gmodel_fits(const grx_model_desc *md, int npairs) {
     return !(md->nb < 1 || md->nb > GB || md->nd != md->nb - 1 || md->nd > GD || md->nl > GL || md->ns > GS || md->nf > 4 || npairs > GP);
 }
@@ -895,7 +918,8 @@ extern "C" int grx_physg_step(grx_physg *p, float *d_root, float *d_dof_pos, flo
     A.torques = d_torques; A.link_state = d_link_state; A.contact_force = d_contact_force; A.avg_ff = d_avg_foot_force;
     A.avg_fl = d_avg_foot_linvel; A.avg_fa = d_avg_foot_angvel; A.sig = reinterpret_cast<unsigned long long *>(d_active_sig);
     grx_count_launch();
-    physg_step_kernel<<<(p->N + GWARPS - 1) / GWARPS, GWARPS * 32, GWARPS * sizeof(GWS), (cudaStream_t)stream>>>(A);
+    const int wpc = g_warps_per_cta(p->N);
+    physg_step_kernel<<<(p->N + wpc - 1) / wpc, wpc * 32, wpc * sizeof(GWS), (cudaStream_t)stream>>>(A);
     CK(cudaGetLastError());
     return GRX_OK;
 }
@@ -969,10 +993,10 @@ int grx::envg_set_self_collision(void *h, const int32_t *pairs, int32_t npairs, 
 int grx::envg_launch_step(void *h, const EnvArgs &A, const grx_task_cfg &cfg, const LayR &L, bool phys, cudaStream_t st) {
     EnvG *g = static_cast<EnvG *>(h);
     const GArgs G = envg_args(g, A, cfg);
-    const int grid = (A.N + GWARPS - 1) / GWARPS;
+    const int wpc = g_warps_per_cta(A.N), grid = (A.N + wpc - 1) / wpc;
     grx_count_launch();
-    if (phys) envg_step_kernel<true><<<grid, GWARPS * 32, GWARPS * sizeof(GWS), st>>>(A, cfg, G, L);
-    else envg_step_kernel<false><<<grid, GWARPS * 32, GWARPS * sizeof(GWS), st>>>(A, cfg, G, L);
+    if (phys) envg_step_kernel<true><<<grid, wpc * 32, wpc * sizeof(GWS), st>>>(A, cfg, G, L);
+    else envg_step_kernel<false><<<grid, wpc * 32, wpc * sizeof(GWS), st>>>(A, cfg, G, L);
     CK(cudaGetLastError());
     return GRX_OK;
 }

@@ -720,8 +720,16 @@ __global__ void __launch_bounds__(HEADS_THREADS, 1) ppo_heads_kernel(const Heads
     if (own) { atomicAdd(&agba[lane], gba); atomicAdd(&agsd[lane], gsd); }
     if (lane == 0) { atomicAdd(&amisc[0], gbc); atomicAdd(&amisc[1], kl_s); atomicAdd(&amisc[2], cnt_s); atomicAdd(&amisc[3], surr_s); atomicAdd(&amisc[4], vl_s); }
     __syncthreads();
-    for (int i = threadIdx.x; i < NA * H; i += blockDim.x) atomicAdd(&a.gW3a[i], aWa[i]);
-    for (int i = threadIdx.x; i < H; i += blockDim.x) { atomicAdd(&a.gW3c[i], aWc[i]); atomicAdd(&a.gb2a[i], ab2a[i]); atomicAdd(&a.gb2c[i], ab2c[i]); }
+    // one vector reduction (red.global.add.v4.f32, sm_90+) per four elements: 148 CTAs x 1664 elements would otherwise be 246 K scalar atomics
+    // on 1664 addresses; every destination starts on a 16-byte boundary (layout_net) and H % 4 == 0
+    auto red4 = [](float *dst, const float *src) {
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(src[0]), "f"(src[1]), "f"(src[2]), "f"(src[3]) : "memory");
+    };
+    for (int i = threadIdx.x * 4; i < NA * H; i += blockDim.x * 4) red4(a.gW3a + i, aWa + i);
+    for (int i = threadIdx.x * 4; i < 3 * H; i += blockDim.x * 4) {
+        const int k = i / H, j = i % H;
+        red4((k == 0 ? a.gW3c : k == 1 ? a.gb2a : a.gb2c) + j, (k == 0 ? aWc : k == 1 ? ab2a : ab2c) + j);
+    }
     if (threadIdx.x < NA) {
         atomicAdd(&a.gb3a[threadIdx.x], agba[threadIdx.x]);
         float gs = agsd[threadIdx.x];
