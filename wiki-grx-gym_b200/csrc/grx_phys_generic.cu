@@ -499,25 +499,40 @@ __device__ void g_substep(GWS &s, const GModel &m, const GArgs &A, int lane, flo
     __syncwarp();
     for (int i = lane; i < nv; i += 32) s.u[i] = (i < nd ? s.qd[i] : s.root[7 + i - nd]) + dt * rhs[i];
     __syncwarp();
-    // ---- projected Gauss-Seidel in velocity space (the oracle's sweep: contacts — normal, then 2 friction rows — then the limits)
-    for (int it = 0; it < cfg.solver_iters; it++) {
-        for (int r = 0; r < nrow; r++) {
-            float v = 0.f;
-            for (int i = lane; i < nv; i += 32) v += s.J[r][i] * s.u[i];
-            v = warp_sum(v);
-            const float l0 = s.lam[r];
-            float ln = l0 - (v - s.bias[r]) / s.Ad[r];
-            if (r < 3 * ncon) {
-                const int c = r / 3, k = r % 3;
-                if (k == 0) ln = fmaxf(ln, 0.f);
-                else { const float lim = (s.cbody2[c] >= 0 ? mu_env : mu) * s.lam[3 * c]; ln = fminf(fmaxf(ln, -lim), lim); }
-            } else ln = fmaxf(ln, 0.f);
-            const float dl = ln - l0;
-            __syncwarp();
-            if (lane == 0) s.lam[r] = ln;
-            for (int i = lane; i < nv; i += 32) s.u[i] += s.Y[r][i] * dl;
-            __syncwarp();
+    // ---- projected Gauss-Seidel in velocity space (the oracle's sweep: contacts — normal, then 2 friction rows — then the limits).  The velocity
+    // vector lives in registers (lane i: u[i] and, for i < nv - 32, u[32 + i]); every lane computes the same multiplier update from the
+    // warp-uniform row product, so lam needs no cross-lane hand-over (each lane reads back its own identical store) and the sweep runs without
+    // a single warp barrier; the next row's J / Y elements are fetched while the butterfly of the current row is in flight.
+    {
+        const bool hi = lane < nv - 32;
+        float u0 = lane < nv ? s.u[lane] : 0.f, u1 = hi ? s.u[32 + lane] : 0.f;
+        float j0 = 0.f, j1 = 0.f, y0 = 0.f, y1 = 0.f;
+        if (nrow > 0) { j0 = lane < nv ? s.J[0][lane] : 0.f; j1 = hi ? s.J[0][32 + lane] : 0.f; y0 = lane < nv ? s.Y[0][lane] : 0.f; y1 = hi ? s.Y[0][32 + lane] : 0.f; }
+        for (int it = 0; it < cfg.solver_iters; it++) {
+            float lam_n = 0.f;   // multiplier of the current contact's normal row (bounds its two friction rows)
+            for (int r = 0; r < nrow; r++) {
+                float v = j0 * u0 + j1 * u1;
+                const float cy0 = y0, cy1 = y1;
+                const int rn = r + 1 < nrow ? r + 1 : 0;   // next row (wraps to the first row of the next sweep)
+                j0 = lane < nv ? s.J[rn][lane] : 0.f; j1 = hi ? s.J[rn][32 + lane] : 0.f;
+                y0 = lane < nv ? s.Y[rn][lane] : 0.f; y1 = hi ? s.Y[rn][32 + lane] : 0.f;
+                v = warp_sum(v);
+                const float l0 = s.lam[r];
+                float ln = l0 - (v - s.bias[r]) / s.Ad[r];
+                if (r < 3 * ncon) {
+                    const int c = r / 3, k = r - 3 * c;
+                    if (k == 0) { ln = fmaxf(ln, 0.f); lam_n = ln; }
+                    else { const float lim = (s.cbody2[c] >= 0 ? mu_env : mu) * lam_n; ln = fminf(fmaxf(ln, -lim), lim); }
+                } else ln = fmaxf(ln, 0.f);
+                const float dl = ln - l0;
+                s.lam[r] = ln;
+                u0 += cy0 * dl; u1 += cy1 * dl;
+            }
         }
+        __syncwarp();
+        if (lane < nv) s.u[lane] = u0;
+        if (hi) s.u[32 + lane] = u1;
+        __syncwarp();
     }
     // ---- net contact force per URDF link (world frame, on the body) = impulse / dt; a self-contact reacts on its second link
     for (int i = lane; i < m.nl * 3; i += 32) s.cf[i] = 0.f;
