@@ -96,7 +96,7 @@ def smoke_check(np_, torch):
     print("smoke: PPO minibatch (tcgen05 TF32 layers, fused heads, backward) on cuda:0 matches the CPU oracle")
 
 
-def ppo_gradient_check(np_, torch, use_tc, atol):
+def ppo_gradient_check(np_, torch, use_tc, atol, dims=(39, 168, 10)):
     """One PPO minibatch (gather -> forward -> fused heads / losses -> backward) at the registered network width through the C ABI,
     every gradient tensor and the KL / loss sums vs the hand-derived CPU oracle (oracle/ppo_oracle.py)."""
     import ctypes as C
@@ -106,7 +106,7 @@ def ppo_gradient_check(np_, torch, use_tc, atol):
     from oracle import ppo_oracle as po
     torch.manual_seed(5)
     tc = make_train_cfg()
-    O, P, A, N, T = 39, 168, 10, 256, 8
+    (O, P, A), N, T = dims, 256, 8   # dims = (39, 168, 10) registered lower-limb task; (105, 234, 32) full-body task (un-fused output heads)
     ac = ActorCriticMLP(O, P, A, **tc["policy"])
     alg = PPO(ac, device="cuda:0", use_tensor_cores=use_tc, **dict(tc["algorithm"], num_mini_batches=2, num_learning_epochs=1))
     alg.init_storage(N, T)

@@ -119,6 +119,15 @@ def test_minibatch_gradients_match_oracle_full_width():
     ppo_gradient_check(np, torch, use_tc=1, atol=6e-3)
 
 
+def test_minibatch_gradients_match_oracle_full_body_width():
+    """The same at the full-body task's shapes (actor 105 -> 512 -> 256 -> 128 -> 32, critic 234 -> ... -> 1): the un-fused output-head path —
+    hidden layers and their weight gradients on the tensor cores, the narrow heads (N = 32 / 1, K = 32 / 1) on the fp32 SIMT kernel within the
+    same grouped calls."""
+    from parity_util import ppo_gradient_check
+    ppo_gradient_check(np, torch, use_tc=0, atol=3e-4, dims=(105, 234, 32))
+    ppo_gradient_check(np, torch, use_tc=1, atol=6e-3, dims=(105, 234, 32))
+
+
 def test_gae_full_size_matches_oracle():
     """T = 64, N = 4096 (BASELINE config): warp-shuffle scan == the sequential reverse loop of base_storage.py:128-141."""
     from grx_b200.ppo import PPO, ActorCriticMLP

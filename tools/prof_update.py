@@ -14,10 +14,11 @@ nmb = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 use_tc = int(sys.argv[4]) if len(sys.argv) > 4 else 1
 tc = make_train_cfg()
 torch.manual_seed(1)
-ac = ActorCriticMLP(39, 168, 10, **tc["policy"])
+O, P, A = (int(x) for x in os.environ.get("GRX_PROF_DIMS", "39,168,10").split(","))   # e.g. 105,234,32 = the full-body task
+ac = ActorCriticMLP(O, P, A, **tc["policy"])
 alg = PPO(ac, device="cuda:0", use_tensor_cores=use_tc, **tc["algorithm"])
 alg.init_storage(N, T)
-obs, cobs = torch.randn(N, 39, device="cuda"), torch.randn(N, 168, device="cuda")
+obs, cobs = torch.randn(N, O, device="cuda"), torch.randn(N, P, device="cuda")
 for s in range(T):
     alg.act(obs, cobs)
     alg.process_env_step(torch.randn(N, device="cuda") * 0.1, torch.rand(N, device="cuda") < 0.01, {})

@@ -160,33 +160,37 @@ thread_local cudaError_t g_launch_err = cudaSuccess;   // first failed tensor-co
 // allows, else the fp32 SIMT kernel per problem.
 template <bool A_KC, bool B_KC, int EPI>
 void dense_group(const GemmArgs *gs, const int *splits, int np, bool use_tc, cudaStream_t st) {
+    // members the tensor-core kernel takes go into ONE grouped launch; the others (narrow output heads of a non-registered policy, unaligned
+    // shapes) run on the fp32 SIMT kernel one by one — a single narrow member must not drag the whole group off the tensor cores
+    bool on_tc[tc::MAXP > 8 ? tc::MAXP : 8] = {false};
     if (use_tc && np <= tc::MAXP) {
         tc::Problem ps[tc::MAXP];
-        bool ok = true;
+        int sp_tc[tc::MAXP], ntc = 0;
         for (int i = 0; i < np; i++) {
             const GemmArgs &g = gs[i];
-            tc::Problem &a = ps[i];
+            tc::Problem a;
             a.A = g.A; a.B = g.B; a.C = g.C; a.bias = g.bias; a.aux = g.aux; a.colsum = EPI == 2 ? g.bias_out : nullptr;
             a.M = g.M; a.N = g.N; a.K = g.K; a.lda = g.lda; a.ldb = g.ldb; a.ldc = g.ldc;
-            ok = ok && tc::supported<A_KC, B_KC>(a);
+            bool ok = tc::supported<A_KC, B_KC>(a);
             if (EPI == 3) ok = ok && g.M >= 64 && g.N >= 32;   // tiny weight gradients (the output heads) stay on the SIMT kernel
             if (EPI == 2) ok = ok && g.K >= 64;
-        }
-        if (ok) {
-            for (int i = 0; i < np; i++) {
-                const GemmArgs &g = gs[i];
-                if (EPI == 3 && g.bias_out) {
-                    const int rpb = 512;
-                    grx_count_launch();
-                    colsum_kernel<<<dim3((g.M + 31) / 32, (g.K + rpb - 1) / rpb), 256, 0, st>>>(g.A, g.K, g.M, g.lda, rpb, g.bias_out);   // A = dY [rows, out]
-                }
+            if (!ok) continue;
+            on_tc[i] = true;
+            sp_tc[ntc] = splits ? splits[i] : 1;
+            ps[ntc++] = a;
+            if (EPI == 3 && g.bias_out) {
+                const int rpb = 512;
+                grx_count_launch();
+                colsum_kernel<<<dim3((g.M + 31) / 32, (g.K + rpb - 1) / rpb), 256, 0, st>>>(g.A, g.K, g.M, g.lda, rpb, g.bias_out);   // A = dY [rows, out]
             }
-            const cudaError_t e = tc::launch_group<A_KC, B_KC, EPI>(ps, np, splits, st);
+        }
+        if (ntc > 0) {
+            const cudaError_t e = tc::launch_group<A_KC, B_KC, EPI>(ps, ntc, splits ? sp_tc : nullptr, st);
             if (e != cudaSuccess && g_launch_err == cudaSuccess) g_launch_err = e;
-            return;
         }
     }
     for (int i = 0; i < np; i++) {
+        if (on_tc[i]) continue;
         const GemmArgs &g = gs[i];
         int sp = splits ? splits[i] : 1;
         if (EPI == 3) {   // SIMT split-K: enough 64 x 64 tiles to fill the GPU
