@@ -96,6 +96,44 @@ def smoke_check(np_, torch):
     print("smoke: PPO minibatch (tcgen05 TF32 layers, fused heads, backward) on cuda:0 matches the CPU oracle")
 
 
+def tf32_emulated_grads(torch, p, b, clip, vcoef, ecoef):
+    """The minibatch's gradients with every hidden-layer GEMM operand (forward, input gradient, weight gradient) TRUNCATED to TF32's 10-bit
+    mantissa — what tcgen05 kind::tf32 does to fp32 operands (tools/tf32_update_error.py: truncation reproduces the measured update error) —
+    fp32 accumulate, output heads in fp32: the arithmetic the tensor-core path performs, on the CPU through autograd.  Separates the error that is
+    inherent to TF32 from implementation error where a gradient is ill-conditioned (the std gradient at 32 actions: large cancelling terms)."""
+    def tf32(x):
+        return (x.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+    class MM(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, a, w):          # a [M, K], w [N, K] -> a w^T
+            ctx.save_for_backward(a, w)
+            return tf32(a) @ tf32(w).t()
+
+        @staticmethod
+        def backward(ctx, g):
+            a, w = ctx.saved_tensors
+            return tf32(g) @ tf32(w), tf32(g).t() @ tf32(a)
+    pa = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+
+    def mlp(net, x):
+        for i in range(4):
+            w, bias = pa[f"{net}.model.{2 * i}.weight"], pa[f"{net}.model.{2 * i}.bias"]
+            x = (MM.apply(x, w) if i < 3 else x @ w.t()) + bias
+            if i < 3:
+                x = torch.nn.functional.elu(x)
+        return x
+    mu, v = mlp("actor", b["obs"]), mlp("critic", b["critic_obs"])
+    dist = torch.distributions.Normal(mu, mu * 0.0 + pa["std"])
+    lp = dist.log_prob(b["actions"]).sum(-1)
+    ratio, A_ = torch.exp(lp - b["old_log_prob"].squeeze(-1)), b["advantages"].squeeze(-1)
+    sl = torch.max(-A_ * ratio, -A_ * torch.clamp(ratio, 1.0 - clip, 1.0 + clip)).mean()
+    vc = b["values"] + (v - b["values"]).clamp(-clip, clip)
+    vl = torch.max((v - b["returns"]).pow(2), (vc - b["returns"]).pow(2)).mean()
+    (sl + vcoef * vl - ecoef * dist.entropy().sum(-1).mean()).backward()
+    return {k: t.grad for k, t in pa.items()}
+
+
 def ppo_gradient_check(np_, torch, use_tc, atol, dims=(39, 168, 10)):
     """One PPO minibatch (gather -> forward -> fused heads / losses -> backward) at the registered network width through the C ABI,
     every gradient tensor and the KL / loss sums vs the hand-derived CPU oracle (oracle/ppo_oracle.py)."""
@@ -132,10 +170,20 @@ def ppo_gradient_check(np_, torch, use_tc, atol, dims=(39, 168, 10)):
              old_mu=flat(st.mu)[sel], old_sigma=flat(st.sigma)[sel])
     stats, grads = po.minibatch_loss_and_grads(p_new, b, 0.2, 1.0, 0.01, True)
     got = alg.grads.cpu()
+    emu = tf32_emulated_grads(torch, p_new, b, 0.2, 1.0, 0.01) if use_tc else None
     for k in p_new:
         gk = ac.view_of(got, k)
         scale = float(grads[k].abs().max()) + 1e-12
-        np_.testing.assert_allclose(gk.numpy() / scale, grads[k].numpy() / scale, rtol=0, atol=atol, err_msg=k)
+        err = float((gk - grads[k]).abs().max()) / scale
+        if err <= atol:
+            continue
+        # beyond the tolerance against the fp32 oracle: accepted only where the SAME deviation is inherent to TF32 operands, i.e. the CUDA result
+        # agrees (within the same tolerance) with the CPU emulation of the tensor-core arithmetic, and the emulation itself is that far from fp32
+        assert emu is not None, (k, err)
+        err_emu = float((gk - emu[k].reshape(gk.shape)).abs().max()) / scale
+        inherent = float((emu[k].reshape(gk.shape) - grads[k]).abs().max()) / scale
+        print(f"ppo_gradient_check {dims} {k}: {err:.2e} of scale vs the fp32 oracle, {err_emu:.2e} vs the TF32 emulation (emulation vs fp32: {inherent:.2e})")
+        assert err_emu <= atol and inherent >= 0.5 * err, (k, err, err_emu, inherent)
     tail = alg.reduce_buf[-8:].cpu()
     rt = 1e-3 if not use_tc else 5e-3
     np_.testing.assert_allclose(float(tail[0] / tail[1]), float(stats["kl_mean"]), rtol=rt)

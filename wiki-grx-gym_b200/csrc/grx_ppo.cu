@@ -1340,8 +1340,8 @@ static void mlp_forward(grx_ppo *p, const NetIO *io, int nn, int M, int nlayers,
         GemmArgs g[2];
         for (int i = 0; i < nn; i++) layer_args(l, i, g[i]);
         if (l < 3) dense_group<true, true, 1>(g, nullptr, nn, p->cfg.use_tensor_cores != 0, st);
-        else dense_group<true, true, 0>(g, nullptr, nn, p->cfg.use_tensor_cores != 0, st);
-    }
+        else dense_group<true, true, 0>(g, nullptr, nn, false, st);   // output heads in fp32 (as on the fused-heads path): mu feeds exp((a - mu)^2 / 2 sigma^2), TF32 rounding
+    }                                                                 // of the head itself costs percents on the ratio and the std gradient (measured), and the GEMM is tiny
 }
 // MLP backward from layer `top` down for `nn` networks: d[top] holds dL/d(output of layer top).  First the input-gradient chain
 // d[l-1] = (d[l] W_l) * ELU'(h[l-1]) (+ db_{l-1} = column sums), one grouped launch per layer; then ALL weight gradients
