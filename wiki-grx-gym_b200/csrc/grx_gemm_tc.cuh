@@ -559,6 +559,16 @@ inline int *forced_tile() {
     }
     return t;
 }
+// macro tile of the split-K weight-gradient groups (EPI 3), {0, 0} = cost model; GRX_DW_TILE=2x256 sets it at load
+inline int *dw_tile() {
+    static int t[2] = {0, 0};
+    static bool init = false;
+    if (!init) {
+        init = true;
+        if (const char *e = getenv("GRX_DW_TILE")) { t[0] = atoi(e); const char *x = strchr(e, 'x'); t[1] = x ? atoi(x + 1) : 0; }
+    }
+    return t;
+}
 // cudaLaunchKernelEx wrapper; pdl = launch with the programmatic stream serialization attribute (see pdl_wait)
 inline bool pdl_enabled() {
     static const int on = [] { const char *e = getenv("GRX_PDL"); return e ? atoi(e) : 1; }();
@@ -646,10 +656,54 @@ inline cudaError_t launch_cfg(const Problem *ps, int np, const int *splits, cuda
 // One launch for `np` (<= MAXP) problems of the same operand layout and epilogue.  The macro tile is picked by a small cost model:
 // these GEMMs are bound by operand bytes pulled into each SM (~70 B/ns per SM through TMA, measured) and the tile list is static
 // round-robin, so cost = rounds x (operand bytes of one tile / 70 B/ns + the epilogue when it cannot overlap the next tile).
+// Split-K weight-gradient groups (EPI 3): macro tile AND split count chosen together so that the tile list fills whole rounds of the SM count.
+// These launches are bound by the operand bytes every SM pulls in (rounds x (128 TMT + BN) x rows per split x 4 B at ~70 B/ns) plus the
+// reduce-add epilogues (one per split), and a tile list of 2.5 rounds costs 3.  Measured on the registered minibatch (10 485 rows, six gradients
+// in one launch, profiles/r3a_dw_tile_experiments.txt): 1 x 128 tiles x 512-row splits 175.6 us per minibatch, 2 x 256 x 768-row splits
+// (140 tiles = one round) 167.3 us.  GRX_DW_AUTO=0 keeps the caller's split count and the generic cost model.
+inline bool dw_auto() {
+    static const int on = [] { const char *e = getenv("GRX_DW_AUTO"); return e ? atoi(e) : 1; }();
+    return on != 0;
+}
+inline void dw_plan(const Problem *ps, int np, int sms, int &bt, int &bb, int &z_out) {
+    struct Cand { int tmt, bn; };
+    static const Cand cands[4] = {{2, 256}, {2, 128}, {1, 256}, {1, 128}};
+    double best = -1.0;
+    int K = 0;
+    for (int i = 0; i < np; i++) K = ps[i].K > K ? ps[i].K : K;
+    for (int ci = 0; ci < 4; ci++) {
+        const int tmt = cands[ci].tmt, bn = cands[ci].bn;
+        long tiles_mn = 0;
+        for (int i = 0; i < np; i++) tiles_mn += (long)((ps[i].M + TM * tmt - 1) / (TM * tmt)) * ((ps[i].N + bn - 1) / bn);
+        const int ct = tmt * (bn / 64);
+        const bool overlap = 2 * tmt * bn <= 512;
+        for (int rounds = 1; rounds <= 4; rounds++) {
+            int z = (int)((long)rounds * sms / tiles_mn);
+            if (z < 1) continue;
+            int kchunk = ((K + z - 1) / z + TK - 1) / TK * TK;
+            if (kchunk < 4 * TK) kchunk = 4 * TK;
+            z = (K + kchunk - 1) / kchunk;
+            const long r = (tiles_mn * z + sms - 1) / sms;
+            const double t_tile = (double)(TM * tmt + bn) * kchunk * 4.0 / 70.0 + (overlap ? 100.0 : 190.0 * ct);
+            const double cost = r * t_tile + 190.0 * ct + 40.0 * z;   // + the reduce-add traffic grows with the number of splits
+            if (best < 0 || cost < best) { best = cost; bt = tmt; bb = bn; z_out = z; }
+        }
+    }
+}
+
 template <bool A_KMAJ, bool B_KMAJ, int EPI>
 inline cudaError_t launch_group(const Problem *ps, int np, const int *splits, cudaStream_t st) {
     if (np < 1 || np > MAXP) return cudaErrorInvalidValue;
     const int sms = sm_count();
+    if (EPI == 3 && splits != nullptr && dw_auto() && dw_tile()[0] == 0 && forced_tile()[0] == 0) {
+        int bt = 1, bb = 128, z = 1, sp[MAXP];
+        dw_plan(ps, np, sms, bt, bb, z);
+        for (int i = 0; i < np; i++) sp[i] = z;
+        if (bt == 2 && bb == 256) return launch_cfg<A_KMAJ, B_KMAJ, EPI == 3 ? 3 : 0, 2, 256, 2>(ps, np, sp, st);
+        if (bt == 2 && bb == 128) return launch_cfg<A_KMAJ, B_KMAJ, EPI == 3 ? 3 : 0, 2, 128, 3>(ps, np, sp, st);
+        if (bt == 1 && bb == 256) return launch_cfg<A_KMAJ, B_KMAJ, EPI == 3 ? 3 : 0, 1, 256, 3>(ps, np, sp, st);
+        return launch_cfg<A_KMAJ, B_KMAJ, EPI == 3 ? 3 : 0, 1, 128, 4>(ps, np, sp, st);
+    }
     struct Cand { int tmt, bn; };
     static const Cand cands[6] = {{2, 256}, {2, 128}, {1, 256}, {1, 128}, {1, 64}, {1, 32}};
     double best = -1.0;
@@ -670,13 +724,14 @@ inline cudaError_t launch_group(const Problem *ps, int np, const int *splits, cu
             tiles += ti;
             bytes += (double)ti * (TM * tmt + bn) * kchunk * 4.0;
         }
-        if (!ok && !(tmt == 1 && bn == 32)) continue;
+        if (!ok && !(tmt == 1 && bn == 32) && !(EPI == 3 && dw_tile()[0] == tmt && dw_tile()[1] == bn)) continue;
         const long rounds = (tiles + sms - 1) / sms;
         const int ct = tmt * (bn >= 64 ? bn / 64 : 1);
         const bool overlap = 2 * tmt * bn <= 512;
         const double t_tile = bytes / (double)tiles / 70.0 + (overlap ? 100.0 : 350.0 * ct);
         double cost = rounds * t_tile + 350.0 * ct + 1500.0;
         if (forced_tile()[0] == tmt && forced_tile()[1] == bn) cost = 0.0;   // profiling / test override (grx_gemm_debug_tile)
+        if (EPI == 3 && dw_tile()[0] == tmt && dw_tile()[1] == bn) { bt = tmt; bb = bn; break; }   // weight-gradient groups: tile chosen by measurement (see dw_tile)
         if (best < 0 || cost < best) { best = cost; bt = tmt; bb = bn; }
     }
     if (EPI != 2) {

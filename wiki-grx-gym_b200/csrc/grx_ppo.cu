@@ -1396,7 +1396,8 @@ static void mlp_backward(grx_ppo *p, const NetIO *io, int nn, float *grads, int 
                 a.bias_out = (l == top && top == 3) ? grads + net.b[l] : nullptr;
                 a.M = net.dims[l + 1]; a.N = l == 0 ? net.ld[0] : net.dims[l]; a.K = M; a.lda = net.dims[l + 1]; a.ldb = l == 0 ? io[i].ldx : net.dims[l];
                 a.ldc = net.ld[l];
-                splits[n] = (M + 511) / 512;
+                static const int dw_chunk = [] { const char *e = getenv("GRX_DW_CHUNK"); const int v = e ? atoi(e) : 512; return v >= 32 ? v : 512; }();
+                splits[n] = (M + dw_chunk - 1) / dw_chunk;   // contraction rows per split
                 if (++n == tc::MAXP) flush();
             }
         }
