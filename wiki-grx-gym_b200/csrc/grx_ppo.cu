@@ -304,15 +304,15 @@ template <int NA>
 __global__ void __launch_bounds__(256) act_heads_kernel(const ActHeadsArgs q) {
     constexpr int H = 128;
     const ActArgs &a = q.a;
-    tc::pdl_wait();
     const int lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     const int c0 = lane * 4;
     const bool own = lane < NA;
-    float4 wa[NA];
+    float4 wa[NA];   // parameters: not written by the forward chain in front of this kernel -> loaded before the dependency wait (see ppo_heads_kernel)
 #pragma unroll
     for (int j = 0; j < NA; j++) wa[j] = *reinterpret_cast<const float4 *>(q.W3a + j * H + c0);
     const float4 wc = *reinterpret_cast<const float4 *>(q.W3c + c0);
     const float sg = own ? a.std[lane] : 1.f, ba = own ? q.b3a[lane] : 0.f, bc = q.b3c[0];
+    tc::pdl_wait();
     for (int n = warp; n < a.N; n += nwarps) {
         const float4 ha = *reinterpret_cast<const float4 *>(q.h3a + (size_t)n * H + c0);
         const float4 hc = *reinterpret_cast<const float4 *>(q.h3c + (size_t)n * H + c0);
@@ -620,10 +620,11 @@ __global__ void __launch_bounds__(HEADS_THREADS, 1) ppo_heads_kernel(const Heads
     __shared__ float acc[NACC];
     for (int i = threadIdx.x; i < NACC; i += blockDim.x) acc[i] = 0.f;
     __syncthreads();
-    tc::pdl_wait();
-    tc::pdl_launch_dependents();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5, nwarps = gridDim.x * wpb;
     const int c0 = lane * 4;
+    // the head weights / std were written by the PREVIOUS minibatch's Adam kernel, which completed before the forward chain in front of this
+    // kernel could start (every kernel of the chain releases its dependents only after its own griddepcontrol.wait): loading them before this
+    // kernel's wait hides their latency under the tail of the last forward layer
     float4 wa[NA], gWa[NA];
 #pragma unroll
     for (int j = 0; j < NA; j++) { wa[j] = *reinterpret_cast<const float4 *>(a.W3a + j * H + c0); gWa[j] = make_float4(0.f, 0.f, 0.f, 0.f); }
@@ -632,6 +633,8 @@ __global__ void __launch_bounds__(HEADS_THREADS, 1) ppo_heads_kernel(const Heads
     const bool own = lane < NA;
     const float sg = own ? a.std[lane] : 1.f, ba = own ? a.b3a[lane] : 0.f, bc = a.b3c[0];
     const float inv2s2 = 1.f / (2.f * sg * sg), logsg = logf(sg);
+    tc::pdl_wait();
+    tc::pdl_launch_dependents();
     float gba = 0.f, gsd = 0.f, gbc = 0.f, kl_s = 0.f, surr_s = 0.f, vl_s = 0.f, cnt_s = 0.f;
     const float invB = 1.0f / (float)a.B;
     // software-pipelined over rows: the loads of the warp's next row are issued before the arithmetic of the current one
