@@ -941,7 +941,7 @@ __global__ void __launch_bounds__(1024) apply_kernel(const PrepArgs a, float *__
         const int epoch = c.comm_epoch + 1;
         // this kernel is a normal (fully serialised) launch behind the last weight-gradient GEMM: this rank's input-layer gradients are final
         if (blockIdx.x == 0 && threadIdx.x < a.world_size) st_release_sys(a.comm.flags[threadIdx.x] + FLAG_PHASE + FLAG_READY + a.comm_rank, epoch);
-        if (threadIdx.x == 0) wait_flag(a.comm_flags + FLAG_DONE, epoch * a.world_size, a.ctl, a.budget_ns);   // phase 0 pushed by everybody
+        if (threadIdx.x == 0) { if (a.one_shot == 1) wait_flag(a.comm_flags + FLAG_DONE, epoch * a.world_size, a.ctl, a.budget_ns); }   // phase 0 pushed by everybody (one_shot == 2: there is no phase 0, this kernel pulls everything)
         else if ((int)threadIdx.x <= a.world_size) wait_flag(a.comm_flags + FLAG_PHASE + FLAG_READY + (threadIdx.x - 1), epoch, a.ctl, a.budget_ns);
     }
     __syncthreads();
@@ -959,7 +959,7 @@ __global__ void __launch_bounds__(1024) apply_kernel(const PrepArgs a, float *__
                 for (int r = 1; r < MAXW; r++)
                     if (r < a.world_size) { x.x += v[r].x; x.y += v[r].y; x.z += v[r].z; x.w += v[r].w; }
                 reinterpret_cast<float4 *>(a.gsum_w)[i] = x;
-                s += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+                if (i < (n >> 2)) s += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;   // the tail (KL / loss sums) is not part of the gradient
             }
         }
 #pragma unroll
@@ -995,7 +995,7 @@ __global__ void __launch_bounds__(1024) apply_kernel(const PrepArgs a, float *__
         if (threadIdx.x < 32) {   // squared norm = sum of the partials of all ranks and phases, in an order that is the same everywhere
             const int per_phase = a.world_size;   // one total per rank
             double t = 0.0;
-            for (int ph = 0; ph < NPHASE; ph++) {
+            for (int ph = a.one_shot == 2 ? 1 : 0; ph < NPHASE; ph++) {
                 const volatile double *tab = reinterpret_cast<const volatile double *>(a.comm_flags + ph * FLAG_PHASE + FLAG_SUMSQ);
                 const int cnt = (ph == 1 && a.one_shot) ? (int)gridDim.x : per_phase;   // one-shot phase 1: the partials of this kernel's own blocks
                 for (int i = threadIdx.x; i < cnt; i += 32) t += tab[i];
@@ -1127,7 +1127,11 @@ struct grx_ppo {
     int apply_grid = 148;   // co-resident grid of apply_kernel (<= SM count)
     unsigned long long comm_budget_ns = 10000000000ull;   // cfg.comm_timeout_ms (GRX_COMM_TIMEOUT_MS overrides)
     int *pipe_sync = nullptr;   // row-block counters of the layer-pipelined launches (tc::launch_pipe), zero between launches
-    bool one_shot = true;   // phase 1 of the gradient all-reduce inside apply_kernel (GRX_COMM_ONESHOT=0: as a second allreduce_kernel launch; fixed for the object's lifetime)
+    // Gradient all-reduce protocol (fixed for the object's lifetime; GRX_COMM_ONESHOT overrides): 0 = two allreduce_kernel phases; 1 = phase 0 as a
+    // kernel hidden behind the input-layer weight-gradient launch, phase 1 pulled inside apply_kernel; 2 = no all-reduce kernel at all: one merged
+    // weight-gradient launch (as on one GPU) and apply_kernel pulls the WHOLE gradient block from every rank (bandwidth-bound: (W - 1) x 1.75 MB
+    // over NVLink, one round trip of latency instead of a flag / push / fence / counter chain per phase)
+    int one_shot = 1;
     CommDev comm;
     std::vector<void *> peer_maps;
     // the all-reduce runs in two phases so that most of it hides behind the last weight-gradient launch:
@@ -1235,7 +1239,7 @@ extern "C" int grx_ppo_create(const grx_ppo_cfg *cfg, int32_t device, grx_ppo **
     if (cfg->comm_timeout_ms > 0) p->comm_budget_ns = (unsigned long long)cfg->comm_timeout_ms * 1000000ull;
     if (const char *e = getenv("GRX_COMM_TIMEOUT_MS")) { const long v = atol(e); if (v > 0) p->comm_budget_ns = (unsigned long long)v * 1000000ull; }
     if (const char *e = getenv("GRX_PPO_TIMING")) p->timing = atoi(e) != 0;
-    if (const char *e = getenv("GRX_COMM_ONESHOT")) p->one_shot = atoi(e) != 0;
+    if (const char *e = getenv("GRX_COMM_ONESHOT")) { const int v = atoi(e); if (v >= 0 && v <= 2) p->one_shot = v; }
     if (p->timing) for (int i = 0; i < 9; i++) CK(cudaEventCreate(&p->tev[i]));
     *out = p;
     return GRX_OK;
@@ -1570,14 +1574,15 @@ static bool overlap_enabled() {   // GRX_COMM_OVERLAP=0: both all-reduce phases 
 static int minibatch_apply(grx_ppo *p, cudaStream_t st, bool use_comm, bool zero_grads = false) {
     const float *gsrc = p->reduce_buf;
     if (use_comm) {   // NVLink all-reduce + norm; the summed gradient lands in gsum on every rank
-        if (!p->phase0_launched) launch_allreduce_phase(p, 0, st);   // not forked by minibatch_grads (stepwise entry): both phases back to back
-        if (!p->one_shot) launch_allreduce_phase(p, 1, st);
+        if (p->one_shot != 2 && !p->phase0_launched) launch_allreduce_phase(p, 0, st);   // not forked by minibatch_grads (stepwise entry): both phases back to back
+        if (p->one_shot == 0) launch_allreduce_phase(p, 1, st);
         p->phase0_launched = false;
         gsrc = p->gsum;
     }
     PrepArgs a; memset(&a, 0, sizeof(a));
     a.comm_flags = use_comm ? p->flags : nullptr; a.comm_rank = p->comm.rank; a.budget_ns = p->comm_budget_ns;
-    a.one_shot = use_comm && p->one_shot ? 1 : 0; a.comm = p->comm; a.r1 = p->phase_ranges[1]; a.gsum_w = p->gsum;
+    a.one_shot = use_comm ? p->one_shot : 0; a.comm = p->comm; a.r1 = p->phase_ranges[1]; a.gsum_w = p->gsum;
+    if (a.one_shot == 2) { a.r1.n = 1; a.r1.lo[0] = 0; a.r1.hi[0] = (int)((p->nparam + TAIL) / 4); }   // the whole block incl. the KL / loss tail
     a.mb_log = p->mb_log; a.mb_log_cap = p->mb_log_cap;
     a.zero = zero_grads ? reinterpret_cast<float4 *>(p->reduce_buf) : nullptr; a.nzero4 = (int)((p->nparam + TAIL) / 4);
     a.ctl = p->ctl; a.tail = gsrc + p->nparam; a.std = p->params; a.A = p->A; a.adaptive = p->cfg.adaptive_schedule;
@@ -1693,10 +1698,10 @@ extern "C" int grx_ppo_update(grx_ppo *p, const int64_t *d_indices, void *stream
                 cudaStreamWaitEvent(p->gstream, p->ev_gfork, 0);
                 launch_gather(p, d_indices, 0, true, 1, set ^ 1, false, p->gstream, false);
                 cudaEventRecord(p->ev_gjoin, p->gstream);
-                rc = minibatch_grads(p, d_indices, 0, true, cs, p->comm_open && overlap_enabled(), set, false);
+                rc = minibatch_grads(p, d_indices, 0, true, cs, p->comm_open && overlap_enabled() && p->one_shot != 2, set, false);
                 cudaStreamWaitEvent(cs, p->ev_gjoin, 0);
             } else {
-                rc = minibatch_grads(p, d_indices, 0, true, cs, p->comm_open && overlap_enabled(), set, inline_gather);
+                rc = minibatch_grads(p, d_indices, 0, true, cs, p->comm_open && overlap_enabled() && p->one_shot != 2, set, inline_gather);
             }
             if (!rc) rc = minibatch_apply(p, cs, p->comm_open, prefetch);
         }
