@@ -1239,6 +1239,9 @@ extern "C" int grx_ppo_create(const grx_ppo_cfg *cfg, int32_t device, grx_ppo **
     if (cfg->comm_timeout_ms > 0) p->comm_budget_ns = (unsigned long long)cfg->comm_timeout_ms * 1000000ull;
     if (const char *e = getenv("GRX_COMM_TIMEOUT_MS")) { const long v = atol(e); if (v > 0) p->comm_budget_ns = (unsigned long long)v * 1000000ull; }
     if (const char *e = getenv("GRX_PPO_TIMING")) p->timing = atoi(e) != 0;
+    // measured on one 8-GPU box (profiles/bench_r3h_*, bench_r3f_*, bench_r3e_*; M env-steps/s): protocol 2 / protocol 1 = 7.82 / 7.65 on 2 GPUs,
+    // 15.30 / 15.03 on 4, 28.88 / 29.39 on 8 — pulling (W - 1) x 1.75 MB per rank is bandwidth-bound and overtakes the latency-bound chain at W > 4
+    p->one_shot = cfg->world_size <= 4 ? 2 : 1;
     if (const char *e = getenv("GRX_COMM_ONESHOT")) { const int v = atoi(e); if (v >= 0 && v <= 2) p->one_shot = v; }
     if (p->timing) for (int i = 0; i < 9; i++) CK(cudaEventCreate(&p->tev[i]));
     *out = p;
