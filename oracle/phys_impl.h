@@ -6,7 +6,8 @@
  * libcarb.gym.plugin.so, libPhysXGpu_64.so); it cannot be run, read or compiled
  * here and the reference holds no golden vectors for it.  This file therefore
  * states OUR dynamics spec ("GRX-dyn v1") in plain C; the CUDA
- * kernel (wiki-grx-gym_b200/csrc/grx_env.cu) must match it to fp32 tolerance.
+ * kernels (wiki-grx-gym_b200/csrc/grx_env.cu for the lower-limb tree,
+ * csrc/grx_phys_generic.cu for any tree incl. self-collision) must match it to fp32 tolerance.
  * The reference call sites this spec stands behind:
  *   legged_robot_fftai.py:51-88  (substep loop, action delay, averages)
  *   legged_robot.py:679-715      (_compute_torques, PD law + motor strength + clip)
