@@ -361,6 +361,10 @@ int grx_ppo_debug_fused(int32_t fwd_chain);
 /* Test / profiling: the layer-pipelined launches (several dependent dense layers in ONE persistent tcgen05 launch; GRX_LAYER_PIPE) on (1) / off (0)
  * at run time, -1 = query; returns the previous setting. */
 int grx_ppo_debug_pipe(int32_t on);
+/* Test (host arithmetic only, no GPU needed): the plan of a split-K weight-gradient group of np problems [M_i x N_i] with contraction length K on
+ * `sms` SMs — macro tile and split count chosen together so that the tile list fills whole rounds; out3 = {row blocks per tile (1|2), columns per
+ * tile (128|256), splits}. */
+int grx_gemm_debug_dw_plan(const int32_t *M, const int32_t *N, int32_t K, int32_t np, int32_t sms, int32_t *out3);
 
 /* Test / profiling: force the macro tile of the tensor-core GEMM (row_blocks in {1, 2} x bn in {32, 64, 128, 256}; 0, 0 = cost model). */
 int grx_gemm_debug_tile(int32_t row_blocks, int32_t bn);

@@ -66,3 +66,31 @@ def test_quat_rotate_inverse_host_helper():
                      2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], dim=1).view(-1, 3, 3)
     want = torch.einsum("nji,nj->ni", R, v)
     np.testing.assert_allclose(quat_rotate_inverse(q, v).numpy(), want.numpy(), atol=1e-12)
+
+
+def test_weight_gradient_plan_fills_whole_rounds():
+    """Host logic of the tensor-core dispatch (tc::dw_plan), no GPU needed: for the registered minibatch (10 485 rows; the six weight gradients of
+    actor + critic in one launch) the plan is 2 x 256 macro tiles x 14 splits = 140 tiles = ONE round of the 148 SMs (measured optimum,
+    profiles/r3a_dw_tile_experiments.txt); in general the tile list never exceeds the planned number of whole rounds and every split is >= 128 rows."""
+    import ctypes as C
+    import numpy as np
+    from grx_b200 import _lib as L
+    lib = L.lib()
+
+    def plan(shapes, K, sms=148):
+        M = (C.c_int32 * len(shapes))(*[s[0] for s in shapes]); N = (C.c_int32 * len(shapes))(*[s[1] for s in shapes])
+        out = (C.c_int32 * 3)()
+        L.check(lib.grx_gemm_debug_dw_plan(M, N, K, len(shapes), sms, out))
+        return tuple(out)
+    six = [(128, 256), (128, 256), (256, 512), (256, 512), (512, 40), (512, 168)]
+    assert plan(six, 10485) == (2, 256, 14)
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        shapes = [six[i] for i in rng.choice(6, size=int(rng.integers(1, 7)), replace=True)]
+        K, sms = int(rng.integers(200, 40000)), int(rng.choice([132, 148, 160]))
+        tmt, bn, z = plan(shapes, K, sms)
+        assert tmt in (1, 2) and bn in (128, 256) and z >= 1
+        kchunk = -(-(-(-K // z)) // 32) * 32
+        assert kchunk >= 128 or z == 1
+        tiles = sum(-(-m // (128 * tmt)) * -(-n // bn) for m, n in shapes) * -(-K // kchunk)
+        assert tiles <= 4 * sms

@@ -1747,6 +1747,19 @@ extern "C" int grx_ppo_debug_pipe(int32_t on) {
     return old;
 }
 
+// Test: the plan of a split-K weight-gradient group (tc::dw_plan: macro tile and split count chosen together so that the tile list fills whole rounds
+// of `sms` SMs).  Host arithmetic only — callable without a GPU.  out3 = {row blocks per tile, columns per tile, splits}.
+extern "C" int grx_gemm_debug_dw_plan(const int32_t *M, const int32_t *N, int32_t K, int32_t np, int32_t sms, int32_t *out3) {
+    if (!M || !N || !out3 || np < 1 || np > tc::MAXP || K < 1 || sms < 1) return grx_set_error(GRX_E_INVALID, "grx_gemm_debug_dw_plan: bad arguments");
+    tc::Problem ps[tc::MAXP];
+    memset(ps, 0, sizeof(ps));
+    for (int i = 0; i < np; i++) { ps[i].M = M[i]; ps[i].N = N[i]; ps[i].K = K; }
+    int bt = 1, bb = 128, z = 1;
+    tc::dw_plan(ps, np, sms, bt, bb, z);
+    out3[0] = bt; out3[1] = bb; out3[2] = z;
+    return GRX_OK;
+}
+
 // Test / profiling: force the macro tile of the tensor-core GEMM ({0, 0} = cost model).  Configurations that do not apply to a launch
 // (ELU' epilogue with more than 128 x 128, padding-only tiles) fall back to the cost model.
 extern "C" int grx_gemm_debug_tile(int32_t row_blocks, int32_t bn) {

@@ -128,5 +128,5 @@ EXPORTED = ["grx_last_error", "grx_version", "grx_abi_sizes", "grx_debug_launch_
             "grx_ppo_create", "grx_ppo_destroy", "grx_ppo_get_buffer", "grx_ppo_act", "grx_ppo_process_env_step",
             "grx_ppo_compute_returns", "grx_ppo_compute_returns_local", "grx_ppo_normalize_advantages",
             "grx_ppo_minibatch_grads", "grx_ppo_minibatch_apply", "grx_ppo_update", "grx_ppo_comm_handle", "grx_ppo_comm_open",
-            "grx_ppo_minibatch_apply_comm", "grx_ppo_debug_timing", "grx_ppo_act_inference", "grx_gemm_debug", "grx_gemm_debug_stamps", "grx_gemm_debug_tile", "grx_ppo_debug_fused", "grx_ppo_debug_pipe", "grx_debug_stamps32",
+            "grx_ppo_minibatch_apply_comm", "grx_ppo_debug_timing", "grx_ppo_act_inference", "grx_gemm_debug", "grx_gemm_debug_stamps", "grx_gemm_debug_tile", "grx_ppo_debug_fused", "grx_ppo_debug_pipe", "grx_gemm_debug_dw_plan", "grx_debug_stamps32",
             "grx_physg_create", "grx_physg_destroy", "grx_physg_set_terrain_plane", "grx_physg_set_terrain_heightfield", "grx_physg_step"]
